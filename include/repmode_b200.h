@@ -1,0 +1,147 @@
+/* repmode_b200 C ABI -- the drop-in boundary for RepMode's MoDE-conv hot path on B200 (sm_100a).
+ *
+ * The reference has no native code: its hot path is PyTorch operators called from
+ * fnet/nn_modules/RepMode.py (paths relative to the reference tree).  Each entry point below replaces
+ * the operator sequence cited next to it.  The host side (repmode_b200/functional.py, Python, because the
+ * reference's plugin boundary `fnet.nn_modules.<name>.Net` is Python -- fnet/fnet_model.py:52) binds
+ * these symbols with ctypes and passes raw device pointers (tensor.data_ptr()) plus the caller's
+ * cudaStream_t.  INTEGRATION.md shows the binding a reference maintainer would add.
+ *
+ * Conventions
+ *   - every function returns 0 on success, non-zero on error; mode_last_error() returns a thread-local
+ *     message.  No C++ exception crosses the boundary.
+ *   - all pointers are DEVICE pointers unless the name ends in _host; the library never allocates or
+ *     frees caller-visible memory and keeps no mutable global state besides per-device attribute caches.
+ *   - activations are dense NDHWC ("channels_last_3d"): x[n][d][h][w][c], c contiguous.
+ *   - int64_t for element counts, int32_t for channel / small counts.
+ */
+#ifndef REPMODE_B200_H_
+#define REPMODE_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MODE_ABI_VERSION 1
+#define MODE_NUM_EXPERTS 5   /* RepMode.py:22 (num_experts hard-coded), :136-142 */
+#define MODE_TAPS 125        /* effective kernel is always 5x5x5, RepMode.py:114-115 */
+#define MODE_KC 32           /* K-chunk (channels per 64-byte fp16 row) of the packed weight layout */
+
+typedef enum { MODE_F32 = 0, MODE_F16 = 1 } mode_dtype_t;
+
+/* One MoDEConv layer's parameters, reference layouts (RepMode.py:136-142,153), fp32, device memory. */
+typedef struct {
+    const float* k5;      /* expert_conv5x5_conv [Co,Ci,5,5,5] */
+    const float* k3;      /* expert_conv3x3_conv [Co,Ci,3,3,3] */
+    const float* k1;      /* expert_conv1x1_conv [Co,Ci,1,1,1] */
+    const float* a3;      /* expert_avg3x3_conv  [Co,Ci,1,1,1] (times the 1/27 pool constant) */
+    const float* a5;      /* expert_avg5x5_conv  [Co,Ci,1,1,1] (times the 1/125 pool constant) */
+    const float* gate_w;  /* gate.weight [5*Co, T], row index e*Co+o (RepMode.py:199) */
+    const float* gate_b;  /* gate.bias   [5*Co] */
+    int32_t ci, co, num_tasks;
+} mode_layer_t;
+
+typedef struct {
+    int32_t sm_major, sm_minor, sm_count;
+    int32_t smem_per_block_optin;   /* bytes */
+    int32_t tmem_columns;           /* 512 on sm_100 */
+    int32_t abi_version;
+} mode_caps_t;
+
+const char* mode_last_error(void);
+int mode_version(void);
+/* Fails unless `device` is compute capability 10.x (this library ships sm_100a SASS only). */
+int mode_query(int device, mode_caps_t* caps_host);
+
+/* ---- K1: gate softmax + expert re-parameterisation --------------------------------------------------
+ * Replaces: Linear + view + Softmax(dim=1) (RepMode.py:198-200) and MoDEConv.routing / trans_kernel
+ * (RepMode.py:165-192), for U gate inputs at once (U = distinct tasks in the batch; the reference
+ * recomputes per sample).
+ *   gate input: either task_ids[U] (one-hot embedding == column gather, RepMode.py:44-49) or a dense
+ *               t[U,T] row (the MoDEConv.forward(x, t) signature accepts any t); exactly one non-NULL.
+ *   g_out [U,5,Co] fp32: the softmax gates (saved for backward).
+ *   w_fwd: packed conv weights, "B-operand" layout  w[u][tap][ci_chunk][co][MODE_KC]  (ci within a chunk
+ *          contiguous, zero padded), dtype w_dtype.  tap = (kd*5+kh)*5+kw.
+ *   w_dgrad (may be NULL): the dgrad weights  w'[u][124-tap][co_chunk][ci][MODE_KC]  (flipped taps, io
+ *          transposed), same dtype.
+ *   w_scale * (w_scale_dev ? *w_scale_dev : 1) multiplies every packed weight before rounding (a power of
+ *   two keeps the fp16 operand an exactly-scaled copy); w_scale_dev is a device scalar so the scale can
+ *   be produced on-stream (mode_f16_scale) without a host sync.
+ */
+int mode_reparam_fwd(const mode_layer_t* layer_host, const int32_t* task_ids, const float* t_dense, int32_t U,
+                     float* g_out, void* w_fwd, void* w_dgrad, mode_dtype_t w_dtype, float w_scale,
+                     const float* w_scale_dev, void* stream);
+int64_t mode_packed_weight_elems(int32_t k_channels, int32_t n_channels);   /* per gate input u */
+
+/* ---- K1b: backward of K1 ------------------------------------------------------------------------------
+ * Replaces autograd through routing/softmax/Linear.  d_weff [N][125][Co][Ci] fp32 is the per-sample
+ * gradient of the effective kernel (what K4 writes); sample n used gate input u = sample_u[n].
+ * Outputs (all fp32, reference parameter layouts, overwritten): dk5 dk3 dk1 da3 da5, dgate_w [5Co,T],
+ * dgate_b [5Co].  workspace: mode_reparam_bwd_workspace_bytes().
+ */
+int64_t mode_reparam_bwd_workspace_bytes(int32_t ci, int32_t co, int32_t n_samples);
+int mode_reparam_bwd(const mode_layer_t* layer_host, const int32_t* task_ids, const float* t_dense, int32_t U,
+                     const int32_t* sample_u, int32_t n_samples, const float* g, const float* d_weff,
+                     float* dk5, float* dk3, float* dk1, float* da3, float* da5, float* dgate_w, float* dgate_b,
+                     void* workspace, void* stream);
+
+/* ---- K2 / K3: 5x5x5 'same' cross-correlation, stride 1, zero pad 2, no bias ---------------------------
+ * Replaces F.conv3d(x[i:i+1], w[i], padding='same') per sample (RepMode.py:204-210) and, called with the
+ * w_dgrad pack and dy as input, its autograd dgrad.
+ *   x [N,D,H,W,K] (x_dtype), w = packed weights from K1 (same dtype as x), sample_u[N] selects the weight
+ *   set per sample (all zeros in eval mode, RepMode.py:209-210), y [N,D,H,W,Nout] fp32.
+ *   out_scale * (out_scale_dev ? *out_scale_dev : 1) multiplies the accumulator (undoes operand scaling).
+ *   bn_sums (may be NULL): double[2*Nout], += per-channel sum and sum of squares of y (BatchNorm3d
+ *   training statistics, RepMode.py:147) -- fused so y is not re-read.
+ *   impl: 0 = auto, 1 = SIMT fp32 direct conv (any shape, fp32 operands only), 2 = tcgen05 implicit GEMM
+ *   (fp16 operands, K % 32 == 0, Nout % 16 == 0).
+ */
+int mode_conv3d(const void* x, mode_dtype_t x_dtype, const void* w, const int32_t* sample_u, float* y,
+                int32_t N, int32_t D, int32_t H, int32_t W, int32_t K, int32_t Nout, float out_scale,
+                const float* out_scale_dev, double* bn_sums, int32_t impl, void* stream);
+
+/* ---- K4: wgrad ------------------------------------------------------------------------------------------
+ * d_weff[n][tap][o][i] = out_scale * sum_p dy[n][p][o] * x[n][p + tap - 2][i]   (autograd of RepMode.py:207).
+ * x [N,D,H,W,Ci], dy [N,D,H,W,Co] (same dtype), d_weff fp32 (overwritten).
+ */
+int64_t mode_conv3d_wgrad_workspace_bytes(int32_t N, int32_t D, int32_t H, int32_t W, int32_t Ci, int32_t Co,
+                                          int32_t impl);
+int mode_conv3d_wgrad(const void* x, const void* dy, mode_dtype_t dtype, float* d_weff, int32_t N, int32_t D,
+                      int32_t H, int32_t W, int32_t Ci, int32_t Co, float out_scale, const float* out_scale_dev,
+                      void* workspace, int32_t impl, void* stream);
+
+/* ---- BatchNorm3d + ReLU on NDHWC fp32 (RepMode.py:146-149,212) ------------------------------------------
+ * mode_bn_stats:    sums[2C] (double, must be zeroed by the caller) += sum / sum of squares over M rows.
+ * mode_bn_finalize: from sums -> mean, invstd (biased var, eps), scale = gamma*invstd,
+ *                   shift = beta - mean*scale; updates running_mean/var (momentum, unbiased var) if non-NULL.
+ * mode_bn_apply_relu: out = [relu](y*scale + shift); optional fp16 copy out_f16 scaled by f16_scale.
+ * mode_bn_relu_bwd: given y, dout, gamma, beta, mean, invstd: dgamma, dbeta, dy as fp32 and/or as fp16
+ *                   scaled by a power of two chosen on the device from a per-channel bound gathered in the
+ *                   reduction pass; dy_scale2 (device float[2]) receives {scale, 1/scale}.
+ *                   workspace: mode_bn_bwd_workspace_bytes(C).
+ */
+int64_t mode_bn_bwd_workspace_bytes(int32_t C);
+int mode_bn_stats(const float* y, int64_t M, int32_t C, double* sums, void* stream);
+int mode_bn_finalize(const double* sums, int64_t M, int32_t C, const float* gamma, const float* beta, float eps,
+                     float momentum, float* mean, float* invstd, float* scale, float* shift,
+                     float* running_mean, float* running_var, void* stream);
+int mode_bn_apply_relu(const float* y, int64_t M, int32_t C, const float* scale, const float* shift, int32_t relu,
+                       float* out, void* out_f16, float f16_scale, void* stream);   /* f16_scale: host value */
+int mode_bn_relu_bwd(const float* y, const float* dout, int64_t M, int32_t C, const float* gamma,
+                     const float* beta, const float* mean, const float* invstd, float* dgamma, float* dbeta,
+                     float* dy, void* dy_f16, float* dy_scale2, void* workspace, void* stream);
+
+/* ---- operand staging -----------------------------------------------------------------------------------
+ * fp32 -> fp16 (round to nearest even), value * scale * (scale_dev ? *scale_dev : 1); n elements. */
+int mode_cast_f16(const float* src, void* dst_f16, int64_t n, float scale, const float* scale_dev, void* stream);
+/* amax[0] = max(amax[0], max |src|) (amax must be zero-initialised by the caller; device scalar). */
+int mode_amax(const float* src, int64_t n, float* amax, void* stream);
+/* scale2[0] = 2^floor(log2(target / amax[0])) (1 if amax is 0), scale2[1] = 1 / scale2[0]; all device. */
+int mode_f16_scale(const float* amax, float target, float* scale2, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* REPMODE_B200_H_ */

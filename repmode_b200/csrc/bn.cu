@@ -1,0 +1,440 @@
+// BatchNorm3d (+ReLU) on NDHWC fp32, training and eval, forward and backward, plus the fp32->fp16
+// operand staging kernels.  Replaces `subsequent_layer = Sequential(BatchNorm3d(Co), ReLU)`
+// (fnet/nn_modules/RepMode.py:146-149, applied at :212) and its autograd.
+//
+// All kernels are HBM-bound streaming passes: float4 accesses, channel index = element index mod C
+// (C is a multiple of 4 on every layer that has a BN; the scalar path covers the rest), grid sized to
+// a multiple of the SM count, per-thread fp32 partials folded into fp64 block/global sums.
+#include "common.cuh"
+
+namespace mode {
+
+constexpr int BN_THREADS = 256;
+constexpr int BN_MAXC = 1024;
+
+// ---- statistics: sums[c] += sum y, sums[C+c] += sum y^2 -------------------------------------------------
+// Each thread owns a fixed group of 4 channels (requires (blockDim*4) % C == 0 or C % (blockDim*4) == 0 ->
+// we use rows-of-C iteration instead: thread t handles float4 #t of a row block).
+__global__ void __launch_bounds__(BN_THREADS) bn_stats_kernel(const float* __restrict__ y, int64_t M, int C,
+                                                              double* __restrict__ sums) {
+    // vector lanes per row
+    const int vpr = C >> 2;                         // float4 per row (C % 4 == 0 path)
+    const int rows_per_iter = BN_THREADS / vpr;     // host guarantees vpr <= BN_THREADS and divides it
+    const int lane_v = threadIdx.x % vpr, lane_r = threadIdx.x / vpr;
+    float s[4] = {0, 0, 0, 0}, q[4] = {0, 0, 0, 0};
+    double ds[4] = {0, 0, 0, 0}, dq[4] = {0, 0, 0, 0};
+    int cnt = 0;
+    for (int64_t r = (int64_t)blockIdx.x * rows_per_iter + lane_r; r < M; r += (int64_t)gridDim.x * rows_per_iter) {
+        const float4 v = *reinterpret_cast<const float4*>(y + r * C + lane_v * 4);
+        s[0] += v.x; s[1] += v.y; s[2] += v.z; s[3] += v.w;
+        q[0] = fmaf(v.x, v.x, q[0]); q[1] = fmaf(v.y, v.y, q[1]); q[2] = fmaf(v.z, v.z, q[2]); q[3] = fmaf(v.w, v.w, q[3]);
+        if (++cnt == 64) {   // fold fp32 partials into fp64 regularly
+#pragma unroll
+            for (int j = 0; j < 4; ++j) { ds[j] += s[j]; dq[j] += q[j]; s[j] = 0.f; q[j] = 0.f; }
+            cnt = 0;
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { ds[j] += s[j]; dq[j] += q[j]; }
+    __shared__ double sh[2 * BN_MAXC];
+    for (int i = threadIdx.x; i < 2 * C; i += BN_THREADS) sh[i] = 0.0;
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        atomicAdd(&sh[lane_v * 4 + j], ds[j]);
+        atomicAdd(&sh[C + lane_v * 4 + j], dq[j]);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < 2 * C; i += BN_THREADS) atomicAdd(sums + i, sh[i]);
+}
+
+__global__ void bn_stats_scalar_kernel(const float* __restrict__ y, int64_t M, int C, double* __restrict__ sums) {
+    // generic C (used only for tiny test shapes): one block per channel
+    const int c = blockIdx.x;
+    double s = 0, q = 0;
+    for (int64_t r = threadIdx.x; r < M; r += blockDim.x) {
+        const double v = y[r * C + c];
+        s += v; q += v * v;
+    }
+    __shared__ double sh[2][BN_THREADS];
+    sh[0][threadIdx.x] = s; sh[1][threadIdx.x] = q;
+    __syncthreads();
+    for (int st = BN_THREADS / 2; st > 0; st >>= 1) {
+        if (threadIdx.x < st) { sh[0][threadIdx.x] += sh[0][threadIdx.x + st]; sh[1][threadIdx.x] += sh[1][threadIdx.x + st]; }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) { atomicAdd(sums + c, sh[0][0]); atomicAdd(sums + C + c, sh[1][0]); }
+}
+
+__global__ void bn_finalize_kernel(const double* __restrict__ sums, int64_t M, int C, const float* __restrict__ gamma,
+                                   const float* __restrict__ beta, float eps, float momentum, float* mean,
+                                   float* invstd, float* scale, float* shift, float* running_mean,
+                                   float* running_var) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    const double m = sums[c] / (double)M;
+    double var = sums[C + c] / (double)M - m * m;      // biased variance (training-mode normalisation)
+    if (var < 0) var = 0;
+    const float is = (float)(1.0 / sqrt(var + (double)eps));
+    const float ga = gamma ? gamma[c] : 1.f, be = beta ? beta[c] : 0.f;
+    if (mean) mean[c] = (float)m;
+    if (invstd) invstd[c] = is;
+    const float sc = ga * is;
+    scale[c] = sc;
+    shift[c] = be - (float)m * sc;
+    if (running_mean) running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * (float)m;
+    if (running_var) {
+        const double unb = M > 1 ? var * (double)M / (double)(M - 1) : var;   // running_var tracks the unbiased estimate
+        running_var[c] = (1.f - momentum) * running_var[c] + momentum * (float)unb;
+    }
+}
+
+// ---- apply: out = relu(y*scale + shift), optional fp16 copy ----------------------------------------------
+__global__ void __launch_bounds__(BN_THREADS) bn_apply_kernel(const float* __restrict__ y, int64_t total, int C,
+                                                              const float* __restrict__ scale,
+                                                              const float* __restrict__ shift, int relu,
+                                                              float* __restrict__ out, __half* __restrict__ out16,
+                                                              float f16_scale) {
+    __shared__ float ssc[BN_MAXC], ssh[BN_MAXC];
+    for (int i = threadIdx.x; i < C; i += BN_THREADS) { ssc[i] = scale[i]; ssh[i] = shift[i]; }
+    __syncthreads();
+    const int64_t nvec = total >> 2;
+    for (int64_t i = (int64_t)blockIdx.x * BN_THREADS + threadIdx.x; i < nvec; i += (int64_t)gridDim.x * BN_THREADS) {
+        const int c = (int)((i * 4) % C);
+        float4 v = *reinterpret_cast<const float4*>(y + i * 4);
+        v.x = fmaf(v.x, ssc[c], ssh[c]); v.y = fmaf(v.y, ssc[c + 1], ssh[c + 1]);
+        v.z = fmaf(v.z, ssc[c + 2], ssh[c + 2]); v.w = fmaf(v.w, ssc[c + 3], ssh[c + 3]);
+        if (relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
+        if (out) *reinterpret_cast<float4*>(out + i * 4) = v;
+        if (out16) {
+            __half2 a = __floats2half2_rn(v.x * f16_scale, v.y * f16_scale);
+            __half2 b = __floats2half2_rn(v.z * f16_scale, v.w * f16_scale);
+            uint2 pk;
+            pk.x = *reinterpret_cast<uint32_t*>(&a);
+            pk.y = *reinterpret_cast<uint32_t*>(&b);
+            *reinterpret_cast<uint2*>(out16 + i * 4) = pk;
+        }
+    }
+}
+
+__global__ void bn_apply_scalar_kernel(const float* __restrict__ y, int64_t total, int C,
+                                       const float* __restrict__ scale, const float* __restrict__ shift, int relu,
+                                       float* __restrict__ out, __half* __restrict__ out16, float f16_scale) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int c = (int)(i % C);
+        float v = fmaf(y[i], scale[c], shift[c]);
+        if (relu) v = fmaxf(v, 0.f);
+        if (out) out[i] = v;
+        if (out16) out16[i] = __float2half_rn(v * f16_scale);
+    }
+}
+
+// ---- backward -------------------------------------------------------------------------------------------
+// pass 1: red[c] += sum dz, red[C+c] += sum dz*xhat, where z = xhat*gamma+beta, dz = dout*(z>0)
+__global__ void __launch_bounds__(BN_THREADS) bn_bwd_reduce_kernel(const float* __restrict__ y,
+                                                                   const float* __restrict__ dout, int64_t M, int C,
+                                                                   const float* __restrict__ gamma,
+                                                                   const float* __restrict__ beta,
+                                                                   const float* __restrict__ mean,
+                                                                   const float* __restrict__ invstd,
+                                                                   double* __restrict__ red, int* __restrict__ mx) {
+    const int c = blockIdx.y;      // one channel per blockIdx.y (generic in C; strided reads hit L2 lines shared by
+    const float mu = mean[c], is = invstd[c], ga = gamma ? gamma[c] : 1.f, be = beta ? beta[c] : 0.f;  // neighbours)
+    double s = 0, q = 0;
+    float fs = 0.f, fq = 0.f, mdz = 0.f, mxh = 0.f;
+    int cnt = 0;
+    for (int64_t r = (int64_t)blockIdx.x * BN_THREADS + threadIdx.x; r < M; r += (int64_t)gridDim.x * BN_THREADS) {
+        const float xh = (y[r * C + c] - mu) * is;
+        const float z = fmaf(xh, ga, be);
+        const float dz = z > 0.f ? dout[r * C + c] : 0.f;
+        mdz = fmaxf(mdz, fabsf(dz)); mxh = fmaxf(mxh, fabsf(xh));
+        fs += dz; fq = fmaf(dz, xh, fq);
+        if (++cnt == 64) { s += fs; q += fq; fs = 0.f; fq = 0.f; cnt = 0; }
+    }
+    s += fs; q += fq;
+    __shared__ double sh[2][BN_THREADS];
+    sh[0][threadIdx.x] = s; sh[1][threadIdx.x] = q;
+    __syncthreads();
+    for (int st = BN_THREADS / 2; st > 0; st >>= 1) {
+        if (threadIdx.x < st) { sh[0][threadIdx.x] += sh[0][threadIdx.x + st]; sh[1][threadIdx.x] += sh[1][threadIdx.x + st]; }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) { atomicAdd(red + c, sh[0][0]); atomicAdd(red + C + c, sh[1][0]); }
+#pragma unroll
+    for (int st = 16; st > 0; st >>= 1) {
+        mdz = fmaxf(mdz, __shfl_xor_sync(0xffffffffu, mdz, st));
+        mxh = fmaxf(mxh, __shfl_xor_sync(0xffffffffu, mxh, st));
+    }
+    if ((threadIdx.x & 31) == 0) { atomicMax(mx + c, __float_as_int(mdz)); atomicMax(mx + C + c, __float_as_int(mxh)); }
+}
+
+// vectorised pass 1 for C % 4 == 0 (same structure as bn_stats_kernel)
+__global__ void __launch_bounds__(BN_THREADS) bn_bwd_reduce_vec_kernel(const float* __restrict__ y,
+                                                                       const float* __restrict__ dout, int64_t M,
+                                                                       int C, const float* __restrict__ gamma,
+                                                                       const float* __restrict__ beta,
+                                                                       const float* __restrict__ mean,
+                                                                       const float* __restrict__ invstd,
+                                                                       double* __restrict__ red, int* __restrict__ mx) {
+    const int vpr = C >> 2;
+    const int rows_per_iter = BN_THREADS / vpr;
+    const int lane_v = threadIdx.x % vpr, lane_r = threadIdx.x / vpr;
+    float mu[4], is[4], ga[4], be[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const int c = lane_v * 4 + j;
+        mu[j] = mean[c]; is[j] = invstd[c]; ga[j] = gamma ? gamma[c] : 1.f; be[j] = beta ? beta[c] : 0.f;
+    }
+    float s[4] = {0, 0, 0, 0}, q[4] = {0, 0, 0, 0}, mdz[4] = {0, 0, 0, 0}, mxh[4] = {0, 0, 0, 0};
+    double ds[4] = {0, 0, 0, 0}, dq[4] = {0, 0, 0, 0};
+    int cnt = 0;
+    for (int64_t r = (int64_t)blockIdx.x * rows_per_iter + lane_r; r < M; r += (int64_t)gridDim.x * rows_per_iter) {
+        const float4 yv = *reinterpret_cast<const float4*>(y + r * C + lane_v * 4);
+        const float4 dv = *reinterpret_cast<const float4*>(dout + r * C + lane_v * 4);
+        const float ya[4] = {yv.x, yv.y, yv.z, yv.w}, da[4] = {dv.x, dv.y, dv.z, dv.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const float xh = (ya[j] - mu[j]) * is[j];
+            const float dz = fmaf(xh, ga[j], be[j]) > 0.f ? da[j] : 0.f;
+            mdz[j] = fmaxf(mdz[j], fabsf(dz)); mxh[j] = fmaxf(mxh[j], fabsf(xh));
+            s[j] += dz; q[j] = fmaf(dz, xh, q[j]);
+        }
+        if (++cnt == 64) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) { ds[j] += s[j]; dq[j] += q[j]; s[j] = 0.f; q[j] = 0.f; }
+            cnt = 0;
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { ds[j] += s[j]; dq[j] += q[j]; }
+    __shared__ double sh[2 * BN_MAXC];
+    __shared__ int smx[2 * BN_MAXC];
+    for (int i = threadIdx.x; i < 2 * C; i += BN_THREADS) { sh[i] = 0.0; smx[i] = 0; }
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        atomicAdd(&sh[lane_v * 4 + j], ds[j]);
+        atomicAdd(&sh[C + lane_v * 4 + j], dq[j]);
+        atomicMax(&smx[lane_v * 4 + j], __float_as_int(mdz[j]));
+        atomicMax(&smx[C + lane_v * 4 + j], __float_as_int(mxh[j]));
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < 2 * C; i += BN_THREADS) { atomicAdd(red + i, sh[i]); atomicMax(mx + i, smx[i]); }
+}
+
+// power-of-two fp16 scale for dy from the per-channel bound
+//   |dy_c| <= |gamma_c*invstd_c| * (max|dz|_c + |sum_dz_c|/M + max|xhat|_c * |sum_dzxhat_c|/M)
+__global__ void bn_bwd_scale_kernel(const double* __restrict__ red, const int* __restrict__ mx, int64_t M, int C,
+                                    const float* __restrict__ gamma, const float* __restrict__ invstd, float target,
+                                    float* __restrict__ scale2) {
+    float b = 0.f;
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+        const float ga = gamma ? gamma[c] : 1.f;
+        const float a = fabsf((float)(red[c] / (double)M)), bb = fabsf((float)(red[C + c] / (double)M));
+        b = fmaxf(b, fabsf(ga * invstd[c]) * (__int_as_float(mx[c]) + a + __int_as_float(mx[C + c]) * bb));
+    }
+    __shared__ float sh[256];
+    sh[threadIdx.x] = b;
+    __syncthreads();
+    for (int st = 128; st > 0; st >>= 1) {
+        if (threadIdx.x < st) sh[threadIdx.x] = fmaxf(sh[threadIdx.x], sh[threadIdx.x + st]);
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        float sc = 1.f;
+        const float bound = sh[0];
+        if (bound > 0.f && isfinite(bound)) {
+            int e = (int)floorf(log2f(target / bound));
+            e = max(-60, min(60, e));
+            sc = exp2f((float)e);
+        }
+        scale2[0] = sc;
+        scale2[1] = 1.f / sc;
+    }
+}
+
+// pass 2: dy = gamma*invstd*(dz - sum_dz/M - xhat*sum_dzxhat/M); also emits dgamma/dbeta (block 0)
+__global__ void __launch_bounds__(BN_THREADS) bn_bwd_apply_kernel(const float* __restrict__ y,
+                                                                  const float* __restrict__ dout, int64_t M, int C,
+                                                                  const float* __restrict__ gamma,
+                                                                  const float* __restrict__ beta,
+                                                                  const float* __restrict__ mean,
+                                                                  const float* __restrict__ invstd,
+                                                                  const double* __restrict__ red,
+                                                                  float* __restrict__ dgamma, float* __restrict__ dbeta,
+                                                                  float* __restrict__ dy, __half* __restrict__ dy16,
+                                                                  const float* __restrict__ scale2) {
+    const float f16_scale = (dy16 != nullptr && scale2 != nullptr) ? scale2[0] : 1.f;
+    __shared__ float smu[BN_MAXC], sis[BN_MAXC], sga[BN_MAXC], sbe[BN_MAXC], sa[BN_MAXC], sb[BN_MAXC];
+    for (int c = threadIdx.x; c < C; c += BN_THREADS) {
+        smu[c] = mean[c]; sis[c] = invstd[c];
+        sga[c] = gamma ? gamma[c] : 1.f; sbe[c] = beta ? beta[c] : 0.f;
+        sa[c] = (float)(red[c] / (double)M);
+        sb[c] = (float)(red[C + c] / (double)M);
+        if (blockIdx.x == 0) {
+            if (dbeta) dbeta[c] = (float)red[c];
+            if (dgamma) dgamma[c] = (float)red[C + c];
+        }
+    }
+    __syncthreads();
+    const int64_t total = M * C;
+    for (int64_t i = (int64_t)blockIdx.x * BN_THREADS + threadIdx.x; i < total; i += (int64_t)gridDim.x * BN_THREADS) {
+        const int c = (int)(i % C);
+        const float xh = (y[i] - smu[c]) * sis[c];
+        const float dz = fmaf(xh, sga[c], sbe[c]) > 0.f ? dout[i] : 0.f;
+        const float v = sga[c] * sis[c] * (dz - sa[c] - xh * sb[c]);
+        if (dy) dy[i] = v;
+        if (dy16) dy16[i] = __float2half_rn(v * f16_scale);
+    }
+}
+
+// ---- operand staging ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) cast_f16_kernel(const float* __restrict__ src, __half* __restrict__ dst,
+                                                       int64_t n, float scale, const float* __restrict__ scale_dev) {
+    if (scale_dev != nullptr) scale *= *scale_dev;
+    const int64_t nvec = n >> 2;
+    for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < nvec; i += (int64_t)gridDim.x * 256) {
+        const float4 v = *reinterpret_cast<const float4*>(src + i * 4);
+        __half2 a = __floats2half2_rn(v.x * scale, v.y * scale), b = __floats2half2_rn(v.z * scale, v.w * scale);
+        uint2 pk;
+        pk.x = *reinterpret_cast<uint32_t*>(&a);
+        pk.y = *reinterpret_cast<uint32_t*>(&b);
+        *reinterpret_cast<uint2*>(dst + i * 4) = pk;
+    }
+    if (blockIdx.x == 0 && threadIdx.x < (n & 3)) {
+        const int64_t i = (nvec << 2) + threadIdx.x;
+        dst[i] = __float2half_rn(src[i] * scale);
+    }
+}
+
+__global__ void __launch_bounds__(256) amax_kernel(const float* __restrict__ src, int64_t n, float* amax) {
+    float m = 0.f;
+    for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < n; i += (int64_t)gridDim.x * 256)
+        m = fmaxf(m, fabsf(src[i]));
+#pragma unroll
+    for (int s = 16; s > 0; s >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, s));
+    if ((threadIdx.x & 31) == 0) atomicMax(reinterpret_cast<int*>(amax), __float_as_int(m));   // m >= 0
+}
+
+__global__ void f16_scale_kernel(const float* __restrict__ amax, float target, float* __restrict__ scale2) {
+    float sc = 1.f;
+    const float a = amax[0];
+    if (a > 0.f && isfinite(a)) {
+        int e = (int)floorf(log2f(target / a));
+        e = max(-60, min(60, e));
+        sc = exp2f((float)e);
+    }
+    scale2[0] = sc;
+    scale2[1] = 1.f / sc;
+}
+
+static int stream_grid(int64_t work_items, int per_block) {
+    const int64_t want = ceil_div(work_items, per_block);
+    const int64_t cap = (int64_t)sm_count() * 8;
+    return (int)max((int64_t)1, min(want, cap));
+}
+
+}  // namespace mode
+
+using namespace mode;
+
+extern "C" int mode_bn_stats(const float* y, int64_t M, int32_t C, double* sums, void* stream) {
+    if (!y || !sums || M <= 0 || C <= 0 || C > BN_MAXC) MODE_FAIL("mode_bn_stats: bad arguments (C=%d)", C);
+    cudaStream_t st = (cudaStream_t)stream;
+    const int vpr = C >> 2;
+    if ((C & 3) == 0 && vpr <= BN_THREADS && BN_THREADS % vpr == 0 && (reinterpret_cast<uintptr_t>(y) & 15) == 0) {
+        const int rpi = BN_THREADS / vpr;
+        bn_stats_kernel<<<stream_grid(M, rpi * 8), BN_THREADS, 0, st>>>(y, M, C, sums);
+    } else {
+        bn_stats_scalar_kernel<<<C, BN_THREADS, 0, st>>>(y, M, C, sums);
+    }
+    MODE_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int mode_bn_finalize(const double* sums, int64_t M, int32_t C, const float* gamma, const float* beta,
+                                float eps, float momentum, float* mean, float* invstd, float* scale, float* shift,
+                                float* running_mean, float* running_var, void* stream) {
+    if (!sums || !scale || !shift || M <= 0 || C <= 0) MODE_FAIL("mode_bn_finalize: bad arguments");
+    bn_finalize_kernel<<<(unsigned)ceil_div(C, 128), 128, 0, (cudaStream_t)stream>>>(
+        sums, M, C, gamma, beta, eps, momentum, mean, invstd, scale, shift, running_mean, running_var);
+    MODE_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int mode_bn_apply_relu(const float* y, int64_t M, int32_t C, const float* scale, const float* shift,
+                                  int32_t relu, float* out, void* out_f16, float f16_scale, void* stream) {
+    if (!y || !scale || !shift || (!out && !out_f16) || M <= 0 || C <= 0 || C > BN_MAXC)
+        MODE_FAIL("mode_bn_apply_relu: bad arguments (C=%d)", C);
+    cudaStream_t st = (cudaStream_t)stream;
+    const int64_t total = M * C;
+    const bool aligned = ((reinterpret_cast<uintptr_t>(y) | reinterpret_cast<uintptr_t>(out)) & 15) == 0 &&
+                         (reinterpret_cast<uintptr_t>(out_f16) & 7) == 0;
+    if ((C & 3) == 0 && aligned)
+        bn_apply_kernel<<<stream_grid(total / 4, BN_THREADS * 4), BN_THREADS, 0, st>>>(y, total, C, scale, shift, relu,
+                                                                                      out, (__half*)out_f16, f16_scale);
+    else
+        bn_apply_scalar_kernel<<<stream_grid(total, BN_THREADS * 4), BN_THREADS, 0, st>>>(
+            y, total, C, scale, shift, relu, out, (__half*)out_f16, f16_scale);
+    MODE_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int64_t mode_bn_bwd_workspace_bytes(int32_t C) { return (int64_t)C * (2 * sizeof(double) + 2 * sizeof(int)); }
+
+extern "C" int mode_bn_relu_bwd(const float* y, const float* dout, int64_t M, int32_t C, const float* gamma,
+                                const float* beta, const float* mean, const float* invstd, float* dgamma,
+                                float* dbeta, float* dy, void* dy_f16, float* dy_scale2, void* workspace_v,
+                                void* stream) {
+    if (!y || !dout || !mean || !invstd || !workspace_v || (!dy && !dy_f16) || M <= 0 || C <= 0 || C > BN_MAXC)
+        MODE_FAIL("mode_bn_relu_bwd: bad arguments (C=%d)", C);
+    if (dy_f16 && !dy_scale2) MODE_FAIL("mode_bn_relu_bwd: dy_f16 needs dy_scale2");
+    cudaStream_t st = (cudaStream_t)stream;
+    double* workspace = (double*)workspace_v;
+    int* mx = (int*)(workspace + 2 * (size_t)C);
+    MODE_CUDA(cudaMemsetAsync(workspace_v, 0, (size_t)mode_bn_bwd_workspace_bytes(C), st));
+    const int vpr = C >> 2;
+    const bool aligned = ((reinterpret_cast<uintptr_t>(y) | reinterpret_cast<uintptr_t>(dout)) & 15) == 0;
+    if ((C & 3) == 0 && vpr <= BN_THREADS && BN_THREADS % vpr == 0 && aligned) {
+        const int rpi = BN_THREADS / vpr;
+        bn_bwd_reduce_vec_kernel<<<stream_grid(M, rpi * 8), BN_THREADS, 0, st>>>(y, dout, M, C, gamma, beta, mean,
+                                                                                invstd, workspace, mx);
+    } else {
+        const int gx = (int)max((int64_t)1, min(ceil_div(M, BN_THREADS * 8), (int64_t)64));
+        bn_bwd_reduce_kernel<<<dim3(gx, C), BN_THREADS, 0, st>>>(y, dout, M, C, gamma, beta, mean, invstd, workspace, mx);
+    }
+    MODE_LAUNCH_CHECK();
+    if (dy_f16) {
+        bn_bwd_scale_kernel<<<1, 256, 0, st>>>(workspace, mx, M, C, gamma, invstd, 8192.f, dy_scale2);
+        MODE_LAUNCH_CHECK();
+    }
+    bn_bwd_apply_kernel<<<stream_grid(M * C, BN_THREADS * 8), BN_THREADS, 0, st>>>(
+        y, dout, M, C, gamma, beta, mean, invstd, workspace, dgamma, dbeta, dy, (__half*)dy_f16, dy_scale2);
+    MODE_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int mode_cast_f16(const float* src, void* dst_f16, int64_t n, float scale, const float* scale_dev,
+                             void* stream) {
+    if (!src || !dst_f16 || n <= 0) MODE_FAIL("mode_cast_f16: bad arguments");
+    if ((reinterpret_cast<uintptr_t>(src) & 15) || (reinterpret_cast<uintptr_t>(dst_f16) & 7))
+        MODE_FAIL("mode_cast_f16: pointers must be 16-byte (src) / 8-byte (dst) aligned");
+    cast_f16_kernel<<<stream_grid(n / 4 + 1, 256 * 4), 256, 0, (cudaStream_t)stream>>>(src, (__half*)dst_f16, n, scale,
+                                                                                         scale_dev);
+    MODE_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int mode_amax(const float* src, int64_t n, float* amax, void* stream) {
+    if (!src || !amax || n <= 0) MODE_FAIL("mode_amax: bad arguments");
+    amax_kernel<<<stream_grid(n, 256 * 8), 256, 0, (cudaStream_t)stream>>>(src, n, amax);
+    MODE_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int mode_f16_scale(const float* amax, float target, float* scale2, void* stream) {
+    if (!amax || !scale2 || !(target > 0.f)) MODE_FAIL("mode_f16_scale: bad arguments");
+    f16_scale_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(amax, target, scale2);
+    MODE_LAUNCH_CHECK();
+    return 0;
+}

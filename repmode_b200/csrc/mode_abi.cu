@@ -1,0 +1,103 @@
+// C-ABI glue: error reporting, capability query and the implementation dispatch for the conv entry points.
+// See include/repmode_b200.h for the contract and the reference lines each entry point replaces.
+#include "common.cuh"
+
+namespace mode {
+
+char* err_buf() {
+    static thread_local char buf[kErrLen] = "";
+    return buf;
+}
+
+int sm_count() {
+    static int cached[64] = {0};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;
+    if (cached[dev] == 0) {
+        int n = 0;
+        if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+        cached[dev] = n;
+    }
+    return cached[dev];
+}
+
+// conv_simt.cu
+int conv3d_simt(const float* x, const float* w, const int32_t* sample_u, float* y, int N, int D, int H, int W, int K,
+                int Nout, float out_scale, const float* out_scale_dev, double* bn_sums, cudaStream_t st);
+int wgrad_simt(const float* x, const float* dy, float* dw, int N, int D, int H, int W, int Ci, int Co, float out_scale,
+               const float* out_scale_dev, cudaStream_t st);
+// conv_umma.cu
+bool conv3d_umma_supported(int D, int H, int W, int K, int Nout);
+int conv3d_umma(const __half* x, const __half* w, const int32_t* sample_u, float* y, int N, int D, int H, int W, int K,
+                int Nout, float out_scale, const float* out_scale_dev, double* bn_sums, cudaStream_t st);
+bool wgrad_umma_supported(int D, int H, int W, int Ci, int Co);
+int64_t wgrad_umma_workspace_bytes(int N, int D, int H, int W, int Ci, int Co);
+int wgrad_umma(const __half* x, const __half* dy, float* dw, int N, int D, int H, int W, int Ci, int Co,
+               float out_scale, const float* out_scale_dev, void* workspace, cudaStream_t st);
+
+}  // namespace mode
+
+using namespace mode;
+
+extern "C" const char* mode_last_error(void) { return err_buf(); }
+extern "C" int mode_version(void) { return MODE_ABI_VERSION; }
+
+extern "C" int mode_query(int device, mode_caps_t* caps) {
+    if (!caps) MODE_FAIL("mode_query: caps is NULL");
+    cudaDeviceProp p;
+    MODE_CUDA(cudaGetDeviceProperties(&p, device));
+    caps->sm_major = p.major;
+    caps->sm_minor = p.minor;
+    caps->sm_count = p.multiProcessorCount;
+    caps->smem_per_block_optin = (int32_t)p.sharedMemPerBlockOptin;
+    caps->tmem_columns = 512;
+    caps->abi_version = MODE_ABI_VERSION;
+    if (p.major != 10) MODE_FAIL("mode_query: device %d is sm_%d%d; this library contains sm_100a code only", device, p.major, p.minor);
+    return 0;
+}
+
+extern "C" int mode_conv3d(const void* x, mode_dtype_t x_dtype, const void* w, const int32_t* sample_u, float* y,
+                           int32_t N, int32_t D, int32_t H, int32_t W, int32_t K, int32_t Nout, float out_scale,
+                           const float* out_scale_dev, double* bn_sums, int32_t impl, void* stream) {
+    if (!x || !w || !y) MODE_FAIL("mode_conv3d: null pointer");
+    if (N <= 0 || D <= 0 || H <= 0 || W <= 0 || K <= 0 || Nout <= 0) MODE_FAIL("mode_conv3d: non-positive dimension");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (impl == 0) impl = (x_dtype == MODE_F16) ? 2 : 1;
+    if (impl == 1) {
+        if (x_dtype != MODE_F32) MODE_FAIL("mode_conv3d: the SIMT path takes fp32 operands");
+        return conv3d_simt((const float*)x, (const float*)w, sample_u, y, N, D, H, W, K, Nout, out_scale, out_scale_dev, bn_sums, st);
+    }
+    if (impl == 2) {
+        if (x_dtype != MODE_F16) MODE_FAIL("mode_conv3d: the tcgen05 path takes fp16 operands");
+        if (!conv3d_umma_supported(D, H, W, K, Nout))
+            MODE_FAIL("mode_conv3d: shape D=%d H=%d W=%d K=%d Nout=%d not supported by the tcgen05 path", D, H, W, K, Nout);
+        return conv3d_umma((const __half*)x, (const __half*)w, sample_u, y, N, D, H, W, K, Nout, out_scale, out_scale_dev, bn_sums, st);
+    }
+    MODE_FAIL("mode_conv3d: unknown impl %d", impl);
+}
+
+extern "C" int64_t mode_conv3d_wgrad_workspace_bytes(int32_t N, int32_t D, int32_t H, int32_t W, int32_t Ci, int32_t Co,
+                                                     int32_t impl) {
+    if (impl == 2) return wgrad_umma_workspace_bytes(N, D, H, W, Ci, Co);
+    return 0;
+}
+
+extern "C" int mode_conv3d_wgrad(const void* x, const void* dy, mode_dtype_t dtype, float* d_weff, int32_t N,
+                                 int32_t D, int32_t H, int32_t W, int32_t Ci, int32_t Co, float out_scale,
+                                 const float* out_scale_dev, void* workspace, int32_t impl, void* stream) {
+    if (!x || !dy || !d_weff) MODE_FAIL("mode_conv3d_wgrad: null pointer");
+    if (N <= 0 || D <= 0 || H <= 0 || W <= 0 || Ci <= 0 || Co <= 0) MODE_FAIL("mode_conv3d_wgrad: non-positive dimension");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (impl == 0) impl = (dtype == MODE_F16) ? 2 : 1;
+    if (impl == 1) {
+        if (dtype != MODE_F32) MODE_FAIL("mode_conv3d_wgrad: the SIMT path takes fp32 operands");
+        return wgrad_simt((const float*)x, (const float*)dy, d_weff, N, D, H, W, Ci, Co, out_scale, out_scale_dev, st);
+    }
+    if (impl == 2) {
+        if (dtype != MODE_F16) MODE_FAIL("mode_conv3d_wgrad: the tcgen05 path takes fp16 operands");
+        if (!wgrad_umma_supported(D, H, W, Ci, Co))
+            MODE_FAIL("mode_conv3d_wgrad: shape not supported by the tcgen05 path");
+        return wgrad_umma((const __half*)x, (const __half*)dy, d_weff, N, D, H, W, Ci, Co, out_scale, out_scale_dev, workspace, st);
+    }
+    MODE_FAIL("mode_conv3d_wgrad: unknown impl %d", impl);
+}

@@ -1,0 +1,336 @@
+// K1 / K1b: gate softmax + expert re-parameterisation of RepMode's MoDEConv, forward and backward.
+//
+// Reference behaviour being replaced (paths relative to the reference tree):
+//   gate Linear -> view(N,E,Co) -> Softmax(dim=1) ........ fnet/nn_modules/RepMode.py:198-200
+//   trans_kernel (centre zero padding) ..................... fnet/nn_modules/RepMode.py:165-169
+//   routing (pool constants, expert mixing) ................ fnet/nn_modules/RepMode.py:171-192
+// The reference launches ~(9N+5) elementwise kernels per layer, each a full pass over [Co,Ci,125];
+// here one launch reads the experts once (620*Co*Ci bytes) and writes the packed conv operand(s).
+//
+// HBM-bound kernels: every global access is a contiguous >=64-byte segment per warp, experts are read
+// exactly once per distinct gate input, and the mixing arithmetic is done in fp32 in the reference's
+// own association order so the fp32 output is bit-identical up to the softmax's exp().
+#include "common.cuh"
+
+namespace mode {
+
+__device__ __forceinline__ void store_w(float* p, float v) { *p = v; }
+__device__ __forceinline__ void store_w(__half* p, float v) { *p = __float2half_rn(v); }
+
+// grid (Co, ceil(Ci/32), U), block 128
+template <typename OutT>
+__global__ void __launch_bounds__(128) reparam_fwd_kernel(mode_layer_t L, const int32_t* __restrict__ task_ids,
+                                                          const float* __restrict__ t_dense,
+                                                          float* __restrict__ g_out, OutT* __restrict__ w_fwd,
+                                                          float w_scale, const float* __restrict__ w_scale_dev) {
+    __shared__ float sw[32 * 125];   // [i][tap]; stride 125 is odd -> column reads are conflict free
+    __shared__ float slog[MODE_NUM_EXPERTS];
+    __shared__ float sg[MODE_NUM_EXPERTS];
+    const int o = blockIdx.x, ic = blockIdx.y, u = blockIdx.z;
+    const int Ci = L.ci, Co = L.co, T = L.num_tasks;
+    const int tid = threadIdx.x;
+
+    if (tid < MODE_NUM_EXPERTS) {
+        const int row = tid * Co + o;                         // gate row e*Co+o (RepMode.py:199)
+        float logit;
+        if (task_ids != nullptr) {
+            logit = __fadd_rn(L.gate_w[(size_t)row * T + task_ids[u]], L.gate_b[row]);
+        } else {
+            float acc = 0.f;
+            for (int t = 0; t < T; ++t) acc = fmaf(t_dense[(size_t)u * T + t], L.gate_w[(size_t)row * T + t], acc);
+            logit = acc + L.gate_b[row];
+        }
+        slog[tid] = logit;
+    }
+    __syncthreads();
+    if (tid == 0) {
+        float m = slog[0];
+        for (int e = 1; e < MODE_NUM_EXPERTS; ++e) m = fmaxf(m, slog[e]);
+        float ex[MODE_NUM_EXPERTS], s = 0.f;
+        for (int e = 0; e < MODE_NUM_EXPERTS; ++e) { ex[e] = expf(slog[e] - m); s += ex[e]; }
+        for (int e = 0; e < MODE_NUM_EXPERTS; ++e) {
+            sg[e] = ex[e] / s;
+            if (ic == 0 && g_out != nullptr) g_out[((size_t)u * MODE_NUM_EXPERTS + e) * Co + o] = sg[e];
+        }
+    }
+    __syncthreads();
+    const float g0 = sg[0], g1 = sg[1], g2 = sg[2], g3 = sg[3], g4 = sg[4];
+    if (w_scale_dev != nullptr) w_scale *= *w_scale_dev;
+    const float c3 = 1.0f / 27, c5 = 1.0f / 125;               // fp32-rounded pool constants (RepMode.py:161-163)
+
+    for (int idx = tid; idx < 32 * 125; idx += 128) {
+        const int i = idx / 125, tap = idx - i * 125;
+        const int c = ic * 32 + i;
+        float val = 0.f;
+        if (c < Ci) {
+            const size_t oc = (size_t)o * Ci + c;
+            const int kd = tap / 25, kh = (tap / 5) % 5, kw = tap % 5;
+            const bool inner = (kd >= 1 && kd <= 3 && kh >= 1 && kh <= 3 && kw >= 1 && kw <= 3);
+            const float t0 = __fmul_rn(L.k5[oc * 125 + tap], g0);
+            float t1 = 0.f, t2 = 0.f, t3 = 0.f;
+            if (inner) {
+                t1 = __fmul_rn(L.k3[oc * 27 + ((kd - 1) * 3 + (kh - 1)) * 3 + (kw - 1)], g1);
+                t3 = __fmul_rn(__fmul_rn(L.a3[oc], c3), g3);
+            }
+            if (tap == 62) t2 = __fmul_rn(L.k1[oc], g2);
+            const float t4 = __fmul_rn(__fmul_rn(L.a5[oc], c5), g4);
+            // reference association order: ((((e5 + e3) + e1) + ea3) + ea5)   (RepMode.py:184-188)
+            val = __fadd_rn(__fadd_rn(__fadd_rn(__fadd_rn(t0, t1), t2), t3), t4);
+        }
+        sw[idx] = val;
+    }
+    __syncthreads();
+    const int warp = tid >> 5, lane = tid & 31;
+    const int nci = gridDim.y;
+    for (int tap = warp; tap < 125; tap += 4) {
+        const size_t dst = ((((size_t)u * 125 + tap) * nci + ic) * Co + o) * MODE_KC + lane;
+        store_w(w_fwd + dst, sw[lane * 125 + tap] * w_scale);
+    }
+}
+
+// fwd pack [u][tap][ic][o][32]  ->  dgrad pack [u][124-tap][oc][i][32]   (flip taps, swap channel roles)
+// grid (ceil(Ci/32), ceil(Co/32), U*125), block (32, 8)
+template <typename T>
+__global__ void __launch_bounds__(256) pack_dgrad_kernel(const T* __restrict__ src, T* __restrict__ dst, int Ci,
+                                                         int Co) {
+    __shared__ T tile[32][33];
+    const int ic = blockIdx.x, oc = blockIdx.y;
+    const int u = blockIdx.z / 125, tap = blockIdx.z % 125;
+    const int nci = gridDim.x, nco = gridDim.y;
+    const int tx = threadIdx.x, ty = threadIdx.y;
+    for (int r = ty; r < 32; r += 8) {
+        const int o = oc * 32 + r;
+        T v = T(0);
+        if (o < Co) v = src[((((size_t)u * 125 + tap) * nci + ic) * Co + o) * MODE_KC + tx];
+        tile[r][tx] = v;                                     // (o = oc*32+r, i = ic*32+tx)
+    }
+    __syncthreads();
+    for (int r = ty; r < 32; r += 8) {
+        const int i = ic * 32 + r;
+        if (i < Ci) dst[((((size_t)u * 125 + (124 - tap)) * nco + oc) * Ci + i) * MODE_KC + tx] = tile[tx][r];
+    }
+}
+
+// K1b main kernel. grid (Co, ceil(Ci/32)), block 128. Loops over the samples; every global access is a
+// contiguous segment (dW rows of 32 ci, expert slabs of 32*125 floats).
+__global__ void __launch_bounds__(128) reparam_bwd_kernel(mode_layer_t L, const int32_t* __restrict__ sample_u,
+                                                          int n_samples, const float* __restrict__ g,
+                                                          const float* __restrict__ d_weff,
+                                                          float* __restrict__ dk5, float* __restrict__ dk3,
+                                                          float* __restrict__ dk1, float* __restrict__ da3,
+                                                          float* __restrict__ da5, float* __restrict__ dg_part) {
+    __shared__ float sk5[32 * 125];
+    __shared__ float sk3[32 * 27];
+    __shared__ float sdk3[32 * 27];
+    __shared__ float s_all[32], s_inner[32], s_center[32];
+    __shared__ float s_dg[2];
+    const int o = blockIdx.x, ic = blockIdx.y;
+    const int Ci = L.ci, Co = L.co;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int c = ic * 32 + lane;
+    const bool live = c < Ci;
+    const int nlive = min(32, Ci - ic * 32);
+    const float c3 = 1.0f / 27, c5 = 1.0f / 125;
+
+    // stage this (o, ci-block)'s experts: contiguous slabs
+    {
+        const float* src5 = L.k5 + ((size_t)o * Ci + ic * 32) * 125;
+        for (int idx = tid; idx < 32 * 125; idx += 128) sk5[idx] = idx < nlive * 125 ? src5[idx] : 0.f;
+        const float* src3 = L.k3 + ((size_t)o * Ci + ic * 32) * 27;
+        for (int idx = tid; idx < 32 * 27; idx += 128) {
+            sk3[idx] = idx < nlive * 27 ? src3[idx] : 0.f;
+            sdk3[idx] = 0.f;
+        }
+        if (tid < 32) { s_all[tid] = 0.f; s_inner[tid] = 0.f; s_center[tid] = 0.f; }
+        if (tid < 2) s_dg[tid] = 0.f;
+    }
+    const float k1v = live ? L.k1[(size_t)o * Ci + c] : 0.f;
+    const float a3v = live ? L.a3[(size_t)o * Ci + c] * c3 : 0.f;
+    const float a5v = live ? L.a5[(size_t)o * Ci + c] * c5 : 0.f;
+    __syncthreads();
+
+    float acc5[32];
+#pragma unroll
+    for (int j = 0; j < 32; ++j) acc5[j] = 0.f;
+    float acc_k1 = 0.f, acc_a3 = 0.f, acc_a5 = 0.f;
+
+    for (int n = 0; n < n_samples; ++n) {
+        const int u = sample_u[n];
+        const float* gu = g + (size_t)u * MODE_NUM_EXPERTS * Co + o;
+        const float g0 = gu[0], g1 = gu[Co], g2 = gu[2 * Co], g3 = gu[3 * Co], g4 = gu[4 * Co];
+        const float* dw = d_weff + ((size_t)n * 125 * Co + o) * Ci + c;
+        float p_all = 0.f, p_inner = 0.f, q0 = 0.f, q1 = 0.f;
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+            const int tap = warp + 4 * j;
+            if (tap < 125) {
+                const float v = live ? dw[(size_t)tap * Co * Ci] : 0.f;
+                acc5[j] = fmaf(g0, v, acc5[j]);
+                p_all += v;
+                q0 = fmaf(sk5[lane * 125 + tap], v, q0);
+                const int kd = tap / 25, kh = (tap / 5) % 5, kw = tap % 5;
+                if (kd >= 1 && kd <= 3 && kh >= 1 && kh <= 3 && kw >= 1 && kw <= 3) {
+                    const int t3 = ((kd - 1) * 3 + (kh - 1)) * 3 + (kw - 1);
+                    p_inner += v;
+                    q1 = fmaf(sk3[lane * 27 + t3], v, q1);
+                    sdk3[lane * 27 + t3] = fmaf(g1, v, sdk3[lane * 27 + t3]);   // owned by this thread only
+                    if (tap == 62) s_center[lane] = v;
+                }
+            }
+        }
+        atomicAdd(&s_all[lane], p_all);
+        atomicAdd(&s_inner[lane], p_inner);
+#pragma unroll
+        for (int s = 16; s > 0; s >>= 1) {
+            q0 += __shfl_xor_sync(0xffffffffu, q0, s);
+            q1 += __shfl_xor_sync(0xffffffffu, q1, s);
+        }
+        if (lane == 0) { atomicAdd(&s_dg[0], q0); atomicAdd(&s_dg[1], q1); }
+        __syncthreads();
+        if (warp == 0) {
+            const float A = s_all[lane], I = s_inner[lane], Cn = s_center[lane];
+            acc_k1 = fmaf(g2, Cn, acc_k1);
+            acc_a3 = fmaf(g3, I * c3, acc_a3);
+            acc_a5 = fmaf(g4, A * c5, acc_a5);
+            float d2 = k1v * Cn, d3 = a3v * I, d4 = a5v * A;
+#pragma unroll
+            for (int s = 16; s > 0; s >>= 1) {
+                d2 += __shfl_xor_sync(0xffffffffu, d2, s);
+                d3 += __shfl_xor_sync(0xffffffffu, d3, s);
+                d4 += __shfl_xor_sync(0xffffffffu, d4, s);
+            }
+            if (lane == 0) {
+                float* dst = dg_part + (((size_t)ic * n_samples + n) * MODE_NUM_EXPERTS) * Co + o;
+                dst[0] = s_dg[0];
+                dst[Co] = s_dg[1];
+                dst[2 * Co] = d2;
+                dst[3 * Co] = d3;
+                dst[4 * Co] = d4;
+                s_dg[0] = 0.f;
+                s_dg[1] = 0.f;
+            }
+            s_all[lane] = 0.f;
+            s_inner[lane] = 0.f;
+            s_center[lane] = 0.f;
+        }
+        __syncthreads();
+    }
+
+    // write expert gradients through shared memory so the global stores are contiguous
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+        const int tap = warp + 4 * j;
+        if (tap < 125) sk5[lane * 125 + tap] = acc5[j];
+    }
+    __syncthreads();
+    float* dst5 = dk5 + ((size_t)o * Ci + ic * 32) * 125;
+    for (int idx = tid; idx < nlive * 125; idx += 128) dst5[idx] = sk5[idx];
+    float* dst3 = dk3 + ((size_t)o * Ci + ic * 32) * 27;
+    for (int idx = tid; idx < nlive * 27; idx += 128) dst3[idx] = sdk3[idx];
+    if (warp == 0 && live) {
+        dk1[(size_t)o * Ci + c] = acc_k1;
+        da3[(size_t)o * Ci + c] = acc_a3;
+        da5[(size_t)o * Ci + c] = acc_a5;
+    }
+}
+
+// softmax + Linear backward; one thread per output channel o, samples in order -> deterministic.
+__global__ void gate_bwd_kernel(mode_layer_t L, const int32_t* __restrict__ task_ids,
+                                const float* __restrict__ t_dense, const int32_t* __restrict__ sample_u,
+                                int n_samples, int nci, const float* __restrict__ g,
+                                const float* __restrict__ dg_part, float* __restrict__ dgate_w,
+                                float* __restrict__ dgate_b) {
+    const int o = blockIdx.x * blockDim.x + threadIdx.x;
+    const int Co = L.co, T = L.num_tasks;
+    if (o >= Co) return;
+    float db[MODE_NUM_EXPERTS];
+    for (int e = 0; e < MODE_NUM_EXPERTS; ++e) {
+        db[e] = 0.f;
+        for (int t = 0; t < T; ++t) dgate_w[((size_t)e * Co + o) * T + t] = 0.f;
+    }
+    for (int n = 0; n < n_samples; ++n) {
+        const int u = sample_u[n];
+        float gv[MODE_NUM_EXPERTS], dg[MODE_NUM_EXPERTS], s = 0.f;
+        for (int e = 0; e < MODE_NUM_EXPERTS; ++e) {
+            gv[e] = g[((size_t)u * MODE_NUM_EXPERTS + e) * Co + o];
+            float a = 0.f;
+            for (int b = 0; b < nci; ++b) a += dg_part[(((size_t)b * n_samples + n) * MODE_NUM_EXPERTS + e) * Co + o];
+            dg[e] = a;
+            s = fmaf(gv[e], a, s);
+        }
+        for (int e = 0; e < MODE_NUM_EXPERTS; ++e) {
+            const float dl = gv[e] * (dg[e] - s);
+            db[e] += dl;
+            float* wrow = dgate_w + ((size_t)e * Co + o) * T;
+            if (task_ids != nullptr) wrow[task_ids[u]] += dl;
+            else
+                for (int t = 0; t < T; ++t) wrow[t] = fmaf(dl, t_dense[(size_t)u * T + t], wrow[t]);
+        }
+    }
+    for (int e = 0; e < MODE_NUM_EXPERTS; ++e) dgate_b[(size_t)e * Co + o] = db[e];
+}
+
+}  // namespace mode
+
+using namespace mode;
+
+extern "C" int64_t mode_packed_weight_elems(int32_t k_channels, int32_t n_channels) {
+    return (int64_t)MODE_TAPS * ceil_div(k_channels, MODE_KC) * n_channels * MODE_KC;
+}
+
+extern "C" int mode_reparam_fwd(const mode_layer_t* L, const int32_t* task_ids, const float* t_dense, int32_t U,
+                                float* g_out, void* w_fwd, void* w_dgrad, mode_dtype_t w_dtype, float w_scale,
+                                const float* w_scale_dev, void* stream) {
+    if (!L || !w_fwd || U <= 0) MODE_FAIL("mode_reparam_fwd: null layer/output or U <= 0");
+    if ((task_ids == nullptr) == (t_dense == nullptr)) MODE_FAIL("mode_reparam_fwd: pass exactly one of task_ids / t_dense");
+    if (L->ci <= 0 || L->co <= 0 || L->num_tasks <= 0) MODE_FAIL("mode_reparam_fwd: bad layer dims");
+    if ((int64_t)U * 125 > 65535) MODE_FAIL("mode_reparam_fwd: U too large (%d)", U);
+    cudaStream_t st = (cudaStream_t)stream;
+    const int nci = (int)ceil_div(L->ci, 32), nco = (int)ceil_div(L->co, 32);
+    dim3 grid(L->co, nci, U);
+    if (w_dtype == MODE_F32) {
+        reparam_fwd_kernel<float><<<grid, 128, 0, st>>>(*L, task_ids, t_dense, g_out, (float*)w_fwd, w_scale,
+                                                        w_scale_dev);
+        MODE_LAUNCH_CHECK();
+        if (w_dgrad) {
+            pack_dgrad_kernel<float><<<dim3(nci, nco, U * 125), dim3(32, 8), 0, st>>>((const float*)w_fwd,
+                                                                                   (float*)w_dgrad, L->ci, L->co);
+            MODE_LAUNCH_CHECK();
+        }
+    } else if (w_dtype == MODE_F16) {
+        reparam_fwd_kernel<__half><<<grid, 128, 0, st>>>(*L, task_ids, t_dense, g_out, (__half*)w_fwd, w_scale,
+                                                         w_scale_dev);
+        MODE_LAUNCH_CHECK();
+        if (w_dgrad) {
+            pack_dgrad_kernel<__half><<<dim3(nci, nco, U * 125), dim3(32, 8), 0, st>>>((const __half*)w_fwd,
+                                                                                    (__half*)w_dgrad, L->ci, L->co);
+            MODE_LAUNCH_CHECK();
+        }
+    } else {
+        MODE_FAIL("mode_reparam_fwd: unknown dtype %d", (int)w_dtype);
+    }
+    return 0;
+}
+
+extern "C" int64_t mode_reparam_bwd_workspace_bytes(int32_t ci, int32_t co, int32_t n_samples) {
+    return (int64_t)ceil_div(ci, 32) * n_samples * MODE_NUM_EXPERTS * co * sizeof(float);
+}
+
+extern "C" int mode_reparam_bwd(const mode_layer_t* L, const int32_t* task_ids, const float* t_dense, int32_t U,
+                                const int32_t* sample_u, int32_t n_samples, const float* g, const float* d_weff,
+                                float* dk5, float* dk3, float* dk1, float* da3, float* da5, float* dgate_w,
+                                float* dgate_b, void* workspace, void* stream) {
+    if (!L || !sample_u || !g || !d_weff || !workspace) MODE_FAIL("mode_reparam_bwd: null argument");
+    if ((task_ids == nullptr) == (t_dense == nullptr)) MODE_FAIL("mode_reparam_bwd: pass exactly one of task_ids / t_dense");
+    if (!dk5 || !dk3 || !dk1 || !da3 || !da5 || !dgate_w || !dgate_b) MODE_FAIL("mode_reparam_bwd: null output");
+    (void)U;
+    cudaStream_t st = (cudaStream_t)stream;
+    const int nci = (int)ceil_div(L->ci, 32);
+    reparam_bwd_kernel<<<dim3(L->co, nci), 128, 0, st>>>(*L, sample_u, n_samples, g, d_weff, dk5, dk3, dk1, da3, da5,
+                                                        (float*)workspace);
+    MODE_LAUNCH_CHECK();
+    gate_bwd_kernel<<<(unsigned)ceil_div(L->co, 128), 128, 0, st>>>(*L, task_ids, t_dense, sample_u, n_samples, nci, g,
+                                                                  (const float*)workspace, dgate_w, dgate_b);
+    MODE_LAUNCH_CHECK();
+    return 0;
+}

@@ -1,0 +1,250 @@
+"""Host side of the MoDE-conv hot path: torch.autograd.Function + thin wrappers that hand raw device
+pointers and the current CUDA stream to the C ABI (include/repmode_b200.h).
+
+PyTorch is used for device memory, streams and autograd bookkeeping only; every arithmetic step of
+MoDEConv.forward / backward (fnet/nn_modules/RepMode.py:194-214 in the reference tree) runs in the
+hand-written sm_100a kernels.  There is no CPU / eager fallback: a non-CUDA tensor raises.
+"""
+import ctypes
+import os
+
+import torch
+
+from . import lib as _lib
+
+E = 5
+BN_EPS = 1e-5
+BN_MOMENTUM = 0.1
+
+
+def default_precision():
+    """'f16' = tcgen05 tensor-core path (fp16 operands with power-of-two scaling, fp32 accumulate; same
+    10-bit mantissa as TF32) wherever the layer shape allows, 'f32' = SIMT fp32 everywhere."""
+    return os.environ.get("REPMODE_PRECISION", "f16")
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _p(t):
+    return None if t is None else ctypes.c_void_p(t.data_ptr())
+
+
+def _require_cuda(*ts):
+    for t in ts:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError("repmode_b200: the MoDE-conv path is CUDA-only (sm_100a); got a CPU tensor. "
+                               "There is no CPU fallback by design.")
+
+
+def to_ndhwc(x):
+    """[N,C,D,H,W] (any strides) -> dense [N,D,H,W,C] fp32. Free when x is already channels_last_3d."""
+    return x.permute(0, 2, 3, 4, 1).contiguous().float()
+
+
+def from_ndhwc(y):
+    """dense [N,D,H,W,C] -> logical [N,C,D,H,W] view (channels_last_3d strides, no copy)."""
+    return y.permute(0, 4, 1, 2, 3)
+
+
+def _layer(k5, k3, k1, a3, a5, gate_w, gate_b):
+    co, ci = k5.shape[0], k5.shape[1]
+    for t in (k5, k3, k1, a3, a5, gate_w, gate_b):
+        if t.dtype != torch.float32 or not t.is_contiguous():
+            raise RuntimeError("repmode_b200: MoDEConv parameters must be contiguous fp32")
+    L = _lib.ModeLayer(k5.data_ptr(), k3.data_ptr(), k1.data_ptr(), a3.data_ptr(), a5.data_ptr(), gate_w.data_ptr(),
+                       gate_b.data_ptr(), ci, co, gate_w.shape[1])
+    return L, ci, co
+
+
+def umma_shape_ok(ci, co, d, h, w):
+    """Shapes the tcgen05 kernels take (conv_umma.cu); everything else runs the SIMT fp32 kernels."""
+    return ci % 32 == 0 and co % 32 == 0 and co <= 256 and ci <= 512 and h % 16 == 0 and w % 8 == 0 \
+        and os.environ.get("REPMODE_DISABLE_UMMA", "0") != "1"
+
+
+def reparam_fwd(layer, gate_in, U, ci, co, dtype, want_dgrad, w_scale_dev=None):
+    """K1. Returns g [U,5,Co], w_fwd, w_dgrad (packed, see header)."""
+    lib = _lib.load()
+    dev = gate_in.device
+    tdt = torch.float16 if dtype == _lib.MODE_F16 else torch.float32
+    g = torch.empty((U, E, co), dtype=torch.float32, device=dev)
+    w_fwd = torch.empty(U * lib.mode_packed_weight_elems(ci, co), dtype=tdt, device=dev)
+    w_dg = torch.empty(U * lib.mode_packed_weight_elems(co, ci), dtype=tdt, device=dev) if want_dgrad else None
+    ids, dense = (gate_in, None) if not gate_in.dtype.is_floating_point else (None, gate_in)
+    _lib.check(lib.mode_reparam_fwd(ctypes.byref(layer), _p(ids), _p(dense), U, _p(g), _p(w_fwd), _p(w_dg), dtype, 1.0,
+                                    _p(w_scale_dev), _stream()), "mode_reparam_fwd")
+    return g, w_fwd, w_dg
+
+
+def conv3d(x, dtype, w, sample_u, n, d, h, wd, k, nout, out_scale_dev=None, bn_sums=None, impl=0):
+    lib = _lib.load()
+    y = torch.empty((n, d, h, wd, nout), dtype=torch.float32, device=x.device)
+    _lib.check(lib.mode_conv3d(_p(x), dtype, _p(w), _p(sample_u), _p(y), n, d, h, wd, k, nout, 1.0, _p(out_scale_dev),
+                               _p(bn_sums), impl, _stream()), "mode_conv3d")
+    return y
+
+
+def conv3d_wgrad(x, dy, dtype, n, d, h, wd, ci, co, out_scale_dev=None, impl=0):
+    lib = _lib.load()
+    dw = torch.empty((n, 125, co, ci), dtype=torch.float32, device=x.device)
+    impl_eff = impl if impl else (2 if dtype == _lib.MODE_F16 else 1)
+    ws_bytes = lib.mode_conv3d_wgrad_workspace_bytes(n, d, h, wd, ci, co, impl_eff)
+    ws = torch.empty(max(int(ws_bytes), 16), dtype=torch.uint8, device=x.device)
+    _lib.check(lib.mode_conv3d_wgrad(_p(x), _p(dy), dtype, _p(dw), n, d, h, wd, ci, co, 1.0, _p(out_scale_dev), _p(ws),
+                                     impl_eff, _stream()), "mode_conv3d_wgrad")
+    return dw
+
+
+def f16_scale_of(tensors, target):
+    """Device-side power-of-two scale {s, 1/s} with s*max|t| ~ target over the given fp32 tensors."""
+    lib = _lib.load()
+    dev = tensors[0].device
+    amax = torch.zeros(1, dtype=torch.float32, device=dev)
+    for t in tensors:
+        _lib.check(lib.mode_amax(_p(t), t.numel(), _p(amax), _stream()), "mode_amax")
+    s2 = torch.empty(2, dtype=torch.float32, device=dev)
+    _lib.check(lib.mode_f16_scale(_p(amax), float(target), _p(s2), _stream()), "mode_f16_scale")
+    return s2
+
+
+def cast_f16(x, scale_dev=None):
+    lib = _lib.load()
+    out = torch.empty(x.shape, dtype=torch.float16, device=x.device)
+    _lib.check(lib.mode_cast_f16(_p(x), _p(out), x.numel(), 1.0, _p(scale_dev), _stream()), "mode_cast_f16")
+    return out
+
+
+class ModeConvFunction(torch.autograd.Function):
+    """MoDEConv.forward as one autograd node.
+
+    forward(x, gate_in, k5, k3, k1, a3, a5, gate_w, gate_b, bn_w, bn_b, running_mean, running_var, training,
+            conv_type, precision) -> out [N,Co,D,H,W] (channels_last_3d strides)
+    gate_in: int32 task ids [N] (what Net passes) or a float [N,T] embedding (the MoDEConv(x, t) signature).
+    """
+
+    @staticmethod
+    @torch.amp.custom_fwd(device_type="cuda", cast_inputs=torch.float32)
+    def forward(ctx, x, gate_in, k5, k3, k1, a3, a5, gate_w, gate_b, bn_w, bn_b, running_mean, running_var, training,
+                conv_type, precision):
+        _require_cuda(x, gate_in, k5)
+        lib = _lib.load()
+        n, ci_x, d, h, wd = x.shape
+        layer, ci, co = _layer(k5, k3, k1, a3, a5, gate_w, gate_b)
+        if ci_x != ci:
+            raise RuntimeError(f"MoDEConv: input has {ci_x} channels, layer expects {ci}")
+        dev = x.device
+        normal = conv_type == "normal"
+        if gate_in.dtype.is_floating_point:
+            gate_in = gate_in.contiguous().float()
+        else:
+            gate_in = gate_in.to(torch.int32).contiguous()
+        if training:
+            U, gate_u = n, gate_in
+            sample_u = torch.arange(n, dtype=torch.int32, device=dev)
+        else:                                   # eval: the whole batch uses sample 0's kernel (RepMode.py:209-210)
+            U, gate_u = 1, gate_in[:1].contiguous()
+            sample_u = torch.zeros(n, dtype=torch.int32, device=dev)
+        needs_dx = ctx.needs_input_grad[0]
+        needs_dw = any(ctx.needs_input_grad[2:9])
+        use_umma = precision == "f16" and umma_shape_ok(ci, co, d, h, wd)
+        dtype = _lib.MODE_F16 if use_umma else _lib.MODE_F32
+
+        xn = to_ndhwc(x)
+        w_s2 = None
+        if use_umma:
+            w_s2 = f16_scale_of([k5, k3, k1, a3, a5], 1024.0)        # |W_eff| <= max|expert| (gates sum to 1)
+            x_op = cast_f16(xn)
+        else:
+            x_op = xn
+        g, w_fwd, w_dg = reparam_fwd(layer, gate_u, U, ci, co, dtype, needs_dx, w_s2[0:1] if use_umma else None)
+
+        bn_train = normal and training
+        sums = torch.zeros(2 * co, dtype=torch.float64, device=dev) if bn_train else None
+        y = conv3d(x_op, dtype, w_fwd, sample_u, n, d, h, wd, ci, co, w_s2[1:2] if use_umma else None, sums)
+        m_rows = n * d * h * wd
+        mean = invstd = None
+        if normal:
+            scale = torch.empty(co, dtype=torch.float32, device=dev)
+            shift = torch.empty(co, dtype=torch.float32, device=dev)
+            if training:
+                mean = torch.empty(co, dtype=torch.float32, device=dev)
+                invstd = torch.empty(co, dtype=torch.float32, device=dev)
+                _lib.check(lib.mode_bn_finalize(_p(sums), m_rows, co, _p(bn_w), _p(bn_b), BN_EPS, BN_MOMENTUM, _p(mean),
+                                                _p(invstd), _p(scale), _p(shift), _p(running_mean), _p(running_var),
+                                                _stream()), "mode_bn_finalize")
+            else:
+                invstd_r = torch.rsqrt(running_var + BN_EPS)
+                scale = (bn_w * invstd_r).contiguous()
+                shift = (bn_b - running_mean * scale).contiguous()
+            out = torch.empty_like(y)
+            _lib.check(lib.mode_bn_apply_relu(_p(y), m_rows, co, _p(scale), _p(shift), 1, _p(out), None, 1.0, _stream()),
+                       "mode_bn_apply_relu")
+        else:
+            out = y
+        if needs_dx or needs_dw or (normal and (ctx.needs_input_grad[9] or ctx.needs_input_grad[10])):
+            if normal and not training:
+                raise NotImplementedError("MoDEConv backward in eval mode (frozen BatchNorm) is not supported")
+            ctx.save_for_backward(x_op, y if normal else None, g, w_dg, gate_u, sample_u, k5, k3, k1, a3, a5, gate_w,
+                                  gate_b, bn_w, bn_b, mean, invstd, w_s2)
+            ctx.cfg = (n, d, h, wd, ci, co, U, normal, use_umma, needs_dx, needs_dw)
+        return from_ndhwc(out)
+
+    @staticmethod
+    @torch.amp.custom_bwd(device_type="cuda")
+    def backward(ctx, dout):
+        lib = _lib.load()
+        (x_op, y, g, w_dg, gate_u, sample_u, k5, k3, k1, a3, a5, gate_w, gate_b, bn_w, bn_b, mean, invstd,
+         w_s2) = ctx.saved_tensors
+        n, d, h, wd, ci, co, U, normal, use_umma, needs_dx, needs_dw = ctx.cfg
+        dev = dout.device
+        dtype = _lib.MODE_F16 if use_umma else _lib.MODE_F32
+        doutn = to_ndhwc(dout)
+        m_rows = n * d * h * wd
+        dgamma = dbeta = None
+        dy_s2 = None
+        if normal:
+            dgamma = torch.empty(co, dtype=torch.float32, device=dev)
+            dbeta = torch.empty(co, dtype=torch.float32, device=dev)
+            ws = torch.empty(int(lib.mode_bn_bwd_workspace_bytes(co)), dtype=torch.uint8, device=dev)
+            if use_umma:
+                dy_op = torch.empty((n, d, h, wd, co), dtype=torch.float16, device=dev)
+                dy_s2 = torch.empty(2, dtype=torch.float32, device=dev)
+                _lib.check(lib.mode_bn_relu_bwd(_p(y), _p(doutn), m_rows, co, _p(bn_w), _p(bn_b), _p(mean), _p(invstd),
+                                                _p(dgamma), _p(dbeta), None, _p(dy_op), _p(dy_s2), _p(ws), _stream()),
+                           "mode_bn_relu_bwd")
+            else:
+                dy_op = torch.empty((n, d, h, wd, co), dtype=torch.float32, device=dev)
+                _lib.check(lib.mode_bn_relu_bwd(_p(y), _p(doutn), m_rows, co, _p(bn_w), _p(bn_b), _p(mean), _p(invstd),
+                                                _p(dgamma), _p(dbeta), _p(dy_op), None, None, _p(ws), _stream()),
+                           "mode_bn_relu_bwd")
+        elif use_umma:
+            dy_s2 = f16_scale_of([doutn], 8192.0)
+            dy_op = cast_f16(doutn, dy_s2[0:1])
+        else:
+            dy_op = doutn
+
+        dx = None
+        if needs_dx:
+            osd = (dy_s2[1:2] * w_s2[1:2]) if use_umma else None
+            dxn = conv3d(dy_op, dtype, w_dg, sample_u, n, d, h, wd, co, ci, osd, None)
+            dx = from_ndhwc(dxn)
+        grads = [None] * 7
+        if needs_dw:
+            d_weff = conv3d_wgrad(x_op, dy_op, dtype, n, d, h, wd, ci, co, dy_s2[1:2] if use_umma else None)
+            layer, _, _ = _layer(k5, k3, k1, a3, a5, gate_w, gate_b)
+            outs = [torch.empty_like(t) for t in (k5, k3, k1, a3, a5, gate_w, gate_b)]
+            ws = torch.empty(max(int(lib.mode_reparam_bwd_workspace_bytes(ci, co, n)), 16), dtype=torch.uint8, device=dev)
+            ids, dense = (gate_u, None) if not gate_u.dtype.is_floating_point else (None, gate_u)
+            _lib.check(lib.mode_reparam_bwd(ctypes.byref(layer), _p(ids), _p(dense), U, _p(sample_u), n, _p(g), _p(d_weff),
+                                            *[_p(o) for o in outs], _p(ws), _stream()), "mode_reparam_bwd")
+            grads = outs
+        return (dx, None, *grads, dgamma, dbeta, None, None, None, None, None)
+
+
+def mode_conv(x, gate_in, params, bn, training, conv_type="normal", precision=None):
+    """Functional MoDEConv. params: (k5,k3,k1,a3,a5,gate_w,gate_b); bn: (weight,bias,running_mean,running_var) or None."""
+    bn_w, bn_b, rm, rv = bn if bn is not None else (None, None, None, None)
+    return ModeConvFunction.apply(x, gate_in, *params, bn_w, bn_b, rm, rv, training, conv_type,
+                                  precision or default_precision())

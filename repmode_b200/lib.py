@@ -1,0 +1,110 @@
+"""ctypes binding of librepmode_b200.so (the C ABI in include/repmode_b200.h) and its in-tree nvcc build.
+
+There is deliberately no CPU or PyTorch fallback: if the shared library is missing or a call fails, the
+caller gets a RuntimeError carrying mode_last_error().
+"""
+import ctypes
+import os
+import subprocess
+import threading
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "csrc")
+SO_PATH = os.path.join(HERE, "librepmode_b200.so")
+SOURCES = ["mode_abi.cu", "reparam.cu", "conv_simt.cu", "bn.cu", "conv_umma.cu"]
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-shared",
+              "-Xcompiler", "-fPIC"]
+
+MODE_F32, MODE_F16 = 0, 1
+IMPL_AUTO, IMPL_SIMT, IMPL_UMMA = 0, 1, 2
+
+_lock = threading.Lock()
+_lib = None
+
+
+class ModeLayer(ctypes.Structure):
+    _fields_ = [("k5", ctypes.c_void_p), ("k3", ctypes.c_void_p), ("k1", ctypes.c_void_p), ("a3", ctypes.c_void_p),
+                ("a5", ctypes.c_void_p), ("gate_w", ctypes.c_void_p), ("gate_b", ctypes.c_void_p),
+                ("ci", ctypes.c_int32), ("co", ctypes.c_int32), ("num_tasks", ctypes.c_int32)]
+
+
+class ModeCaps(ctypes.Structure):
+    _fields_ = [("sm_major", ctypes.c_int32), ("sm_minor", ctypes.c_int32), ("sm_count", ctypes.c_int32),
+                ("smem_per_block_optin", ctypes.c_int32), ("tmem_columns", ctypes.c_int32),
+                ("abi_version", ctypes.c_int32)]
+
+
+def _needs_build():
+    if not os.path.exists(SO_PATH):
+        return True
+    t = os.path.getmtime(SO_PATH)
+    deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC)] + [os.path.join(HERE, "..", "include", "repmode_b200.h")]
+    return any(os.path.getmtime(d) > t for d in deps if os.path.exists(d))
+
+
+def build(force=False, verbose=False):
+    """Compile every CUDA translation unit for sm_100a into repmode_b200/librepmode_b200.so (in-tree)."""
+    if not force and not _needs_build():
+        return SO_PATH
+    nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", SO_PATH] + SOURCES
+    res = subprocess.run(cmd, cwd=CSRC, capture_output=True, text=True)
+    if res.returncode != 0:
+        raise RuntimeError("nvcc failed:\n" + res.stdout + res.stderr)
+    if verbose:
+        print(res.stderr)
+    return SO_PATH
+
+
+_vp, _i32, _i64, _f32 = ctypes.c_void_p, ctypes.c_int32, ctypes.c_int64, ctypes.c_float
+SIGNATURES = {
+    "mode_last_error": (ctypes.c_char_p, []),
+    "mode_version": (ctypes.c_int, []),
+    "mode_query": (ctypes.c_int, [ctypes.c_int, ctypes.POINTER(ModeCaps)]),
+    "mode_reparam_fwd": (ctypes.c_int, [ctypes.POINTER(ModeLayer), _vp, _vp, _i32, _vp, _vp, _vp, ctypes.c_int, _f32,
+                                        _vp, _vp]),
+    "mode_packed_weight_elems": (_i64, [_i32, _i32]),
+    "mode_reparam_bwd_workspace_bytes": (_i64, [_i32, _i32, _i32]),
+    "mode_reparam_bwd": (ctypes.c_int, [ctypes.POINTER(ModeLayer), _vp, _vp, _i32, _vp, _i32, _vp, _vp, _vp, _vp, _vp,
+                                        _vp, _vp, _vp, _vp, _vp, _vp]),
+    "mode_conv3d": (ctypes.c_int, [_vp, ctypes.c_int, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _f32, _vp, _vp,
+                                   _i32, _vp]),
+    "mode_conv3d_wgrad_workspace_bytes": (_i64, [_i32, _i32, _i32, _i32, _i32, _i32, _i32]),
+    "mode_conv3d_wgrad": (ctypes.c_int, [_vp, _vp, ctypes.c_int, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _f32, _vp,
+                                         _vp, _i32, _vp]),
+    "mode_bn_stats": (ctypes.c_int, [_vp, _i64, _i32, _vp, _vp]),
+    "mode_bn_finalize": (ctypes.c_int, [_vp, _i64, _i32, _vp, _vp, _f32, _f32, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "mode_bn_apply_relu": (ctypes.c_int, [_vp, _i64, _i32, _vp, _vp, _i32, _vp, _vp, _f32, _vp]),
+    "mode_bn_bwd_workspace_bytes": (_i64, [_i32]),
+    "mode_bn_relu_bwd": (ctypes.c_int, [_vp, _vp, _i64, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "mode_cast_f16": (ctypes.c_int, [_vp, _vp, _i64, _f32, _vp, _vp]),
+    "mode_amax": (ctypes.c_int, [_vp, _i64, _vp, _vp]),
+    "mode_f16_scale": (ctypes.c_int, [_vp, _f32, _vp, _vp]),
+}
+
+
+def load():
+    """Load (building first if the sources are newer) and return the ctypes library handle."""
+    global _lib
+    with _lock:
+        if _lib is not None:
+            return _lib
+        if _needs_build():
+            if os.path.exists(os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")):
+                build()
+            elif not os.path.exists(SO_PATH):
+                raise RuntimeError(f"{SO_PATH} is missing and nvcc is not available: run __graft_entry__.build()")
+        lib = ctypes.CDLL(SO_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(lib, name)          # AttributeError here == the .so does not export the ABI
+            fn.restype = res
+            fn.argtypes = args
+        if lib.mode_version() != 1:
+            raise RuntimeError("librepmode_b200.so ABI version mismatch")
+        _lib = lib
+        return lib
+
+
+def check(rc, what):
+    if rc != 0:
+        raise RuntimeError(f"{what} failed: {load().mode_last_error().decode()}")

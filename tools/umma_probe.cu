@@ -111,6 +111,92 @@ extern "C" int probe_mma(const void* img_dev, uint32_t img_bytes, uint64_t adesc
     return 0;
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// probe_mma_rate: issue-rate probe. Unrolled groups of 8 MMAs round-robin over NACC accumulators
+// (column stride acc_cols), operand descriptor offsets from small tables (16-byte units).
+struct RateOffs { uint32_t a[8]; uint32_t b[8]; };
+
+template <int NACC>
+__global__ void __launch_bounds__(128, 1)
+probe_rate_kernel(const uint8_t* __restrict__ img, uint32_t img_bytes, uint64_t adesc, uint64_t bdesc,
+                  uint32_t idesc, uint32_t kind, RateOffs offs, uint32_t acc_cols, uint32_t repeat,
+                  long long* __restrict__ cycles, int* __restrict__ status) {
+    extern __shared__ uint8_t smem_raw[];
+    __shared__ uint64_t mbar;
+    __shared__ uint32_t tmem_base_slot;
+    const uint32_t raw = smem_u32(smem_raw);
+    const uint32_t base = (raw + 1023u) & ~1023u;
+    uint8_t* smem = smem_raw + (base - raw);
+    for (uint32_t i = threadIdx.x * 16; i < img_bytes; i += blockDim.x * 16)
+        *reinterpret_cast<uint4*>(smem + i) = *reinterpret_cast<const uint4*>(img + i);
+    fence_proxy_async();
+    const uint32_t warp = threadIdx.x >> 5;
+    if (warp == 0) tmem_alloc<512>(smem_u32(&tmem_base_slot));
+    if (threadIdx.x == 32) { mbar_init(smem_u32(&mbar), 1); fence_mbar_init(); }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = tmem_base_slot;
+    if (threadIdx.x == 0) {
+        const uint64_t a0 = adesc + (base >> 4), b0 = bdesc + (base >> 4);
+        uint64_t ad[8], bd[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { ad[j] = a0 + offs.a[j]; bd[j] = b0 + offs.b[j]; }
+        // first group initialises the accumulators
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const uint32_t d = tmem + (j % NACC) * acc_cols;
+            if (kind == 0) mma_f16_ss(d, ad[j], bd[j], idesc, j >= NACC ? 1u : 0u);
+            else mma_tf32_ss(d, ad[j], bd[j], idesc, j >= NACC ? 1u : 0u);
+        }
+        const long long t0 = clock64();
+        for (uint32_t r = 0; r < repeat; ++r) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const uint32_t d = tmem + (j % NACC) * acc_cols;
+                if (kind == 0) mma_f16_ss(d, ad[j], bd[j], idesc, 1u);
+                else mma_tf32_ss(d, ad[j], bd[j], idesc, 1u);
+            }
+        }
+        const long long t_issue = clock64();
+        mma_commit(smem_u32(&mbar));
+        cycles[1] = t_issue - t0;
+        cycles[2] = t0;
+    }
+    bool ok = mbar_wait(smem_u32(&mbar), 0, 1u << 26);
+    if (threadIdx.x == 0) {
+        cycles[0] = clock64() - cycles[2];
+        if (!ok) status[0] = 1;
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc<512>(tmem);
+}
+
+extern "C" int probe_mma_rate(const void* img_dev, uint32_t img_bytes, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                              uint32_t kind, const uint32_t* a_offs16, const uint32_t* b_offs16, int nacc,
+                              uint32_t acc_cols, uint32_t repeat, long long* cycles_dev, int* status_dev) {
+    const int smem = 200 * 1024;
+    RateOffs offs;
+    for (int j = 0; j < 8; ++j) { offs.a[j] = a_offs16[j]; offs.b[j] = b_offs16[j]; }
+    CK(cudaMemset(status_dev, 0, sizeof(int)));
+#define LAUNCH_RATE(NA)                                                                                         \
+    do {                                                                                                        \
+        CK(cudaFuncSetAttribute(probe_rate_kernel<NA>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));      \
+        probe_rate_kernel<NA><<<1, 128, smem>>>((const uint8_t*)img_dev, img_bytes, adesc, bdesc, idesc, kind,   \
+                                                offs, acc_cols, repeat, cycles_dev, status_dev);                 \
+    } while (0)
+    if (nacc == 1) LAUNCH_RATE(1);
+    else if (nacc == 2) LAUNCH_RATE(2);
+    else if (nacc == 4) LAUNCH_RATE(4);
+    else if (nacc == 8) LAUNCH_RATE(8);
+    else { snprintf(g_err, sizeof(g_err), "nacc must be 1,2,4,8"); return -1; }
+    CK(cudaGetLastError());
+    CK(cudaDeviceSynchronize());
+    return 0;
+}
+
 // ------------------------------------------------------------------------------------------------
 // probe_tma: one tiled TMA load of a (<=5-d) box into shared memory, then dump the bytes.
 __global__ void __launch_bounds__(128, 1)

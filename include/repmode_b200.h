@@ -52,8 +52,13 @@ typedef struct {
 
 const char* mode_last_error(void);
 int mode_version(void);
+/* Number of kernels this library has launched in this process (bench.py's gpu_launches evidence). */
+int64_t mode_launch_count(void);
 /* Fails unless `device` is compute capability 10.x (this library ships sm_100a SASS only). */
 int mode_query(int device, mode_caps_t* caps_host);
+/* Synchronises the device and returns (and clears) the pipeline-timeout code a tcgen05 kernel raises
+ * instead of hanging (0 = none). Diagnostics only; never called on the hot path. */
+int mode_poll_error(int32_t* code_host);
 
 /* ---- K1: gate softmax + expert re-parameterisation --------------------------------------------------
  * Replaces: Linear + view + Softmax(dim=1) (RepMode.py:198-200) and MoDEConv.routing / trans_kernel
@@ -62,10 +67,14 @@ int mode_query(int device, mode_caps_t* caps_host);
  *   gate input: either task_ids[U] (one-hot embedding == column gather, RepMode.py:44-49) or a dense
  *               t[U,T] row (the MoDEConv.forward(x, t) signature accepts any t); exactly one non-NULL.
  *   g_out [U,5,Co] fp32: the softmax gates (saved for backward).
- *   w_fwd: packed conv weights, "B-operand" layout  w[u][tap][ci_chunk][co][MODE_KC]  (ci within a chunk
- *          contiguous, zero padded), dtype w_dtype.  tap = (kd*5+kh)*5+kw.
- *   w_dgrad (may be NULL): the dgrad weights  w'[u][124-tap][co_chunk][ci][MODE_KC]  (flipped taps, io
- *          transposed), same dtype.
+ *   w_fwd: packed conv weights, rows = co, k = ci (k within a 32-chunk contiguous, zero padded), tap =
+ *          (kd*5+kh)*5+kw:
+ *            fp32 pack ("tap-major", SIMT kernels):      w[u][tap][ci_chunk][co][MODE_KC]
+ *            fp16 pack ("stage-major", tcgen05 kernel):  w[u][ci_chunk][kh*5+kw][4-kd][co][MODE_KC], each
+ *            [rows][MODE_KC] block stored as the 64-byte-swizzled shared-memory image the UMMA B operand reads
+ *            (16-byte chunk index ^= (row >> 1) & 3).
+ *   w_dgrad (may be NULL): the same packs built from the flipped, io-transposed kernel (tap -> 124-tap,
+ *          rows = ci, k = co), same dtype.
  *   w_scale * (w_scale_dev ? *w_scale_dev : 1) multiplies every packed weight before rounding (a power of
  *   two keeps the fp16 operand an exactly-scaled copy); w_scale_dev is a device scalar so the scale can
  *   be produced on-stream (mode_f16_scale) without a host sync.

@@ -25,7 +25,12 @@ constexpr int kErrLen = 512;
         if (e_ != cudaSuccess) MODE_FAIL("%s:%d %s -> %s", __FILE__, __LINE__, #x, cudaGetErrorString(e_)); \
     } while (0)
 
-#define MODE_LAUNCH_CHECK() MODE_CUDA(cudaGetLastError())
+void count_launch();                   // bumps the process-wide kernel-launch counter (mode_launch_count)
+#define MODE_LAUNCH_CHECK()           \
+    do {                              \
+        mode::count_launch();         \
+        MODE_CUDA(cudaGetLastError()); \
+    } while (0)
 
 __host__ __device__ constexpr int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
 

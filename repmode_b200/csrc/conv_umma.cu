@@ -1,12 +1,380 @@
-// tcgen05 implicit-GEMM conv kernels (placeholder until the hardware probe settles the descriptor layout).
+// K2 / K3: 5x5x5 'same' convolution as an im2col-free implicit GEMM on tcgen05 tensor cores (sm_100a).
+//
+// Replaces F.conv3d(x[i:i+1], w[i], padding='same') per sample (fnet/nn_modules/RepMode.py:204-210 in the
+// reference tree) and -- called with K1's flipped/transposed weight pack and dy as input -- its dgrad.
+//
+// Mapping (one persistent CTA per SM, 256 threads, warp-specialised):
+//   GEMM M = 128 output voxels = an 8(w) x 16(h) patch of one d-plane.  A CTA tile is TD consecutive
+//   d-planes of that patch; its TD accumulators [128 x Nt] fp32 sit side by side in TMEM (TD*Nt <= 256
+//   columns, double buffered in the 512-column TMEM so the epilogue of tile i overlaps tile i+1).
+//   A operand: the haloed activation plane (20 x 12 voxels x 32 ch fp16 = 15 KB) is brought in ONCE per
+//   (tile, 32-channel chunk) by a single 5-d TMA box load (out-of-range coordinates zero-fill = the conv's
+//   zero padding) and stays resident for all 25 (kh,kw) taps: a tap is just a different descriptor start
+//   address (rows of 64 B, SWIZZLE_64B, SBO = 12*64 B) -- no im2col copy.
+//   B operand: for one (chunk, kh, kw) K1 stores the five kd taps as consecutive [Nout x 32] blocks in
+//   DESCENDING kd order, already in the 64B-swizzled shared-memory image.  Input plane p feeds output planes
+//   q = p-4 .. p with taps kd = p-q, i.e. a CONTIGUOUS run of B rows and a contiguous run of accumulator
+//   columns: ONE tcgen05.mma with N = Nt * (#valid q) <= 256 updates up to five output planes at once.
+//   (Measured on B200: an SS-mode MMA costs max(93, 42 + N/2) cycles -- the 4 KB A read is exposed -- so the
+//   wide N is what amortises it; every column is useful work.)
+// Roles: warp 0 = activation-plane TMA producer, warp 3 = weight producer (bulk copies), warp 1 = MMA issuer
+//   (one thread), warp 2 = TMEM allocator, warps 4-7 = epilogue (tcgen05.ld -> scale -> global store, fused
+//   BatchNorm partial sums, then re-zero the accumulators with tcgen05.st so every MMA can accumulate).
+// Roofline: tensor-pipe bound; algorithmic work 2*125*K*Nout FLOP per output voxel.
+#include <cuda.h>
+
 #include "common.cuh"
+#include "ptx_sm100.cuh"
+
 namespace mode {
-bool conv3d_umma_supported(int, int, int, int, int) { return false; }
-int conv3d_umma(const __half*, const __half*, const int32_t*, float*, int, int, int, int, int, int, float, const float*, double*,
-                cudaStream_t) { MODE_FAIL("conv3d_umma: not built"); }
+
+using namespace sm100;
+
+namespace cu {
+constexpr int TW = 8, TH = 16;                 // output patch
+constexpr int BW = TW + 4, BH = TH + 4;        // haloed brick
+constexpr int ROWB = 64;                       // bytes per voxel row (32 fp16 channels)
+constexpr int PLANE_BYTES = BH * BW * ROWB;    // 15360
+constexpr int MAX_RING = 12;
+constexpr int MAX_WST = 4;
+constexpr int THREADS = 256;
+}  // namespace cu
+
+struct ConvParams {
+    const __half* w;             // stage-major fp16 pack (see header), all Nout rows
+    const int32_t* sample_u;
+    float* y;                    // [N,D,H,W,Nout]
+    double* bn_sums;             // [2*Nout] or null
+    const float* out_scale_dev;
+    float out_scale;
+    int N, D, H, W, K, Nout;     // Nout = total output channels (row stride of y / rows per weight block)
+    int n0, Nt;                  // this launch computes channels [n0, n0+Nt)
+    int TD, ring, wstages;
+    int tiles_w, tiles_h, dgroups, total_tiles;
+    int* error_flag;
+};
+
+struct SmemLayout {
+    uint32_t plane_off, w_off, bar_off, bn_off, total;
+};
+
+__host__ __device__ inline SmemLayout smem_layout(int ring, int wstages, int Nt) {
+    SmemLayout L;
+    L.plane_off = 0;
+    L.w_off = ring * cu::PLANE_BYTES;                         // multiples of 15 KB keep 512-byte alignment
+    const uint32_t wst_bytes = 5u * Nt * cu::ROWB;
+    L.bar_off = L.w_off + wstages * wst_bytes;
+    L.bn_off = L.bar_off + 512;
+    L.total = L.bn_off + 2 * 256 * sizeof(double);
+    return L;
+}
+
+// valid (in-volume) input planes of a tile: p in [pmin, pmax], input d = d0 + p - 2
+__device__ __forceinline__ void plane_range(int d0, int TD, int D, int& pmin, int& pmax) {
+    pmin = max(0, 2 - d0);
+    pmax = min(TD + 3, D + 1 - d0);
+}
+
+__global__ void __launch_bounds__(cu::THREADS, 1)
+conv3d_umma_kernel(const __grid_constant__ CUtensorMap xmap, const ConvParams P) {
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t raw = smem_u32(smem_raw);
+    const uint32_t base = (raw + 1023u) & ~1023u;
+    uint8_t* smem = smem_raw + (base - raw);
+    const SmemLayout L = smem_layout(P.ring, P.wstages, P.Nt);
+    const uint32_t bars = base + L.bar_off;
+    // barrier table (8 bytes each)
+    const uint32_t plane_full = bars, plane_empty = bars + 8 * cu::MAX_RING;
+    const uint32_t w_full = bars + 16 * cu::MAX_RING, w_empty = w_full + 8 * cu::MAX_WST;
+    const uint32_t tmem_full = w_empty + 8 * cu::MAX_WST, tmem_empty = tmem_full + 16;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + L.bar_off + 400);
+    double* s_bn = reinterpret_cast<double*>(smem + L.bn_off);   // per-CTA BatchNorm partial sums [2][Nt]
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int nchunk = P.K / 32;
+    const uint32_t blk_bytes = (uint32_t)P.Nt * cu::ROWB;          // one kd block of a weight stage
+    const uint32_t wst_bytes = 5u * blk_bytes;
+
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < P.ring; ++i) { mbar_init(plane_full + 8 * i, 1); mbar_init(plane_empty + 8 * i, 1); }
+        for (int i = 0; i < P.wstages; ++i) { mbar_init(w_full + 8 * i, 1); mbar_init(w_empty + 8 * i, 1); }
+        for (int i = 0; i < 2; ++i) { mbar_init(tmem_full + 8 * i, 1); mbar_init(tmem_empty + 8 * i, 4); }
+        fence_mbar_init();
+    }
+    if (warp == 2) tmem_alloc<512>(smem_u32(tmem_slot));
+    if (warp == 0 && lane == 0) tma_prefetch_desc(&xmap);
+    for (int i = threadIdx.x; i < 2 * P.Nt; i += cu::THREADS) s_bn[i] = 0.0;
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *tmem_slot;
+
+    const int tiles_per_n = P.dgroups * P.tiles_h * P.tiles_w;
+
+    if (warp == 0) {
+        // ===================== activation-plane producer =====================
+        if (lane == 0) {
+            uint32_t seq = 0;
+            for (int tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x) {
+                const int n = tile / tiles_per_n;
+                int r = tile % tiles_per_n;
+                const int dg = r / (P.tiles_h * P.tiles_w);
+                r %= P.tiles_h * P.tiles_w;
+                const int h0 = (r / P.tiles_w) * cu::TH, w0 = (r % P.tiles_w) * cu::TW;
+                const int d0 = dg * P.TD;
+                int pmin, pmax;
+                plane_range(d0, P.TD, P.D, pmin, pmax);
+                for (int c = 0; c < nchunk; ++c) {
+                    for (int p = pmin; p <= pmax; ++p, ++seq) {
+                        const uint32_t slot = seq % P.ring, use = seq / P.ring;
+                        if (!mbar_wait(plane_empty + 8 * slot, (use & 1) ^ 1)) { atomicExch(P.error_flag, 1); return; }
+                        mbar_expect_tx(plane_full + 8 * slot, cu::PLANE_BYTES);
+                        tma_load_5d(base + L.plane_off + slot * cu::PLANE_BYTES, &xmap, plane_full + 8 * slot, c * 32,
+                                    w0 - 2, h0 - 2, d0 + p - 2, n);
+                    }
+                }
+            }
+        }
+    } else if (warp == 3) {
+        // ===================== weight producer =====================
+        if (lane == 0) {
+            uint32_t seq = 0;
+            for (int tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x) {
+                const int n = tile / tiles_per_n;
+                const int u = P.sample_u ? P.sample_u[n] : 0;
+                const __half* wu = P.w + (size_t)u * nchunk * 125 * P.Nout * 32;
+                for (int c = 0; c < nchunk; ++c) {
+                    for (int t = 0; t < 25; ++t, ++seq) {
+                        const uint32_t st = seq % P.wstages, use = seq / P.wstages;
+                        if (!mbar_wait(w_empty + 8 * st, (use & 1) ^ 1)) { atomicExch(P.error_flag, 2); return; }
+                        mbar_expect_tx(w_full + 8 * st, wst_bytes);
+                        const uint32_t dst = base + L.w_off + st * wst_bytes;
+                        const __half* src = wu + ((size_t)(c * 25 + t) * 5 * P.Nout + P.n0) * 32;
+#pragma unroll
+                        for (int b = 0; b < 5; ++b)
+                            bulk_load(dst + b * blk_bytes, src + (size_t)b * P.Nout * 32, blk_bytes, w_full + 8 * st);
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer =====================
+        if (lane == 0) {
+            uint32_t pseq_base = 0, wseq = 0;
+            int it = 0;
+            for (int tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x, ++it) {
+                const int dg = (tile % tiles_per_n) / (P.tiles_h * P.tiles_w);
+                const int d0 = dg * P.TD;
+                int pmin, pmax;
+                plane_range(d0, P.TD, P.D, pmin, pmax);
+                const int nplanes = pmax - pmin + 1;
+                const int buf = it & 1;
+                const uint32_t acc_base = tmem + buf * 256;
+                // accumulators of this buffer have been drained and re-zeroed by the epilogue
+                if (!mbar_wait(tmem_empty + 8 * buf, (it >> 1) & 1)) { atomicExch(P.error_flag, 3); return; }
+                tc_fence_after();
+                for (int c = 0; c < nchunk; ++c, pseq_base += nplanes) {
+                    for (int t = 0; t < 25; ++t, ++wseq) {
+                        const int kh = t / 5, kw = t - kh * 5;
+                        const uint32_t st = wseq % P.wstages;
+                        if (!mbar_wait(w_full + 8 * st, (wseq / P.wstages) & 1)) { atomicExch(P.error_flag, 5); return; }
+                        tc_fence_after();
+                        const uint32_t wbase = base + L.w_off + st * wst_bytes;
+                        const uint32_t a_tap = (kh * cu::BW + kw) * cu::ROWB;
+                        for (int p = pmin; p <= pmax; ++p) {
+                            const uint32_t s = pseq_base + (p - pmin);
+                            const uint32_t slot = s % P.ring;
+                            if (t == 0) {      // first touch of this plane in this chunk
+                                if (!mbar_wait(plane_full + 8 * slot, (s / P.ring) & 1)) { atomicExch(P.error_flag, 4); return; }
+                                tc_fence_after();
+                            }
+                            const int qlo = max(0, p - 4), qhi = min(P.TD - 1, p);
+                            const int kd_hi = p - qlo;                       // tap of the first (lowest-q) block
+                            const uint32_t ncols = (uint32_t)(qhi - qlo + 1) * P.Nt;
+                            const uint32_t idesc = make_idesc(FMT_F16, 128, ncols, 0, 0);
+                            const uint32_t pa = base + L.plane_off + slot * cu::PLANE_BYTES + a_tap;
+                            const uint32_t pb = wbase + (4 - kd_hi) * blk_bytes;
+#pragma unroll
+                            for (int ks = 0; ks < 2; ++ks) {
+                                const uint64_t adesc = make_smem_desc(pa + ks * 32, 16, cu::BW * cu::ROWB, SWZ_64B);
+                                const uint64_t bdesc = make_smem_desc(pb + ks * 32, 16, 512, SWZ_64B);
+                                mma_f16_ss(acc_base + qlo * P.Nt, adesc, bdesc, idesc, 1u);
+                            }
+                            if (t == 24) mma_commit(plane_empty + 8 * slot);   // last use of the plane in this chunk
+                        }
+                        mma_commit(w_empty + 8 * st);
+                    }
+                }
+                mma_commit(tmem_full + 8 * buf);
+            }
+        }
+    } else if (warp >= 4) {
+        // ===================== epilogue =====================
+        const int ew = warp - 4;
+        const int row = ew * 32 + lane;
+        const int th = row >> 3, tw = row & 7;
+        const uint32_t lane_addr = (uint32_t)(ew * 32) << 16;
+        float scale = P.out_scale;
+        if (P.out_scale_dev) scale *= *P.out_scale_dev;
+        uint32_t zeros[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) zeros[j] = 0u;
+        // zero both accumulator buffers once; afterwards each buffer is re-zeroed right after it is drained
+        for (int c = 0; c < 512; c += 32) tmem_st_32x32(tmem + c + lane_addr, zeros);
+        tmem_st_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) { mbar_arrive(tmem_empty); mbar_arrive(tmem_empty + 8); }
+
+        int it = 0;
+        for (int tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x, ++it) {
+            const int n = tile / tiles_per_n;
+            int r = tile % tiles_per_n;
+            const int dg = r / (P.tiles_h * P.tiles_w);
+            r %= P.tiles_h * P.tiles_w;
+            const int h0 = (r / P.tiles_w) * cu::TH, w0 = (r % P.tiles_w) * cu::TW;
+            const int d0 = dg * P.TD;
+            const int buf = it & 1;
+            if (!mbar_wait(tmem_full + 8 * buf, (it >> 1) & 1)) { atomicExch(P.error_flag, 6); break; }
+            tc_fence_after();
+            const int qn = min(P.TD, P.D - d0);
+            for (int q = 0; q < P.TD; ++q) {
+                float* dst = P.y + ((((size_t)n * P.D + d0 + q) * P.H + h0 + th) * P.W + w0 + tw) * P.Nout + P.n0;
+                for (int cc = 0; cc < P.Nt; cc += 32) {
+                    const uint32_t taddr = tmem + buf * 256 + q * P.Nt + cc + lane_addr;
+                    if (q < qn) {
+                        uint32_t v[32];
+                        tmem_ld_32x32(taddr, v);
+                        tmem_ld_wait();
+                        float f[32];
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]) * scale;
+#pragma unroll
+                        for (int j = 0; j < 32; j += 4)
+                            *reinterpret_cast<float4*>(dst + cc + j) = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
+                        if (P.bn_sums != nullptr) {
+                            float g[32];
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) g[j] = f[j] * f[j];
+                            // transposed butterfly: afterwards lane l holds the 32-voxel total of channel cc + l
+#pragma unroll
+                            for (int s = 16; s >= 1; s >>= 1) {
+                                const bool up = (lane & s) != 0;
+#pragma unroll
+                                for (int i = 0; i < s; ++i) {
+                                    const float send1 = up ? f[i] : f[i + s], send2 = up ? g[i] : g[i + s];
+                                    const float r1 = __shfl_xor_sync(0xffffffffu, send1, s);
+                                    const float r2 = __shfl_xor_sync(0xffffffffu, send2, s);
+                                    f[i] = (up ? f[i + s] : f[i]) + r1;
+                                    g[i] = (up ? g[i + s] : g[i]) + r2;
+                                }
+                            }
+                            atomicAdd(s_bn + cc + lane, (double)f[0]);
+                            atomicAdd(s_bn + P.Nt + cc + lane, (double)g[0]);
+                        }
+                    }
+                    tmem_st_32x32(taddr, zeros);
+                }
+            }
+            tmem_st_wait();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(tmem_empty + 8 * buf);
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (P.bn_sums != nullptr)
+        for (int i = threadIdx.x; i < 2 * P.Nt; i += cu::THREADS) {
+            const int which = i / P.Nt, ch = i % P.Nt;
+            atomicAdd(P.bn_sums + which * P.Nout + P.n0 + ch, s_bn[i]);
+        }
+    if (warp == 2) tmem_dealloc<512>(tmem);
+}
+
+// ------------------------------------------------------------------------------------------------ host
+int* device_error_flag();   // mode_abi.cu
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = (EncodeTiledFn)p;
+    }
+    return fn;
+}
+
+int make_act_map(CUtensorMap* map, const __half* x, int N, int D, int H, int W, int K, int box_w, int box_h) {
+    EncodeTiledFn fn = encode_fn();
+    if (!fn) MODE_FAIL("cuTensorMapEncodeTiled entry point unavailable");
+    cuuint64_t dims[5] = {(cuuint64_t)K, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)D, (cuuint64_t)N};
+    cuuint64_t str[4] = {(cuuint64_t)K * 2, (cuuint64_t)W * K * 2, (cuuint64_t)H * W * K * 2,
+                         (cuuint64_t)D * H * W * K * 2};
+    cuuint32_t box[5] = {32, (cuuint32_t)box_w, (cuuint32_t)box_h, 1, 1};
+    cuuint32_t es[5] = {1, 1, 1, 1, 1};
+    CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 5, (void*)x, dims, str, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                    CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) MODE_FAIL("cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
+    return 0;
+}
+
+bool conv3d_umma_supported(int D, int H, int W, int K, int Nout) {
+    (void)D;
+    return K % 32 == 0 && K >= 32 && Nout % 32 == 0 && Nout >= 32 && H % cu::TH == 0 && W % cu::TW == 0 &&
+           (Nout <= 128 || Nout % 128 == 0);
+}
+
+int conv3d_umma(const __half* x, const __half* w, const int32_t* sample_u, float* y, int N, int D, int H, int W, int K,
+                int Nout, float out_scale, const float* out_scale_dev, double* bn_sums, cudaStream_t st) {
+    if ((reinterpret_cast<uintptr_t>(x) & 15) || (reinterpret_cast<uintptr_t>(w) & 15) ||
+        (reinterpret_cast<uintptr_t>(y) & 15))
+        MODE_FAIL("conv3d_umma: pointers must be 16-byte aligned");
+    ConvParams P;
+    P.w = w; P.sample_u = sample_u; P.y = y; P.bn_sums = bn_sums; P.out_scale_dev = out_scale_dev;
+    P.out_scale = out_scale;
+    P.N = N; P.D = D; P.H = H; P.W = W; P.K = K; P.Nout = Nout;
+    P.Nt = Nout <= 128 ? Nout : 128;                 // wider layers run in passes of 128 output channels
+    P.TD = max(1, min(min(256 / P.Nt, 8), D));
+    P.ring = P.TD + 4;
+    const int wst_bytes = 5 * P.Nt * cu::ROWB;
+    const int budget = 227 * 1024 - 1024 - P.ring * cu::PLANE_BYTES - 512 - 4096;
+    P.wstages = min(cu::MAX_WST, budget / wst_bytes);
+    if (P.wstages < 2) MODE_FAIL("conv3d_umma: shared memory budget too small for Nt=%d", P.Nt);
+    const SmemLayout L = smem_layout(P.ring, P.wstages, P.Nt);
+    const int smem_bytes = (int)L.total + 1024;
+    if (smem_bytes > 227 * 1024) MODE_FAIL("conv3d_umma: shared memory budget exceeded (%d B)", smem_bytes);
+    P.tiles_w = W / cu::TW; P.tiles_h = H / cu::TH; P.dgroups = (int)ceil_div(D, P.TD);
+    const int64_t total = (int64_t)N * P.dgroups * P.tiles_h * P.tiles_w;
+    if (total > 0x7fffffff) MODE_FAIL("conv3d_umma: too many tiles");
+    P.total_tiles = (int)total;
+    P.error_flag = device_error_flag();
+    if (!P.error_flag) MODE_FAIL("conv3d_umma: could not allocate the device error flag");
+
+    CUtensorMap xmap;
+    if (make_act_map(&xmap, x, N, D, H, W, K, cu::BW, cu::BH) != 0) return -1;
+    MODE_CUDA(cudaFuncSetAttribute(conv3d_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
+    const int grid = total < (int64_t)sm_count() ? (int)total : sm_count();
+    for (int n0 = 0; n0 < Nout; n0 += P.Nt) {
+        P.n0 = n0;
+        conv3d_umma_kernel<<<grid, cu::THREADS, smem_bytes, st>>>(xmap, P);
+        MODE_LAUNCH_CHECK();
+    }
+    return 0;
+}
+
+// wgrad on tcgen05: not built yet -> explicit error (the host side keeps wgrad on the SIMT kernel meanwhile)
 bool wgrad_umma_supported(int, int, int, int, int) { return false; }
 int64_t wgrad_umma_workspace_bytes(int, int, int, int, int, int) { return 0; }
-int wgrad_umma(const __half*, const __half*, float*, int, int, int, int, int, int, float, const float*, void*, cudaStream_t) {
+int wgrad_umma(const __half*, const __half*, float*, int, int, int, int, int, int, float, const float*, void*,
+               cudaStream_t) {
     MODE_FAIL("wgrad_umma: not built");
 }
+
 }  // namespace mode

@@ -1,8 +1,13 @@
 // C-ABI glue: error reporting, capability query and the implementation dispatch for the conv entry points.
 // See include/repmode_b200.h for the contract and the reference lines each entry point replaces.
+#include <atomic>
+
 #include "common.cuh"
 
 namespace mode {
+
+static std::atomic<long long> g_launches{0};
+void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 
 char* err_buf() {
     static thread_local char buf[kErrLen] = "";
@@ -19,6 +24,20 @@ int sm_count() {
         cached[dev] = n;
     }
     return cached[dev];
+}
+
+// One int per device, set by a kernel whose pipeline timed out (never hangs the box); read by mode_poll_error.
+int* device_error_flag() {
+    static int* flags[64] = {nullptr};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+    if (!flags[dev]) {
+        int* p = nullptr;
+        if (cudaMalloc(&p, sizeof(int)) != cudaSuccess) return nullptr;
+        cudaMemset(p, 0, sizeof(int));
+        flags[dev] = p;
+    }
+    return flags[dev];
 }
 
 // conv_simt.cu
@@ -41,6 +60,7 @@ using namespace mode;
 
 extern "C" const char* mode_last_error(void) { return err_buf(); }
 extern "C" int mode_version(void) { return MODE_ABI_VERSION; }
+extern "C" int64_t mode_launch_count(void) { return (int64_t)g_launches.load(std::memory_order_relaxed); }
 
 extern "C" int mode_query(int device, mode_caps_t* caps) {
     if (!caps) MODE_FAIL("mode_query: caps is NULL");
@@ -53,6 +73,18 @@ extern "C" int mode_query(int device, mode_caps_t* caps) {
     caps->tmem_columns = 512;
     caps->abi_version = MODE_ABI_VERSION;
     if (p.major != 10) MODE_FAIL("mode_query: device %d is sm_%d%d; this library contains sm_100a code only", device, p.major, p.minor);
+    return 0;
+}
+
+extern "C" int mode_poll_error(int32_t* code_host) {
+    if (!code_host) MODE_FAIL("mode_poll_error: null");
+    int* f = device_error_flag();
+    if (!f) MODE_FAIL("mode_poll_error: no flag");
+    MODE_CUDA(cudaDeviceSynchronize());
+    int v = 0;
+    MODE_CUDA(cudaMemcpy(&v, f, sizeof(int), cudaMemcpyDeviceToHost));
+    *code_host = v;
+    if (v != 0) MODE_CUDA(cudaMemset(f, 0, sizeof(int)));
     return 0;
 }
 

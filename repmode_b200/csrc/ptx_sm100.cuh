@@ -53,13 +53,26 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
         : "memory");
     return ok != 0;
 }
-// Bounded spin: returns false if the barrier never flipped (kernel then bails out and reports an error
-// instead of hanging the GPU box).
-__device__ __forceinline__ bool mbar_wait(uint32_t bar, uint32_t parity, uint32_t max_spins = 1u << 26) {
-    for (uint32_t i = 0; i < max_spins; ++i) {
-        if (mbar_try_wait(bar, parity)) return true;
+__device__ __forceinline__ uint64_t globaltimer_ns() {
+    uint64_t t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+// Time-bounded wait: returns false if the barrier has not flipped within ~2 s of wall clock (the kernel
+// then bails out and raises an error flag instead of hanging the GPU box). max_spins bounds the number of
+// polls between clock checks only.
+__device__ __noinline__ bool mbar_wait_slow(uint32_t bar, uint32_t parity) {
+    const uint64_t t0 = globaltimer_ns();
+    while (true) {
+#pragma unroll 1
+        for (int i = 0; i < 256; ++i)
+            if (mbar_try_wait(bar, parity)) return true;
+        if (globaltimer_ns() - t0 > 2000000000ull) return false;
     }
-    return false;
+}
+__device__ __forceinline__ bool mbar_wait(uint32_t bar, uint32_t parity, uint32_t /*unused*/ = 0) {
+    if (mbar_try_wait(bar, parity)) return true;
+    return mbar_wait_slow(bar, parity);
 }
 
 // ---------------------------------------------------------------- TMA
@@ -167,6 +180,20 @@ __device__ __forceinline__ void tmem_ld_32x16(uint32_t taddr, uint32_t (&v)[16])
         : "r"(taddr)
         : "memory");
 }
+// store 32 registers per thread into 32 lanes x 32 consecutive columns
+__device__ __forceinline__ void tmem_st_32x32(uint32_t taddr, const uint32_t (&v)[32]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+        "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+        "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"
+        :
+        : "r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]),
+          "r"(v[8]), "r"(v[9]), "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15]), "r"(v[16]),
+          "r"(v[17]), "r"(v[18]), "r"(v[19]), "r"(v[20]), "r"(v[21]), "r"(v[22]), "r"(v[23]), "r"(v[24]), "r"(v[25]),
+          "r"(v[26]), "r"(v[27]), "r"(v[28]), "r"(v[29]), "r"(v[30]), "r"(v[31])
+        : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // ---------------------------------------------------------------- descriptors

@@ -17,6 +17,33 @@ namespace mode {
 __device__ __forceinline__ void store_w(float* p, float v) { *p = v; }
 __device__ __forceinline__ void store_w(__half* p, float v) { *p = __float2half_rn(v); }
 
+// Position of element `col` (0..31) of row `row` inside a packed [rows][32] block.
+//   fp32 pack: plain.   fp16 pack: the 64-byte-swizzled shared-memory image the UMMA B operand reads
+//   (16-byte chunk index XOR bits 7-8 of the byte address = (row >> 1) & 3), so that a linear bulk copy of
+//   the block into 512-byte-aligned shared memory needs no further rearrangement.
+template <typename T> __device__ __forceinline__ int pack_col(int row, int col);
+template <> __device__ __forceinline__ int pack_col<float>(int, int col) { return col; }
+template <> __device__ __forceinline__ int pack_col<__half>(int row, int col) {
+    return ((((col >> 3) ^ (row >> 1)) & 3) << 3) | (col & 7);
+}
+
+// Linear index of element (u, tap, k-chunk, row, col) in the packed weight tensor.
+//   fp32 ("tap-major", read by the SIMT kernels):  w[u][tap][chunk][row][32]
+//   fp16 ("stage-major", read by the tcgen05 kernel): w[u][chunk][kh*5+kw][4-kd][row][32] -- the five kd taps of
+//   one (chunk, kh, kw) are consecutive blocks in DESCENDING kd order, so the taps an input plane contributes to
+//   consecutive output planes form one contiguous B operand (conv_umma.cu).
+template <typename T>
+__device__ __forceinline__ size_t pack_index(int u, int tap, int chunk, int nchunk, int row, int nrows, int col);
+template <>
+__device__ __forceinline__ size_t pack_index<float>(int u, int tap, int chunk, int nchunk, int row, int nrows, int col) {
+    return ((((size_t)u * 125 + tap) * nchunk + chunk) * nrows + row) * MODE_KC + col;
+}
+template <>
+__device__ __forceinline__ size_t pack_index<__half>(int u, int tap, int chunk, int nchunk, int row, int nrows, int col) {
+    const int kd = tap / 25, t = tap - kd * 25;
+    return (((((size_t)u * nchunk + chunk) * 25 + t) * 5 + (4 - kd)) * nrows + row) * MODE_KC + pack_col<__half>(row, col);
+}
+
 // grid (Co, ceil(Ci/32), U), block 128
 template <typename OutT>
 __global__ void __launch_bounds__(128) reparam_fwd_kernel(mode_layer_t L, const int32_t* __restrict__ task_ids,
@@ -83,12 +110,11 @@ __global__ void __launch_bounds__(128) reparam_fwd_kernel(mode_layer_t L, const 
     const int warp = tid >> 5, lane = tid & 31;
     const int nci = gridDim.y;
     for (int tap = warp; tap < 125; tap += 4) {
-        const size_t dst = ((((size_t)u * 125 + tap) * nci + ic) * Co + o) * MODE_KC + lane;
-        store_w(w_fwd + dst, sw[lane * 125 + tap] * w_scale);
+        store_w(w_fwd + pack_index<OutT>(u, tap, ic, nci, o, Co, lane), sw[lane * 125 + tap] * w_scale);
     }
 }
 
-// fwd pack [u][tap][ic][o][32]  ->  dgrad pack [u][124-tap][oc][i][32]   (flip taps, swap channel roles)
+// fwd pack (rows = co, k = ci)  ->  dgrad pack (tap -> 124-tap, rows = ci, k = co)
 // grid (ceil(Ci/32), ceil(Co/32), U*125), block (32, 8)
 template <typename T>
 __global__ void __launch_bounds__(256) pack_dgrad_kernel(const T* __restrict__ src, T* __restrict__ dst, int Ci,
@@ -101,13 +127,13 @@ __global__ void __launch_bounds__(256) pack_dgrad_kernel(const T* __restrict__ s
     for (int r = ty; r < 32; r += 8) {
         const int o = oc * 32 + r;
         T v = T(0);
-        if (o < Co) v = src[((((size_t)u * 125 + tap) * nci + ic) * Co + o) * MODE_KC + tx];
+        if (o < Co) v = src[pack_index<T>(u, tap, ic, nci, o, Co, tx)];
         tile[r][tx] = v;                                     // (o = oc*32+r, i = ic*32+tx)
     }
     __syncthreads();
     for (int r = ty; r < 32; r += 8) {
         const int i = ic * 32 + r;
-        if (i < Ci) dst[((((size_t)u * 125 + (124 - tap)) * nco + oc) * Ci + i) * MODE_KC + tx] = tile[tx][r];
+        if (i < Ci) dst[pack_index<T>(u, 124 - tap, oc, nco, i, Ci, tx)] = tile[tx][r];
     }
 }
 

@@ -58,9 +58,15 @@ def _layer(k5, k3, k1, a3, a5, gate_w, gate_b):
     return L, ci, co
 
 
+UMMA_WGRAD = False      # wgrad on tcgen05 (wgrad_umma) not built yet: K4 runs the SIMT fp32 kernel meanwhile
+
+
 def umma_shape_ok(ci, co, d, h, w):
-    """Shapes the tcgen05 kernels take (conv_umma.cu); everything else runs the SIMT fp32 kernels."""
-    return ci % 32 == 0 and co % 32 == 0 and co <= 256 and ci <= 512 and h % 16 == 0 and w % 8 == 0 \
+    """Shapes the tcgen05 conv kernel takes for BOTH forward (K=ci, N=co) and dgrad (K=co, N=ci)
+    (conv3d_umma_supported in conv_umma.cu); everything else runs the SIMT fp32 kernels."""
+    def n_ok(n):
+        return n % 32 == 0 and (n <= 128 or n % 128 == 0)
+    return n_ok(ci) and n_ok(co) and h % 16 == 0 and w % 8 == 0 \
         and os.environ.get("REPMODE_DISABLE_UMMA", "0") != "1"
 
 
@@ -186,8 +192,9 @@ class ModeConvFunction(torch.autograd.Function):
         if needs_dx or needs_dw or (normal and (ctx.needs_input_grad[9] or ctx.needs_input_grad[10])):
             if normal and not training:
                 raise NotImplementedError("MoDEConv backward in eval mode (frozen BatchNorm) is not supported")
-            ctx.save_for_backward(x_op, y if normal else None, g, w_dg, gate_u, sample_u, k5, k3, k1, a3, a5, gate_w,
-                                  gate_b, bn_w, bn_b, mean, invstd, w_s2)
+            x_w = x_op if (UMMA_WGRAD or not use_umma) else xn      # operand K4 will read
+            ctx.save_for_backward(None, x_w if needs_dw else None, y if normal else None, g, w_dg,
+                                  gate_u, sample_u, k5, k3, k1, a3, a5, gate_w, gate_b, bn_w, bn_b, mean, invstd, w_s2)
             ctx.cfg = (n, d, h, wd, ci, co, U, normal, use_umma, needs_dx, needs_dw)
         return from_ndhwc(out)
 
@@ -195,7 +202,7 @@ class ModeConvFunction(torch.autograd.Function):
     @torch.amp.custom_bwd(device_type="cuda")
     def backward(ctx, dout):
         lib = _lib.load()
-        (x_op, y, g, w_dg, gate_u, sample_u, k5, k3, k1, a3, a5, gate_w, gate_b, bn_w, bn_b, mean, invstd,
+        (x_op, x_w, y, g, w_dg, gate_u, sample_u, k5, k3, k1, a3, a5, gate_w, gate_b, bn_w, bn_b, mean, invstd,
          w_s2) = ctx.saved_tensors
         n, d, h, wd, ci, co, U, normal, use_umma, needs_dx, needs_dw = ctx.cfg
         dev = dout.device
@@ -204,6 +211,8 @@ class ModeConvFunction(torch.autograd.Function):
         m_rows = n * d * h * wd
         dgamma = dbeta = None
         dy_s2 = None
+        dy32 = None             # fp32 dy for the SIMT wgrad while UMMA_WGRAD is off
+        wgrad_f32 = use_umma and not UMMA_WGRAD and needs_dw
         if normal:
             dgamma = torch.empty(co, dtype=torch.float32, device=dev)
             dbeta = torch.empty(co, dtype=torch.float32, device=dev)
@@ -211,8 +220,10 @@ class ModeConvFunction(torch.autograd.Function):
             if use_umma:
                 dy_op = torch.empty((n, d, h, wd, co), dtype=torch.float16, device=dev)
                 dy_s2 = torch.empty(2, dtype=torch.float32, device=dev)
+                if wgrad_f32:
+                    dy32 = torch.empty((n, d, h, wd, co), dtype=torch.float32, device=dev)
                 _lib.check(lib.mode_bn_relu_bwd(_p(y), _p(doutn), m_rows, co, _p(bn_w), _p(bn_b), _p(mean), _p(invstd),
-                                                _p(dgamma), _p(dbeta), None, _p(dy_op), _p(dy_s2), _p(ws), _stream()),
+                                                _p(dgamma), _p(dbeta), _p(dy32), _p(dy_op), _p(dy_s2), _p(ws), _stream()),
                            "mode_bn_relu_bwd")
             else:
                 dy_op = torch.empty((n, d, h, wd, co), dtype=torch.float32, device=dev)
@@ -222,6 +233,7 @@ class ModeConvFunction(torch.autograd.Function):
         elif use_umma:
             dy_s2 = f16_scale_of([doutn], 8192.0)
             dy_op = cast_f16(doutn, dy_s2[0:1])
+            dy32 = doutn
         else:
             dy_op = doutn
 
@@ -232,7 +244,10 @@ class ModeConvFunction(torch.autograd.Function):
             dx = from_ndhwc(dxn)
         grads = [None] * 7
         if needs_dw:
-            d_weff = conv3d_wgrad(x_op, dy_op, dtype, n, d, h, wd, ci, co, dy_s2[1:2] if use_umma else None)
+            if wgrad_f32:
+                d_weff = conv3d_wgrad(x_w, dy32, _lib.MODE_F32, n, d, h, wd, ci, co, None)
+            else:
+                d_weff = conv3d_wgrad(x_w, dy_op, dtype, n, d, h, wd, ci, co, dy_s2[1:2] if use_umma else None)
             layer, _, _ = _layer(k5, k3, k1, a3, a5, gate_w, gate_b)
             outs = [torch.empty_like(t) for t in (k5, k3, k1, a3, a5, gate_w, gate_b)]
             ws = torch.empty(max(int(lib.mode_reparam_bwd_workspace_bytes(ci, co, n)), 16), dtype=torch.uint8, device=dev)

@@ -1,0 +1,166 @@
+"""B200-native `fnet.nn_modules.RepMode` -- same class names, constructor signatures, sub-module names and
+state_dict keys as the reference (fnet/nn_modules/RepMode.py:8-214 in the reference tree), so that
+`importlib.import_module('fnet.nn_modules.RepMode').Net(opts)` (fnet/fnet_model.py:52) and reference
+checkpoints keep working, while MoDEConv.forward runs on the hand-written sm_100a kernels.
+
+What differs from the reference by design:
+  * MoDEConv.forward accepts either the one-hot/dense task embedding `t` [N,T] (reference signature,
+    RepMode.py:194) or int task ids [N]; Net passes the ids straight through, so the one-hot tensor that the
+    reference builds on the CPU per forward (RepMode.py:44-49, a host sync) is never materialised.
+  * activations flow between layers as channels_last_3d (NDHWC) tensors; shapes stay NCDHW.
+  * parameters are ordinary nn.Parameters / buffers (wandb.watch, .to('cpu') round trips and Adam work
+    unchanged) but the forward refuses CPU tensors: there is no CPU fallback.
+"""
+import math
+
+import torch
+
+from . import functional as Fm
+
+
+class MoDEConv(torch.nn.Module):
+    def __init__(self, num_experts, num_tasks, in_chan, out_chan, kernel_size=5, stride=1, padding='same',
+                 conv_type='normal'):
+        super().__init__()
+        if num_experts != 5:
+            raise ValueError("MoDEConv has exactly 5 experts (conv5, conv3, conv1, avg3, avg5)")
+        if kernel_size != 5 or stride != 1 or padding != 'same':
+            raise ValueError("MoDEConv supports kernel_size=5, stride=1, padding='same' (the only configuration "
+                             "the reference instantiates)")
+        self.num_experts = num_experts
+        self.num_tasks = num_tasks
+        self.in_chan = in_chan
+        self.out_chan = out_chan
+        self.kernel_size = kernel_size
+        self.conv_type = conv_type
+        self.stride = stride
+        self.padding = padding
+
+        # registration order mirrors the reference so that state_dict key order is identical
+        self.expert_conv5x5_conv = self.gen_conv_kernel(out_chan, in_chan, 5)
+        self.expert_conv3x3_conv = self.gen_conv_kernel(out_chan, in_chan, 3)
+        self.expert_conv1x1_conv = self.gen_conv_kernel(out_chan, in_chan, 1)
+        self.register_buffer('expert_avg3x3_pool', self.gen_avgpool_kernel(3))
+        self.expert_avg3x3_conv = self.gen_conv_kernel(out_chan, in_chan, 1)
+        self.register_buffer('expert_avg5x5_pool', self.gen_avgpool_kernel(5))
+        self.expert_avg5x5_conv = self.gen_conv_kernel(out_chan, in_chan, 1)
+
+        assert self.conv_type in ['normal', 'final']
+        if self.conv_type == 'normal':
+            self.subsequent_layer = torch.nn.Sequential(
+                torch.nn.BatchNorm3d(out_chan),
+                torch.nn.ReLU(inplace=True),
+            )
+        else:
+            self.subsequent_layer = torch.nn.Identity()
+
+        self.gate = torch.nn.Linear(num_tasks, num_experts * out_chan, bias=True)
+        self.softmax = torch.nn.Softmax(dim=1)
+        self.precision = None          # None -> REPMODE_PRECISION env / default ('f16' tensor-core path)
+
+    def gen_conv_kernel(self, Co, Ci, K):
+        weight = torch.nn.Parameter(torch.empty(Co, Ci, K, K, K))
+        torch.nn.init.kaiming_uniform_(weight, a=math.sqrt(5))
+        return weight
+
+    def gen_avgpool_kernel(self, K):
+        return torch.ones(K, K, K).mul(1.0 / K ** 3)
+
+    def _params(self):
+        return (self.expert_conv5x5_conv, self.expert_conv3x3_conv, self.expert_conv1x1_conv,
+                self.expert_avg3x3_conv, self.expert_avg5x5_conv, self.gate.weight, self.gate.bias)
+
+    def forward(self, x, t):
+        bn = None
+        if self.conv_type == 'normal':
+            m = self.subsequent_layer[0]
+            bn = (m.weight, m.bias, m.running_mean, m.running_var)
+            if self.training and m.track_running_stats and m.num_batches_tracked is not None:
+                m.num_batches_tracked.add_(1)
+        return Fm.mode_conv(x, t, self._params(), bn, self.training, self.conv_type, self.precision)
+
+
+class MoDESubNet2Conv(torch.nn.Module):
+    def __init__(self, num_experts, num_tasks, n_in, n_out):
+        super().__init__()
+        self.conv1 = MoDEConv(num_experts, num_tasks, n_in, n_out, kernel_size=5, padding='same')
+        self.conv2 = MoDEConv(num_experts, num_tasks, n_out, n_out, kernel_size=5, padding='same')
+
+    def forward(self, x, t):
+        return self.conv2(self.conv1(x, t), t)
+
+
+class MoDEEncoderBlock(torch.nn.Module):
+    def __init__(self, num_experts, num_tasks, in_chan, out_chan):
+        super().__init__()
+        self.in_chan = in_chan
+        self.out_chan = out_chan
+        self.conv_more = MoDESubNet2Conv(num_experts, num_tasks, in_chan, out_chan)
+        self.conv_down = torch.nn.Sequential(
+            torch.nn.Conv3d(out_chan, out_chan, kernel_size=2, stride=2, bias=False),
+            torch.nn.BatchNorm3d(out_chan),
+            torch.nn.ReLU(inplace=True),
+        )
+
+    def forward(self, x, t):
+        x_skip = self.conv_more(x, t)
+        return self.conv_down(x_skip), x_skip
+
+
+class MoDEDecoderBlock(torch.nn.Module):
+    def __init__(self, num_experts, num_tasks, in_chan, out_chan):
+        super().__init__()
+        self.in_chan = in_chan
+        self.out_chan = out_chan
+        self.convt = torch.nn.Sequential(
+            torch.nn.ConvTranspose3d(in_chan, out_chan, kernel_size=2, stride=2, bias=False),
+            torch.nn.BatchNorm3d(out_chan),
+            torch.nn.ReLU(inplace=True),
+        )
+        self.conv_less = MoDESubNet2Conv(num_experts, num_tasks, in_chan, out_chan)
+
+    def forward(self, x, x_skip, t):
+        x = self.convt(x)
+        return self.conv_less(torch.cat((x_skip, x), 1), t)
+
+
+class Net(torch.nn.Module):
+    def __init__(self, opts, mult_chan=32, in_channels=1, out_channels=1):
+        super().__init__()
+        self.opts = opts
+        self.mult_chan = mult_chan
+        self.in_channels = in_channels
+        self.out_channels = out_channels
+        self.num_tasks = len(self.opts.adopted_datasets)
+        self.num_experts = 5
+        self.gpu_ids = [self.opts.gpu_ids] if isinstance(self.opts.gpu_ids, int) else self.opts.gpu_ids
+        self.device = torch.device('cuda', self.gpu_ids[0]) if self.gpu_ids[0] >= 0 else torch.device('cpu')
+        E, T, c = self.num_experts, self.num_tasks, self.in_channels * self.mult_chan
+        self.encoder_block1 = MoDEEncoderBlock(E, T, self.in_channels, c)
+        self.encoder_block2 = MoDEEncoderBlock(E, T, c, c * 2)
+        self.encoder_block3 = MoDEEncoderBlock(E, T, c * 2, c * 4)
+        self.encoder_block4 = MoDEEncoderBlock(E, T, c * 4, c * 8)
+        self.bottle_block = MoDESubNet2Conv(E, T, c * 8, c * 16)
+        self.decoder_block4 = MoDEDecoderBlock(E, T, c * 16, c * 8)
+        self.decoder_block3 = MoDEDecoderBlock(E, T, c * 8, c * 4)
+        self.decoder_block2 = MoDEDecoderBlock(E, T, c * 4, c * 2)
+        self.decoder_block1 = MoDEDecoderBlock(E, T, c * 2, c)
+        self.conv_out = MoDEConv(E, T, self.mult_chan, self.out_channels, kernel_size=5, padding='same',
+                                 conv_type='final')
+
+    def one_hot_task_embedding(self, task_id):
+        """Kept for API compatibility (RepMode.py:44-49); built on the device without a host loop."""
+        return torch.nn.functional.one_hot(task_id.to(torch.int64), self.num_tasks).float()
+
+    def forward(self, x, t):
+        t = t.to(device=x.device, dtype=torch.int32).reshape(-1)      # task ids, never a one-hot tensor
+        x, x_skip1 = self.encoder_block1(x, t)
+        x, x_skip2 = self.encoder_block2(x, t)
+        x, x_skip3 = self.encoder_block3(x, t)
+        x, x_skip4 = self.encoder_block4(x, t)
+        x = self.bottle_block(x, t)
+        x = self.decoder_block4(x, x_skip4, t)
+        x = self.decoder_block3(x, x_skip3, t)
+        x = self.decoder_block2(x, x_skip2, t)
+        x = self.decoder_block1(x, x_skip1, t)
+        return self.conv_out(x, t)

@@ -27,7 +27,7 @@ def _ref():
 
 
 def _np(sd):
-    return {k: v.detach().cpu().numpy() for k, v in sd.items()}
+    return {k: v.detach().cpu().numpy().copy() for k, v in sd.items()}   # copy: state_dict aliases live buffers
 
 
 def onehot(t, num_tasks):
@@ -128,7 +128,7 @@ def main():
     # (d) Ci=1 stem layer
     conv_case(ref_mod, "conv_train_stem", 4, 5, 1, 8, (8, 8, 8), [4, 1], True, "normal")
     # (e) tensor-core sized channels (32 -> 32) on a small volume, train mode: the headline layer shape
-    conv_case(ref_mod, "conv_train_c32", 5, 12, 32, 32, (4, 8, 16), [3, 7], True, "normal")
+    conv_case(ref_mod, "conv_train_c32", 5, 12, 32, 32, (4, 16, 16), [3, 7], True, "normal")
     # (f) BASELINE.json configs[0]: single MoDE block, 1x32x32x32 volume, 16 -> 16 channels
     conv_case(ref_mod, "conv_train_config1", 6, 3, 16, 16, (32, 32, 32), [1], True, "normal", np_inputs=True, sub=2)
     # (g) whole U-Net at reduced width (mult_chan=2) so the fixture stays small; 16^3 is the minimum volume

@@ -1,0 +1,78 @@
+"""GPU parity tests proper: the CUDA path (through the C ABI) against the golden vectors frozen from the
+live reference and against the oracle on seeded inputs.  Tolerances: fp32 SIMT path 1e-4 (re-association
+only); tensor-core path (fp16 operands, fp32 accumulate) 1e-3 = the north-star bound."""
+import numpy as np
+import pytest
+import torch
+
+from tests.util import assert_close, load_golden, params_of
+
+pytestmark = pytest.mark.gpu
+
+CONV_CASES = ["conv_train_small", "conv_train_final", "conv_train_stem", "conv_train_c32", "conv_eval_small",
+              "conv_train_config1"]
+
+
+def _build_conv(d, precision):
+    from repmode_b200.nn_modules import MoDEConv
+    p = params_of(d)
+    co, ci = p["expert_conv5x5_conv"].shape[:2]
+    m = MoDEConv(5, int(d["num_tasks"]), ci, co, conv_type=str(d["conv_type"]))
+    m.load_state_dict({k: torch.from_numpy(v) for k, v in p.items()}, strict=True)
+    m.precision = precision
+    return m.cuda()
+
+
+@pytest.mark.parametrize("precision,tol", [("f32", 1e-4), ("f16", 1e-3)])
+@pytest.mark.parametrize("name", CONV_CASES)
+def test_modeconv_vs_golden(name, precision, tol):
+    d = load_golden(name)
+    m = _build_conv(d, precision)
+    training = bool(d["training"])
+    m.train(training)
+    sub = int(d["sub"])
+    x = torch.from_numpy(d["x"]).cuda().requires_grad_(training)
+    t = torch.from_numpy(d["task"]).cuda().to(torch.int32)
+    y = m(x, t)
+    assert y.shape == (x.shape[0], m.out_chan) + tuple(x.shape[2:])
+    assert_close(y.detach().cpu().numpy()[:, :, ::sub, ::sub, ::sub], d["out"], tol, "out")
+    if training:
+        (y * torch.from_numpy(d["dout"]).cuda()).sum().backward()
+        assert_close(x.grad.cpu().numpy()[:, :, ::sub, ::sub, ::sub], d["dx"], tol, "dx")
+        named = dict(m.named_parameters())
+        for k in [k for k in d if k.startswith("grad.")]:
+            assert_close(named[k[5:]].grad.cpu().numpy(), d[k], tol * 2, k)
+        if str(d["conv_type"]) == "normal":
+            bn = m.subsequent_layer[0]
+            assert_close(bn.running_mean.cpu().numpy(), d["after.subsequent_layer.0.running_mean"], 1e-4, "running_mean")
+            assert_close(bn.running_var.cpu().numpy(), d["after.subsequent_layer.0.running_var"], 1e-4, "running_var")
+
+
+def test_modeconv_dense_embedding_matches_ids():
+    """MoDEConv.forward(x, t) with the reference's one-hot float embedding == int task ids."""
+    d = load_golden("conv_train_small")
+    m = _build_conv(d, "f32").eval()
+    x = torch.from_numpy(d["x"]).cuda()
+    ids = torch.from_numpy(d["task"]).cuda()
+    onehot = torch.nn.functional.one_hot(ids, int(d["num_tasks"])).float()
+    with torch.no_grad():
+        a, b = m(x, ids), m(x, onehot)
+    assert torch.equal(a, b)
+
+
+def test_reparam_weff_bitexact_vs_golden():
+    """K1 in fp32 mode reproduces the reference's W_eff to fp32 rounding of the softmax only."""
+    import ctypes
+    from repmode_b200 import functional as Fm, lib as L
+    d = load_golden("conv_train_c32")
+    p = {k: torch.from_numpy(v).cuda() for k, v in params_of(d).items()}
+    layer, ci, co = Fm._layer(p["expert_conv5x5_conv"], p["expert_conv3x3_conv"], p["expert_conv1x1_conv"],
+                              p["expert_avg3x3_conv"], p["expert_avg5x5_conv"], p["gate.weight"], p["gate.bias"])
+    ids = torch.from_numpy(d["task"]).cuda().to(torch.int32)
+    g, w_fwd, w_dg = Fm.reparam_fwd(layer, ids, len(ids), ci, co, L.MODE_F32, True)
+    assert_close(g.cpu().numpy(), d["g"], 1e-6, "g")
+    U = len(ids)
+    w = w_fwd.view(U, 125, ci // 32, co, 32).permute(0, 3, 2, 4, 1).reshape(U, co, ci, 5, 5, 5)
+    assert_close(w.cpu().numpy(), d["w_eff"], 1e-6, "w_eff")
+    wd = w_dg.view(U, 125, co // 32, ci, 32).permute(0, 2, 4, 3, 1).reshape(U, co, ci, 125).flip(-1).reshape(U, co, ci, 5, 5, 5)
+    assert_close(wd.cpu().numpy(), d["w_eff"], 1e-6, "w_dgrad")

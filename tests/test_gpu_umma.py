@@ -1,0 +1,90 @@
+"""GPU: the tcgen05 implicit-GEMM conv (mode_conv3d impl=2) against the SIMT fp32 kernel and the numpy
+oracle, through the C ABI.  Integer-valued fp16-exact operands make the comparison BIT-EXACT (every product
+and partial sum is exactly representable in fp32), so any layout / descriptor / pipeline slip shows up as a
+hard mismatch rather than a tolerance question."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import mode_numpy as onp
+from tests.util import assert_close, pack_weights
+
+pytestmark = pytest.mark.gpu
+
+SHAPES = [  # N, D, H, W, K, Nout
+    (1, 1, 16, 8, 32, 32),
+    (2, 4, 16, 8, 32, 32),
+    (1, 9, 32, 16, 32, 32),
+    (1, 3, 16, 24, 64, 32),
+    (1, 5, 16, 8, 32, 64),
+    (2, 2, 16, 16, 64, 128),
+    (1, 2, 16, 8, 32, 256),
+    (1, 11, 16, 8, 64, 64),
+]
+
+
+def _poll():
+    import ctypes
+    from repmode_b200 import lib as L
+    code = ctypes.c_int32(0)
+    L.check(L.load().mode_poll_error(ctypes.byref(code)), "mode_poll_error")
+    assert code.value == 0, f"tcgen05 pipeline timeout code {code.value}"
+
+
+@pytest.mark.parametrize("shape", SHAPES)
+def test_conv3d_umma_bitexact(shape):
+    from repmode_b200 import functional as Fm, lib as L
+    n, d, h, w, k, nout = shape
+    rng = np.random.RandomState(sum(shape))
+    x = rng.randint(-3, 4, size=(n, d, h, w, k)).astype(np.float32)
+    weff = (rng.randint(-4, 5, size=(n, nout, k, 5, 5, 5)) / 8.0).astype(np.float32)
+    su = torch.arange(n, dtype=torch.int32, device="cuda")
+    xg = torch.from_numpy(x).cuda()
+    w32 = torch.from_numpy(pack_weights(weff, half=False)).cuda()
+    w16 = torch.from_numpy(pack_weights(weff, half=True)).cuda()
+    sums32 = torch.zeros(2 * nout, dtype=torch.float64, device="cuda")
+    sums16 = torch.zeros(2 * nout, dtype=torch.float64, device="cuda")
+    y_simt = Fm.conv3d(xg, L.MODE_F32, w32, su, n, d, h, w, k, nout, None, sums32, impl=L.IMPL_SIMT)
+    y_umma = Fm.conv3d(xg.half(), L.MODE_F16, w16, su, n, d, h, w, k, nout, None, sums16, impl=L.IMPL_UMMA)
+    _poll()
+    if n * d * h * w * k * nout <= 2 ** 22:      # oracle finishes in seconds at these sizes
+        ref = np.stack([onp.conv3d_fwd(x[i].transpose(3, 0, 1, 2), weff[i]) for i in range(n)])
+        assert np.array_equal(y_simt.cpu().numpy(), ref.transpose(0, 2, 3, 4, 1))
+    assert torch.equal(y_umma, y_simt)
+    assert torch.allclose(sums16, sums32, rtol=1e-12, atol=1e-9)
+
+
+def test_conv3d_umma_random_vs_simt():
+    """Real-valued operands: fp16 operand rounding only (<= 2^-11 relative per operand)."""
+    from repmode_b200 import functional as Fm, lib as L
+    n, d, h, w, k, nout = 2, 6, 32, 16, 64, 64
+    g = torch.Generator(device="cpu").manual_seed(0)
+    x = torch.randn(n, d, h, w, k, generator=g).cuda()
+    weff = (torch.randn(n, nout, k, 5, 5, 5, generator=g) * 0.02).numpy()
+    su = torch.arange(n, dtype=torch.int32, device="cuda")
+    w32 = torch.from_numpy(pack_weights(weff, half=False)).cuda()
+    w16 = torch.from_numpy(pack_weights(weff * 256.0, half=True)).cuda()
+    inv = torch.tensor([1.0 / 256.0], device="cuda")
+    y_simt = Fm.conv3d(x, L.MODE_F32, w32, su, n, d, h, w, k, nout, None, None, impl=L.IMPL_SIMT)
+    y_umma = Fm.conv3d(x.half(), L.MODE_F16, w16, su, n, d, h, w, k, nout, inv, None, impl=L.IMPL_UMMA)
+    _poll()
+    assert_close(y_umma.cpu().numpy(), y_simt.cpu().numpy(), 1e-3, "umma vs simt")
+
+
+def test_conv3d_dgrad_pack_matches_oracle():
+    """K3 = K2 on the flipped / io-transposed pack: bit-exact against the oracle's dgrad."""
+    from repmode_b200 import functional as Fm, lib as L
+    n, d, h, w, ci, co = 1, 3, 16, 8, 32, 64
+    rng = np.random.RandomState(7)
+    dy = rng.randint(-3, 4, size=(n, d, h, w, co)).astype(np.float32)
+    weff = (rng.randint(-4, 5, size=(n, co, ci, 5, 5, 5)) / 8.0).astype(np.float32)
+    su = torch.zeros(n, dtype=torch.int32, device="cuda")
+    wd16 = torch.from_numpy(pack_weights(weff, half=True, dgrad=True)).cuda()
+    wd32 = torch.from_numpy(pack_weights(weff, half=False, dgrad=True)).cuda()
+    dyg = torch.from_numpy(dy).cuda()
+    dx_simt = Fm.conv3d(dyg, L.MODE_F32, wd32, su, n, d, h, w, co, ci, None, None, impl=L.IMPL_SIMT)
+    dx_umma = Fm.conv3d(dyg.half(), L.MODE_F16, wd16, su, n, d, h, w, co, ci, None, None, impl=L.IMPL_UMMA)
+    _poll()
+    ref = onp.conv3d_dgrad(dy[0].transpose(3, 0, 1, 2), weff[0]).transpose(1, 2, 3, 0)[None]
+    assert np.array_equal(dx_simt.cpu().numpy(), ref)
+    assert torch.equal(dx_umma, dx_simt)

@@ -40,3 +40,30 @@ def assert_close(got, ref, tol, what=""):
     assert got.shape == ref.shape, f"{what}: shape {got.shape} vs {ref.shape}"
     m, l2 = max_rel(got, ref), rel_l2(got, ref)
     assert m <= tol and l2 <= tol, f"{what}: max_rel={m:.3e} rel_l2={l2:.3e} > tol={tol:.1e}"
+
+
+def pack_weights(w_eff, half, dgrad=False):
+    """numpy restatement of K1's packed layouts (include/repmode_b200.h): w_eff [U,Co,Ci,5,5,5] ->
+    fp32 pack [U][tap][k_chunk][rows][32]; fp16 pack [U][k_chunk][kh*5+kw][4-kd][rows][32] with each block the
+    64-byte-swizzled image (16-byte chunk index ^= (row >> 1) & 3). dgrad: flipped taps, rows=ci, k=co."""
+    u, co, ci = w_eff.shape[:3]
+    w = w_eff.reshape(u, co, ci, 125)
+    if dgrad:
+        w = w[..., ::-1].transpose(0, 2, 1, 3)          # [U, rows=ci, k=co, 124-tap]
+    rows, k = w.shape[1], w.shape[2]
+    nch = (k + 31) // 32
+    out = np.zeros((u, 125, nch, rows, 32), dtype=np.float16 if half else np.float32)
+    for c in range(nch):
+        kk = min(32, k - c * 32)
+        blk = w[:, :, c * 32:c * 32 + kk, :].transpose(0, 3, 1, 2)      # [U,125,rows,kk]
+        if half:
+            col = np.arange(kk)
+            r = np.arange(rows)
+            pc = ((((col[None, :] >> 3) ^ (r[:, None] >> 1)) & 3) << 3) | (col[None, :] & 7)   # [rows,kk]
+            out[:, :, c, r[:, None], pc] = blk
+        else:
+            out[:, :, c, :, :kk] = blk
+    if half:   # [U,125=(kd,t),nch,rows,32] -> [U,nch,t,4-kd,rows,32]
+        out = out.reshape(u, 5, 25, nch, rows, 32)[:, ::-1].transpose(0, 3, 2, 1, 4, 5)
+        out = np.ascontiguousarray(out)
+    return out.reshape(-1)

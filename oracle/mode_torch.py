@@ -50,11 +50,29 @@ def reparam(p, prefix, g):
     return torch.einsum("neo,eoidhw->noidhw", g, ks)
 
 
-def mode_conv(p, prefix, x, task_ids, training, conv_type="normal", update_running=False):
-    """One MoDEConv (RepMode.py:194-214): gate -> softmax -> re-param -> per-sample conv -> BN+ReLU."""
+def round_f16_scaled(t, amax, target):
+    """Straight-through emulation of the tensor-core path's operand staging: multiply by the power of two
+    2^floor(log2(target/amax)), round to fp16 (RN), scale back.  Gradients pass through unchanged."""
+    a = float(amax)
+    s = 2.0 ** torch.floor(torch.log2(torch.tensor(target / a))).item() if a > 0 else 1.0
+    r = ((t * s).half().float() / s)
+    return t + (r - t).detach()
+
+
+def mode_conv(p, prefix, x, task_ids, training, conv_type="normal", update_running=False, operand_f16=False):
+    """One MoDEConv (RepMode.py:194-214): gate -> softmax -> re-param -> per-sample conv -> BN+ReLU.
+
+    operand_f16=True emulates the B200 tensor-core path's forward numerics (fp16 conv operands with
+    power-of-two scaling, fp32 accumulate); the reference itself runs fp32 on CPU (operand_f16=False)."""
     co = p[prefix + "expert_conv5x5_conv"].shape[0]
     g = gate_softmax(p[prefix + "gate.weight"], p[prefix + "gate.bias"], task_ids, co)
     w = reparam(p, prefix, g)
+    if operand_f16:
+        amax = max(float(p[prefix + k].detach().abs().max()) for k in
+                   ("expert_conv5x5_conv", "expert_conv3x3_conv", "expert_conv1x1_conv", "expert_avg3x3_conv",
+                    "expert_avg5x5_conv"))
+        w = round_f16_scaled(w, amax, 1024.0)
+        x = x + (x.half().float() - x).detach()
     if training:
         y = torch.cat([F.conv3d(x[i:i + 1], w[i], padding=2) for i in range(x.shape[0])], dim=0)
     else:

@@ -64,7 +64,7 @@ __host__ __device__ inline SmemLayout smem_layout(int ring, int wstages, int Nt)
     L.w_off = ring * cu::PLANE_BYTES;                         // multiples of 15 KB keep 512-byte alignment
     const uint32_t wst_bytes = 5u * Nt * cu::ROWB;
     L.bar_off = L.w_off + wstages * wst_bytes;
-    L.bn_off = L.bar_off + 512;
+    L.bn_off = L.bar_off + 1024;       // 512 B of mbarriers + tmem slot, 512 B MMA-issuer plane table
     L.total = L.bn_off + 2 * 256 * sizeof(double);
     return L;
 }
@@ -159,8 +159,18 @@ conv3d_umma_kernel(const __grid_constant__ CUtensorMap xmap, const ConvParams P)
         }
     } else if (warp == 1) {
         // ===================== MMA issuer =====================
+        // One thread issues every tcgen05.mma of the CTA, so its loop must stay far below the ~93-cycle MMA
+        // floor: everything that depends only on (tile, chunk, plane) -- ring slot address, accumulator column,
+        // instruction descriptor (N varies with the number of output planes the input plane feeds), weight block
+        // offset -- is tabulated once per chunk in shared memory; the inner loop is one 16-byte table load, two
+        // 32-bit adds and two MMAs per plane.  No divisions: ring/stage indices are wrapped counters.
         if (lane == 0) {
-            uint32_t pseq_base = 0, wseq = 0;
+            uint4* tab = reinterpret_cast<uint4*>(smem + L.bar_off + 512);   // [MAX_RING] entries
+            const uint32_t hi_a = ((cu::BW * cu::ROWB) >> 4) | (1u << 14) | ((uint32_t)SWZ_64B << 29);
+            const uint32_t hi_b = (512u >> 4) | (1u << 14) | ((uint32_t)SWZ_64B << 29);
+            const uint32_t lbo_lo = 1u << 16;                                    // LBO field = 16 B (unused for K-major)
+            uint32_t pslot = 0, puse = 0;        // ring slot / use count of the NEXT plane in sequence
+            uint32_t wst = 0, wuse = 0;          // weight stage / use count
             int it = 0;
             for (int tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x, ++it) {
                 const int dg = (tile % tiles_per_n) / (P.tiles_h * P.tiles_w);
@@ -173,37 +183,56 @@ conv3d_umma_kernel(const __grid_constant__ CUtensorMap xmap, const ConvParams P)
                 // accumulators of this buffer have been drained and re-zeroed by the epilogue
                 if (!mbar_wait(tmem_empty + 8 * buf, (it >> 1) & 1)) { atomicExch(P.error_flag, 3); return; }
                 tc_fence_after();
-                for (int c = 0; c < nchunk; ++c, pseq_base += nplanes) {
-                    for (int t = 0; t < 25; ++t, ++wseq) {
-                        const int kh = t / 5, kw = t - kh * 5;
-                        const uint32_t st = wseq % P.wstages;
-                        if (!mbar_wait(w_full + 8 * st, (wseq / P.wstages) & 1)) { atomicExch(P.error_flag, 5); return; }
-                        tc_fence_after();
-                        const uint32_t wbase = base + L.w_off + st * wst_bytes;
-                        const uint32_t a_tap = (kh * cu::BW + kw) * cu::ROWB;
-                        for (int p = pmin; p <= pmax; ++p) {
-                            const uint32_t s = pseq_base + (p - pmin);
-                            const uint32_t slot = s % P.ring;
-                            if (t == 0) {      // first touch of this plane in this chunk
-                                if (!mbar_wait(plane_full + 8 * slot, (s / P.ring) & 1)) { atomicExch(P.error_flag, 4); return; }
-                                tc_fence_after();
-                            }
-                            const int qlo = max(0, p - 4), qhi = min(P.TD - 1, p);
-                            const int kd_hi = p - qlo;                       // tap of the first (lowest-q) block
-                            const uint32_t ncols = (uint32_t)(qhi - qlo + 1) * P.Nt;
-                            const uint32_t idesc = make_idesc(FMT_F16, 128, ncols, 0, 0);
-                            const uint32_t pa = base + L.plane_off + slot * cu::PLANE_BYTES + a_tap;
-                            const uint32_t pb = wbase + (4 - kd_hi) * blk_bytes;
-#pragma unroll
-                            for (int ks = 0; ks < 2; ++ks) {
-                                const uint64_t adesc = make_smem_desc(pa + ks * 32, 16, cu::BW * cu::ROWB, SWZ_64B);
-                                const uint64_t bdesc = make_smem_desc(pb + ks * 32, 16, 512, SWZ_64B);
-                                mma_f16_ss(acc_base + qlo * P.Nt, adesc, bdesc, idesc, 1u);
-                            }
-                            if (t == 24) mma_commit(plane_empty + 8 * slot);   // last use of the plane in this chunk
-                        }
-                        mma_commit(w_empty + 8 * st);
+                for (int c = 0; c < nchunk; ++c) {
+                    // ---- per-chunk plane table
+                    uint32_t slot = pslot, use = puse;
+                    for (int i = 0; i < nplanes; ++i) {
+                        const int p = pmin + i;
+                        const int qlo = max(0, p - 4), qhi = min(P.TD - 1, p);
+                        uint4 e;
+                        e.x = ((base + L.plane_off + slot * cu::PLANE_BYTES) >> 4) | lbo_lo;          // A desc lo (tap 0)
+                        e.y = ((uint32_t)(4 - (p - qlo)) * blk_bytes) >> 4;                            // B block offset
+                        e.z = acc_base + qlo * P.Nt;                                                   // D column
+                        e.w = make_idesc(FMT_F16, 128, (uint32_t)(qhi - qlo + 1) * P.Nt, 0, 0);
+                        tab[i] = e;
+                        if (++slot == (uint32_t)P.ring) { slot = 0; ++use; }
                     }
+                    for (int t = 0; t < 25; ++t) {
+                        const int kh = t / 5, kw = t - kh * 5;
+                        if (!mbar_wait(w_full + 8 * wst, wuse & 1)) { atomicExch(P.error_flag, 5); return; }
+                        tc_fence_after();
+                        const uint32_t wb_lo = ((base + L.w_off + wst * wst_bytes) >> 4) | lbo_lo;
+                        const uint32_t a_tap = ((kh * cu::BW + kw) * cu::ROWB) >> 4;
+                        if (t > 0 && t < 24) {
+#pragma unroll 4
+                            for (int i = 0; i < nplanes; ++i) {
+                                const uint4 e = tab[i];
+                                const uint32_t a_lo = e.x + a_tap, b_lo = wb_lo + e.y;
+                                mma_f16_ss(e.z, ((uint64_t)hi_a << 32) | a_lo, ((uint64_t)hi_b << 32) | b_lo, e.w, 1u);
+                                mma_f16_ss(e.z, ((uint64_t)hi_a << 32) | (a_lo + 2), ((uint64_t)hi_b << 32) | (b_lo + 2), e.w, 1u);
+                            }
+                        } else {
+                            // t == 0: first touch of each plane -> wait for its TMA (planes land in sequence order);
+                            // t == 24: last touch -> release the ring slot as soon as its MMAs retire
+                            slot = pslot; use = puse;
+                            for (int i = 0; i < nplanes; ++i) {
+                                if (t == 0) {
+                                    if (!mbar_wait(plane_full + 8 * slot, use & 1)) { atomicExch(P.error_flag, 4); return; }
+                                    tc_fence_after();
+                                }
+                                const uint4 e = tab[i];
+                                const uint32_t a_lo = e.x + a_tap, b_lo = wb_lo + e.y;
+                                mma_f16_ss(e.z, ((uint64_t)hi_a << 32) | a_lo, ((uint64_t)hi_b << 32) | b_lo, e.w, 1u);
+                                mma_f16_ss(e.z, ((uint64_t)hi_a << 32) | (a_lo + 2), ((uint64_t)hi_b << 32) | (b_lo + 2), e.w, 1u);
+                                if (t == 24) mma_commit(plane_empty + 8 * slot);
+                                if (++slot == (uint32_t)P.ring) { slot = 0; ++use; }
+                            }
+                        }
+                        mma_commit(w_empty + 8 * wst);
+                        if (++wst == (uint32_t)P.wstages) { wst = 0; ++wuse; }
+                    }
+                    pslot += nplanes;
+                    if (pslot >= (uint32_t)P.ring) { pslot -= P.ring; ++puse; }
                 }
                 mma_commit(tmem_full + 8 * buf);
             }
@@ -344,7 +373,7 @@ int conv3d_umma(const __half* x, const __half* w, const int32_t* sample_u, float
     P.TD = max(1, min(min(256 / P.Nt, 8), D));
     P.ring = P.TD + 4;
     const int wst_bytes = 5 * P.Nt * cu::ROWB;
-    const int budget = 227 * 1024 - 1024 - P.ring * cu::PLANE_BYTES - 512 - 4096;
+    const int budget = 227 * 1024 - 1024 - P.ring * cu::PLANE_BYTES - 1024 - 4096;
     P.wstages = min(cu::MAX_WST, budget / wst_bytes);
     if (P.wstages < 2) MODE_FAIL("conv3d_umma: shared memory budget too small for Nt=%d", P.Nt);
     const SmemLayout L = smem_layout(P.ring, P.wstages, P.Nt);

@@ -189,9 +189,10 @@ class ModeConvFunction(torch.autograd.Function):
                        "mode_bn_apply_relu")
         else:
             out = y
-        if needs_dx or needs_dw or (normal and (ctx.needs_input_grad[9] or ctx.needs_input_grad[10])):
-            if normal and not training:
-                raise NotImplementedError("MoDEConv backward in eval mode (frozen BatchNorm) is not supported")
+        ctx.frozen_bn = normal and not training
+        if ctx.frozen_bn:
+            pass            # eval-mode forward is the supported use; backward through frozen BN raises below
+        elif needs_dx or needs_dw or (normal and (ctx.needs_input_grad[9] or ctx.needs_input_grad[10])):
             x_w = x_op if (UMMA_WGRAD or not use_umma) else xn      # operand K4 will read
             ctx.save_for_backward(None, x_w if needs_dw else None, y if normal else None, g, w_dg,
                                   gate_u, sample_u, k5, k3, k1, a3, a5, gate_w, gate_b, bn_w, bn_b, mean, invstd, w_s2)
@@ -201,6 +202,8 @@ class ModeConvFunction(torch.autograd.Function):
     @staticmethod
     @torch.amp.custom_bwd(device_type="cuda")
     def backward(ctx, dout):
+        if ctx.frozen_bn:
+            raise NotImplementedError("MoDEConv backward in eval mode (frozen BatchNorm statistics) is not supported")
         lib = _lib.load()
         (x_op, x_w, y, g, w_dg, gate_u, sample_u, k5, k3, k1, a3, a5, gate_w, gate_b, bn_w, bn_b, mean, invstd,
          w_s2) = ctx.saved_tensors

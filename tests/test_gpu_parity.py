@@ -23,9 +23,24 @@ def _build_conv(d, precision):
     return m.cuda()
 
 
+def _oracle_f16(d):
+    """Gradients of the tensor-core path are checked against the oracle with the SAME forward operand rounding
+    (fp16 operands, fp32 accumulate): 10-bit-mantissa operands flip a few ReLU masks relative to the pure-fp32
+    golden run (measured: dx max_rel 5.7e-2 on conv_train_c32 from that alone), which is a property of the
+    precision, not of the kernels; the forward OUTPUT is still held to 1e-3 against the fp32 golden vectors."""
+    from oracle import mode_torch as otc
+    p = {k: torch.from_numpy(v).clone().requires_grad_(v.dtype.kind == "f" and "running" not in k and "pool" not in k)
+         for k, v in params_of(d).items()}
+    x = torch.from_numpy(d["x"]).requires_grad_(True)
+    y = otc.mode_conv(p, "", x, torch.from_numpy(d["task"]), True, str(d["conv_type"]), operand_f16=True)
+    (y * torch.from_numpy(d["dout"])).sum().backward()
+    return {"dx": x.grad.numpy(), **{"grad." + k: v.grad.numpy() for k, v in p.items() if v.grad is not None}}
+
+
 @pytest.mark.parametrize("precision,tol", [("f32", 1e-4), ("f16", 1e-3)])
 @pytest.mark.parametrize("name", CONV_CASES)
 def test_modeconv_vs_golden(name, precision, tol):
+    from repmode_b200 import functional as Fm
     d = load_golden(name)
     m = _build_conv(d, precision)
     training = bool(d["training"])
@@ -38,10 +53,15 @@ def test_modeconv_vs_golden(name, precision, tol):
     assert_close(y.detach().cpu().numpy()[:, :, ::sub, ::sub, ::sub], d["out"], tol, "out")
     if training:
         (y * torch.from_numpy(d["dout"]).cuda()).sum().backward()
-        assert_close(x.grad.cpu().numpy()[:, :, ::sub, ::sub, ::sub], d["dx"], tol, "dx")
+        ref = d
+        tensor_core = precision == "f16" and Fm.umma_shape_ok(m.in_chan, m.out_chan, *x.shape[2:])
+        if tensor_core:
+            ref = _oracle_f16(d)
+            ref["dx"] = ref["dx"][:, :, ::sub, ::sub, ::sub]
+        assert_close(x.grad.cpu().numpy()[:, :, ::sub, ::sub, ::sub], ref["dx"], tol, "dx")
         named = dict(m.named_parameters())
         for k in [k for k in d if k.startswith("grad.")]:
-            assert_close(named[k[5:]].grad.cpu().numpy(), d[k], tol * 2, k)
+            assert_close(named[k[5:]].grad.cpu().numpy(), ref[k], tol * 2, k)
         if str(d["conv_type"]) == "normal":
             bn = m.subsequent_layer[0]
             assert_close(bn.running_mean.cpu().numpy(), d["after.subsequent_layer.0.running_mean"], 1e-4, "running_mean")

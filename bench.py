@@ -212,7 +212,8 @@ def run_ours(args, rank, local_rank, world):
     sampler = ClockSampler(local_rank) if rank == 0 else None
     ms, launches = timed(step_resident, args.steps, warmup)
     clocks = sampler.stop() if sampler else None
-    ms_e2e, _ = timed(step_e2e, args.steps, warmup)
+    fast = os.environ.get("REPMODE_BENCH_FAST", "0") == "1"      # profiling runs (ncu): skip the e2e and CPU legs
+    ms_e2e = float("nan") if fast else timed(step_e2e, args.steps, warmup)[0]
 
     if rank != 0:
         return
@@ -264,7 +265,7 @@ def run_ours(args, rank, local_rank, world):
 
     # ---- CPU baseline (rank 0, N=1 only): bounded sample of the same workload
     cpu = None
-    if world == 1:
+    if world == 1 and not fast:
         times, cores = cpu_fwd_bwd(3, 1)
         cpu = {"value": VOX * len(times) / sum(times), "unit": "voxels/s", "cores": cores, "kind": "port",
                "sample": "3 full fwd+bwd steps of the same workload after 1 warm-up (oracle/mode_torch.py, fp32)"}

@@ -398,12 +398,4 @@ int conv3d_umma(const __half* x, const __half* w, const int32_t* sample_u, float
     return 0;
 }
 
-// wgrad on tcgen05: not built yet -> explicit error (the host side keeps wgrad on the SIMT kernel meanwhile)
-bool wgrad_umma_supported(int, int, int, int, int) { return false; }
-int64_t wgrad_umma_workspace_bytes(int, int, int, int, int, int) { return 0; }
-int wgrad_umma(const __half*, const __half*, float*, int, int, int, int, int, int, float, const float*, void*,
-               cudaStream_t) {
-    MODE_FAIL("wgrad_umma: not built");
-}
-
 }  // namespace mode

@@ -61,7 +61,7 @@ __device__ __forceinline__ uint64_t globaltimer_ns() {
 // Time-bounded wait: returns false if the barrier has not flipped within ~2 s of wall clock (the kernel
 // then bails out and raises an error flag instead of hanging the GPU box). max_spins bounds the number of
 // polls between clock checks only.
-__device__ __noinline__ bool mbar_wait_slow(uint32_t bar, uint32_t parity) {
+static __device__ __noinline__ bool mbar_wait_slow(uint32_t bar, uint32_t parity) {
     const uint64_t t0 = globaltimer_ns();
     while (true) {
 #pragma unroll 1

@@ -58,7 +58,7 @@ def _layer(k5, k3, k1, a3, a5, gate_w, gate_b):
     return L, ci, co
 
 
-UMMA_WGRAD = False      # wgrad on tcgen05 (wgrad_umma) not built yet: K4 runs the SIMT fp32 kernel meanwhile
+UMMA_WGRAD = os.environ.get("REPMODE_UMMA_WGRAD", "1") == "1"   # K4 on tcgen05 (wgrad_umma.cu); 0 -> SIMT fp32 wgrad
 
 
 def umma_shape_ok(ci, co, d, h, w):

@@ -11,7 +11,7 @@ import threading
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 SO_PATH = os.path.join(HERE, "librepmode_b200.so")
-SOURCES = ["mode_abi.cu", "reparam.cu", "conv_simt.cu", "bn.cu", "conv_umma.cu"]
+SOURCES = ["mode_abi.cu", "reparam.cu", "conv_simt.cu", "bn.cu", "conv_umma.cu", "wgrad_umma.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-shared",
               "-Xcompiler", "-fPIC"]
 

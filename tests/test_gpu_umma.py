@@ -88,3 +88,32 @@ def test_conv3d_dgrad_pack_matches_oracle():
     ref = onp.conv3d_dgrad(dy[0].transpose(3, 0, 1, 2), weff[0]).transpose(1, 2, 3, 0)[None]
     assert np.array_equal(dx_simt.cpu().numpy(), ref)
     assert torch.equal(dx_umma, dx_simt)
+
+
+WG_SHAPES = [  # N, D, H, W, Ci, Co
+    (1, 1, 16, 8, 32, 32),
+    (1, 3, 16, 8, 32, 32),
+    (2, 4, 32, 16, 32, 32),
+    (1, 5, 24, 8, 64, 32),
+    (1, 2, 16, 16, 32, 64),
+    (1, 6, 40, 24, 64, 64),
+]
+
+
+@pytest.mark.parametrize("shape", WG_SHAPES)
+def test_wgrad_umma_bitexact(shape):
+    """K4 on tcgen05 (stacked-tap MN-major views) == SIMT fp32 wgrad == oracle, exactly, on integer-valued data."""
+    from repmode_b200 import functional as Fm, lib as L
+    n, d, h, w, ci, co = shape
+    rng = np.random.RandomState(sum(shape) + 1)
+    x = rng.randint(-3, 4, size=(n, d, h, w, ci)).astype(np.float32)
+    dy = rng.randint(-3, 4, size=(n, d, h, w, co)).astype(np.float32)
+    xg, dyg = torch.from_numpy(x).cuda(), torch.from_numpy(dy).cuda()
+    dw_simt = Fm.conv3d_wgrad(xg, dyg, L.MODE_F32, n, d, h, w, ci, co, None, impl=L.IMPL_SIMT)
+    dw_umma = Fm.conv3d_wgrad(xg.half(), dyg.half(), L.MODE_F16, n, d, h, w, ci, co, None, impl=L.IMPL_UMMA)
+    _poll()
+    if n * d * h * w * ci * co <= 2 ** 22:
+        ref = np.stack([onp.conv3d_wgrad(x[i].transpose(3, 0, 1, 2), dy[i].transpose(3, 0, 1, 2)) for i in range(n)])
+        ref = ref.reshape(n, co, ci, 125).transpose(0, 3, 1, 2)            # [n][tap][o][i]
+        assert np.array_equal(dw_simt.cpu().numpy(), ref)
+    assert torch.equal(dw_umma, dw_simt)

@@ -173,16 +173,40 @@ def run_ours(args, rank, local_rank, world):
             for p in params:
                 dist.all_reduce(p.grad)
 
-    def step_e2e():
-        for p in params:
-            p.grad = None
-        xd = x_host.to(dev, non_blocking=True).requires_grad_(True)
-        y = m(xd, task)
-        y.backward(dout)
-        if world > 1:
+    # e2e: the caller holds pinned NCDHW host tensors; every step's input crosses PCIe inside the timed region.
+    # Like any input pipeline the copy of step i+1 is issued (side stream, double buffer) before step i computes;
+    # the first copy of a timed run is not overlapped and nothing is copied for a step that is not run.
+    copy_stream = torch.cuda.Stream(device=dev)
+    xbuf = [torch.empty(x_host.shape, device=dev), torch.empty(x_host.shape, device=dev)]
+    ev_copied = [torch.cuda.Event(), torch.cuda.Event()]
+    ev_used = [torch.cuda.Event(), torch.cuda.Event()]
+
+    def issue_copy(i):
+        b = i & 1
+        with torch.cuda.stream(copy_stream):
+            copy_stream.wait_event(ev_used[b])
+            xbuf[b].copy_(x_host, non_blocking=True)
+            ev_copied[b].record(copy_stream)
+
+    def run_e2e(steps):
+        for b in (0, 1):
+            ev_used[b].record(stream)
+        issue_copy(0)
+        for i in range(steps):
+            b = i & 1
+            if i + 1 < steps:
+                issue_copy(i + 1)
+            stream.wait_event(ev_copied[b])
             for p in params:
-                dist.all_reduce(p.grad)
-        return m.gate.bias.grad.cpu()                                                     # D2H read of a step result
+                p.grad = None
+            xd = xbuf[b].detach().requires_grad_(True)
+            y = m(xd, task)
+            y.backward(dout)
+            ev_used[b].record(stream)
+            if world > 1:
+                for p in params:
+                    dist.all_reduce(p.grad)
+            _ = m.gate.bias.grad.cpu()                                                    # D2H read of a step result
 
     def barrier():
         if world > 1:
@@ -213,7 +237,20 @@ def run_ours(args, rank, local_rank, world):
     ms, launches = timed(step_resident, args.steps, warmup)
     clocks = sampler.stop() if sampler else None
     fast = os.environ.get("REPMODE_BENCH_FAST", "0") == "1"      # profiling runs (ncu): skip the e2e and CPU legs
-    ms_e2e = float("nan") if fast else timed(step_e2e, args.steps, warmup)[0]
+    ms_e2e = float("nan")
+    if not fast:
+        run_e2e(warmup)
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        run_e2e(args.steps)
+        e1.record(stream)
+        barrier()
+        ms_e2e = e0.elapsed_time(e1)
+        if world > 1:
+            tms = torch.tensor([ms_e2e], device=dev, dtype=torch.float64)
+            dist.all_reduce(tms, op=dist.ReduceOp.MAX)
+            ms_e2e = float(tms.item())
 
     if rank != 0:
         return
@@ -281,7 +318,8 @@ def run_ours(args, rank, local_rank, world):
                    "precision": Fm.default_precision()},
         "e2e": {"value": e2e, "unit": "voxels/s", "h2d_bytes_per_step": x_host.numel() * 4 * world,
                 "d2h_bytes_per_step": m.gate.bias.numel() * 4 * world, "ms_per_step": ms_e2e / args.steps,
-                "api": "MoDEConv.forward(x_host_pinned NCDHW -> device) + backward, gate.bias.grad.cpu()"},
+                "api": "MoDEConv.forward(x from pinned NCDHW host memory, double-buffered H2D on a side stream) + "
+                       "backward, gate.bias.grad.cpu() every step"},
         "gpu_launches": int(launches),
         "clocks": clocks,
         "roofline": roofline,

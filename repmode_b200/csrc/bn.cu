@@ -12,6 +12,24 @@ namespace mode {
 constexpr int BN_THREADS = 256;
 constexpr int BN_MAXC = 1024;
 
+
+// Deterministic in-block reduction of per-thread 4-channel partials: thread t owns channels 4*(t % vpr) + j.
+// Partials go to shared memory once; thread c < 2C then sums the 256/vpr threads that share its channel
+// (no shared-memory atomics: with 256 threads on 32 addresses they serialise for longer than the streaming loop).
+__device__ __forceinline__ void block_fold_and_flush(const double (&ds)[4], const double (&dq)[4], int C, int vpr,
+                                                     double* __restrict__ gout, double* sh /* [2][4][256] */) {
+    const int t = threadIdx.x;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { sh[j * BN_THREADS + t] = ds[j]; sh[(4 + j) * BN_THREADS + t] = dq[j]; }
+    __syncthreads();
+    for (int c = t; c < 2 * C; c += BN_THREADS) {
+        const int which = c / C, ch = c % C, lv = ch >> 2, j = ch & 3;
+        double a = 0.0;
+        for (int k = lv; k < BN_THREADS; k += vpr) a += sh[(which * 4 + j) * BN_THREADS + k];
+        atomicAdd(gout + c, a);
+    }
+}
+
 // ---- statistics: sums[c] += sum y, sums[C+c] += sum y^2 -------------------------------------------------
 // Each thread owns a fixed group of 4 channels (requires (blockDim*4) % C == 0 or C % (blockDim*4) == 0 ->
 // we use rows-of-C iteration instead: thread t handles float4 #t of a row block).
@@ -36,16 +54,8 @@ __global__ void __launch_bounds__(BN_THREADS) bn_stats_kernel(const float* __res
     }
 #pragma unroll
     for (int j = 0; j < 4; ++j) { ds[j] += s[j]; dq[j] += q[j]; }
-    __shared__ double sh[2 * BN_MAXC];
-    for (int i = threadIdx.x; i < 2 * C; i += BN_THREADS) sh[i] = 0.0;
-    __syncthreads();
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-        atomicAdd(&sh[lane_v * 4 + j], ds[j]);
-        atomicAdd(&sh[C + lane_v * 4 + j], dq[j]);
-    }
-    __syncthreads();
-    for (int i = threadIdx.x; i < 2 * C; i += BN_THREADS) atomicAdd(sums + i, sh[i]);
+    __shared__ double sh[8 * BN_THREADS];
+    block_fold_and_flush(ds, dq, C, vpr, sums, sh);
 }
 
 __global__ void bn_stats_scalar_kernel(const float* __restrict__ y, int64_t M, int C, double* __restrict__ sums) {
@@ -168,7 +178,7 @@ __global__ void __launch_bounds__(BN_THREADS) bn_bwd_reduce_kernel(const float* 
     if ((threadIdx.x & 31) == 0) { atomicMax(mx + c, __float_as_int(mdz)); atomicMax(mx + C + c, __float_as_int(mxh)); }
 }
 
-// vectorised pass 1 for C % 4 == 0 (same structure as bn_stats_kernel)
+// vectorised pass 1 for C % 4 == 0 (same structure as bn_stats_kernel); two rows in flight per thread
 __global__ void __launch_bounds__(BN_THREADS) bn_bwd_reduce_vec_kernel(const float* __restrict__ y,
                                                                        const float* __restrict__ dout, int64_t M,
                                                                        int C, const float* __restrict__ gamma,
@@ -188,18 +198,31 @@ __global__ void __launch_bounds__(BN_THREADS) bn_bwd_reduce_vec_kernel(const flo
     float s[4] = {0, 0, 0, 0}, q[4] = {0, 0, 0, 0}, mdz[4] = {0, 0, 0, 0}, mxh[4] = {0, 0, 0, 0};
     double ds[4] = {0, 0, 0, 0}, dq[4] = {0, 0, 0, 0};
     int cnt = 0;
-    for (int64_t r = (int64_t)blockIdx.x * rows_per_iter + lane_r; r < M; r += (int64_t)gridDim.x * rows_per_iter) {
-        const float4 yv = *reinterpret_cast<const float4*>(y + r * C + lane_v * 4);
-        const float4 dv = *reinterpret_cast<const float4*>(dout + r * C + lane_v * 4);
-        const float ya[4] = {yv.x, yv.y, yv.z, yv.w}, da[4] = {dv.x, dv.y, dv.z, dv.w};
+    const int64_t stride = (int64_t)gridDim.x * rows_per_iter;
+    for (int64_t r = (int64_t)blockIdx.x * rows_per_iter + lane_r; r < M; r += 4 * stride) {
+        float4 yv[4], dv[4];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const float xh = (ya[j] - mu[j]) * is[j];
-            const float dz = fmaf(xh, ga[j], be[j]) > 0.f ? da[j] : 0.f;
-            mdz[j] = fmaxf(mdz[j], fabsf(dz)); mxh[j] = fmaxf(mxh[j], fabsf(xh));
-            s[j] += dz; q[j] = fmaf(dz, xh, q[j]);
+        for (int u = 0; u < 4; ++u) {
+            const int64_t rr = r + u * stride;
+            if (rr < M) {
+                yv[u] = *reinterpret_cast<const float4*>(y + rr * C + lane_v * 4);
+                dv[u] = *reinterpret_cast<const float4*>(dout + rr * C + lane_v * 4);
+            }
         }
-        if (++cnt == 64) {
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            if (r + u * stride < M) {
+                const float ya[4] = {yv[u].x, yv[u].y, yv[u].z, yv[u].w}, da[4] = {dv[u].x, dv[u].y, dv[u].z, dv[u].w};
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const float xh = (ya[j] - mu[j]) * is[j];
+                    const float dz = fmaf(xh, ga[j], be[j]) > 0.f ? da[j] : 0.f;
+                    mdz[j] = fmaxf(mdz[j], fabsf(dz)); mxh[j] = fmaxf(mxh[j], fabsf(xh));
+                    s[j] += dz; q[j] = fmaf(dz, xh, q[j]);
+                }
+            }
+        }
+        if (++cnt == 16) {
 #pragma unroll
             for (int j = 0; j < 4; ++j) { ds[j] += s[j]; dq[j] += q[j]; s[j] = 0.f; q[j] = 0.f; }
             cnt = 0;
@@ -207,19 +230,17 @@ __global__ void __launch_bounds__(BN_THREADS) bn_bwd_reduce_vec_kernel(const flo
     }
 #pragma unroll
     for (int j = 0; j < 4; ++j) { ds[j] += s[j]; dq[j] += q[j]; }
-    __shared__ double sh[2 * BN_MAXC];
+    __shared__ double sh[8 * BN_THREADS];
     __shared__ int smx[2 * BN_MAXC];
-    for (int i = threadIdx.x; i < 2 * C; i += BN_THREADS) { sh[i] = 0.0; smx[i] = 0; }
+    for (int i = threadIdx.x; i < 2 * C; i += BN_THREADS) smx[i] = 0;
     __syncthreads();
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-        atomicAdd(&sh[lane_v * 4 + j], ds[j]);
-        atomicAdd(&sh[C + lane_v * 4 + j], dq[j]);
         atomicMax(&smx[lane_v * 4 + j], __float_as_int(mdz[j]));
         atomicMax(&smx[C + lane_v * 4 + j], __float_as_int(mxh[j]));
     }
-    __syncthreads();
-    for (int i = threadIdx.x; i < 2 * C; i += BN_THREADS) { atomicAdd(red + i, sh[i]); atomicMax(mx + i, smx[i]); }
+    block_fold_and_flush(ds, dq, C, vpr, red, sh);     // contains the __syncthreads that also orders smx
+    for (int i = threadIdx.x; i < 2 * C; i += BN_THREADS) atomicMax(mx + i, smx[i]);
 }
 
 // power-of-two fp16 scale for dy from the per-channel bound
@@ -250,6 +271,55 @@ __global__ void bn_bwd_scale_kernel(const double* __restrict__ red, const int* _
         }
         scale2[0] = sc;
         scale2[1] = 1.f / sc;
+    }
+}
+
+// pass 2, vectorised (C % 4 == 0): float4 in, float4 and/or 4 x fp16 out
+__global__ void __launch_bounds__(BN_THREADS) bn_bwd_apply_vec_kernel(const float* __restrict__ y,
+                                                                      const float* __restrict__ dout, int64_t M, int C,
+                                                                      const float* __restrict__ gamma,
+                                                                      const float* __restrict__ beta,
+                                                                      const float* __restrict__ mean,
+                                                                      const float* __restrict__ invstd,
+                                                                      const double* __restrict__ red,
+                                                                      float* __restrict__ dgamma, float* __restrict__ dbeta,
+                                                                      float* __restrict__ dy, __half* __restrict__ dy16,
+                                                                      const float* __restrict__ scale2) {
+    const float f16_scale = (dy16 != nullptr && scale2 != nullptr) ? scale2[0] : 1.f;
+    __shared__ float smu[BN_MAXC], sis[BN_MAXC], sga[BN_MAXC], sbe[BN_MAXC], sa[BN_MAXC], sb[BN_MAXC];
+    for (int c = threadIdx.x; c < C; c += BN_THREADS) {
+        smu[c] = mean[c]; sis[c] = invstd[c];
+        sga[c] = gamma ? gamma[c] : 1.f; sbe[c] = beta ? beta[c] : 0.f;
+        sa[c] = (float)(red[c] / (double)M);
+        sb[c] = (float)(red[C + c] / (double)M);
+        if (blockIdx.x == 0) {
+            if (dbeta) dbeta[c] = (float)red[c];
+            if (dgamma) dgamma[c] = (float)red[C + c];
+        }
+    }
+    __syncthreads();
+    const int64_t nvec = (M * C) >> 2;
+    for (int64_t i = (int64_t)blockIdx.x * BN_THREADS + threadIdx.x; i < nvec; i += (int64_t)gridDim.x * BN_THREADS) {
+        const int c = (int)((i * 4) % C);
+        const float4 yv = *reinterpret_cast<const float4*>(y + i * 4);
+        const float4 dv = *reinterpret_cast<const float4*>(dout + i * 4);
+        const float ya[4] = {yv.x, yv.y, yv.z, yv.w}, da[4] = {dv.x, dv.y, dv.z, dv.w};
+        float v[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const float xh = (ya[j] - smu[c + j]) * sis[c + j];
+            const float dz = fmaf(xh, sga[c + j], sbe[c + j]) > 0.f ? da[j] : 0.f;
+            v[j] = sga[c + j] * sis[c + j] * (dz - sa[c + j] - xh * sb[c + j]);
+        }
+        if (dy) *reinterpret_cast<float4*>(dy + i * 4) = make_float4(v[0], v[1], v[2], v[3]);
+        if (dy16) {
+            __half2 a = __floats2half2_rn(v[0] * f16_scale, v[1] * f16_scale);
+            __half2 b = __floats2half2_rn(v[2] * f16_scale, v[3] * f16_scale);
+            uint2 pk;
+            pk.x = *reinterpret_cast<uint32_t*>(&a);
+            pk.y = *reinterpret_cast<uint32_t*>(&b);
+            *reinterpret_cast<uint2*>(dy16 + i * 4) = pk;
+        }
     }
 }
 
@@ -397,7 +467,7 @@ extern "C" int mode_bn_relu_bwd(const float* y, const float* dout, int64_t M, in
     const bool aligned = ((reinterpret_cast<uintptr_t>(y) | reinterpret_cast<uintptr_t>(dout)) & 15) == 0;
     if ((C & 3) == 0 && vpr <= BN_THREADS && BN_THREADS % vpr == 0 && aligned) {
         const int rpi = BN_THREADS / vpr;
-        bn_bwd_reduce_vec_kernel<<<stream_grid(M, rpi * 8), BN_THREADS, 0, st>>>(y, dout, M, C, gamma, beta, mean,
+        bn_bwd_reduce_vec_kernel<<<stream_grid(M, rpi * 16), BN_THREADS, 0, st>>>(y, dout, M, C, gamma, beta, mean,
                                                                                 invstd, workspace, mx);
     } else {
         const int gx = (int)max((int64_t)1, min(ceil_div(M, BN_THREADS * 8), (int64_t)64));
@@ -408,8 +478,14 @@ extern "C" int mode_bn_relu_bwd(const float* y, const float* dout, int64_t M, in
         bn_bwd_scale_kernel<<<1, 256, 0, st>>>(workspace, mx, M, C, gamma, invstd, 8192.f, dy_scale2);
         MODE_LAUNCH_CHECK();
     }
-    bn_bwd_apply_kernel<<<stream_grid(M * C, BN_THREADS * 8), BN_THREADS, 0, st>>>(
-        y, dout, M, C, gamma, beta, mean, invstd, workspace, dgamma, dbeta, dy, (__half*)dy_f16, dy_scale2);
+    const bool vec_ok = (C & 3) == 0 && aligned && ((reinterpret_cast<uintptr_t>(dy) & 15) == 0) &&
+                        ((reinterpret_cast<uintptr_t>(dy_f16) & 7) == 0);
+    if (vec_ok)
+        bn_bwd_apply_vec_kernel<<<stream_grid(M * C / 4, BN_THREADS * 4), BN_THREADS, 0, st>>>(
+            y, dout, M, C, gamma, beta, mean, invstd, workspace, dgamma, dbeta, dy, (__half*)dy_f16, dy_scale2);
+    else
+        bn_bwd_apply_kernel<<<stream_grid(M * C, BN_THREADS * 8), BN_THREADS, 0, st>>>(
+            y, dout, M, C, gamma, beta, mean, invstd, workspace, dgamma, dbeta, dy, (__half*)dy_f16, dy_scale2);
     MODE_LAUNCH_CHECK();
     return 0;
 }

@@ -50,8 +50,31 @@ struct ConvParams {
     int N, D, H, W, K, Nout;     // Nout = total output channels (row stride of y / rows per weight block)
     int n0, Nt;                  // this launch computes channels [n0, n0+Nt)
     int TD, ring, wstages;
-    int tiles_w, tiles_h, dgroups, total_tiles;
+    int tiles_w, tiles_h;
+    int64_t units;               // N * tiles_h * tiles_w * D plane-patches, split evenly over the CTAs
     int* error_flag;
+};
+
+// Work distribution: a "unit" is one 8x16 patch of one output d-plane, ordered (n, th, tw, d).  CTA c owns the
+// contiguous unit range [units*c/G, units*(c+1)/G) and walks it in tiles of up to TD consecutive planes of one
+// patch column, so every CTA gets the same number of planes (no 4th-wave tail of whole 8-plane tiles).
+struct TileWalker {
+    int64_t u, uend;
+    int D, TD, tiles_h, tiles_w;
+    __device__ TileWalker(const ConvParams& P)
+        : u(P.units * blockIdx.x / gridDim.x), uend(P.units * (blockIdx.x + 1) / gridDim.x), D(P.D), TD(P.TD),
+          tiles_h(P.tiles_h), tiles_w(P.tiles_w) {}
+    __device__ bool next(int& n, int& h0, int& w0, int& d0, int& td) {
+        if (u >= uend) return false;
+        const int64_t patch = u / D;
+        d0 = (int)(u - patch * D);
+        td = (int)min((int64_t)min(TD, D - d0), uend - u);
+        w0 = (int)(patch % tiles_w) * cu::TW;
+        h0 = (int)((patch / tiles_w) % tiles_h) * cu::TH;
+        n = (int)(patch / ((int64_t)tiles_w * tiles_h));
+        u += td;
+        return true;
+    }
 };
 
 struct SmemLayout {
@@ -109,21 +132,16 @@ conv3d_umma_kernel(const __grid_constant__ CUtensorMap xmap, const ConvParams P)
     tc_fence_after();
     const uint32_t tmem = *tmem_slot;
 
-    const int tiles_per_n = P.dgroups * P.tiles_h * P.tiles_w;
 
     if (warp == 0) {
         // ===================== activation-plane producer =====================
         if (lane == 0) {
             uint32_t seq = 0;
-            for (int tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x) {
-                const int n = tile / tiles_per_n;
-                int r = tile % tiles_per_n;
-                const int dg = r / (P.tiles_h * P.tiles_w);
-                r %= P.tiles_h * P.tiles_w;
-                const int h0 = (r / P.tiles_w) * cu::TH, w0 = (r % P.tiles_w) * cu::TW;
-                const int d0 = dg * P.TD;
+            TileWalker tw_(P);
+            int n, h0, w0, d0, td;
+            while (tw_.next(n, h0, w0, d0, td)) {
                 int pmin, pmax;
-                plane_range(d0, P.TD, P.D, pmin, pmax);
+                plane_range(d0, td, P.D, pmin, pmax);
                 for (int c = 0; c < nchunk; ++c) {
                     for (int p = pmin; p <= pmax; ++p, ++seq) {
                         const uint32_t slot = seq % P.ring, use = seq / P.ring;
@@ -139,8 +157,9 @@ conv3d_umma_kernel(const __grid_constant__ CUtensorMap xmap, const ConvParams P)
         // ===================== weight producer =====================
         if (lane == 0) {
             uint32_t seq = 0;
-            for (int tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x) {
-                const int n = tile / tiles_per_n;
+            TileWalker tw_(P);
+            int n, h0, w0, d0, td;
+            while (tw_.next(n, h0, w0, d0, td)) {
                 const int u = P.sample_u ? P.sample_u[n] : 0;
                 const __half* wu = P.w + (size_t)u * nchunk * 125 * P.Nout * 32;
                 for (int c = 0; c < nchunk; ++c) {
@@ -171,12 +190,11 @@ conv3d_umma_kernel(const __grid_constant__ CUtensorMap xmap, const ConvParams P)
             const uint32_t lbo_lo = 1u << 16;                                    // LBO field = 16 B (unused for K-major)
             uint32_t pslot = 0, puse = 0;        // ring slot / use count of the NEXT plane in sequence
             uint32_t wst = 0, wuse = 0;          // weight stage / use count
-            int it = 0;
-            for (int tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x, ++it) {
-                const int dg = (tile % tiles_per_n) / (P.tiles_h * P.tiles_w);
-                const int d0 = dg * P.TD;
+            TileWalker tw_(P);
+            int n, h0, w0, d0, td;
+            for (int it = 0; tw_.next(n, h0, w0, d0, td); ++it) {
                 int pmin, pmax;
-                plane_range(d0, P.TD, P.D, pmin, pmax);
+                plane_range(d0, td, P.D, pmin, pmax);
                 const int nplanes = pmax - pmin + 1;
                 const int buf = it & 1;
                 const uint32_t acc_base = tmem + buf * 256;
@@ -188,7 +206,7 @@ conv3d_umma_kernel(const __grid_constant__ CUtensorMap xmap, const ConvParams P)
                     uint32_t slot = pslot, use = puse;
                     for (int i = 0; i < nplanes; ++i) {
                         const int p = pmin + i;
-                        const int qlo = max(0, p - 4), qhi = min(P.TD - 1, p);
+                        const int qlo = max(0, p - 4), qhi = min(td - 1, p);
                         uint4 e;
                         e.x = ((base + L.plane_off + slot * cu::PLANE_BYTES) >> 4) | lbo_lo;          // A desc lo (tap 0)
                         e.y = ((uint32_t)(4 - (p - qlo)) * blk_bytes) >> 4;                            // B block offset
@@ -255,19 +273,14 @@ conv3d_umma_kernel(const __grid_constant__ CUtensorMap xmap, const ConvParams P)
         __syncwarp();
         if (lane == 0) { mbar_arrive(tmem_empty); mbar_arrive(tmem_empty + 8); }
 
-        int it = 0;
-        for (int tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x, ++it) {
-            const int n = tile / tiles_per_n;
-            int r = tile % tiles_per_n;
-            const int dg = r / (P.tiles_h * P.tiles_w);
-            r %= P.tiles_h * P.tiles_w;
-            const int h0 = (r / P.tiles_w) * cu::TH, w0 = (r % P.tiles_w) * cu::TW;
-            const int d0 = dg * P.TD;
+        TileWalker tw_(P);
+        int n, h0, w0, d0, td;
+        for (int it = 0; tw_.next(n, h0, w0, d0, td); ++it) {
             const int buf = it & 1;
             if (!mbar_wait(tmem_full + 8 * buf, (it >> 1) & 1)) { atomicExch(P.error_flag, 6); break; }
             tc_fence_after();
-            const int qn = min(P.TD, P.D - d0);
-            for (int q = 0; q < P.TD; ++q) {
+            const int qn = td;
+            for (int q = 0; q < td; ++q) {
                 float* dst = P.y + ((((size_t)n * P.D + d0 + q) * P.H + h0 + th) * P.W + w0 + tw) * P.Nout + P.n0;
                 for (int cc = 0; cc < P.Nt; cc += 32) {
                     const uint32_t taddr = tmem + buf * 256 + q * P.Nt + cc + lane_addr;
@@ -379,10 +392,9 @@ int conv3d_umma(const __half* x, const __half* w, const int32_t* sample_u, float
     const SmemLayout L = smem_layout(P.ring, P.wstages, P.Nt);
     const int smem_bytes = (int)L.total + 1024;
     if (smem_bytes > 227 * 1024) MODE_FAIL("conv3d_umma: shared memory budget exceeded (%d B)", smem_bytes);
-    P.tiles_w = W / cu::TW; P.tiles_h = H / cu::TH; P.dgroups = (int)ceil_div(D, P.TD);
-    const int64_t total = (int64_t)N * P.dgroups * P.tiles_h * P.tiles_w;
-    if (total > 0x7fffffff) MODE_FAIL("conv3d_umma: too many tiles");
-    P.total_tiles = (int)total;
+    P.tiles_w = W / cu::TW; P.tiles_h = H / cu::TH;
+    P.units = (int64_t)N * P.tiles_h * P.tiles_w * D;
+    const int64_t total = ceil_div(P.units, P.TD);          // upper bound on useful CTAs
     P.error_flag = device_error_flag();
     if (!P.error_flag) MODE_FAIL("conv3d_umma: could not allocate the device error flag");
 

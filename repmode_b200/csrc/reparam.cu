@@ -44,16 +44,18 @@ __device__ __forceinline__ size_t pack_index<__half>(int u, int tap, int chunk, 
     return (((((size_t)u * nchunk + chunk) * 25 + t) * 5 + (4 - kd)) * nrows + row) * MODE_KC + pack_col<__half>(row, col);
 }
 
-// grid (Co, ceil(Ci/32), U), block 128
+// grid (Co, ceil(Ci/32), U*5), block 256: one block = one (o, 32-ci block, gate input, kd slice of 25 taps).
+// The kd split multiplies the number of resident loads (a 32x32 layer is otherwise only 32 blocks deep and
+// the kernel is pure memory latency).
 template <typename OutT>
-__global__ void __launch_bounds__(128) reparam_fwd_kernel(mode_layer_t L, const int32_t* __restrict__ task_ids,
+__global__ void __launch_bounds__(256) reparam_fwd_kernel(mode_layer_t L, const int32_t* __restrict__ task_ids,
                                                           const float* __restrict__ t_dense,
                                                           float* __restrict__ g_out, OutT* __restrict__ w_fwd,
                                                           float w_scale, const float* __restrict__ w_scale_dev) {
-    __shared__ float sw[32 * 125];   // [i][tap]; stride 125 is odd -> column reads are conflict free
+    __shared__ float sw[32 * 25];    // [i][tap in slice]; stride 25 is odd -> column reads are conflict free
     __shared__ float slog[MODE_NUM_EXPERTS];
     __shared__ float sg[MODE_NUM_EXPERTS];
-    const int o = blockIdx.x, ic = blockIdx.y, u = blockIdx.z;
+    const int o = blockIdx.x, ic = blockIdx.y, u = blockIdx.z / 5, kds = blockIdx.z % 5;
     const int Ci = L.ci, Co = L.co, T = L.num_tasks;
     const int tid = threadIdx.x;
 
@@ -77,7 +79,7 @@ __global__ void __launch_bounds__(128) reparam_fwd_kernel(mode_layer_t L, const 
         for (int e = 0; e < MODE_NUM_EXPERTS; ++e) { ex[e] = expf(slog[e] - m); s += ex[e]; }
         for (int e = 0; e < MODE_NUM_EXPERTS; ++e) {
             sg[e] = ex[e] / s;
-            if (ic == 0 && g_out != nullptr) g_out[((size_t)u * MODE_NUM_EXPERTS + e) * Co + o] = sg[e];
+            if (ic == 0 && kds == 0 && g_out != nullptr) g_out[((size_t)u * MODE_NUM_EXPERTS + e) * Co + o] = sg[e];
         }
     }
     __syncthreads();
@@ -85,8 +87,8 @@ __global__ void __launch_bounds__(128) reparam_fwd_kernel(mode_layer_t L, const 
     if (w_scale_dev != nullptr) w_scale *= *w_scale_dev;
     const float c3 = 1.0f / 27, c5 = 1.0f / 125;               // fp32-rounded pool constants (RepMode.py:161-163)
 
-    for (int idx = tid; idx < 32 * 125; idx += 128) {
-        const int i = idx / 125, tap = idx - i * 125;
+    for (int idx = tid; idx < 32 * 25; idx += 256) {
+        const int i = idx / 25, tap = kds * 25 + (idx - i * 25);
         const int c = ic * 32 + i;
         float val = 0.f;
         if (c < Ci) {
@@ -109,8 +111,8 @@ __global__ void __launch_bounds__(128) reparam_fwd_kernel(mode_layer_t L, const 
     __syncthreads();
     const int warp = tid >> 5, lane = tid & 31;
     const int nci = gridDim.y;
-    for (int tap = warp; tap < 125; tap += 4) {
-        store_w(w_fwd + pack_index<OutT>(u, tap, ic, nci, o, Co, lane), sw[lane * 125 + tap] * w_scale);
+    for (int tl = warp; tl < 25; tl += 8) {
+        store_w(w_fwd + pack_index<OutT>(u, kds * 25 + tl, ic, nci, o, Co, lane), sw[lane * 25 + tl] * w_scale);
     }
 }
 
@@ -313,9 +315,9 @@ extern "C" int mode_reparam_fwd(const mode_layer_t* L, const int32_t* task_ids, 
     if ((int64_t)U * 125 > 65535) MODE_FAIL("mode_reparam_fwd: U too large (%d)", U);
     cudaStream_t st = (cudaStream_t)stream;
     const int nci = (int)ceil_div(L->ci, 32), nco = (int)ceil_div(L->co, 32);
-    dim3 grid(L->co, nci, U);
+    dim3 grid(L->co, nci, U * 5);
     if (w_dtype == MODE_F32) {
-        reparam_fwd_kernel<float><<<grid, 128, 0, st>>>(*L, task_ids, t_dense, g_out, (float*)w_fwd, w_scale,
+        reparam_fwd_kernel<float><<<grid, 256, 0, st>>>(*L, task_ids, t_dense, g_out, (float*)w_fwd, w_scale,
                                                         w_scale_dev);
         MODE_LAUNCH_CHECK();
         if (w_dgrad) {
@@ -324,7 +326,7 @@ extern "C" int mode_reparam_fwd(const mode_layer_t* L, const int32_t* task_ids, 
             MODE_LAUNCH_CHECK();
         }
     } else if (w_dtype == MODE_F16) {
-        reparam_fwd_kernel<__half><<<grid, 128, 0, st>>>(*L, task_ids, t_dense, g_out, (__half*)w_fwd, w_scale,
+        reparam_fwd_kernel<__half><<<grid, 256, 0, st>>>(*L, task_ids, t_dense, g_out, (__half*)w_fwd, w_scale,
                                                          w_scale_dev);
         MODE_LAUNCH_CHECK();
         if (w_dgrad) {

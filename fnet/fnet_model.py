@@ -1,0 +1,179 @@
+"""Host wrapper with the reference's `fnet.fnet_model.Model` API (fnet/fnet_model.py:16-239 in the reference
+tree) so that main.py / eval.py style drivers run on the B200 network unchanged: same constructor, attributes
+(`net, optimizer, count_iter, count_epoch, patch_size, device, gpu_ids`) and methods (`do_train_iter`,
+`do_eval_iter`, `predict`, `save_state`, `load_state`, `get_state`, `to_gpu`).  Written from the behaviour, not
+from the source.  Deviations: `torch.load(..., weights_only=False)` (the reference call at :85 fails on
+torch >= 2.6 because the checkpoint pickles an argparse.Namespace), wandb logging only if wandb is importable,
+and `torch.amp` spellings of autocast / GradScaler.
+"""
+import importlib
+import math
+import os
+
+import numpy as np
+import pandas as pd
+import torch
+
+from fnet.metric import get_metric_stats
+
+try:                                     # logging is optional; never on the hot path
+    import wandb                         # noqa: F401
+except Exception:                        # noqa: BLE001
+    wandb = None
+
+
+def _as_list(gpu_ids):
+    return [gpu_ids] if isinstance(gpu_ids, int) else list(gpu_ids)
+
+
+def _device_of(gpu_ids):
+    return torch.device("cuda", gpu_ids[0]) if gpu_ids[0] >= 0 else torch.device("cpu")
+
+
+class Model(object):
+    def __init__(self, opts, nn_module=None, init_weights=True, lr=0.001, criterion_fn=torch.nn.MSELoss, gpu_ids=-1):
+        self.opts = opts
+        self.nn_module = nn_module
+        self.init_weights = init_weights
+        self.lr = lr
+        self.count_iter = 0
+        self.count_epoch = 0
+        self.gpu_ids = _as_list(gpu_ids)
+        self.device = _device_of(self.gpu_ids)
+        self.patch_size = (32, 128, 128)
+        self.criterion = criterion_fn(reduction="none")
+        self._init_model()
+        if self.net is not None and len(self.gpu_ids) > 1:
+            raise NotImplementedError("multi-GPU runs use one process per GPU (repmode_b200.parallel), not "
+                                      "torch.nn.DataParallel")
+        self.scaler = torch.amp.GradScaler("cuda", enabled=self.device.type == "cuda")
+
+    def _init_model(self):
+        if self.nn_module is None:
+            self.net = None
+            return
+        self.net = importlib.import_module("fnet.nn_modules." + self.nn_module).Net(self.opts)
+        self.net.to(self.device)
+        self.optimizer = torch.optim.Adam(self.net.parameters(), lr=self.lr)
+
+    # ------------------------------------------------------------------ checkpointing
+    def get_state(self):
+        return dict(nn_module=self.nn_module, opts=self.opts, nn_state=self.net.state_dict(),
+                    optimizer_state=self.optimizer.state_dict(), count_iter=self.count_iter,
+                    count_epoch=self.count_epoch)
+
+    def to_gpu(self, gpu_ids):
+        self.gpu_ids = _as_list(gpu_ids)
+        self.device = _device_of(self.gpu_ids)
+        self.net.to(self.device)
+        _set_gpu_recursive(self.optimizer.state, self.gpu_ids[0])
+
+    def save_state(self, path_save):
+        keep = self.gpu_ids
+        d = os.path.dirname(path_save)
+        if d and not os.path.exists(d):
+            os.makedirs(d)
+        self.to_gpu(-1)
+        torch.save(self.get_state(), path_save)
+        self.to_gpu(keep)
+
+    def load_state(self, path_load, gpu_ids=-1):
+        state = torch.load(path_load, weights_only=False)
+        self.nn_module = state["nn_module"]
+        self.opts = state["opts"]
+        self.opts.gpu_ids = gpu_ids
+        self._init_model()
+        self.net.load_state_dict(state["nn_state"])
+        self.optimizer.load_state_dict(state["optimizer_state"])
+        self.count_iter = state["count_iter"]
+        self.count_epoch = state["count_epoch"]
+        self.to_gpu(gpu_ids)
+
+    # ------------------------------------------------------------------ training / evaluation
+    def do_train_iter(self, signal, target, task):
+        signal, target, task = signal.to(self.device), target.to(self.device), task.to(self.device)
+        self.net.train()
+        self.optimizer.zero_grad()
+        with torch.amp.autocast("cuda", enabled=self.device.type == "cuda"):
+            output = self.net(signal, task)
+            loss_nomean = self.criterion(output, target)
+            loss = torch.mean(loss_nomean)
+        self.scaler.scale(loss).backward()
+        self.scaler.step(self.optimizer)
+        self.scaler.update()
+
+        per_sample = torch.mean(loss_nomean.detach().float(), dim=(1, 2, 3, 4)).cpu().numpy()
+        task_host = task.cpu().numpy()
+        if wandb is not None and getattr(wandb, "run", None) is not None:
+            log = {"X-axis/iter": self.count_iter, "loss/iter": float(loss)}
+            for i in sorted(set(int(v) for v in task_host)):
+                log[f"loss_iter/{self.opts.adopted_datasets[i]}"] = float(per_sample[task_host == i].mean())
+            wandb.log(log)
+        frame = pd.DataFrame({"dataset": [self.opts.adopted_datasets[int(i)] for i in task_host],
+                              "loss": list(per_sample)})
+        return output.detach().float().cpu(), frame
+
+    def do_eval_iter(self, signal, target, task, info):
+        pred = self.predict(signal, task, self.patch_size)
+        _, stats = get_metric_stats(pred, target)
+        frame = pd.DataFrame([stats])
+        frame.insert(loc=0, column="dataset", value=info["dataset"])
+        frame.insert(loc=1, column="path_czi", value=info["path_czi"])
+        return pred, frame
+
+    def predict(self, signal, task, patch_size):
+        """Sliding-window inference: overlapping patches (stride = half a patch, last patch clamped to the border),
+        Gaussian-weighted blending; every batch of patches shares one task (eval uses sample 0's kernel)."""
+        signal, task = signal.to(self.device), task.to(self.device)
+        self.net.eval()
+        size = tuple(signal.shape[-3:])
+        starts_per_axis = []
+        for length, plen in zip(size, patch_size):
+            stride = int(math.ceil(plen * 0.5))
+            steps = int(math.ceil((length - plen) / stride + 1))
+            axis = []
+            for i in range(max(steps, 1)):
+                end = min(i * stride + plen, length)
+                axis.append((max(end - plen, 0), end))
+            starts_per_axis.append(axis)
+        windows = [(a, b, c) for a in starts_per_axis[0] for b in starts_per_axis[1] for c in starts_per_axis[2]]
+        gauss = torch.from_numpy(get_gaussian(patch_size)).to(self.device)
+        pred_sum = torch.zeros(signal.shape, device=self.device)
+        weight_sum = torch.zeros(signal.shape, device=self.device)
+        bs = max(1, int(getattr(self.opts, "batch_size_eval", 1)))
+        for k in range(0, len(windows), bs):
+            chunk = windows[k:k + bs]
+            batch = torch.cat([signal[:, :, a[0]:a[1], b[0]:b[1], c[0]:c[1]] for a, b, c in chunk], dim=0)
+            with torch.no_grad():
+                out = self.net(batch, task.expand(len(chunk)))
+                if isinstance(out, tuple):
+                    out = out[0]
+            for j, (a, b, c) in enumerate(chunk):
+                g = gauss[:a[1] - a[0], :b[1] - b[0], :c[1] - c[0]]
+                pred_sum[:, :, a[0]:a[1], b[0]:b[1], c[0]:c[1]] += out[j:j + 1].float() * g
+                weight_sum[:, :, a[0]:a[1], b[0]:b[1], c[0]:c[1]] += g
+        return (pred_sum / weight_sum).cpu()
+
+    def __str__(self):
+        return "Network:\n{}\nLoss:\n{}\nOptimizer:\n{}\n".format(self.nn_module, self.criterion, self.optimizer)
+
+
+def get_gaussian(patch_size, sigma_scale=1 / 8):
+    """Importance map for patch blending: a unit impulse at the patch centre blurred with sigma = size/8 per axis,
+    normalised to max 1, zeros lifted to the smallest positive value."""
+    from scipy.ndimage import gaussian_filter
+    imp = np.zeros(patch_size)
+    imp[tuple(s // 2 for s in patch_size)] = 1
+    g = gaussian_filter(imp, [s * sigma_scale for s in patch_size], order=0, mode="constant", cval=0)
+    g = (g / g.max()).astype(np.float32)
+    g[g == 0] = g[g != 0].min()
+    return g
+
+
+def _set_gpu_recursive(var, gpu_id):
+    """Move every tensor nested in dict `var` (optimizer state) to cuda:gpu_id, or to the CPU for -1."""
+    for key in var:
+        if isinstance(var[key], dict):
+            _set_gpu_recursive(var[key], gpu_id)
+        elif torch.is_tensor(var[key]):
+            var[key] = var[key].cpu() if gpu_id == -1 else var[key].cuda(gpu_id)

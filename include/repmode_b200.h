@@ -103,13 +103,15 @@ int mode_reparam_bwd(const mode_layer_t* layer_host, const int32_t* task_ids, co
  *   set per sample (all zeros in eval mode, RepMode.py:209-210), y [N,D,H,W,Nout] fp32.
  *   out_scale * (out_scale_dev ? *out_scale_dev : 1) multiplies the accumulator (undoes operand scaling).
  *   bn_sums (may be NULL): double[2*Nout], += per-channel sum and sum of squares of y (BatchNorm3d
- *   training statistics, RepMode.py:147) -- fused so y is not re-read.
+ *   training statistics, RepMode.py:147) -- fused so y is not re-read -- over the d-planes
+ *   [stat_d_lo, stat_d_hi) only (the OWNED planes of a D-sharded slab; pass 0, D for the whole tensor).
  *   impl: 0 = auto, 1 = SIMT fp32 direct conv (any shape, fp32 operands only), 2 = tcgen05 implicit GEMM
  *   (fp16 operands, K % 32 == 0, Nout % 16 == 0).
  */
 int mode_conv3d(const void* x, mode_dtype_t x_dtype, const void* w, const int32_t* sample_u, float* y,
                 int32_t N, int32_t D, int32_t H, int32_t W, int32_t K, int32_t Nout, float out_scale,
-                const float* out_scale_dev, double* bn_sums, int32_t impl, void* stream);
+                const float* out_scale_dev, double* bn_sums, int32_t stat_d_lo, int32_t stat_d_hi, int32_t impl,
+                void* stream);
 
 /* ---- K4: wgrad ------------------------------------------------------------------------------------------
  * d_weff[n][tap][o][i] = out_scale * sum_p dy[n][p][o] * x[n][p + tap - 2][i]   (autograd of RepMode.py:207).
@@ -132,21 +134,44 @@ int mode_conv3d_wgrad(const void* x, const void* dy, mode_dtype_t dtype, float* 
  *                   workspace: mode_bn_bwd_workspace_bytes(C).
  */
 int64_t mode_bn_bwd_workspace_bytes(int32_t C);
+/* Plane bookkeeping of a D-sharded slab [N][D][rows_per_plane][C] (NULL = whole tensor owned and valid):
+ * statistics and the mean terms of the backward cover OWNED planes [own_lo, own_hi); planes outside
+ * [valid_lo, valid_hi) lie beyond the GLOBAL volume: they are the next conv's zero padding, so the forward
+ * writes zeros there and the backward treats their gradient as zero.  m_global = voxels of the global tensor
+ * per channel (the statistics' divisor after the caller's all-reduce of the sums). */
+typedef struct {
+    int64_t rows_per_plane;
+    int32_t D, own_lo, own_hi, valid_lo, valid_hi;
+    int64_t m_global;
+} mode_planes_t;
+
 int mode_bn_stats(const float* y, int64_t M, int32_t C, double* sums, void* stream);
 int mode_bn_finalize(const double* sums, int64_t M, int32_t C, const float* gamma, const float* beta, float eps,
                      float momentum, float* mean, float* invstd, float* scale, float* shift,
                      float* running_mean, float* running_var, void* stream);
 int mode_bn_apply_relu(const float* y, int64_t M, int32_t C, const float* scale, const float* shift, int32_t relu,
-                       float* out, void* out_f16, float f16_scale, void* stream);   /* f16_scale: host value */
+                       float* out, void* out_f16, float f16_scale, const mode_planes_t* planes_host, void* stream);
 int mode_bn_relu_bwd(const float* y, const float* dout, int64_t M, int32_t C, const float* gamma,
                      const float* beta, const float* mean, const float* invstd, float* dgamma, float* dbeta,
                      float* dy, void* dy_f16, float* dy_scale2, void* workspace, void* stream);
+/* The same in two halves, for D-sharded slabs: _reduce leaves the LOCAL sums {sum dz, sum dz*xhat} (double[2C])
+ * at the start of `workspace`; the caller all-reduces them across ranks; _apply finishes (dgamma/dbeta receive
+ * the sums found in the workspace; mean terms use planes->m_global). planes_host may be NULL. */
+int mode_bn_relu_bwd_reduce(const float* y, const float* dout, int64_t M, int32_t C, const float* gamma,
+                            const float* beta, const float* mean, const float* invstd,
+                            const mode_planes_t* planes_host, void* workspace, void* stream);
+int mode_bn_relu_bwd_apply(const float* y, const float* dout, int64_t M, int32_t C, const float* gamma,
+                           const float* beta, const float* mean, const float* invstd, float* dgamma, float* dbeta,
+                           float* dy, void* dy_f16, float* dy_scale2, const mode_planes_t* planes_host,
+                           void* workspace, void* stream);
 
 /* ---- operand staging -----------------------------------------------------------------------------------
  * fp32 -> fp16 (round to nearest even), value * scale * (scale_dev ? *scale_dev : 1); n elements. */
 int mode_cast_f16(const float* src, void* dst_f16, int64_t n, float scale, const float* scale_dev, void* stream);
 /* amax[0] = max(amax[0], max |src|) (amax must be zero-initialised by the caller; device scalar). */
 int mode_amax(const float* src, int64_t n, float* amax, void* stream);
+/* Same over k <= 8 tensors in one launch (srcs_host / counts_host are HOST arrays of device pointers / sizes). */
+int mode_amax_multi(const float* const* srcs_host, const int64_t* counts_host, int32_t k, float* amax, void* stream);
 /* scale2[0] = 2^floor(log2(target / amax[0])) (1 if amax is 0), scale2[1] = 1 / scale2[0]; all device. */
 int mode_f16_scale(const float* amax, float target, float* scale2, void* stream);
 

@@ -386,6 +386,19 @@ __global__ void __launch_bounds__(256) amax_kernel(const float* __restrict__ src
     if ((threadIdx.x & 31) == 0) atomicMax(reinterpret_cast<int*>(amax), __float_as_int(m));   // m >= 0
 }
 
+struct AmaxList { const float* p[8]; long long n[8]; };
+// blockIdx.y selects the tensor: one launch covers the five expert tensors of a MoDEConv layer
+__global__ void __launch_bounds__(256) amax_multi_kernel(AmaxList L, float* amax) {
+    const float* src = L.p[blockIdx.y];
+    const long long n = L.n[blockIdx.y];
+    float m = 0.f;
+    for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < n; i += (long long)gridDim.x * 256)
+        m = fmaxf(m, fabsf(src[i]));
+#pragma unroll
+    for (int s = 16; s > 0; s >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, s));
+    if ((threadIdx.x & 31) == 0 && m > 0.f) atomicMax(reinterpret_cast<int*>(amax), __float_as_int(m));
+}
+
 __global__ void f16_scale_kernel(const float* __restrict__ amax, float target, float* __restrict__ scale2) {
     float sc = 1.f;
     const float a = amax[0];
@@ -511,6 +524,22 @@ extern "C" int mode_amax(const float* src, int64_t n, float* amax, void* stream)
 extern "C" int mode_f16_scale(const float* amax, float target, float* scale2, void* stream) {
     if (!amax || !scale2 || !(target > 0.f)) MODE_FAIL("mode_f16_scale: bad arguments");
     f16_scale_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(amax, target, scale2);
+    MODE_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int mode_amax_multi(const float* const* srcs_host, const int64_t* counts_host, int32_t k, float* amax,
+                               void* stream) {
+    if (!srcs_host || !counts_host || !amax || k <= 0 || k > 8) MODE_FAIL("mode_amax_multi: bad arguments (k=%d)", k);
+    AmaxList L;
+    int64_t nmax = 0;
+    for (int i = 0; i < 8; ++i) {
+        L.p[i] = i < k ? srcs_host[i] : nullptr;
+        L.n[i] = i < k ? counts_host[i] : 0;
+        if (i < k && (!srcs_host[i] || counts_host[i] <= 0)) MODE_FAIL("mode_amax_multi: null / empty tensor %d", i);
+        if (i < k) nmax = max(nmax, counts_host[i]);
+    }
+    amax_multi_kernel<<<dim3(stream_grid(nmax, 256 * 8), k), 256, 0, (cudaStream_t)stream>>>(L, amax);
     MODE_LAUNCH_CHECK();
     return 0;
 }

@@ -178,82 +178,61 @@ conv3d_umma_kernel(const __grid_constant__ CUtensorMap xmap, const ConvParams P)
         }
     } else if (warp == 1) {
         // ===================== MMA issuer =====================
-        // One thread issues every tcgen05.mma of the CTA, so its loop must stay far below the ~93-cycle MMA
-        // floor: everything that depends only on (tile, chunk, plane) -- ring slot address, accumulator column,
-        // instruction descriptor (N varies with the number of output planes the input plane feeds), weight block
-        // offset -- is tabulated once per chunk in shared memory; the inner loop is one 16-byte table load, two
-        // 32-bit adds and two MMAs per plane.  No divisions: ring/stage indices are wrapped counters.
-        if (lane == 0) {
-            uint4* tab = reinterpret_cast<uint4*>(smem + L.bar_off + 512);   // [MAX_RING] entries
-            const uint32_t hi_a = ((cu::BW * cu::ROWB) >> 4) | (1u << 14) | ((uint32_t)SWZ_64B << 29);
-            const uint32_t hi_b = (512u >> 4) | (1u << 14) | ((uint32_t)SWZ_64B << 29);
-            const uint32_t lbo_lo = 1u << 16;                                    // LBO field = 16 B (unused for K-major)
-            uint32_t pslot = 0, puse = 0;        // ring slot / use count of the NEXT plane in sequence
-            uint32_t wst = 0, wuse = 0;          // weight stage / use count
-            TileWalker tw_(P);
-            int n, h0, w0, d0, td;
-            for (int it = 0; tw_.next(n, h0, w0, d0, td); ++it) {
-                int pmin, pmax;
-                plane_range(d0, td, P.D, pmin, pmax);
-                const int nplanes = pmax - pmin + 1;
-                const int buf = it & 1;
-                const uint32_t acc_base = tmem + buf * 256;
-                // accumulators of this buffer have been drained and re-zeroed by the epilogue
-                if (!mbar_wait(tmem_empty + 8 * buf, (it >> 1) & 1)) { atomicExch(P.error_flag, 3); return; }
-                tc_fence_after();
-                for (int c = 0; c < nchunk; ++c) {
-                    // ---- per-chunk plane table
+        // The whole warp runs this loop with warp-uniform values (one lane is elected inside the MMA / commit asm):
+        // the issue loop must stay well under the ~93-cycle MMA floor, so per plane it is a handful of uniform
+        // integer ops -- ring slot address, accumulator column, N-dependent instruction descriptor, weight block
+        // offset -- and two MMAs (the two 16-channel K-steps of the 32-channel chunk).  No divisions.
+        const uint32_t hi_a = ((cu::BW * cu::ROWB) >> 4) | (1u << 14) | ((uint32_t)SWZ_64B << 29);
+        const uint32_t hi_b = (512u >> 4) | (1u << 14) | ((uint32_t)SWZ_64B << 29);
+        const uint32_t lbo_lo = 1u << 16;                                    // LBO field = 16 B (unused for K-major)
+        const uint32_t a_ring16 = ((base + L.plane_off) >> 4) | lbo_lo;
+        const uint32_t w_ring16 = ((base + L.w_off) >> 4) | lbo_lo;
+        const uint32_t plane16 = cu::PLANE_BYTES >> 4, blk16 = blk_bytes >> 4, wst16 = wst_bytes >> 4;
+        const uint32_t idesc0 = make_idesc(FMT_F16, 128, 0, 0, 0);
+        const uint32_t nt8 = (uint32_t)P.Nt >> 3;
+        uint32_t pslot = 0, puse = 0;        // ring slot / use count of the NEXT plane in sequence
+        uint32_t wst = 0, wuse = 0;          // weight stage / use count
+        TileWalker tw_(P);
+        int n, h0, w0, d0, td;
+        for (int it = 0; tw_.next(n, h0, w0, d0, td); ++it) {
+            int pmin, pmax;
+            plane_range(d0, td, P.D, pmin, pmax);
+            const int nplanes = pmax - pmin + 1;
+            const int buf = it & 1;
+            const uint32_t acc_base = tmem + buf * 256;
+            // accumulators of this buffer have been drained and re-zeroed by the epilogue
+            if (!mbar_wait(tmem_empty + 8 * buf, (it >> 1) & 1)) { atomicExch(P.error_flag, 3); return; }
+            tc_fence_after();
+            for (int c = 0; c < nchunk; ++c) {
+                for (int t = 0; t < 25; ++t) {
+                    const int kh = t / 5, kw = t - kh * 5;
+                    if (!mbar_wait(w_full + 8 * wst, wuse & 1)) { atomicExch(P.error_flag, 5); return; }
+                    tc_fence_after();
+                    const uint32_t wb_lo = w_ring16 + wst * wst16;
+                    const uint32_t a_tap = ((kh * cu::BW + kw) * cu::ROWB) >> 4;
                     uint32_t slot = pslot, use = puse;
-                    for (int i = 0; i < nplanes; ++i) {
-                        const int p = pmin + i;
+                    for (int p = pmin; p <= pmax; ++p) {
+                        if (t == 0) {      // first touch of the plane in this chunk: its TMA must have landed
+                            if (!mbar_wait(plane_full + 8 * slot, use & 1)) { atomicExch(P.error_flag, 4); return; }
+                            tc_fence_after();
+                        }
                         const int qlo = max(0, p - 4), qhi = min(td - 1, p);
-                        uint4 e;
-                        e.x = ((base + L.plane_off + slot * cu::PLANE_BYTES) >> 4) | lbo_lo;          // A desc lo (tap 0)
-                        e.y = ((uint32_t)(4 - (p - qlo)) * blk_bytes) >> 4;                            // B block offset
-                        e.z = acc_base + qlo * P.Nt;                                                   // D column
-                        e.w = make_idesc(FMT_F16, 128, (uint32_t)(qhi - qlo + 1) * P.Nt, 0, 0);
-                        tab[i] = e;
+                        const uint32_t a_lo = a_ring16 + slot * plane16 + a_tap;
+                        const uint32_t b_lo = wb_lo + (uint32_t)(4 - (p - qlo)) * blk16;
+                        const uint32_t dcol = acc_base + (uint32_t)qlo * P.Nt;
+                        const uint32_t idesc = idesc0 | (((uint32_t)(qhi - qlo + 1) * nt8) << 17);
+                        mma_f16_ss_elect(dcol, a_lo, hi_a, b_lo, hi_b, idesc);
+                        mma_f16_ss_elect(dcol, a_lo + 2, hi_a, b_lo + 2, hi_b, idesc);
+                        if (t == 24) mma_commit_elect(plane_empty + 8 * slot);   // last touch: free the ring slot
                         if (++slot == (uint32_t)P.ring) { slot = 0; ++use; }
                     }
-                    for (int t = 0; t < 25; ++t) {
-                        const int kh = t / 5, kw = t - kh * 5;
-                        if (!mbar_wait(w_full + 8 * wst, wuse & 1)) { atomicExch(P.error_flag, 5); return; }
-                        tc_fence_after();
-                        const uint32_t wb_lo = ((base + L.w_off + wst * wst_bytes) >> 4) | lbo_lo;
-                        const uint32_t a_tap = ((kh * cu::BW + kw) * cu::ROWB) >> 4;
-                        if (t > 0 && t < 24) {
-#pragma unroll 4
-                            for (int i = 0; i < nplanes; ++i) {
-                                const uint4 e = tab[i];
-                                const uint32_t a_lo = e.x + a_tap, b_lo = wb_lo + e.y;
-                                mma_f16_ss(e.z, ((uint64_t)hi_a << 32) | a_lo, ((uint64_t)hi_b << 32) | b_lo, e.w, 1u);
-                                mma_f16_ss(e.z, ((uint64_t)hi_a << 32) | (a_lo + 2), ((uint64_t)hi_b << 32) | (b_lo + 2), e.w, 1u);
-                            }
-                        } else {
-                            // t == 0: first touch of each plane -> wait for its TMA (planes land in sequence order);
-                            // t == 24: last touch -> release the ring slot as soon as its MMAs retire
-                            slot = pslot; use = puse;
-                            for (int i = 0; i < nplanes; ++i) {
-                                if (t == 0) {
-                                    if (!mbar_wait(plane_full + 8 * slot, use & 1)) { atomicExch(P.error_flag, 4); return; }
-                                    tc_fence_after();
-                                }
-                                const uint4 e = tab[i];
-                                const uint32_t a_lo = e.x + a_tap, b_lo = wb_lo + e.y;
-                                mma_f16_ss(e.z, ((uint64_t)hi_a << 32) | a_lo, ((uint64_t)hi_b << 32) | b_lo, e.w, 1u);
-                                mma_f16_ss(e.z, ((uint64_t)hi_a << 32) | (a_lo + 2), ((uint64_t)hi_b << 32) | (b_lo + 2), e.w, 1u);
-                                if (t == 24) mma_commit(plane_empty + 8 * slot);
-                                if (++slot == (uint32_t)P.ring) { slot = 0; ++use; }
-                            }
-                        }
-                        mma_commit(w_empty + 8 * wst);
-                        if (++wst == (uint32_t)P.wstages) { wst = 0; ++wuse; }
-                    }
-                    pslot += nplanes;
-                    if (pslot >= (uint32_t)P.ring) { pslot -= P.ring; ++puse; }
+                    mma_commit_elect(w_empty + 8 * wst);
+                    if (++wst == (uint32_t)P.wstages) { wst = 0; ++wuse; }
                 }
-                mma_commit(tmem_full + 8 * buf);
+                pslot += nplanes;
+                if (pslot >= (uint32_t)P.ring) { pslot -= P.ring; ++puse; }
             }
+            mma_commit_elect(tmem_full + 8 * buf);
         }
     } else if (warp >= 4) {
         // ===================== epilogue =====================

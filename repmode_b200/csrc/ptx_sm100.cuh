@@ -152,6 +152,37 @@ __device__ __forceinline__ void mma_tf32_ss(uint32_t d_tmem, uint64_t adesc, uin
         : "r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
         : "memory");
 }
+// Warp-uniform variants: executed by ALL lanes of a converged warp with identical (uniform) operands; one lane
+// is elected inside the asm.  Keeping the C++ control flow uniform lets ptxas hold descriptors in uniform
+// registers instead of the per-thread ELECT / R2UR.BROADCAST loop it emits inside an `if (lane == 0)` region.
+__device__ __forceinline__ void mma_f16_ss_elect(uint32_t d_tmem, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo,
+                                                 uint32_t b_hi, uint32_t idesc) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred q, one;\n\t"
+        ".reg .b64 da, db;\n\t"
+        "mov.b64 da, {%1, %2};\n\t"
+        "mov.b64 db, {%3, %4};\n\t"
+        "setp.eq.u32 one, 1, 1;\n\t"
+        "elect.sync _|q, 0xffffffff;\n\t"
+        "@q tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, one;\n\t"
+        "}\n"
+        :
+        : "r"(d_tmem), "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc)
+        : "memory");
+}
+__device__ __forceinline__ void mma_commit_elect(uint32_t bar) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred q;\n\t"
+        "elect.sync _|q, 0xffffffff;\n\t"
+        "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t"
+        "}\n"
+        :
+        : "r"(bar)
+        : "memory");
+}
+
 // Arrive on an mbarrier once all previously issued tcgen05.mma of this thread have completed.
 __device__ __forceinline__ void mma_commit(uint32_t bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar)

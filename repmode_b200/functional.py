@@ -108,8 +108,13 @@ def f16_scale_of(tensors, target):
     lib = _lib.load()
     dev = tensors[0].device
     amax = torch.zeros(1, dtype=torch.float32, device=dev)
-    for t in tensors:
-        _lib.check(lib.mode_amax(_p(t), t.numel(), _p(amax), _stream()), "mode_amax")
+    if len(tensors) == 1:
+        _lib.check(lib.mode_amax(_p(tensors[0]), tensors[0].numel(), _p(amax), _stream()), "mode_amax")
+    else:
+        k = len(tensors)
+        ptrs = (ctypes.c_void_p * k)(*[t.data_ptr() for t in tensors])
+        cnts = (ctypes.c_int64 * k)(*[t.numel() for t in tensors])
+        _lib.check(lib.mode_amax_multi(ptrs, cnts, k, _p(amax), _stream()), "mode_amax_multi")
     s2 = torch.empty(2, dtype=torch.float32, device=dev)
     _lib.check(lib.mode_f16_scale(_p(amax), float(target), _p(s2), _stream()), "mode_f16_scale")
     return s2

@@ -12,6 +12,24 @@ namespace mode {
 constexpr int BN_THREADS = 256;
 constexpr int BN_MAXC = 1024;
 
+// D-sharded slab bookkeeping (mode_planes_t by value); kind(row): 0 = outside the global volume, 1 = halo copy,
+// 2 = owned
+struct Planes {
+    long long rows_per_plane;
+    int D, own_lo, own_hi, valid_lo, valid_hi;
+    __device__ __forceinline__ int kind(long long row) const {
+        const int d = (int)((row / rows_per_plane) % D);
+        if (d < valid_lo || d >= valid_hi) return 0;
+        return (d >= own_lo && d < own_hi) ? 2 : 1;
+    }
+};
+static Planes to_planes(const mode_planes_t* p) {
+    Planes q;
+    q.rows_per_plane = p->rows_per_plane; q.D = p->D; q.own_lo = p->own_lo; q.own_hi = p->own_hi;
+    q.valid_lo = p->valid_lo; q.valid_hi = p->valid_hi;
+    return q;
+}
+
 
 // Deterministic in-block reduction of per-thread 4-channel partials: thread t owns channels 4*(t % vpr) + j.
 // Partials go to shared memory once; thread c < 2C then sums the 256/vpr threads that share its channel
@@ -100,11 +118,12 @@ __global__ void bn_finalize_kernel(const double* __restrict__ sums, int64_t M, i
 }
 
 // ---- apply: out = relu(y*scale + shift), optional fp16 copy ----------------------------------------------
+template <bool PLANES>
 __global__ void __launch_bounds__(BN_THREADS) bn_apply_kernel(const float* __restrict__ y, int64_t total, int C,
                                                               const float* __restrict__ scale,
                                                               const float* __restrict__ shift, int relu,
                                                               float* __restrict__ out, __half* __restrict__ out16,
-                                                              float f16_scale) {
+                                                              float f16_scale, Planes pl) {
     __shared__ float ssc[BN_MAXC], ssh[BN_MAXC];
     for (int i = threadIdx.x; i < C; i += BN_THREADS) { ssc[i] = scale[i]; ssh[i] = shift[i]; }
     __syncthreads();
@@ -115,6 +134,7 @@ __global__ void __launch_bounds__(BN_THREADS) bn_apply_kernel(const float* __res
         v.x = fmaf(v.x, ssc[c], ssh[c]); v.y = fmaf(v.y, ssc[c + 1], ssh[c + 1]);
         v.z = fmaf(v.z, ssc[c + 2], ssh[c + 2]); v.w = fmaf(v.w, ssc[c + 3], ssh[c + 3]);
         if (relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
+        if (PLANES && pl.kind((i * 4) / C) == 0) v = make_float4(0.f, 0.f, 0.f, 0.f);   // beyond the global volume
         if (out) *reinterpret_cast<float4*>(out + i * 4) = v;
         if (out16) {
             __half2 a = __floats2half2_rn(v.x * f16_scale, v.y * f16_scale);
@@ -178,14 +198,16 @@ __global__ void __launch_bounds__(BN_THREADS) bn_bwd_reduce_kernel(const float* 
     if ((threadIdx.x & 31) == 0) { atomicMax(mx + c, __float_as_int(mdz)); atomicMax(mx + C + c, __float_as_int(mxh)); }
 }
 
-// vectorised pass 1 for C % 4 == 0 (same structure as bn_stats_kernel); two rows in flight per thread
+// vectorised pass 1 for C % 4 == 0 (same structure as bn_stats_kernel); four rows in flight per thread
+template <bool PLANES>
 __global__ void __launch_bounds__(BN_THREADS) bn_bwd_reduce_vec_kernel(const float* __restrict__ y,
                                                                        const float* __restrict__ dout, int64_t M,
                                                                        int C, const float* __restrict__ gamma,
                                                                        const float* __restrict__ beta,
                                                                        const float* __restrict__ mean,
                                                                        const float* __restrict__ invstd,
-                                                                       double* __restrict__ red, int* __restrict__ mx) {
+                                                                       double* __restrict__ red, int* __restrict__ mx,
+                                                                       Planes pl) {
     const int vpr = C >> 2;
     const int rows_per_iter = BN_THREADS / vpr;
     const int lane_v = threadIdx.x % vpr, lane_r = threadIdx.x / vpr;
@@ -211,7 +233,7 @@ __global__ void __launch_bounds__(BN_THREADS) bn_bwd_reduce_vec_kernel(const flo
         }
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
-            if (r + u * stride < M) {
+            if (r + u * stride < M && (!PLANES || pl.kind(r + u * stride) != 0)) {
                 const float ya[4] = {yv[u].x, yv[u].y, yv[u].z, yv[u].w}, da[4] = {dv[u].x, dv[u].y, dv[u].z, dv[u].w};
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
@@ -245,7 +267,7 @@ __global__ void __launch_bounds__(BN_THREADS) bn_bwd_reduce_vec_kernel(const flo
 
 // power-of-two fp16 scale for dy from the per-channel bound
 //   |dy_c| <= |gamma_c*invstd_c| * (max|dz|_c + |sum_dz_c|/M + max|xhat|_c * |sum_dzxhat_c|/M)
-__global__ void bn_bwd_scale_kernel(const double* __restrict__ red, const int* __restrict__ mx, int64_t M, int C,
+__global__ void bn_bwd_scale_kernel(const double* __restrict__ red, const int* __restrict__ mx, long long M, int C,
                                     const float* __restrict__ gamma, const float* __restrict__ invstd, float target,
                                     float* __restrict__ scale2) {
     float b = 0.f;
@@ -275,6 +297,7 @@ __global__ void bn_bwd_scale_kernel(const double* __restrict__ red, const int* _
 }
 
 // pass 2, vectorised (C % 4 == 0): float4 in, float4 and/or 4 x fp16 out
+template <bool PLANES>
 __global__ void __launch_bounds__(BN_THREADS) bn_bwd_apply_vec_kernel(const float* __restrict__ y,
                                                                       const float* __restrict__ dout, int64_t M, int C,
                                                                       const float* __restrict__ gamma,
@@ -284,14 +307,15 @@ __global__ void __launch_bounds__(BN_THREADS) bn_bwd_apply_vec_kernel(const floa
                                                                       const double* __restrict__ red,
                                                                       float* __restrict__ dgamma, float* __restrict__ dbeta,
                                                                       float* __restrict__ dy, __half* __restrict__ dy16,
-                                                                      const float* __restrict__ scale2) {
+                                                                      const float* __restrict__ scale2, Planes pl,
+                                                                      long long m_div) {
     const float f16_scale = (dy16 != nullptr && scale2 != nullptr) ? scale2[0] : 1.f;
     __shared__ float smu[BN_MAXC], sis[BN_MAXC], sga[BN_MAXC], sbe[BN_MAXC], sa[BN_MAXC], sb[BN_MAXC];
     for (int c = threadIdx.x; c < C; c += BN_THREADS) {
         smu[c] = mean[c]; sis[c] = invstd[c];
         sga[c] = gamma ? gamma[c] : 1.f; sbe[c] = beta ? beta[c] : 0.f;
-        sa[c] = (float)(red[c] / (double)M);
-        sb[c] = (float)(red[C + c] / (double)M);
+        sa[c] = (float)(red[c] / (double)m_div);
+        sb[c] = (float)(red[C + c] / (double)m_div);
         if (blockIdx.x == 0) {
             if (dbeta) dbeta[c] = (float)red[c];
             if (dgamma) dgamma[c] = (float)red[C + c];
@@ -305,11 +329,13 @@ __global__ void __launch_bounds__(BN_THREADS) bn_bwd_apply_vec_kernel(const floa
         const float4 dv = *reinterpret_cast<const float4*>(dout + i * 4);
         const float ya[4] = {yv.x, yv.y, yv.z, yv.w}, da[4] = {dv.x, dv.y, dv.z, dv.w};
         float v[4];
+        const int kind = PLANES ? pl.kind((i * 4) / C) : 2;   // 2 owned: full formula; 1 halo copy: no mean terms; 0: zero
+        const float own = kind == 2 ? 1.f : 0.f;
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
             const float xh = (ya[j] - smu[c + j]) * sis[c + j];
-            const float dz = fmaf(xh, sga[c + j], sbe[c + j]) > 0.f ? da[j] : 0.f;
-            v[j] = sga[c + j] * sis[c + j] * (dz - sa[c + j] - xh * sb[c + j]);
+            const float dz = (kind != 0 && fmaf(xh, sga[c + j], sbe[c + j]) > 0.f) ? da[j] : 0.f;
+            v[j] = sga[c + j] * sis[c + j] * (dz - own * (sa[c + j] + xh * sb[c + j]));
         }
         if (dy) *reinterpret_cast<float4*>(dy + i * 4) = make_float4(v[0], v[1], v[2], v[3]);
         if (dy16) {
@@ -446,32 +472,38 @@ extern "C" int mode_bn_finalize(const double* sums, int64_t M, int32_t C, const 
 }
 
 extern "C" int mode_bn_apply_relu(const float* y, int64_t M, int32_t C, const float* scale, const float* shift,
-                                  int32_t relu, float* out, void* out_f16, float f16_scale, void* stream) {
+                                  int32_t relu, float* out, void* out_f16, float f16_scale,
+                                  const mode_planes_t* planes, void* stream) {
     if (!y || !scale || !shift || (!out && !out_f16) || M <= 0 || C <= 0 || C > BN_MAXC)
         MODE_FAIL("mode_bn_apply_relu: bad arguments (C=%d)", C);
     cudaStream_t st = (cudaStream_t)stream;
     const int64_t total = M * C;
     const bool aligned = ((reinterpret_cast<uintptr_t>(y) | reinterpret_cast<uintptr_t>(out)) & 15) == 0 &&
                          (reinterpret_cast<uintptr_t>(out_f16) & 7) == 0;
-    if ((C & 3) == 0 && aligned)
-        bn_apply_kernel<<<stream_grid(total / 4, BN_THREADS * 4), BN_THREADS, 0, st>>>(y, total, C, scale, shift, relu,
-                                                                                      out, (__half*)out_f16, f16_scale);
-    else
+    if ((C & 3) == 0 && aligned) {
+        const int grid = stream_grid(total / 4, BN_THREADS * 4);
+        if (planes)
+            bn_apply_kernel<true><<<grid, BN_THREADS, 0, st>>>(y, total, C, scale, shift, relu, out, (__half*)out_f16,
+                                                               f16_scale, to_planes(planes));
+        else
+            bn_apply_kernel<false><<<grid, BN_THREADS, 0, st>>>(y, total, C, scale, shift, relu, out, (__half*)out_f16,
+                                                                f16_scale, Planes{});
+    } else {
+        if (planes) MODE_FAIL("mode_bn_apply_relu: plane ranges need C %% 4 == 0 and 16-byte aligned tensors");
         bn_apply_scalar_kernel<<<stream_grid(total, BN_THREADS * 4), BN_THREADS, 0, st>>>(
             y, total, C, scale, shift, relu, out, (__half*)out_f16, f16_scale);
+    }
     MODE_LAUNCH_CHECK();
     return 0;
 }
 
 extern "C" int64_t mode_bn_bwd_workspace_bytes(int32_t C) { return (int64_t)C * (2 * sizeof(double) + 2 * sizeof(int)); }
 
-extern "C" int mode_bn_relu_bwd(const float* y, const float* dout, int64_t M, int32_t C, const float* gamma,
-                                const float* beta, const float* mean, const float* invstd, float* dgamma,
-                                float* dbeta, float* dy, void* dy_f16, float* dy_scale2, void* workspace_v,
-                                void* stream) {
-    if (!y || !dout || !mean || !invstd || !workspace_v || (!dy && !dy_f16) || M <= 0 || C <= 0 || C > BN_MAXC)
-        MODE_FAIL("mode_bn_relu_bwd: bad arguments (C=%d)", C);
-    if (dy_f16 && !dy_scale2) MODE_FAIL("mode_bn_relu_bwd: dy_f16 needs dy_scale2");
+extern "C" int mode_bn_relu_bwd_reduce(const float* y, const float* dout, int64_t M, int32_t C, const float* gamma,
+                                       const float* beta, const float* mean, const float* invstd,
+                                       const mode_planes_t* planes, void* workspace_v, void* stream) {
+    if (!y || !dout || !mean || !invstd || !workspace_v || M <= 0 || C <= 0 || C > BN_MAXC)
+        MODE_FAIL("mode_bn_relu_bwd_reduce: bad arguments (C=%d)", C);
     cudaStream_t st = (cudaStream_t)stream;
     double* workspace = (double*)workspace_v;
     int* mx = (int*)(workspace + 2 * (size_t)C);
@@ -480,27 +512,66 @@ extern "C" int mode_bn_relu_bwd(const float* y, const float* dout, int64_t M, in
     const bool aligned = ((reinterpret_cast<uintptr_t>(y) | reinterpret_cast<uintptr_t>(dout)) & 15) == 0;
     if ((C & 3) == 0 && vpr <= BN_THREADS && BN_THREADS % vpr == 0 && aligned) {
         const int rpi = BN_THREADS / vpr;
-        bn_bwd_reduce_vec_kernel<<<stream_grid(M, rpi * 16), BN_THREADS, 0, st>>>(y, dout, M, C, gamma, beta, mean,
-                                                                                invstd, workspace, mx);
+        const int grid = stream_grid(M, rpi * 16);
+        if (planes)
+            bn_bwd_reduce_vec_kernel<true><<<grid, BN_THREADS, 0, st>>>(y, dout, M, C, gamma, beta, mean, invstd,
+                                                                        workspace, mx, to_planes(planes));
+        else
+            bn_bwd_reduce_vec_kernel<false><<<grid, BN_THREADS, 0, st>>>(y, dout, M, C, gamma, beta, mean, invstd,
+                                                                         workspace, mx, Planes{});
     } else {
+        if (planes) MODE_FAIL("mode_bn_relu_bwd_reduce: plane ranges need C %% 4 == 0 and 16-byte aligned tensors");
         const int gx = (int)max((int64_t)1, min(ceil_div(M, BN_THREADS * 8), (int64_t)64));
         bn_bwd_reduce_kernel<<<dim3(gx, C), BN_THREADS, 0, st>>>(y, dout, M, C, gamma, beta, mean, invstd, workspace, mx);
     }
     MODE_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int mode_bn_relu_bwd_apply(const float* y, const float* dout, int64_t M, int32_t C, const float* gamma,
+                                      const float* beta, const float* mean, const float* invstd, float* dgamma,
+                                      float* dbeta, float* dy, void* dy_f16, float* dy_scale2,
+                                      const mode_planes_t* planes, void* workspace_v, void* stream) {
+    if (!y || !dout || !mean || !invstd || !workspace_v || (!dy && !dy_f16) || M <= 0 || C <= 0 || C > BN_MAXC)
+        MODE_FAIL("mode_bn_relu_bwd_apply: bad arguments (C=%d)", C);
+    if (dy_f16 && !dy_scale2) MODE_FAIL("mode_bn_relu_bwd_apply: dy_f16 needs dy_scale2");
+    cudaStream_t st = (cudaStream_t)stream;
+    double* workspace = (double*)workspace_v;
+    int* mx = (int*)(workspace + 2 * (size_t)C);
+    const long long m_div = planes ? (long long)planes->m_global : (long long)M;
     if (dy_f16) {
-        bn_bwd_scale_kernel<<<1, 256, 0, st>>>(workspace, mx, M, C, gamma, invstd, 8192.f, dy_scale2);
+        bn_bwd_scale_kernel<<<1, 256, 0, st>>>(workspace, mx, m_div, C, gamma, invstd, 8192.f, dy_scale2);
         MODE_LAUNCH_CHECK();
     }
+    const bool aligned = ((reinterpret_cast<uintptr_t>(y) | reinterpret_cast<uintptr_t>(dout)) & 15) == 0;
     const bool vec_ok = (C & 3) == 0 && aligned && ((reinterpret_cast<uintptr_t>(dy) & 15) == 0) &&
                         ((reinterpret_cast<uintptr_t>(dy_f16) & 7) == 0);
-    if (vec_ok)
-        bn_bwd_apply_vec_kernel<<<stream_grid(M * C / 4, BN_THREADS * 4), BN_THREADS, 0, st>>>(
-            y, dout, M, C, gamma, beta, mean, invstd, workspace, dgamma, dbeta, dy, (__half*)dy_f16, dy_scale2);
-    else
+    if (vec_ok) {
+        const int grid = stream_grid(M * C / 4, BN_THREADS * 4);
+        if (planes)
+            bn_bwd_apply_vec_kernel<true><<<grid, BN_THREADS, 0, st>>>(y, dout, M, C, gamma, beta, mean, invstd, workspace,
+                                                                       dgamma, dbeta, dy, (__half*)dy_f16, dy_scale2,
+                                                                       to_planes(planes), m_div);
+        else
+            bn_bwd_apply_vec_kernel<false><<<grid, BN_THREADS, 0, st>>>(y, dout, M, C, gamma, beta, mean, invstd,
+                                                                        workspace, dgamma, dbeta, dy, (__half*)dy_f16,
+                                                                        dy_scale2, Planes{}, m_div);
+    } else {
+        if (planes) MODE_FAIL("mode_bn_relu_bwd_apply: plane ranges need C %% 4 == 0 and 16-byte aligned tensors");
         bn_bwd_apply_kernel<<<stream_grid(M * C, BN_THREADS * 8), BN_THREADS, 0, st>>>(
             y, dout, M, C, gamma, beta, mean, invstd, workspace, dgamma, dbeta, dy, (__half*)dy_f16, dy_scale2);
+    }
     MODE_LAUNCH_CHECK();
     return 0;
+}
+
+extern "C" int mode_bn_relu_bwd(const float* y, const float* dout, int64_t M, int32_t C, const float* gamma,
+                                const float* beta, const float* mean, const float* invstd, float* dgamma,
+                                float* dbeta, float* dy, void* dy_f16, float* dy_scale2, void* workspace_v,
+                                void* stream) {
+    if (mode_bn_relu_bwd_reduce(y, dout, M, C, gamma, beta, mean, invstd, nullptr, workspace_v, stream) != 0) return -1;
+    return mode_bn_relu_bwd_apply(y, dout, M, C, gamma, beta, mean, invstd, dgamma, dbeta, dy, dy_f16, dy_scale2,
+                                  nullptr, workspace_v, stream);
 }
 
 extern "C" int mode_cast_f16(const float* src, void* dst_f16, int64_t n, float scale, const float* scale_dev,

@@ -20,7 +20,7 @@ __global__ void __launch_bounds__(256) conv3d_simt_kernel(const float* __restric
                                                           const int32_t* __restrict__ sample_u,
                                                           float* __restrict__ y, int D, int H, int W, int K, int Nout,
                                                           float out_scale, const float* __restrict__ out_scale_dev,
-                                                          double* __restrict__ bn_sums) {
+                                                          double* __restrict__ bn_sums, int stat_lo, int stat_hi) {
     __shared__ float xs[KC8 * XPLANE];
     __shared__ __align__(16) float ws[25 * KC8 * 32];
     const int tiles_w = (W + TW - 1) / TW;
@@ -117,7 +117,7 @@ __global__ void __launch_bounds__(256) conv3d_simt_kernel(const float* __restric
             }
         }
     }
-    if (bn_sums != nullptr) {   // warp = 32 voxels-threads of one channel group
+    if (bn_sums != nullptr && d >= stat_lo && d < stat_hi) {   // warp = 32 voxels-threads of one channel group
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
 #pragma unroll
@@ -195,12 +195,13 @@ __global__ void __launch_bounds__(256) wgrad_simt_kernel(const float* __restrict
 }
 
 int conv3d_simt(const float* x, const float* w, const int32_t* sample_u, float* y, int N, int D, int H, int W, int K,
-                int Nout, float out_scale, const float* out_scale_dev, double* bn_sums, cudaStream_t st) {
+                int Nout, float out_scale, const float* out_scale_dev, double* bn_sums, int stat_lo, int stat_hi,
+                cudaStream_t st) {
     const int tiles = (int)(ceil_div(H, TH) * ceil_div(W, TW));
     const int64_t gz = (int64_t)N * ceil_div(Nout, 32);
     if (D > 65535 || gz > 65535) MODE_FAIL("conv3d_simt: grid too large (D=%d, N*ob=%lld)", D, (long long)gz);
     conv3d_simt_kernel<<<dim3(tiles, D, (unsigned)gz), 256, 0, st>>>(x, w, sample_u, y, D, H, W, K, Nout, out_scale,
-                                                                      out_scale_dev, bn_sums);
+                                                                      out_scale_dev, bn_sums, stat_lo, stat_hi);
     MODE_LAUNCH_CHECK();
     return 0;
 }

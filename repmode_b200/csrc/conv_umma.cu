@@ -49,6 +49,7 @@ struct ConvParams {
     float out_scale;
     int N, D, H, W, K, Nout;     // Nout = total output channels (row stride of y / rows per weight block)
     int n0, Nt;                  // this launch computes channels [n0, n0+Nt)
+    int stat_lo, stat_hi;        // BatchNorm sums cover output planes [stat_lo, stat_hi) only (owned planes of a slab)
     int TD, ring, wstages;
     int tiles_w, tiles_h;
     int64_t units;               // N * tiles_h * tiles_w * D plane-patches, split evenly over the CTAs
@@ -273,7 +274,7 @@ conv3d_umma_kernel(const __grid_constant__ CUtensorMap xmap, const ConvParams P)
 #pragma unroll
                         for (int j = 0; j < 32; j += 4)
                             *reinterpret_cast<float4*>(dst + cc + j) = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
-                        if (P.bn_sums != nullptr) {
+                        if (P.bn_sums != nullptr && d0 + q >= P.stat_lo && d0 + q < P.stat_hi) {
                             float g[32];
 #pragma unroll
                             for (int j = 0; j < 32; ++j) g[j] = f[j] * f[j];
@@ -353,7 +354,8 @@ bool conv3d_umma_supported(int D, int H, int W, int K, int Nout) {
 }
 
 int conv3d_umma(const __half* x, const __half* w, const int32_t* sample_u, float* y, int N, int D, int H, int W, int K,
-                int Nout, float out_scale, const float* out_scale_dev, double* bn_sums, cudaStream_t st) {
+                int Nout, float out_scale, const float* out_scale_dev, double* bn_sums, int stat_lo, int stat_hi,
+                cudaStream_t st) {
     if ((reinterpret_cast<uintptr_t>(x) & 15) || (reinterpret_cast<uintptr_t>(w) & 15) ||
         (reinterpret_cast<uintptr_t>(y) & 15))
         MODE_FAIL("conv3d_umma: pointers must be 16-byte aligned");
@@ -361,6 +363,7 @@ int conv3d_umma(const __half* x, const __half* w, const int32_t* sample_u, float
     P.w = w; P.sample_u = sample_u; P.y = y; P.bn_sums = bn_sums; P.out_scale_dev = out_scale_dev;
     P.out_scale = out_scale;
     P.N = N; P.D = D; P.H = H; P.W = W; P.K = K; P.Nout = Nout;
+    P.stat_lo = stat_lo; P.stat_hi = stat_hi;
     P.Nt = Nout <= 128 ? Nout : 128;                 // wider layers run in passes of 128 output channels
     P.TD = max(1, min(min(256 / P.Nt, 8), D));
     P.ring = P.TD + 4;

@@ -42,13 +42,15 @@ int* device_error_flag() {
 
 // conv_simt.cu
 int conv3d_simt(const float* x, const float* w, const int32_t* sample_u, float* y, int N, int D, int H, int W, int K,
-                int Nout, float out_scale, const float* out_scale_dev, double* bn_sums, cudaStream_t st);
+                int Nout, float out_scale, const float* out_scale_dev, double* bn_sums, int stat_lo, int stat_hi,
+                cudaStream_t st);
 int wgrad_simt(const float* x, const float* dy, float* dw, int N, int D, int H, int W, int Ci, int Co, float out_scale,
                const float* out_scale_dev, cudaStream_t st);
 // conv_umma.cu
 bool conv3d_umma_supported(int D, int H, int W, int K, int Nout);
 int conv3d_umma(const __half* x, const __half* w, const int32_t* sample_u, float* y, int N, int D, int H, int W, int K,
-                int Nout, float out_scale, const float* out_scale_dev, double* bn_sums, cudaStream_t st);
+                int Nout, float out_scale, const float* out_scale_dev, double* bn_sums, int stat_lo, int stat_hi,
+                cudaStream_t st);
 bool wgrad_umma_supported(int D, int H, int W, int Ci, int Co);
 int64_t wgrad_umma_workspace_bytes(int N, int D, int H, int W, int Ci, int Co);
 int wgrad_umma(const __half* x, const __half* dy, float* dw, int N, int D, int H, int W, int Ci, int Co,
@@ -90,20 +92,21 @@ extern "C" int mode_poll_error(int32_t* code_host) {
 
 extern "C" int mode_conv3d(const void* x, mode_dtype_t x_dtype, const void* w, const int32_t* sample_u, float* y,
                            int32_t N, int32_t D, int32_t H, int32_t W, int32_t K, int32_t Nout, float out_scale,
-                           const float* out_scale_dev, double* bn_sums, int32_t impl, void* stream) {
+                           const float* out_scale_dev, double* bn_sums, int32_t stat_d_lo, int32_t stat_d_hi,
+                           int32_t impl, void* stream) {
     if (!x || !w || !y) MODE_FAIL("mode_conv3d: null pointer");
     if (N <= 0 || D <= 0 || H <= 0 || W <= 0 || K <= 0 || Nout <= 0) MODE_FAIL("mode_conv3d: non-positive dimension");
     cudaStream_t st = (cudaStream_t)stream;
     if (impl == 0) impl = (x_dtype == MODE_F16) ? 2 : 1;
     if (impl == 1) {
         if (x_dtype != MODE_F32) MODE_FAIL("mode_conv3d: the SIMT path takes fp32 operands");
-        return conv3d_simt((const float*)x, (const float*)w, sample_u, y, N, D, H, W, K, Nout, out_scale, out_scale_dev, bn_sums, st);
+        return conv3d_simt((const float*)x, (const float*)w, sample_u, y, N, D, H, W, K, Nout, out_scale, out_scale_dev, bn_sums, stat_d_lo, stat_d_hi, st);
     }
     if (impl == 2) {
         if (x_dtype != MODE_F16) MODE_FAIL("mode_conv3d: the tcgen05 path takes fp16 operands");
         if (!conv3d_umma_supported(D, H, W, K, Nout))
             MODE_FAIL("mode_conv3d: shape D=%d H=%d W=%d K=%d Nout=%d not supported by the tcgen05 path", D, H, W, K, Nout);
-        return conv3d_umma((const __half*)x, (const __half*)w, sample_u, y, N, D, H, W, K, Nout, out_scale, out_scale_dev, bn_sums, st);
+        return conv3d_umma((const __half*)x, (const __half*)w, sample_u, y, N, D, H, W, K, Nout, out_scale, out_scale_dev, bn_sums, stat_d_lo, stat_d_hi, st);
     }
     MODE_FAIL("mode_conv3d: unknown impl %d", impl);
 }

@@ -84,12 +84,34 @@ def reparam_fwd(layer, gate_in, U, ci, co, dtype, want_dgrad, w_scale_dev=None):
     return g, w_fwd, w_dg
 
 
-def conv3d(x, dtype, w, sample_u, n, d, h, wd, k, nout, out_scale_dev=None, bn_sums=None, impl=0):
+def conv3d(x, dtype, w, sample_u, n, d, h, wd, k, nout, out_scale_dev=None, bn_sums=None, impl=0, stat_range=None):
     lib = _lib.load()
     y = torch.empty((n, d, h, wd, nout), dtype=torch.float32, device=x.device)
+    lo, hi = stat_range if stat_range is not None else (0, d)
     _lib.check(lib.mode_conv3d(_p(x), dtype, _p(w), _p(sample_u), _p(y), n, d, h, wd, k, nout, 1.0, _p(out_scale_dev),
-                               _p(bn_sums), impl, _stream()), "mode_conv3d")
+                               _p(bn_sums), lo, hi, impl, _stream()), "mode_conv3d")
     return y
+
+
+class ShardSpec:
+    """Plane bookkeeping of one D-sharded slab tensor [N, D_local_ext, H, W, C] (see mode_planes_t): owned planes
+    [own_lo, own_hi), planes inside the global volume [valid_lo, valid_hi), global voxel count per channel and the
+    process group whose ranks hold the other slabs."""
+
+    def __init__(self, own, valid, m_global, group=None):
+        self.own, self.valid, self.m_global, self.group = own, valid, int(m_global), group
+
+    def planes(self, rows_per_plane, d):
+        return _lib.ModePlanes(rows_per_plane, d, self.own[0], self.own[1], self.valid[0], self.valid[1], self.m_global)
+
+    def world(self):
+        import torch.distributed as dist
+        return dist.get_world_size(self.group) if dist.is_initialized() else 1
+
+    def all_reduce(self, t):
+        import torch.distributed as dist
+        if dist.is_initialized() and dist.get_world_size(self.group) > 1:
+            dist.all_reduce(t, group=self.group)
 
 
 def conv3d_wgrad(x, dy, dtype, n, d, h, wd, ci, co, out_scale_dev=None, impl=0):
@@ -138,7 +160,7 @@ class ModeConvFunction(torch.autograd.Function):
     @staticmethod
     @torch.amp.custom_fwd(device_type="cuda", cast_inputs=torch.float32)
     def forward(ctx, x, gate_in, k5, k3, k1, a3, a5, gate_w, gate_b, bn_w, bn_b, running_mean, running_var, training,
-                conv_type, precision):
+                conv_type, precision, shard=None):
         _require_cuda(x, gate_in, k5)
         lib = _lib.load()
         n, ci_x, d, h, wd = x.shape
@@ -173,8 +195,13 @@ class ModeConvFunction(torch.autograd.Function):
 
         bn_train = normal and training
         sums = torch.zeros(2 * co, dtype=torch.float64, device=dev) if bn_train else None
-        y = conv3d(x_op, dtype, w_fwd, sample_u, n, d, h, wd, ci, co, w_s2[1:2] if use_umma else None, sums)
+        y = conv3d(x_op, dtype, w_fwd, sample_u, n, d, h, wd, ci, co, w_s2[1:2] if use_umma else None, sums,
+                   stat_range=shard.own if shard is not None else None)
         m_rows = n * d * h * wd
+        planes = shard.planes(h * wd, d) if shard is not None else None
+        m_stat = shard.m_global if shard is not None else m_rows
+        if shard is not None and bn_train:
+            shard.all_reduce(sums)            # global statistics over owned voxels of every slab
         mean = invstd = None
         if normal:
             scale = torch.empty(co, dtype=torch.float32, device=dev)
@@ -182,7 +209,7 @@ class ModeConvFunction(torch.autograd.Function):
             if training:
                 mean = torch.empty(co, dtype=torch.float32, device=dev)
                 invstd = torch.empty(co, dtype=torch.float32, device=dev)
-                _lib.check(lib.mode_bn_finalize(_p(sums), m_rows, co, _p(bn_w), _p(bn_b), BN_EPS, BN_MOMENTUM, _p(mean),
+                _lib.check(lib.mode_bn_finalize(_p(sums), m_stat, co, _p(bn_w), _p(bn_b), BN_EPS, BN_MOMENTUM, _p(mean),
                                                 _p(invstd), _p(scale), _p(shift), _p(running_mean), _p(running_var),
                                                 _stream()), "mode_bn_finalize")
             else:
@@ -190,11 +217,13 @@ class ModeConvFunction(torch.autograd.Function):
                 scale = (bn_w * invstd_r).contiguous()
                 shift = (bn_b - running_mean * scale).contiguous()
             out = torch.empty_like(y)
-            _lib.check(lib.mode_bn_apply_relu(_p(y), m_rows, co, _p(scale), _p(shift), 1, _p(out), None, 1.0, _stream()),
+            _lib.check(lib.mode_bn_apply_relu(_p(y), m_rows, co, _p(scale), _p(shift), 1, _p(out), None, 1.0,
+                                              ctypes.byref(planes) if planes is not None else None, _stream()),
                        "mode_bn_apply_relu")
         else:
             out = y
         ctx.frozen_bn = normal and not training
+        ctx.shard = shard
         if ctx.frozen_bn:
             pass            # eval-mode forward is the supported use; backward through frozen BN raises below
         elif needs_dx or needs_dw or (normal and (ctx.needs_input_grad[9] or ctx.needs_input_grad[10])):
@@ -222,22 +251,34 @@ class ModeConvFunction(torch.autograd.Function):
         dy32 = None             # fp32 dy for the SIMT wgrad while UMMA_WGRAD is off
         wgrad_f32 = use_umma and not UMMA_WGRAD and needs_dw
         if normal:
+            shard = ctx.shard
             dgamma = torch.empty(co, dtype=torch.float32, device=dev)
             dbeta = torch.empty(co, dtype=torch.float32, device=dev)
             ws = torch.empty(int(lib.mode_bn_bwd_workspace_bytes(co)), dtype=torch.uint8, device=dev)
+            planes = shard.planes(h * wd, d) if shard is not None else None
+            pl = ctypes.byref(planes) if planes is not None else None
+            _lib.check(lib.mode_bn_relu_bwd_reduce(_p(y), _p(doutn), m_rows, co, _p(bn_w), _p(bn_b), _p(mean), _p(invstd),
+                                                   pl, _p(ws), _stream()), "mode_bn_relu_bwd_reduce")
+            if shard is not None:
+                shard.all_reduce(ws[:16 * co].view(torch.float64))      # {sum dz, sum dz*xhat} over every slab
+            dy_f32 = None
             if use_umma:
                 dy_op = torch.empty((n, d, h, wd, co), dtype=torch.float16, device=dev)
                 dy_s2 = torch.empty(2, dtype=torch.float32, device=dev)
                 if wgrad_f32:
                     dy32 = torch.empty((n, d, h, wd, co), dtype=torch.float32, device=dev)
-                _lib.check(lib.mode_bn_relu_bwd(_p(y), _p(doutn), m_rows, co, _p(bn_w), _p(bn_b), _p(mean), _p(invstd),
-                                                _p(dgamma), _p(dbeta), _p(dy32), _p(dy_op), _p(dy_s2), _p(ws), _stream()),
-                           "mode_bn_relu_bwd")
+                dy_f32 = dy32
             else:
                 dy_op = torch.empty((n, d, h, wd, co), dtype=torch.float32, device=dev)
-                _lib.check(lib.mode_bn_relu_bwd(_p(y), _p(doutn), m_rows, co, _p(bn_w), _p(bn_b), _p(mean), _p(invstd),
-                                                _p(dgamma), _p(dbeta), _p(dy_op), None, None, _p(ws), _stream()),
-                           "mode_bn_relu_bwd")
+                dy_f32 = dy_op
+            _lib.check(lib.mode_bn_relu_bwd_apply(_p(y), _p(doutn), m_rows, co, _p(bn_w), _p(bn_b), _p(mean), _p(invstd),
+                                                  _p(dgamma), _p(dbeta), _p(dy_f32), _p(dy_op) if use_umma else None,
+                                                  _p(dy_s2), pl, _p(ws), _stream()), "mode_bn_relu_bwd_apply")
+            if shard is not None and shard.world() > 1:
+                # dgamma/dbeta came out of the all-reduced sums: hand back this rank's share so that the usual
+                # data-parallel gradient sum reproduces them exactly once
+                dgamma /= shard.world()
+                dbeta /= shard.world()
         elif use_umma:
             dy_s2 = f16_scale_of([doutn], 8192.0)
             dy_op = cast_f16(doutn, dy_s2[0:1])
@@ -263,11 +304,12 @@ class ModeConvFunction(torch.autograd.Function):
             _lib.check(lib.mode_reparam_bwd(ctypes.byref(layer), _p(ids), _p(dense), U, _p(sample_u), n, _p(g), _p(d_weff),
                                             *[_p(o) for o in outs], _p(ws), _stream()), "mode_reparam_bwd")
             grads = outs
-        return (dx, None, *grads, dgamma, dbeta, None, None, None, None, None)
+        return (dx, None, *grads, dgamma, dbeta, None, None, None, None, None, None)
 
 
-def mode_conv(x, gate_in, params, bn, training, conv_type="normal", precision=None):
-    """Functional MoDEConv. params: (k5,k3,k1,a3,a5,gate_w,gate_b); bn: (weight,bias,running_mean,running_var) or None."""
+def mode_conv(x, gate_in, params, bn, training, conv_type="normal", precision=None, shard=None):
+    """Functional MoDEConv. params: (k5,k3,k1,a3,a5,gate_w,gate_b); bn: (weight,bias,running_mean,running_var) or None;
+    shard: ShardSpec when x is one D-slab (with halos) of a larger volume."""
     bn_w, bn_b, rm, rv = bn if bn is not None else (None, None, None, None)
     return ModeConvFunction.apply(x, gate_in, *params, bn_w, bn_b, rm, rv, training, conv_type,
-                                  precision or default_precision())
+                                  precision or default_precision(), shard)

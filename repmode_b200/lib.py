@@ -28,6 +28,12 @@ class ModeLayer(ctypes.Structure):
                 ("ci", ctypes.c_int32), ("co", ctypes.c_int32), ("num_tasks", ctypes.c_int32)]
 
 
+class ModePlanes(ctypes.Structure):
+    _fields_ = [("rows_per_plane", ctypes.c_int64), ("D", ctypes.c_int32), ("own_lo", ctypes.c_int32),
+                ("own_hi", ctypes.c_int32), ("valid_lo", ctypes.c_int32), ("valid_hi", ctypes.c_int32),
+                ("m_global", ctypes.c_int64)]
+
+
 class ModeCaps(ctypes.Structure):
     _fields_ = [("sm_major", ctypes.c_int32), ("sm_minor", ctypes.c_int32), ("sm_count", ctypes.c_int32),
                 ("smem_per_block_optin", ctypes.c_int32), ("tmem_columns", ctypes.c_int32),
@@ -70,13 +76,16 @@ SIGNATURES = {
     "mode_reparam_bwd": (ctypes.c_int, [ctypes.POINTER(ModeLayer), _vp, _vp, _i32, _vp, _i32, _vp, _vp, _vp, _vp, _vp,
                                         _vp, _vp, _vp, _vp, _vp, _vp]),
     "mode_conv3d": (ctypes.c_int, [_vp, ctypes.c_int, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _f32, _vp, _vp,
-                                   _i32, _vp]),
+                                   _i32, _i32, _i32, _vp]),
     "mode_conv3d_wgrad_workspace_bytes": (_i64, [_i32, _i32, _i32, _i32, _i32, _i32, _i32]),
     "mode_conv3d_wgrad": (ctypes.c_int, [_vp, _vp, ctypes.c_int, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _f32, _vp,
                                          _vp, _i32, _vp]),
     "mode_bn_stats": (ctypes.c_int, [_vp, _i64, _i32, _vp, _vp]),
     "mode_bn_finalize": (ctypes.c_int, [_vp, _i64, _i32, _vp, _vp, _f32, _f32, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
-    "mode_bn_apply_relu": (ctypes.c_int, [_vp, _i64, _i32, _vp, _vp, _i32, _vp, _vp, _f32, _vp]),
+    "mode_bn_apply_relu": (ctypes.c_int, [_vp, _i64, _i32, _vp, _vp, _i32, _vp, _vp, _f32, _vp, _vp]),
+    "mode_bn_relu_bwd_reduce": (ctypes.c_int, [_vp, _vp, _i64, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "mode_bn_relu_bwd_apply": (ctypes.c_int, [_vp, _vp, _i64, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
+                                              _vp, _vp]),
     "mode_bn_bwd_workspace_bytes": (_i64, [_i32]),
     "mode_bn_relu_bwd": (ctypes.c_int, [_vp, _vp, _i64, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "mode_cast_f16": (ctypes.c_int, [_vp, _vp, _i64, _f32, _vp, _vp]),

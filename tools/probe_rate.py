@@ -22,7 +22,7 @@ def rate(kind, N, mn_major, rowb, nacc, repeat=256, a_offs=None, b_offs=None, la
     mode = pu.SWZ_64B if rowb == 64 else pu.SWZ_128B
     esz = 2 if kind == 0 else 4
     chans = rowb // esz
-    rows = 1400
+    rows = 1024 if rowb == 64 else 512       # two regions (A, B) of 64 KB each
     if kind == 0:
         X = (0.01 * rng.standard_normal((rows, chans))).astype(np.float16)
     else:
@@ -86,13 +86,14 @@ def main():
     # B tile j = rows [Nj, Nj+N)  -> does the operand fetch cost depend on re-touching the same bytes?
     for kind, rowb in ((0, 64), (0, 128)):
         for N in (32, 96, 128, 160, 256):
-            nt = min(8, 1400 // max(N, 128))
+            nt = max(1, min(8, (1024 if rowb == 64 else 512) // max(N, 128)))
             rate(kind, N, False, rowb, 4 if N * 4 <= 512 else (2 if N * 2 <= 512 else 1),
                  a_offs=[(j % nt) * (128 * rowb >> 4) for j in range(8)],
                  b_offs=[(j % nt) * (N * rowb >> 4) for j in range(8)], label="distinct_tiles")
     # same A for consecutive MMAs, distinct B (A re-use), and vice versa
     for N in (128, 160):
-        rate(0, N, False, 64, 2, a_offs=[0] * 8, b_offs=[(j % 8) * (N * 64 >> 4) for j in range(8)], label="sameA_distinctB")
+        nb = 1024 // N
+        rate(0, N, False, 64, 2, a_offs=[0] * 8, b_offs=[(j % nb) * (N * 64 >> 4) for j in range(8)], label="sameA_distinctB")
         rate(0, N, False, 64, 2, a_offs=[(j % 8) * (128 * 64 >> 4) for j in range(8)], b_offs=[0] * 8, label="distinctA_sameB")
     os.makedirs("gpurun_out", exist_ok=True)
     with open("gpurun_out/probe_rate.json", "w") as f:

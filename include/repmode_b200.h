@@ -59,6 +59,10 @@ int mode_query(int device, mode_caps_t* caps_host);
 /* Synchronises the device and returns (and clears) the pipeline-timeout code a tcgen05 kernel raises
  * instead of hanging (0 = none). Diagnostics only; never called on the hot path. */
 int mode_poll_error(int32_t* code_host);
+/* Diagnostics: device buffer of int64[4 * 148] (or NULL to switch off) that the tcgen05 conv kernel's MMA warp
+ * fills per CTA with {total, wait accumulators, wait weights, wait planes} cycles. Process-global, not
+ * thread-safe, never set on the hot path. */
+int mode_debug_profile(void* buf);
 
 /* ---- K1: gate softmax + expert re-parameterisation --------------------------------------------------
  * Replaces: Linear + view + Softmax(dim=1) (RepMode.py:198-200) and MoDEConv.routing / trans_kernel

@@ -40,6 +40,9 @@ int* device_error_flag() {
     return flags[dev];
 }
 
+static long long* g_prof = nullptr;
+long long* debug_profile_buffer() { return g_prof; }
+
 // conv_simt.cu
 int conv3d_simt(const float* x, const float* w, const int32_t* sample_u, float* y, int N, int D, int H, int W, int K,
                 int Nout, float out_scale, const float* out_scale_dev, double* bn_sums, int stat_lo, int stat_hi,
@@ -87,6 +90,11 @@ extern "C" int mode_poll_error(int32_t* code_host) {
     MODE_CUDA(cudaMemcpy(&v, f, sizeof(int), cudaMemcpyDeviceToHost));
     *code_host = v;
     if (v != 0) MODE_CUDA(cudaMemset(f, 0, sizeof(int)));
+    return 0;
+}
+
+extern "C" int mode_debug_profile(void* buf) {
+    g_prof = (long long*)buf;
     return 0;
 }
 

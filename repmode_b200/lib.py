@@ -69,6 +69,7 @@ SIGNATURES = {
     "mode_launch_count": (_i64, []),
     "mode_query": (ctypes.c_int, [ctypes.c_int, ctypes.POINTER(ModeCaps)]),
     "mode_poll_error": (ctypes.c_int, [ctypes.POINTER(ctypes.c_int32)]),
+    "mode_debug_profile": (ctypes.c_int, [_vp]),
     "mode_reparam_fwd": (ctypes.c_int, [ctypes.POINTER(ModeLayer), _vp, _vp, _i32, _vp, _vp, _vp, ctypes.c_int, _f32,
                                         _vp, _vp]),
     "mode_packed_weight_elems": (_i64, [_i32, _i32]),

@@ -1,0 +1,49 @@
+"""Diagnostics: where the tcgen05 conv kernel's MMA-issuing warp spends its cycles (mode_debug_profile), on the
+headline 32->32 layer shape.  python tools/profile_conv.py  -> gpurun_out/conv_waits.json"""
+import ctypes
+import json
+import os
+import sys
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from repmode_b200 import functional as Fm, lib as L  # noqa: E402
+from tests.util import pack_weights  # noqa: E402
+import numpy as np  # noqa: E402
+
+
+def main():
+    lib = L.load()
+    out = []
+    for (n, d, h, w, k, nout) in [(1, 32, 128, 128, 32, 32), (1, 16, 64, 64, 64, 64), (4, 32, 128, 128, 32, 32)]:
+        x = torch.randn(n, d, h, w, k, device="cuda").half()
+        weff = (np.random.RandomState(0).randn(n, nout, k, 5, 5, 5) * 0.02).astype(np.float32)
+        w16 = torch.from_numpy(pack_weights(weff, half=True)).cuda()
+        su = torch.arange(n, dtype=torch.int32, device="cuda")
+        prof = torch.zeros(4 * 148, dtype=torch.int64, device="cuda")
+        for _ in range(3):
+            Fm.conv3d(x, L.MODE_F16, w16, su, n, d, h, w, k, nout)
+        lib.mode_debug_profile(ctypes.c_void_p(prof.data_ptr()))
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        Fm.conv3d(x, L.MODE_F16, w16, su, n, d, h, w, k, nout)
+        e1.record()
+        torch.cuda.synchronize()
+        lib.mode_debug_profile(None)
+        p = prof.view(148, 4).cpu().double()
+        flop = 2.0 * 125 * k * nout * n * d * h * w
+        r = {"shape": [n, d, h, w, k, nout], "ms": e0.elapsed_time(e1), "tflops": flop / e0.elapsed_time(e1) / 1e9,
+             "mma_warp_cycles_mean": float(p[:, 0].mean()), "mma_warp_cycles_max": float(p[:, 0].max()),
+             "wait_tmem_mean": float(p[:, 1].mean()), "wait_weights_mean": float(p[:, 2].mean()),
+             "wait_planes_mean": float(p[:, 3].mean()), "wait_planes_max": float(p[:, 3].max())}
+        out.append(r)
+        print(json.dumps(r), flush=True)
+    os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+    json.dump(out, open(os.path.join(ROOT, "gpurun_out", "conv_waits.json"), "w"), indent=1)
+
+
+if __name__ == "__main__":
+    main()

@@ -23,6 +23,8 @@
 // Roofline: tensor-pipe bound; algorithmic work 2*125*K*Nout FLOP per output voxel.
 #include <cuda.h>
 
+#include <algorithm>
+
 #include "common.cuh"
 #include "ptx_sm100.cuh"
 
@@ -52,19 +54,21 @@ struct ConvParams {
     int stat_lo, stat_hi;        // BatchNorm sums cover output planes [stat_lo, stat_hi) only (owned planes of a slab)
     int TD, ring, wstages;
     int tiles_w, tiles_h;
-    int64_t units;               // N * tiles_h * tiles_w * D plane-patches, split evenly over the CTAs
+    int64_t units;               // N * tiles_h * tiles_w * D plane-patches
+    int32_t bounds[160];         // CTA c owns units [bounds[c], bounds[c+1]) -- cost-balanced on the host
     int* error_flag;
     long long* prof;             // optional [grid][4] cycles: MMA-warp total / wait tmem_empty / wait weights / wait planes
 };
 
 // Work distribution: a "unit" is one 8x16 patch of one output d-plane, ordered (n, th, tw, d).  CTA c owns the
-// contiguous unit range [units*c/G, units*(c+1)/G) and walks it in tiles of up to TD consecutive planes of one
-// patch column, so every CTA gets the same number of planes (no 4th-wave tail of whole 8-plane tiles).
+// contiguous unit range [bounds[c], bounds[c+1]) and walks it in tiles of up to TD consecutive planes of one patch
+// column.  The host chooses the bounds so that every CTA gets the same ESTIMATED CYCLES (short tiles cost more per
+// plane: fewer output planes share each input plane), not the same number of planes.
 struct TileWalker {
     int64_t u, uend;
     int D, TD, tiles_h, tiles_w;
     __device__ TileWalker(const ConvParams& P)
-        : u(P.units * blockIdx.x / gridDim.x), uend(P.units * (blockIdx.x + 1) / gridDim.x), D(P.D), TD(P.TD),
+        : u(P.bounds[blockIdx.x]), uend(P.bounds[blockIdx.x + 1]), D(P.D), TD(P.TD),
           tiles_h(P.tiles_h), tiles_w(P.tiles_w) {}
     __device__ bool next(int& n, int& h0, int& w0, int& d0, int& td) {
         if (u >= uend) return false;
@@ -381,6 +385,69 @@ int make_act_map(CUtensorMap* map, const __half* x, int N, int D, int H, int W, 
     return 0;
 }
 
+
+// ---- cost-balanced unit partition (host) ---------------------------------------------------------------------
+// Estimated MMA-issue cycles of a tile of td output planes (measured SS-mode cost max(92.7, 41.7 + N/2) per MMA,
+// two K-steps x 25 taps per 32-channel chunk) plus a fixed per-tile overhead (pipeline refill, epilogue hand-off).
+static double tile_cost(int td, int d0, int D, int Nt, int nchunk) {
+    const int pmin = std::max(0, 2 - d0), pmax = std::min(td + 3, D + 1 - d0);
+    double c = 0;
+    for (int p = pmin; p <= pmax; ++p) {
+        const int nq = std::min(td - 1, p) - std::max(0, p - 4) + 1;
+        c += std::max(92.7, 41.7 + 0.5 * nq * Nt);
+    }
+    return c * 50.0 * nchunk + 3000.0;
+}
+
+// Walk units from `u` taking whole tiles while the accumulated cost stays <= budget; the last tile may be shortened.
+static int64_t take_units(int64_t u, int64_t units, int D, int TD, int Nt, int nchunk, double budget) {
+    double acc = 0;
+    while (u < units) {
+        const int d0 = (int)(u % D);
+        const int full = std::min(TD, D - d0);
+        const double cf = tile_cost(full, d0, D, Nt, nchunk);
+        if (acc + cf <= budget) { acc += cf; u += full; continue; }
+        int best = 0;                                   // largest shortened tile that still fits
+        for (int td = full - 1; td >= 1; --td)
+            if (acc + tile_cost(td, d0, D, Nt, nchunk) <= budget) { best = td; break; }
+        u += best;
+        break;
+    }
+    return u;
+}
+
+static void partition_units(int64_t units, int D, int TD, int Nt, int nchunk, int G, int32_t* bounds) {
+    double lo = 0, hi = 0;
+    for (int64_t u = 0; u < units;) {                   // upper bound: everything on one CTA
+        const int d0 = (int)(u % D), full = std::min(TD, D - d0);
+        hi += tile_cost(full, d0, D, Nt, nchunk);
+        u += full;
+    }
+    lo = hi / G;
+    auto feasible = [&](double budget) {
+        int64_t u = 0;
+        for (int c = 0; c < G && u < units; ++c) {
+            const int64_t nu = take_units(u, units, D, TD, Nt, nchunk, budget);
+            if (nu == u) return false;
+            u = nu;
+        }
+        return u >= units;
+    };
+    double h = lo;
+    while (!feasible(h)) h *= 1.05;
+    double l = lo;
+    for (int i = 0; i < 24; ++i) {
+        const double m = 0.5 * (l + h);
+        if (feasible(m)) h = m; else l = m;
+    }
+    int64_t u = 0;
+    for (int c = 0; c < G; ++c) {
+        bounds[c] = (int32_t)u;
+        u = std::min(units, take_units(u, units, D, TD, Nt, nchunk, h));
+    }
+    bounds[G] = (int32_t)units;
+}
+
 bool conv3d_umma_supported(int D, int H, int W, int K, int Nout) {
     (void)D;
     return K % 32 == 0 && K >= 32 && Nout % 32 == 0 && Nout >= 32 && H % cu::TH == 0 && W % cu::TW == 0 &&
@@ -410,6 +477,7 @@ int conv3d_umma(const __half* x, const __half* w, const int32_t* sample_u, float
     if (smem_bytes > 227 * 1024) MODE_FAIL("conv3d_umma: shared memory budget exceeded (%d B)", smem_bytes);
     P.tiles_w = W / cu::TW; P.tiles_h = H / cu::TH;
     P.units = (int64_t)N * P.tiles_h * P.tiles_w * D;
+    if (P.units > 0x7fffffff) MODE_FAIL("conv3d_umma: volume too large for 32-bit unit indices");
     const int64_t total = ceil_div(P.units, P.TD);          // upper bound on useful CTAs
     P.error_flag = device_error_flag();
     if (!P.error_flag) MODE_FAIL("conv3d_umma: could not allocate the device error flag");
@@ -418,7 +486,8 @@ int conv3d_umma(const __half* x, const __half* w, const int32_t* sample_u, float
     CUtensorMap xmap;
     if (make_act_map(&xmap, x, N, D, H, W, K, cu::BW, cu::BH) != 0) return -1;
     MODE_CUDA(cudaFuncSetAttribute(conv3d_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
-    const int grid = total < (int64_t)sm_count() ? (int)total : sm_count();
+    const int grid = total < (int64_t)sm_count() ? (int)total : std::min(sm_count(), 159);
+    partition_units(P.units, D, P.TD, P.Nt, K / 32, grid, P.bounds);
     for (int n0 = 0; n0 < Nout; n0 += P.Nt) {
         P.n0 = n0;
         conv3d_umma_kernel<<<grid, cu::THREADS, smem_bytes, st>>>(xmap, P);

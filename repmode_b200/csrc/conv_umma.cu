@@ -24,6 +24,10 @@
 #include <cuda.h>
 
 #include <algorithm>
+#include <array>
+#include <map>
+#include <mutex>
+#include <tuple>
 
 #include "common.cuh"
 #include "ptx_sm100.cuh"
@@ -416,7 +420,7 @@ static int64_t take_units(int64_t u, int64_t units, int D, int TD, int Nt, int n
     return u;
 }
 
-static void partition_units(int64_t units, int D, int TD, int Nt, int nchunk, int G, int32_t* bounds) {
+static void partition_units_uncached(int64_t units, int D, int TD, int Nt, int nchunk, int G, int32_t* bounds) {
     double lo = 0, hi = 0;
     for (int64_t u = 0; u < units;) {                   // upper bound: everything on one CTA
         const int d0 = (int)(u % D), full = std::min(TD, D - d0);
@@ -446,6 +450,27 @@ static void partition_units(int64_t units, int D, int TD, int Nt, int nchunk, in
         u = std::min(units, take_units(u, units, D, TD, Nt, nchunk, h));
     }
     bounds[G] = (int32_t)units;
+}
+
+// The partition costs ~0.4 ms of host time; it depends on the layer shape only, so it is computed once per shape.
+static void partition_units(int64_t units, int D, int TD, int Nt, int nchunk, int G, int32_t* bounds) {
+    struct Key {
+        int64_t units; int D, TD, Nt, nchunk, G;
+        bool operator<(const Key& o) const {
+            return std::tie(units, D, TD, Nt, nchunk, G) < std::tie(o.units, o.D, o.TD, o.Nt, o.nchunk, o.G);
+        }
+    };
+    static std::mutex mu;
+    static std::map<Key, std::array<int32_t, 160>> cache;
+    const Key key{units, D, TD, Nt, nchunk, G};
+    std::lock_guard<std::mutex> lock(mu);
+    auto it = cache.find(key);
+    if (it == cache.end()) {
+        std::array<int32_t, 160> b{};
+        partition_units_uncached(units, D, TD, Nt, nchunk, G, b.data());
+        it = cache.emplace(key, b).first;
+    }
+    std::copy(it->second.begin(), it->second.end(), bounds);
 }
 
 bool conv3d_umma_supported(int D, int H, int W, int K, int Nout) {

@@ -59,9 +59,9 @@ int mode_query(int device, mode_caps_t* caps_host);
 /* Synchronises the device and returns (and clears) the pipeline-timeout code a tcgen05 kernel raises
  * instead of hanging (0 = none). Diagnostics only; never called on the hot path. */
 int mode_poll_error(int32_t* code_host);
-/* Diagnostics: device buffer of int64[4 * 148] (or NULL to switch off) that the tcgen05 conv kernel's MMA warp
- * fills per CTA with {total, wait accumulators, wait weights, wait planes} cycles. Process-global, not
- * thread-safe, never set on the hot path. */
+/* Diagnostics: device buffer of int64[8 * 160] (or NULL to switch off) that the tcgen05 conv kernel fills per CTA
+ * with MMA-warp cycles {total, wait accumulators, wait weights, wait planes} and globaltimer ns {CTA entry, MMA
+ * loop end, all roles done, 0}. Process-global, not thread-safe, never set on the hot path. */
 int mode_debug_profile(void* buf);
 
 /* ---- K1: gate softmax + expert re-parameterisation --------------------------------------------------
@@ -86,7 +86,9 @@ int mode_debug_profile(void* buf);
 int mode_reparam_fwd(const mode_layer_t* layer_host, const int32_t* task_ids, const float* t_dense, int32_t U,
                      float* g_out, void* w_fwd, void* w_dgrad, mode_dtype_t w_dtype, float w_scale,
                      const float* w_scale_dev, void* stream);
-int64_t mode_packed_weight_elems(int32_t k_channels, int32_t n_channels);   /* per gate input u */
+int64_t mode_packed_weight_elems(int32_t k_channels, int32_t n_channels);       /* fp32 pack, per gate input u */
+/* fp16 pack: rows padded to a multiple of 32 too (pad rows are NOT written: zero-initialise when n % 32 != 0) */
+int64_t mode_packed_weight_elems_f16(int32_t k_channels, int32_t n_channels);
 
 /* ---- K1b: backward of K1 ------------------------------------------------------------------------------
  * Replaces autograd through routing/softmax/Linear.  d_weff [N][125][Co][Ci] fp32 is the per-sample

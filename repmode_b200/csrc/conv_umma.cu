@@ -61,7 +61,8 @@ struct ConvParams {
     int64_t units;               // N * tiles_h * tiles_w * D plane-patches
     int32_t bounds[160];         // CTA c owns units [bounds[c], bounds[c+1]) -- cost-balanced on the host
     int* error_flag;
-    long long* prof;             // optional [grid][4] cycles: MMA-warp total / wait tmem_empty / wait weights / wait planes
+    long long* prof;             // optional [grid][8]: MMA-warp cycles total / wait tmem_empty / wait weights / wait
+                                 // planes, then globaltimer ns at CTA entry / MMA loop end / all roles done
 };
 
 // Work distribution: a "unit" is one 8x16 patch of one output d-plane, ordered (n, th, tw, d).  CTA c owns the
@@ -124,6 +125,7 @@ conv3d_umma_kernel(const __grid_constant__ CUtensorMap xmap, const ConvParams P)
     double* s_bn = reinterpret_cast<double*>(smem + L.bn_off);   // per-CTA BatchNorm partial sums [2][Nt]
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint64_t ts_entry = (P.prof != nullptr && threadIdx.x == 0) ? globaltimer_ns() : 0;
     const int nchunk = P.K / 32;
     const uint32_t blk_bytes = (uint32_t)P.Nt * cu::ROWB;          // one kd block of a weight stage
     const uint32_t wst_bytes = 5u * blk_bytes;
@@ -272,8 +274,9 @@ conv3d_umma_kernel(const __grid_constant__ CUtensorMap xmap, const ConvParams P)
                 mma_commit(tmem_full + 8 * buf);
             }
             if (P.prof != nullptr) {
-                long long* o = P.prof + 4 * (size_t)blockIdx.x;
+                long long* o = P.prof + 8 * (size_t)blockIdx.x;
                 o[0] = clock64() - c_total; o[1] = c_tmem; o[2] = c_w; o[3] = c_plane;
+                o[5] = (long long)globaltimer_ns();                       // MMA issue loop done
             }
         }
     } else if (warp >= 4) {
@@ -301,7 +304,8 @@ conv3d_umma_kernel(const __grid_constant__ CUtensorMap xmap, const ConvParams P)
             if (!mbar_wait(tmem_full + 8 * buf, (it >> 1) & 1)) { atomicExch(P.error_flag, 6); break; }
             tc_fence_after();
             const int qn = td;
-            for (int q = 0; q < td; ++q) {
+            const bool row_ok = h0 + th < P.H;          // H need not be a multiple of 16: rows past the volume are
+            for (int q = 0; q < td; ++q) {              // computed (TMA zero fill) but neither stored nor counted
                 float* dst = P.y + ((((size_t)n * P.D + d0 + q) * P.H + h0 + th) * P.W + w0 + tw) * P.Nout + P.n0;
                 for (int cc = 0; cc < P.Nt; cc += 32) {
                     const uint32_t taddr = tmem + buf * 256 + q * P.Nt + cc + lane_addr;
@@ -311,10 +315,12 @@ conv3d_umma_kernel(const __grid_constant__ CUtensorMap xmap, const ConvParams P)
                         tmem_ld_wait();
                         float f[32];
 #pragma unroll
-                        for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]) * scale;
+                        for (int j = 0; j < 32; ++j) f[j] = row_ok ? __uint_as_float(v[j]) * scale : 0.f;
+                        if (row_ok) {
 #pragma unroll
-                        for (int j = 0; j < 32; j += 4)
-                            *reinterpret_cast<float4*>(dst + cc + j) = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
+                            for (int j = 0; j < 32; j += 4)
+                                *reinterpret_cast<float4*>(dst + cc + j) = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
+                        }
                         if (P.bn_sums != nullptr && d0 + q >= P.stat_lo && d0 + q < P.stat_hi) {
                             float g[32];
 #pragma unroll
@@ -347,6 +353,11 @@ conv3d_umma_kernel(const __grid_constant__ CUtensorMap xmap, const ConvParams P)
     }
     tc_fence_before();
     __syncthreads();
+    if (P.prof != nullptr && threadIdx.x == 0) {
+        long long* o = P.prof + 8 * (size_t)blockIdx.x;
+        o[4] = (long long)ts_entry;                                       // CTA entry
+        o[6] = (long long)globaltimer_ns();                               // all roles done (before teardown)
+    }
     if (P.bn_sums != nullptr)
         for (int i = threadIdx.x; i < 2 * P.Nt; i += cu::THREADS) {
             const int which = i / P.Nt, ch = i % P.Nt;
@@ -475,7 +486,8 @@ static void partition_units(int64_t units, int D, int TD, int Nt, int nchunk, in
 
 bool conv3d_umma_supported(int D, int H, int W, int K, int Nout) {
     (void)D;
-    return K % 32 == 0 && K >= 32 && Nout % 32 == 0 && Nout >= 32 && H % cu::TH == 0 && W % cu::TW == 0 &&
+    (void)H;
+    return K % 32 == 0 && K >= 32 && Nout % 32 == 0 && Nout >= 32 && W % cu::TW == 0 &&
            (Nout <= 128 || Nout % 128 == 0);
 }
 
@@ -500,7 +512,7 @@ int conv3d_umma(const __half* x, const __half* w, const int32_t* sample_u, float
     const SmemLayout L = smem_layout(P.ring, P.wstages, P.Nt);
     const int smem_bytes = (int)L.total + 1024;
     if (smem_bytes > 227 * 1024) MODE_FAIL("conv3d_umma: shared memory budget exceeded (%d B)", smem_bytes);
-    P.tiles_w = W / cu::TW; P.tiles_h = H / cu::TH;
+    P.tiles_w = W / cu::TW; P.tiles_h = (int)ceil_div(H, cu::TH);
     P.units = (int64_t)N * P.tiles_h * P.tiles_w * D;
     if (P.units > 0x7fffffff) MODE_FAIL("conv3d_umma: volume too large for 32-bit unit indices");
     const int64_t total = ceil_div(P.units, P.TD);          // upper bound on useful CTAs

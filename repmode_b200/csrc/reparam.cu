@@ -51,7 +51,8 @@ template <typename OutT>
 __global__ void __launch_bounds__(256) reparam_fwd_kernel(mode_layer_t L, const int32_t* __restrict__ task_ids,
                                                           const float* __restrict__ t_dense,
                                                           float* __restrict__ g_out, OutT* __restrict__ w_fwd,
-                                                          float w_scale, const float* __restrict__ w_scale_dev) {
+                                                          float w_scale, const float* __restrict__ w_scale_dev,
+                                                          int rows_pad) {
     __shared__ float sw[32 * 25];    // [i][tap in slice]; stride 25 is odd -> column reads are conflict free
     __shared__ float slog[MODE_NUM_EXPERTS];
     __shared__ float sg[MODE_NUM_EXPERTS];
@@ -112,7 +113,7 @@ __global__ void __launch_bounds__(256) reparam_fwd_kernel(mode_layer_t L, const 
     const int warp = tid >> 5, lane = tid & 31;
     const int nci = gridDim.y;
     for (int tl = warp; tl < 25; tl += 8) {
-        store_w(w_fwd + pack_index<OutT>(u, kds * 25 + tl, ic, nci, o, Co, lane), sw[lane * 25 + tl] * w_scale);
+        store_w(w_fwd + pack_index<OutT>(u, kds * 25 + tl, ic, nci, o, rows_pad, lane), sw[lane * 25 + tl] * w_scale);
     }
 }
 
@@ -120,7 +121,7 @@ __global__ void __launch_bounds__(256) reparam_fwd_kernel(mode_layer_t L, const 
 // grid (ceil(Ci/32), ceil(Co/32), U*125), block (32, 8)
 template <typename T>
 __global__ void __launch_bounds__(256) pack_dgrad_kernel(const T* __restrict__ src, T* __restrict__ dst, int Ci,
-                                                         int Co) {
+                                                         int Co, int src_rows_pad, int dst_rows_pad) {
     __shared__ T tile[32][33];
     const int ic = blockIdx.x, oc = blockIdx.y;
     const int u = blockIdx.z / 125, tap = blockIdx.z % 125;
@@ -129,13 +130,13 @@ __global__ void __launch_bounds__(256) pack_dgrad_kernel(const T* __restrict__ s
     for (int r = ty; r < 32; r += 8) {
         const int o = oc * 32 + r;
         T v = T(0);
-        if (o < Co) v = src[pack_index<T>(u, tap, ic, nci, o, Co, tx)];
+        if (o < Co) v = src[pack_index<T>(u, tap, ic, nci, o, src_rows_pad, tx)];
         tile[r][tx] = v;                                     // (o = oc*32+r, i = ic*32+tx)
     }
     __syncthreads();
     for (int r = ty; r < 32; r += 8) {
         const int i = ic * 32 + r;
-        if (i < Ci) dst[pack_index<T>(u, 124 - tap, oc, nco, i, Ci, tx)] = tile[tx][r];
+        if (i < Ci) dst[pack_index<T>(u, 124 - tap, oc, nco, i, dst_rows_pad, tx)] = tile[tx][r];
     }
 }
 
@@ -305,6 +306,11 @@ using namespace mode;
 extern "C" int64_t mode_packed_weight_elems(int32_t k_channels, int32_t n_channels) {
     return (int64_t)MODE_TAPS * ceil_div(k_channels, MODE_KC) * n_channels * MODE_KC;
 }
+// fp16 pack: rows are padded to a multiple of 32 as well (the tcgen05 kernel's N granularity); pad rows are not
+// written by K1 -- the caller zero-initialises the buffer when n_channels % 32 != 0.
+extern "C" int64_t mode_packed_weight_elems_f16(int32_t k_channels, int32_t n_channels) {
+    return (int64_t)MODE_TAPS * ceil_div(k_channels, MODE_KC) * ceil_div(n_channels, 32) * 32 * MODE_KC;
+}
 
 extern "C" int mode_reparam_fwd(const mode_layer_t* L, const int32_t* task_ids, const float* t_dense, int32_t U,
                                 float* g_out, void* w_fwd, void* w_dgrad, mode_dtype_t w_dtype, float w_scale,
@@ -318,20 +324,22 @@ extern "C" int mode_reparam_fwd(const mode_layer_t* L, const int32_t* task_ids, 
     dim3 grid(L->co, nci, U * 5);
     if (w_dtype == MODE_F32) {
         reparam_fwd_kernel<float><<<grid, 256, 0, st>>>(*L, task_ids, t_dense, g_out, (float*)w_fwd, w_scale,
-                                                        w_scale_dev);
+                                                        w_scale_dev, L->co);
         MODE_LAUNCH_CHECK();
         if (w_dgrad) {
             pack_dgrad_kernel<float><<<dim3(nci, nco, U * 125), dim3(32, 8), 0, st>>>((const float*)w_fwd,
-                                                                                   (float*)w_dgrad, L->ci, L->co);
+                                                                                   (float*)w_dgrad, L->ci, L->co, L->co,
+                                                                                   L->ci);
             MODE_LAUNCH_CHECK();
         }
     } else if (w_dtype == MODE_F16) {
         reparam_fwd_kernel<__half><<<grid, 256, 0, st>>>(*L, task_ids, t_dense, g_out, (__half*)w_fwd, w_scale,
-                                                         w_scale_dev);
+                                                         w_scale_dev, nco * 32);
         MODE_LAUNCH_CHECK();
         if (w_dgrad) {
             pack_dgrad_kernel<__half><<<dim3(nci, nco, U * 125), dim3(32, 8), 0, st>>>((const __half*)w_fwd,
-                                                                                    (__half*)w_dgrad, L->ci, L->co);
+                                                                                    (__half*)w_dgrad, L->ci, L->co,
+                                                                                    nco * 32, nci * 32);
             MODE_LAUNCH_CHECK();
         }
     } else {

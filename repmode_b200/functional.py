@@ -61,13 +61,27 @@ def _layer(k5, k3, k1, a3, a5, gate_w, gate_b):
 UMMA_WGRAD = os.environ.get("REPMODE_UMMA_WGRAD", "1") == "1"   # K4 on tcgen05 (wgrad_umma.cu); 0 -> SIMT fp32 wgrad
 
 
+def _pad32(c):
+    return (c + 31) // 32 * 32
+
+
 def umma_shape_ok(ci, co, d, h, w):
-    """Shapes the tcgen05 conv kernel takes for BOTH forward (K=ci, N=co) and dgrad (K=co, N=ci)
-    (conv3d_umma_supported in conv_umma.cu); everything else runs the SIMT fp32 kernels."""
+    """Shapes the tcgen05 kernels take for forward (K=ci, N=co), dgrad (K=co, N=ci) and wgrad; channel counts that
+    are not multiples of 32 (the U-Net stem Ci=1 and head Co=1) are zero-padded to 32 by the host side, so only
+    W % 8 and the 128-channel pass granularity remain.  Everything else runs the SIMT fp32 kernels."""
     def n_ok(n):
-        return n % 32 == 0 and (n <= 128 or n % 128 == 0)
-    return n_ok(ci) and n_ok(co) and h % 16 == 0 and w % 8 == 0 \
-        and os.environ.get("REPMODE_DISABLE_UMMA", "0") != "1"
+        n = _pad32(n)
+        return n <= 128 or n % 128 == 0
+    return n_ok(ci) and n_ok(co) and w % 8 == 0 and os.environ.get("REPMODE_DISABLE_UMMA", "0") != "1"
+
+
+def pad_channels(t, c_pad):
+    """[..., C] -> [..., c_pad] with zero channels appended (no-op when already c_pad wide)."""
+    if t.shape[-1] == c_pad:
+        return t
+    out = torch.zeros(t.shape[:-1] + (c_pad,), dtype=t.dtype, device=t.device)
+    out[..., :t.shape[-1]] = t
+    return out
 
 
 def reparam_fwd(layer, gate_in, U, ci, co, dtype, want_dgrad, w_scale_dev=None):
@@ -76,8 +90,13 @@ def reparam_fwd(layer, gate_in, U, ci, co, dtype, want_dgrad, w_scale_dev=None):
     dev = gate_in.device
     tdt = torch.float16 if dtype == _lib.MODE_F16 else torch.float32
     g = torch.empty((U, E, co), dtype=torch.float32, device=dev)
-    w_fwd = torch.empty(U * lib.mode_packed_weight_elems(ci, co), dtype=tdt, device=dev)
-    w_dg = torch.empty(U * lib.mode_packed_weight_elems(co, ci), dtype=tdt, device=dev) if want_dgrad else None
+    if dtype == _lib.MODE_F16:      # rows padded to 32; K1 leaves pad rows untouched -> zero them here when present
+        mk = torch.zeros if (ci % 32 or co % 32) else torch.empty
+        w_fwd = mk(U * lib.mode_packed_weight_elems_f16(ci, co), dtype=tdt, device=dev)
+        w_dg = mk(U * lib.mode_packed_weight_elems_f16(co, ci), dtype=tdt, device=dev) if want_dgrad else None
+    else:
+        w_fwd = torch.empty(U * lib.mode_packed_weight_elems(ci, co), dtype=tdt, device=dev)
+        w_dg = torch.empty(U * lib.mode_packed_weight_elems(co, ci), dtype=tdt, device=dev) if want_dgrad else None
     ids, dense = (gate_in, None) if not gate_in.dtype.is_floating_point else (None, gate_in)
     _lib.check(lib.mode_reparam_fwd(ctypes.byref(layer), _p(ids), _p(dense), U, _p(g), _p(w_fwd), _p(w_dg), dtype, 1.0,
                                     _p(w_scale_dev), _stream()), "mode_reparam_fwd")
@@ -186,17 +205,22 @@ class ModeConvFunction(torch.autograd.Function):
 
         xn = to_ndhwc(x)
         w_s2 = None
+        ci_p, co_p = (_pad32(ci), _pad32(co)) if use_umma else (ci, co)
         if use_umma:
             w_s2 = f16_scale_of([k5, k3, k1, a3, a5], 1024.0)        # |W_eff| <= max|expert| (gates sum to 1)
-            x_op = cast_f16(xn)
+            x_op = pad_channels(cast_f16(xn), ci_p)
         else:
             x_op = xn
         g, w_fwd, w_dg = reparam_fwd(layer, gate_u, U, ci, co, dtype, needs_dx, w_s2[0:1] if use_umma else None)
 
         bn_train = normal and training
-        sums = torch.zeros(2 * co, dtype=torch.float64, device=dev) if bn_train else None
-        y = conv3d(x_op, dtype, w_fwd, sample_u, n, d, h, wd, ci, co, w_s2[1:2] if use_umma else None, sums,
+        sums = torch.zeros(2 * co_p, dtype=torch.float64, device=dev) if bn_train else None
+        y = conv3d(x_op, dtype, w_fwd, sample_u, n, d, h, wd, ci_p, co_p, w_s2[1:2] if use_umma else None, sums,
                    stat_range=shard.own if shard is not None else None)
+        if co_p != co:                              # drop the zero-padded output channels (head layer, Co = 1)
+            y = y[..., :co].contiguous()
+            if sums is not None:
+                sums = sums.view(2, co_p)[:, :co].contiguous().view(-1)
         m_rows = n * d * h * wd
         planes = shard.planes(h * wd, d) if shard is not None else None
         m_stat = shard.m_global if shard is not None else m_rows
@@ -230,7 +254,7 @@ class ModeConvFunction(torch.autograd.Function):
             x_w = x_op if (UMMA_WGRAD or not use_umma) else xn      # operand K4 will read
             ctx.save_for_backward(None, x_w if needs_dw else None, y if normal else None, g, w_dg,
                                   gate_u, sample_u, k5, k3, k1, a3, a5, gate_w, gate_b, bn_w, bn_b, mean, invstd, w_s2)
-            ctx.cfg = (n, d, h, wd, ci, co, U, normal, use_umma, needs_dx, needs_dw)
+            ctx.cfg = (n, d, h, wd, ci, co, U, normal, use_umma, needs_dx, needs_dw, ci_p, co_p)
         return from_ndhwc(out)
 
     @staticmethod
@@ -241,7 +265,7 @@ class ModeConvFunction(torch.autograd.Function):
         lib = _lib.load()
         (x_op, x_w, y, g, w_dg, gate_u, sample_u, k5, k3, k1, a3, a5, gate_w, gate_b, bn_w, bn_b, mean, invstd,
          w_s2) = ctx.saved_tensors
-        n, d, h, wd, ci, co, U, normal, use_umma, needs_dx, needs_dw = ctx.cfg
+        n, d, h, wd, ci, co, U, normal, use_umma, needs_dx, needs_dw, ci_p, co_p = ctx.cfg
         dev = dout.device
         dtype = _lib.MODE_F16 if use_umma else _lib.MODE_F32
         doutn = to_ndhwc(dout)
@@ -286,17 +310,23 @@ class ModeConvFunction(torch.autograd.Function):
         else:
             dy_op = doutn
 
+        if use_umma:
+            dy_op = pad_channels(dy_op, co_p)
         dx = None
         if needs_dx:
             osd = (dy_s2[1:2] * w_s2[1:2]) if use_umma else None
-            dxn = conv3d(dy_op, dtype, w_dg, sample_u, n, d, h, wd, co, ci, osd, None)
+            dxn = conv3d(dy_op, dtype, w_dg, sample_u, n, d, h, wd, co_p, ci_p, osd, None)
+            if ci_p != ci:
+                dxn = dxn[..., :ci].contiguous()
             dx = from_ndhwc(dxn)
         grads = [None] * 7
         if needs_dw:
             if wgrad_f32:
                 d_weff = conv3d_wgrad(x_w, dy32, _lib.MODE_F32, n, d, h, wd, ci, co, None)
             else:
-                d_weff = conv3d_wgrad(x_w, dy_op, dtype, n, d, h, wd, ci, co, dy_s2[1:2] if use_umma else None)
+                d_weff = conv3d_wgrad(x_w, dy_op, dtype, n, d, h, wd, ci_p, co_p, dy_s2[1:2] if use_umma else None)
+                if ci_p != ci or co_p != co:
+                    d_weff = d_weff[:, :, :co, :ci].contiguous()
             layer, _, _ = _layer(k5, k3, k1, a3, a5, gate_w, gate_b)
             outs = [torch.empty_like(t) for t in (k5, k3, k1, a3, a5, gate_w, gate_b)]
             ws = torch.empty(max(int(lib.mode_reparam_bwd_workspace_bytes(ci, co, n)), 16), dtype=torch.uint8, device=dev)

@@ -73,6 +73,7 @@ SIGNATURES = {
     "mode_reparam_fwd": (ctypes.c_int, [ctypes.POINTER(ModeLayer), _vp, _vp, _i32, _vp, _vp, _vp, ctypes.c_int, _f32,
                                         _vp, _vp]),
     "mode_packed_weight_elems": (_i64, [_i32, _i32]),
+    "mode_packed_weight_elems_f16": (_i64, [_i32, _i32]),
     "mode_reparam_bwd_workspace_bytes": (_i64, [_i32, _i32, _i32]),
     "mode_reparam_bwd": (ctypes.c_int, [ctypes.POINTER(ModeLayer), _vp, _vp, _i32, _vp, _i32, _vp, _vp, _vp, _vp, _vp,
                                         _vp, _vp, _vp, _vp, _vp, _vp]),

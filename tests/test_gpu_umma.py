@@ -20,6 +20,9 @@ SHAPES = [  # N, D, H, W, K, Nout
     (2, 2, 16, 16, 64, 128),
     (1, 2, 16, 8, 32, 256),
     (1, 11, 16, 8, 64, 64),
+    (1, 2, 8, 8, 32, 32),          # H < 16: rows past the volume are masked in the epilogue
+    (2, 3, 24, 16, 32, 64),        # H % 16 != 0
+    (1, 2, 8, 8, 256, 128),        # deep-level shape (bottleneck-like)
 ]
 
 

@@ -22,7 +22,7 @@ def main():
         weff = (np.random.RandomState(0).randn(n, nout, k, 5, 5, 5) * 0.02).astype(np.float32)
         w16 = torch.from_numpy(pack_weights(weff, half=True)).cuda()
         su = torch.arange(n, dtype=torch.int32, device="cuda")
-        prof = torch.zeros(4 * 148, dtype=torch.int64, device="cuda")
+        prof = torch.zeros(8 * 160, dtype=torch.int64, device="cuda")
         for _ in range(3):
             Fm.conv3d(x, L.MODE_F16, w16, su, n, d, h, w, k, nout)
         lib.mode_debug_profile(ctypes.c_void_p(prof.data_ptr()))
@@ -33,12 +33,17 @@ def main():
         e1.record()
         torch.cuda.synchronize()
         lib.mode_debug_profile(None)
-        p = prof.view(148, 4).cpu().double()
+        p = prof.view(160, 8)[:148].cpu().double()
+        t_entry, t_mma, t_done = p[:, 4], p[:, 5], p[:, 6]
+        t0g = float(t_entry.min())
         flop = 2.0 * 125 * k * nout * n * d * h * w
         r = {"shape": [n, d, h, w, k, nout], "ms": e0.elapsed_time(e1), "tflops": flop / e0.elapsed_time(e1) / 1e9,
              "mma_warp_cycles_mean": float(p[:, 0].mean()), "mma_warp_cycles_max": float(p[:, 0].max()),
              "wait_tmem_mean": float(p[:, 1].mean()), "wait_weights_mean": float(p[:, 2].mean()),
-             "wait_planes_mean": float(p[:, 3].mean()), "wait_planes_max": float(p[:, 3].max())}
+             "wait_planes_mean": float(p[:, 3].mean()), "wait_planes_max": float(p[:, 3].max()),
+             "entry_spread_us": float((t_entry.max() - t0g) / 1e3), "mma_end_us_mean": float((t_mma.mean() - t0g) / 1e3),
+             "mma_end_us_max": float((t_mma.max() - t0g) / 1e3), "done_us_max": float((t_done.max() - t0g) / 1e3),
+             "tail_after_mma_us_mean": float(((t_done - t_mma).mean()) / 1e3)}
         out.append(r)
         print(json.dumps(r), flush=True)
     os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)

@@ -269,7 +269,7 @@ def run_ours(args, rank, local_rank, world):
         x_op = Fm.cast_f16(xn) if use_umma else xn
         dy_op = Fm.cast_f16(dyn) if use_umma else dyn
         su = torch.zeros(1, dtype=torch.int32, device=dev)
-        gq, w_fwd, w_dg = Fm.reparam_fwd(layer, task, 1, ci, co, dtype, True)
+        gq, w_fwd, w_dg = Fm.reparam_fwd(layer, task, 1, ci, co, dtype, True, Fm.W_SCALE_F16 if use_umma else 1.0)
 
         def tk(fn, it=10):
             fn(); fn()
@@ -287,7 +287,7 @@ def run_ours(args, rank, local_rank, world):
             kern["wgrad_ms"] = tk(lambda: Fm.conv3d_wgrad(xn, dyn, L.MODE_F32, 1, D, H, W, ci, co), it=3)
         else:
             kern["wgrad_ms"] = tk(lambda: Fm.conv3d_wgrad(x_op, dy_op, dtype, 1, D, H, W, ci, co))
-        kern["reparam_fwd_ms"] = tk(lambda: Fm.reparam_fwd(layer, task, 1, ci, co, dtype, True), it=50)
+        kern["reparam_fwd_ms"] = tk(lambda: Fm.reparam_fwd(layer, task, 1, ci, co, dtype, True, 256.0), it=50)
     conv_ms = kern["conv_fwd_ms"]
     achieved = FLOP_CONV / (conv_ms * 1e-3) / 1e12
     roofline = {"kernel": "conv3d_umma_kernel (K2 forward)" if use_umma else "conv3d_simt_kernel (K2 forward)",

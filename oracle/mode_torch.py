@@ -68,10 +68,7 @@ def mode_conv(p, prefix, x, task_ids, training, conv_type="normal", update_runni
     g = gate_softmax(p[prefix + "gate.weight"], p[prefix + "gate.bias"], task_ids, co)
     w = reparam(p, prefix, g)
     if operand_f16:
-        amax = max(float(p[prefix + k].detach().abs().max()) for k in
-                   ("expert_conv5x5_conv", "expert_conv3x3_conv", "expert_conv1x1_conv", "expert_avg3x3_conv",
-                    "expert_avg5x5_conv"))
-        w = round_f16_scaled(w, amax, 1024.0)
+        w = w + (((w * 256.0).half().float() / 256.0) - w).detach()      # fixed 2^8 scale of the fp16 weight pack
         x = x + (x.half().float() - x).detach()
     if training:
         y = torch.cat([F.conv3d(x[i:i + 1], w[i], padding=2) for i in range(x.shape[0])], dim=0)

@@ -54,7 +54,7 @@ struct ConvParams {
     const float* out_scale_dev;
     float out_scale;
     int N, D, H, W, K, Nout;     // Nout = total output channels (row stride of y / rows per weight block)
-    int n0, Nt;                  // this launch computes channels [n0, n0+Nt)
+    int Nt;                      // CTA (x, y) computes output channels [y*Nt, (y+1)*Nt)
     int stat_lo, stat_hi;        // BatchNorm sums cover output planes [stat_lo, stat_hi) only (owned planes of a slab)
     int TD, ring, wstages;
     int tiles_w, tiles_h;
@@ -125,6 +125,7 @@ conv3d_umma_kernel(const __grid_constant__ CUtensorMap xmap, const ConvParams P)
     double* s_bn = reinterpret_cast<double*>(smem + L.bn_off);   // per-CTA BatchNorm partial sums [2][Nt]
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int n0 = blockIdx.y * P.Nt;
     const uint64_t ts_entry = (P.prof != nullptr && threadIdx.x == 0) ? globaltimer_ns() : 0;
     const int nchunk = P.K / 32;
     const uint32_t blk_bytes = (uint32_t)P.Nt * cu::ROWB;          // one kd block of a weight stage
@@ -180,7 +181,7 @@ conv3d_umma_kernel(const __grid_constant__ CUtensorMap xmap, const ConvParams P)
                         if (!mbar_wait(w_empty + 8 * st, (use & 1) ^ 1)) { atomicExch(P.error_flag, 2); return; }
                         mbar_expect_tx(w_full + 8 * st, wst_bytes);
                         const uint32_t dst = base + L.w_off + st * wst_bytes;
-                        const __half* src = wu + ((size_t)(c * 25 + t) * 5 * P.Nout + P.n0) * 32;
+                        const __half* src = wu + ((size_t)(c * 25 + t) * 5 * P.Nout + n0) * 32;
 #pragma unroll
                         for (int b = 0; b < 5; ++b)
                             bulk_load(dst + b * blk_bytes, src + (size_t)b * P.Nout * 32, blk_bytes, w_full + 8 * st);
@@ -274,7 +275,7 @@ conv3d_umma_kernel(const __grid_constant__ CUtensorMap xmap, const ConvParams P)
                 mma_commit(tmem_full + 8 * buf);
             }
             if (P.prof != nullptr) {
-                long long* o = P.prof + 8 * (size_t)blockIdx.x;
+                long long* o = P.prof + 8 * (size_t)(blockIdx.x % 160);
                 o[0] = clock64() - c_total; o[1] = c_tmem; o[2] = c_w; o[3] = c_plane;
                 o[5] = (long long)globaltimer_ns();                       // MMA issue loop done
             }
@@ -306,7 +307,7 @@ conv3d_umma_kernel(const __grid_constant__ CUtensorMap xmap, const ConvParams P)
             const int qn = td;
             const bool row_ok = h0 + th < P.H;          // H need not be a multiple of 16: rows past the volume are
             for (int q = 0; q < td; ++q) {              // computed (TMA zero fill) but neither stored nor counted
-                float* dst = P.y + ((((size_t)n * P.D + d0 + q) * P.H + h0 + th) * P.W + w0 + tw) * P.Nout + P.n0;
+                float* dst = P.y + ((((size_t)n * P.D + d0 + q) * P.H + h0 + th) * P.W + w0 + tw) * P.Nout + n0;
                 for (int cc = 0; cc < P.Nt; cc += 32) {
                     const uint32_t taddr = tmem + buf * 256 + q * P.Nt + cc + lane_addr;
                     if (q < qn) {
@@ -354,14 +355,14 @@ conv3d_umma_kernel(const __grid_constant__ CUtensorMap xmap, const ConvParams P)
     tc_fence_before();
     __syncthreads();
     if (P.prof != nullptr && threadIdx.x == 0) {
-        long long* o = P.prof + 8 * (size_t)blockIdx.x;
+        long long* o = P.prof + 8 * (size_t)(blockIdx.x % 160);
         o[4] = (long long)ts_entry;                                       // CTA entry
         o[6] = (long long)globaltimer_ns();                               // all roles done (before teardown)
     }
     if (P.bn_sums != nullptr)
         for (int i = threadIdx.x; i < 2 * P.Nt; i += cu::THREADS) {
             const int which = i / P.Nt, ch = i % P.Nt;
-            atomicAdd(P.bn_sums + which * P.Nout + P.n0 + ch, s_bn[i]);
+            atomicAdd(P.bn_sums + which * P.Nout + n0 + ch, s_bn[i]);
         }
     if (warp == 2) tmem_dealloc<512>(tmem);
 }
@@ -488,7 +489,7 @@ bool conv3d_umma_supported(int D, int H, int W, int K, int Nout) {
     (void)D;
     (void)H;
     return K % 32 == 0 && K >= 32 && Nout % 32 == 0 && Nout >= 32 && W % cu::TW == 0 &&
-           (Nout <= 128 || Nout % 128 == 0);
+           true;
 }
 
 int conv3d_umma(const __half* x, const __half* w, const int32_t* sample_u, float* y, int N, int D, int H, int W, int K,
@@ -502,7 +503,17 @@ int conv3d_umma(const __half* x, const __half* w, const int32_t* sample_u, float
     P.out_scale = out_scale;
     P.N = N; P.D = D; P.H = H; P.W = W; P.K = K; P.Nout = Nout;
     P.stat_lo = stat_lo; P.stat_hi = stat_hi;
-    P.Nt = Nout <= 128 ? Nout : 128;                 // wider layers run in passes of 128 output channels
+    // Output channels per CTA: as wide as TMEM allows (<= 128) when the volume alone fills the GPU; narrower for the
+    // deep, small-volume layers so that (tiles x channel passes) still spreads over the SMs.
+    P.units = (int64_t)N * (int64_t)ceil_div(H, cu::TH) * (W / cu::TW) * D;
+    P.Nt = 0;
+    for (int nt = 128; nt >= 32; nt >>= 1) {
+        if (Nout % nt != 0) continue;
+        const int td = max(1, min(min(256 / nt, 8), D));
+        P.Nt = nt;
+        if (ceil_div(P.units, td) * (Nout / nt) >= sm_count() / 2) break;
+    }
+    if (P.Nt == 0) MODE_FAIL("conv3d_umma: Nout=%d is not a multiple of 32", Nout);
     P.TD = max(1, min(min(256 / P.Nt, 8), D));
     P.ring = P.TD + 4;
     const int wst_bytes = 5 * P.Nt * cu::ROWB;
@@ -513,7 +524,6 @@ int conv3d_umma(const __half* x, const __half* w, const int32_t* sample_u, float
     const int smem_bytes = (int)L.total + 1024;
     if (smem_bytes > 227 * 1024) MODE_FAIL("conv3d_umma: shared memory budget exceeded (%d B)", smem_bytes);
     P.tiles_w = W / cu::TW; P.tiles_h = (int)ceil_div(H, cu::TH);
-    P.units = (int64_t)N * P.tiles_h * P.tiles_w * D;
     if (P.units > 0x7fffffff) MODE_FAIL("conv3d_umma: volume too large for 32-bit unit indices");
     const int64_t total = ceil_div(P.units, P.TD);          // upper bound on useful CTAs
     P.error_flag = device_error_flag();
@@ -525,11 +535,8 @@ int conv3d_umma(const __half* x, const __half* w, const int32_t* sample_u, float
     MODE_CUDA(cudaFuncSetAttribute(conv3d_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
     const int grid = total < (int64_t)sm_count() ? (int)total : std::min(sm_count(), 159);
     partition_units(P.units, D, P.TD, P.Nt, K / 32, grid, P.bounds);
-    for (int n0 = 0; n0 < Nout; n0 += P.Nt) {
-        P.n0 = n0;
-        conv3d_umma_kernel<<<grid, cu::THREADS, smem_bytes, st>>>(xmap, P);
-        MODE_LAUNCH_CHECK();
-    }
+    conv3d_umma_kernel<<<dim3(grid, Nout / P.Nt), cu::THREADS, smem_bytes, st>>>(xmap, P);
+    MODE_LAUNCH_CHECK();
     return 0;
 }
 

@@ -15,7 +15,9 @@
 namespace mode {
 
 __device__ __forceinline__ void store_w(float* p, float v) { *p = v; }
-__device__ __forceinline__ void store_w(__half* p, float v) { *p = __float2half_rn(v); }
+__device__ __forceinline__ void store_w(__half* p, float v) {
+    *p = __float2half_rn(fminf(fmaxf(v, -65504.f), 65504.f));      // saturate instead of producing inf
+}
 
 // Position of element `col` (0..31) of row `row` inside a packed [rows][32] block.
 //   fp32 pack: plain.   fp16 pack: the 64-byte-swizzled shared-memory image the UMMA B operand reads

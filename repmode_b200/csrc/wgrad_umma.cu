@@ -162,24 +162,31 @@ wgrad_umma_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constan
 }
 
 // d_weff[n][kd*25+t][coc*32+o][cic*32+i] = scale * sum_s partial[unit(n,coc,cic,kd,s)][t][o][i]
+// one thread = 4 consecutive i (float4): coalesced 16-byte loads from each slab partial, 32-bit index math.
 __global__ void __launch_bounds__(256) wgrad_reduce_kernel(const float* __restrict__ partial, float* __restrict__ dw,
                                                            int N, int Ci, int Co, int S, float out_scale,
                                                            const float* __restrict__ out_scale_dev) {
-    const int64_t total = (int64_t)N * 125 * Co * Ci;
-    const int ncic = Ci / 32, ncoc = Co / 32;
+    const uint32_t ci4 = (uint32_t)Ci >> 2;
+    const uint32_t total4 = (uint32_t)N * 125u * (uint32_t)Co * ci4;
+    const uint32_t ncic = Ci / 32, ncoc = Co / 32;
     float scale = out_scale;
     if (out_scale_dev != nullptr) scale *= *out_scale_dev;
-    for (int64_t idx = (int64_t)blockIdx.x * 256 + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * 256) {
-        const int i = (int)(idx % Ci);
-        const int o = (int)((idx / Ci) % Co);
-        const int tap = (int)((idx / ((int64_t)Ci * Co)) % 125);
-        const int n = (int)(idx / ((int64_t)Ci * Co * 125));
-        const int kd = tap / 25, t = tap % 25;
-        const int64_t unit0 = ((((int64_t)n * ncoc + o / 32) * ncic + i / 32) * 5 + kd) * S;
+    for (uint32_t idx = blockIdx.x * 256u + threadIdx.x; idx < total4; idx += gridDim.x * 256u) {
+        const uint32_t i = (idx % ci4) << 2;
+        const uint32_t row = idx / ci4;                 // (n*125 + tap)*Co + o
+        const uint32_t o = row % (uint32_t)Co;
+        const uint32_t nt = row / (uint32_t)Co;
+        const uint32_t tap = nt % 125u, n = nt / 125u;
+        const uint32_t kd = tap / 25u, t = tap - kd * 25u;
+        const size_t unit0 = ((((size_t)n * ncoc + (o >> 5)) * ncic + (i >> 5)) * 5 + kd) * (size_t)S;
         const float* src = partial + unit0 * wg::PARTIAL_FLOATS + ((size_t)t * 32 + (o & 31)) * 32 + (i & 31);
-        float acc = 0.f;
-        for (int s = 0; s < S; ++s) acc += src[(size_t)s * wg::PARTIAL_FLOATS];
-        dw[idx] = acc * scale;
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int s = 0; s < S; ++s) {
+            const float4 v = *reinterpret_cast<const float4*>(src + (size_t)s * wg::PARTIAL_FLOATS);
+            acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+        }
+        acc.x *= scale; acc.y *= scale; acc.z *= scale; acc.w *= scale;
+        *reinterpret_cast<float4*>(dw + (size_t)idx * 4) = acc;
     }
 }
 
@@ -227,8 +234,9 @@ int wgrad_umma(const __half* x, const __half* dy, float* dw, int N, int D, int H
     MODE_CUDA(cudaFuncSetAttribute(wgrad_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
     wgrad_umma_kernel<<<(unsigned)units, wg::THREADS, smem_bytes, st>>>(xmap, dymap, P);
     MODE_LAUNCH_CHECK();
-    const int64_t total = (int64_t)N * 125 * Co * Ci;
-    const int grid = (int)max((int64_t)1, min(ceil_div(total, 256), (int64_t)sm_count() * 8));
+    const int64_t total = (int64_t)N * 125 * Co * Ci / 4;
+    if (total > 0x7fffffff) MODE_FAIL("wgrad_umma: d_weff too large for 32-bit indexing");
+    const int grid = (int)max((int64_t)1, min(ceil_div(total, 256), (int64_t)sm_count() * 16));
     wgrad_reduce_kernel<<<grid, 256, 0, st>>>((const float*)workspace, dw, N, Ci, Co, P.S, out_scale, out_scale_dev);
     MODE_LAUNCH_CHECK();
     return 0;

@@ -69,10 +69,7 @@ def umma_shape_ok(ci, co, d, h, w):
     """Shapes the tcgen05 kernels take for forward (K=ci, N=co), dgrad (K=co, N=ci) and wgrad; channel counts that
     are not multiples of 32 (the U-Net stem Ci=1 and head Co=1) are zero-padded to 32 by the host side, so only
     W % 8 and the 128-channel pass granularity remain.  Everything else runs the SIMT fp32 kernels."""
-    def n_ok(n):
-        n = _pad32(n)
-        return n <= 128 or n % 128 == 0
-    return n_ok(ci) and n_ok(co) and w % 8 == 0 and os.environ.get("REPMODE_DISABLE_UMMA", "0") != "1"
+    return w % 8 == 0 and os.environ.get("REPMODE_DISABLE_UMMA", "0") != "1"
 
 
 def pad_channels(t, c_pad):
@@ -84,7 +81,12 @@ def pad_channels(t, c_pad):
     return out
 
 
-def reparam_fwd(layer, gate_in, U, ci, co, dtype, want_dgrad, w_scale_dev=None):
+W_SCALE_F16 = 256.0     # fixed power-of-two scale of the fp16 weight pack: |W_eff| <= max|expert| is O(1e-2..1) for
+                        # BatchNorm-ed conv nets, so values stay far from fp16's 65504 (K1 saturates) and at least
+                        # 2^-8 * 6e-5 = 2.4e-7 in absolute resolution; no per-call amax pass over the experts
+
+
+def reparam_fwd(layer, gate_in, U, ci, co, dtype, want_dgrad, w_scale=1.0):
     """K1. Returns g [U,5,Co], w_fwd, w_dgrad (packed, see header)."""
     lib = _lib.load()
     dev = gate_in.device
@@ -98,16 +100,18 @@ def reparam_fwd(layer, gate_in, U, ci, co, dtype, want_dgrad, w_scale_dev=None):
         w_fwd = torch.empty(U * lib.mode_packed_weight_elems(ci, co), dtype=tdt, device=dev)
         w_dg = torch.empty(U * lib.mode_packed_weight_elems(co, ci), dtype=tdt, device=dev) if want_dgrad else None
     ids, dense = (gate_in, None) if not gate_in.dtype.is_floating_point else (None, gate_in)
-    _lib.check(lib.mode_reparam_fwd(ctypes.byref(layer), _p(ids), _p(dense), U, _p(g), _p(w_fwd), _p(w_dg), dtype, 1.0,
-                                    _p(w_scale_dev), _stream()), "mode_reparam_fwd")
+    _lib.check(lib.mode_reparam_fwd(ctypes.byref(layer), _p(ids), _p(dense), U, _p(g), _p(w_fwd), _p(w_dg), dtype,
+                                    float(w_scale), None, _stream()), "mode_reparam_fwd")
     return g, w_fwd, w_dg
 
 
-def conv3d(x, dtype, w, sample_u, n, d, h, wd, k, nout, out_scale_dev=None, bn_sums=None, impl=0, stat_range=None):
+def conv3d(x, dtype, w, sample_u, n, d, h, wd, k, nout, out_scale_dev=None, bn_sums=None, impl=0, stat_range=None,
+           out_scale=1.0):
     lib = _lib.load()
     y = torch.empty((n, d, h, wd, nout), dtype=torch.float32, device=x.device)
     lo, hi = stat_range if stat_range is not None else (0, d)
-    _lib.check(lib.mode_conv3d(_p(x), dtype, _p(w), _p(sample_u), _p(y), n, d, h, wd, k, nout, 1.0, _p(out_scale_dev),
+    _lib.check(lib.mode_conv3d(_p(x), dtype, _p(w), _p(sample_u), _p(y), n, d, h, wd, k, nout, float(out_scale),
+                               _p(out_scale_dev),
                                _p(bn_sums), lo, hi, impl, _stream()), "mode_conv3d")
     return y
 
@@ -206,17 +210,17 @@ class ModeConvFunction(torch.autograd.Function):
         xn = to_ndhwc(x)
         w_s2 = None
         ci_p, co_p = (_pad32(ci), _pad32(co)) if use_umma else (ci, co)
+        w_scale = W_SCALE_F16 if use_umma else 1.0
         if use_umma:
-            w_s2 = f16_scale_of([k5, k3, k1, a3, a5], 1024.0)        # |W_eff| <= max|expert| (gates sum to 1)
             x_op = pad_channels(cast_f16(xn), ci_p)
         else:
             x_op = xn
-        g, w_fwd, w_dg = reparam_fwd(layer, gate_u, U, ci, co, dtype, needs_dx, w_s2[0:1] if use_umma else None)
+        g, w_fwd, w_dg = reparam_fwd(layer, gate_u, U, ci, co, dtype, needs_dx, w_scale)
 
         bn_train = normal and training
         sums = torch.zeros(2 * co_p, dtype=torch.float64, device=dev) if bn_train else None
-        y = conv3d(x_op, dtype, w_fwd, sample_u, n, d, h, wd, ci_p, co_p, w_s2[1:2] if use_umma else None, sums,
-                   stat_range=shard.own if shard is not None else None)
+        y = conv3d(x_op, dtype, w_fwd, sample_u, n, d, h, wd, ci_p, co_p, None, sums,
+                   stat_range=shard.own if shard is not None else None, out_scale=1.0 / w_scale)
         if co_p != co:                              # drop the zero-padded output channels (head layer, Co = 1)
             y = y[..., :co].contiguous()
             if sums is not None:
@@ -314,8 +318,8 @@ class ModeConvFunction(torch.autograd.Function):
             dy_op = pad_channels(dy_op, co_p)
         dx = None
         if needs_dx:
-            osd = (dy_s2[1:2] * w_s2[1:2]) if use_umma else None
-            dxn = conv3d(dy_op, dtype, w_dg, sample_u, n, d, h, wd, co_p, ci_p, osd, None)
+            dxn = conv3d(dy_op, dtype, w_dg, sample_u, n, d, h, wd, co_p, ci_p, dy_s2[1:2] if use_umma else None, None,
+                         out_scale=(1.0 / W_SCALE_F16) if use_umma else 1.0)
             if ci_p != ci:
                 dxn = dxn[..., :ci].contiguous()
             dx = from_ndhwc(dxn)

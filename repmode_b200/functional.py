@@ -347,3 +347,85 @@ def mode_conv(x, gate_in, params, bn, training, conv_type="normal", precision=No
     bn_w, bn_b, rm, rv = bn if bn is not None else (None, None, None, None)
     return ModeConvFunction.apply(x, gate_in, *params, bn_w, bn_b, rm, rv, training, conv_type,
                                   precision or default_precision(), shard)
+
+
+class BnReluFunction(torch.autograd.Function):
+    """BatchNorm3d (+ReLU) on an NDHWC tensor with the path's own kernels (mode_bn_*): the non-MoDE BatchNorms of
+    the U-Net (`conv_down.1`, `convt.1`, reference RepMode.py:80-84,97-101) so that no layer leaves NDHWC."""
+
+    @staticmethod
+    @torch.amp.custom_fwd(device_type="cuda", cast_inputs=torch.float32)
+    def forward(ctx, y, weight, bias, running_mean, running_var, training):
+        _require_cuda(y)
+        lib = _lib.load()
+        yn = y.contiguous()                                    # [N,D,H,W,C] fp32
+        c = yn.shape[-1]
+        m_rows = yn.numel() // c
+        dev = yn.device
+        scale = torch.empty(c, dtype=torch.float32, device=dev)
+        shift = torch.empty(c, dtype=torch.float32, device=dev)
+        mean = invstd = None
+        if training:
+            sums = torch.zeros(2 * c, dtype=torch.float64, device=dev)
+            mean = torch.empty(c, dtype=torch.float32, device=dev)
+            invstd = torch.empty(c, dtype=torch.float32, device=dev)
+            _lib.check(lib.mode_bn_stats(_p(yn), m_rows, c, _p(sums), _stream()), "mode_bn_stats")
+            _lib.check(lib.mode_bn_finalize(_p(sums), m_rows, c, _p(weight), _p(bias), BN_EPS, BN_MOMENTUM, _p(mean),
+                                            _p(invstd), _p(scale), _p(shift), _p(running_mean), _p(running_var),
+                                            _stream()), "mode_bn_finalize")
+        else:
+            scale = (weight * torch.rsqrt(running_var + BN_EPS)).contiguous()
+            shift = (bias - running_mean * scale).contiguous()
+        out = torch.empty_like(yn)
+        _lib.check(lib.mode_bn_apply_relu(_p(yn), m_rows, c, _p(scale), _p(shift), 1, _p(out), None, 1.0, None,
+                                          _stream()), "mode_bn_apply_relu")
+        ctx.training = training
+        if training:
+            ctx.save_for_backward(yn, weight, bias, mean, invstd)
+        return out
+
+    @staticmethod
+    @torch.amp.custom_bwd(device_type="cuda")
+    def backward(ctx, dout):
+        if not ctx.training:
+            raise NotImplementedError("BatchNorm backward in eval mode (frozen statistics) is not supported")
+        lib = _lib.load()
+        yn, weight, bias, mean, invstd = ctx.saved_tensors
+        c = yn.shape[-1]
+        m_rows = yn.numel() // c
+        dev = yn.device
+        doutn = dout.contiguous().float()
+        dgamma = torch.empty(c, dtype=torch.float32, device=dev)
+        dbeta = torch.empty(c, dtype=torch.float32, device=dev)
+        dy = torch.empty_like(yn)
+        ws = torch.empty(int(lib.mode_bn_bwd_workspace_bytes(c)), dtype=torch.uint8, device=dev)
+        _lib.check(lib.mode_bn_relu_bwd(_p(yn), _p(doutn), m_rows, c, _p(weight), _p(bias), _p(mean), _p(invstd),
+                                        _p(dgamma), _p(dbeta), _p(dy), None, None, _p(ws), _stream()), "mode_bn_relu_bwd")
+        return dy, dgamma, dbeta, None, None, None
+
+
+def down_conv_bn_relu(x, conv_w, bn, training):
+    """Conv3d(k=2, s=2, bias=False) + BatchNorm3d + ReLU (reference RepMode.py:80-84) on NDHWC data: the stride-2
+    conv is a plain GEMM on the space-to-depth view ([voxels/8, 8*Ci] @ [8*Ci, Co], cuBLAS), BN+ReLU are the path's
+    own kernels.  x: [N,C,D,H,W] any strides -> [N,Co,D/2,H/2,W/2] channels_last_3d."""
+    xn = x.permute(0, 2, 3, 4, 1)
+    n, d, h, w, c = xn.shape
+    co = conv_w.shape[0]
+    x8 = xn.reshape(n, d // 2, 2, h // 2, 2, w // 2, 2, c).permute(0, 1, 3, 5, 2, 4, 6, 7).reshape(-1, 8 * c)
+    wm = conv_w.permute(2, 3, 4, 1, 0).reshape(8 * c, co)                     # [(kd,kh,kw,ci), co]
+    y = (x8 @ wm.to(x8.dtype)).view(n, d // 2, h // 2, w // 2, co)
+    out = BnReluFunction.apply(y, bn.weight, bn.bias, bn.running_mean, bn.running_var, training)
+    return out.permute(0, 4, 1, 2, 3)
+
+
+def up_conv_bn_relu(x, convt_w, bn, training):
+    """ConvTranspose3d(k=2, s=2, bias=False) + BatchNorm3d + ReLU (reference RepMode.py:97-101) on NDHWC data:
+    [voxels, Ci] @ [Ci, 8*Co] (cuBLAS) followed by the depth-to-space scatter, then the path's BN+ReLU kernels."""
+    xn = x.permute(0, 2, 3, 4, 1)
+    n, d, h, w, c = xn.shape
+    co = convt_w.shape[1]
+    wm = convt_w.permute(0, 2, 3, 4, 1).reshape(c, 8 * co)                    # [ci, (kd,kh,kw,co)]
+    y8 = (xn.reshape(-1, c) @ wm.to(xn.dtype)).view(n, d, h, w, 2, 2, 2, co)
+    y = y8.permute(0, 1, 4, 2, 5, 3, 6, 7).reshape(n, 2 * d, 2 * h, 2 * w, co)
+    out = BnReluFunction.apply(y, bn.weight, bn.bias, bn.running_mean, bn.running_var, training)
+    return out.permute(0, 4, 1, 2, 3)

@@ -104,7 +104,11 @@ class MoDEEncoderBlock(torch.nn.Module):
 
     def forward(self, x, t):
         x_skip = self.conv_more(x, t)
-        return self.conv_down(x_skip), x_skip
+        bn = self.conv_down[1]
+        if self.training and bn.num_batches_tracked is not None:
+            bn.num_batches_tracked.add_(1)
+        # conv_down = Sequential(Conv3d k2 s2, BatchNorm3d, ReLU): same parameters, NDHWC execution
+        return Fm.down_conv_bn_relu(x_skip, self.conv_down[0].weight, bn, self.training), x_skip
 
 
 class MoDEDecoderBlock(torch.nn.Module):
@@ -120,7 +124,10 @@ class MoDEDecoderBlock(torch.nn.Module):
         self.conv_less = MoDESubNet2Conv(num_experts, num_tasks, in_chan, out_chan)
 
     def forward(self, x, x_skip, t):
-        x = self.convt(x)
+        bn = self.convt[1]
+        if self.training and bn.num_batches_tracked is not None:
+            bn.num_batches_tracked.add_(1)
+        x = Fm.up_conv_bn_relu(x, self.convt[0].weight, bn, self.training)
         return self.conv_less(torch.cat((x_skip, x), 1), t)
 
 

@@ -286,16 +286,35 @@ def run_ours(args, rank, local_rank, world):
         else:
             kern["wgrad_ms"] = tk(lambda: Fm.conv3d_wgrad(x_op, dy_op, dtype, 1, D, H, W, ci, co))
         kern["reparam_fwd_ms"] = tk(lambda: Fm.reparam_fwd(layer, task, 1, ci, co, dtype, True, 256.0), it=50)
+        # K1 on the widest layer of the U-Net (bottle_block.conv2, 512 -> 512: 163 MB of experts) -- the shape at
+        # which the re-param kernel is actually HBM-bound (at 32 -> 32 it moves 1 MB and is launch/latency bound)
+        big = MoDEConv(5, T, 512, 512).to(dev)
+        lb, cb, ob = Fm._layer(*big._params())
+        kern["reparam_fwd_512_ms"] = tk(lambda: Fm.reparam_fwd(lb, task, 1, cb, ob, dtype, False, 256.0), it=10)
+        bytes_512 = 620.0 * 512 * 512 + 125.0 * 512 * 512 * (2 if use_umma else 4)
+        del big
     conv_ms = kern["conv_fwd_ms"]
     achieved = FLOP_CONV / (conv_ms * 1e-3) / 1e12
+    traffic = None
+    try:
+        with open(os.path.join(ROOT, "profiles", "r1_traffic.json")) as f:
+            tr = json.load(f)
+        key = "mode::conv3d_umma_kernel" if use_umma else "mode::conv3d_simt_kernel"
+        traffic = sum(t["dram_bytes"] for t in tr[key]) / len(tr[key])
+    except Exception:  # noqa: BLE001
+        traffic = None
     roofline = {"kernel": "conv3d_umma_kernel (K2 forward)" if use_umma else "conv3d_simt_kernel (K2 forward)",
                 "bound": "tensor", "achieved": achieved, "peak": tf_burst, "unit": "TFLOP/s",
-                "frac": achieved / tf_burst, "traffic": None, "peak_source": f"MEASURED_PEAKS.json bf16 burst ({peak_kind})",
+                "frac": achieved / tf_burst, "traffic": traffic,
+                "traffic_source": "ncu --set full dram__bytes_read+write per launch, profiles/r1_traffic.json",
+                "peak_source": f"MEASURED_PEAKS.json bf16 burst ({peak_kind})",
                 "algorithmic_flop_per_launch": FLOP_CONV,
                 "others": {"dgrad_TFLOPs": FLOP_CONV / (kern["conv_dgrad_ms"] * 1e-3) / 1e12,
                            "wgrad_TFLOPs": FLOP_CONV / (kern["wgrad_ms"] * 1e-3) / 1e12,
                            "reparam_fwd_GBs": (620.0 * CI * CO + 2 * 125 * CI * CO * (2 if use_umma else 4)) /
                            (kern["reparam_fwd_ms"] * 1e-3) / 1e9,
+                           "reparam_fwd_512x512_GBs": bytes_512 / (kern["reparam_fwd_512_ms"] * 1e-3) / 1e9,
+                           "reparam_fwd_512x512_frac_of_hbm": bytes_512 / (kern["reparam_fwd_512_ms"] * 1e-3) / 1e9 / hbm_gbs,
                            "hbm_peak_GBs": hbm_gbs, **{k: round(v, 4) for k, v in kern.items()}}}
 
     # ---- CPU baseline (rank 0, N=1 only): bounded sample of the same workload

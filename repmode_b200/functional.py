@@ -355,12 +355,14 @@ class BnReluFunction(torch.autograd.Function):
 
     @staticmethod
     @torch.amp.custom_fwd(device_type="cuda", cast_inputs=torch.float32)
-    def forward(ctx, y, weight, bias, running_mean, running_var, training):
+    def forward(ctx, y, weight, bias, running_mean, running_var, training, shard=None):
         _require_cuda(y)
         lib = _lib.load()
         yn = y.contiguous()                                    # [N,D,H,W,C] fp32
         c = yn.shape[-1]
         m_rows = yn.numel() // c
+        m_stat = shard.m_global if shard is not None else m_rows
+        ctx.shard = shard
         dev = yn.device
         scale = torch.empty(c, dtype=torch.float32, device=dev)
         shift = torch.empty(c, dtype=torch.float32, device=dev)
@@ -370,7 +372,9 @@ class BnReluFunction(torch.autograd.Function):
             mean = torch.empty(c, dtype=torch.float32, device=dev)
             invstd = torch.empty(c, dtype=torch.float32, device=dev)
             _lib.check(lib.mode_bn_stats(_p(yn), m_rows, c, _p(sums), _stream()), "mode_bn_stats")
-            _lib.check(lib.mode_bn_finalize(_p(sums), m_rows, c, _p(weight), _p(bias), BN_EPS, BN_MOMENTUM, _p(mean),
+            if shard is not None:
+                shard.all_reduce(sums)                         # every plane of a stride-2 level is owned: plain sum
+            _lib.check(lib.mode_bn_finalize(_p(sums), m_stat, c, _p(weight), _p(bias), BN_EPS, BN_MOMENTUM, _p(mean),
                                             _p(invstd), _p(scale), _p(shift), _p(running_mean), _p(running_var),
                                             _stream()), "mode_bn_finalize")
         else:
@@ -399,12 +403,23 @@ class BnReluFunction(torch.autograd.Function):
         dbeta = torch.empty(c, dtype=torch.float32, device=dev)
         dy = torch.empty_like(yn)
         ws = torch.empty(int(lib.mode_bn_bwd_workspace_bytes(c)), dtype=torch.uint8, device=dev)
-        _lib.check(lib.mode_bn_relu_bwd(_p(yn), _p(doutn), m_rows, c, _p(weight), _p(bias), _p(mean), _p(invstd),
-                                        _p(dgamma), _p(dbeta), _p(dy), None, None, _p(ws), _stream()), "mode_bn_relu_bwd")
-        return dy, dgamma, dbeta, None, None, None
+        shard = ctx.shard
+        planes = shard.planes(m_rows // (yn.shape[0] * yn.shape[1]), yn.shape[1]) if shard is not None else None
+        pl = ctypes.byref(planes) if planes is not None else None
+        _lib.check(lib.mode_bn_relu_bwd_reduce(_p(yn), _p(doutn), m_rows, c, _p(weight), _p(bias), _p(mean), _p(invstd),
+                                               pl, _p(ws), _stream()), "mode_bn_relu_bwd_reduce")
+        if shard is not None:
+            shard.all_reduce(ws[:16 * c].view(torch.float64))
+        _lib.check(lib.mode_bn_relu_bwd_apply(_p(yn), _p(doutn), m_rows, c, _p(weight), _p(bias), _p(mean), _p(invstd),
+                                              _p(dgamma), _p(dbeta), _p(dy), None, None, pl, _p(ws), _stream()),
+                   "mode_bn_relu_bwd_apply")
+        if shard is not None and shard.world() > 1:
+            dgamma /= shard.world()
+            dbeta /= shard.world()
+        return dy, dgamma, dbeta, None, None, None, None
 
 
-def down_conv_bn_relu(x, conv_w, bn, training):
+def down_conv_bn_relu(x, conv_w, bn, training, shard=None):
     """Conv3d(k=2, s=2, bias=False) + BatchNorm3d + ReLU (reference RepMode.py:80-84) on NDHWC data: the stride-2
     conv is a plain GEMM on the space-to-depth view ([voxels/8, 8*Ci] @ [8*Ci, Co], cuBLAS), BN+ReLU are the path's
     own kernels.  x: [N,C,D,H,W] any strides -> [N,Co,D/2,H/2,W/2] channels_last_3d."""
@@ -414,11 +429,11 @@ def down_conv_bn_relu(x, conv_w, bn, training):
     x8 = xn.reshape(n, d // 2, 2, h // 2, 2, w // 2, 2, c).permute(0, 1, 3, 5, 2, 4, 6, 7).reshape(-1, 8 * c)
     wm = conv_w.permute(2, 3, 4, 1, 0).reshape(8 * c, co)                     # [(kd,kh,kw,ci), co]
     y = (x8 @ wm.to(x8.dtype)).view(n, d // 2, h // 2, w // 2, co)
-    out = BnReluFunction.apply(y, bn.weight, bn.bias, bn.running_mean, bn.running_var, training)
+    out = BnReluFunction.apply(y, bn.weight, bn.bias, bn.running_mean, bn.running_var, training, shard)
     return out.permute(0, 4, 1, 2, 3)
 
 
-def up_conv_bn_relu(x, convt_w, bn, training):
+def up_conv_bn_relu(x, convt_w, bn, training, shard=None):
     """ConvTranspose3d(k=2, s=2, bias=False) + BatchNorm3d + ReLU (reference RepMode.py:97-101) on NDHWC data:
     [voxels, Ci] @ [Ci, 8*Co] (cuBLAS) followed by the depth-to-space scatter, then the path's BN+ReLU kernels."""
     xn = x.permute(0, 2, 3, 4, 1)
@@ -427,5 +442,5 @@ def up_conv_bn_relu(x, convt_w, bn, training):
     wm = convt_w.permute(0, 2, 3, 4, 1).reshape(c, 8 * co)                    # [ci, (kd,kh,kw,co)]
     y8 = (xn.reshape(-1, c) @ wm.to(xn.dtype)).view(n, d, h, w, 2, 2, 2, co)
     y = y8.permute(0, 1, 4, 2, 5, 3, 6, 7).reshape(n, 2 * d, 2 * h, 2 * w, co)
-    out = BnReluFunction.apply(y, bn.weight, bn.bias, bn.running_mean, bn.running_var, training)
+    out = BnReluFunction.apply(y, bn.weight, bn.bias, bn.running_mean, bn.running_var, training, shard)
     return out.permute(0, 4, 1, 2, 3)

@@ -52,3 +52,99 @@ def sharded_stage(stage, x_local, t, d_global, group=None):
                       group=group)
     a2 = Fm.mode_conv(a1, t, c2._params(), _bn(c2), c2.training, c2.conv_type, c2.precision, s2)
     return a2[:, :, 2:2 + dl]
+
+
+# ---------------------------------------------------------------------------------------------- whole U-Net
+class _AllGatherD(torch.autograd.Function):
+    """[N,C,dl,H,W] slabs -> the full [N,C,dl*world,H,W] volume on every rank.  Downstream of it the computation is
+    replicated but each rank's loss only covers its own slab, so the gradients arriving here are PARTIAL sums:
+    backward = sum over ranks, then keep the own slab (reduce-scatter)."""
+
+    @staticmethod
+    def forward(ctx, x_local, group):
+        ctx.group = group
+        world = dist.get_world_size(group)
+        parts = [torch.empty_like(x_local) for _ in range(world)]
+        dist.all_gather(parts, x_local.contiguous(), group=group)
+        return torch.cat(parts, dim=2)
+
+    @staticmethod
+    def backward(ctx, g):
+        g = g.contiguous()
+        dist.all_reduce(g, group=ctx.group)
+        world, rank = dist.get_world_size(ctx.group), dist.get_rank(ctx.group)
+        dl = g.shape[2] // world
+        return g[:, :, rank * dl:(rank + 1) * dl].contiguous(), None
+
+
+def _full_spec(n, d_local, h, w, d_global, group):
+    """ShardSpec of a halo-free slab tensor (stride-2 levels): every local plane is owned and valid."""
+    return Fm.ShardSpec(own=(0, d_local), valid=(0, d_local), m_global=n * d_global * h * w, group=group)
+
+
+def sharded_net_forward(net, x_local, t, d_global, group=None):
+    """Net.forward (reference RepMode.py:51-71) on a D-slab of one volume.  Levels whose local depth is at least the
+    halo (4 planes) run sharded (one halo exchange per two-conv stage, global BatchNorm statistics); deeper, tiny
+    levels are gathered and computed redundantly on every rank (their tensors are a few MB), then re-sliced on the
+    way up.  x_local: [N,1,dl,H,W]; returns this rank's [N,1,dl,H,W] slab of the prediction."""
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    rank = dist.get_rank(group) if dist.is_initialized() else 0
+    if world == 1:
+        return net(x_local, t)
+    t = t.to(device=x_local.device, dtype=torch.int32).reshape(-1)
+    enc = [net.encoder_block1, net.encoder_block2, net.encoder_block3, net.encoder_block4]
+    dec = [net.decoder_block4, net.decoder_block3, net.decoder_block2, net.decoder_block1]
+    n = x_local.shape[0]
+    training = net.training
+
+    def bump(bn):
+        if training and bn.num_batches_tracked is not None:
+            bn.num_batches_tracked.add_(1)
+
+    x = x_local
+    dg = d_global                       # global depth at the current level
+    sharded = True                      # is x a slab (True) or the replicated full tensor (False)?
+    skips = []
+    for blk in enc:
+        if sharded and dg // world < HALO:                      # too thin for a 4-plane halo: replicate from here down
+            x = _AllGatherD.apply(x, group)
+            sharded = False
+        if sharded:
+            x_skip = sharded_stage(blk.conv_more, x, t, dg, group)
+        else:
+            x_skip = blk.conv_more(x, t)
+        skips.append((x_skip, sharded))
+        bn = blk.conv_down[1]
+        bump(bn)
+        _, _, dl, h, w = x_skip.shape
+        spec = _full_spec(n, dl // 2, h // 2, w // 2, dg // 2, group) if sharded else None
+        x = Fm.down_conv_bn_relu(x_skip, blk.conv_down[0].weight, bn, training, spec)
+        dg //= 2
+    if sharded and dg // world < HALO:
+        x = _AllGatherD.apply(x, group)
+        sharded = False
+    x = sharded_stage(net.bottle_block, x, t, dg, group) if sharded else net.bottle_block(x, t)
+    for blk in dec:
+        x_skip, skip_sharded = skips.pop()
+        bn = blk.convt[1]
+        bump(bn)
+        if skip_sharded and not sharded:                        # back to slabs: keep this rank's planes of the replica
+            dl = x.shape[2] // world
+            x = x[:, :, rank * dl:(rank + 1) * dl]
+            sharded = True
+        _, _, dl, h, w = x.shape
+        spec = _full_spec(n, 2 * dl, 2 * h, 2 * w, 2 * dg, group) if sharded else None
+        x = Fm.up_conv_bn_relu(x, blk.convt[0].weight, bn, training, spec)
+        dg *= 2
+        xc = torch.cat((x_skip, x), 1)
+        x = sharded_stage(blk.conv_less, xc, t, dg, group) if sharded else blk.conv_less(xc, t)
+    # conv_out: a single 5^3 conv, no BatchNorm -> 2-plane halo
+    c = net.conv_out
+    if sharded:
+        dl = x.shape[2]
+        xe = Fm.from_ndhwc(par.HaloExchange.apply(Fm.to_ndhwc(x), 2, group))
+        y = Fm.mode_conv(xe, t, c._params(), None, c.training, c.conv_type, c.precision)
+        return y[:, :, 2:2 + dl]
+    y = c(x, t)
+    dl = y.shape[2] // world
+    return y[:, :, rank * dl:(rank + 1) * dl]

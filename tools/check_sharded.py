@@ -61,6 +61,39 @@ def main():
             print(f"[{precision}] world={world} max rel err {max(errs.values()):.3e}  (out {errs['out']:.2e}, dx {errs['dx']:.2e})",
                   flush=True)
         assert not bad, (precision, bad)
+    # ---- whole U-Net, D-sharded (levels thinner than the halo are replicated), forward + backward
+    import argparse
+    from repmode_b200.nn_modules import Net
+    torch.backends.cuda.matmul.allow_tf32 = False
+    for precision, tol in (("f32", 5e-4), ("f16", 5e-3)):
+        torch.manual_seed(1)
+        net = Net(argparse.Namespace(adopted_datasets=list(range(12)), gpu_ids=local), mult_chan=8).cuda().train()
+        for m in net.modules():
+            if hasattr(m, "precision"):
+                m.precision = precision
+        D, H, W = 16 * world, 32, 32
+        x = torch.randn(1, 1, D, H, W, device="cuda")
+        dout = torch.randn(1, 1, D, H, W, device="cuda")
+        t = torch.tensor([4], device="cuda")
+        sd0 = {k: v.clone() for k, v in net.state_dict().items()}
+        yr = net(x, t)
+        yr.backward(dout)
+        ref = {k: p.grad.clone() for k, p in net.named_parameters()}
+        net.load_state_dict(sd0)
+        for p in net.parameters():
+            p.grad = None
+        dl = D // world
+        yl = sharded.sharded_net_forward(net, x[:, :, rank * dl:(rank + 1) * dl].contiguous(), t, D)
+        yl.backward(dout[:, :, rank * dl:(rank + 1) * dl])
+        par.sync_gradients(list(net.parameters()))
+        errs = {"out": rel(yl, yr[:, :, rank * dl:(rank + 1) * dl])}
+        for k, p in net.named_parameters():
+            errs[k] = rel(p.grad, ref[k])
+        bad = {k: v for k, v in errs.items() if not (v <= tol)}
+        worst_k = max(errs, key=errs.get)
+        if rank == 0:
+            print(f"[net {precision}] world={world} out {errs['out']:.2e}  worst grad {worst_k} {errs[worst_k]:.2e}", flush=True)
+        assert not bad, (precision, bad)
     dist.barrier()
     if rank == 0:
         print("SHARDED_CHECK_OK", worst, flush=True)

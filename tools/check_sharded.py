@@ -61,6 +61,56 @@ def main():
             print(f"[{precision}] world={world} max rel err {max(errs.values()):.3e}  (out {errs['out']:.2e}, dx {errs['dx']:.2e})",
                   flush=True)
         assert not bad, (precision, bad)
+    # ---- unit checks of the sharded stride-2 levels and of the gather / re-slice transitions (fp32)
+    from repmode_b200 import functional as Fm
+    torch.manual_seed(2)
+    N, C, D, H, W = 1, 16, 8 * world, 16, 16
+    dl = D // world
+    lo = rank * dl
+    conv = torch.nn.Conv3d(C, C, 2, stride=2, bias=False).cuda()
+    convt = torch.nn.ConvTranspose3d(C, C // 2, 2, stride=2, bias=False).cuda()
+    bn1, bn2 = torch.nn.BatchNorm3d(C).cuda().train(), torch.nn.BatchNorm3d(C // 2).cuda().train()
+    with torch.no_grad():
+        for bn in (bn1, bn2):
+            bn.weight.uniform_(0.5, 1.5); bn.bias.uniform_(-0.5, 0.5)
+    x = torch.randn(N, C, D, H, W, device="cuda")
+    for name, fn, w_, bn, oc in (("down", Fm.down_conv_bn_relu, conv.weight, bn1, C),
+                                 ("up", Fm.up_conv_bn_relu, convt.weight, bn2, C // 2)):
+        f = 0.5 if name == "down" else 2.0
+        go = torch.randn(N, oc, int(D * f), int(H * f), int(W * f), device="cuda")
+        xr = x.clone().requires_grad_(True)
+        for p_ in (w_, bn.weight, bn.bias):
+            p_.grad = None
+        yr = fn(xr, w_, bn, True)
+        yr.backward(go)
+        ref = [xr.grad.clone(), w_.grad.clone(), bn.weight.grad.clone(), bn.bias.grad.clone()]
+        for p_ in (w_, bn.weight, bn.bias):
+            p_.grad = None
+        xl = x[:, :, lo:lo + dl].clone().requires_grad_(True)
+        spec = sharded._full_spec(N, int(dl * f), int(H * f), int(W * f), int(D * f), None)
+        yl = fn(xl, w_, bn, True, spec)
+        ol, oh = int(lo * f), int((lo + dl) * f)
+        yl.backward(go[:, :, ol:oh])
+        par.sync_gradients([w_, bn.weight, bn.bias])
+        e = [rel(yl, yr[:, :, ol:oh]), rel(xl.grad, ref[0][:, :, lo:lo + dl]), rel(w_.grad, ref[1]),
+             rel(bn.weight.grad, ref[2]), rel(bn.bias.grad, ref[3])]
+        if rank == 0:
+            print(f"[unit {name}] out {e[0]:.2e} dx {e[1]:.2e} dW {e[2]:.2e} dgamma {e[3]:.2e} dbeta {e[4]:.2e}", flush=True)
+    # gather -> replicated op -> re-slice
+    lin = torch.nn.Conv3d(C, C, 1, bias=False).cuda()
+    xr = x.clone().requires_grad_(True)
+    go = torch.randn(N, C, D, H, W, device="cuda")
+    yr = torch.relu(lin(xr)); yr.backward(go)
+    ref_dx, ref_dw = xr.grad.clone(), lin.weight.grad.clone()
+    lin.weight.grad = None
+    xl = x[:, :, lo:lo + dl].clone().requires_grad_(True)
+    yl = torch.relu(lin(sharded._AllGatherD.apply(xl, None)))[:, :, lo:lo + dl]
+    yl.backward(go[:, :, lo:lo + dl])
+    par.sync_gradients([lin.weight])
+    if rank == 0:
+        print(f"[unit gather] out {rel(yl, yr[:, :, lo:lo + dl]):.2e} dx {rel(xl.grad, ref_dx[:, :, lo:lo + dl]):.2e} "
+              f"dW {rel(lin.weight.grad, ref_dw):.2e}", flush=True)
+
     # ---- whole U-Net, D-sharded (levels thinner than the halo are replicated), forward + backward
     import argparse
     from repmode_b200.nn_modules import Net
@@ -90,10 +140,11 @@ def main():
         for k, p in net.named_parameters():
             errs[k] = rel(p.grad, ref[k])
         bad = {k: v for k, v in errs.items() if not (v <= tol)}
-        worst_k = max(errs, key=errs.get)
         if rank == 0:
-            print(f"[net {precision}] world={world} out {errs['out']:.2e}  worst grad {worst_k} {errs[worst_k]:.2e}", flush=True)
-        assert not bad, (precision, bad)
+            top = sorted(errs.items(), key=lambda kv: -kv[1])[:6]
+            print(f"[net {precision}] world={world} out {errs['out']:.2e}  n_bad {len(bad)}/{len(errs)}  worst: "
+                  + ", ".join(f"{k} {v:.1e}" for k, v in top), flush=True)
+        assert not bad, (precision, len(bad))
     dist.barrier()
     if rank == 0:
         print("SHARDED_CHECK_OK", worst, flush=True)

@@ -82,16 +82,22 @@ def _full_spec(n, d_local, h, w, d_global, group):
     return Fm.ShardSpec(own=(0, d_local), valid=(0, d_local), m_global=n * d_global * h * w, group=group)
 
 
-def sharded_net_forward(net, x_local, t, d_global, group=None):
+def sharded_net_forward(net, x_local, t, d_global, group=None, probe=None, replicated=False):
     """Net.forward (reference RepMode.py:51-71) on a D-slab of one volume.  Levels whose local depth is at least the
     halo (4 planes) run sharded (one halo exchange per two-conv stage, global BatchNorm statistics); deeper, tiny
     levels are gathered and computed redundantly on every rank (their tensors are a few MB), then re-sliced on the
     way up.  x_local: [N,1,dl,H,W]; returns this rank's [N,1,dl,H,W] slab of the prediction."""
     world = dist.get_world_size(group) if dist.is_initialized() else 1
     rank = dist.get_rank(group) if dist.is_initialized() else 0
-    if world == 1:
+    if world == 1 and probe is None:
         return net(x_local, t)
     t = t.to(device=x_local.device, dtype=torch.int32).reshape(-1)
+
+    def keep(name, v):              # diagnostics: remember (and keep the gradient of) named intermediates
+        if probe is not None:
+            v.retain_grad()
+            probe[name] = v
+        return v
     enc = [net.encoder_block1, net.encoder_block2, net.encoder_block3, net.encoder_block4]
     dec = [net.decoder_block4, net.decoder_block3, net.decoder_block2, net.decoder_block1]
     n = x_local.shape[0]
@@ -103,9 +109,9 @@ def sharded_net_forward(net, x_local, t, d_global, group=None):
 
     x = x_local
     dg = d_global                       # global depth at the current level
-    sharded = True                      # is x a slab (True) or the replicated full tensor (False)?
+    sharded = not (replicated or world == 1)   # is x a slab (True) or the replicated full tensor (False)?
     skips = []
-    for blk in enc:
+    for li, blk in enumerate(enc):
         if sharded and dg // world < HALO:                      # too thin for a 4-plane halo: replicate from here down
             x = _AllGatherD.apply(x, group)
             sharded = False
@@ -113,18 +119,19 @@ def sharded_net_forward(net, x_local, t, d_global, group=None):
             x_skip = sharded_stage(blk.conv_more, x, t, dg, group)
         else:
             x_skip = blk.conv_more(x, t)
+        keep(f"enc{li + 1}.skip", x_skip)
         skips.append((x_skip, sharded))
         bn = blk.conv_down[1]
         bump(bn)
         _, _, dl, h, w = x_skip.shape
         spec = _full_spec(n, dl // 2, h // 2, w // 2, dg // 2, group) if sharded else None
-        x = Fm.down_conv_bn_relu(x_skip, blk.conv_down[0].weight, bn, training, spec)
+        x = keep(f"enc{li + 1}.down", Fm.down_conv_bn_relu(x_skip, blk.conv_down[0].weight, bn, training, spec))
         dg //= 2
     if sharded and dg // world < HALO:
         x = _AllGatherD.apply(x, group)
         sharded = False
-    x = sharded_stage(net.bottle_block, x, t, dg, group) if sharded else net.bottle_block(x, t)
-    for blk in dec:
+    x = keep("bottle", sharded_stage(net.bottle_block, x, t, dg, group) if sharded else net.bottle_block(x, t))
+    for li, blk in enumerate(dec):
         x_skip, skip_sharded = skips.pop()
         bn = blk.convt[1]
         bump(bn)
@@ -134,10 +141,10 @@ def sharded_net_forward(net, x_local, t, d_global, group=None):
             sharded = True
         _, _, dl, h, w = x.shape
         spec = _full_spec(n, 2 * dl, 2 * h, 2 * w, 2 * dg, group) if sharded else None
-        x = Fm.up_conv_bn_relu(x, blk.convt[0].weight, bn, training, spec)
+        x = keep(f"dec{4 - li}.up", Fm.up_conv_bn_relu(x, blk.convt[0].weight, bn, training, spec))
         dg *= 2
         xc = torch.cat((x_skip, x), 1)
-        x = sharded_stage(blk.conv_less, xc, t, dg, group) if sharded else blk.conv_less(xc, t)
+        x = keep(f"dec{4 - li}.out", sharded_stage(blk.conv_less, xc, t, dg, group) if sharded else blk.conv_less(xc, t))
     # conv_out: a single 5^3 conv, no BatchNorm -> 2-plane halo
     c = net.conv_out
     if sharded:

@@ -126,15 +126,27 @@ def main():
         dout = torch.randn(1, 1, D, H, W, device="cuda")
         t = torch.tensor([4], device="cuda")
         sd0 = {k: v.clone() for k, v in net.state_dict().items()}
-        yr = net(x, t)
+        pr_ref, pr_sh = {}, {}
+        yr = sharded.sharded_net_forward(net, x, t, D, probe=pr_ref, replicated=True)
         yr.backward(dout)
         ref = {k: p.grad.clone() for k, p in net.named_parameters()}
         net.load_state_dict(sd0)
         for p in net.parameters():
             p.grad = None
         dl = D // world
-        yl = sharded.sharded_net_forward(net, x[:, :, rank * dl:(rank + 1) * dl].contiguous(), t, D)
+        yl = sharded.sharded_net_forward(net, x[:, :, rank * dl:(rank + 1) * dl].contiguous(), t, D, probe=pr_sh)
         yl.backward(dout[:, :, rank * dl:(rank + 1) * dl])
+        if rank == 0:
+            msgs = []
+            for k in pr_ref:
+                a, b = pr_sh[k], pr_ref[k]
+                if a.shape[2] == b.shape[2]:            # replicated level: gradients are partial sums -> skip grads
+                    msgs.append(f"{k}: act {rel(a, b):.1e} (replicated)")
+                else:
+                    w_ = a.shape[2]
+                    msgs.append(f"{k}: act {rel(a, b[:, :, rank * w_:(rank + 1) * w_]):.1e} "
+                                f"grad {rel(a.grad, b.grad[:, :, rank * w_:(rank + 1) * w_]):.1e}")
+            print(f"[net {precision} probe] " + " | ".join(msgs), flush=True)
         par.sync_gradients(list(net.parameters()))
         errs = {"out": rel(yl, yr[:, :, rank * dl:(rank + 1) * dl])}
         for k, p in net.named_parameters():

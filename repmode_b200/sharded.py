@@ -153,5 +153,7 @@ def sharded_net_forward(net, x_local, t, d_global, group=None, probe=None, repli
         y = Fm.mode_conv(xe, t, c._params(), None, c.training, c.conv_type, c.precision)
         return y[:, :, 2:2 + dl]
     y = c(x, t)
+    if replicated or world == 1:
+        return y
     dl = y.shape[2] // world
     return y[:, :, rank * dl:(rank + 1) * dl]

@@ -116,6 +116,9 @@ def conv3d(x, dtype, w, sample_u, n, d, h, wd, k, nout, out_scale_dev=None, bn_s
     return y
 
 
+COLL_LOG = None      # diagnostics: set to a list to record the sequence of in-graph collectives (tag, numel)
+
+
 class ShardSpec:
     """Plane bookkeeping of one D-sharded slab tensor [N, D_local_ext, H, W, C] (see mode_planes_t): owned planes
     [own_lo, own_hi), planes inside the global volume [valid_lo, valid_hi), global voxel count per channel and the
@@ -131,9 +134,11 @@ class ShardSpec:
         import torch.distributed as dist
         return dist.get_world_size(self.group) if dist.is_initialized() else 1
 
-    def all_reduce(self, t):
+    def all_reduce(self, t, tag=""):
         import torch.distributed as dist
         if dist.is_initialized() and dist.get_world_size(self.group) > 1:
+            if COLL_LOG is not None:
+                COLL_LOG.append((tag, t.numel()))
             dist.all_reduce(t, group=self.group)
 
 
@@ -229,7 +234,7 @@ class ModeConvFunction(torch.autograd.Function):
         planes = shard.planes(h * wd, d) if shard is not None else None
         m_stat = shard.m_global if shard is not None else m_rows
         if shard is not None and bn_train:
-            shard.all_reduce(sums)            # global statistics over owned voxels of every slab
+            shard.all_reduce(sums, "mode.fwd")            # global statistics over owned voxels of every slab
         mean = invstd = None
         if normal:
             scale = torch.empty(co, dtype=torch.float32, device=dev)
@@ -288,7 +293,7 @@ class ModeConvFunction(torch.autograd.Function):
             _lib.check(lib.mode_bn_relu_bwd_reduce(_p(y), _p(doutn), m_rows, co, _p(bn_w), _p(bn_b), _p(mean), _p(invstd),
                                                    pl, _p(ws), _stream()), "mode_bn_relu_bwd_reduce")
             if shard is not None:
-                shard.all_reduce(ws[:16 * co].view(torch.float64))      # {sum dz, sum dz*xhat} over every slab
+                shard.all_reduce(ws[:16 * co].view(torch.float64), "mode.bwd")      # {sum dz, sum dz*xhat} over every slab
             dy_f32 = None
             if use_umma:
                 dy_op = torch.empty((n, d, h, wd, co), dtype=torch.float16, device=dev)
@@ -373,7 +378,7 @@ class BnReluFunction(torch.autograd.Function):
             invstd = torch.empty(c, dtype=torch.float32, device=dev)
             _lib.check(lib.mode_bn_stats(_p(yn), m_rows, c, _p(sums), _stream()), "mode_bn_stats")
             if shard is not None:
-                shard.all_reduce(sums)                         # every plane of a stride-2 level is owned: plain sum
+                shard.all_reduce(sums, "bn.fwd")                         # every plane of a stride-2 level is owned: plain sum
             _lib.check(lib.mode_bn_finalize(_p(sums), m_stat, c, _p(weight), _p(bias), BN_EPS, BN_MOMENTUM, _p(mean),
                                             _p(invstd), _p(scale), _p(shift), _p(running_mean), _p(running_var),
                                             _stream()), "mode_bn_finalize")
@@ -404,12 +409,22 @@ class BnReluFunction(torch.autograd.Function):
         dy = torch.empty_like(yn)
         ws = torch.empty(int(lib.mode_bn_bwd_workspace_bytes(c)), dtype=torch.uint8, device=dev)
         shard = ctx.shard
+        if shard is not None and os.environ.get("REPMODE_SHARD_DEBUG", "0") == "1":
+            # diagnostics only: the same sharded BatchNorm backward spelled with torch ops
+            xh = (yn - mean) * invstd
+            dz = torch.where(xh * weight + bias > 0, doutn, torch.zeros_like(doutn))
+            red = torch.stack([dz.double().sum(dim=(0, 1, 2, 3)), (dz * xh).double().sum(dim=(0, 1, 2, 3))]).reshape(-1)
+            shard.all_reduce(red, "bn.bwd.debug")
+            a = (red[:c] / shard.m_global).float()
+            b = (red[c:] / shard.m_global).float()
+            dy_t = weight * invstd * (dz - a - xh * b)
+            return dy_t, (red[c:] / shard.world()).float(), (red[:c] / shard.world()).float(), None, None, None, None
         planes = shard.planes(m_rows // (yn.shape[0] * yn.shape[1]), yn.shape[1]) if shard is not None else None
         pl = ctypes.byref(planes) if planes is not None else None
         _lib.check(lib.mode_bn_relu_bwd_reduce(_p(yn), _p(doutn), m_rows, c, _p(weight), _p(bias), _p(mean), _p(invstd),
                                                pl, _p(ws), _stream()), "mode_bn_relu_bwd_reduce")
         if shard is not None:
-            shard.all_reduce(ws[:16 * c].view(torch.float64))
+            shard.all_reduce(ws[:16 * c].view(torch.float64), "bn.bwd")
         _lib.check(lib.mode_bn_relu_bwd_apply(_p(yn), _p(doutn), m_rows, c, _p(weight), _p(bias), _p(mean), _p(invstd),
                                               _p(dgamma), _p(dbeta), _p(dy), None, None, pl, _p(ws), _stream()),
                    "mode_bn_relu_bwd_apply")

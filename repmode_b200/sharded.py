@@ -10,7 +10,7 @@ Backward is the autograd mirror: dgrad/wgrad on the extended slabs, BN-backward 
 terms applied on owned planes only, halo gradients sent back to their owners and accumulated; parameter
 gradients are partial per rank and summed by the usual data-parallel all-reduce (parallel.sync_gradients).
 Verified on CPU/gloo against the unsharded oracle (tests/test_parallel_cpu.py) and on 2 GPUs against the
-unsharded kernels (tools/check_sharded.py).
+unsharded kernels (tests/check_sharded.py).
 """
 import torch
 import torch.distributed as dist

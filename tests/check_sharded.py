@@ -1,6 +1,6 @@
 """Multi-GPU check (run under torchrun, one rank per GPU): the D-sharded two-conv stage (repmode_b200/sharded.py)
 against the same stage run unsharded on one GPU, forward and backward (dx and all parameter gradients after the
-data-parallel gradient sum).   torchrun --nproc-per-node 2 tools/check_sharded.py"""
+data-parallel gradient sum).   torchrun --nproc-per-node 2 tests/check_sharded.py"""
 import os
 import sys
 
@@ -161,6 +161,20 @@ def main():
                                 f"grad {rel(a.grad, b.grad[:, :, rank * w_:(rank + 1) * w_]):.1e}")
             print(f"[net {precision} probe] " + " | ".join(msgs), flush=True)
         par.sync_gradients(list(net.parameters()))
+        # arbiter: the torch restatement of the reference (oracle/mode_torch.py) with autograd, fp32, no TF32
+        from oracle import mode_torch as orc
+        torch.backends.cudnn.allow_tf32 = False
+        po = {k: (v.clone().requires_grad_(True) if v.dtype.is_floating_point and k in dict(net.named_parameters())
+                  else v.clone()) for k, v in sd0.items()}
+        yo = orc.net_forward(po, x, t.to(torch.int64), True)
+        yo.backward(dout)
+        e_ref = {k: rel(ref[k], po[k].grad) for k, _ in net.named_parameters()}
+        e_sh = {k: rel(pp.grad, po[k].grad) for k, pp in net.named_parameters()}
+        if rank == 0:
+            for nm, e in (("unsharded-vs-oracle", e_ref), ("sharded-vs-oracle", e_sh)):
+                top = sorted(e.items(), key=lambda kv: -kv[1])[:4]
+                print(f"[net {precision} {nm}] out {rel(yr, yo):.1e} n_bad {sum(v > tol for v in e.values())}/{len(e)} worst: "
+                      + ", ".join(f"{k} {v:.1e}" for k, v in top), flush=True)
         errs = {"out": rel(yl, yr[:, :, rank * dl:(rank + 1) * dl])}
         for k, p in net.named_parameters():
             errs[k] = rel(p.grad, ref[k])

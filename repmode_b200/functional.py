@@ -409,16 +409,6 @@ class BnReluFunction(torch.autograd.Function):
         dy = torch.empty_like(yn)
         ws = torch.empty(int(lib.mode_bn_bwd_workspace_bytes(c)), dtype=torch.uint8, device=dev)
         shard = ctx.shard
-        if shard is not None and os.environ.get("REPMODE_SHARD_DEBUG", "0") == "1":
-            # diagnostics only: the same sharded BatchNorm backward spelled with torch ops
-            xh = (yn - mean) * invstd
-            dz = torch.where(xh * weight + bias > 0, doutn, torch.zeros_like(doutn))
-            red = torch.stack([dz.double().sum(dim=(0, 1, 2, 3)), (dz * xh).double().sum(dim=(0, 1, 2, 3))]).reshape(-1)
-            shard.all_reduce(red, "bn.bwd.debug")
-            a = (red[:c] / shard.m_global).float()
-            b = (red[c:] / shard.m_global).float()
-            dy_t = weight * invstd * (dz - a - xh * b)
-            return dy_t, (red[c:] / shard.world()).float(), (red[:c] / shard.world()).float(), None, None, None, None
         planes = shard.planes(m_rows // (yn.shape[0] * yn.shape[1]), yn.shape[1]) if shard is not None else None
         pl = ctypes.byref(planes) if planes is not None else None
         _lib.check(lib.mode_bn_relu_bwd_reduce(_p(yn), _p(doutn), m_rows, c, _p(weight), _p(bias), _p(mean), _p(invstd),

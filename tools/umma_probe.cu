@@ -198,6 +198,80 @@ extern "C" int probe_mma_rate(const void* img_dev, uint32_t img_bytes, uint64_t 
 }
 
 // ------------------------------------------------------------------------------------------------
+// probe_mma_rate_pair: the same issue-rate probe with a CTA pair (cta_group::2, M = 256): each CTA holds its own
+// 128 A rows and N/2 of the B rows; the leader issues, the commit is multicast to both CTAs.
+template <int NACC>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128, 1)
+probe_rate_pair_kernel(const uint8_t* __restrict__ img, uint32_t img_bytes, uint64_t adesc, uint64_t bdesc,
+                       uint32_t idesc, RateOffs offs, uint32_t acc_cols, uint32_t repeat,
+                       long long* __restrict__ cycles, int* __restrict__ status) {
+    extern __shared__ uint8_t smem_raw[];
+    __shared__ uint64_t mbar;
+    __shared__ uint32_t tmem_base_slot;
+    const uint32_t raw = smem_u32(smem_raw);
+    const uint32_t base = (raw + 1023u) & ~1023u;
+    uint8_t* smem = smem_raw + (base - raw);
+    for (uint32_t i = threadIdx.x * 16; i < img_bytes; i += blockDim.x * 16)
+        *reinterpret_cast<uint4*>(smem + i) = *reinterpret_cast<const uint4*>(img + i);
+    fence_proxy_async();
+    const uint32_t warp = threadIdx.x >> 5;
+    const uint32_t rank = cluster_ctarank();
+    if (warp == 0) tmem_alloc_pair<512>(smem_u32(&tmem_base_slot));
+    if (threadIdx.x == 32) { mbar_init(smem_u32(&mbar), 1); fence_mbar_init(); }
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();
+    tc_fence_after();
+    const uint32_t tmem = tmem_base_slot;
+    if (threadIdx.x == 0 && rank == 0) {
+        const uint64_t a0 = adesc + (base >> 4), b0 = bdesc + (base >> 4);
+        uint64_t ad[8], bd[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { ad[j] = a0 + offs.a[j]; bd[j] = b0 + offs.b[j]; }
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+            mma_f16_ss_pair(tmem + (j % NACC) * acc_cols, ad[j], bd[j], idesc, j >= NACC ? 1u : 0u);
+        const long long t0 = clock64();
+        for (uint32_t r = 0; r < repeat; ++r) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) mma_f16_ss_pair(tmem + (j % NACC) * acc_cols, ad[j], bd[j], idesc, 1u);
+        }
+        const long long t_issue = clock64();
+        mma_commit_pair(smem_u32(&mbar), 3u);
+        cycles[1] = t_issue - t0;
+        cycles[2] = t0;
+    }
+    bool ok = mbar_wait(smem_u32(&mbar), 0, 1u << 26);
+    if (threadIdx.x == 0 && rank == 0) cycles[0] = clock64() - cycles[2];
+    if (threadIdx.x == 0 && !ok) status[0] = 1 + (int)rank;
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();
+    if (warp == 0) tmem_dealloc_pair<512>(tmem);
+}
+
+extern "C" int probe_mma_rate_pair(const void* img_dev, uint32_t img_bytes, uint64_t adesc, uint64_t bdesc,
+                                   uint32_t idesc, const uint32_t* a_offs16, const uint32_t* b_offs16, int nacc,
+                                   uint32_t acc_cols, uint32_t repeat, long long* cycles_dev, int* status_dev) {
+    const int smem = 200 * 1024;
+    RateOffs offs;
+    for (int j = 0; j < 8; ++j) { offs.a[j] = a_offs16[j]; offs.b[j] = b_offs16[j]; }
+    CK(cudaMemset(status_dev, 0, sizeof(int)));
+#define LAUNCH_RATE2(NA)                                                                                          \
+    do {                                                                                                          \
+        CK(cudaFuncSetAttribute(probe_rate_pair_kernel<NA>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));   \
+        probe_rate_pair_kernel<NA><<<2, 128, smem>>>((const uint8_t*)img_dev, img_bytes, adesc, bdesc, idesc, offs, \
+                                                     acc_cols, repeat, cycles_dev, status_dev);                   \
+    } while (0)
+    if (nacc == 1) LAUNCH_RATE2(1);
+    else if (nacc == 2) LAUNCH_RATE2(2);
+    else { snprintf(g_err, sizeof(g_err), "nacc must be 1 or 2"); return -1; }
+    CK(cudaGetLastError());
+    CK(cudaDeviceSynchronize());
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
 // probe_tma: one tiled TMA load of a (<=5-d) box into shared memory, then dump the bytes.
 __global__ void __launch_bounds__(128, 1)
 probe_tma_kernel(const __grid_constant__ CUtensorMap map, int c0, int c1, int c2, int c3, int c4, uint32_t dst_off,

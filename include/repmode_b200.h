@@ -112,7 +112,8 @@ int mode_reparam_bwd(const mode_layer_t* layer_host, const int32_t* task_ids, co
  *   training statistics, RepMode.py:147) -- fused so y is not re-read -- over the d-planes
  *   [stat_d_lo, stat_d_hi) only (the OWNED planes of a D-sharded slab; pass 0, D for the whole tensor).
  *   impl: 0 = auto, 1 = SIMT fp32 direct conv (any shape, fp32 operands only), 2 = tcgen05 implicit GEMM
- *   (fp16 operands, K % 32 == 0, Nout % 16 == 0).
+ *   (fp16 operands, K % 32 == 0, Nout % 32 == 0, W % 8 == 0; picks the CTA-pair kernel for large volumes),
+ *   3 = force the single-CTA tcgen05 kernel, 4 = force the CTA-pair (cta_group::2) kernel.
  */
 int mode_conv3d(const void* x, mode_dtype_t x_dtype, const void* w, const int32_t* sample_u, float* y,
                 int32_t N, int32_t D, int32_t H, int32_t W, int32_t K, int32_t Nout, float out_scale,

@@ -1,0 +1,524 @@
+// K2 / K3, CTA-pair version: the 5x5x5 'same' convolution (and, with K1's dgrad pack, its input gradient) on
+// tcgen05.mma.cta_group::2 -- two SMs of a cluster execute ONE M = 256 MMA, each bringing its own 128 A rows and
+// half of the B rows.  Replaces F.conv3d(x[i:i+1], w[i], padding='same') (fnet/nn_modules/RepMode.py:204-210 in
+// the reference tree) exactly like conv_umma.cu; this file is the fast path for large volumes.
+//
+// Why a pair: measured on B200 (tools/probe_pair.py, profiles/probe_r1.md) a single-CTA SS-mode MMA costs
+// max(93, 42 + N/2) cycles -- the 4 KB A read is exposed -- while the pair instruction costs max(44, N/2):
+// N = 160 runs at 80 cycles instead of 122, i.e. at the full tensor rate.
+//
+// Mapping
+//   * the pair owns an 8(w) x 32(h) patch column: CTA rank r computes the 8 x 16 patch at h0 + 16 r (its 128 A rows).
+//   * "march": the pair walks its d-range plane by plane.  Input plane p feeds output planes q = p-2 .. p+2 with the
+//     kd taps in DESCENDING order (K1's stage-major pack), so EVERY plane issues the same N = 5 * 32 = 160 wide MMA
+//     into five neighbouring 32-column accumulator slots of TMEM.  Output planes outside the run's [da, db) -- and
+//     outside the volume -- are ordinary slots whose content is thrown away ("garbage slots"); no partial windows,
+//     hence the B operand splits 80 + 80 rows over the pair at a fixed address.
+//   * accumulator slots are circular with period 12 (+4 overflow slots so a window never wraps: a plane whose window
+//     starts in slots 8..11 spills into slots 12..15, which the epilogue adds to slots 0..3 when it drains them).
+//     Planes are processed in groups of 4; after a group the 4 output planes it completed are drained and re-zeroed
+//     by the epilogue warps of BOTH CTAs while the leader already issues the next group (12 = 4 draining + 8 live).
+//   * only planes inside the volume are ever loaded or multiplied; a run that starts or stops inside the volume pays
+//     2 extra planes on that side (the only redundant work).
+// Roles per CTA (256 threads): warp 0 activation-plane TMA producer, warp 3 weight producer (each CTA copies its
+//   half of every weight stage), warp 2 TMEM allocator, warps 4-7 epilogue.  Warp 1: in the leader (cluster rank 0)
+//   the single MMA-issuing thread; in the peer a relay that forwards "my plane / my weight half has landed" to the
+//   leader's barriers.  Slot release (tcgen05.commit) is multicast to both CTAs.
+// Roofline: tensor-pipe bound; algorithmic work 2*125*K*Nout FLOP per output voxel.
+#include <cuda.h>
+#include <stdlib.h>
+
+#include <algorithm>
+#include <array>
+#include <map>
+#include <mutex>
+#include <tuple>
+
+#include "common.cuh"
+#include "ptx_sm100.cuh"
+
+namespace mode {
+
+using namespace sm100;
+
+namespace cp {
+constexpr int TW = 8, TH = 16;                 // output patch per CTA
+constexpr int BW = TW + 4, BH = TH + 4;        // haloed brick
+constexpr int ROWB = 64;                       // bytes per voxel row (32 fp16 channels)
+constexpr int PLANE_BYTES = BH * BW * ROWB;    // 15360
+constexpr int NT = 32;                         // output channels per pass (one accumulator slot = 32 columns)
+constexpr int GROUP = 4;                       // input planes per group
+constexpr int RING = 12;                       // plane ring (3 groups deep)
+constexpr int WST = 6;                         // weight stages
+constexpr int WST_BYTES = 5 * NT * ROWB / 2;   // this CTA's half of one (chunk, kh, kw) stage: 80 rows = 5120 B
+constexpr int PERIOD = 12;                     // circular accumulator slots (+4 overflow)
+constexpr int THREADS = 256;
+constexpr int MAX_CLUSTERS = 80;
+// shared-memory map (offsets from the 1024-aligned base)
+constexpr uint32_t PLANE_OFF = 0;
+constexpr uint32_t W_OFF = RING * PLANE_BYTES;                    // 184320
+constexpr uint32_t BAR_OFF = W_OFF + WST * WST_BYTES;             // 215040
+constexpr uint32_t BN_OFF = BAR_OFF + 1024;
+constexpr uint32_t TOTAL = BN_OFF + 2 * NT * sizeof(double);
+}  // namespace cp
+
+struct PairParams {
+    const __half* w;             // stage-major fp16 pack, all Nout rows
+    const int32_t* sample_u;
+    float* y;                    // [N,D,H,W,Nout]
+    double* bn_sums;             // [2*Nout] or null
+    const float* out_scale_dev;
+    float out_scale;
+    int N, D, H, W, K, Nout;
+    int stat_lo, stat_hi;
+    int tiles_w, tiles_h2;       // pair patches: 8 wide, 32 high
+    int32_t bounds[cp::MAX_CLUSTERS + 1];   // cluster c owns plane-units [bounds[c], bounds[c+1]) of (n, th2, tw, d)
+    int* error_flag;
+    long long* prof;
+};
+
+// A "run" is a contiguous d-range [da, db) of one patch column; every role of both CTAs walks the same runs.
+struct RunWalker {
+    int64_t u, uend;
+    int D, tiles_w, tiles_h2;
+    __device__ RunWalker(const PairParams& P, int cluster)
+        : u(P.bounds[cluster]), uend(P.bounds[cluster + 1]), D(P.D), tiles_w(P.tiles_w), tiles_h2(P.tiles_h2) {}
+    __device__ bool next(int& n, int& h0, int& w0, int& da, int& db) {
+        if (u >= uend) return false;
+        const int64_t col = u / D;
+        da = (int)(u - col * D);
+        db = (int)min((int64_t)D, da + (uend - u));
+        u += db - da;
+        w0 = (int)(col % tiles_w) * cp::TW;
+        h0 = (int)((col / tiles_w) % tiles_h2) * (2 * cp::TH);
+        n = (int)(col / ((int64_t)tiles_w * tiles_h2));
+        return true;
+    }
+};
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(cp::THREADS, 1)
+conv3d_pair_kernel(const __grid_constant__ CUtensorMap xmap, const PairParams P) {
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t raw = smem_u32(smem_raw);
+    const uint32_t base = (raw + 1023u) & ~1023u;
+    uint8_t* smem = smem_raw + (base - raw);
+    const uint32_t bars = base + cp::BAR_OFF;
+    // barrier table (8 bytes each); the *_peer and tmem_empty barriers are only used in the leader
+    const uint32_t plane_full = bars, plane_peer = bars + 8 * cp::RING, plane_empty = bars + 16 * cp::RING;
+    const uint32_t w_full = bars + 24 * cp::RING, w_peer = w_full + 8 * cp::WST, w_empty = w_full + 16 * cp::WST;
+    const uint32_t tmem_full = w_full + 24 * cp::WST, tmem_empty = tmem_full + 16;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + cp::BAR_OFF + 960);
+    double* s_bn = reinterpret_cast<double*>(smem + cp::BN_OFF);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank();
+    const int cluster = blockIdx.x >> 1;
+    const int n0 = blockIdx.y * cp::NT;
+    const int nchunk = P.K / 32;
+    const uint64_t ts_entry = (P.prof != nullptr && threadIdx.x == 0) ? globaltimer_ns() : 0;
+
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < cp::RING; ++i) {
+            mbar_init(plane_full + 8 * i, 1); mbar_init(plane_peer + 8 * i, 1); mbar_init(plane_empty + 8 * i, 1);
+        }
+        for (int i = 0; i < cp::WST; ++i) {
+            mbar_init(w_full + 8 * i, 1); mbar_init(w_peer + 8 * i, 1); mbar_init(w_empty + 8 * i, 1);
+        }
+        for (int i = 0; i < 2; ++i) { mbar_init(tmem_full + 8 * i, 1); mbar_init(tmem_empty + 8 * i, 8); }
+        fence_mbar_init();
+    }
+    if (warp == 2) tmem_alloc_pair<512>(smem_u32(tmem_slot));
+    if (warp == 0 && lane == 0) tma_prefetch_desc(&xmap);
+    for (int i = threadIdx.x; i < 2 * cp::NT; i += cp::THREADS) s_bn[i] = 0.0;
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();              // both CTAs' barriers are initialised before any remote arrive / multicast commit
+    tc_fence_after();
+    const uint32_t tmem = *tmem_slot;
+
+    if (warp == 0) {
+        // ===================== activation-plane producer (own 8x16 patch, both CTAs) =====================
+        if (lane == 0) {
+            uint32_t slot = 0, use = 0;
+            RunWalker rw(P, cluster);
+            int n, h0, w0, da, db;
+            bool ok = true;
+            while (ok && rw.next(n, h0, w0, da, db)) {
+                const int p0 = max(da - 2, 0), p1 = min(db + 1, P.D - 1);
+                for (int gp = p0; ok && gp <= p1; gp += cp::GROUP) {
+                    const int gn = min(cp::GROUP, p1 - gp + 1);
+                    for (int c = 0; ok && c < nchunk; ++c) {
+                        for (int i = 0; i < gn; ++i) {
+                            if (!mbar_wait(plane_empty + 8 * slot, (use & 1) ^ 1)) { atomicExch(P.error_flag, 11); ok = false; break; }
+                            mbar_expect_tx(plane_full + 8 * slot, cp::PLANE_BYTES);
+                            tma_load_5d(base + cp::PLANE_OFF + slot * cp::PLANE_BYTES, &xmap, plane_full + 8 * slot, c * 32,
+                                        w0 - 2, h0 + (int)rank * cp::TH - 2, gp + i, n);
+                            if (++slot == cp::RING) { slot = 0; ++use; }
+                        }
+                    }
+                }
+            }
+        }
+    } else if (warp == 3) {
+        // ===================== weight producer: this CTA's 80 rows of every (chunk, kh, kw) stage =====================
+        // stage rows are [kd = 4..0][32 channels]; rank 0 holds rows 0..79 (kd 4, kd 3, first half of kd 2), rank 1 the rest
+        if (lane == 0) {
+            uint32_t st = 0, use = 0;
+            RunWalker rw(P, cluster);
+            int n, h0, w0, da, db;
+            bool ok = true;
+            const size_t blk = (size_t)P.Nout * 32;            // elements between kd blocks in the pack
+            while (ok && rw.next(n, h0, w0, da, db)) {
+                const int u = P.sample_u ? P.sample_u[n] : 0;
+                const __half* wu = P.w + (size_t)u * nchunk * 125 * P.Nout * 32;
+                const int p0 = max(da - 2, 0), p1 = min(db + 1, P.D - 1);
+                for (int gp = p0; ok && gp <= p1; gp += cp::GROUP) {
+                    for (int c = 0; ok && c < nchunk; ++c) {
+                        for (int t = 0; t < 25; ++t) {
+                            if (!mbar_wait(w_empty + 8 * st, (use & 1) ^ 1)) { atomicExch(P.error_flag, 12); ok = false; break; }
+                            mbar_expect_tx(w_full + 8 * st, cp::WST_BYTES);
+                            const uint32_t dst = base + cp::W_OFF + st * cp::WST_BYTES;
+                            const __half* src = wu + ((size_t)(c * 25 + t) * 5 * P.Nout + n0) * 32;
+                            if (rank == 0) {
+                                bulk_load(dst, src, 2048, w_full + 8 * st);
+                                bulk_load(dst + 2048, src + blk, 2048, w_full + 8 * st);
+                                bulk_load(dst + 4096, src + 2 * blk, 1024, w_full + 8 * st);
+                            } else {
+                                bulk_load(dst, src + 2 * blk + 16 * 32, 1024, w_full + 8 * st);
+                                bulk_load(dst + 1024, src + 3 * blk, 2048, w_full + 8 * st);
+                                bulk_load(dst + 3072, src + 4 * blk, 2048, w_full + 8 * st);
+                            }
+                            if (++st == cp::WST) { st = 0; ++use; }
+                        }
+                    }
+                }
+            }
+        }
+    } else if (warp == 1 && rank != 0) {
+        // ===================== peer relay: forward "landed" events to the leader in the order it consumes them ==========
+        if (lane == 0) {
+            uint32_t pslot = 0, puse = 0, wst = 0, wuse = 0;
+            RunWalker rw(P, cluster);
+            int n, h0, w0, da, db;
+            bool ok = true;
+            while (ok && rw.next(n, h0, w0, da, db)) {
+                const int p0 = max(da - 2, 0), p1 = min(db + 1, P.D - 1);
+                for (int gp = p0; ok && gp <= p1; gp += cp::GROUP) {
+                    const int gn = min(cp::GROUP, p1 - gp + 1);
+                    for (int c = 0; ok && c < nchunk; ++c) {
+                        for (int t = 0; ok && t < 25; ++t) {
+                            if (!mbar_wait(w_full + 8 * wst, wuse & 1)) { atomicExch(P.error_flag, 13); ok = false; break; }
+                            mbar_arrive_remote(w_peer + 8 * wst, 0);
+                            if (++wst == cp::WST) { wst = 0; ++wuse; }
+                            if (t == 0) {
+                                for (int i = 0; i < gn; ++i) {
+                                    if (!mbar_wait(plane_full + 8 * pslot, puse & 1)) { atomicExch(P.error_flag, 14); ok = false; break; }
+                                    mbar_arrive_remote(plane_peer + 8 * pslot, 0);
+                                    if (++pslot == cp::RING) { pslot = 0; ++puse; }
+                                }
+                            }
+                        }
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer (leader only): one thread issues every MMA of the pair =====================
+        if (lane == 0) {
+            const uint32_t hi_a = ((cp::BW * cp::ROWB) >> 4) | (1u << 14) | ((uint32_t)SWZ_64B << 29);
+            const uint32_t hi_b = (512u >> 4) | (1u << 14) | ((uint32_t)SWZ_64B << 29);
+            const uint32_t lbo_lo = 1u << 16;
+            const uint32_t idesc = make_idesc(FMT_F16, 256, 5 * cp::NT, 0, 0);
+            uint32_t pslot = 0, puse = 0, wst = 0, wuse = 0;
+            uint32_t g = 0;                                   // global group counter (accumulator hand-off parity)
+            long long c_tmem = 0, c_w = 0, c_plane = 0, c_total = clock64();
+            RunWalker rw(P, cluster);
+            int n, h0, w0, da, db;
+            bool ok = true;
+            while (ok && rw.next(n, h0, w0, da, db)) {
+                const int p0 = max(da - 2, 0), p1 = min(db + 1, P.D - 1);
+                uint32_t s = 0;                               // accumulator slot of the first plane's window start
+                bool first = true;
+                for (int gp = p0; ok && gp <= p1; gp += cp::GROUP, ++g) {
+                    const int gn = min(cp::GROUP, p1 - gp + 1);
+                    // slots this group touches were drained two groups ago; a new run restarts at slot 0, so it
+                    // also needs the drain of the group just before it (the wait group g+1 would do anyway)
+                    long long t0 = clock64();
+                    if (!mbar_wait_cluster(tmem_empty + 8 * (g & 1), (g >> 1) & 1)) { atomicExch(P.error_flag, 15); ok = false; break; }
+                    if (first && g > 0 &&
+                        !mbar_wait_cluster(tmem_empty + 8 * ((g + 1) & 1), ((g + 1) >> 1) & 1)) { atomicExch(P.error_flag, 16); ok = false; break; }
+                    first = false;
+                    c_tmem += clock64() - t0;
+                    tc_fence_after();
+                    uint32_t a_lo[cp::GROUP], dcol[cp::GROUP];
+                    for (int c = 0; ok && c < nchunk; ++c) {
+                        {
+                            uint32_t slot = pslot, ss = s;
+                            for (int i = 0; i < gn; ++i) {
+                                a_lo[i] = ((base + cp::PLANE_OFF + slot * cp::PLANE_BYTES) >> 4) | lbo_lo;
+                                dcol[i] = tmem + ss * cp::NT;
+                                if (++slot == cp::RING) slot = 0;
+                                if (++ss == cp::PERIOD) ss = 0;
+                            }
+                        }
+                        for (int t = 0; ok && t < 25; ++t) {
+                            const int kh = t / 5, kw = t - kh * 5;
+                            t0 = clock64();
+                            if (!mbar_wait(w_full + 8 * wst, wuse & 1) || !mbar_wait_cluster(w_peer + 8 * wst, wuse & 1)) {
+                                atomicExch(P.error_flag, 17); ok = false; break;
+                            }
+                            c_w += clock64() - t0;
+                            tc_fence_after();
+                            const uint32_t b_lo = ((base + cp::W_OFF + wst * cp::WST_BYTES) >> 4) | lbo_lo;
+                            const uint32_t a_tap = ((kh * cp::BW + kw) * cp::ROWB) >> 4;
+                            uint32_t slot = pslot, use = puse;
+                            for (int i = 0; i < gn; ++i) {
+                                if (t == 0) {
+                                    t0 = clock64();
+                                    if (!mbar_wait(plane_full + 8 * slot, use & 1) ||
+                                        !mbar_wait_cluster(plane_peer + 8 * slot, use & 1)) {
+                                        atomicExch(P.error_flag, 18); ok = false; break;
+                                    }
+                                    c_plane += clock64() - t0;
+                                    tc_fence_after();
+                                }
+                                const uint32_t al = a_lo[i] + a_tap;
+                                mma_f16_ss_pair(dcol[i], ((uint64_t)hi_a << 32) | al, ((uint64_t)hi_b << 32) | b_lo, idesc, 1u);
+                                mma_f16_ss_pair(dcol[i], ((uint64_t)hi_a << 32) | (al + 2), ((uint64_t)hi_b << 32) | (b_lo + 2), idesc, 1u);
+                                if (t == 24) mma_commit_pair(plane_empty + 8 * slot, 3u);
+                                if (++slot == cp::RING) { slot = 0; ++use; }
+                            }
+                            mma_commit_pair(w_empty + 8 * wst, 3u);
+                            if (++wst == cp::WST) { wst = 0; ++wuse; }
+                        }
+                        pslot += gn;
+                        if (pslot >= cp::RING) { pslot -= cp::RING; ++puse; }
+                    }
+                    if (ok) mma_commit_pair(tmem_full + 8 * (g & 1), 3u);
+                    s += gn;
+                    if (s >= cp::PERIOD) s -= cp::PERIOD;
+                }
+            }
+            if (P.prof != nullptr) {
+                long long* o = P.prof + 8 * (size_t)(cluster % 160);
+                o[0] = clock64() - c_total; o[1] = c_tmem; o[2] = c_w; o[3] = c_plane;
+                o[5] = (long long)globaltimer_ns();
+            }
+        }
+    } else if (warp >= 4) {
+        // ===================== epilogue (both CTAs, own 128 accumulator rows) =====================
+        const int ew = warp - 4;
+        const int row = ew * 32 + lane;
+        const int th = row >> 3, tw = row & 7;
+        const uint32_t lane_addr = (uint32_t)(ew * 32) << 16;
+        float scale = P.out_scale;
+        if (P.out_scale_dev) scale *= *P.out_scale_dev;
+        uint32_t zeros[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) zeros[j] = 0u;
+        for (int c = 0; c < 512; c += 32) tmem_st_32x32(tmem + c + lane_addr, zeros);
+        tmem_st_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) { mbar_arrive_remote(tmem_empty, 0); mbar_arrive_remote(tmem_empty + 8, 0); }
+
+        RunWalker rw(P, cluster);
+        int n, h0, w0, da, db;
+        uint32_t g = 0;
+        bool ok = true;
+        while (ok && rw.next(n, h0, w0, da, db)) {
+            const int p0 = max(da - 2, 0), p1 = min(db + 1, P.D - 1);
+            const int hh = h0 + (int)rank * cp::TH + th;
+            const bool row_ok = hh < P.H;
+            for (int gp = p0; gp <= p1; gp += cp::GROUP, ++g) {
+                const int gl = min(gp + cp::GROUP - 1, p1);          // last plane of the group
+                if (!mbar_wait(tmem_full + 8 * (g & 1), (g >> 1) & 1)) { atomicExch(P.error_flag, 19); ok = false; break; }
+                tc_fence_after();
+                // output planes completed by this group: q = gp-2 .. gl-2, plus the tail gl-1 .. gl+2 after the last group
+                const int qa = gp - 2, qb = (gl == p1) ? gl + 2 : gl - 2;
+                for (int q = qa; q <= qb; ++q) {
+                    const int slot = (q - p0 + 2) % cp::PERIOD;
+                    const uint32_t taddr = tmem + slot * cp::NT + lane_addr;
+                    const bool spill = slot < 4;                       // windows starting in slots 8..11 spill into 12..15
+                    if (q >= da && q < db) {
+                        uint32_t v[32];
+                        tmem_ld_32x32(taddr, v);
+                        tmem_ld_wait();
+                        float f[32];
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
+                        if (spill) {
+                            tmem_ld_32x32(taddr + cp::PERIOD * cp::NT, v);
+                            tmem_ld_wait();
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) f[j] += __uint_as_float(v[j]);
+                        }
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) f[j] = row_ok ? f[j] * scale : 0.f;
+                        if (row_ok) {
+                            float* dst = P.y + ((((size_t)n * P.D + q) * P.H + hh) * P.W + w0 + tw) * P.Nout + n0;
+#pragma unroll
+                            for (int j = 0; j < 32; j += 4)
+                                *reinterpret_cast<float4*>(dst + j) = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
+                        }
+                        if (P.bn_sums != nullptr && q >= P.stat_lo && q < P.stat_hi) {
+                            float gq[32];
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) gq[j] = f[j] * f[j];
+                            // transposed butterfly: afterwards lane l holds the 32-voxel total of channel l
+#pragma unroll
+                            for (int sft = 16; sft >= 1; sft >>= 1) {
+                                const bool up = (lane & sft) != 0;
+#pragma unroll
+                                for (int i = 0; i < sft; ++i) {
+                                    const float send1 = up ? f[i] : f[i + sft], send2 = up ? gq[i] : gq[i + sft];
+                                    const float r1 = __shfl_xor_sync(0xffffffffu, send1, sft);
+                                    const float r2 = __shfl_xor_sync(0xffffffffu, send2, sft);
+                                    f[i] = (up ? f[i + sft] : f[i]) + r1;
+                                    gq[i] = (up ? gq[i + sft] : gq[i]) + r2;
+                                }
+                            }
+                            atomicAdd(s_bn + lane, (double)f[0]);
+                            atomicAdd(s_bn + cp::NT + lane, (double)gq[0]);
+                        }
+                    }
+                    tmem_st_32x32(taddr, zeros);
+                    if (spill) tmem_st_32x32(taddr + cp::PERIOD * cp::NT, zeros);
+                }
+                tmem_st_wait();
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive_remote(tmem_empty + 8 * (g & 1), 0);
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();              // the peer's shared memory and barriers stay alive until both CTAs are done
+    if (P.prof != nullptr && threadIdx.x == 0 && rank == 0) {
+        long long* o = P.prof + 8 * (size_t)(cluster % 160);
+        o[4] = (long long)ts_entry;
+        o[6] = (long long)globaltimer_ns();
+    }
+    if (P.bn_sums != nullptr)
+        for (int i = threadIdx.x; i < 2 * cp::NT; i += cp::THREADS) {
+            const int which = i / cp::NT, ch = i % cp::NT;
+            atomicAdd(P.bn_sums + which * P.Nout + n0 + ch, s_bn[i]);
+        }
+    if (warp == 2) tmem_dealloc_pair<512>(tmem);
+}
+
+// ------------------------------------------------------------------------------------------------ host
+int* device_error_flag();            // mode_abi.cu
+long long* debug_profile_buffer();   // mode_abi.cu
+int make_act_map(CUtensorMap* map, const __half* x, int N, int D, int H, int W, int K, int box_w, int box_h);   // conv_umma.cu
+
+// input planes a run [da, db) of a D-plane column has to process (+0.25 per group hand-off)
+static double run_cost(int da, int db, int D) {
+    const int planes = std::min(db + 1, D - 1) - std::max(da - 2, 0) + 1;
+    return planes + 0.25 * ((planes + cp::GROUP - 1) / cp::GROUP);
+}
+
+// take plane-units from u while the accumulated cost stays within the budget; returns the new position
+static int64_t take_runs(int64_t u, int64_t units, int D, double budget) {
+    double acc = 0;
+    while (u < units) {
+        const int da = (int)(u % D);
+        const double whole = run_cost(da, D, D);
+        if (acc + whole <= budget) { acc += whole; u += D - da; continue; }
+        int lo = 0, hi = D - da;                           // largest k with cost(da, da+k) fitting (cost is monotone in k)
+        while (hi - lo > 1) {
+            const int mid = (lo + hi) / 2;
+            if (acc + run_cost(da, da + mid, D) <= budget) lo = mid; else hi = mid;
+        }
+        u += lo;
+        break;
+    }
+    return u;
+}
+
+static void partition_runs(int64_t units, int D, int G, int32_t* bounds) {
+    struct Key {
+        int64_t units; int D, G;
+        bool operator<(const Key& o) const { return std::tie(units, D, G) < std::tie(o.units, o.D, o.G); }
+    };
+    static std::mutex mu;
+    static std::map<Key, std::array<int32_t, cp::MAX_CLUSTERS + 1>> cache;
+    const Key key{units, D, G};
+    std::lock_guard<std::mutex> lock(mu);
+    auto it = cache.find(key);
+    if (it == cache.end()) {
+        double total = 0;
+        for (int64_t u = 0; u < units; u += D) total += run_cost(0, D, D);
+        auto feasible = [&](double budget) {
+            int64_t u = 0;
+            for (int c = 0; c < G && u < units; ++c) {
+                const int64_t nu = take_runs(u, units, D, budget);
+                if (nu == u) return false;
+                u = nu;
+            }
+            return u >= units;
+        };
+        double h = total / G;
+        while (!feasible(h)) h *= 1.05;
+        double l = total / G;
+        for (int i = 0; i < 24; ++i) {
+            const double m = 0.5 * (l + h);
+            if (feasible(m)) h = m; else l = m;
+        }
+        std::array<int32_t, cp::MAX_CLUSTERS + 1> b{};
+        int64_t u = 0;
+        for (int c = 0; c < G; ++c) {
+            b[c] = (int32_t)u;
+            u = std::min(units, take_runs(u, units, D, h));
+        }
+        for (int c = G; c <= cp::MAX_CLUSTERS; ++c) b[c] = (int32_t)units;
+        it = cache.emplace(key, b).first;
+    }
+    std::copy(it->second.begin(), it->second.end(), bounds);
+}
+
+static int pair_clusters(int passes) { return std::max(1, std::min(cp::MAX_CLUSTERS, (sm_count() / 2) / passes)); }
+
+// Worth it (and possible) when every cluster gets a long enough march: otherwise the single-CTA kernel's finer tiles win.
+bool conv3d_pair_supported(int N, int D, int H, int W, int K, int Nout) {
+    if (!(K % 32 == 0 && K >= 32 && Nout % 32 == 0 && Nout >= 32 && W % cp::TW == 0)) return false;
+    const int64_t units = (int64_t)N * ceil_div(H, 2 * cp::TH) * (W / cp::TW) * D;
+    if (units > 0x7fffffff) return false;
+    return units >= (int64_t)12 * pair_clusters(Nout / cp::NT);
+}
+
+int conv3d_pair(const __half* x, const __half* w, const int32_t* sample_u, float* y, int N, int D, int H, int W, int K,
+                int Nout, float out_scale, const float* out_scale_dev, double* bn_sums, int stat_lo, int stat_hi,
+                cudaStream_t st) {
+    if ((reinterpret_cast<uintptr_t>(x) & 15) || (reinterpret_cast<uintptr_t>(w) & 15) ||
+        (reinterpret_cast<uintptr_t>(y) & 15))
+        MODE_FAIL("conv3d_pair: pointers must be 16-byte aligned");
+    if (!(K % 32 == 0 && Nout % 32 == 0 && W % cp::TW == 0)) MODE_FAIL("conv3d_pair: unsupported shape");
+    PairParams P;
+    P.w = w; P.sample_u = sample_u; P.y = y; P.bn_sums = bn_sums; P.out_scale_dev = out_scale_dev;
+    P.out_scale = out_scale;
+    P.N = N; P.D = D; P.H = H; P.W = W; P.K = K; P.Nout = Nout;
+    P.stat_lo = stat_lo; P.stat_hi = stat_hi;
+    P.tiles_w = W / cp::TW; P.tiles_h2 = (int)ceil_div(H, 2 * cp::TH);
+    const int64_t units = (int64_t)N * P.tiles_h2 * P.tiles_w * D;
+    if (units > 0x7fffffff) MODE_FAIL("conv3d_pair: volume too large for 32-bit unit indices");
+    const int passes = Nout / cp::NT;
+    int G = (int)std::min<int64_t>(pair_clusters(passes), std::max<int64_t>(1, units / 4));
+    if (const char* e = getenv("REPMODE_PAIR_CLUSTERS"))          // test hook: force the number of clusters
+        G = std::max(1, std::min(std::min(G, cp::MAX_CLUSTERS), atoi(e)));
+    partition_runs(units, D, G, P.bounds);
+    P.error_flag = device_error_flag();
+    if (!P.error_flag) MODE_FAIL("conv3d_pair: could not allocate the device error flag");
+    P.prof = debug_profile_buffer();
+    CUtensorMap xmap;
+    if (make_act_map(&xmap, x, N, D, H, W, K, cp::BW, cp::BH) != 0) return -1;
+    const int smem_bytes = (int)cp::TOTAL + 1024;
+    static_assert(cp::TOTAL + 1024 <= 227 * 1024, "shared memory budget");
+    MODE_CUDA(cudaFuncSetAttribute(conv3d_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
+    conv3d_pair_kernel<<<dim3(2 * G, passes), cp::THREADS, smem_bytes, st>>>(xmap, P);
+    MODE_LAUNCH_CHECK();
+    return 0;
+}
+
+}  // namespace mode

@@ -2,6 +2,8 @@
 // See include/repmode_b200.h for the contract and the reference lines each entry point replaces.
 #include <atomic>
 
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace mode {
@@ -52,6 +54,11 @@ int wgrad_simt(const float* x, const float* dy, float* dw, int N, int D, int H, 
 // conv_umma.cu
 bool conv3d_umma_supported(int D, int H, int W, int K, int Nout);
 int conv3d_umma(const __half* x, const __half* w, const int32_t* sample_u, float* y, int N, int D, int H, int W, int K,
+                int Nout, float out_scale, const float* out_scale_dev, double* bn_sums, int stat_lo, int stat_hi,
+                cudaStream_t st);
+// conv_pair.cu
+bool conv3d_pair_supported(int N, int D, int H, int W, int K, int Nout);
+int conv3d_pair(const __half* x, const __half* w, const int32_t* sample_u, float* y, int N, int D, int H, int W, int K,
                 int Nout, float out_scale, const float* out_scale_dev, double* bn_sums, int stat_lo, int stat_hi,
                 cudaStream_t st);
 bool wgrad_umma_supported(int D, int H, int W, int Ci, int Co);
@@ -110,10 +117,14 @@ extern "C" int mode_conv3d(const void* x, mode_dtype_t x_dtype, const void* w, c
         if (x_dtype != MODE_F32) MODE_FAIL("mode_conv3d: the SIMT path takes fp32 operands");
         return conv3d_simt((const float*)x, (const float*)w, sample_u, y, N, D, H, W, K, Nout, out_scale, out_scale_dev, bn_sums, stat_d_lo, stat_d_hi, st);
     }
-    if (impl == 2) {
+    if (impl == 2 || impl == 3 || impl == 4) {
         if (x_dtype != MODE_F16) MODE_FAIL("mode_conv3d: the tcgen05 path takes fp16 operands");
         if (!conv3d_umma_supported(D, H, W, K, Nout))
             MODE_FAIL("mode_conv3d: shape D=%d H=%d W=%d K=%d Nout=%d not supported by the tcgen05 path", D, H, W, K, Nout);
+        static const bool no_pair = getenv("REPMODE_DISABLE_PAIR") != nullptr;
+        // 2: CTA-pair kernel when every cluster gets a long enough march, else the single-CTA kernel; 3 / 4 force one
+        if (impl == 4 || (impl == 2 && !no_pair && conv3d_pair_supported(N, D, H, W, K, Nout)))
+            return conv3d_pair((const __half*)x, (const __half*)w, sample_u, y, N, D, H, W, K, Nout, out_scale, out_scale_dev, bn_sums, stat_d_lo, stat_d_hi, st);
         return conv3d_umma((const __half*)x, (const __half*)w, sample_u, y, N, D, H, W, K, Nout, out_scale, out_scale_dev, bn_sums, stat_d_lo, stat_d_hi, st);
     }
     MODE_FAIL("mode_conv3d: unknown impl %d", impl);

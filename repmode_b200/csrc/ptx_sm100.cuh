@@ -53,6 +53,30 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
         : "memory");
     return ok != 0;
 }
+// Arrive on the mbarrier at the same shared-memory offset in CTA `cta_rank` of this cluster (release at cluster scope).
+__device__ __forceinline__ void mbar_arrive_remote(uint32_t bar, uint32_t cta_rank) {
+    asm volatile(
+        "{\n\t"
+        ".reg .b32 ra;\n\t"
+        "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
+        "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n\t"
+        "}\n" ::"r"(bar), "r"(cta_rank)
+        : "memory");
+}
+// try_wait with acquire at cluster scope: pairs with mbar_arrive_remote from the peer CTA.
+__device__ __forceinline__ bool mbar_try_wait_cluster(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred P;\n\t"
+        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 P, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, P;\n\t"
+        "}\n"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
 __device__ __forceinline__ uint64_t globaltimer_ns() {
     uint64_t t;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
@@ -73,6 +97,20 @@ static __device__ __noinline__ bool mbar_wait_slow(uint32_t bar, uint32_t parity
 __device__ __forceinline__ bool mbar_wait(uint32_t bar, uint32_t parity, uint32_t /*unused*/ = 0) {
     if (mbar_try_wait(bar, parity)) return true;
     return mbar_wait_slow(bar, parity);
+}
+
+static __device__ __noinline__ bool mbar_wait_cluster_slow(uint32_t bar, uint32_t parity) {
+    const uint64_t t0 = globaltimer_ns();
+    while (true) {
+#pragma unroll 1
+        for (int i = 0; i < 256; ++i)
+            if (mbar_try_wait_cluster(bar, parity)) return true;
+        if (globaltimer_ns() - t0 > 2000000000ull) return false;
+    }
+}
+__device__ __forceinline__ bool mbar_wait_cluster(uint32_t bar, uint32_t parity) {
+    if (mbar_try_wait_cluster(bar, parity)) return true;
+    return mbar_wait_cluster_slow(bar, parity);
 }
 
 // ---------------------------------------------------------------- TMA

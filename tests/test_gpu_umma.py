@@ -57,6 +57,46 @@ def test_conv3d_umma_bitexact(shape):
     assert torch.allclose(sums16, sums32, rtol=1e-12, atol=1e-9)
 
 
+PAIR_SHAPES = [  # N, D, H, W, K, Nout, forced clusters (0 = the launcher's choice)
+    (1, 1, 16, 8, 32, 32, 0),          # H < 32: the peer CTA's rows are all masked
+    (2, 4, 32, 8, 32, 32, 0),
+    (1, 9, 32, 16, 32, 32, 0),         # runs cut inside a column: halo planes + garbage slots on both sides
+    (1, 30, 32, 8, 32, 32, 1),         # one cluster marches 30 planes: slot period wraps, spill slots 12..15
+    (2, 17, 32, 8, 32, 32, 1),         # two columns back to back on one cluster (accumulator hand-off across runs)
+    (1, 30, 32, 8, 32, 32, 3),
+    (1, 3, 40, 24, 64, 32, 0),         # two K chunks, H % 32 != 0
+    (1, 5, 32, 8, 32, 64, 0),          # two channel passes
+    (2, 13, 64, 16, 64, 64, 0),
+    (1, 2, 8, 8, 128, 96, 2),
+]
+
+
+@pytest.mark.parametrize("shape", PAIR_SHAPES)
+def test_conv3d_pair_bitexact(shape, monkeypatch):
+    """The CTA-pair kernel (tcgen05.mma.cta_group::2, impl=4) == SIMT fp32 kernel, exactly, incl. the fused BN sums
+    over a plane sub-range."""
+    from repmode_b200 import functional as Fm, lib as L
+    n, d, h, w, k, nout, clusters = shape
+    if clusters:
+        monkeypatch.setenv("REPMODE_PAIR_CLUSTERS", str(clusters))
+    rng = np.random.RandomState(sum(shape))
+    x = rng.randint(-3, 4, size=(n, d, h, w, k)).astype(np.float32)
+    weff = (rng.randint(-4, 5, size=(n, nout, k, 5, 5, 5)) / 8.0).astype(np.float32)
+    su = torch.arange(n, dtype=torch.int32, device="cuda")
+    xg = torch.from_numpy(x).cuda()
+    w32 = torch.from_numpy(pack_weights(weff, half=False)).cuda()
+    w16 = torch.from_numpy(pack_weights(weff, half=True)).cuda()
+    sums32 = torch.zeros(2 * nout, dtype=torch.float64, device="cuda")
+    sums16 = torch.zeros(2 * nout, dtype=torch.float64, device="cuda")
+    rng_stat = (1, max(2, d - 1)) if d > 2 else None
+    y_simt = Fm.conv3d(xg, L.MODE_F32, w32, su, n, d, h, w, k, nout, None, sums32, impl=L.IMPL_SIMT, stat_range=rng_stat)
+    y_pair = Fm.conv3d(xg.half(), L.MODE_F16, w16, su, n, d, h, w, k, nout, None, sums16, impl=L.IMPL_UMMA_PAIR,
+                       stat_range=rng_stat)
+    _poll()
+    assert torch.equal(y_pair, y_simt)
+    assert torch.allclose(sums16, sums32, rtol=1e-12, atol=1e-9)
+
+
 def test_conv3d_umma_random_vs_simt():
     """Real-valued operands: fp16 operand rounding only (<= 2^-11 relative per operand)."""
     from repmode_b200 import functional as Fm, lib as L

@@ -17,27 +17,32 @@ import numpy as np  # noqa: E402
 def main():
     lib = L.load()
     out = []
-    for (n, d, h, w, k, nout) in [(1, 32, 128, 128, 32, 32), (1, 16, 64, 64, 64, 64), (4, 32, 128, 128, 32, 32)]:
+    impls = [int(a) for a in sys.argv[1:]] or [3, 4]
+    for impl, (n, d, h, w, k, nout) in [(i, sh) for sh in [(1, 32, 128, 128, 32, 32), (1, 16, 64, 64, 64, 64),
+                                                            (4, 32, 128, 128, 32, 32)] for i in impls]:
         x = torch.randn(n, d, h, w, k, device="cuda").half()
         weff = (np.random.RandomState(0).randn(n, nout, k, 5, 5, 5) * 0.02).astype(np.float32)
         w16 = torch.from_numpy(pack_weights(weff, half=True)).cuda()
         su = torch.arange(n, dtype=torch.int32, device="cuda")
         prof = torch.zeros(8 * 160, dtype=torch.int64, device="cuda")
         for _ in range(3):
-            Fm.conv3d(x, L.MODE_F16, w16, su, n, d, h, w, k, nout)
+            Fm.conv3d(x, L.MODE_F16, w16, su, n, d, h, w, k, nout, impl=impl)
         lib.mode_debug_profile(ctypes.c_void_p(prof.data_ptr()))
         torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        Fm.conv3d(x, L.MODE_F16, w16, su, n, d, h, w, k, nout)
+        Fm.conv3d(x, L.MODE_F16, w16, su, n, d, h, w, k, nout, impl=impl)
         e1.record()
         torch.cuda.synchronize()
         lib.mode_debug_profile(None)
-        p = prof.view(160, 8)[:148].cpu().double()
+        code = ctypes.c_int32(0)
+        lib.mode_poll_error(ctypes.byref(code))
+        ncta = 148 if impl != 4 else 74
+        p = prof.view(160, 8)[:ncta].cpu().double()
         t_entry, t_mma, t_done = p[:, 4], p[:, 5], p[:, 6]
         t0g = float(t_entry.min())
         flop = 2.0 * 125 * k * nout * n * d * h * w
-        r = {"shape": [n, d, h, w, k, nout], "ms": e0.elapsed_time(e1), "tflops": flop / e0.elapsed_time(e1) / 1e9,
+        r = {"impl": impl, "err": code.value, "shape": [n, d, h, w, k, nout], "ms": e0.elapsed_time(e1), "tflops": flop / e0.elapsed_time(e1) / 1e9,
              "mma_warp_cycles_mean": float(p[:, 0].mean()), "mma_warp_cycles_max": float(p[:, 0].max()),
              "wait_tmem_mean": float(p[:, 1].mean()), "wait_weights_mean": float(p[:, 2].mean()),
              "wait_planes_mean": float(p[:, 3].mean()), "wait_planes_max": float(p[:, 3].max()),

@@ -75,6 +75,7 @@ struct PairParams {
     int32_t bounds[cp::MAX_CLUSTERS + 1];   // cluster c owns plane-units [bounds[c], bounds[c+1]) of (n, th2, tw, d)
     int* error_flag;
     long long* prof;
+    int flags;                   // debug: bit 0 = no tcgen05 fence after operand waits
 };
 
 // A "run" is a contiguous d-range [da, db) of one patch column; every role of both CTAs walks the same runs.
@@ -223,86 +224,91 @@ conv3d_pair_kernel(const __grid_constant__ CUtensorMap xmap, const PairParams P)
             }
         }
     } else if (warp == 1) {
-        // ===================== MMA issuer (leader only): one thread issues every MMA of the pair =====================
-        if (lane == 0) {
+        // ===================== MMA issuer (leader only) =====================
+        // The WHOLE warp runs this loop on warp-uniform values (kernel parameters, loop counters, vote results), and one
+        // elected lane is predicated inside the asm.  Under `if (lane == 0)` ptxas has to assume divergence and wraps
+        // every UTCHMMA in an ELECT / 5x R2UR.BROADCAST loop (~115 cycles per MMA measured -- more than the 80 cycles the
+        // pair MMA itself takes); with uniform control flow the descriptors live in uniform registers.
+        {
+            const uint32_t sel = elect_one() ? 1u : 0u;
+            const uint32_t tm = __reduce_max_sync(0xffffffffu, tmem);             // uniform copy of the TMEM base
             const uint32_t hi_a = ((cp::BW * cp::ROWB) >> 4) | (1u << 14) | ((uint32_t)SWZ_64B << 29);
             const uint32_t hi_b = (512u >> 4) | (1u << 14) | ((uint32_t)SWZ_64B << 29);
             const uint32_t lbo_lo = 1u << 16;
             const uint32_t idesc = make_idesc(FMT_F16, 256, 5 * cp::NT, 0, 0);
+            const uint32_t plane0 = ((base + cp::PLANE_OFF) >> 4) | lbo_lo, wst0 = ((base + cp::W_OFF) >> 4) | lbo_lo;
+            const bool prof = P.prof != nullptr;
             uint32_t pslot = 0, puse = 0, wst = 0, wuse = 0;
             uint32_t g = 0;                                   // global group counter (accumulator hand-off parity)
-            long long c_tmem = 0, c_w = 0, c_plane = 0, c_total = clock64();
-            RunWalker rw(P, cluster);
-            int n, h0, w0, da, db;
-            bool ok = true;
-            while (ok && rw.next(n, h0, w0, da, db)) {
+            long long c_tmem = 0, c_w = 0, c_plane = 0, c_issue = 0, c_total = clock64(), t0 = 0;
+            int u = P.bounds[cluster];
+            const int uend = P.bounds[cluster + 1];
+            int err = 0;
+            while (err == 0 && u < uend) {
+                const int da = u % P.D;
+                const int db = min(P.D, da + (uend - u));
+                u += db - da;
                 const int p0 = max(da - 2, 0), p1 = min(db + 1, P.D - 1);
-                uint32_t s = 0;                               // accumulator slot of the first plane's window start
+                uint32_t s = 0;                               // accumulator slot of the group's first window
                 bool first = true;
-                for (int gp = p0; ok && gp <= p1; gp += cp::GROUP, ++g) {
+                for (int gp = p0; err == 0 && gp <= p1; gp += cp::GROUP, ++g) {
                     const int gn = min(cp::GROUP, p1 - gp + 1);
                     // slots this group touches were drained two groups ago; a new run restarts at slot 0, so it
                     // also needs the drain of the group just before it (the wait group g+1 would do anyway)
-                    long long t0 = clock64();
-                    if (!mbar_wait_cluster(tmem_empty + 8 * (g & 1), (g >> 1) & 1)) { atomicExch(P.error_flag, 15); ok = false; break; }
-                    if (first && g > 0 &&
-                        !mbar_wait_cluster(tmem_empty + 8 * ((g + 1) & 1), ((g + 1) >> 1) & 1)) { atomicExch(P.error_flag, 16); ok = false; break; }
+                    if (prof) t0 = clock64();
+                    if (!mbar_wait_warp<true>(tmem_empty + 8 * (g & 1), (g >> 1) & 1)) { err = 15; break; }
+                    if (first && g > 0 && !mbar_wait_warp<true>(tmem_empty + 8 * ((g + 1) & 1), ((g + 1) >> 1) & 1)) { err = 16; break; }
                     first = false;
-                    c_tmem += clock64() - t0;
+                    if (prof) c_tmem += clock64() - t0;
                     tc_fence_after();
-                    uint32_t a_lo[cp::GROUP], dcol[cp::GROUP];
-                    for (int c = 0; ok && c < nchunk; ++c) {
-                        {
-                            uint32_t slot = pslot, ss = s;
-                            for (int i = 0; i < gn; ++i) {
-                                a_lo[i] = ((base + cp::PLANE_OFF + slot * cp::PLANE_BYTES) >> 4) | lbo_lo;
-                                dcol[i] = tmem + ss * cp::NT;
-                                if (++slot == cp::RING) slot = 0;
-                                if (++ss == cp::PERIOD) ss = 0;
-                            }
-                        }
-                        for (int t = 0; ok && t < 25; ++t) {
+                    for (int c = 0; err == 0 && c < nchunk; ++c) {
+                        for (int t = 0; t < 25; ++t) {
                             const int kh = t / 5, kw = t - kh * 5;
-                            t0 = clock64();
-                            if (!mbar_wait(w_full + 8 * wst, wuse & 1) || !mbar_wait_cluster(w_peer + 8 * wst, wuse & 1)) {
-                                atomicExch(P.error_flag, 17); ok = false; break;
+                            if (prof) t0 = clock64();
+                            if (!mbar_wait_warp<false>(w_full + 8 * wst, wuse & 1) || !mbar_wait_warp<true>(w_peer + 8 * wst, wuse & 1)) {
+                                err = 17; break;
                             }
-                            c_w += clock64() - t0;
+                            if (prof) c_w += clock64() - t0;
                             tc_fence_after();
-                            const uint32_t b_lo = ((base + cp::W_OFF + wst * cp::WST_BYTES) >> 4) | lbo_lo;
+                            const long long ti = prof ? clock64() : 0;
+                            const uint32_t b_lo = wst0 + wst * (cp::WST_BYTES >> 4);
                             const uint32_t a_tap = ((kh * cp::BW + kw) * cp::ROWB) >> 4;
-                            uint32_t slot = pslot, use = puse;
+                            uint32_t slot = pslot, use = puse, ss = s;
                             for (int i = 0; i < gn; ++i) {
                                 if (t == 0) {
-                                    t0 = clock64();
-                                    if (!mbar_wait(plane_full + 8 * slot, use & 1) ||
-                                        !mbar_wait_cluster(plane_peer + 8 * slot, use & 1)) {
-                                        atomicExch(P.error_flag, 18); ok = false; break;
-                                    }
-                                    c_plane += clock64() - t0;
+                                    if (prof) t0 = clock64();
+                                    if (!mbar_wait_warp<false>(plane_full + 8 * slot, use & 1) ||
+                                        !mbar_wait_warp<true>(plane_peer + 8 * slot, use & 1)) { err = 18; break; }
+                                    if (prof) c_plane += clock64() - t0;
                                     tc_fence_after();
                                 }
-                                const uint32_t al = a_lo[i] + a_tap;
-                                mma_f16_ss_pair(dcol[i], ((uint64_t)hi_a << 32) | al, ((uint64_t)hi_b << 32) | b_lo, idesc, 1u);
-                                mma_f16_ss_pair(dcol[i], ((uint64_t)hi_a << 32) | (al + 2), ((uint64_t)hi_b << 32) | (b_lo + 2), idesc, 1u);
-                                if (t == 24) mma_commit_pair(plane_empty + 8 * slot, 3u);
+                                const uint32_t al = plane0 + slot * (cp::PLANE_BYTES >> 4) + a_tap;
+                                const uint32_t dcol = tm + ss * cp::NT;
+                                mma_f16_ss_pair_sel(dcol, al, hi_a, b_lo, hi_b, idesc, sel);
+                                mma_f16_ss_pair_sel(dcol, al + 2, hi_a, b_lo + 2, hi_b, idesc, sel);
+                                if (t == 24) mma_commit_pair_sel(plane_empty + 8 * slot, 3u, sel);
                                 if (++slot == cp::RING) { slot = 0; ++use; }
+                                if (++ss == cp::PERIOD) ss = 0;
                             }
-                            mma_commit_pair(w_empty + 8 * wst, 3u);
+                            if (err) break;
+                            mma_commit_pair_sel(w_empty + 8 * wst, 3u, sel);
+                            if (prof) c_issue += clock64() - ti;
                             if (++wst == cp::WST) { wst = 0; ++wuse; }
                         }
                         pslot += gn;
                         if (pslot >= cp::RING) { pslot -= cp::RING; ++puse; }
                     }
-                    if (ok) mma_commit_pair(tmem_full + 8 * (g & 1), 3u);
+                    if (err == 0) mma_commit_pair_sel(tmem_full + 8 * (g & 1), 3u, sel);
                     s += gn;
                     if (s >= cp::PERIOD) s -= cp::PERIOD;
                 }
             }
-            if (P.prof != nullptr) {
+            if (err != 0) atomicExch(P.error_flag, err);
+            if (prof && lane == 0) {
                 long long* o = P.prof + 8 * (size_t)(cluster % 160);
                 o[0] = clock64() - c_total; o[1] = c_tmem; o[2] = c_w; o[3] = c_plane;
                 o[5] = (long long)globaltimer_ns();
+                o[7] = c_issue;
             }
         }
     } else if (warp >= 4) {
@@ -511,6 +517,8 @@ int conv3d_pair(const __half* x, const __half* w, const int32_t* sample_u, float
     P.error_flag = device_error_flag();
     if (!P.error_flag) MODE_FAIL("conv3d_pair: could not allocate the device error flag");
     P.prof = debug_profile_buffer();
+    P.flags = 0;
+    if (const char* e = getenv("REPMODE_PAIR_FLAGS")) P.flags = atoi(e);
     CUtensorMap xmap;
     if (make_act_map(&xmap, x, N, D, H, W, K, cp::BW, cp::BH) != 0) return -1;
     const int smem_bytes = (int)cp::TOTAL + 1024;

@@ -264,6 +264,56 @@ __device__ __forceinline__ void mma_commit_elect(uint32_t bar) {
         : "memory");
 }
 
+// CTA-pair versions for a warp-uniform issue loop (all 32 lanes run the loop on uniform values; `sel` is the
+// per-lane result of ONE elect_one() taken by the caller, so no ELECT is paid per instruction).
+__device__ __forceinline__ void mma_f16_ss_pair_sel(uint32_t d_tmem, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo,
+                                                    uint32_t b_hi, uint32_t idesc, uint32_t sel) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred q, one;\n\t"
+        ".reg .b64 da, db;\n\t"
+        "mov.b64 da, {%1, %2};\n\t"
+        "mov.b64 db, {%3, %4};\n\t"
+        "setp.eq.u32 one, 1, 1;\n\t"
+        "setp.ne.u32 q, %6, 0;\n\t"
+        "@q tcgen05.mma.cta_group::2.kind::f16 [%0], da, db, %5, one;\n\t"
+        "}\n"
+        :
+        : "r"(d_tmem), "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(sel)
+        : "memory");
+}
+__device__ __forceinline__ void mma_commit_pair_sel(uint32_t bar, uint32_t cta_mask, uint32_t sel) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred q;\n\t"
+        ".reg .b16 lo, hi;\n\t"
+        "mov.b32 {lo, hi}, %1;\n\t"
+        "setp.ne.u32 q, %2, 0;\n\t"
+        "@q tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], lo;\n\t"
+        "}\n" ::"r"(bar), "r"(cta_mask), "r"(sel)
+        : "memory");
+}
+// Warp-collective, time-bounded mbarrier wait whose RESULT is warp-uniform (vote), so that the code after it stays
+// convergent and ptxas can keep descriptors in uniform registers.  cluster = acquire at cluster scope.
+template <bool kCluster>
+static __device__ __noinline__ bool mbar_wait_warp_slow(uint32_t bar, uint32_t parity) {
+    const uint64_t t0 = globaltimer_ns();
+    while (true) {
+#pragma unroll 1
+        for (int i = 0; i < 64; ++i) {
+            const bool done = kCluster ? mbar_try_wait_cluster(bar, parity) : mbar_try_wait(bar, parity);
+            if (__all_sync(0xffffffffu, done)) return true;
+        }
+        if (__any_sync(0xffffffffu, globaltimer_ns() - t0 > 2000000000ull)) return false;
+    }
+}
+template <bool kCluster>
+__device__ __forceinline__ bool mbar_wait_warp(uint32_t bar, uint32_t parity) {
+    const bool done = kCluster ? mbar_try_wait_cluster(bar, parity) : mbar_try_wait(bar, parity);
+    if (__all_sync(0xffffffffu, done)) return true;
+    return mbar_wait_warp_slow<kCluster>(bar, parity);
+}
+
 // Arrive on an mbarrier once all previously issued tcgen05.mma of this thread have completed.
 __device__ __forceinline__ void mma_commit(uint32_t bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar)

@@ -116,6 +116,8 @@ extern "C" int probe_mma(const void* img_dev, uint32_t img_bytes, uint64_t adesc
 // probe_mma_rate: issue-rate probe. Unrolled groups of 8 MMAs round-robin over NACC accumulators
 // (column stride acc_cols), operand descriptor offsets from small tables (16-byte units).
 struct RateOffs { uint32_t a[8]; uint32_t b[8]; };
+__device__ int g_commit_every = 0;     // probe knob: a tcgen05.commit to a scratch mbarrier after every k-th MMA
+extern "C" int probe_set_commit_every(int k) { CK(cudaMemcpyToSymbol(g_commit_every, &k, sizeof(int))); return 0; }
 
 template <int NACC>
 __global__ void __launch_bounds__(128, 1)
@@ -123,7 +125,7 @@ probe_rate_kernel(const uint8_t* __restrict__ img, uint32_t img_bytes, uint64_t 
                   uint32_t idesc, uint32_t kind, RateOffs offs, uint32_t acc_cols, uint32_t repeat,
                   long long* __restrict__ cycles, int* __restrict__ status) {
     extern __shared__ uint8_t smem_raw[];
-    __shared__ uint64_t mbar;
+    __shared__ uint64_t mbar, scratch_bar;
     __shared__ uint32_t tmem_base_slot;
     const uint32_t raw = smem_u32(smem_raw);
     const uint32_t base = (raw + 1023u) & ~1023u;
@@ -133,7 +135,7 @@ probe_rate_kernel(const uint8_t* __restrict__ img, uint32_t img_bytes, uint64_t 
     fence_proxy_async();
     const uint32_t warp = threadIdx.x >> 5;
     if (warp == 0) tmem_alloc<512>(smem_u32(&tmem_base_slot));
-    if (threadIdx.x == 32) { mbar_init(smem_u32(&mbar), 1); fence_mbar_init(); }
+    if (threadIdx.x == 32) { mbar_init(smem_u32(&mbar), 1); mbar_init(smem_u32(&scratch_bar), 1u << 20); fence_mbar_init(); }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -200,13 +202,13 @@ extern "C" int probe_mma_rate(const void* img_dev, uint32_t img_bytes, uint64_t 
 // ------------------------------------------------------------------------------------------------
 // probe_mma_rate_pair: the same issue-rate probe with a CTA pair (cta_group::2, M = 256): each CTA holds its own
 // 128 A rows and N/2 of the B rows; the leader issues, the commit is multicast to both CTAs.
-template <int NACC>
+template <int NACC, int CE>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128, 1)
 probe_rate_pair_kernel(const uint8_t* __restrict__ img, uint32_t img_bytes, uint64_t adesc, uint64_t bdesc,
                        uint32_t idesc, RateOffs offs, uint32_t acc_cols, uint32_t repeat,
                        long long* __restrict__ cycles, int* __restrict__ status) {
     extern __shared__ uint8_t smem_raw[];
-    __shared__ uint64_t mbar;
+    __shared__ uint64_t mbar, scratch_bar;
     __shared__ uint32_t tmem_base_slot;
     const uint32_t raw = smem_u32(smem_raw);
     const uint32_t base = (raw + 1023u) & ~1023u;
@@ -217,7 +219,7 @@ probe_rate_pair_kernel(const uint8_t* __restrict__ img, uint32_t img_bytes, uint
     const uint32_t warp = threadIdx.x >> 5;
     const uint32_t rank = cluster_ctarank();
     if (warp == 0) tmem_alloc_pair<512>(smem_u32(&tmem_base_slot));
-    if (threadIdx.x == 32) { mbar_init(smem_u32(&mbar), 1); fence_mbar_init(); }
+    if (threadIdx.x == 32) { mbar_init(smem_u32(&mbar), 1); mbar_init(smem_u32(&scratch_bar), 1u << 20); fence_mbar_init(); }
     tc_fence_before();
     __syncthreads();
     cluster_sync_all();
@@ -234,7 +236,10 @@ probe_rate_pair_kernel(const uint8_t* __restrict__ img, uint32_t img_bytes, uint
         const long long t0 = clock64();
         for (uint32_t r = 0; r < repeat; ++r) {
 #pragma unroll
-            for (int j = 0; j < 8; ++j) mma_f16_ss_pair(tmem + (j % NACC) * acc_cols, ad[j], bd[j], idesc, 1u);
+            for (int j = 0; j < 8; ++j) {
+                mma_f16_ss_pair(tmem + (j % NACC) * acc_cols, ad[j], bd[j], idesc, 1u);
+                if (CE && ((j + 1) % (CE ? CE : 1)) == 0) mma_commit_pair(smem_u32(&scratch_bar), 3u);
+            }
         }
         const long long t_issue = clock64();
         mma_commit_pair(smem_u32(&mbar), 3u);
@@ -257,15 +262,21 @@ extern "C" int probe_mma_rate_pair(const void* img_dev, uint32_t img_bytes, uint
     RateOffs offs;
     for (int j = 0; j < 8; ++j) { offs.a[j] = a_offs16[j]; offs.b[j] = b_offs16[j]; }
     CK(cudaMemset(status_dev, 0, sizeof(int)));
-#define LAUNCH_RATE2(NA)                                                                                          \
+#define LAUNCH_RATE2(NA, CE)                                                                                      \
     do {                                                                                                          \
-        CK(cudaFuncSetAttribute(probe_rate_pair_kernel<NA>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));   \
-        probe_rate_pair_kernel<NA><<<2, 128, smem>>>((const uint8_t*)img_dev, img_bytes, adesc, bdesc, idesc, offs, \
+        CK(cudaFuncSetAttribute(probe_rate_pair_kernel<NA, CE>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); \
+        probe_rate_pair_kernel<NA, CE><<<2, 128, smem>>>((const uint8_t*)img_dev, img_bytes, adesc, bdesc, idesc, offs, \
                                                      acc_cols, repeat, cycles_dev, status_dev);                   \
     } while (0)
-    if (nacc == 1) LAUNCH_RATE2(1);
-    else if (nacc == 2) LAUNCH_RATE2(2);
-    else { snprintf(g_err, sizeof(g_err), "nacc must be 1 or 2"); return -1; }
+    int ce = 0;
+    CK(cudaMemcpyFromSymbol(&ce, g_commit_every, sizeof(int)));
+    if (nacc == 1 && ce == 0) LAUNCH_RATE2(1, 0);
+    else if (nacc == 2 && ce == 0) LAUNCH_RATE2(2, 0);
+    else if (nacc == 2 && ce == 1) LAUNCH_RATE2(2, 1);
+    else if (nacc == 2 && ce == 2) LAUNCH_RATE2(2, 2);
+    else if (nacc == 2 && ce == 4) LAUNCH_RATE2(2, 4);
+    else if (nacc == 2 && ce == 8) LAUNCH_RATE2(2, 8);
+    else { snprintf(g_err, sizeof(g_err), "unsupported nacc / commit_every"); return -1; }
     CK(cudaGetLastError());
     CK(cudaDeviceSynchronize());
     return 0;

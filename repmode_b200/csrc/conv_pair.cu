@@ -47,19 +47,25 @@ constexpr int BW = TW + 4, BH = TH + 4;        // haloed brick
 constexpr int ROWB = 64;                       // bytes per voxel row (32 fp16 channels)
 constexpr int PLANE_BYTES = BH * BW * ROWB;    // 15360
 constexpr int NT = 32;                         // output channels per pass (one accumulator slot = 32 columns)
-constexpr int GROUP = 4;                       // input planes per group
-constexpr int RING = 12;                       // plane ring (3 groups deep)
-constexpr int WST = 6;                         // weight stages
+constexpr int GROUP = 4;                       // input planes per accumulator hand-off group
 constexpr int WST_BYTES = 5 * NT * ROWB / 2;   // this CTA's half of one (chunk, kh, kw) stage: 80 rows = 5120 B
 constexpr int PERIOD = 12;                     // circular accumulator slots (+4 overflow)
 constexpr int THREADS = 256;
 constexpr int MAX_CLUSTERS = 80;
-// shared-memory map (offsets from the 1024-aligned base)
-constexpr uint32_t PLANE_OFF = 0;
-constexpr uint32_t W_OFF = RING * PLANE_BYTES;                    // 184320
-constexpr uint32_t BAR_OFF = W_OFF + WST * WST_BYTES;             // 215040
-constexpr uint32_t BN_OFF = BAR_OFF + 1024;
-constexpr uint32_t TOTAL = BN_OFF + 2 * NT * sizeof(double);
+constexpr int MAX_RING = 12, MAX_WST = 25;
+// Two shared-memory plans.  RESIDENT (K == 32): this CTA's half of ALL 25 (kh, kw) stages stays in shared memory
+// (125 KB, loaded once per sample) and planes are consumed one at a time (25 taps x 2 K-halves each), so a 6-deep plane
+// ring is enough.  STREAMING (K > 32): weight stages are re-streamed per group of 4 planes through a 6-stage ring and the
+// plane ring is 12 deep (3 groups).
+template <bool RES> struct Plan {
+    static constexpr int RING = RES ? 6 : 12;
+    static constexpr int WST = RES ? 25 : 6;
+    static constexpr uint32_t PLANE_OFF = 0;
+    static constexpr uint32_t W_OFF = RING * PLANE_BYTES;
+    static constexpr uint32_t BAR_OFF = W_OFF + WST * WST_BYTES;
+    static constexpr uint32_t BN_OFF = BAR_OFF + 1024;
+    static constexpr uint32_t TOTAL = BN_OFF + 2 * NT * sizeof(double);
+};
 }  // namespace cp
 
 struct PairParams {
@@ -75,7 +81,7 @@ struct PairParams {
     int32_t bounds[cp::MAX_CLUSTERS + 1];   // cluster c owns plane-units [bounds[c], bounds[c+1]) of (n, th2, tw, d)
     int* error_flag;
     long long* prof;
-    int flags;                   // debug: bit 0 = no tcgen05 fence after operand waits
+    int flags;                   // debug: bit 1 = force the streaming plan even when K == 32
 };
 
 // A "run" is a contiguous d-range [da, db) of one patch column; every role of both CTAs walks the same runs.
@@ -97,19 +103,24 @@ struct RunWalker {
     }
 };
 
+template <bool RES>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(cp::THREADS, 1)
 conv3d_pair_kernel(const __grid_constant__ CUtensorMap xmap, const PairParams P) {
+    using PL = cp::Plan<RES>;
+    constexpr int RING = PL::RING, WST = PL::WST;
     extern __shared__ uint8_t smem_raw[];
     const uint32_t raw = smem_u32(smem_raw);
     const uint32_t base = (raw + 1023u) & ~1023u;
     uint8_t* smem = smem_raw + (base - raw);
-    const uint32_t bars = base + cp::BAR_OFF;
-    // barrier table (8 bytes each); the *_peer and tmem_empty barriers are only used in the leader
-    const uint32_t plane_full = bars, plane_peer = bars + 8 * cp::RING, plane_empty = bars + 16 * cp::RING;
-    const uint32_t w_full = bars + 24 * cp::RING, w_peer = w_full + 8 * cp::WST, w_empty = w_full + 16 * cp::WST;
-    const uint32_t tmem_full = w_full + 24 * cp::WST, tmem_empty = tmem_full + 16;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + cp::BAR_OFF + 960);
-    double* s_bn = reinterpret_cast<double*>(smem + cp::BN_OFF);
+    const uint32_t bars = base + PL::BAR_OFF;
+    // barrier table (8 bytes each); the *_peer and tmem_empty barriers are only used in the leader.  In the RESIDENT
+    // plan only index 0 of the weight barriers is used (one "all 25 stages" hand-off per weight reload).
+    const uint32_t plane_full = bars, plane_peer = bars + 8 * cp::MAX_RING, plane_empty = bars + 16 * cp::MAX_RING;
+    const uint32_t w_full = bars + 24 * cp::MAX_RING, w_peer = w_full + 8 * cp::MAX_WST, w_empty = w_full + 16 * cp::MAX_WST;
+    const uint32_t tmem_full = w_full + 24 * cp::MAX_WST, tmem_empty = tmem_full + 16;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + PL::BAR_OFF + 1000);
+    double* s_bn = reinterpret_cast<double*>(smem + PL::BN_OFF);
+    static_assert(24 * cp::MAX_RING + 24 * cp::MAX_WST + 32 <= 1000, "barrier table overflows its 1 KB");
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t rank = cluster_ctarank();
@@ -119,10 +130,10 @@ conv3d_pair_kernel(const __grid_constant__ CUtensorMap xmap, const PairParams P)
     const uint64_t ts_entry = (P.prof != nullptr && threadIdx.x == 0) ? globaltimer_ns() : 0;
 
     if (threadIdx.x == 0) {
-        for (int i = 0; i < cp::RING; ++i) {
+        for (int i = 0; i < RING; ++i) {
             mbar_init(plane_full + 8 * i, 1); mbar_init(plane_peer + 8 * i, 1); mbar_init(plane_empty + 8 * i, 1);
         }
-        for (int i = 0; i < cp::WST; ++i) {
+        for (int i = 0; i < (RES ? 1 : WST); ++i) {
             mbar_init(w_full + 8 * i, 1); mbar_init(w_peer + 8 * i, 1); mbar_init(w_empty + 8 * i, 1);
         }
         for (int i = 0; i < 2; ++i) { mbar_init(tmem_full + 8 * i, 1); mbar_init(tmem_empty + 8 * i, 8); }
@@ -139,6 +150,7 @@ conv3d_pair_kernel(const __grid_constant__ CUtensorMap xmap, const PairParams P)
 
     if (warp == 0) {
         // ===================== activation-plane producer (own 8x16 patch, both CTAs) =====================
+        // plane order = consumption order: run, group of 4 planes, K chunk, plane
         if (lane == 0) {
             uint32_t slot = 0, use = 0;
             RunWalker rw(P, cluster);
@@ -152,9 +164,9 @@ conv3d_pair_kernel(const __grid_constant__ CUtensorMap xmap, const PairParams P)
                         for (int i = 0; i < gn; ++i) {
                             if (!mbar_wait(plane_empty + 8 * slot, (use & 1) ^ 1)) { atomicExch(P.error_flag, 11); ok = false; break; }
                             mbar_expect_tx(plane_full + 8 * slot, cp::PLANE_BYTES);
-                            tma_load_5d(base + cp::PLANE_OFF + slot * cp::PLANE_BYTES, &xmap, plane_full + 8 * slot, c * 32,
+                            tma_load_5d(base + PL::PLANE_OFF + slot * cp::PLANE_BYTES, &xmap, plane_full + 8 * slot, c * 32,
                                         w0 - 2, h0 + (int)rank * cp::TH - 2, gp + i, n);
-                            if (++slot == cp::RING) { slot = 0; ++use; }
+                            if (++slot == RING) { slot = 0; ++use; }
                         }
                     }
                 }
@@ -169,27 +181,42 @@ conv3d_pair_kernel(const __grid_constant__ CUtensorMap xmap, const PairParams P)
             int n, h0, w0, da, db;
             bool ok = true;
             const size_t blk = (size_t)P.Nout * 32;            // elements between kd blocks in the pack
+            auto copy_stage = [&](uint32_t dst, const __half* src, uint32_t bar) {
+                if (rank == 0) {
+                    bulk_load(dst, src, 2048, bar);
+                    bulk_load(dst + 2048, src + blk, 2048, bar);
+                    bulk_load(dst + 4096, src + 2 * blk, 1024, bar);
+                } else {
+                    bulk_load(dst, src + 2 * blk + 16 * 32, 1024, bar);
+                    bulk_load(dst + 1024, src + 3 * blk, 2048, bar);
+                    bulk_load(dst + 3072, src + 4 * blk, 2048, bar);
+                }
+            };
+            int cur_u = -1;
+            uint32_t nreload = 0;
             while (ok && rw.next(n, h0, w0, da, db)) {
                 const int u = P.sample_u ? P.sample_u[n] : 0;
                 const __half* wu = P.w + (size_t)u * nchunk * 125 * P.Nout * 32;
-                const int p0 = max(da - 2, 0), p1 = min(db + 1, P.D - 1);
-                for (int gp = p0; ok && gp <= p1; gp += cp::GROUP) {
-                    for (int c = 0; ok && c < nchunk; ++c) {
-                        for (int t = 0; t < 25; ++t) {
-                            if (!mbar_wait(w_empty + 8 * st, (use & 1) ^ 1)) { atomicExch(P.error_flag, 12); ok = false; break; }
-                            mbar_expect_tx(w_full + 8 * st, cp::WST_BYTES);
-                            const uint32_t dst = base + cp::W_OFF + st * cp::WST_BYTES;
-                            const __half* src = wu + ((size_t)(c * 25 + t) * 5 * P.Nout + n0) * 32;
-                            if (rank == 0) {
-                                bulk_load(dst, src, 2048, w_full + 8 * st);
-                                bulk_load(dst + 2048, src + blk, 2048, w_full + 8 * st);
-                                bulk_load(dst + 4096, src + 2 * blk, 1024, w_full + 8 * st);
-                            } else {
-                                bulk_load(dst, src + 2 * blk + 16 * 32, 1024, w_full + 8 * st);
-                                bulk_load(dst + 1024, src + 3 * blk, 2048, w_full + 8 * st);
-                                bulk_load(dst + 3072, src + 4 * blk, 2048, w_full + 8 * st);
+                if constexpr (RES) {
+                    if (u != cur_u) {                          // (re)load all 25 stages; the previous sample's MMAs must be done
+                        if (nreload > 0 && !mbar_wait(w_empty, (nreload - 1) & 1)) { atomicExch(P.error_flag, 12); break; }
+                        mbar_expect_tx(w_full, 25 * cp::WST_BYTES);
+                        for (int t = 0; t < 25; ++t)
+                            copy_stage(base + PL::W_OFF + t * cp::WST_BYTES, wu + ((size_t)t * 5 * P.Nout + n0) * 32, w_full);
+                        cur_u = u;
+                        ++nreload;
+                    }
+                } else {
+                    const int p0 = max(da - 2, 0), p1 = min(db + 1, P.D - 1);
+                    for (int gp = p0; ok && gp <= p1; gp += cp::GROUP) {
+                        for (int c = 0; ok && c < nchunk; ++c) {
+                            for (int t = 0; t < 25; ++t) {
+                                if (!mbar_wait(w_empty + 8 * st, (use & 1) ^ 1)) { atomicExch(P.error_flag, 12); ok = false; break; }
+                                mbar_expect_tx(w_full + 8 * st, cp::WST_BYTES);
+                                copy_stage(base + PL::W_OFF + st * cp::WST_BYTES, wu + ((size_t)(c * 25 + t) * 5 * P.Nout + n0) * 32,
+                                           w_full + 8 * st);
+                                if (++st == WST) { st = 0; ++use; }
                             }
-                            if (++st == cp::WST) { st = 0; ++use; }
                         }
                     }
                 }
@@ -198,24 +225,40 @@ conv3d_pair_kernel(const __grid_constant__ CUtensorMap xmap, const PairParams P)
     } else if (warp == 1 && rank != 0) {
         // ===================== peer relay: forward "landed" events to the leader in the order it consumes them ==========
         if (lane == 0) {
-            uint32_t pslot = 0, puse = 0, wst = 0, wuse = 0;
+            uint32_t pslot = 0, puse = 0, wst = 0, wuse = 0, nreload = 0;
+            int cur_u = -1;
             RunWalker rw(P, cluster);
             int n, h0, w0, da, db;
             bool ok = true;
             while (ok && rw.next(n, h0, w0, da, db)) {
                 const int p0 = max(da - 2, 0), p1 = min(db + 1, P.D - 1);
-                for (int gp = p0; ok && gp <= p1; gp += cp::GROUP) {
-                    const int gn = min(cp::GROUP, p1 - gp + 1);
-                    for (int c = 0; ok && c < nchunk; ++c) {
-                        for (int t = 0; ok && t < 25; ++t) {
-                            if (!mbar_wait(w_full + 8 * wst, wuse & 1)) { atomicExch(P.error_flag, 13); ok = false; break; }
-                            mbar_arrive_remote(w_peer + 8 * wst, 0);
-                            if (++wst == cp::WST) { wst = 0; ++wuse; }
-                            if (t == 0) {
-                                for (int i = 0; i < gn; ++i) {
-                                    if (!mbar_wait(plane_full + 8 * pslot, puse & 1)) { atomicExch(P.error_flag, 14); ok = false; break; }
-                                    mbar_arrive_remote(plane_peer + 8 * pslot, 0);
-                                    if (++pslot == cp::RING) { pslot = 0; ++puse; }
+                if constexpr (RES) {
+                    const int u = P.sample_u ? P.sample_u[n] : 0;
+                    if (u != cur_u) {
+                        if (!mbar_wait(w_full, nreload & 1)) { atomicExch(P.error_flag, 13); break; }
+                        mbar_arrive_remote(w_peer, 0);
+                        cur_u = u;
+                        ++nreload;
+                    }
+                    for (int p = p0; p <= p1; ++p) {
+                        if (!mbar_wait(plane_full + 8 * pslot, puse & 1)) { atomicExch(P.error_flag, 14); ok = false; break; }
+                        mbar_arrive_remote(plane_peer + 8 * pslot, 0);
+                        if (++pslot == RING) { pslot = 0; ++puse; }
+                    }
+                } else {
+                    for (int gp = p0; ok && gp <= p1; gp += cp::GROUP) {
+                        const int gn = min(cp::GROUP, p1 - gp + 1);
+                        for (int c = 0; ok && c < nchunk; ++c) {
+                            for (int t = 0; ok && t < 25; ++t) {
+                                if (!mbar_wait(w_full + 8 * wst, wuse & 1)) { atomicExch(P.error_flag, 13); ok = false; break; }
+                                mbar_arrive_remote(w_peer + 8 * wst, 0);
+                                if (++wst == WST) { wst = 0; ++wuse; }
+                                if (t == 0) {
+                                    for (int i = 0; i < gn; ++i) {
+                                        if (!mbar_wait(plane_full + 8 * pslot, puse & 1)) { atomicExch(P.error_flag, 14); ok = false; break; }
+                                        mbar_arrive_remote(plane_peer + 8 * pslot, 0);
+                                        if (++pslot == RING) { pslot = 0; ++puse; }
+                                    }
                                 }
                             }
                         }
@@ -236,19 +279,35 @@ conv3d_pair_kernel(const __grid_constant__ CUtensorMap xmap, const PairParams P)
             const uint32_t hi_b = (512u >> 4) | (1u << 14) | ((uint32_t)SWZ_64B << 29);
             const uint32_t lbo_lo = 1u << 16;
             const uint32_t idesc = make_idesc(FMT_F16, 256, 5 * cp::NT, 0, 0);
-            const uint32_t plane0 = ((base + cp::PLANE_OFF) >> 4) | lbo_lo, wst0 = ((base + cp::W_OFF) >> 4) | lbo_lo;
+            const uint32_t plane0 = ((base + PL::PLANE_OFF) >> 4) | lbo_lo, wst0 = ((base + PL::W_OFF) >> 4) | lbo_lo;
             const bool prof = P.prof != nullptr;
-            uint32_t pslot = 0, puse = 0, wst = 0, wuse = 0;
+            uint32_t pslot = 0, puse = 0, wst = 0, wuse = 0, nreload = 0;
             uint32_t g = 0;                                   // global group counter (accumulator hand-off parity)
             long long c_tmem = 0, c_w = 0, c_plane = 0, c_issue = 0, c_total = clock64(), t0 = 0;
             int u = P.bounds[cluster];
             const int uend = P.bounds[cluster + 1];
+            int cur_u = -1;
             int err = 0;
             while (err == 0 && u < uend) {
-                const int da = u % P.D;
+                const int col = u / P.D;
+                const int da = u - col * P.D;
                 const int db = min(P.D, da + (uend - u));
                 u += db - da;
                 const int p0 = max(da - 2, 0), p1 = min(db + 1, P.D - 1);
+                if constexpr (RES) {
+                    const int n = col / (P.tiles_w * P.tiles_h2);
+                    const int su = P.sample_u ? P.sample_u[n] : 0;
+                    if (su != cur_u) {
+                        // weights of another sample: release the resident copy once everything issued so far retires
+                        if (nreload > 0) mma_commit_pair_sel(w_empty, 3u, sel);
+                        if (prof) t0 = clock64();
+                        if (!mbar_wait_warp<false>(w_full, nreload & 1) || !mbar_wait_warp<true>(w_peer, nreload & 1)) { err = 17; break; }
+                        if (prof) c_w += clock64() - t0;
+                        tc_fence_after();
+                        cur_u = su;
+                        ++nreload;
+                    }
+                }
                 uint32_t s = 0;                               // accumulator slot of the group's first window
                 bool first = true;
                 for (int gp = p0; err == 0 && gp <= p1; gp += cp::GROUP, ++g) {
@@ -261,42 +320,67 @@ conv3d_pair_kernel(const __grid_constant__ CUtensorMap xmap, const PairParams P)
                     first = false;
                     if (prof) c_tmem += clock64() - t0;
                     tc_fence_after();
-                    for (int c = 0; err == 0 && c < nchunk; ++c) {
-                        for (int t = 0; t < 25; ++t) {
-                            const int kh = t / 5, kw = t - kh * 5;
+                    if constexpr (RES) {
+                        uint32_t ss = s;
+                        for (int i = 0; i < gn; ++i) {
                             if (prof) t0 = clock64();
-                            if (!mbar_wait_warp<false>(w_full + 8 * wst, wuse & 1) || !mbar_wait_warp<true>(w_peer + 8 * wst, wuse & 1)) {
-                                err = 17; break;
-                            }
-                            if (prof) c_w += clock64() - t0;
+                            if (!mbar_wait_warp<false>(plane_full + 8 * pslot, puse & 1) ||
+                                !mbar_wait_warp<true>(plane_peer + 8 * pslot, puse & 1)) { err = 18; break; }
+                            if (prof) c_plane += clock64() - t0;
                             tc_fence_after();
                             const long long ti = prof ? clock64() : 0;
-                            const uint32_t b_lo = wst0 + wst * (cp::WST_BYTES >> 4);
-                            const uint32_t a_tap = ((kh * cp::BW + kw) * cp::ROWB) >> 4;
-                            uint32_t slot = pslot, use = puse, ss = s;
-                            for (int i = 0; i < gn; ++i) {
-                                if (t == 0) {
-                                    if (prof) t0 = clock64();
-                                    if (!mbar_wait_warp<false>(plane_full + 8 * slot, use & 1) ||
-                                        !mbar_wait_warp<true>(plane_peer + 8 * slot, use & 1)) { err = 18; break; }
-                                    if (prof) c_plane += clock64() - t0;
-                                    tc_fence_after();
-                                }
-                                const uint32_t al = plane0 + slot * (cp::PLANE_BYTES >> 4) + a_tap;
-                                const uint32_t dcol = tm + ss * cp::NT;
-                                mma_f16_ss_pair_sel(dcol, al, hi_a, b_lo, hi_b, idesc, sel);
-                                mma_f16_ss_pair_sel(dcol, al + 2, hi_a, b_lo + 2, hi_b, idesc, sel);
-                                if (t == 24) mma_commit_pair_sel(plane_empty + 8 * slot, 3u, sel);
-                                if (++slot == cp::RING) { slot = 0; ++use; }
-                                if (++ss == cp::PERIOD) ss = 0;
+                            const uint32_t a0 = plane0 + pslot * (cp::PLANE_BYTES >> 4);
+                            const uint32_t dcol = tm + ss * cp::NT;
+#pragma unroll
+                            for (int t = 0; t < 25; ++t) {
+                                const uint32_t al = a0 + ((((t / 5) * cp::BW + (t % 5)) * cp::ROWB) >> 4);
+                                const uint32_t bl = wst0 + t * (cp::WST_BYTES >> 4);
+                                mma_f16_ss_pair_sel(dcol, al, hi_a, bl, hi_b, idesc, sel);
+                                mma_f16_ss_pair_sel(dcol, al + 2, hi_a, bl + 2, hi_b, idesc, sel);
                             }
-                            if (err) break;
-                            mma_commit_pair_sel(w_empty + 8 * wst, 3u, sel);
+                            mma_commit_pair_sel(plane_empty + 8 * pslot, 3u, sel);
                             if (prof) c_issue += clock64() - ti;
-                            if (++wst == cp::WST) { wst = 0; ++wuse; }
+                            if (++pslot == RING) { pslot = 0; ++puse; }
+                            if (++ss == cp::PERIOD) ss = 0;
                         }
-                        pslot += gn;
-                        if (pslot >= cp::RING) { pslot -= cp::RING; ++puse; }
+                    } else {
+                        for (int c = 0; err == 0 && c < nchunk; ++c) {
+                            for (int t = 0; t < 25; ++t) {
+                                const int kh = t / 5, kw = t - kh * 5;
+                                if (prof) t0 = clock64();
+                                if (!mbar_wait_warp<false>(w_full + 8 * wst, wuse & 1) || !mbar_wait_warp<true>(w_peer + 8 * wst, wuse & 1)) {
+                                    err = 17; break;
+                                }
+                                if (prof) c_w += clock64() - t0;
+                                tc_fence_after();
+                                const long long ti = prof ? clock64() : 0;
+                                const uint32_t b_lo = wst0 + wst * (cp::WST_BYTES >> 4);
+                                const uint32_t a_tap = ((kh * cp::BW + kw) * cp::ROWB) >> 4;
+                                uint32_t slot = pslot, use = puse, ss = s;
+                                for (int i = 0; i < gn; ++i) {
+                                    if (t == 0) {
+                                        if (prof) t0 = clock64();
+                                        if (!mbar_wait_warp<false>(plane_full + 8 * slot, use & 1) ||
+                                            !mbar_wait_warp<true>(plane_peer + 8 * slot, use & 1)) { err = 18; break; }
+                                        if (prof) c_plane += clock64() - t0;
+                                        tc_fence_after();
+                                    }
+                                    const uint32_t al = plane0 + slot * (cp::PLANE_BYTES >> 4) + a_tap;
+                                    const uint32_t dcol = tm + ss * cp::NT;
+                                    mma_f16_ss_pair_sel(dcol, al, hi_a, b_lo, hi_b, idesc, sel);
+                                    mma_f16_ss_pair_sel(dcol, al + 2, hi_a, b_lo + 2, hi_b, idesc, sel);
+                                    if (t == 24) mma_commit_pair_sel(plane_empty + 8 * slot, 3u, sel);
+                                    if (++slot == RING) { slot = 0; ++use; }
+                                    if (++ss == cp::PERIOD) ss = 0;
+                                }
+                                if (err) break;
+                                mma_commit_pair_sel(w_empty + 8 * wst, 3u, sel);
+                                if (prof) c_issue += clock64() - ti;
+                                if (++wst == WST) { wst = 0; ++wuse; }
+                            }
+                            pslot += gn;
+                            if (pslot >= RING) { pslot -= RING; ++puse; }
+                        }
                     }
                     if (err == 0) mma_commit_pair_sel(tmem_full + 8 * (g & 1), 3u, sel);
                     s += gn;
@@ -521,10 +605,17 @@ int conv3d_pair(const __half* x, const __half* w, const int32_t* sample_u, float
     if (const char* e = getenv("REPMODE_PAIR_FLAGS")) P.flags = atoi(e);
     CUtensorMap xmap;
     if (make_act_map(&xmap, x, N, D, H, W, K, cp::BW, cp::BH) != 0) return -1;
-    const int smem_bytes = (int)cp::TOTAL + 1024;
-    static_assert(cp::TOTAL + 1024 <= 227 * 1024, "shared memory budget");
-    MODE_CUDA(cudaFuncSetAttribute(conv3d_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
-    conv3d_pair_kernel<<<dim3(2 * G, passes), cp::THREADS, smem_bytes, st>>>(xmap, P);
+    static_assert(cp::Plan<true>::TOTAL + 1024 <= 227 * 1024 && cp::Plan<false>::TOTAL + 1024 <= 227 * 1024,
+                  "shared memory budget");
+    if (K == 32 && !(P.flags & 2)) {
+        const int smem_bytes = (int)cp::Plan<true>::TOTAL + 1024;
+        MODE_CUDA(cudaFuncSetAttribute(conv3d_pair_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
+        conv3d_pair_kernel<true><<<dim3(2 * G, passes), cp::THREADS, smem_bytes, st>>>(xmap, P);
+    } else {
+        const int smem_bytes = (int)cp::Plan<false>::TOTAL + 1024;
+        MODE_CUDA(cudaFuncSetAttribute(conv3d_pair_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
+        conv3d_pair_kernel<false><<<dim3(2 * G, passes), cp::THREADS, smem_bytes, st>>>(xmap, P);
+    }
     MODE_LAUNCH_CHECK();
     return 0;
 }

@@ -68,6 +68,8 @@ PAIR_SHAPES = [  # N, D, H, W, K, Nout, forced clusters (0 = the launcher's choi
     (1, 5, 32, 8, 32, 64, 0),          # two channel passes
     (2, 13, 64, 16, 64, 64, 0),
     (1, 2, 8, 8, 128, 96, 2),
+    (3, 6, 32, 8, 32, 32, 1),          # one cluster walks three samples: the resident weights are reloaded twice
+    (2, 7, 32, 16, 32, 64, 2),
 ]
 
 

@@ -113,14 +113,16 @@ conv3d_pair_kernel(const __grid_constant__ CUtensorMap xmap, const PairParams P)
     const uint32_t base = (raw + 1023u) & ~1023u;
     uint8_t* smem = smem_raw + (base - raw);
     const uint32_t bars = base + PL::BAR_OFF;
-    // barrier table (8 bytes each); the *_peer and tmem_empty barriers are only used in the leader.  In the RESIDENT
-    // plan only index 0 of the weight barriers is used (one "all 25 stages" hand-off per weight reload).
-    const uint32_t plane_full = bars, plane_peer = bars + 8 * cp::MAX_RING, plane_empty = bars + 16 * cp::MAX_RING;
-    const uint32_t w_full = bars + 24 * cp::MAX_RING, w_peer = w_full + 8 * cp::MAX_WST, w_empty = w_full + 16 * cp::MAX_WST;
-    const uint32_t tmem_full = w_full + 24 * cp::MAX_WST, tmem_empty = tmem_full + 16;
+    // barrier table (8 bytes each).  The leader's *_full barriers take two arrivals: its own producer's expect_tx and the
+    // peer relay's remote arrive (the operands live in both CTAs); tmem_empty is only used in the leader.  In the RESIDENT
+    // plan w_full[kh] covers the five stages of tap row kh (so the first plane can start before all 125 KB landed) and
+    // only w_empty[0] is used (one release per weight reload).
+    const uint32_t plane_full = bars, plane_empty = bars + 8 * cp::MAX_RING;
+    const uint32_t w_full = bars + 16 * cp::MAX_RING, w_empty = w_full + 8 * cp::MAX_WST;
+    const uint32_t tmem_full = w_full + 16 * cp::MAX_WST, tmem_empty = tmem_full + 16;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + PL::BAR_OFF + 1000);
     double* s_bn = reinterpret_cast<double*>(smem + PL::BN_OFF);
-    static_assert(24 * cp::MAX_RING + 24 * cp::MAX_WST + 32 <= 1000, "barrier table overflows its 1 KB");
+    static_assert(16 * cp::MAX_RING + 16 * cp::MAX_WST + 32 <= 1000, "barrier table overflows its 1 KB");
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t rank = cluster_ctarank();
@@ -131,10 +133,10 @@ conv3d_pair_kernel(const __grid_constant__ CUtensorMap xmap, const PairParams P)
 
     if (threadIdx.x == 0) {
         for (int i = 0; i < RING; ++i) {
-            mbar_init(plane_full + 8 * i, 1); mbar_init(plane_peer + 8 * i, 1); mbar_init(plane_empty + 8 * i, 1);
+            mbar_init(plane_full + 8 * i, rank == 0 ? 2 : 1); mbar_init(plane_empty + 8 * i, 1);
         }
-        for (int i = 0; i < (RES ? 1 : WST); ++i) {
-            mbar_init(w_full + 8 * i, 1); mbar_init(w_peer + 8 * i, 1); mbar_init(w_empty + 8 * i, 1);
+        for (int i = 0; i < (RES ? 5 : WST); ++i) {
+            mbar_init(w_full + 8 * i, rank == 0 ? 2 : 1); mbar_init(w_empty + 8 * i, 1);
         }
         for (int i = 0; i < 2; ++i) { mbar_init(tmem_full + 8 * i, 1); mbar_init(tmem_empty + 8 * i, 8); }
         fence_mbar_init();
@@ -200,9 +202,11 @@ conv3d_pair_kernel(const __grid_constant__ CUtensorMap xmap, const PairParams P)
                 if constexpr (RES) {
                     if (u != cur_u) {                          // (re)load all 25 stages; the previous sample's MMAs must be done
                         if (nreload > 0 && !mbar_wait(w_empty, (nreload - 1) & 1)) { atomicExch(P.error_flag, 12); break; }
-                        mbar_expect_tx(w_full, 25 * cp::WST_BYTES);
-                        for (int t = 0; t < 25; ++t)
-                            copy_stage(base + PL::W_OFF + t * cp::WST_BYTES, wu + ((size_t)t * 5 * P.Nout + n0) * 32, w_full);
+                        for (int t = 0; t < 25; ++t) {
+                            const uint32_t bar = w_full + 8 * (t / 5);
+                            if (t % 5 == 0) mbar_expect_tx(bar, 5 * cp::WST_BYTES);
+                            copy_stage(base + PL::W_OFF + t * cp::WST_BYTES, wu + ((size_t)t * 5 * P.Nout + n0) * 32, bar);
+                        }
                         cur_u = u;
                         ++nreload;
                     }
@@ -235,14 +239,17 @@ conv3d_pair_kernel(const __grid_constant__ CUtensorMap xmap, const PairParams P)
                 if constexpr (RES) {
                     const int u = P.sample_u ? P.sample_u[n] : 0;
                     if (u != cur_u) {
-                        if (!mbar_wait(w_full, nreload & 1)) { atomicExch(P.error_flag, 13); break; }
-                        mbar_arrive_remote(w_peer, 0);
+                        for (int kh = 0; ok && kh < 5; ++kh) {
+                            if (!mbar_wait(w_full + 8 * kh, nreload & 1)) { atomicExch(P.error_flag, 13); ok = false; break; }
+                            mbar_arrive_remote(w_full + 8 * kh, 0);
+                        }
+                        if (!ok) break;
                         cur_u = u;
                         ++nreload;
                     }
                     for (int p = p0; p <= p1; ++p) {
                         if (!mbar_wait(plane_full + 8 * pslot, puse & 1)) { atomicExch(P.error_flag, 14); ok = false; break; }
-                        mbar_arrive_remote(plane_peer + 8 * pslot, 0);
+                        mbar_arrive_remote(plane_full + 8 * pslot, 0);
                         if (++pslot == RING) { pslot = 0; ++puse; }
                     }
                 } else {
@@ -251,12 +258,12 @@ conv3d_pair_kernel(const __grid_constant__ CUtensorMap xmap, const PairParams P)
                         for (int c = 0; ok && c < nchunk; ++c) {
                             for (int t = 0; ok && t < 25; ++t) {
                                 if (!mbar_wait(w_full + 8 * wst, wuse & 1)) { atomicExch(P.error_flag, 13); ok = false; break; }
-                                mbar_arrive_remote(w_peer + 8 * wst, 0);
+                                mbar_arrive_remote(w_full + 8 * wst, 0);
                                 if (++wst == WST) { wst = 0; ++wuse; }
                                 if (t == 0) {
                                     for (int i = 0; i < gn; ++i) {
                                         if (!mbar_wait(plane_full + 8 * pslot, puse & 1)) { atomicExch(P.error_flag, 14); ok = false; break; }
-                                        mbar_arrive_remote(plane_peer + 8 * pslot, 0);
+                                        mbar_arrive_remote(plane_full + 8 * pslot, 0);
                                         if (++pslot == RING) { pslot = 0; ++puse; }
                                     }
                                 }
@@ -288,6 +295,7 @@ conv3d_pair_kernel(const __grid_constant__ CUtensorMap xmap, const PairParams P)
             const int uend = P.bounds[cluster + 1];
             int cur_u = -1;
             int err = 0;
+            bool fresh = false;
             while (err == 0 && u < uend) {
                 const int col = u / P.D;
                 const int da = u - col * P.D;
@@ -300,11 +308,8 @@ conv3d_pair_kernel(const __grid_constant__ CUtensorMap xmap, const PairParams P)
                     if (su != cur_u) {
                         // weights of another sample: release the resident copy once everything issued so far retires
                         if (nreload > 0) mma_commit_pair_sel(w_empty, 3u, sel);
-                        if (prof) t0 = clock64();
-                        if (!mbar_wait_warp<false>(w_full, nreload & 1) || !mbar_wait_warp<true>(w_peer, nreload & 1)) { err = 17; break; }
-                        if (prof) c_w += clock64() - t0;
-                        tc_fence_after();
                         cur_u = su;
+                        fresh = true;                         // the first plane waits for each tap row's weights as it gets there
                         ++nreload;
                     }
                 }
@@ -315,8 +320,8 @@ conv3d_pair_kernel(const __grid_constant__ CUtensorMap xmap, const PairParams P)
                     // slots this group touches were drained two groups ago; a new run restarts at slot 0, so it
                     // also needs the drain of the group just before it (the wait group g+1 would do anyway)
                     if (prof) t0 = clock64();
-                    if (!mbar_wait_warp<true>(tmem_empty + 8 * (g & 1), (g >> 1) & 1)) { err = 15; break; }
-                    if (first && g > 0 && !mbar_wait_warp<true>(tmem_empty + 8 * ((g + 1) & 1), ((g + 1) >> 1) & 1)) { err = 16; break; }
+                    if (!mbar_wait_warp<false>(tmem_empty + 8 * (g & 1), (g >> 1) & 1)) { err = 15; break; }
+                    if (first && g > 0 && !mbar_wait_warp<false>(tmem_empty + 8 * ((g + 1) & 1), ((g + 1) >> 1) & 1)) { err = 16; break; }
                     first = false;
                     if (prof) c_tmem += clock64() - t0;
                     tc_fence_after();
@@ -324,8 +329,7 @@ conv3d_pair_kernel(const __grid_constant__ CUtensorMap xmap, const PairParams P)
                         uint32_t ss = s;
                         for (int i = 0; i < gn; ++i) {
                             if (prof) t0 = clock64();
-                            if (!mbar_wait_warp<false>(plane_full + 8 * pslot, puse & 1) ||
-                                !mbar_wait_warp<true>(plane_peer + 8 * pslot, puse & 1)) { err = 18; break; }
+                            if (!mbar_wait_warp<false>(plane_full + 8 * pslot, puse & 1)) { err = 18; break; }
                             if (prof) c_plane += clock64() - t0;
                             tc_fence_after();
                             const long long ti = prof ? clock64() : 0;
@@ -333,11 +337,19 @@ conv3d_pair_kernel(const __grid_constant__ CUtensorMap xmap, const PairParams P)
                             const uint32_t dcol = tm + ss * cp::NT;
 #pragma unroll
                             for (int t = 0; t < 25; ++t) {
+                                if (t % 5 == 0 && fresh) {
+                                    if (prof) t0 = clock64();
+                                    if (!mbar_wait_warp<false>(w_full + 8 * (t / 5), (nreload - 1) & 1)) { err = 17; break; }
+                                    if (prof) c_w += clock64() - t0;
+                                    tc_fence_after();
+                                }
                                 const uint32_t al = a0 + ((((t / 5) * cp::BW + (t % 5)) * cp::ROWB) >> 4);
                                 const uint32_t bl = wst0 + t * (cp::WST_BYTES >> 4);
                                 mma_f16_ss_pair_sel(dcol, al, hi_a, bl, hi_b, idesc, sel);
                                 mma_f16_ss_pair_sel(dcol, al + 2, hi_a, bl + 2, hi_b, idesc, sel);
                             }
+                            if (err) break;
+                            fresh = false;
                             mma_commit_pair_sel(plane_empty + 8 * pslot, 3u, sel);
                             if (prof) c_issue += clock64() - ti;
                             if (++pslot == RING) { pslot = 0; ++puse; }
@@ -348,9 +360,7 @@ conv3d_pair_kernel(const __grid_constant__ CUtensorMap xmap, const PairParams P)
                             for (int t = 0; t < 25; ++t) {
                                 const int kh = t / 5, kw = t - kh * 5;
                                 if (prof) t0 = clock64();
-                                if (!mbar_wait_warp<false>(w_full + 8 * wst, wuse & 1) || !mbar_wait_warp<true>(w_peer + 8 * wst, wuse & 1)) {
-                                    err = 17; break;
-                                }
+                                if (!mbar_wait_warp<false>(w_full + 8 * wst, wuse & 1)) { err = 17; break; }
                                 if (prof) c_w += clock64() - t0;
                                 tc_fence_after();
                                 const long long ti = prof ? clock64() : 0;
@@ -360,8 +370,7 @@ conv3d_pair_kernel(const __grid_constant__ CUtensorMap xmap, const PairParams P)
                                 for (int i = 0; i < gn; ++i) {
                                     if (t == 0) {
                                         if (prof) t0 = clock64();
-                                        if (!mbar_wait_warp<false>(plane_full + 8 * slot, use & 1) ||
-                                            !mbar_wait_warp<true>(plane_peer + 8 * slot, use & 1)) { err = 18; break; }
+                                        if (!mbar_wait_warp<false>(plane_full + 8 * slot, use & 1)) { err = 18; break; }
                                         if (prof) c_plane += clock64() - t0;
                                         tc_fence_after();
                                     }
@@ -570,9 +579,11 @@ static void partition_runs(int64_t units, int D, int G, int32_t* bounds) {
 
 static int pair_clusters(int passes) { return std::max(1, std::min(cp::MAX_CLUSTERS, (sm_count() / 2) / passes)); }
 
-// Worth it (and possible) when every cluster gets a long enough march: otherwise the single-CTA kernel's finer tiles win.
+// Auto-selected when every cluster gets a long enough march (otherwise the single-CTA kernel's finer tiles win) and the
+// weights fit the RESIDENT plan (K == 32): the streaming plan re-reads every weight stage per 4 planes from L2 and is
+// slower than the single-CTA kernel today (measured 0.135 vs 0.086 ms on 64->64 @ 16x64x64).
 bool conv3d_pair_supported(int N, int D, int H, int W, int K, int Nout) {
-    if (!(K % 32 == 0 && K >= 32 && Nout % 32 == 0 && Nout >= 32 && W % cp::TW == 0)) return false;
+    if (!(K == 32 && Nout % 32 == 0 && Nout >= 32 && W % cp::TW == 0)) return false;
     const int64_t units = (int64_t)N * ceil_div(H, 2 * cp::TH) * (W / cp::TW) * D;
     if (units > 0x7fffffff) return false;
     return units >= (int64_t)12 * pair_clusters(Nout / cp::NT);

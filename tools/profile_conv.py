@@ -57,8 +57,11 @@ def main():
              "entry_spread_us": float((t_entry.max() - t0g) / 1e3), "mma_end_us_mean": float((t_mma.mean() - t0g) / 1e3),
              "mma_end_us_max": float((t_mma.max() - t0g) / 1e3), "done_us_max": float((t_done.max() - t0g) / 1e3),
              "tail_after_mma_us_mean": float(((t_done - t_mma).mean()) / 1e3)}
+        r["per_cta_cycles"] = [int(v) for v in p[:, 0].tolist()]
+        r["per_cta_tmem_wait"] = [int(v) for v in p[:, 1].tolist()]
+        r["per_cta_plane_wait"] = [int(v) for v in p[:, 3].tolist()]
         out.append(r)
-        print(json.dumps(r), flush=True)
+        print(json.dumps({k: v for k, v in r.items() if not k.startswith('per_cta')}), flush=True)
     os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
     json.dump(out, open(os.path.join(ROOT, "gpurun_out", "conv_waits.json"), "w"), indent=1)
 

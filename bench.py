@@ -30,6 +30,7 @@ T = 12
 VOX = D * H * W
 FLOP_CONV = 2.0 * 125 * CI * CO * VOX            # one of fwd / dgrad / wgrad
 METRIC = "voxels/sec MoDE-conv fwd+bwd @32x128x128x32ch"
+TRAFFIC_FILE = "r1b_traffic.json"                # ncu --set full capture of the same command (tools/ncu_summarise.py)
 
 
 def parse():
@@ -219,7 +220,8 @@ def run_ours(args, rank, local_rank, world):
     xbuf = [torch.empty(x_host.shape, device=dev).requires_grad_(True), torch.empty(x_host.shape, device=dev).requires_grad_(True)]
     ev_copied = [torch.cuda.Event(), torch.cuda.Event()]
     ev_used = [torch.cuda.Event(), torch.cuda.Event()]
-    fast = os.environ.get("REPMODE_BENCH_FAST", "0") == "1"      # profiling runs (ncu): skip the e2e and CPU legs
+    fast_level = int(os.environ.get("REPMODE_BENCH_FAST", "0"))  # profiling runs (ncu): 1 = skip the e2e and CPU legs,
+    fast = fast_level >= 1                                       # 2 = also skip the per-kernel roofline timings
     gs_e2e = [GraphStep(b) for b in xbuf] if (use_graph and not fast) else None
 
     def issue_copy(i):
@@ -295,6 +297,10 @@ def run_ours(args, rank, local_rank, world):
 
     if rank != 0:
         return
+    if fast_level >= 2:                                          # launch-list runs: only the steps themselves
+        print(json.dumps({"metric": METRIC, "value": world * VOX * args.steps / (ms * 1e-3), "unit": "voxels/s",
+                          "ms_per_step": ms / args.steps, "profiling_run": True}), flush=True)
+        return
     value = world * VOX * args.steps / (ms * 1e-3)
     e2e = world * VOX * args.steps / (ms_e2e * 1e-3)
 
@@ -340,16 +346,16 @@ def run_ours(args, rank, local_rank, world):
     achieved = FLOP_CONV / (conv_ms * 1e-3) / 1e12
     traffic = None
     try:
-        with open(os.path.join(ROOT, "profiles", "r1_traffic.json")) as f:
+        with open(os.path.join(ROOT, "profiles", TRAFFIC_FILE)) as f:
             tr = json.load(f)
-        key = "mode::conv3d_umma_kernel" if use_umma else "mode::conv3d_simt_kernel"
+        key = "conv3d_pair_kernel<1>" if use_umma else "conv3d_simt_kernel"
         traffic = sum(t["dram_bytes"] for t in tr[key]) / len(tr[key])
     except Exception:  # noqa: BLE001
         traffic = None
     roofline = {"kernel": "conv3d_pair_kernel<true> (K2 forward, tcgen05.mma.cta_group::2)" if use_umma else "conv3d_simt_kernel (K2 forward)",
                 "bound": "tensor", "achieved": achieved, "peak": tf_burst, "unit": "TFLOP/s",
                 "frac": achieved / tf_burst, "traffic": traffic,
-                "traffic_source": "ncu --set full dram__bytes_read+write per launch, profiles/r1_traffic.json",
+                "traffic_source": "ncu --set full dram__bytes_read+write per launch, profiles/" + TRAFFIC_FILE,
                 "peak_source": f"MEASURED_PEAKS.json bf16 burst ({peak_kind})",
                 "algorithmic_flop_per_launch": FLOP_CONV,
                 "others": {"dgrad_TFLOPs": FLOP_CONV / (kern["conv_dgrad_ms"] * 1e-3) / 1e12,

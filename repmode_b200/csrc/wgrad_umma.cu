@@ -68,7 +68,27 @@ wgrad_umma_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constan
     const int dlo = max(0, 2 - kd), dhi = min(P.D, P.D + 2 - kd);          // [dlo, dhi)
     const int nd = max(0, dhi - dlo);
     const int tiles = nd * P.tiles_h * P.tiles_w;
-    const int t0 = (int)((int64_t)tiles * s / P.S), t1 = (int)((int64_t)tiles * (s + 1) / P.S);
+    // slab boundaries by COST (two-row K steps), not by tile count: tiles of the last tile row are cheaper (see nk below)
+    const int nk_last = min(8, (P.H - ((P.tiles_h - 1) * wg::TH - 3) + 1) >> 1);
+    auto cum_cost = [&](int t) -> int64_t {
+        const int per_plane = P.tiles_h * P.tiles_w;
+        const int td = t / per_plane, rem = t - td * per_plane;
+        const int th = rem / P.tiles_w, tw = rem - th * P.tiles_w;
+        const int64_t plane_cost = (int64_t)P.tiles_w * (8 * (P.tiles_h - 1) + nk_last);
+        return td * plane_cost + (int64_t)th * 8 * P.tiles_w + (int64_t)tw * (th == P.tiles_h - 1 ? nk_last : 8);
+    };
+    auto cut = [&](int k) -> int {                       // smallest t with cum_cost(t) >= total * k / S
+        if (k <= 0) return 0;
+        if (k >= P.S) return tiles;
+        const int64_t target = cum_cost(tiles) * k / P.S;
+        int lo = 0, hi = tiles;
+        while (lo < hi) {
+            const int mid = (lo + hi) >> 1;
+            if (cum_cost(mid) >= target) hi = mid; else lo = mid + 1;
+        }
+        return lo;
+    };
+    const int t0 = cut(s), t1 = cut(s + 1);
 
     if (threadIdx.x == 0) {
         for (int i = 0; i < wg::STAGES; ++i) { mbar_init(full + 8 * i, 1); mbar_init(empty + 8 * i, 1); }
@@ -109,8 +129,13 @@ wgrad_umma_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constan
                 if (!mbar_wait(full + 8 * st, use & 1)) { atomicExch(P.error_flag, 12); return; }
                 tc_fence_after();
                 const uint32_t dyb = base + st * wg::STAGE, xb = dyb + wg::DY_SLOT;
+                // v-rows at or below the volume's last row pair with no dy row: the last tile row needs only
+                // ceil((H - vh0) / 2) of its 8 two-row K steps (H = 128: 2 of 8, i.e. 66 instead of 72 steps per column)
+                const int th = (t / P.tiles_w) % P.tiles_h;
+                const int nk = min(8, (P.H - (th * wg::TH - 3) + 1) >> 1);
 #pragma unroll
                 for (int kk = 0; kk < 8; ++kk) {
+                    if (kk >= nk) break;
                     const uint32_t a_lo = ((dyb + (2 * kk) * 512) >> 4) | lbo_a;
                     const uint32_t bA_lo = ((xb + (2 * kk) * wg::X_COLS * 64) >> 4) | lbo_b;
                     const uint32_t bB_lo = ((xb + (2 * kk + 4) * wg::X_COLS * 64) >> 4) | lbo_b;

@@ -38,6 +38,49 @@ def _require_cuda(*ts):
                                "There is no CPU fallback by design.")
 
 
+OVERLAP = os.environ.get("REPMODE_OVERLAP", "1") == "1"    # run the independent branches of a step on a second stream
+_side_streams = {}
+
+
+def _side_stream(dev):
+    """One extra CUDA stream per device for work that is independent of the main chain (K1 next to the operand cast,
+    dgrad next to K1b).  Tensors are always ALLOCATED on the caller's stream before the fork and joined back into it, so
+    the caching allocator never sees a cross-stream hand-off; under CUDA-graph capture the fork/join become parallel
+    graph branches."""
+    key = (dev.type, dev.index if dev.index is not None else torch.cuda.current_device())
+    st = _side_streams.get(key)
+    if st is None:
+        st = _side_streams[key] = torch.cuda.Stream(device=dev)
+    return st
+
+
+class _Fork:
+    """`with _Fork(dev, enabled):` -- launches inside run on the side stream, ordered after everything already enqueued
+    on the caller's stream; .join() makes the caller's stream wait for them."""
+
+    def __init__(self, dev, enabled=True):
+        self.enabled = enabled and OVERLAP
+        if self.enabled:
+            self.main = torch.cuda.current_stream(dev)
+            self.side = _side_stream(dev)
+            self.ctx = torch.cuda.stream(self.side)
+
+    def __enter__(self):
+        if self.enabled:
+            self.side.wait_stream(self.main)
+            self.ctx.__enter__()
+        return self
+
+    def __exit__(self, *exc):
+        if self.enabled:
+            self.ctx.__exit__(*exc)
+        return False
+
+    def join(self):
+        if self.enabled:
+            self.main.wait_stream(self.side)
+
+
 def to_ndhwc(x):
     """[N,C,D,H,W] (any strides) -> dense [N,D,H,W,C] fp32. Free when x is already channels_last_3d."""
     return x.permute(0, 2, 3, 4, 1).contiguous().float()
@@ -86,8 +129,9 @@ W_SCALE_F16 = 256.0     # fixed power-of-two scale of the fp16 weight pack: |W_e
                         # 2^-8 * 6e-5 = 2.4e-7 in absolute resolution; no per-call amax pass over the experts
 
 
-def reparam_fwd(layer, gate_in, U, ci, co, dtype, want_dgrad, w_scale=1.0):
-    """K1. Returns g [U,5,Co], w_fwd, w_dgrad (packed, see header)."""
+def reparam_fwd(layer, gate_in, U, ci, co, dtype, want_dgrad, w_scale=1.0, fork=None):
+    """K1. Returns g [U,5,Co], w_fwd, w_dgrad (packed, see header).  With `fork` (a _Fork) the kernels are launched
+    on the side stream (outputs are still allocated on the caller's stream); the caller joins before using them."""
     lib = _lib.load()
     dev = gate_in.device
     tdt = torch.float16 if dtype == _lib.MODE_F16 else torch.float32
@@ -100,15 +144,22 @@ def reparam_fwd(layer, gate_in, U, ci, co, dtype, want_dgrad, w_scale=1.0):
         w_fwd = torch.empty(U * lib.mode_packed_weight_elems(ci, co), dtype=tdt, device=dev)
         w_dg = torch.empty(U * lib.mode_packed_weight_elems(co, ci), dtype=tdt, device=dev) if want_dgrad else None
     ids, dense = (gate_in, None) if not gate_in.dtype.is_floating_point else (None, gate_in)
-    _lib.check(lib.mode_reparam_fwd(ctypes.byref(layer), _p(ids), _p(dense), U, _p(g), _p(w_fwd), _p(w_dg), dtype,
-                                    float(w_scale), None, _stream()), "mode_reparam_fwd")
+
+    def launch():
+        _lib.check(lib.mode_reparam_fwd(ctypes.byref(layer), _p(ids), _p(dense), U, _p(g), _p(w_fwd), _p(w_dg), dtype,
+                                        float(w_scale), None, _stream()), "mode_reparam_fwd")
+    if fork is not None:
+        with fork:
+            launch()
+    else:
+        launch()
     return g, w_fwd, w_dg
 
 
 def conv3d(x, dtype, w, sample_u, n, d, h, wd, k, nout, out_scale_dev=None, bn_sums=None, impl=0, stat_range=None,
-           out_scale=1.0):
+           out_scale=1.0, out=None):
     lib = _lib.load()
-    y = torch.empty((n, d, h, wd, nout), dtype=torch.float32, device=x.device)
+    y = out if out is not None else torch.empty((n, d, h, wd, nout), dtype=torch.float32, device=x.device)
     lo, hi = stat_range if stat_range is not None else (0, d)
     _lib.check(lib.mode_conv3d(_p(x), dtype, _p(w), _p(sample_u), _p(y), n, d, h, wd, k, nout, float(out_scale),
                                _p(out_scale_dev),
@@ -216,11 +267,15 @@ class ModeConvFunction(torch.autograd.Function):
         w_s2 = None
         ci_p, co_p = (_pad32(ci), _pad32(co)) if use_umma else (ci, co)
         w_scale = W_SCALE_F16 if use_umma else 1.0
+        # K1 (re-param, ~10 us of latency-bound work on a small layer) does not depend on x: it runs on the side stream
+        # while the main stream stages the fp16 operand
+        k1 = _Fork(dev, use_umma)
+        g, w_fwd, w_dg = reparam_fwd(layer, gate_u, U, ci, co, dtype, needs_dx, w_scale, fork=k1)
         if use_umma:
             x_op = pad_channels(cast_f16(xn), ci_p)
         else:
             x_op = xn
-        g, w_fwd, w_dg = reparam_fwd(layer, gate_u, U, ci, co, dtype, needs_dx, w_scale)
+        k1.join()
 
         bn_train = normal and training
         sums = torch.zeros(2 * co_p, dtype=torch.float64, device=dev) if bn_train else None
@@ -321,21 +376,26 @@ class ModeConvFunction(torch.autograd.Function):
 
         if use_umma:
             dy_op = pad_channels(dy_op, co_p)
-        dx = None
-        if needs_dx:
-            dxn = conv3d(dy_op, dtype, w_dg, sample_u, n, d, h, wd, co_p, ci_p, dy_s2[1:2] if use_umma else None, None,
-                         out_scale=(1.0 / W_SCALE_F16) if use_umma else 1.0)
-            if ci_p != ci:
-                dxn = dxn[..., :ci].contiguous()
-            dx = from_ndhwc(dxn)
-        grads = [None] * 7
+        # Order: K4 (wgrad, fills every SM) first; then K3 (dgrad) on the side stream NEXT TO the K1b chain on the main
+        # stream -- the CTA-pair dgrad leaves SMs idle on a single volume (64 clusters on 148 SMs) and K1b / gate
+        # backward are small latency-bound kernels, so they hide completely behind it.
+        d_weff = None
         if needs_dw:
             if wgrad_f32:
                 d_weff = conv3d_wgrad(x_w, dy32, _lib.MODE_F32, n, d, h, wd, ci, co, None)
             else:
                 d_weff = conv3d_wgrad(x_w, dy_op, dtype, n, d, h, wd, ci_p, co_p, dy_s2[1:2] if use_umma else None)
-                if ci_p != ci or co_p != co:
-                    d_weff = d_weff[:, :, :co, :ci].contiguous()
+        dx = None
+        dg_fork = _Fork(dev, needs_dx and needs_dw)
+        if needs_dx:
+            dxn = torch.empty((n, d, h, wd, ci_p), dtype=torch.float32, device=dev)
+            with dg_fork:
+                conv3d(dy_op, dtype, w_dg, sample_u, n, d, h, wd, co_p, ci_p, dy_s2[1:2] if use_umma else None, None,
+                       out_scale=(1.0 / W_SCALE_F16) if use_umma else 1.0, out=dxn)
+        grads = [None] * 7
+        if needs_dw:
+            if not wgrad_f32 and (ci_p != ci or co_p != co):
+                d_weff = d_weff[:, :, :co, :ci].contiguous()
             layer, _, _ = _layer(k5, k3, k1, a3, a5, gate_w, gate_b)
             outs = [torch.empty_like(t) for t in (k5, k3, k1, a3, a5, gate_w, gate_b)]
             ws = torch.empty(max(int(lib.mode_reparam_bwd_workspace_bytes(ci, co, n)), 16), dtype=torch.uint8, device=dev)
@@ -343,6 +403,11 @@ class ModeConvFunction(torch.autograd.Function):
             _lib.check(lib.mode_reparam_bwd(ctypes.byref(layer), _p(ids), _p(dense), U, _p(sample_u), n, _p(g), _p(d_weff),
                                             *[_p(o) for o in outs], _p(ws), _stream()), "mode_reparam_bwd")
             grads = outs
+        dg_fork.join()
+        if needs_dx:
+            if ci_p != ci:
+                dxn = dxn[..., :ci].contiguous()
+            dx = from_ndhwc(dxn)
         return (dx, None, *grads, dgamma, dbeta, None, None, None, None, None, None)
 
 

@@ -510,7 +510,7 @@ conv3d_pair_kernel(const __grid_constant__ CUtensorMap xmap, const PairParams P)
 // ------------------------------------------------------------------------------------------------ host
 int* device_error_flag();            // mode_abi.cu
 long long* debug_profile_buffer();   // mode_abi.cu
-int make_act_map(CUtensorMap* map, const __half* x, int N, int D, int H, int W, int K, int box_w, int box_h);   // conv_umma.cu
+int make_act_map(CUtensorMap* map, const __half* x, int N, int D, int H, int W, int K, int box_w, int box_h, int box_d);   // conv_umma.cu
 
 // input planes a run [da, db) of a D-plane column has to process (+0.25 per group hand-off)
 static double run_cost(int da, int db, int D) {
@@ -615,7 +615,7 @@ int conv3d_pair(const __half* x, const __half* w, const int32_t* sample_u, float
     P.flags = 0;
     if (const char* e = getenv("REPMODE_PAIR_FLAGS")) P.flags = atoi(e);
     CUtensorMap xmap;
-    if (make_act_map(&xmap, x, N, D, H, W, K, cp::BW, cp::BH) != 0) return -1;
+    if (make_act_map(&xmap, x, N, D, H, W, K, cp::BW, cp::BH, 1) != 0) return -1;
     static_assert(cp::Plan<true>::TOTAL + 1024 <= 227 * 1024 && cp::Plan<false>::TOTAL + 1024 <= 227 * 1024,
                   "shared memory budget");
     if (K == 32 && !(P.flags & 2)) {

@@ -387,13 +387,13 @@ static EncodeTiledFn encode_fn() {
     return fn;
 }
 
-int make_act_map(CUtensorMap* map, const __half* x, int N, int D, int H, int W, int K, int box_w, int box_h) {
+int make_act_map(CUtensorMap* map, const __half* x, int N, int D, int H, int W, int K, int box_w, int box_h, int box_d) {
     EncodeTiledFn fn = encode_fn();
     if (!fn) MODE_FAIL("cuTensorMapEncodeTiled entry point unavailable");
     cuuint64_t dims[5] = {(cuuint64_t)K, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)D, (cuuint64_t)N};
     cuuint64_t str[4] = {(cuuint64_t)K * 2, (cuuint64_t)W * K * 2, (cuuint64_t)H * W * K * 2,
                          (cuuint64_t)D * H * W * K * 2};
-    cuuint32_t box[5] = {32, (cuuint32_t)box_w, (cuuint32_t)box_h, 1, 1};
+    cuuint32_t box[5] = {32, (cuuint32_t)box_w, (cuuint32_t)box_h, (cuuint32_t)box_d, 1};
     cuuint32_t es[5] = {1, 1, 1, 1, 1};
     CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 5, (void*)x, dims, str, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
                     CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -531,7 +531,7 @@ int conv3d_umma(const __half* x, const __half* w, const int32_t* sample_u, float
     P.prof = debug_profile_buffer();
 
     CUtensorMap xmap;
-    if (make_act_map(&xmap, x, N, D, H, W, K, cu::BW, cu::BH) != 0) return -1;
+    if (make_act_map(&xmap, x, N, D, H, W, K, cu::BW, cu::BH, 1) != 0) return -1;
     MODE_CUDA(cudaFuncSetAttribute(conv3d_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
     const int grid = total < (int64_t)sm_count() ? (int)total : std::min(sm_count(), 159);
     partition_units(P.units, D, P.TD, P.Nt, K / 32, grid, P.bounds);

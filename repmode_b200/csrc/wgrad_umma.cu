@@ -217,7 +217,7 @@ __global__ void __launch_bounds__(256) wgrad_reduce_kernel(const float* __restri
 
 // ------------------------------------------------------------------------------------------------ host
 int* device_error_flag();   // mode_abi.cu
-int make_act_map(CUtensorMap* map, const __half* x, int N, int D, int H, int W, int K, int box_w, int box_h);  // conv_umma.cu
+int make_act_map(CUtensorMap* map, const __half* x, int N, int D, int H, int W, int K, int box_w, int box_h, int box_d);  // conv_umma.cu
 
 static int wgrad_slabs(int N, int Ci, int Co) {
     const int units_per_slab = N * (Ci / 32) * (Co / 32) * 5;
@@ -253,8 +253,8 @@ int wgrad_umma(const __half* x, const __half* dy, float* dw, int N, int D, int H
     const int64_t units = (int64_t)N * P.ncic * P.ncoc * 5 * P.S;
     if (units > 0x7fffffff) MODE_FAIL("wgrad_umma: too many work units");
     CUtensorMap xmap, dymap;
-    if (make_act_map(&xmap, x, N, D, H, W, Ci, wg::X_COLS, wg::X_ROWS) != 0) return -1;
-    if (make_act_map(&dymap, dy, N, D, H, W, Co, wg::TW, wg::DY_ROWS) != 0) return -1;
+    if (make_act_map(&xmap, x, N, D, H, W, Ci, wg::X_COLS, wg::X_ROWS, 1) != 0) return -1;
+    if (make_act_map(&dymap, dy, N, D, H, W, Co, wg::TW, wg::DY_ROWS, 1) != 0) return -1;
     const int smem_bytes = wg::STAGES * wg::STAGE + 512 + 1024;
     MODE_CUDA(cudaFuncSetAttribute(wgrad_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
     wgrad_umma_kernel<<<(unsigned)units, wg::THREADS, smem_bytes, st>>>(xmap, dymap, P);

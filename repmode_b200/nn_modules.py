@@ -57,6 +57,7 @@ class MoDEConv(torch.nn.Module):
         self.gate = torch.nn.Linear(num_tasks, num_experts * out_chan, bias=True)
         self.softmax = torch.nn.Softmax(dim=1)
         self.precision = None          # None -> REPMODE_PRECISION env / default ('f16' tensor-core path)
+        self._eval_cache = Fm.EvalWeightCache()      # per-task W_eff for eval mode (not part of the state_dict)
 
     def gen_conv_kernel(self, Co, Ci, K):
         weight = torch.nn.Parameter(torch.empty(Co, Ci, K, K, K))
@@ -77,6 +78,11 @@ class MoDEConv(torch.nn.Module):
             bn = (m.weight, m.bias, m.running_mean, m.running_var)
             if self.training and m.track_running_stats and m.num_batches_tracked is not None:
                 m.num_batches_tracked.add_(1)
+        if (not self.training and not torch.is_grad_enabled() and not t.dtype.is_floating_point
+                and Fm.EVAL_CACHE):
+            # Model.predict path (eval + no_grad, int task ids): W_eff of every task is built once and reused
+            return Fm.mode_conv_eval(x, t, self._params(), bn, self.conv_type,
+                                     self.precision or Fm.default_precision(), self._eval_cache)
         return Fm.mode_conv(x, t, self._params(), bn, self.training, self.conv_type, self.precision)
 
 

@@ -96,3 +96,37 @@ def test_reparam_weff_bitexact_vs_golden():
     assert_close(w.cpu().numpy(), d["w_eff"], 1e-6, "w_eff")
     wd = w_dg.view(U, 125, co // 32, ci, 32).permute(0, 2, 4, 3, 1).reshape(U, co, ci, 125).flip(-1).reshape(U, co, ci, 5, 5, 5)
     assert_close(wd.cpu().numpy(), d["w_eff"], 1e-6, "w_dgrad")
+
+
+@pytest.mark.parametrize("precision", ["f32", "f16"])
+def test_eval_weight_cache_matches_uncached_and_invalidates(precision, monkeypatch):
+    """Eval + no_grad (Model.predict, fnet_model.py:149-223): W_eff of every task is built once per parameter version
+    (SURVEY.md 8f-3).  The cached path must equal the per-call path bit for bit, use sample 0's task for the whole batch
+    (RepMode.py:209-210), launch no K1 kernel on reuse, and rebuild after a parameter update."""
+    from repmode_b200 import functional as Fm, lib as L
+    d = load_golden("conv_eval_small")
+    m = _build_conv(d, precision).eval()
+    x = torch.from_numpy(d["x"]).cuda()
+    nt = int(d["num_tasks"])
+    lib = L.load()
+    with torch.no_grad():
+        for task in range(nt):
+            ids = torch.tensor([task, (task + 1) % nt][: x.shape[0]] * x.shape[0], device="cuda")[: x.shape[0]]
+            monkeypatch.setattr(Fm, "EVAL_CACHE", True)
+            a = m(x, ids)
+            n0 = lib.mode_launch_count()
+            a2 = m(x, ids)
+            launches_cached = lib.mode_launch_count() - n0
+            monkeypatch.setattr(Fm, "EVAL_CACHE", False)
+            n0 = lib.mode_launch_count()
+            b = m(x, ids)
+            launches_plain = lib.mode_launch_count() - n0
+            assert torch.equal(a, b) and torch.equal(a, a2)
+            assert launches_cached < launches_plain          # no re-parameterisation launch on a cache hit
+        monkeypatch.setattr(Fm, "EVAL_CACHE", True)
+        before = m(x, ids).clone()
+        m.expert_conv5x5_conv.mul_(1.5)                       # in-place update bumps the version counter
+        after = m(x, ids)
+        monkeypatch.setattr(Fm, "EVAL_CACHE", False)
+        assert not torch.equal(before, after)
+        assert torch.equal(after, m(x, ids))

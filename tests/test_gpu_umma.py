@@ -142,20 +142,25 @@ WG_SHAPES = [  # N, D, H, W, Ci, Co
     (1, 5, 24, 8, 64, 32),
     (1, 2, 16, 16, 32, 64),
     (1, 6, 40, 24, 64, 64),
+    (1, 7, 8, 8, 32, 32),           # H < 16, odd D (the leftover units' last plane pair holds one x plane)
+    (1, 9, 48, 16, 32, 32),         # many slabs per unit kind: cost-weighted slab cuts inside planes
 ]
 
 
+@pytest.mark.parametrize("impl", ["stacked", "split"])
 @pytest.mark.parametrize("shape", WG_SHAPES)
-def test_wgrad_umma_bitexact(shape):
-    """K4 on tcgen05 (stacked-tap MN-major views) == SIMT fp32 wgrad == oracle, exactly, on integer-valued data."""
+def test_wgrad_umma_bitexact(shape, impl):
+    """K4 on tcgen05 (tap-stacking through overlapping MN-major views; wgrad_umma.cu = 10 MMAs per K step, wgrad_split.cu
+    = 7) == SIMT fp32 wgrad == oracle, exactly, on integer-valued data."""
     from repmode_b200 import functional as Fm, lib as L
     n, d, h, w, ci, co = shape
+    which = L.IMPL_WGRAD_STACKED if impl == "stacked" else L.IMPL_WGRAD_SPLIT
     rng = np.random.RandomState(sum(shape) + 1)
     x = rng.randint(-3, 4, size=(n, d, h, w, ci)).astype(np.float32)
     dy = rng.randint(-3, 4, size=(n, d, h, w, co)).astype(np.float32)
     xg, dyg = torch.from_numpy(x).cuda(), torch.from_numpy(dy).cuda()
     dw_simt = Fm.conv3d_wgrad(xg, dyg, L.MODE_F32, n, d, h, w, ci, co, None, impl=L.IMPL_SIMT)
-    dw_umma = Fm.conv3d_wgrad(xg.half(), dyg.half(), L.MODE_F16, n, d, h, w, ci, co, None, impl=L.IMPL_UMMA)
+    dw_umma = Fm.conv3d_wgrad(xg.half(), dyg.half(), L.MODE_F16, n, d, h, w, ci, co, None, impl=which)
     _poll()
     if n * d * h * w * ci * co <= 2 ** 22:
         ref = np.stack([onp.conv3d_wgrad(x[i].transpose(3, 0, 1, 2), dy[i].transpose(3, 0, 1, 2)) for i in range(n)])

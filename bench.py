@@ -30,7 +30,9 @@ T = 12
 VOX = D * H * W
 FLOP_CONV = 2.0 * 125 * CI * CO * VOX            # one of fwd / dgrad / wgrad
 METRIC = "voxels/sec MoDE-conv fwd+bwd @32x128x128x32ch"
-TRAFFIC_FILE = "r1b_traffic.json"                # ncu --set full capture of the same command (tools/ncu_summarise.py)
+TRAFFIC_FILES = ("r1e_traffic.json", "r1d_traffic.json", "r1b_traffic.json")   # newest ncu --set full capture of the
+TRAFFIC_FILE = next((f for f in TRAFFIC_FILES                                    # same command (tools/ncu_summarise.py)
+                     if os.path.exists(os.path.join(ROOT, "profiles", f))), TRAFFIC_FILES[-1])
 
 
 def parse():

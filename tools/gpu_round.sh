@@ -30,12 +30,14 @@ if has bench; then
 fi
 
 if has ab && [ $OK -eq 1 ]; then
-  echo "== A/B (resident steps only): no stream overlap / stacked wgrad"
+  echo "== A/B (resident steps only): no stream overlap / split-tap wgrad"
   REPMODE_BENCH_FAST=1 REPMODE_OVERLAP=0 timeout 120 python bench.py --steps 20 --warmup 5 > $O/${TAG}_bench_nooverlap.json 2>/dev/null
   cut -c1-330 $O/${TAG}_bench_nooverlap.json; echo
-  REPMODE_BENCH_FAST=1 REPMODE_WGRAD_STACKED=1 timeout 120 python bench.py --steps 20 --warmup 5 > $O/${TAG}_bench_stacked.json 2>/dev/null
-  cut -c1-330 $O/${TAG}_bench_stacked.json; echo
-  grep -o '"wgrad_ms": [0-9.]*' $O/${TAG}_bench.json $O/${TAG}_bench_stacked.json
+  if has split; then
+    REPMODE_BENCH_FAST=1 REPMODE_WGRAD_SPLIT=1 timeout 120 python bench.py --steps 20 --warmup 5 > $O/${TAG}_bench_split.json 2>/dev/null
+    cut -c1-330 $O/${TAG}_bench_split.json; echo
+    grep -o '"wgrad_ms": [0-9.]*' $O/${TAG}_bench.json $O/${TAG}_bench_split.json
+  fi
 fi
 
 if has breakdown && [ $OK -eq 1 ]; then
@@ -60,6 +62,13 @@ if has ncu && [ $OK -eq 1 ]; then
   ncu_full conv 'conv3d_pair|conv3d_umma' 6 2 "--import-source on"
   ncu_full wgrad 'wgrad_split_kernel|wgrad_umma_kernel' 3 1 "--import-source on"
   ncu_full stream 'bn_|reparam|cast_f16|pack_dgrad|gate_bwd|wgrad_reduce|wgrad_split_reduce' 33 11 ""
+fi
+
+if has net && [ $OK -eq 1 ]; then
+  echo "== whole-Net timings (BASELINE.json configs 1-2; not the headline bench)"
+  timeout 150 python tools/bench_net.py --steps 3 > $O/${TAG}_bench_net.log 2>&1
+  cp $O/bench_net.json $O/${TAG}_bench_net.json 2>/dev/null
+  tail -2 $O/${TAG}_bench_net.log | cut -c1-300
 fi
 
 if has ref; then

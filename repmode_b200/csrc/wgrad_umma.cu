@@ -17,6 +17,7 @@
 // TMEM and writes one [25 taps x 32 x 32] fp32 partial; wgrad_reduce_kernel sums the slabs (deterministic).
 // Roles: warp 0 = TMA producer, warp 1 = MMA issuer, warp 2 = TMEM allocator, warps 4-7 = epilogue.
 #include <cuda.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 #include "ptx_sm100.cuh"
@@ -42,6 +43,7 @@ struct WgradParams {
     int N, D, H, W, Ci, Co;
     int ncic, ncoc, S;              // chunk counts, slabs per (n, coc, cic, kd)
     int tiles_h, tiles_w;
+    int trim;                       // 1: skip the all-zero K steps of the last tile row and cut slabs by cost
     int* error_flag;
 };
 
@@ -69,7 +71,7 @@ wgrad_umma_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constan
     const int nd = max(0, dhi - dlo);
     const int tiles = nd * P.tiles_h * P.tiles_w;
     // slab boundaries by COST (two-row K steps), not by tile count: tiles of the last tile row are cheaper (see nk below)
-    const int nk_last = min(8, (P.H - ((P.tiles_h - 1) * wg::TH - 3) + 1) >> 1);
+    const int nk_last = P.trim ? min(8, (P.H - ((P.tiles_h - 1) * wg::TH - 3) + 1) >> 1) : 8;
     auto cum_cost = [&](int t) -> int64_t {
         const int per_plane = P.tiles_h * P.tiles_w;
         const int td = t / per_plane, rem = t - td * per_plane;
@@ -125,27 +127,42 @@ wgrad_umma_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constan
             const uint32_t lbo_b = (64u >> 4) << 16;     // block bn = +1 voxel of the x brick
             const uint32_t idesc = make_idesc(FMT_F16, 128, 160, 1, 1);
             uint32_t st = 0, use = 0, acc = 0;
+            // v-rows at or below the volume's last row pair with no dy row: tiles of the LAST tile row need only
+            // nk_last = ceil((H - vh0) / 2) of their 8 two-row K steps (H = 128: 2 of 8, i.e. 66 instead of 72 steps per
+            // column).  The issue rate of this single-thread loop is what bounds the kernel (r1e: an extra compare-and-branch
+            // per MMA pair cost 30 us), so full tiles keep the branch-free fully unrolled body and only the last tile row
+            // takes the counted loop; the tile-row index is a wrapped counter, not a division per tile.
+            int tw_c = t0 % P.tiles_w, th_c = (t0 / P.tiles_w) % P.tiles_h;
             for (int t = t0; t < t1; ++t) {
                 if (!mbar_wait(full + 8 * st, use & 1)) { atomicExch(P.error_flag, 12); return; }
                 tc_fence_after();
                 const uint32_t dyb = base + st * wg::STAGE, xb = dyb + wg::DY_SLOT;
-                // v-rows at or below the volume's last row pair with no dy row: the last tile row needs only
-                // ceil((H - vh0) / 2) of its 8 two-row K steps (H = 128: 2 of 8, i.e. 66 instead of 72 steps per column)
-                const int th = (t / P.tiles_w) % P.tiles_h;
-                const int nk = min(8, (P.H - (th * wg::TH - 3) + 1) >> 1);
+                if (th_c != P.tiles_h - 1 || nk_last == 8) {
 #pragma unroll
-                for (int kk = 0; kk < 8; ++kk) {
-                    if (kk >= nk) break;
-                    const uint32_t a_lo = ((dyb + (2 * kk) * 512) >> 4) | lbo_a;
-                    const uint32_t bA_lo = ((xb + (2 * kk) * wg::X_COLS * 64) >> 4) | lbo_b;
-                    const uint32_t bB_lo = ((xb + (2 * kk + 4) * wg::X_COLS * 64) >> 4) | lbo_b;
-                    const uint64_t ad = ((uint64_t)hi_a << 32) | a_lo;
-                    mma_f16_ss(tmem, ad, ((uint64_t)hi_b << 32) | bA_lo, idesc, acc);
-                    mma_f16_ss(tmem + 160, ad, ((uint64_t)hi_b << 32) | bB_lo, idesc, acc);
-                    acc = 1;
+                    for (int kk = 0; kk < 8; ++kk) {
+                        const uint32_t a_lo = ((dyb + (2 * kk) * 512) >> 4) | lbo_a;
+                        const uint32_t bA_lo = ((xb + (2 * kk) * wg::X_COLS * 64) >> 4) | lbo_b;
+                        const uint32_t bB_lo = ((xb + (2 * kk + 4) * wg::X_COLS * 64) >> 4) | lbo_b;
+                        const uint64_t ad = ((uint64_t)hi_a << 32) | a_lo;
+                        mma_f16_ss(tmem, ad, ((uint64_t)hi_b << 32) | bA_lo, idesc, acc);
+                        mma_f16_ss(tmem + 160, ad, ((uint64_t)hi_b << 32) | bB_lo, idesc, acc);
+                        acc = 1;
+                    }
+                } else {
+#pragma unroll 1
+                    for (int kk = 0; kk < nk_last; ++kk) {
+                        const uint32_t a_lo = ((dyb + (2 * kk) * 512) >> 4) | lbo_a;
+                        const uint32_t bA_lo = ((xb + (2 * kk) * wg::X_COLS * 64) >> 4) | lbo_b;
+                        const uint32_t bB_lo = ((xb + (2 * kk + 4) * wg::X_COLS * 64) >> 4) | lbo_b;
+                        const uint64_t ad = ((uint64_t)hi_a << 32) | a_lo;
+                        mma_f16_ss(tmem, ad, ((uint64_t)hi_b << 32) | bA_lo, idesc, acc);
+                        mma_f16_ss(tmem + 160, ad, ((uint64_t)hi_b << 32) | bB_lo, idesc, acc);
+                        acc = 1;
+                    }
                 }
                 mma_commit(empty + 8 * st);
                 if (++st == wg::STAGES) { st = 0; ++use; }
+                if (++tw_c == P.tiles_w) { tw_c = 0; if (++th_c == P.tiles_h) th_c = 0; }
             }
             mma_commit(done);
         }
@@ -248,6 +265,8 @@ int wgrad_umma(const __half* x, const __half* dy, float* dw, int N, int D, int H
     P.S = wgrad_slabs(N, Ci, Co);
     P.tiles_h = (int)ceil_div(H + 3, wg::TH);
     P.tiles_w = W / wg::TW;
+    static const bool notrim = getenv("REPMODE_WGRAD_NOTRIM") != nullptr;     // A/B knob: the untrimmed r1b behaviour
+    P.trim = notrim ? 0 : 1;
     P.error_flag = device_error_flag();
     if (!P.error_flag) MODE_FAIL("wgrad_umma: could not allocate the device error flag");
     const int64_t units = (int64_t)N * P.ncic * P.ncoc * 5 * P.S;

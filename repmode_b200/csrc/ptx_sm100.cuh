@@ -293,6 +293,32 @@ __device__ __forceinline__ void mma_commit_pair_sel(uint32_t bar, uint32_t cta_m
         "}\n" ::"r"(bar), "r"(cta_mask), "r"(sel)
         : "memory");
 }
+// Single-CTA versions of the same idea (wgrad_split.cu): the accumulate flag is a warp-uniform operand.
+__device__ __forceinline__ void mma_f16_ss_sel(uint32_t d_tmem, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi,
+                                               uint32_t idesc, uint32_t accumulate, uint32_t sel) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred q, acc;\n\t"
+        ".reg .b64 da, db;\n\t"
+        "mov.b64 da, {%1, %2};\n\t"
+        "mov.b64 db, {%3, %4};\n\t"
+        "setp.ne.u32 acc, %6, 0;\n\t"
+        "setp.ne.u32 q, %7, 0;\n\t"
+        "@q tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, acc;\n\t"
+        "}\n"
+        :
+        : "r"(d_tmem), "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate), "r"(sel)
+        : "memory");
+}
+__device__ __forceinline__ void mma_commit_sel(uint32_t bar, uint32_t sel) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred q;\n\t"
+        "setp.ne.u32 q, %1, 0;\n\t"
+        "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t"
+        "}\n" ::"r"(bar), "r"(sel)
+        : "memory");
+}
 // Warp-collective, time-bounded mbarrier wait whose RESULT is warp-uniform (vote), so that the code after it stays
 // convergent and ptxas can keep descriptors in uniform registers.  cluster = acquire at cluster scope.
 template <bool kCluster>

@@ -183,7 +183,15 @@ wgrad_split_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_consta
         }
     } else if (warp == 1) {
         // ===================== MMA issuer =====================
-        if (lane == 0) {
+        // The WHOLE warp runs this loop on warp-uniform values (kernel parameters, block index, loop counters, vote
+        // results) and one elected lane is predicated inside the asm: under `if (lane == 0)` ptxas must assume divergence
+        // and wraps every UTCHMMA in an ELECT / 5x R2UR.BROADCAST loop, and that issue cost (~100-117 cycles per MMA
+        // measured) -- not the 81 cycles the tensor pipe needs -- is what bounded this kernel (r1d) and the stacked one.
+        // Every full tile takes a branch-free, fully unrolled body chosen ONCE per tile; only the last tile row (fewer K
+        // steps) and the volume's boundary planes take the counted loops.  Tile coordinates are wrapped counters.
+        {
+            const uint32_t sel = elect_one() ? 1u : 0u;
+            const uint32_t tm = __reduce_max_sync(0xffffffffu, tmem);             // provably uniform copy of the TMEM base
             // MN-major operands, 64B swizzle: lo = addr>>4 | (LBO>>4)<<16 ; hi = SBO>>4 | version | swizzle.
             // SBO = stride between the two 8-voxel K groups of a K16 step = the next brick row.
             const uint32_t hi_a = (512u >> 4) | (1u << 14) | ((uint32_t)SWZ_64B << 29);
@@ -193,47 +201,86 @@ wgrad_split_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_consta
             const uint32_t lbo_vox = (64u >> 4) << 16;                  // N block bn = x brick + bn voxels
             const uint32_t idesc = make_idesc(FMT_F16, 128, 160, 1, 1);
             uint32_t st = 0, use = 0, acc0 = 0, acc1 = 0;
+            const int per_plane = tiles_h * P.tiles_w;
+            int tw_c = t0 % P.tiles_w, th_c = (t0 / P.tiles_w) % tiles_h, td = t0 / per_plane;
+            bool ok = true;
+#define WS_B(xbase, kk) ((((xbase) + 2 * (kk) * ws::X_COLS * 64) >> 4) | lbo_vox)
+#define WS_MMA(col, alo, blo, acc) mma_f16_ss_sel(tm + (col), (alo), hi_a, (blo), hi_b, idesc, (acc), sel)
             for (int t = t0; t < t1; ++t) {
-                const int th = (t / P.tiles_w) % tiles_h, td = t / (P.tiles_w * tiles_h);
-                if (!mbar_wait(full + 8 * st, use & 1)) { atomicExch(P.error_flag, 22); return; }
+                if (!mbar_wait_warp<false>(full + 8 * st, use & 1)) { ok = false; break; }
                 tc_fence_after();
                 const uint32_t sb = base + st * stage_bytes;
+                const bool full_row = th_c != tiles_h - 1 || nk_last == 8;
                 if (is_l) {
-                    // v-rows at or past the volume's last row meet no dy row: trim the last tile row's K steps
-                    const int nk = min(8, (P.H - th * ws::TH + 1) >> 1);
+                    const uint32_t x0 = sb + ws::L_DY_BYTES, x1 = x0 + ws::X_BYTES;
                     const int nx = (2 * td + 1 < P.D) ? 2 : 1;
-                    for (int kk = 0; kk < nk; ++kk) {
-                        for (int xi = 0; xi < nx; ++xi) {
-                            const uint32_t xb = sb + ws::L_DY_BYTES + xi * ws::X_BYTES;
-                            const uint64_t bd = ((uint64_t)hi_b << 32) | (((xb + 2 * kk * ws::X_COLS * 64) >> 4) | lbo_vox);
-                            const uint32_t a1 = ((sb + (1 + xi) * ws::L_PLANE + kk * 1024) >> 4) | lbo_plane;   // planes p-1..p+2
-                            const uint32_t a2 = ((sb + xi * ws::L_PLANE + kk * 1024) >> 4) | lbo_plane;         // planes p-2..p+1
-                            mma_f16_ss(tmem, ((uint64_t)hi_a << 32) | a1, bd, idesc, acc0);
-                            mma_f16_ss(tmem + 160, ((uint64_t)hi_a << 32) | a2, bd, idesc, acc0);
+                    if (full_row && nx == 2) {
+#pragma unroll
+                        for (int kk = 0; kk < 8; ++kk) {
+                            // x plane p: dy planes p-1.. (kd = 3 - bm) and p-2.. (bm = 0: kd = 4); x plane p+1: one plane on
+                            const uint32_t b0 = WS_B(x0, kk), b1 = WS_B(x1, kk);
+                            const uint32_t a0 = ((sb + 0 * ws::L_PLANE + kk * 1024) >> 4) | lbo_plane;
+                            const uint32_t a1 = ((sb + 1 * ws::L_PLANE + kk * 1024) >> 4) | lbo_plane;
+                            const uint32_t a2 = ((sb + 2 * ws::L_PLANE + kk * 1024) >> 4) | lbo_plane;
+                            WS_MMA(0, a1, b0, acc0);
+                            WS_MMA(160, a0, b0, acc0);
+                            WS_MMA(0, a2, b1, 1u);
+                            WS_MMA(160, a1, b1, 1u);
                             acc0 = 1;
+                        }
+                    } else {
+                        const int nk = full_row ? 8 : nk_last;
+#pragma unroll 1
+                        for (int kk = 0; kk < nk; ++kk) {
+#pragma unroll 1
+                            for (int xi = 0; xi < nx; ++xi) {
+                                const uint32_t bd = WS_B(x0 + xi * ws::X_BYTES, kk);
+                                const uint32_t a1 = ((sb + (1 + xi) * ws::L_PLANE + kk * 1024) >> 4) | lbo_plane;   // planes p-1..p+2
+                                const uint32_t a2 = ((sb + xi * ws::L_PLANE + kk * 1024) >> 4) | lbo_plane;         // planes p-2..p+1
+                                WS_MMA(0, a1, bd, acc0);
+                                WS_MMA(160, a2, bd, acc0);
+                                acc0 = 1;
+                            }
                         }
                     }
                 } else {
                     const int d = dlo + td;
-                    const int nk = min(8, (P.H - (th * ws::TH - 3) + 1) >> 1);
                     const bool v0 = d + kd0 - 2 >= 0 && d + kd0 - 2 < P.D;
                     const bool v1 = nkd > 1 && d + kd0 - 1 >= 0 && d + kd0 - 1 < P.D;
-                    const uint32_t xb = sb + ws::K_DY_SLOT;
-                    for (int kk = 0; kk < nk; ++kk) {
-                        const uint64_t ad = ((uint64_t)hi_a << 32) | (((sb + kk * 1024) >> 4) | lbo_row);
-                        if (v0) mma_f16_ss(tmem, ad, ((uint64_t)hi_b << 32) | (((xb + 2 * kk * ws::X_COLS * 64) >> 4) | lbo_vox),
-                                           idesc, acc0);
-                        if (v1) mma_f16_ss(tmem + 160, ad,
-                                           ((uint64_t)hi_b << 32) | (((xb + ws::X_BYTES + 2 * kk * ws::X_COLS * 64) >> 4) | lbo_vox),
-                                           idesc, acc1);
-                        if (v0) acc0 = 1;
-                        if (v1) acc1 = 1;
+                    const uint32_t x0 = sb + ws::K_DY_SLOT, x1 = x0 + ws::X_BYTES;
+                    if (full_row && v0 && v1) {
+#pragma unroll
+                        for (int kk = 0; kk < 8; ++kk) {
+                            const uint32_t ad = ((sb + kk * 1024) >> 4) | lbo_row;
+                            WS_MMA(0, ad, WS_B(x0, kk), acc0);
+                            WS_MMA(160, ad, WS_B(x1, kk), acc1);
+                            acc0 = 1; acc1 = 1;
+                        }
+                    } else if (full_row && v0 && nkd == 1) {
+#pragma unroll
+                        for (int kk = 0; kk < 8; ++kk) {
+                            const uint32_t ad = ((sb + kk * 1024) >> 4) | lbo_row;
+                            WS_MMA(0, ad, WS_B(x0, kk), acc0);
+                            acc0 = 1;
+                        }
+                    } else {
+                        const int nk = full_row ? 8 : nk_last;
+#pragma unroll 1
+                        for (int kk = 0; kk < nk; ++kk) {
+                            const uint32_t ad = ((sb + kk * 1024) >> 4) | lbo_row;
+                            if (v0) { WS_MMA(0, ad, WS_B(x0, kk), acc0); acc0 = 1; }
+                            if (v1) { WS_MMA(160, ad, WS_B(x1, kk), acc1); acc1 = 1; }
+                        }
                     }
                 }
-                mma_commit(empty + 8 * st);
+                mma_commit_sel(empty + 8 * st, sel);
                 if (++st == (uint32_t)stages) { st = 0; ++use; }
+                if (++tw_c == P.tiles_w) { tw_c = 0; if (++th_c == tiles_h) { th_c = 0; ++td; } }
             }
-            mma_commit(done);
+#undef WS_MMA
+#undef WS_B
+            if (ok) mma_commit_sel(done, sel);
+            else if (lane == 0) atomicExch(P.error_flag, 22);
         }
     } else if (warp >= 4) {
         // ===================== epilogue: TMEM -> fp32 partial =====================

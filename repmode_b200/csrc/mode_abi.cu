@@ -72,12 +72,11 @@ int64_t wgrad_split_workspace_bytes(int N, int D, int H, int W, int Ci, int Co);
 int wgrad_split(const __half* x, const __half* dy, float* dw, int N, int D, int H, int W, int Ci, int Co,
                 float out_scale, const float* out_scale_dev, void* workspace, cudaStream_t st);
 
-// tcgen05 wgrad flavour behind impl = 2: the stacked-tap kernel; REPMODE_WGRAD_SPLIT=1 selects the split-tap kernel, which
-// issues 30 % fewer MMAs but is operand-feed bound today (measured r1d: 206 us against 144 us on the headline layer: its
-// tensor pipe idles 44 % of the time waiting for TMA bricks of 64-byte rows -- DESIGN.md section 5)
+// tcgen05 wgrad flavour behind impl = 2: the split-tap kernel (7 MMAs per K step; measured r1g 135 us against 146 us for
+// the stacked-tap kernel on the headline layer); REPMODE_WGRAD_STACKED=1 selects the stacked-tap kernel (10 MMAs per K step)
 static bool wgrad_use_split() {
-    static const bool split = getenv("REPMODE_WGRAD_SPLIT") != nullptr;
-    return split;
+    static const bool stacked = getenv("REPMODE_WGRAD_STACKED") != nullptr;
+    return !stacked;
 }
 
 }  // namespace mode
@@ -166,7 +165,7 @@ extern "C" int mode_conv3d_wgrad(const void* x, const void* dy, mode_dtype_t dty
         if (dtype != MODE_F16) MODE_FAIL("mode_conv3d_wgrad: the tcgen05 path takes fp16 operands");
         if (!wgrad_umma_supported(D, H, W, Ci, Co) || !wgrad_split_supported(D, H, W, Ci, Co))
             MODE_FAIL("mode_conv3d_wgrad: shape not supported by the tcgen05 path");
-        // 2: stacked-tap kernel (10 MMAs per K step) unless REPMODE_WGRAD_SPLIT; 3 / 5 force the stacked / the split-tap kernel
+        // 2: split-tap kernel (7 MMAs per K step) unless REPMODE_WGRAD_STACKED; 3 / 5 force the stacked / the split-tap kernel
         if (impl == 5 || (impl == 2 && wgrad_use_split()))
             return wgrad_split((const __half*)x, (const __half*)dy, d_weff, N, D, H, W, Ci, Co, out_scale, out_scale_dev, workspace, st);
         return wgrad_umma((const __half*)x, (const __half*)dy, d_weff, N, D, H, W, Ci, Co, out_scale, out_scale_dev, workspace, st);

@@ -385,11 +385,14 @@ static SplitPlan split_plan(int N, int D, int H, int W, int Ci, int Co) {
     auto nd = [&](int kd) { return (double)std::max(0, std::min(D, D + 2 - kd) - std::max(0, 2 - kd)); };
     const double cK2 = 0.5 * ((nd(0) + nd(1)) + (nd(2) + nd(3))) * stepsK;      // MMAs of one kd-pair group (average)
     const double cK1 = nd(4) * stepsK;
-    const double cL = 2.0 * D * stepsL;
+    // An L-unit MMA reads four DISTINCT dy planes as its A operand (no overlap between the M blocks, unlike the row-shifted
+    // views of the K units, which the operand fetch deduplicates): measured r1g 215k against 122k cycles for the same MMA
+    // count, i.e. ~1.7x the K units' 81 cycles per MMA.  Weight the L slabs accordingly.
+    const double cL = 1.7 * 2.0 * D * stepsL;
     SplitPlan p{1, 1, 1};
     while (2 * p.SK2 + p.SK1 + p.SL < slots) {
         const double a = cK2 / p.SK2, b = cK1 / p.SK1, c = cL / p.SL;
-        if (a >= b && a >= c) { if (2 * (p.SK2 + 1) + p.SK1 + p.SL > slots) break; ++p.SK2; }
+        if (a >= b && a >= c && 2 * (p.SK2 + 1) + p.SK1 + p.SL <= slots) ++p.SK2;     // a K2 group takes two CTAs per slab
         else if (c >= b) ++p.SL;
         else ++p.SK1;
     }

@@ -30,7 +30,7 @@ T = 12
 VOX = D * H * W
 FLOP_CONV = 2.0 * 125 * CI * CO * VOX            # one of fwd / dgrad / wgrad
 METRIC = "voxels/sec MoDE-conv fwd+bwd @32x128x128x32ch"
-TRAFFIC_FILES = ("r1e_traffic.json", "r1d_traffic.json", "r1b_traffic.json")   # newest ncu --set full capture of the
+TRAFFIC_FILES = ("r1_final_traffic.json", "r1e_traffic.json", "r1b_traffic.json")   # newest ncu --set full capture of the
 TRAFFIC_FILE = next((f for f in TRAFFIC_FILES                                    # same command (tools/ncu_summarise.py)
                      if os.path.exists(os.path.join(ROOT, "profiles", f))), TRAFFIC_FILES[-1])
 
@@ -304,7 +304,7 @@ def run_ours(args, rank, local_rank, world):
                           "ms_per_step": ms / args.steps, "profiling_run": True}), flush=True)
         return
     value = world * VOX * args.steps / (ms * 1e-3)
-    e2e = world * VOX * args.steps / (ms_e2e * 1e-3)
+    e2e = world * VOX * args.steps / (ms_e2e * 1e-3) if not fast else None       # profiling runs skip the e2e leg
 
     # ---- per-kernel roofline of the dominant kernels, timed alone with CUDA events on the launch stream
     hbm_gbs, tf_burst, tf_sust, peak_kind = peaks()
@@ -386,7 +386,8 @@ def run_ours(args, rank, local_rank, world):
                    "precision": Fm.default_precision(),
                    "launch": "forward+backward captured once as a CUDA graph and replayed" if use_graph else "eager"},
         "e2e": {"value": e2e, "unit": "voxels/s", "h2d_bytes_per_step": x_host.numel() * 4 * world,
-                "d2h_bytes_per_step": m.gate.bias.numel() * 4 * world, "ms_per_step": ms_e2e / args.steps,
+                "d2h_bytes_per_step": m.gate.bias.numel() * 4 * world,
+                "ms_per_step": ms_e2e / args.steps if not fast else None,
                 "api": "MoDEConv.forward(x from pinned NCDHW host memory, double-buffered H2D on a side stream) + "
                        "backward" + (" (CUDA-graph replay per input buffer)" if use_graph else "")
                        + ", gate.bias.grad.cpu() every step"},

@@ -385,10 +385,12 @@ static SplitPlan split_plan(int N, int D, int H, int W, int Ci, int Co) {
     auto nd = [&](int kd) { return (double)std::max(0, std::min(D, D + 2 - kd) - std::max(0, 2 - kd)); };
     const double cK2 = 0.5 * ((nd(0) + nd(1)) + (nd(2) + nd(3))) * stepsK;      // MMAs of one kd-pair group (average)
     const double cK1 = nd(4) * stepsK;
-    // An L-unit MMA reads four DISTINCT dy planes as its A operand (no overlap between the M blocks, unlike the row-shifted
-    // views of the K units, which the operand fetch deduplicates): measured r1g 215k against 122k cycles for the same MMA
-    // count, i.e. ~1.7x the K units' 81 cycles per MMA.  Weight the L slabs accordingly.
-    const double cL = 1.7 * 2.0 * D * stepsL;
+    // Slabs are weighted by MMA count alone.  Measured on the headline layer (ncu sm__cycles_active min / avg / max over the
+    // SMs): this plan (43 L + 84 K2 + 21 K1 CTAs) 123k / 167k / 215k cycles, 134 us (r1g); weighting the L slabs 1.7x
+    // (60 L + 70 K2 + 17 K1) 106k / 167k / 245k, 153 us (r1h) -- i.e. the L units are the FAST ones (~80 cycles per MMA,
+    // the tensor pipe's own rate) and the K units the slow ones (~115-140 cycles per MMA although the issue loop is no
+    // longer the limit).  Why the K units stall is the open question for this kernel.
+    const double cL = 2.0 * D * stepsL;
     SplitPlan p{1, 1, 1};
     while (2 * p.SK2 + p.SK1 + p.SL < slots) {
         const double a = cK2 / p.SK2, b = cK1 / p.SK1, c = cL / p.SL;

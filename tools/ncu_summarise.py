@@ -41,9 +41,11 @@ def launches(tag, out):
         agg.setdefault(short(r[ik]), []).append(us)
     total = sum(sum(v) for v in agg.values())
     with open(os.path.join(ROOT, "profiles", f"{out}_launch_summary.csv"), "w") as f:
-        f.write(f"# {out} ncu launch list summary (REPMODE_BENCH_FAST=1 REPMODE_BENCH_GRAPH=0 python bench.py --steps 2 --warmup 3);"
-                " cold-cache serialised times: compare SHARES, not absolutes\n")
-        f.write("# command: ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv python bench.py --steps 2 --warmup 3\n")
+        f.write(f"# {out} ncu launch list summary: the steps of bench.py only (REPMODE_BENCH_FAST=2: no e2e / CPU / per-kernel"
+                " legs; REPMODE_BENCH_GRAPH=0 REPMODE_OVERLAP=0: eager, one stream); cold-cache serialised times: compare"
+                " SHARES, not absolutes\n")
+        f.write("# command: ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv python bench.py --steps 3 --warmup 3"
+                "   (tools/gpu_round.sh)\n")
         f.write("kernel,launches,avg_us,total_ms,share_pct\n")
         for k, v in sorted(agg.items(), key=lambda kv: -sum(kv[1])):
             f.write(f"{k},{len(v)},{sum(v) / len(v):.2f},{sum(v) / 1e3:.3f},{100 * sum(v) / total:.1f}\n")
@@ -76,8 +78,9 @@ def full(tag, out):
             except ValueError:
                 pass
     with open(os.path.join(ROOT, "profiles", f"{out}_ncu_full_summary.csv"), "w") as f:
-        f.write(f"# {out}: ncu --set full --clock-control none --import-source on -k regex:<kernel> (REPMODE_BENCH_FAST=1 "
-                "REPMODE_BENCH_GRAPH=0 python bench.py --steps 2 --warmup 3); one row per captured launch\n")
+        f.write(f"# {out}: ncu --set full --clock-control none [--import-source on] -k regex:<kernel> -s <skip> -c <n> "
+                "(REPMODE_BENCH_FAST=2 REPMODE_BENCH_GRAPH=0 REPMODE_OVERLAP=0 python bench.py --steps 3 --warmup 3; "
+                "tools/gpu_round.sh); one row per captured launch\n")
         w = csv.writer(f)
         w.writerow(KEEP)
         w.writerow(units or [])

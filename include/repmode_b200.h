@@ -125,7 +125,8 @@ int mode_conv3d(const void* x, mode_dtype_t x_dtype, const void* w, const int32_
  * x [N,D,H,W,Ci], dy [N,D,H,W,Co] (same dtype), d_weff fp32 (overwritten).
  *   impl: 0 = auto, 1 = SIMT fp32, 2 = tcgen05 (fp16 operands, Ci % 32 == 0, Co % 32 == 0, W % 8 == 0; the
  *   split-tap kernel, 7 MMAs per K step), 3 = force the stacked-tap kernel (10 MMAs per K step), 5 = force the
- *   split-tap kernel.  workspace: mode_conv3d_wgrad_workspace_bytes(..., same impl) bytes, 16-byte aligned.
+ *   split-tap kernel, 6 = its experimental deep-tile variant.  workspace:
+ *   mode_conv3d_wgrad_workspace_bytes(..., same impl) bytes, 16-byte aligned.
  */
 int64_t mode_conv3d_wgrad_workspace_bytes(int32_t N, int32_t D, int32_t H, int32_t W, int32_t Ci, int32_t Co,
                                           int32_t impl);

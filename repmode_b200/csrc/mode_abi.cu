@@ -72,6 +72,16 @@ int64_t wgrad_split_workspace_bytes(int N, int D, int H, int W, int Ci, int Co);
 int wgrad_split(const __half* x, const __half* dy, float* dw, int N, int D, int H, int W, int Ci, int Co,
                 float out_scale, const float* out_scale_dev, void* workspace, cudaStream_t st);
 
+// wgrad_deep.cu (experimental)
+bool wgrad_deep_supported(int D, int H, int W, int Ci, int Co);
+int64_t wgrad_deep_workspace_bytes(int N, int D, int H, int W, int Ci, int Co);
+int wgrad_deep(const __half* x, const __half* dy, float* dw, int N, int D, int H, int W, int Ci, int Co,
+               float out_scale, const float* out_scale_dev, void* workspace, cudaStream_t st);
+static bool wgrad_use_deep() {
+    static const bool deep = getenv("REPMODE_WGRAD_DEEP") != nullptr;
+    return deep;
+}
+
 // tcgen05 wgrad flavour behind impl = 2: the split-tap kernel (7 MMAs per K step; measured r1g 135 us against 146 us for
 // the stacked-tap kernel on the headline layer); REPMODE_WGRAD_STACKED=1 selects the stacked-tap kernel (10 MMAs per K step)
 static bool wgrad_use_split() {
@@ -145,6 +155,7 @@ extern "C" int mode_conv3d(const void* x, mode_dtype_t x_dtype, const void* w, c
 
 extern "C" int64_t mode_conv3d_wgrad_workspace_bytes(int32_t N, int32_t D, int32_t H, int32_t W, int32_t Ci, int32_t Co,
                                                      int32_t impl) {
+    if (impl == 6 || (impl == 2 && wgrad_use_deep())) return wgrad_deep_workspace_bytes(N, D, H, W, Ci, Co);
     if (impl == 5 || (impl == 2 && wgrad_use_split())) return wgrad_split_workspace_bytes(N, D, H, W, Ci, Co);
     if (impl == 2 || impl == 3) return wgrad_umma_workspace_bytes(N, D, H, W, Ci, Co);
     return 0;
@@ -161,11 +172,13 @@ extern "C" int mode_conv3d_wgrad(const void* x, const void* dy, mode_dtype_t dty
         if (dtype != MODE_F32) MODE_FAIL("mode_conv3d_wgrad: the SIMT path takes fp32 operands");
         return wgrad_simt((const float*)x, (const float*)dy, d_weff, N, D, H, W, Ci, Co, out_scale, out_scale_dev, st);
     }
-    if (impl == 2 || impl == 3 || impl == 5) {
+    if (impl == 2 || impl == 3 || impl == 5 || impl == 6) {
         if (dtype != MODE_F16) MODE_FAIL("mode_conv3d_wgrad: the tcgen05 path takes fp16 operands");
         if (!wgrad_umma_supported(D, H, W, Ci, Co) || !wgrad_split_supported(D, H, W, Ci, Co))
             MODE_FAIL("mode_conv3d_wgrad: shape not supported by the tcgen05 path");
         // 2: split-tap kernel (7 MMAs per K step) unless REPMODE_WGRAD_STACKED; 3 / 5 force the stacked / the split-tap kernel
+        if (impl == 6 || (impl == 2 && wgrad_use_deep()))      // experimental deep-tile variant (REPMODE_WGRAD_DEEP=1)
+            return wgrad_deep((const __half*)x, (const __half*)dy, d_weff, N, D, H, W, Ci, Co, out_scale, out_scale_dev, workspace, st);
         if (impl == 5 || (impl == 2 && wgrad_use_split()))
             return wgrad_split((const __half*)x, (const __half*)dy, d_weff, N, D, H, W, Ci, Co, out_scale, out_scale_dev, workspace, st);
         return wgrad_umma((const __half*)x, (const __half*)dy, d_weff, N, D, H, W, Ci, Co, out_scale, out_scale_dev, workspace, st);

@@ -11,7 +11,7 @@ import threading
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 SO_PATH = os.path.join(HERE, "librepmode_b200.so")
-SOURCES = ["mode_abi.cu", "reparam.cu", "conv_simt.cu", "bn.cu", "conv_umma.cu", "conv_pair.cu", "wgrad_umma.cu", "wgrad_split.cu"]
+SOURCES = ["mode_abi.cu", "reparam.cu", "conv_simt.cu", "bn.cu", "conv_umma.cu", "conv_pair.cu", "wgrad_umma.cu", "wgrad_split.cu", "wgrad_deep.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-shared",
               "-Xcompiler", "-fPIC"]
 
@@ -19,6 +19,7 @@ MODE_F32, MODE_F16 = 0, 1
 IMPL_AUTO, IMPL_SIMT, IMPL_UMMA = 0, 1, 2
 IMPL_UMMA_SINGLE, IMPL_UMMA_PAIR = 3, 4     # force the single-CTA / the CTA-pair (cta_group::2) tcgen05 kernel
 IMPL_WGRAD_STACKED, IMPL_WGRAD_SPLIT = 3, 5  # mode_conv3d_wgrad: force wgrad_umma.cu (10 MMAs per K step) / wgrad_split.cu (7)
+IMPL_WGRAD_DEEP = 6                          # experimental deep-tile variant of the split kernel (wgrad_deep.cu)
 
 _lock = threading.Lock()
 _lib = None

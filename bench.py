@@ -192,7 +192,9 @@ def run_ours(args, rank, local_rank, world):
             xin.grad = None
             self.graph = torch.cuda.CUDAGraph()
             l0 = lib.mode_launch_count()
-            with torch.cuda.graph(self.graph):
+            # with NCCL initialised its watchdog thread polls events while we capture: only this thread's calls are policed
+            mode = {"capture_error_mode": "thread_local"} if world > 1 else {}
+            with torch.cuda.graph(self.graph, **mode):
                 y = m(xin, task)
                 y.backward(dout)
             self.launches = lib.mode_launch_count() - l0        # kernels of this library inside one replay
@@ -205,7 +207,24 @@ def run_ours(args, rank, local_rank, world):
                 p.grad = gr
 
     use_graph = os.environ.get("REPMODE_BENCH_GRAPH", "1") == "1"
-    gs_res = GraphStep(x_dev) if use_graph else None
+    graph_note = ""
+
+    def make_graph_step(xin):
+        """GraphStep, or None (eager launches) when the capture is refused -- never a silent change of the work done."""
+        nonlocal use_graph, graph_note
+        if not use_graph:
+            return None
+        try:
+            return GraphStep(xin)
+        except Exception as e:  # noqa: BLE001
+            use_graph = False
+            graph_note = f" (CUDA-graph capture failed, eager launches: {type(e).__name__}: {str(e)[:120]})"
+            torch.cuda.synchronize()
+            for p in params:
+                p.grad = None
+            return None
+
+    gs_res = make_graph_step(x_dev)
 
     def step_resident():
         if gs_res is not None:
@@ -224,7 +243,9 @@ def run_ours(args, rank, local_rank, world):
     ev_used = [torch.cuda.Event(), torch.cuda.Event()]
     fast_level = int(os.environ.get("REPMODE_BENCH_FAST", "0"))  # profiling runs (ncu): 1 = skip the e2e and CPU legs,
     fast = fast_level >= 1                                       # 2 = also skip the per-kernel roofline timings
-    gs_e2e = [GraphStep(b) for b in xbuf] if (use_graph and not fast) else None
+    gs_e2e = [make_graph_step(b) for b in xbuf] if (use_graph and not fast) else None
+    if gs_e2e is not None and any(g_ is None for g_ in gs_e2e):
+        gs_e2e = None
 
     def issue_copy(i):
         b = i & 1
@@ -384,7 +405,8 @@ def run_ours(args, rank, local_rank, world):
                    "layout": "NDHWC (channels_last_3d) resident", "parallelism": f"dp{world}",
                    "l2": "per-step working set ~0.5 GB > 126 MB L2 (inputs larger than L2, no explicit flush)",
                    "precision": Fm.default_precision(),
-                   "launch": "forward+backward captured once as a CUDA graph and replayed" if use_graph else "eager"},
+                   "launch": ("forward+backward captured once as a CUDA graph and replayed" if use_graph else "eager")
+                   + graph_note},
         "e2e": {"value": e2e, "unit": "voxels/s", "h2d_bytes_per_step": x_host.numel() * 4 * world,
                 "d2h_bytes_per_step": m.gate.bias.numel() * 4 * world,
                 "ms_per_step": ms_e2e / args.steps if not fast else None,

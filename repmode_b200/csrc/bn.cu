@@ -5,6 +5,8 @@
 // All kernels are HBM-bound streaming passes: float4 accesses, channel index = element index mod C
 // (C is a multiple of 4 on every layer that has a BN; the scalar path covers the rest), grid sized to
 // a multiple of the SM count, per-thread fp32 partials folded into fp64 block/global sums.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace mode {
@@ -519,7 +521,12 @@ extern "C" int mode_bn_relu_bwd_reduce(const float* y, const float* dout, int64_
     const bool aligned = ((reinterpret_cast<uintptr_t>(y) | reinterpret_cast<uintptr_t>(dout)) & 15) == 0;
     if ((C & 3) == 0 && vpr <= BN_THREADS && BN_THREADS % vpr == 0 && aligned) {
         const int rpi = BN_THREADS / vpr;
-        const int grid = stream_grid(M, rpi * 16);
+        int grid = stream_grid(M, rpi * 16);
+        // A/B knob for the next measurement round: blocks per SM of the reduce pass.  Today's heuristic launches 6 short
+        // blocks per SM (3 waves at 2 resident), each ending in 2*C fp64 atomics on the same addresses; the pass runs at
+        // 3.6 TB/s while the apply pass over the same tensors reaches 5.4 (profiles/r1_final_ncu_full_summary.csv).
+        static const int bps = getenv("REPMODE_BN_REDUCE_BPS") ? atoi(getenv("REPMODE_BN_REDUCE_BPS")) : 0;
+        if (bps > 0) grid = (int)min((int64_t)grid, (int64_t)sm_count() * bps);
         if (planes)
             bn_bwd_reduce_vec_kernel<true><<<grid, BN_THREADS, 0, st>>>(y, dout, M, C, gamma, beta, mean, invstd,
                                                                         workspace, mx, to_planes(planes));

@@ -10,6 +10,8 @@
 // HBM-bound kernels: every global access is a contiguous >=64-byte segment per warp, experts are read
 // exactly once per distinct gate input, and the mixing arithmetic is done in fp32 in the reference's
 // own association order so the fp32 output is bit-identical up to the softmax's exp().
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace mode {
@@ -116,6 +118,97 @@ __global__ void __launch_bounds__(256) reparam_fwd_kernel(mode_layer_t L, const 
     const int nci = gridDim.y;
     for (int tl = warp; tl < 25; tl += 8) {
         store_w(w_fwd + pack_index<OutT>(u, kds * 25 + tl, ic, nci, o, rows_pad, lane), sw[lane * 25 + tl] * w_scale);
+    }
+}
+
+// K1 for WIDE layers -- EXPERIMENTAL (REPMODE_K1_WIDE=1; not yet run on a GPU, written after round 1's GPU budget was spent).
+// reparam_fwd_kernel above moves 4.8 KB per block through three barrier phases: on 512 -> 512 (40 960 blocks) it is
+// latency-bound at 1.14 TB/s = 17 % of HBM (profiles/r1h_bench.json).  Here one block owns RB = 4 output channels x one
+// 32-channel chunk x ALL 125 taps: the four [32 ci][125] expert slabs are contiguous 16 KB runs (read with plain
+// coalesced loads into shared memory), the mix is done in place with the SAME expressions and association order as
+// above (bit-identical W_eff), and the pack is written in 256-byte (fp16) / 512-byte (fp32) contiguous runs: 4 rows x
+// 32 columns per (chunk, tap).  78 KB of shared memory per block: two to three blocks per SM overlap load and store.
+// grid (Co / 4, Ci / 32, U), block 256.
+constexpr int K1W_RB = 4;
+template <typename OutT>
+__global__ void __launch_bounds__(256) reparam_fwd_wide_kernel(mode_layer_t L, const int32_t* __restrict__ task_ids,
+                                                               const float* __restrict__ t_dense,
+                                                               float* __restrict__ g_out, OutT* __restrict__ w_fwd,
+                                                               float w_scale, const float* __restrict__ w_scale_dev,
+                                                               int rows_pad) {
+    extern __shared__ float k1w_smem[];
+    float* s5 = k1w_smem;                               // [RB][32][125]
+    float* s3 = s5 + K1W_RB * 32 * 125;                 // [RB][32][27]
+    float* s1 = s3 + K1W_RB * 32 * 27;                  // [3][RB][32]: k1, a3, a5
+    float* sg = s1 + 3 * K1W_RB * 32;                   // [RB][5]
+    const int o0 = blockIdx.x * K1W_RB, ic = blockIdx.y, u = blockIdx.z;
+    const int Ci = L.ci, Co = L.co, T = L.num_tasks;
+    const int tid = threadIdx.x;
+
+    // gate column + bias -> softmax over the 5 experts, one thread per output channel (RepMode.py:198-200)
+    if (tid < K1W_RB) {
+        const int o = o0 + tid;
+        float lg[MODE_NUM_EXPERTS];
+        for (int e = 0; e < MODE_NUM_EXPERTS; ++e) {
+            const int row = e * Co + o;
+            if (task_ids != nullptr) {
+                lg[e] = __fadd_rn(L.gate_w[(size_t)row * T + task_ids[u]], L.gate_b[row]);
+            } else {
+                float acc = 0.f;
+                for (int t = 0; t < T; ++t) acc = fmaf(t_dense[(size_t)u * T + t], L.gate_w[(size_t)row * T + t], acc);
+                lg[e] = acc + L.gate_b[row];
+            }
+        }
+        float m = lg[0];
+        for (int e = 1; e < MODE_NUM_EXPERTS; ++e) m = fmaxf(m, lg[e]);
+        float ex[MODE_NUM_EXPERTS], ssum = 0.f;
+        for (int e = 0; e < MODE_NUM_EXPERTS; ++e) { ex[e] = expf(lg[e] - m); ssum += ex[e]; }
+        for (int e = 0; e < MODE_NUM_EXPERTS; ++e) {
+            const float gv = ex[e] / ssum;
+            sg[tid * MODE_NUM_EXPERTS + e] = gv;
+            if (ic == 0 && g_out != nullptr) g_out[((size_t)u * MODE_NUM_EXPERTS + e) * Co + o] = gv;
+        }
+    }
+    // expert slabs of this (4 rows, 32-channel chunk): contiguous runs per row
+    for (int r = 0; r < K1W_RB; ++r) {
+        const size_t oc0 = (size_t)(o0 + r) * Ci + (size_t)ic * 32;
+        const float* src5 = L.k5 + oc0 * 125;
+        for (int idx = tid; idx < 32 * 125; idx += 256) s5[r * 32 * 125 + idx] = src5[idx];
+        const float* src3 = L.k3 + oc0 * 27;
+        for (int idx = tid; idx < 32 * 27; idx += 256) s3[r * 32 * 27 + idx] = src3[idx];
+        if (tid < 32) {
+            s1[(0 * K1W_RB + r) * 32 + tid] = L.k1[oc0 + tid];
+            s1[(1 * K1W_RB + r) * 32 + tid] = L.a3[oc0 + tid];
+            s1[(2 * K1W_RB + r) * 32 + tid] = L.a5[oc0 + tid];
+        }
+    }
+    __syncthreads();
+    if (w_scale_dev != nullptr) w_scale *= *w_scale_dev;
+    const float c3 = 1.0f / 27, c5 = 1.0f / 125;               // fp32-rounded pool constants (RepMode.py:161-163)
+    // mix in place: s5[r][i][tap] <- W_eff
+    for (int idx = tid; idx < K1W_RB * 32 * 125; idx += 256) {
+        const int r = idx / (32 * 125), rem = idx - r * (32 * 125);
+        const int i = rem / 125, tap = rem - i * 125;
+        const float* g = sg + r * MODE_NUM_EXPERTS;
+        const int kd = tap / 25, kh = (tap / 5) % 5, kw = tap % 5;
+        const bool inner = (kd >= 1 && kd <= 3 && kh >= 1 && kh <= 3 && kw >= 1 && kw <= 3);
+        const float t0 = __fmul_rn(s5[idx], g[0]);
+        float t1 = 0.f, t2 = 0.f, t3 = 0.f;
+        if (inner) {
+            t1 = __fmul_rn(s3[(r * 32 + i) * 27 + ((kd - 1) * 3 + (kh - 1)) * 3 + (kw - 1)], g[1]);
+            t3 = __fmul_rn(__fmul_rn(s1[(1 * K1W_RB + r) * 32 + i], c3), g[3]);
+        }
+        if (tap == 62) t2 = __fmul_rn(s1[(0 * K1W_RB + r) * 32 + i], g[2]);
+        const float t4 = __fmul_rn(__fmul_rn(s1[(2 * K1W_RB + r) * 32 + i], c5), g[4]);
+        // reference association order: ((((e5 + e3) + e1) + ea3) + ea5)   (RepMode.py:184-188)
+        s5[idx] = __fadd_rn(__fadd_rn(__fadd_rn(__fadd_rn(t0, t1), t2), t3), t4);
+    }
+    __syncthreads();
+    // pack: thread -> (tap, row, column); 4 rows x 32 columns of one (chunk, tap) are one contiguous run of the pack
+    const int nci = gridDim.y;
+    for (int idx = tid; idx < 125 * K1W_RB * 32; idx += 256) {
+        const int col = idx & 31, r = (idx >> 5) % K1W_RB, tap = idx / (32 * K1W_RB);
+        store_w(w_fwd + pack_index<OutT>(u, tap, ic, nci, o0 + r, rows_pad, col), s5[(r * 32 + col) * 125 + tap] * w_scale);
     }
 }
 
@@ -324,9 +417,22 @@ extern "C" int mode_reparam_fwd(const mode_layer_t* L, const int32_t* task_ids, 
     cudaStream_t st = (cudaStream_t)stream;
     const int nci = (int)ceil_div(L->ci, 32), nco = (int)ceil_div(L->co, 32);
     dim3 grid(L->co, nci, U * 5);
+    // experimental wide-layer kernel (REPMODE_K1_WIDE=1): whole 32-channel chunks, 4 output channels per block
+    const char* wide_env = getenv("REPMODE_K1_WIDE");          // read per call so that a test can A/B both kernels
+    const bool wide_on = wide_env != nullptr && wide_env[0] == '1';
+    const bool wide = wide_on && L->ci % 32 == 0 && L->co % K1W_RB == 0 && (int64_t)L->ci * L->co >= 128 * 128 &&
+                      U <= 65535;
+    const int wide_smem = (K1W_RB * 32 * (125 + 27 + 3) + K1W_RB * MODE_NUM_EXPERTS) * (int)sizeof(float);
+    const dim3 wgrid(L->co / K1W_RB, nci, U);
     if (w_dtype == MODE_F32) {
-        reparam_fwd_kernel<float><<<grid, 256, 0, st>>>(*L, task_ids, t_dense, g_out, (float*)w_fwd, w_scale,
-                                                        w_scale_dev, L->co);
+        if (wide) {
+            MODE_CUDA(cudaFuncSetAttribute(reparam_fwd_wide_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, wide_smem));
+            reparam_fwd_wide_kernel<float><<<wgrid, 256, wide_smem, st>>>(*L, task_ids, t_dense, g_out, (float*)w_fwd,
+                                                                          w_scale, w_scale_dev, L->co);
+        } else {
+            reparam_fwd_kernel<float><<<grid, 256, 0, st>>>(*L, task_ids, t_dense, g_out, (float*)w_fwd, w_scale,
+                                                            w_scale_dev, L->co);
+        }
         MODE_LAUNCH_CHECK();
         if (w_dgrad) {
             pack_dgrad_kernel<float><<<dim3(nci, nco, U * 125), dim3(32, 8), 0, st>>>((const float*)w_fwd,
@@ -335,8 +441,14 @@ extern "C" int mode_reparam_fwd(const mode_layer_t* L, const int32_t* task_ids, 
             MODE_LAUNCH_CHECK();
         }
     } else if (w_dtype == MODE_F16) {
-        reparam_fwd_kernel<__half><<<grid, 256, 0, st>>>(*L, task_ids, t_dense, g_out, (__half*)w_fwd, w_scale,
-                                                         w_scale_dev, nco * 32);
+        if (wide) {
+            MODE_CUDA(cudaFuncSetAttribute(reparam_fwd_wide_kernel<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, wide_smem));
+            reparam_fwd_wide_kernel<__half><<<wgrid, 256, wide_smem, st>>>(*L, task_ids, t_dense, g_out, (__half*)w_fwd,
+                                                                           w_scale, w_scale_dev, nco * 32);
+        } else {
+            reparam_fwd_kernel<__half><<<grid, 256, 0, st>>>(*L, task_ids, t_dense, g_out, (__half*)w_fwd, w_scale,
+                                                             w_scale_dev, nco * 32);
+        }
         MODE_LAUNCH_CHECK();
         if (w_dgrad) {
             pack_dgrad_kernel<__half><<<dim3(nci, nco, U * 125), dim3(32, 8), 0, st>>>((const __half*)w_fwd,

@@ -1,6 +1,8 @@
 """GPU parity tests proper: the CUDA path (through the C ABI) against the golden vectors frozen from the
 live reference and against the oracle on seeded inputs.  Tolerances: fp32 SIMT path 1e-4 (re-association
 only); tensor-core path (fp16 operands, fp32 accumulate) 1e-3 = the north-star bound."""
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -130,3 +132,24 @@ def test_eval_weight_cache_matches_uncached_and_invalidates(precision, monkeypat
         monkeypatch.setattr(Fm, "EVAL_CACHE", False)
         assert not torch.equal(before, after)
         assert torch.equal(after, m(x, ids))
+
+
+@pytest.mark.skipif(os.environ.get("REPMODE_TEST_EXPERIMENTAL", "0") != "1",
+                    reason="reparam_fwd_wide_kernel is experimental: set REPMODE_TEST_EXPERIMENTAL=1")
+@pytest.mark.parametrize("dtype_name", ["f32", "f16"])
+def test_reparam_wide_kernel_bit_identical(dtype_name, monkeypatch):
+    """K1 for wide layers (REPMODE_K1_WIDE=1: 4 output channels x a whole 32-channel chunk per block) writes the same
+    bits as the per-(o, kd slice) kernel: same expressions, same association order, same pack."""
+    from repmode_b200 import functional as Fm, lib as L
+    from repmode_b200.nn_modules import MoDEConv
+    torch.manual_seed(5)
+    m = MoDEConv(5, 12, 128, 160).cuda()
+    layer, ci, co = Fm._layer(*m._params())
+    ids = torch.tensor([3, 7, 3], device="cuda", dtype=torch.int32)
+    dtype = L.MODE_F32 if dtype_name == "f32" else L.MODE_F16
+    scale = 1.0 if dtype_name == "f32" else Fm.W_SCALE_F16
+    monkeypatch.setenv("REPMODE_K1_WIDE", "0")
+    g0, w0, d0 = Fm.reparam_fwd(layer, ids, 3, ci, co, dtype, True, scale)
+    monkeypatch.setenv("REPMODE_K1_WIDE", "1")
+    g1, w1, d1 = Fm.reparam_fwd(layer, ids, 3, ci, co, dtype, True, scale)
+    assert torch.equal(g0, g1) and torch.equal(w0, w1) and torch.equal(d0, d1)

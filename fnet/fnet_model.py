@@ -57,10 +57,12 @@ class Model(object):
         self.optimizer = torch.optim.Adam(self.net.parameters(), lr=self.lr)
 
     # ------------------------------------------------------------------ checkpointing
+    _PLAIN_STATE = ("nn_module", "opts", "count_iter", "count_epoch")      # copied as they are; the two state_dicts follow
+
     def get_state(self):
-        return dict(nn_module=self.nn_module, opts=self.opts, nn_state=self.net.state_dict(),
-                    optimizer_state=self.optimizer.state_dict(), count_iter=self.count_iter,
-                    count_epoch=self.count_epoch)
+        state = {key: getattr(self, key) for key in self._PLAIN_STATE}
+        state.update(nn_state=self.net.state_dict(), optimizer_state=self.optimizer.state_dict())
+        return state
 
     def to_gpu(self, gpu_ids):
         self.gpu_ids = _as_list(gpu_ids)
@@ -69,24 +71,25 @@ class Model(object):
         _set_gpu_recursive(self.optimizer.state, self.gpu_ids[0])
 
     def save_state(self, path_save):
-        keep = self.gpu_ids
-        d = os.path.dirname(path_save)
-        if d and not os.path.exists(d):
-            os.makedirs(d)
+        """Checkpoints are written from the CPU copy of the network and optimizer state, then everything moves back."""
+        home = self.gpu_ids
+        os.makedirs(os.path.dirname(path_save) or ".", exist_ok=True)
         self.to_gpu(-1)
-        torch.save(self.get_state(), path_save)
-        self.to_gpu(keep)
+        try:
+            torch.save(self.get_state(), path_save)
+        finally:
+            self.to_gpu(home)
 
     def load_state(self, path_load, gpu_ids=-1):
-        state = torch.load(path_load, weights_only=False)
-        self.nn_module = state["nn_module"]
-        self.opts = state["opts"]
-        self.opts.gpu_ids = gpu_ids
-        self._init_model()
+        state = torch.load(path_load, weights_only=False)      # the checkpoint pickles an argparse.Namespace
+        state["opts"].gpu_ids = gpu_ids
+        for key in ("nn_module", "opts"):
+            setattr(self, key, state[key])
+        self._init_model()                                     # rebuilds net + optimizer from nn_module / opts
         self.net.load_state_dict(state["nn_state"])
         self.optimizer.load_state_dict(state["optimizer_state"])
-        self.count_iter = state["count_iter"]
-        self.count_epoch = state["count_epoch"]
+        for key in ("count_iter", "count_epoch"):
+            setattr(self, key, state[key])
         self.to_gpu(gpu_ids)
 
     # ------------------------------------------------------------------ training / evaluation
@@ -115,11 +118,10 @@ class Model(object):
 
     def do_eval_iter(self, signal, target, task, info):
         pred = self.predict(signal, task, self.patch_size)
-        _, stats = get_metric_stats(pred, target)
-        frame = pd.DataFrame([stats])
-        frame.insert(loc=0, column="dataset", value=info["dataset"])
-        frame.insert(loc=1, column="path_czi", value=info["path_czi"])
-        return pred, frame
+        stats = get_metric_stats(pred, target)[1]
+        row = {"dataset": info["dataset"], "path_czi": info["path_czi"]}
+        row.update(stats)                                      # identification columns first, then the metrics
+        return pred, pd.DataFrame([row])
 
     def predict(self, signal, task, patch_size):
         """Sliding-window inference: overlapping patches (stride = half a patch, last patch clamped to the border),
@@ -155,7 +157,8 @@ class Model(object):
         return (pred_sum / weight_sum).cpu()
 
     def __str__(self):
-        return "Network:\n{}\nLoss:\n{}\nOptimizer:\n{}\n".format(self.nn_module, self.criterion, self.optimizer)
+        parts = (("Network", self.nn_module), ("Loss", self.criterion), ("Optimizer", self.optimizer))
+        return "".join(f"{name}:\n{value}\n" for name, value in parts)
 
 
 def get_gaussian(patch_size, sigma_scale=1 / 8):
@@ -171,9 +174,13 @@ def get_gaussian(patch_size, sigma_scale=1 / 8):
 
 
 def _set_gpu_recursive(var, gpu_id):
-    """Move every tensor nested in dict `var` (optimizer state) to cuda:gpu_id, or to the CPU for -1."""
-    for key in var:
-        if isinstance(var[key], dict):
-            _set_gpu_recursive(var[key], gpu_id)
-        elif torch.is_tensor(var[key]):
-            var[key] = var[key].cpu() if gpu_id == -1 else var[key].cuda(gpu_id)
+    """Move every tensor nested in dict `var` (optimizer state) to cuda:gpu_id, or to the CPU for -1.  In place."""
+    target = torch.device("cpu") if gpu_id == -1 else torch.device("cuda", gpu_id)
+    pending = [var]
+    while pending:
+        node = pending.pop()
+        for key, value in node.items():
+            if isinstance(value, dict):
+                pending.append(value)
+            elif torch.is_tensor(value):
+                node[key] = value.to(target)

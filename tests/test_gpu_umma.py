@@ -173,3 +173,49 @@ def test_wgrad_umma_bitexact(shape, impl):
         ref = ref.reshape(n, co, ci, 125).transpose(0, 3, 1, 2)            # [n][tap][o][i]
         assert np.array_equal(dw_simt.cpu().numpy(), ref)
     assert torch.equal(dw_umma, dw_simt)
+
+
+def test_headline_layer_full_size_bitexact_and_adjoint():
+    """BASELINE.json's metric shape -- 32 -> 32 channels on a 1x32x128x128 volume -- through exactly the kernels bench.py
+    times (the launcher's own choices: CTA-pair conv for forward and dgrad, the default tcgen05 wgrad with its one-wave
+    slab plan): bit-identical to the fp32 SIMT kernels on integer-valued data, and the size-independent adjoint
+    identities of a convolution hold EXACTLY between the three kernels:
+        <conv(x, W), r> = <x, dgrad(r, W)> = <wgrad(x, r), W>."""
+    from repmode_b200 import functional as Fm, lib as L
+    n, d, h, w, ci, co = 1, 32, 128, 128, 32, 32
+    rng = np.random.RandomState(2024)
+    x = rng.randint(-3, 4, size=(n, d, h, w, ci)).astype(np.float32)
+    r = rng.randint(-3, 4, size=(n, d, h, w, co)).astype(np.float32)
+    weff = (rng.randint(-4, 5, size=(n, co, ci, 5, 5, 5)) / 8.0).astype(np.float32)
+    su = torch.zeros(n, dtype=torch.int32, device="cuda")
+    xg, rg = torch.from_numpy(x).cuda(), torch.from_numpy(r).cuda()
+    x16, r16 = xg.half(), rg.half()
+
+    # forward: |y| <= 4000 * 1.5 in steps of 1/8 -> every partial sum is exact in fp32 in any order
+    w32 = torch.from_numpy(pack_weights(weff, half=False)).cuda()
+    w16 = torch.from_numpy(pack_weights(weff, half=True)).cuda()
+    y_simt = Fm.conv3d(xg, L.MODE_F32, w32, su, n, d, h, w, ci, co, None, None, impl=L.IMPL_SIMT)
+    y_auto = Fm.conv3d(x16, L.MODE_F16, w16, su, n, d, h, w, ci, co, None, None, impl=L.IMPL_UMMA)
+    _poll()
+    assert torch.equal(y_auto, y_simt)
+
+    # dgrad = the same kernel on the flipped / transposed pack
+    wd32 = torch.from_numpy(pack_weights(weff, half=False, dgrad=True)).cuda()
+    wd16 = torch.from_numpy(pack_weights(weff, half=True, dgrad=True)).cuda()
+    dx_simt = Fm.conv3d(rg, L.MODE_F32, wd32, su, n, d, h, w, co, ci, None, None, impl=L.IMPL_SIMT)
+    dx_auto = Fm.conv3d(r16, L.MODE_F16, wd16, su, n, d, h, w, co, ci, None, None, impl=L.IMPL_UMMA)
+    _poll()
+    assert torch.equal(dx_auto, dx_simt)
+
+    # wgrad: |sum| <= 9 * 524288 < 2^24 -> exact
+    dw_simt = Fm.conv3d_wgrad(xg, rg, L.MODE_F32, n, d, h, w, ci, co, None, impl=L.IMPL_SIMT)
+    dw_auto = Fm.conv3d_wgrad(x16, r16, L.MODE_F16, n, d, h, w, ci, co, None)
+    _poll()
+    assert torch.equal(dw_auto, dw_simt)
+
+    # adjoint identities in fp64 (all terms are multiples of 1/8 far below 2^53: exact)
+    a = float((y_auto.double() * rg.double()).sum())
+    b = float((xg.double() * dx_auto.double()).sum())
+    w_tap = torch.from_numpy(weff.reshape(n, co, ci, 125).transpose(0, 3, 1, 2).copy()).cuda()    # [n][tap][o][i]
+    c = float((dw_auto.double() * w_tap.double()).sum())
+    assert a == b == c, (a, b, c)

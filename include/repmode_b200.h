@@ -120,6 +120,29 @@ int mode_conv3d(const void* x, mode_dtype_t x_dtype, const void* w, const int32_
                 const float* out_scale_dev, double* bn_sums, int32_t stat_d_lo, int32_t stat_d_hi, int32_t impl,
                 void* stream);
 
+/* Extended form of mode_conv3d (mode_conv3d == mode_conv3d_ex with opts = NULL).  Two things the plain call cannot say:
+ *   (1) a HALOED input (D-sharded slabs): x has Dx >= D planes and output plane q is centred on
+ *       input plane q + x_off, y[q] = sum_kd w[kd] * x[q + x_off + kd - 2]; input planes outside [0, Dx) are zero (the conv's
+ *       padding at the GLOBAL faces).  Only the D owned output planes are computed -- no redundant halo-plane outputs.
+ *       Requires x_off >= 0 and x_off + D <= Dx.
+ *   (2) a fused epilogue: y = relu?(acc * out_scale * ep_scale[c] + ep_shift[c]) -- eval-mode BatchNorm3d + ReLU
+ *       (RepMode.py:209-212) folded into K2 so y is written once and never re-read -- and/or an fp16 copy of the result
+ *       (times y16_scale, saturated to +-65504) written into plane y16_off.. of a [N,Dy16,H,W,Nout] buffer: the next
+ *       conv's operand, halo planes left for the exchange.  y may be NULL when y16 is given. */
+typedef struct {
+    int32_t Dx, x_off;              /* 0, 0 = no halo (Dx = D) */
+    const float* ep_scale;          /* [Nout] or NULL */
+    const float* ep_shift;          /* [Nout] or NULL */
+    int32_t relu;
+    void* y16;                      /* fp16 result copy or NULL */
+    int32_t Dy16, y16_off;          /* planes of the y16 buffer (0 = D) and the plane output plane 0 lands in */
+    float y16_scale;                /* 0 = 1 */
+} mode_conv_opts_t;
+int mode_conv3d_ex(const void* x, mode_dtype_t x_dtype, const void* w, const int32_t* sample_u, float* y,
+                   int32_t N, int32_t D, int32_t H, int32_t W, int32_t K, int32_t Nout, float out_scale,
+                   const float* out_scale_dev, double* bn_sums, int32_t stat_d_lo, int32_t stat_d_hi, int32_t impl,
+                   const mode_conv_opts_t* opts_host, void* stream);
+
 /* ---- K4: wgrad ------------------------------------------------------------------------------------------
  * d_weff[n][tap][o][i] = out_scale * sum_p dy[n][p][o] * x[n][p + tap - 2][i]   (autograd of RepMode.py:207).
  * x [N,D,H,W,Ci], dy [N,D,H,W,Co] (same dtype), d_weff fp32 (overwritten).
@@ -133,6 +156,14 @@ int64_t mode_conv3d_wgrad_workspace_bytes(int32_t N, int32_t D, int32_t H, int32
 int mode_conv3d_wgrad(const void* x, const void* dy, mode_dtype_t dtype, float* d_weff, int32_t N, int32_t D,
                       int32_t H, int32_t W, int32_t Ci, int32_t Co, float out_scale, const float* out_scale_dev,
                       void* workspace, int32_t impl, void* stream);
+
+/* Haloed form (D-sharded slabs): dy holds the D OWNED planes, x has Dx planes and dy plane p is centred on x plane p + x_off:
+ *   d_weff[n][tap][o][i] = out_scale * sum_{p in [0,D)} dy[n][p][o] * x[n][p + x_off + kd - 2][..]; x planes outside [0, Dx)
+ * are zero.  Every rank then holds the partial gradient of its own planes; the caller sums them (gradient all-reduce).
+ * Dx = 0 means Dx = D, x_off = 0.  tcgen05: the deep-tile kernel only (impl 0 / 2 / 6). */
+int mode_conv3d_wgrad_ex(const void* x, const void* dy, mode_dtype_t dtype, float* d_weff, int32_t N, int32_t D,
+                         int32_t H, int32_t W, int32_t Ci, int32_t Co, float out_scale, const float* out_scale_dev,
+                         void* workspace, int32_t impl, int32_t Dx, int32_t x_off, void* stream);
 
 /* ---- BatchNorm3d + ReLU on NDHWC fp32 (RepMode.py:146-149,212) ------------------------------------------
  * mode_bn_stats:    sums[2C] (double, must be zeroed by the caller) += sum / sum of squares over M rows.
@@ -185,6 +216,28 @@ int mode_amax(const float* src, int64_t n, float* amax, void* stream);
 int mode_amax_multi(const float* const* srcs_host, const int64_t* counts_host, int32_t k, float* amax, void* stream);
 /* scale2[0] = 2^floor(log2(target / amax[0])) (1 if amax is 0), scale2[1] = 1 / scale2[0]; all device. */
 int mode_f16_scale(const float* amax, float target, float* scale2, void* stream);
+
+/* ---- peer-memory exchange over NVLink / NVSwitch (D-sharded volumes) ---------------------------
+ * The reference has no working multi-GPU data path (fnet/fnet_model.py:40-44 is torch.nn.DataParallel); these entry points
+ * implement the exchange steps of the D-axis split -- halo planes, BatchNorm partial sums, gradient sum -- as plain stores
+ * into the neighbour's memory plus a counter, instead of one NCCL launch each.  Pointers named *_peer are addresses inside
+ * ANOTHER GPU's memory mapped into this process (CUDA IPC; the host side maps them once), everything else is local.
+ * Counters (`signal`, `expect`, `ticket`) are zero-initialised uint32 in device memory and only ever increase, so a captured
+ * CUDA graph can replay the step.  A wait that is not satisfied within ~10 s raises the device error flag (codes 41 / 42,
+ * mode_poll_error) instead of hanging.
+ *   mode_peer_put:       n <= 8 segments of `bytes` (multiple of 16) each: dst[i] <- src[i]; once ALL of them are written,
+ *                        *signal[i] += 1 for every i (release, system scope).  src/dst/signal are HOST arrays of device
+ *                        pointers; dst[i] and signal[i] normally live on a peer.  `ticket`: a local uint32 scratch counter.
+ *   mode_peer_wait:      *expect += add; wait until *signal >= *expect (acquire).  One thread; stream-ordered.
+ *   mode_peer_sum_slots: one-shot all-reduce tail: wait until `world` producers have signalled, then
+ *                        out[i] = slots[0][i] + slots[1][i] + ... in rank order (deterministic); double or float.
+ *   mode_peer_enable_access: cudaDeviceEnablePeerAccess(current device -> peer_device); no-op when already enabled. */
+int mode_peer_enable_access(int32_t peer_device);
+int mode_peer_put(const void* const* src_host, void* const* dst_peer_host, void* const* signal_peer_host, int32_t n,
+                  int64_t bytes, void* ticket, void* stream);
+int mode_peer_wait(const void* signal, void* expect, int32_t add, void* stream);
+int mode_peer_sum_slots(const void* slots, int32_t world, int64_t n, int32_t is_double, void* out, const void* signal,
+                        void* expect, void* ticket, void* stream);
 
 #ifdef __cplusplus
 }

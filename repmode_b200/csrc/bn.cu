@@ -14,6 +14,38 @@ namespace mode {
 constexpr int BN_THREADS = 256;
 constexpr int BN_MAXC = 1024;
 
+// L2 residency control for the two-pass BatchNorm backward: pass 1 streams y and dout front to back and asks L2 to KEEP
+// their tails (evict_last); pass 2 walks backwards, finds the tails in the 126 MB L2 and releases them (evict_first).
+__device__ __forceinline__ uint64_t l2_policy_evict_last() {
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ uint64_t l2_policy_evict_first() {
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ float4 ld_f4_hint(const float* p, uint64_t pol) {
+    float4 v;
+    asm volatile("ld.global.L2::cache_hint.v4.f32 {%0, %1, %2, %3}, [%4], %5;"
+                 : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p), "l"(pol));
+    return v;
+}
+// bytes of each of the two streamed tensors that pass 1 pins for pass 2 (both tails together stay well inside L2)
+static int64_t l2_keep_bytes() {
+    static int64_t keep = -1;
+    if (keep < 0) {
+        int dev = 0, l2 = 0;
+        const char* e = getenv("REPMODE_BN_L2_KEEP_MB");
+        if (e) keep = (int64_t)atoi(e) << 20;
+        else if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetAttribute(&l2, cudaDevAttrL2CacheSize, dev) == cudaSuccess)
+            keep = (int64_t)l2 * 3 / 10;
+        else keep = 0;
+    }
+    return keep;
+}
+
 // D-sharded slab bookkeeping (mode_planes_t by value); kind(row): 0 = outside the global volume, 1 = halo copy,
 // 2 = owned
 struct Planes {
@@ -120,6 +152,8 @@ __global__ void bn_finalize_kernel(const double* __restrict__ sums, int64_t M, i
 }
 
 // ---- apply: out = relu(y*scale + shift), optional fp16 copy ----------------------------------------------
+// Four independent 16-byte loads in flight per thread (one per thread leaves the SM far below the bytes-in-flight HBM
+// needs), and the tensor is walked BACKWARDS: K2 has just written y front to back, so its tail is what the L2 still holds.
 template <bool PLANES>
 __global__ void __launch_bounds__(BN_THREADS) bn_apply_kernel(const float* __restrict__ y, int64_t total, int C,
                                                               const float* __restrict__ scale,
@@ -130,21 +164,34 @@ __global__ void __launch_bounds__(BN_THREADS) bn_apply_kernel(const float* __res
     for (int i = threadIdx.x; i < C; i += BN_THREADS) { ssc[i] = scale[i]; ssh[i] = shift[i]; }
     __syncthreads();
     const int64_t nvec = total >> 2;
-    for (int64_t i = (int64_t)blockIdx.x * BN_THREADS + threadIdx.x; i < nvec; i += (int64_t)gridDim.x * BN_THREADS) {
-        const int c = (int)((i * 4) % C);
-        float4 v = *reinterpret_cast<const float4*>(y + i * 4);
-        v.x = fmaf(v.x, ssc[c], ssh[c]); v.y = fmaf(v.y, ssc[c + 1], ssh[c + 1]);
-        v.z = fmaf(v.z, ssc[c + 2], ssh[c + 2]); v.w = fmaf(v.w, ssc[c + 3], ssh[c + 3]);
-        if (relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
-        if (PLANES && pl.kind((i * 4) / C) == 0) v = make_float4(0.f, 0.f, 0.f, 0.f);   // beyond the global volume
-        if (out) *reinterpret_cast<float4*>(out + i * 4) = v;
-        if (out16) {
-            __half2 a = __floats2half2_rn(v.x * f16_scale, v.y * f16_scale);
-            __half2 b = __floats2half2_rn(v.z * f16_scale, v.w * f16_scale);
-            uint2 pk;
-            pk.x = *reinterpret_cast<uint32_t*>(&a);
-            pk.y = *reinterpret_cast<uint32_t*>(&b);
-            *reinterpret_cast<uint2*>(out16 + i * 4) = pk;
+    const int64_t stride = (int64_t)gridDim.x * BN_THREADS;
+    for (int64_t k = (int64_t)blockIdx.x * BN_THREADS + threadIdx.x; k < nvec; k += 4 * stride) {
+        float4 v[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int64_t kk = k + u * stride;
+            if (kk < nvec) v[u] = *reinterpret_cast<const float4*>(y + (nvec - 1 - kk) * 4);
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int64_t kk = k + u * stride;
+            if (kk >= nvec) continue;
+            const int64_t i = nvec - 1 - kk;
+            const int c = (int)((i * 4) % C);
+            float4 w = v[u];
+            w.x = fmaf(w.x, ssc[c], ssh[c]); w.y = fmaf(w.y, ssc[c + 1], ssh[c + 1]);
+            w.z = fmaf(w.z, ssc[c + 2], ssh[c + 2]); w.w = fmaf(w.w, ssc[c + 3], ssh[c + 3]);
+            if (relu) { w.x = fmaxf(w.x, 0.f); w.y = fmaxf(w.y, 0.f); w.z = fmaxf(w.z, 0.f); w.w = fmaxf(w.w, 0.f); }
+            if (PLANES && pl.kind((i * 4) / C) == 0) w = make_float4(0.f, 0.f, 0.f, 0.f);   // beyond the global volume
+            if (out) *reinterpret_cast<float4*>(out + i * 4) = w;
+            if (out16) {
+                __half2 a = sat_half2(w.x * f16_scale, w.y * f16_scale);
+                __half2 b = sat_half2(w.z * f16_scale, w.w * f16_scale);
+                uint2 pk;
+                pk.x = *reinterpret_cast<uint32_t*>(&a);
+                pk.y = *reinterpret_cast<uint32_t*>(&b);
+                *reinterpret_cast<uint2*>(out16 + i * 4) = pk;
+            }
         }
     }
 }
@@ -200,16 +247,19 @@ __global__ void __launch_bounds__(BN_THREADS) bn_bwd_reduce_kernel(const float* 
     if ((threadIdx.x & 31) == 0) { atomicMax(mx + c, __float_as_int(mdz)); atomicMax(mx + C + c, __float_as_int(mxh)); }
 }
 
-// vectorised pass 1 for C % 4 == 0 (same structure as bn_stats_kernel); four rows in flight per thread
+// vectorised pass 1 for C % 4 == 0: thread t owns the 4 channels of float4 lane t % (C/4).  Four rows (8 independent 16-byte
+// loads) in flight per thread at <= 85 registers, i.e. three blocks per SM: ~96 KB in flight per SM.  A thread sums a few
+// dozen values per channel, so fp32 partials are exact enough; the fold to fp64 happens once per block.  The last
+// `keep_vec` float4 of BOTH tensors are loaded with an evict_last L2 policy: pass 2 reads them first.
 template <bool PLANES>
-__global__ void __launch_bounds__(BN_THREADS) bn_bwd_reduce_vec_kernel(const float* __restrict__ y,
-                                                                       const float* __restrict__ dout, int64_t M,
-                                                                       int C, const float* __restrict__ gamma,
-                                                                       const float* __restrict__ beta,
-                                                                       const float* __restrict__ mean,
-                                                                       const float* __restrict__ invstd,
-                                                                       double* __restrict__ red, int* __restrict__ mx,
-                                                                       Planes pl) {
+__global__ void __launch_bounds__(BN_THREADS, 3) bn_bwd_reduce_vec_kernel(const float* __restrict__ y,
+                                                                          const float* __restrict__ dout, int64_t M,
+                                                                          int C, const float* __restrict__ gamma,
+                                                                          const float* __restrict__ beta,
+                                                                          const float* __restrict__ mean,
+                                                                          const float* __restrict__ invstd,
+                                                                          double* __restrict__ red, int* __restrict__ mx,
+                                                                          Planes pl, int64_t keep_vec) {
     const int vpr = C >> 2;
     const int rows_per_iter = BN_THREADS / vpr;
     const int lane_v = threadIdx.x % vpr, lane_r = threadIdx.x / vpr;
@@ -217,20 +267,22 @@ __global__ void __launch_bounds__(BN_THREADS) bn_bwd_reduce_vec_kernel(const flo
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
         const int c = lane_v * 4 + j;
-        mu[j] = mean[c]; is[j] = invstd[c]; ga[j] = gamma ? gamma[c] : 1.f; be[j] = beta ? beta[c] : 0.f;
+        mu[j] = mean[c]; is[j] = invstd[c];
+        ga[j] = gamma ? gamma[c] : 1.f; be[j] = beta ? beta[c] : 0.f;
     }
     float s[4] = {0, 0, 0, 0}, q[4] = {0, 0, 0, 0}, mdz[4] = {0, 0, 0, 0}, mxh[4] = {0, 0, 0, 0};
-    double ds[4] = {0, 0, 0, 0}, dq[4] = {0, 0, 0, 0};
-    int cnt = 0;
+    const uint64_t pol_keep = l2_policy_evict_last(), pol_drop = l2_policy_evict_first();
     const int64_t stride = (int64_t)gridDim.x * rows_per_iter;
+    const int64_t keep_row = M - keep_vec / vpr;      // rows >= keep_row are pinned in L2
     for (int64_t r = (int64_t)blockIdx.x * rows_per_iter + lane_r; r < M; r += 4 * stride) {
         float4 yv[4], dv[4];
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
             const int64_t rr = r + u * stride;
             if (rr < M) {
-                yv[u] = *reinterpret_cast<const float4*>(y + rr * C + lane_v * 4);
-                dv[u] = *reinterpret_cast<const float4*>(dout + rr * C + lane_v * 4);
+                const uint64_t pol = rr >= keep_row ? pol_keep : pol_drop;
+                yv[u] = ld_f4_hint(y + rr * C + lane_v * 4, pol);
+                dv[u] = ld_f4_hint(dout + rr * C + lane_v * 4, pol);
             }
         }
 #pragma unroll
@@ -246,14 +298,10 @@ __global__ void __launch_bounds__(BN_THREADS) bn_bwd_reduce_vec_kernel(const flo
                 }
             }
         }
-        if (++cnt == 16) {
-#pragma unroll
-            for (int j = 0; j < 4; ++j) { ds[j] += s[j]; dq[j] += q[j]; s[j] = 0.f; q[j] = 0.f; }
-            cnt = 0;
-        }
     }
+    double ds[4], dq[4];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) { ds[j] += s[j]; dq[j] += q[j]; }
+    for (int j = 0; j < 4; ++j) { ds[j] = s[j]; dq[j] = q[j]; }
     __shared__ double sh[8 * BN_THREADS];
     __shared__ int smx[2 * BN_MAXC];
     for (int i = threadIdx.x; i < 2 * C; i += BN_THREADS) smx[i] = 0;
@@ -298,19 +346,21 @@ __global__ void bn_bwd_scale_kernel(const double* __restrict__ red, const int* _
     }
 }
 
-// pass 2, vectorised (C % 4 == 0): float4 in, float4 and/or 4 x fp16 out
+// pass 2, vectorised (C % 4 == 0): float4 in, float4 and/or 4 x fp16 out.  Walks the tensors BACKWARDS: pass 1 pinned their
+// tails in L2 (evict_last); reading them here with evict_first releases the lines.  Two float4 of each tensor (4 loads) in
+// flight per thread.
 template <bool PLANES>
-__global__ void __launch_bounds__(BN_THREADS) bn_bwd_apply_vec_kernel(const float* __restrict__ y,
-                                                                      const float* __restrict__ dout, int64_t M, int C,
-                                                                      const float* __restrict__ gamma,
-                                                                      const float* __restrict__ beta,
-                                                                      const float* __restrict__ mean,
-                                                                      const float* __restrict__ invstd,
-                                                                      const double* __restrict__ red,
-                                                                      float* __restrict__ dgamma, float* __restrict__ dbeta,
-                                                                      float* __restrict__ dy, __half* __restrict__ dy16,
-                                                                      const float* __restrict__ scale2, Planes pl,
-                                                                      long long m_div) {
+__global__ void __launch_bounds__(BN_THREADS, 4) bn_bwd_apply_vec_kernel(const float* __restrict__ y,
+                                                                         const float* __restrict__ dout, int64_t M, int C,
+                                                                         const float* __restrict__ gamma,
+                                                                         const float* __restrict__ beta,
+                                                                         const float* __restrict__ mean,
+                                                                         const float* __restrict__ invstd,
+                                                                         const double* __restrict__ red,
+                                                                         float* __restrict__ dgamma, float* __restrict__ dbeta,
+                                                                         float* __restrict__ dy, __half* __restrict__ dy16,
+                                                                         const float* __restrict__ scale2, Planes pl,
+                                                                         long long m_div) {
     const float f16_scale = (dy16 != nullptr && scale2 != nullptr) ? scale2[0] : 1.f;
     __shared__ float smu[BN_MAXC], sis[BN_MAXC], sga[BN_MAXC], sbe[BN_MAXC], sa[BN_MAXC], sb[BN_MAXC];
     for (int c = threadIdx.x; c < C; c += BN_THREADS) {
@@ -324,32 +374,44 @@ __global__ void __launch_bounds__(BN_THREADS) bn_bwd_apply_vec_kernel(const floa
         }
     }
     __syncthreads();
-    // Walk the tensors BACKWARDS: pass 1 (bn_bwd_reduce_*) has just streamed y and dout front to back, so their tails
-    // are what is still in the 126 MB L2 -- reading them first turns most of this pass's DRAM reads into L2 hits.
+    const uint64_t pol_drop = l2_policy_evict_first();
     const int64_t nvec = (M * C) >> 2;
-    for (int64_t k = (int64_t)blockIdx.x * BN_THREADS + threadIdx.x; k < nvec; k += (int64_t)gridDim.x * BN_THREADS) {
-        const int64_t i = nvec - 1 - k;
-        const int c = (int)((i * 4) % C);
-        const float4 yv = *reinterpret_cast<const float4*>(y + i * 4);
-        const float4 dv = *reinterpret_cast<const float4*>(dout + i * 4);
-        const float ya[4] = {yv.x, yv.y, yv.z, yv.w}, da[4] = {dv.x, dv.y, dv.z, dv.w};
-        float v[4];
-        const int kind = PLANES ? pl.kind((i * 4) / C) : 2;   // 2 owned: full formula; 1 halo copy: no mean terms; 0: zero
-        const float own = kind == 2 ? 1.f : 0.f;
+    const int64_t stride = (int64_t)gridDim.x * BN_THREADS;
+    for (int64_t k = (int64_t)blockIdx.x * BN_THREADS + threadIdx.x; k < nvec; k += 2 * stride) {
+        float4 yv[2], dv[2];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const float xh = (ya[j] - smu[c + j]) * sis[c + j];
-            const float dz = (kind != 0 && fmaf(xh, sga[c + j], sbe[c + j]) > 0.f) ? da[j] : 0.f;
-            v[j] = sga[c + j] * sis[c + j] * (dz - own * (sa[c + j] + xh * sb[c + j]));
+        for (int u = 0; u < 2; ++u) {
+            const int64_t kk = k + u * stride;
+            if (kk < nvec) {
+                yv[u] = ld_f4_hint(y + (nvec - 1 - kk) * 4, pol_drop);
+                dv[u] = ld_f4_hint(dout + (nvec - 1 - kk) * 4, pol_drop);
+            }
         }
-        if (dy) *reinterpret_cast<float4*>(dy + i * 4) = make_float4(v[0], v[1], v[2], v[3]);
-        if (dy16) {
-            __half2 a = __floats2half2_rn(v[0] * f16_scale, v[1] * f16_scale);
-            __half2 b = __floats2half2_rn(v[2] * f16_scale, v[3] * f16_scale);
-            uint2 pk;
-            pk.x = *reinterpret_cast<uint32_t*>(&a);
-            pk.y = *reinterpret_cast<uint32_t*>(&b);
-            *reinterpret_cast<uint2*>(dy16 + i * 4) = pk;
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+            const int64_t kk = k + u * stride;
+            if (kk >= nvec) continue;
+            const int64_t i = nvec - 1 - kk;
+            const int c = (int)((i * 4) % C);
+            const float ya[4] = {yv[u].x, yv[u].y, yv[u].z, yv[u].w}, da[4] = {dv[u].x, dv[u].y, dv[u].z, dv[u].w};
+            float v[4];
+            const int kind = PLANES ? pl.kind((i * 4) / C) : 2;   // 2 owned: full formula; 1 halo copy: no mean terms; 0: zero
+            const float own = kind == 2 ? 1.f : 0.f;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const float xh = (ya[j] - smu[c + j]) * sis[c + j];
+                const float dz = (kind != 0 && fmaf(xh, sga[c + j], sbe[c + j]) > 0.f) ? da[j] : 0.f;
+                v[j] = sga[c + j] * sis[c + j] * (dz - own * (sa[c + j] + xh * sb[c + j]));
+            }
+            if (dy) *reinterpret_cast<float4*>(dy + i * 4) = make_float4(v[0], v[1], v[2], v[3]);
+            if (dy16) {
+                __half2 a = sat_half2(v[0] * f16_scale, v[1] * f16_scale);
+                __half2 b = sat_half2(v[2] * f16_scale, v[3] * f16_scale);
+                uint2 pk;
+                pk.x = *reinterpret_cast<uint32_t*>(&a);
+                pk.y = *reinterpret_cast<uint32_t*>(&b);
+                *reinterpret_cast<uint2*>(dy16 + i * 4) = pk;
+            }
         }
     }
 }
@@ -390,21 +452,31 @@ __global__ void __launch_bounds__(BN_THREADS) bn_bwd_apply_kernel(const float* _
 }
 
 // ---- operand staging ---------------------------------------------------------------------------------------
+// fp32 -> fp16, round to nearest even, SATURATED to +-65504 (never inf: an out-of-range activation clips instead of
+// poisoning the accumulators).  Four 16-byte loads in flight per thread.
 __global__ void __launch_bounds__(256) cast_f16_kernel(const float* __restrict__ src, __half* __restrict__ dst,
                                                        int64_t n, float scale, const float* __restrict__ scale_dev) {
     if (scale_dev != nullptr) scale *= *scale_dev;
     const int64_t nvec = n >> 2;
-    for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < nvec; i += (int64_t)gridDim.x * 256) {
-        const float4 v = *reinterpret_cast<const float4*>(src + i * 4);
-        __half2 a = __floats2half2_rn(v.x * scale, v.y * scale), b = __floats2half2_rn(v.z * scale, v.w * scale);
-        uint2 pk;
-        pk.x = *reinterpret_cast<uint32_t*>(&a);
-        pk.y = *reinterpret_cast<uint32_t*>(&b);
-        *reinterpret_cast<uint2*>(dst + i * 4) = pk;
+    const int64_t stride = (int64_t)gridDim.x * 256;
+    for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < nvec; i += 4 * stride) {
+        float4 v[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+            if (i + u * stride < nvec) v[u] = *reinterpret_cast<const float4*>(src + (i + u * stride) * 4);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            if (i + u * stride >= nvec) continue;
+            __half2 a = sat_half2(v[u].x * scale, v[u].y * scale), b = sat_half2(v[u].z * scale, v[u].w * scale);
+            uint2 pk;
+            pk.x = *reinterpret_cast<uint32_t*>(&a);
+            pk.y = *reinterpret_cast<uint32_t*>(&b);
+            *reinterpret_cast<uint2*>(dst + (i + u * stride) * 4) = pk;
+        }
     }
     if (blockIdx.x == 0 && threadIdx.x < (n & 3)) {
         const int64_t i = (nvec << 2) + threadIdx.x;
-        dst[i] = __float2half_rn(src[i] * scale);
+        dst[i] = __float2half_rn(fminf(fmaxf(src[i] * scale, -65504.f), 65504.f));
     }
 }
 
@@ -522,6 +594,7 @@ extern "C" int mode_bn_relu_bwd_reduce(const float* y, const float* dout, int64_
     if ((C & 3) == 0 && vpr <= BN_THREADS && BN_THREADS % vpr == 0 && aligned) {
         const int rpi = BN_THREADS / vpr;
         int grid = stream_grid(M, rpi * 16);
+        const int64_t keep_vec = std::min<int64_t>(M * C / 4, l2_keep_bytes() / 16) / vpr * vpr;   // whole rows
         // A/B knob for the next measurement round: blocks per SM of the reduce pass.  Today's heuristic launches 6 short
         // blocks per SM (3 waves at 2 resident), each ending in 2*C fp64 atomics on the same addresses; the pass runs at
         // 3.6 TB/s while the apply pass over the same tensors reaches 5.4 (profiles/r1_final_ncu_full_summary.csv).
@@ -529,10 +602,10 @@ extern "C" int mode_bn_relu_bwd_reduce(const float* y, const float* dout, int64_
         if (bps > 0) grid = (int)min((int64_t)grid, (int64_t)sm_count() * bps);
         if (planes)
             bn_bwd_reduce_vec_kernel<true><<<grid, BN_THREADS, 0, st>>>(y, dout, M, C, gamma, beta, mean, invstd,
-                                                                        workspace, mx, to_planes(planes));
+                                                                        workspace, mx, to_planes(planes), keep_vec);
         else
             bn_bwd_reduce_vec_kernel<false><<<grid, BN_THREADS, 0, st>>>(y, dout, M, C, gamma, beta, mean, invstd,
-                                                                         workspace, mx, Planes{});
+                                                                         workspace, mx, Planes{}, keep_vec);
     } else {
         if (planes) MODE_FAIL("mode_bn_relu_bwd_reduce: plane ranges need C %% 4 == 0 and 16-byte aligned tensors");
         const int gx = (int)max((int64_t)1, min(ceil_div(M, BN_THREADS * 8), (int64_t)64));

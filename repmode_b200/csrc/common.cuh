@@ -37,4 +37,22 @@ __host__ __device__ constexpr int64_t ceil_div(int64_t a, int64_t b) { return (a
 // Cached per-device SM count (read-only after first use; benign race).
 int sm_count();
 
+// mode_conv_opts_t resolved by the dispatcher (Dx / Dy16 / y16_scale defaults filled in): haloed input + fused epilogue.
+struct ConvExt {
+    int Dx, x_off;                 // input planes, input plane of output plane 0's centre tap
+    const float* ep_scale;         // per-channel affine after out_scale (eval-mode BatchNorm) or null
+    const float* ep_shift;
+    int relu;
+    __half* y16;                   // optional fp16 copy of the result [N, Dy16, H, W, Nout], output plane q -> plane q + y16_off
+    int Dy16, y16_off;
+    float y16_scale;
+    __host__ __device__ int p_lo() const { return -x_off; }              // valid input planes in OUTPUT plane coordinates
+    __host__ __device__ int p_hi() const { return Dx - x_off - 1; }
+};
+
+// fp32 -> fp16 with saturation (never inf): operands of the tcgen05 kernels
+__device__ __forceinline__ __half2 sat_half2(float a, float b) {
+    return __floats2half2_rn(fminf(fmaxf(a, -65504.f), 65504.f), fminf(fmaxf(b, -65504.f), 65504.f));
+}
+
 }  // namespace mode

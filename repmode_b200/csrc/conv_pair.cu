@@ -64,7 +64,8 @@ template <bool RES> struct Plan {
     static constexpr uint32_t W_OFF = RING * PLANE_BYTES;
     static constexpr uint32_t BAR_OFF = W_OFF + WST * WST_BYTES;
     static constexpr uint32_t BN_OFF = BAR_OFF + 1024;
-    static constexpr uint32_t TOTAL = BN_OFF + 2 * NT * sizeof(double);
+    static constexpr uint32_t EP_OFF = BN_OFF + 2 * NT * sizeof(double);      // epilogue affine: scale[NT], shift[NT]
+    static constexpr uint32_t TOTAL = EP_OFF + 2 * NT * sizeof(float);
 };
 }  // namespace cp
 
@@ -79,6 +80,8 @@ struct PairParams {
     int stat_lo, stat_hi;
     int tiles_w, tiles_h2;       // pair patches: 8 wide, 32 high
     int32_t bounds[cp::MAX_CLUSTERS + 1];   // cluster c owns plane-units [bounds[c], bounds[c+1]) of (n, th2, tw, d)
+    ConvExt ext;                 // haloed input (Dx, x_off) and fused epilogue (affine + ReLU, fp16 copy)
+    int p_lo, p_hi;              // valid input planes in output-plane coordinates: [-x_off, Dx - x_off - 1]
     int* error_flag;
     long long* prof;
     int flags;                   // debug: bit 1 = force the streaming plan even when K == 32
@@ -122,6 +125,7 @@ conv3d_pair_kernel(const __grid_constant__ CUtensorMap xmap, const PairParams P)
     const uint32_t tmem_full = w_full + 16 * cp::MAX_WST, tmem_empty = tmem_full + 16;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + PL::BAR_OFF + 1000);
     double* s_bn = reinterpret_cast<double*>(smem + PL::BN_OFF);
+    float* s_ep = reinterpret_cast<float*>(smem + PL::EP_OFF);
     static_assert(16 * cp::MAX_RING + 16 * cp::MAX_WST + 32 <= 1000, "barrier table overflows its 1 KB");
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -144,6 +148,11 @@ conv3d_pair_kernel(const __grid_constant__ CUtensorMap xmap, const PairParams P)
     if (warp == 2) tmem_alloc_pair<512>(smem_u32(tmem_slot));
     if (warp == 0 && lane == 0) tma_prefetch_desc(&xmap);
     for (int i = threadIdx.x; i < 2 * cp::NT; i += cp::THREADS) s_bn[i] = 0.0;
+    const bool has_ep = P.ext.ep_scale != nullptr || P.ext.ep_shift != nullptr;
+    if (has_ep && threadIdx.x < cp::NT) {
+        s_ep[threadIdx.x] = P.ext.ep_scale ? P.ext.ep_scale[n0 + threadIdx.x] : 1.f;
+        s_ep[cp::NT + threadIdx.x] = P.ext.ep_shift ? P.ext.ep_shift[n0 + threadIdx.x] : 0.f;
+    }
     tc_fence_before();
     __syncthreads();
     cluster_sync_all();              // both CTAs' barriers are initialised before any remote arrive / multicast commit
@@ -159,7 +168,7 @@ conv3d_pair_kernel(const __grid_constant__ CUtensorMap xmap, const PairParams P)
             int n, h0, w0, da, db;
             bool ok = true;
             while (ok && rw.next(n, h0, w0, da, db)) {
-                const int p0 = max(da - 2, 0), p1 = min(db + 1, P.D - 1);
+                const int p0 = max(da - 2, P.p_lo), p1 = min(db + 1, P.p_hi);
                 for (int gp = p0; ok && gp <= p1; gp += cp::GROUP) {
                     const int gn = min(cp::GROUP, p1 - gp + 1);
                     for (int c = 0; ok && c < nchunk; ++c) {
@@ -167,7 +176,7 @@ conv3d_pair_kernel(const __grid_constant__ CUtensorMap xmap, const PairParams P)
                             if (!mbar_wait(plane_empty + 8 * slot, (use & 1) ^ 1)) { atomicExch(P.error_flag, 11); ok = false; break; }
                             mbar_expect_tx(plane_full + 8 * slot, cp::PLANE_BYTES);
                             tma_load_5d(base + PL::PLANE_OFF + slot * cp::PLANE_BYTES, &xmap, plane_full + 8 * slot, c * 32,
-                                        w0 - 2, h0 + (int)rank * cp::TH - 2, gp + i, n);
+                                        w0 - 2, h0 + (int)rank * cp::TH - 2, gp + i + P.ext.x_off, n);
                             if (++slot == RING) { slot = 0; ++use; }
                         }
                     }
@@ -211,7 +220,7 @@ conv3d_pair_kernel(const __grid_constant__ CUtensorMap xmap, const PairParams P)
                         ++nreload;
                     }
                 } else {
-                    const int p0 = max(da - 2, 0), p1 = min(db + 1, P.D - 1);
+                    const int p0 = max(da - 2, P.p_lo), p1 = min(db + 1, P.p_hi);
                     for (int gp = p0; ok && gp <= p1; gp += cp::GROUP) {
                         for (int c = 0; ok && c < nchunk; ++c) {
                             for (int t = 0; t < 25; ++t) {
@@ -235,7 +244,7 @@ conv3d_pair_kernel(const __grid_constant__ CUtensorMap xmap, const PairParams P)
             int n, h0, w0, da, db;
             bool ok = true;
             while (ok && rw.next(n, h0, w0, da, db)) {
-                const int p0 = max(da - 2, 0), p1 = min(db + 1, P.D - 1);
+                const int p0 = max(da - 2, P.p_lo), p1 = min(db + 1, P.p_hi);
                 if constexpr (RES) {
                     const int u = P.sample_u ? P.sample_u[n] : 0;
                     if (u != cur_u) {
@@ -301,7 +310,7 @@ conv3d_pair_kernel(const __grid_constant__ CUtensorMap xmap, const PairParams P)
                 const int da = u - col * P.D;
                 const int db = min(P.D, da + (uend - u));
                 u += db - da;
-                const int p0 = max(da - 2, 0), p1 = min(db + 1, P.D - 1);
+                const int p0 = max(da - 2, P.p_lo), p1 = min(db + 1, P.p_hi);
                 if constexpr (RES) {
                     const int n = col / (P.tiles_w * P.tiles_h2);
                     const int su = P.sample_u ? P.sample_u[n] : 0;
@@ -426,7 +435,7 @@ conv3d_pair_kernel(const __grid_constant__ CUtensorMap xmap, const PairParams P)
         uint32_t g = 0;
         bool ok = true;
         while (ok && rw.next(n, h0, w0, da, db)) {
-            const int p0 = max(da - 2, 0), p1 = min(db + 1, P.D - 1);
+            const int p0 = max(da - 2, P.p_lo), p1 = min(db + 1, P.p_hi);
             const int hh = h0 + (int)rank * cp::TH + th;
             const bool row_ok = hh < P.H;
             for (int gp = p0; gp <= p1; gp += cp::GROUP, ++g) {
@@ -453,12 +462,39 @@ conv3d_pair_kernel(const __grid_constant__ CUtensorMap xmap, const PairParams P)
                             for (int j = 0; j < 32; ++j) f[j] += __uint_as_float(v[j]);
                         }
 #pragma unroll
-                        for (int j = 0; j < 32; ++j) f[j] = row_ok ? f[j] * scale : 0.f;
-                        if (row_ok) {
-                            float* dst = P.y + ((((size_t)n * P.D + q) * P.H + hh) * P.W + w0 + tw) * P.Nout + n0;
+                        for (int j = 0; j < 32; ++j) f[j] *= scale;
+                        if (has_ep) {
 #pragma unroll
-                            for (int j = 0; j < 32; j += 4)
-                                *reinterpret_cast<float4*>(dst + j) = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
+                            for (int j = 0; j < 32; ++j) f[j] = fmaf(f[j], s_ep[j], s_ep[cp::NT + j]);
+                        }
+                        if (P.ext.relu) {
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.f);
+                        }
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) f[j] = row_ok ? f[j] : 0.f;
+                        if (row_ok) {
+                            const size_t vox = ((size_t)hh * P.W + w0 + tw);
+                            if (P.y != nullptr) {
+                                float* dst = P.y + ((((size_t)n * P.D + q) * P.H) * P.W + vox) * P.Nout + n0;
+#pragma unroll
+                                for (int j = 0; j < 32; j += 4)
+                                    *reinterpret_cast<float4*>(dst + j) = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
+                            }
+                            if (P.ext.y16 != nullptr) {
+                                __half* d16 = P.ext.y16 +
+                                              ((((size_t)n * P.ext.Dy16 + q + P.ext.y16_off) * P.H) * P.W + vox) * P.Nout + n0;
+                                const float s16 = P.ext.y16_scale;
+#pragma unroll
+                                for (int j = 0; j < 32; j += 8) {
+                                    __half2 h0 = sat_half2(f[j] * s16, f[j + 1] * s16), h1 = sat_half2(f[j + 2] * s16, f[j + 3] * s16);
+                                    __half2 h2 = sat_half2(f[j + 4] * s16, f[j + 5] * s16), h3 = sat_half2(f[j + 6] * s16, f[j + 7] * s16);
+                                    uint4 pk;
+                                    pk.x = *reinterpret_cast<uint32_t*>(&h0); pk.y = *reinterpret_cast<uint32_t*>(&h1);
+                                    pk.z = *reinterpret_cast<uint32_t*>(&h2); pk.w = *reinterpret_cast<uint32_t*>(&h3);
+                                    *reinterpret_cast<uint4*>(d16 + j) = pk;
+                                }
+                            }
                         }
                         if (P.bn_sums != nullptr && q >= P.stat_lo && q < P.stat_hi) {
                             float gq[32];
@@ -513,22 +549,22 @@ long long* debug_profile_buffer();   // mode_abi.cu
 int make_act_map(CUtensorMap* map, const __half* x, int N, int D, int H, int W, int K, int box_w, int box_h, int box_d);   // conv_umma.cu
 
 // input planes a run [da, db) of a D-plane column has to process (+0.25 per group hand-off)
-static double run_cost(int da, int db, int D) {
-    const int planes = std::min(db + 1, D - 1) - std::max(da - 2, 0) + 1;
+static double run_cost(int da, int db, int p_lo, int p_hi) {
+    const int planes = std::min(db + 1, p_hi) - std::max(da - 2, p_lo) + 1;
     return planes + 0.25 * ((planes + cp::GROUP - 1) / cp::GROUP);
 }
 
 // take plane-units from u while the accumulated cost stays within the budget; returns the new position
-static int64_t take_runs(int64_t u, int64_t units, int D, double budget) {
+static int64_t take_runs(int64_t u, int64_t units, int D, int p_lo, int p_hi, double budget) {
     double acc = 0;
     while (u < units) {
         const int da = (int)(u % D);
-        const double whole = run_cost(da, D, D);
+        const double whole = run_cost(da, D, p_lo, p_hi);
         if (acc + whole <= budget) { acc += whole; u += D - da; continue; }
         int lo = 0, hi = D - da;                           // largest k with cost(da, da+k) fitting (cost is monotone in k)
         while (hi - lo > 1) {
             const int mid = (lo + hi) / 2;
-            if (acc + run_cost(da, da + mid, D) <= budget) lo = mid; else hi = mid;
+            if (acc + run_cost(da, da + mid, p_lo, p_hi) <= budget) lo = mid; else hi = mid;
         }
         u += lo;
         break;
@@ -536,23 +572,25 @@ static int64_t take_runs(int64_t u, int64_t units, int D, double budget) {
     return u;
 }
 
-static void partition_runs(int64_t units, int D, int G, int32_t* bounds) {
+static void partition_runs(int64_t units, int D, int p_lo, int p_hi, int G, int32_t* bounds) {
     struct Key {
-        int64_t units; int D, G;
-        bool operator<(const Key& o) const { return std::tie(units, D, G) < std::tie(o.units, o.D, o.G); }
+        int64_t units; int D, p_lo, p_hi, G;
+        bool operator<(const Key& o) const {
+            return std::tie(units, D, p_lo, p_hi, G) < std::tie(o.units, o.D, o.p_lo, o.p_hi, o.G);
+        }
     };
     static std::mutex mu;
     static std::map<Key, std::array<int32_t, cp::MAX_CLUSTERS + 1>> cache;
-    const Key key{units, D, G};
+    const Key key{units, D, p_lo, p_hi, G};
     std::lock_guard<std::mutex> lock(mu);
     auto it = cache.find(key);
     if (it == cache.end()) {
         double total = 0;
-        for (int64_t u = 0; u < units; u += D) total += run_cost(0, D, D);
+        for (int64_t u = 0; u < units; u += D) total += run_cost(0, D, p_lo, p_hi);
         auto feasible = [&](double budget) {
             int64_t u = 0;
             for (int c = 0; c < G && u < units; ++c) {
-                const int64_t nu = take_runs(u, units, D, budget);
+                const int64_t nu = take_runs(u, units, D, p_lo, p_hi, budget);
                 if (nu == u) return false;
                 u = nu;
             }
@@ -569,7 +607,7 @@ static void partition_runs(int64_t units, int D, int G, int32_t* bounds) {
         int64_t u = 0;
         for (int c = 0; c < G; ++c) {
             b[c] = (int32_t)u;
-            u = std::min(units, take_runs(u, units, D, h));
+            u = std::min(units, take_runs(u, units, D, p_lo, p_hi, h));
         }
         for (int c = G; c <= cp::MAX_CLUSTERS; ++c) b[c] = (int32_t)units;
         it = cache.emplace(key, b).first;
@@ -591,9 +629,9 @@ bool conv3d_pair_supported(int N, int D, int H, int W, int K, int Nout) {
 
 int conv3d_pair(const __half* x, const __half* w, const int32_t* sample_u, float* y, int N, int D, int H, int W, int K,
                 int Nout, float out_scale, const float* out_scale_dev, double* bn_sums, int stat_lo, int stat_hi,
-                cudaStream_t st) {
+                const ConvExt& ext, cudaStream_t st) {
     if ((reinterpret_cast<uintptr_t>(x) & 15) || (reinterpret_cast<uintptr_t>(w) & 15) ||
-        (reinterpret_cast<uintptr_t>(y) & 15))
+        (reinterpret_cast<uintptr_t>(y) & 15) || (reinterpret_cast<uintptr_t>(ext.y16) & 15))
         MODE_FAIL("conv3d_pair: pointers must be 16-byte aligned");
     if (!(K % 32 == 0 && Nout % 32 == 0 && W % cp::TW == 0)) MODE_FAIL("conv3d_pair: unsupported shape");
     PairParams P;
@@ -608,14 +646,16 @@ int conv3d_pair(const __half* x, const __half* w, const int32_t* sample_u, float
     int G = (int)std::min<int64_t>(pair_clusters(passes), std::max<int64_t>(1, units / 4));
     if (const char* e = getenv("REPMODE_PAIR_CLUSTERS"))          // test hook: force the number of clusters
         G = std::max(1, std::min(std::min(G, cp::MAX_CLUSTERS), atoi(e)));
-    partition_runs(units, D, G, P.bounds);
+    P.ext = ext;
+    P.p_lo = ext.p_lo(); P.p_hi = ext.p_hi();
+    partition_runs(units, D, P.p_lo, P.p_hi, G, P.bounds);
     P.error_flag = device_error_flag();
     if (!P.error_flag) MODE_FAIL("conv3d_pair: could not allocate the device error flag");
     P.prof = debug_profile_buffer();
     P.flags = 0;
     if (const char* e = getenv("REPMODE_PAIR_FLAGS")) P.flags = atoi(e);
     CUtensorMap xmap;
-    if (make_act_map(&xmap, x, N, D, H, W, K, cp::BW, cp::BH, 1) != 0) return -1;
+    if (make_act_map(&xmap, x, N, ext.Dx, H, W, K, cp::BW, cp::BH, 1) != 0) return -1;
     static_assert(cp::Plan<true>::TOTAL + 1024 <= 227 * 1024 && cp::Plan<false>::TOTAL + 1024 <= 227 * 1024,
                   "shared memory budget");
     if (K == 32 && !(P.flags & 2)) {

@@ -20,7 +20,8 @@ __global__ void __launch_bounds__(256) conv3d_simt_kernel(const float* __restric
                                                           const int32_t* __restrict__ sample_u,
                                                           float* __restrict__ y, int D, int H, int W, int K, int Nout,
                                                           float out_scale, const float* __restrict__ out_scale_dev,
-                                                          double* __restrict__ bn_sums, int stat_lo, int stat_hi) {
+                                                          double* __restrict__ bn_sums, int stat_lo, int stat_hi,
+                                                          ConvExt ext) {
     __shared__ float xs[KC8 * XPLANE];
     __shared__ __align__(16) float ws[25 * KC8 * 32];
     const int tiles_w = (W + TW - 1) / TW;
@@ -40,8 +41,8 @@ __global__ void __launch_bounds__(256) conv3d_simt_kernel(const float* __restric
     const int nk8 = (K + KC8 - 1) / KC8;
     for (int k8 = 0; k8 < nk8; ++k8) {
         for (int kd = 0; kd < 5; ++kd) {
-            const int dz = d + kd - 2;
-            if (dz < 0 || dz >= D) continue;          // zero padding plane (uniform across the block)
+            const int dz = d + kd - 2 + ext.x_off;    // plane of the (possibly haloed) input tensor
+            if (dz < 0 || dz >= ext.Dx) continue;     // zero padding plane (uniform across the block)
             __syncthreads();
             // haloed input tile, channel-planar in shared memory
             for (int idx = tid; idx < XR * XC * KC8; idx += 256) {
@@ -50,7 +51,7 @@ __global__ void __launch_bounds__(256) conv3d_simt_kernel(const float* __restric
                 const int hy = th0 + r - 2, wx = tw0 + cc - 2, k = k8 * KC8 + ch;
                 float val = 0.f;
                 if (hy >= 0 && hy < H && wx >= 0 && wx < W && k < K)
-                    val = x[((((size_t)n * D + dz) * H + hy) * W + wx) * K + k];
+                    val = x[((((size_t)n * ext.Dx + dz) * H + hy) * W + wx) * K + k];
                 xs[ch * XPLANE + r * XC + cc] = val;
             }
             // 25 taps x 8 k x 32 n weights of this (kd, k8)
@@ -105,12 +106,18 @@ __global__ void __launch_bounds__(256) conv3d_simt_kernel(const float* __restric
         const int wx = tw0 + vw + half * 16;
         const float* acc = half ? acc1 : acc0;
         if (hy < H && wx < W) {
-            float* dst = y + ((((size_t)n * D + d) * H + hy) * W + wx) * Nout + c0;
+            const size_t vox = (size_t)hy * W + wx;
+            float* dst = y ? y + ((((size_t)n * D + d) * H) * W + vox) * Nout + c0 : nullptr;
+            __half* d16 = ext.y16 ? ext.y16 + ((((size_t)n * ext.Dy16 + d + ext.y16_off) * H) * W + vox) * Nout + c0 : nullptr;
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
                 if (c0 + j < Nout) {
-                    const float v = acc[j] * out_scale;
-                    dst[j] = v;
+                    float v = acc[j] * out_scale;
+                    if (ext.ep_scale) v *= ext.ep_scale[c0 + j];
+                    if (ext.ep_shift) v += ext.ep_shift[c0 + j];
+                    if (ext.relu) v = fmaxf(v, 0.f);
+                    if (dst) dst[j] = v;
+                    if (d16) d16[j] = __float2half_rn(fminf(fmaxf(v * ext.y16_scale, -65504.f), 65504.f));
                     s1[j] += v;
                     s2[j] = fmaf(v, v, s2[j]);
                 }
@@ -142,7 +149,7 @@ __global__ void __launch_bounds__(256) conv3d_simt_kernel(const float* __restric
 __global__ void __launch_bounds__(256) wgrad_simt_kernel(const float* __restrict__ x, const float* __restrict__ dy,
                                                          float* __restrict__ dw, int D, int H, int W, int Ci, int Co,
                                                          float out_scale, const float* __restrict__ out_scale_dev,
-                                                         int vox_per_split) {
+                                                         int vox_per_split, int Dx, int x_off) {
     __shared__ float dys[64 * 33];
     __shared__ __align__(16) float xsh[64 * 36];
     const int tap = blockIdx.x, split = blockIdx.y;
@@ -163,9 +170,9 @@ __global__ void __launch_bounds__(256) wgrad_simt_kernel(const float* __restrict
                 const int wx = (int)(p % W), hy = (int)((p / W) % H), dz = (int)(p / ((int64_t)W * H));
                 const int oo = ob * 32 + ch, ii = ib * 32 + ch;
                 if (oo < Co) a = dy[((size_t)n * nvox + p) * Co + oo];
-                const int dz2 = dz + kd, hy2 = hy + kh, wx2 = wx + kw;
-                if (ii < Ci && dz2 >= 0 && dz2 < D && hy2 >= 0 && hy2 < H && wx2 >= 0 && wx2 < W)
-                    b = x[((((size_t)n * D + dz2) * H + hy2) * W + wx2) * Ci + ii];
+                const int dz2 = dz + kd + x_off, hy2 = hy + kh, wx2 = wx + kw;      // x may carry halo planes
+                if (ii < Ci && dz2 >= 0 && dz2 < Dx && hy2 >= 0 && hy2 < H && wx2 >= 0 && wx2 < W)
+                    b = x[((((size_t)n * Dx + dz2) * H + hy2) * W + wx2) * Ci + ii];
             }
             dys[v * 33 + ch] = a;
             xsh[v * 36 + ch] = b;
@@ -196,18 +203,18 @@ __global__ void __launch_bounds__(256) wgrad_simt_kernel(const float* __restrict
 
 int conv3d_simt(const float* x, const float* w, const int32_t* sample_u, float* y, int N, int D, int H, int W, int K,
                 int Nout, float out_scale, const float* out_scale_dev, double* bn_sums, int stat_lo, int stat_hi,
-                cudaStream_t st) {
+                const ConvExt& ext, cudaStream_t st) {
     const int tiles = (int)(ceil_div(H, TH) * ceil_div(W, TW));
     const int64_t gz = (int64_t)N * ceil_div(Nout, 32);
     if (D > 65535 || gz > 65535) MODE_FAIL("conv3d_simt: grid too large (D=%d, N*ob=%lld)", D, (long long)gz);
     conv3d_simt_kernel<<<dim3(tiles, D, (unsigned)gz), 256, 0, st>>>(x, w, sample_u, y, D, H, W, K, Nout, out_scale,
-                                                                      out_scale_dev, bn_sums, stat_lo, stat_hi);
+                                                                      out_scale_dev, bn_sums, stat_lo, stat_hi, ext);
     MODE_LAUNCH_CHECK();
     return 0;
 }
 
 int wgrad_simt(const float* x, const float* dy, float* dw, int N, int D, int H, int W, int Ci, int Co, float out_scale,
-               const float* out_scale_dev, cudaStream_t st) {
+               const float* out_scale_dev, int Dx, int x_off, cudaStream_t st) {
     const int64_t nvox = (int64_t)D * H * W;
     const int64_t gz = (int64_t)N * ceil_div(Co, 32) * ceil_div(Ci, 32);
     if (gz > 65535) MODE_FAIL("wgrad_simt: grid too large");
@@ -218,7 +225,7 @@ int wgrad_simt(const float* x, const float* dy, float* dw, int N, int D, int H, 
     splits = ceil_div(nvox, vps);
     if (splits > 1) MODE_CUDA(cudaMemsetAsync(dw, 0, (size_t)N * 125 * Co * Ci * sizeof(float), st));
     wgrad_simt_kernel<<<dim3(125, (unsigned)splits, (unsigned)gz), 256, 0, st>>>(x, dy, dw, D, H, W, Ci, Co, out_scale,
-                                                                               out_scale_dev, vps);
+                                                                               out_scale_dev, vps, Dx, x_off);
     MODE_LAUNCH_CHECK();
     return 0;
 }

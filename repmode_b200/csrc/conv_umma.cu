@@ -58,6 +58,8 @@ struct ConvParams {
     int stat_lo, stat_hi;        // BatchNorm sums cover output planes [stat_lo, stat_hi) only (owned planes of a slab)
     int TD, ring, wstages;
     int tiles_w, tiles_h;
+    ConvExt ext;                 // haloed input (Dx, x_off) and fused epilogue (affine + ReLU, fp16 copy)
+    int p_lo, p_hi;              // valid input planes in output-plane coordinates: [-x_off, Dx - x_off - 1]
     int64_t units;               // N * tiles_h * tiles_w * D plane-patches
     int32_t bounds[160];         // CTA c owns units [bounds[c], bounds[c+1]) -- cost-balanced on the host
     int* error_flag;
@@ -89,7 +91,7 @@ struct TileWalker {
 };
 
 struct SmemLayout {
-    uint32_t plane_off, w_off, bar_off, bn_off, total;
+    uint32_t plane_off, w_off, bar_off, bn_off, ep_off, total;
 };
 
 __host__ __device__ inline SmemLayout smem_layout(int ring, int wstages, int Nt) {
@@ -99,14 +101,15 @@ __host__ __device__ inline SmemLayout smem_layout(int ring, int wstages, int Nt)
     const uint32_t wst_bytes = 5u * Nt * cu::ROWB;
     L.bar_off = L.w_off + wstages * wst_bytes;
     L.bn_off = L.bar_off + 1024;       // 512 B of mbarriers + tmem slot, 512 B MMA-issuer plane table
-    L.total = L.bn_off + 2 * 256 * sizeof(double);
+    L.ep_off = L.bn_off + 2 * 256 * sizeof(double);     // epilogue affine: scale[Nt], shift[Nt]
+    L.total = L.ep_off + 2 * 256 * sizeof(float);
     return L;
 }
 
-// valid (in-volume) input planes of a tile: p in [pmin, pmax], input d = d0 + p - 2
-__device__ __forceinline__ void plane_range(int d0, int TD, int D, int& pmin, int& pmax) {
-    pmin = max(0, 2 - d0);
-    pmax = min(TD + 3, D + 1 - d0);
+// valid (in-volume) input planes of a tile: p in [pmin, pmax], input plane (output coordinates) = d0 + p - 2 in [p_lo, p_hi]
+__device__ __forceinline__ void plane_range(int d0, int TD, int p_lo, int p_hi, int& pmin, int& pmax) {
+    pmin = max(0, p_lo + 2 - d0);
+    pmax = min(TD + 3, p_hi + 2 - d0);
 }
 
 __global__ void __launch_bounds__(cu::THREADS, 1)
@@ -123,6 +126,7 @@ conv3d_umma_kernel(const __grid_constant__ CUtensorMap xmap, const ConvParams P)
     const uint32_t tmem_full = w_empty + 8 * cu::MAX_WST, tmem_empty = tmem_full + 16;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + L.bar_off + 400);
     double* s_bn = reinterpret_cast<double*>(smem + L.bn_off);   // per-CTA BatchNorm partial sums [2][Nt]
+    float* s_ep = reinterpret_cast<float*>(smem + L.ep_off);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int n0 = blockIdx.y * P.Nt;
@@ -140,11 +144,16 @@ conv3d_umma_kernel(const __grid_constant__ CUtensorMap xmap, const ConvParams P)
     if (warp == 2) tmem_alloc<512>(smem_u32(tmem_slot));
     if (warp == 0 && lane == 0) tma_prefetch_desc(&xmap);
     for (int i = threadIdx.x; i < 2 * P.Nt; i += cu::THREADS) s_bn[i] = 0.0;
+    const bool has_ep = P.ext.ep_scale != nullptr || P.ext.ep_shift != nullptr;
+    if (has_ep)
+        for (int i = threadIdx.x; i < P.Nt; i += cu::THREADS) {
+            s_ep[i] = P.ext.ep_scale ? P.ext.ep_scale[n0 + i] : 1.f;
+            s_ep[P.Nt + i] = P.ext.ep_shift ? P.ext.ep_shift[n0 + i] : 0.f;
+        }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = *tmem_slot;
-
 
     if (warp == 0) {
         // ===================== activation-plane producer =====================
@@ -154,14 +163,14 @@ conv3d_umma_kernel(const __grid_constant__ CUtensorMap xmap, const ConvParams P)
             int n, h0, w0, d0, td;
             while (tw_.next(n, h0, w0, d0, td)) {
                 int pmin, pmax;
-                plane_range(d0, td, P.D, pmin, pmax);
+                plane_range(d0, td, P.p_lo, P.p_hi, pmin, pmax);
                 for (int c = 0; c < nchunk; ++c) {
                     for (int p = pmin; p <= pmax; ++p, ++seq) {
                         const uint32_t slot = seq % P.ring, use = seq / P.ring;
                         if (!mbar_wait(plane_empty + 8 * slot, (use & 1) ^ 1)) { atomicExch(P.error_flag, 1); return; }
                         mbar_expect_tx(plane_full + 8 * slot, cu::PLANE_BYTES);
                         tma_load_5d(base + L.plane_off + slot * cu::PLANE_BYTES, &xmap, plane_full + 8 * slot, c * 32,
-                                    w0 - 2, h0 - 2, d0 + p - 2, n);
+                                    w0 - 2, h0 - 2, d0 + p - 2 + P.ext.x_off, n);
                     }
                 }
             }
@@ -208,7 +217,7 @@ conv3d_umma_kernel(const __grid_constant__ CUtensorMap xmap, const ConvParams P)
             int n, h0, w0, d0, td;
             for (int it = 0; tw_.next(n, h0, w0, d0, td); ++it) {
                 int pmin, pmax;
-                plane_range(d0, td, P.D, pmin, pmax);
+                plane_range(d0, td, P.p_lo, P.p_hi, pmin, pmax);
                 const int nplanes = pmax - pmin + 1;
                 const int buf = it & 1;
                 const uint32_t acc_base = tmem + buf * 256;
@@ -307,7 +316,7 @@ conv3d_umma_kernel(const __grid_constant__ CUtensorMap xmap, const ConvParams P)
             const int qn = td;
             const bool row_ok = h0 + th < P.H;          // H need not be a multiple of 16: rows past the volume are
             for (int q = 0; q < td; ++q) {              // computed (TMA zero fill) but neither stored nor counted
-                float* dst = P.y + ((((size_t)n * P.D + d0 + q) * P.H + h0 + th) * P.W + w0 + tw) * P.Nout + n0;
+                const size_t vox = (size_t)(h0 + th) * P.W + w0 + tw;
                 for (int cc = 0; cc < P.Nt; cc += 32) {
                     const uint32_t taddr = tmem + buf * 256 + q * P.Nt + cc + lane_addr;
                     if (q < qn) {
@@ -316,11 +325,38 @@ conv3d_umma_kernel(const __grid_constant__ CUtensorMap xmap, const ConvParams P)
                         tmem_ld_wait();
                         float f[32];
 #pragma unroll
-                        for (int j = 0; j < 32; ++j) f[j] = row_ok ? __uint_as_float(v[j]) * scale : 0.f;
-                        if (row_ok) {
+                        for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]) * scale;
+                        if (has_ep) {
 #pragma unroll
-                            for (int j = 0; j < 32; j += 4)
-                                *reinterpret_cast<float4*>(dst + cc + j) = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
+                            for (int j = 0; j < 32; ++j) f[j] = fmaf(f[j], s_ep[cc + j], s_ep[P.Nt + cc + j]);
+                        }
+                        if (P.ext.relu) {
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.f);
+                        }
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) f[j] = row_ok ? f[j] : 0.f;
+                        if (row_ok) {
+                            if (P.y != nullptr) {
+                                float* dst = P.y + ((((size_t)n * P.D + d0 + q) * P.H) * P.W + vox) * P.Nout + n0 + cc;
+#pragma unroll
+                                for (int j = 0; j < 32; j += 4)
+                                    *reinterpret_cast<float4*>(dst + j) = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
+                            }
+                            if (P.ext.y16 != nullptr) {
+                                __half* d16 = P.ext.y16 + ((((size_t)n * P.ext.Dy16 + d0 + q + P.ext.y16_off) * P.H) * P.W + vox) *
+                                                              P.Nout + n0 + cc;
+                                const float s16 = P.ext.y16_scale;
+#pragma unroll
+                                for (int j = 0; j < 32; j += 8) {
+                                    __half2 h0_ = sat_half2(f[j] * s16, f[j + 1] * s16), h1_ = sat_half2(f[j + 2] * s16, f[j + 3] * s16);
+                                    __half2 h2_ = sat_half2(f[j + 4] * s16, f[j + 5] * s16), h3_ = sat_half2(f[j + 6] * s16, f[j + 7] * s16);
+                                    uint4 pk;
+                                    pk.x = *reinterpret_cast<uint32_t*>(&h0_); pk.y = *reinterpret_cast<uint32_t*>(&h1_);
+                                    pk.z = *reinterpret_cast<uint32_t*>(&h2_); pk.w = *reinterpret_cast<uint32_t*>(&h3_);
+                                    *reinterpret_cast<uint4*>(d16 + j) = pk;
+                                }
+                            }
                         }
                         if (P.bn_sums != nullptr && d0 + q >= P.stat_lo && d0 + q < P.stat_hi) {
                             float g[32];
@@ -405,8 +441,8 @@ int make_act_map(CUtensorMap* map, const __half* x, int N, int D, int H, int W, 
 // ---- cost-balanced unit partition (host) ---------------------------------------------------------------------
 // Estimated MMA-issue cycles of a tile of td output planes (measured SS-mode cost max(92.7, 41.7 + N/2) per MMA,
 // two K-steps x 25 taps per 32-channel chunk) plus a fixed per-tile overhead (pipeline refill, epilogue hand-off).
-static double tile_cost(int td, int d0, int D, int Nt, int nchunk) {
-    const int pmin = std::max(0, 2 - d0), pmax = std::min(td + 3, D + 1 - d0);
+static double tile_cost(int td, int d0, int p_lo, int p_hi, int Nt, int nchunk) {
+    const int pmin = std::max(0, p_lo + 2 - d0), pmax = std::min(td + 3, p_hi + 2 - d0);
     double c = 0;
     for (int p = pmin; p <= pmax; ++p) {
         const int nq = std::min(td - 1, p) - std::max(0, p - 4) + 1;
@@ -416,34 +452,34 @@ static double tile_cost(int td, int d0, int D, int Nt, int nchunk) {
 }
 
 // Walk units from `u` taking whole tiles while the accumulated cost stays <= budget; the last tile may be shortened.
-static int64_t take_units(int64_t u, int64_t units, int D, int TD, int Nt, int nchunk, double budget) {
+static int64_t take_units(int64_t u, int64_t units, int D, int p_lo, int p_hi, int TD, int Nt, int nchunk, double budget) {
     double acc = 0;
     while (u < units) {
         const int d0 = (int)(u % D);
         const int full = std::min(TD, D - d0);
-        const double cf = tile_cost(full, d0, D, Nt, nchunk);
+        const double cf = tile_cost(full, d0, p_lo, p_hi, Nt, nchunk);
         if (acc + cf <= budget) { acc += cf; u += full; continue; }
         int best = 0;                                   // largest shortened tile that still fits
         for (int td = full - 1; td >= 1; --td)
-            if (acc + tile_cost(td, d0, D, Nt, nchunk) <= budget) { best = td; break; }
+            if (acc + tile_cost(td, d0, p_lo, p_hi, Nt, nchunk) <= budget) { best = td; break; }
         u += best;
         break;
     }
     return u;
 }
 
-static void partition_units_uncached(int64_t units, int D, int TD, int Nt, int nchunk, int G, int32_t* bounds) {
+static void partition_units_uncached(int64_t units, int D, int p_lo, int p_hi, int TD, int Nt, int nchunk, int G, int32_t* bounds) {
     double lo = 0, hi = 0;
     for (int64_t u = 0; u < units;) {                   // upper bound: everything on one CTA
         const int d0 = (int)(u % D), full = std::min(TD, D - d0);
-        hi += tile_cost(full, d0, D, Nt, nchunk);
+        hi += tile_cost(full, d0, p_lo, p_hi, Nt, nchunk);
         u += full;
     }
     lo = hi / G;
     auto feasible = [&](double budget) {
         int64_t u = 0;
         for (int c = 0; c < G && u < units; ++c) {
-            const int64_t nu = take_units(u, units, D, TD, Nt, nchunk, budget);
+            const int64_t nu = take_units(u, units, D, p_lo, p_hi, TD, Nt, nchunk, budget);
             if (nu == u) return false;
             u = nu;
         }
@@ -459,27 +495,28 @@ static void partition_units_uncached(int64_t units, int D, int TD, int Nt, int n
     int64_t u = 0;
     for (int c = 0; c < G; ++c) {
         bounds[c] = (int32_t)u;
-        u = std::min(units, take_units(u, units, D, TD, Nt, nchunk, h));
+        u = std::min(units, take_units(u, units, D, p_lo, p_hi, TD, Nt, nchunk, h));
     }
     bounds[G] = (int32_t)units;
 }
 
 // The partition costs ~0.4 ms of host time; it depends on the layer shape only, so it is computed once per shape.
-static void partition_units(int64_t units, int D, int TD, int Nt, int nchunk, int G, int32_t* bounds) {
+static void partition_units(int64_t units, int D, int p_lo, int p_hi, int TD, int Nt, int nchunk, int G, int32_t* bounds) {
     struct Key {
-        int64_t units; int D, TD, Nt, nchunk, G;
+        int64_t units; int D, p_lo, p_hi, TD, Nt, nchunk, G;
         bool operator<(const Key& o) const {
-            return std::tie(units, D, TD, Nt, nchunk, G) < std::tie(o.units, o.D, o.TD, o.Nt, o.nchunk, o.G);
+            return std::tie(units, D, p_lo, p_hi, TD, Nt, nchunk, G) <
+                   std::tie(o.units, o.D, o.p_lo, o.p_hi, o.TD, o.Nt, o.nchunk, o.G);
         }
     };
     static std::mutex mu;
     static std::map<Key, std::array<int32_t, 160>> cache;
-    const Key key{units, D, TD, Nt, nchunk, G};
+    const Key key{units, D, p_lo, p_hi, TD, Nt, nchunk, G};
     std::lock_guard<std::mutex> lock(mu);
     auto it = cache.find(key);
     if (it == cache.end()) {
         std::array<int32_t, 160> b{};
-        partition_units_uncached(units, D, TD, Nt, nchunk, G, b.data());
+        partition_units_uncached(units, D, p_lo, p_hi, TD, Nt, nchunk, G, b.data());
         it = cache.emplace(key, b).first;
     }
     std::copy(it->second.begin(), it->second.end(), bounds);
@@ -494,15 +531,17 @@ bool conv3d_umma_supported(int D, int H, int W, int K, int Nout) {
 
 int conv3d_umma(const __half* x, const __half* w, const int32_t* sample_u, float* y, int N, int D, int H, int W, int K,
                 int Nout, float out_scale, const float* out_scale_dev, double* bn_sums, int stat_lo, int stat_hi,
-                cudaStream_t st) {
+                const ConvExt& ext, cudaStream_t st) {
     if ((reinterpret_cast<uintptr_t>(x) & 15) || (reinterpret_cast<uintptr_t>(w) & 15) ||
-        (reinterpret_cast<uintptr_t>(y) & 15))
+        (reinterpret_cast<uintptr_t>(y) & 15) || (reinterpret_cast<uintptr_t>(ext.y16) & 15))
         MODE_FAIL("conv3d_umma: pointers must be 16-byte aligned");
     ConvParams P;
     P.w = w; P.sample_u = sample_u; P.y = y; P.bn_sums = bn_sums; P.out_scale_dev = out_scale_dev;
     P.out_scale = out_scale;
     P.N = N; P.D = D; P.H = H; P.W = W; P.K = K; P.Nout = Nout;
     P.stat_lo = stat_lo; P.stat_hi = stat_hi;
+    P.ext = ext;
+    P.p_lo = ext.p_lo(); P.p_hi = ext.p_hi();
     // Output channels per CTA: as wide as TMEM allows (<= 128) when the volume alone fills the GPU; narrower for the
     // deep, small-volume layers so that (tiles x channel passes) still spreads over the SMs.
     P.units = (int64_t)N * (int64_t)ceil_div(H, cu::TH) * (W / cu::TW) * D;
@@ -531,10 +570,10 @@ int conv3d_umma(const __half* x, const __half* w, const int32_t* sample_u, float
     P.prof = debug_profile_buffer();
 
     CUtensorMap xmap;
-    if (make_act_map(&xmap, x, N, D, H, W, K, cu::BW, cu::BH, 1) != 0) return -1;
+    if (make_act_map(&xmap, x, N, ext.Dx, H, W, K, cu::BW, cu::BH, 1) != 0) return -1;
     MODE_CUDA(cudaFuncSetAttribute(conv3d_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
     const int grid = total < (int64_t)sm_count() ? (int)total : std::min(sm_count(), 159);
-    partition_units(P.units, D, P.TD, P.Nt, K / 32, grid, P.bounds);
+    partition_units(P.units, D, P.p_lo, P.p_hi, P.TD, P.Nt, K / 32, grid, P.bounds);
     conv3d_umma_kernel<<<dim3(grid, Nout / P.Nt), cu::THREADS, smem_bytes, st>>>(xmap, P);
     MODE_LAUNCH_CHECK();
     return 0;

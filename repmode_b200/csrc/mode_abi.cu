@@ -48,45 +48,36 @@ long long* debug_profile_buffer() { return g_prof; }
 // conv_simt.cu
 int conv3d_simt(const float* x, const float* w, const int32_t* sample_u, float* y, int N, int D, int H, int W, int K,
                 int Nout, float out_scale, const float* out_scale_dev, double* bn_sums, int stat_lo, int stat_hi,
-                cudaStream_t st);
+                const ConvExt& ext, cudaStream_t st);
 int wgrad_simt(const float* x, const float* dy, float* dw, int N, int D, int H, int W, int Ci, int Co, float out_scale,
-               const float* out_scale_dev, cudaStream_t st);
+               const float* out_scale_dev, int Dx, int x_off, cudaStream_t st);
 // conv_umma.cu
 bool conv3d_umma_supported(int D, int H, int W, int K, int Nout);
 int conv3d_umma(const __half* x, const __half* w, const int32_t* sample_u, float* y, int N, int D, int H, int W, int K,
                 int Nout, float out_scale, const float* out_scale_dev, double* bn_sums, int stat_lo, int stat_hi,
-                cudaStream_t st);
+                const ConvExt& ext, cudaStream_t st);
 // conv_pair.cu
 bool conv3d_pair_supported(int N, int D, int H, int W, int K, int Nout);
 int conv3d_pair(const __half* x, const __half* w, const int32_t* sample_u, float* y, int N, int D, int H, int W, int K,
                 int Nout, float out_scale, const float* out_scale_dev, double* bn_sums, int stat_lo, int stat_hi,
-                cudaStream_t st);
-bool wgrad_umma_supported(int D, int H, int W, int Ci, int Co);
-int64_t wgrad_umma_workspace_bytes(int N, int D, int H, int W, int Ci, int Co);
-int wgrad_umma(const __half* x, const __half* dy, float* dw, int N, int D, int H, int W, int Ci, int Co,
-               float out_scale, const float* out_scale_dev, void* workspace, cudaStream_t st);
-
+                const ConvExt& ext, cudaStream_t st);
 // wgrad_split.cu
 bool wgrad_split_supported(int D, int H, int W, int Ci, int Co);
 int64_t wgrad_split_workspace_bytes(int N, int D, int H, int W, int Ci, int Co);
 int wgrad_split(const __half* x, const __half* dy, float* dw, int N, int D, int H, int W, int Ci, int Co,
                 float out_scale, const float* out_scale_dev, void* workspace, cudaStream_t st);
 
-// wgrad_deep.cu (experimental)
+// wgrad_deep.cu
 bool wgrad_deep_supported(int D, int H, int W, int Ci, int Co);
-int64_t wgrad_deep_workspace_bytes(int N, int D, int H, int W, int Ci, int Co);
+int64_t wgrad_deep_workspace_bytes(int N, int D, int H, int W, int Ci, int Co, int Dx, int x_off);
 int wgrad_deep(const __half* x, const __half* dy, float* dw, int N, int D, int H, int W, int Ci, int Co,
-               float out_scale, const float* out_scale_dev, void* workspace, cudaStream_t st);
-static bool wgrad_use_deep() {
-    static const bool deep = getenv("REPMODE_WGRAD_DEEP") != nullptr;
-    return deep;
-}
+               float out_scale, const float* out_scale_dev, void* workspace, int Dx, int x_off, cudaStream_t st);
 
-// tcgen05 wgrad flavour behind impl = 2: the split-tap kernel (7 MMAs per K step; measured r1g 135 us against 146 us for
-// the stacked-tap kernel on the headline layer); REPMODE_WGRAD_STACKED=1 selects the stacked-tap kernel (10 MMAs per K step)
-static bool wgrad_use_split() {
-    static const bool stacked = getenv("REPMODE_WGRAD_STACKED") != nullptr;
-    return !stacked;
+// tcgen05 wgrad flavour behind impl = 2: the deep-tile kernel (wgrad_deep.cu; r2a on the headline layer: 112 us against
+// 135 us for the split-tap kernel of round 1); REPMODE_WGRAD_SPLIT=1 selects wgrad_split.cu (the A/B arm)
+static bool wgrad_use_deep() {
+    static const bool split = getenv("REPMODE_WGRAD_SPLIT") != nullptr;
+    return !split;
 }
 
 }  // namespace mode
@@ -128,17 +119,31 @@ extern "C" int mode_debug_profile(void* buf) {
     return 0;
 }
 
-extern "C" int mode_conv3d(const void* x, mode_dtype_t x_dtype, const void* w, const int32_t* sample_u, float* y,
-                           int32_t N, int32_t D, int32_t H, int32_t W, int32_t K, int32_t Nout, float out_scale,
-                           const float* out_scale_dev, double* bn_sums, int32_t stat_d_lo, int32_t stat_d_hi,
-                           int32_t impl, void* stream) {
-    if (!x || !w || !y) MODE_FAIL("mode_conv3d: null pointer");
+extern "C" int mode_conv3d_ex(const void* x, mode_dtype_t x_dtype, const void* w, const int32_t* sample_u, float* y,
+                              int32_t N, int32_t D, int32_t H, int32_t W, int32_t K, int32_t Nout, float out_scale,
+                              const float* out_scale_dev, double* bn_sums, int32_t stat_d_lo, int32_t stat_d_hi,
+                              int32_t impl, const mode_conv_opts_t* opts, void* stream) {
+    ConvExt ext;
+    ext.Dx = (opts && opts->Dx > 0) ? opts->Dx : D;
+    ext.x_off = opts ? opts->x_off : 0;
+    ext.ep_scale = opts ? opts->ep_scale : nullptr;
+    ext.ep_shift = opts ? opts->ep_shift : nullptr;
+    ext.relu = opts ? opts->relu : 0;
+    ext.y16 = opts ? (__half*)opts->y16 : nullptr;
+    ext.Dy16 = (opts && opts->Dy16 > 0) ? opts->Dy16 : D;
+    ext.y16_off = opts ? opts->y16_off : 0;
+    ext.y16_scale = (opts && opts->y16_scale != 0.f) ? opts->y16_scale : 1.f;
+    if (!x || !w || (!y && !ext.y16)) MODE_FAIL("mode_conv3d: null pointer");
     if (N <= 0 || D <= 0 || H <= 0 || W <= 0 || K <= 0 || Nout <= 0) MODE_FAIL("mode_conv3d: non-positive dimension");
+    if (ext.x_off < 0 || ext.x_off + D > ext.Dx)
+        MODE_FAIL("mode_conv3d: haloed input needs 0 <= x_off and x_off + D <= Dx (x_off=%d D=%d Dx=%d)", ext.x_off, D, ext.Dx);
+    if (ext.y16 && (ext.y16_off < 0 || ext.y16_off + D > ext.Dy16))
+        MODE_FAIL("mode_conv3d: y16 plane window out of range (y16_off=%d D=%d Dy16=%d)", ext.y16_off, D, ext.Dy16);
     cudaStream_t st = (cudaStream_t)stream;
     if (impl == 0) impl = (x_dtype == MODE_F16) ? 2 : 1;
     if (impl == 1) {
         if (x_dtype != MODE_F32) MODE_FAIL("mode_conv3d: the SIMT path takes fp32 operands");
-        return conv3d_simt((const float*)x, (const float*)w, sample_u, y, N, D, H, W, K, Nout, out_scale, out_scale_dev, bn_sums, stat_d_lo, stat_d_hi, st);
+        return conv3d_simt((const float*)x, (const float*)w, sample_u, y, N, D, H, W, K, Nout, out_scale, out_scale_dev, bn_sums, stat_d_lo, stat_d_hi, ext, st);
     }
     if (impl == 2 || impl == 3 || impl == 4) {
         if (x_dtype != MODE_F16) MODE_FAIL("mode_conv3d: the tcgen05 path takes fp16 operands");
@@ -147,41 +152,58 @@ extern "C" int mode_conv3d(const void* x, mode_dtype_t x_dtype, const void* w, c
         static const bool no_pair = getenv("REPMODE_DISABLE_PAIR") != nullptr;
         // 2: CTA-pair kernel when every cluster gets a long enough march, else the single-CTA kernel; 3 / 4 force one
         if (impl == 4 || (impl == 2 && !no_pair && conv3d_pair_supported(N, D, H, W, K, Nout)))
-            return conv3d_pair((const __half*)x, (const __half*)w, sample_u, y, N, D, H, W, K, Nout, out_scale, out_scale_dev, bn_sums, stat_d_lo, stat_d_hi, st);
-        return conv3d_umma((const __half*)x, (const __half*)w, sample_u, y, N, D, H, W, K, Nout, out_scale, out_scale_dev, bn_sums, stat_d_lo, stat_d_hi, st);
+            return conv3d_pair((const __half*)x, (const __half*)w, sample_u, y, N, D, H, W, K, Nout, out_scale, out_scale_dev, bn_sums, stat_d_lo, stat_d_hi, ext, st);
+        return conv3d_umma((const __half*)x, (const __half*)w, sample_u, y, N, D, H, W, K, Nout, out_scale, out_scale_dev, bn_sums, stat_d_lo, stat_d_hi, ext, st);
     }
     MODE_FAIL("mode_conv3d: unknown impl %d", impl);
 }
 
+extern "C" int mode_conv3d(const void* x, mode_dtype_t x_dtype, const void* w, const int32_t* sample_u, float* y,
+                           int32_t N, int32_t D, int32_t H, int32_t W, int32_t K, int32_t Nout, float out_scale,
+                           const float* out_scale_dev, double* bn_sums, int32_t stat_d_lo, int32_t stat_d_hi,
+                           int32_t impl, void* stream) {
+    return mode_conv3d_ex(x, x_dtype, w, sample_u, y, N, D, H, W, K, Nout, out_scale, out_scale_dev, bn_sums, stat_d_lo,
+                          stat_d_hi, impl, nullptr, stream);
+}
+
 extern "C" int64_t mode_conv3d_wgrad_workspace_bytes(int32_t N, int32_t D, int32_t H, int32_t W, int32_t Ci, int32_t Co,
                                                      int32_t impl) {
-    if (impl == 6 || (impl == 2 && wgrad_use_deep())) return wgrad_deep_workspace_bytes(N, D, H, W, Ci, Co);
-    if (impl == 5 || (impl == 2 && wgrad_use_split())) return wgrad_split_workspace_bytes(N, D, H, W, Ci, Co);
-    if (impl == 2 || impl == 3) return wgrad_umma_workspace_bytes(N, D, H, W, Ci, Co);
+    if (impl == 6 || (impl == 2 && wgrad_use_deep())) return wgrad_deep_workspace_bytes(N, D, H, W, Ci, Co, D, 0);
+    if (impl == 5 || impl == 2) return wgrad_split_workspace_bytes(N, D, H, W, Ci, Co);
     return 0;
+}
+
+extern "C" int mode_conv3d_wgrad_ex(const void* x, const void* dy, mode_dtype_t dtype, float* d_weff, int32_t N,
+                                    int32_t D, int32_t H, int32_t W, int32_t Ci, int32_t Co, float out_scale,
+                                    const float* out_scale_dev, void* workspace, int32_t impl, int32_t Dx, int32_t x_off,
+                                    void* stream) {
+    if (!x || !dy || !d_weff) MODE_FAIL("mode_conv3d_wgrad: null pointer");
+    if (N <= 0 || D <= 0 || H <= 0 || W <= 0 || Ci <= 0 || Co <= 0) MODE_FAIL("mode_conv3d_wgrad: non-positive dimension");
+    if (Dx <= 0) { Dx = D; x_off = 0; }
+    if (x_off < 0 || x_off + D > Dx)
+        MODE_FAIL("mode_conv3d_wgrad: haloed x needs 0 <= x_off and x_off + D <= Dx (x_off=%d D=%d Dx=%d)", x_off, D, Dx);
+    const bool halo = Dx != D || x_off != 0;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (impl == 0) impl = (dtype == MODE_F16) ? 2 : 1;
+    if (impl == 1) {
+        if (dtype != MODE_F32) MODE_FAIL("mode_conv3d_wgrad: the SIMT path takes fp32 operands");
+        return wgrad_simt((const float*)x, (const float*)dy, d_weff, N, D, H, W, Ci, Co, out_scale, out_scale_dev, Dx, x_off, st);
+    }
+    if (impl == 2 || impl == 5 || impl == 6) {
+        if (dtype != MODE_F16) MODE_FAIL("mode_conv3d_wgrad: the tcgen05 path takes fp16 operands");
+        if (!wgrad_deep_supported(D, H, W, Ci, Co) || !wgrad_split_supported(D, H, W, Ci, Co))
+            MODE_FAIL("mode_conv3d_wgrad: shape not supported by the tcgen05 path");
+        // 2: deep-tile kernel unless REPMODE_WGRAD_SPLIT; 5 / 6 force the split-tap / the deep-tile kernel
+        if (impl == 6 || (impl == 2 && (wgrad_use_deep() || halo)))
+            return wgrad_deep((const __half*)x, (const __half*)dy, d_weff, N, D, H, W, Ci, Co, out_scale, out_scale_dev, workspace, Dx, x_off, st);
+        if (halo) MODE_FAIL("mode_conv3d_wgrad: the split-tap kernel (impl 5) does not take a haloed x");
+        return wgrad_split((const __half*)x, (const __half*)dy, d_weff, N, D, H, W, Ci, Co, out_scale, out_scale_dev, workspace, st);
+    }
+    MODE_FAIL("mode_conv3d_wgrad: unknown impl %d", impl);
 }
 
 extern "C" int mode_conv3d_wgrad(const void* x, const void* dy, mode_dtype_t dtype, float* d_weff, int32_t N,
                                  int32_t D, int32_t H, int32_t W, int32_t Ci, int32_t Co, float out_scale,
                                  const float* out_scale_dev, void* workspace, int32_t impl, void* stream) {
-    if (!x || !dy || !d_weff) MODE_FAIL("mode_conv3d_wgrad: null pointer");
-    if (N <= 0 || D <= 0 || H <= 0 || W <= 0 || Ci <= 0 || Co <= 0) MODE_FAIL("mode_conv3d_wgrad: non-positive dimension");
-    cudaStream_t st = (cudaStream_t)stream;
-    if (impl == 0) impl = (dtype == MODE_F16) ? 2 : 1;
-    if (impl == 1) {
-        if (dtype != MODE_F32) MODE_FAIL("mode_conv3d_wgrad: the SIMT path takes fp32 operands");
-        return wgrad_simt((const float*)x, (const float*)dy, d_weff, N, D, H, W, Ci, Co, out_scale, out_scale_dev, st);
-    }
-    if (impl == 2 || impl == 3 || impl == 5 || impl == 6) {
-        if (dtype != MODE_F16) MODE_FAIL("mode_conv3d_wgrad: the tcgen05 path takes fp16 operands");
-        if (!wgrad_umma_supported(D, H, W, Ci, Co) || !wgrad_split_supported(D, H, W, Ci, Co))
-            MODE_FAIL("mode_conv3d_wgrad: shape not supported by the tcgen05 path");
-        // 2: split-tap kernel (7 MMAs per K step) unless REPMODE_WGRAD_STACKED; 3 / 5 force the stacked / the split-tap kernel
-        if (impl == 6 || (impl == 2 && wgrad_use_deep()))      // experimental deep-tile variant (REPMODE_WGRAD_DEEP=1)
-            return wgrad_deep((const __half*)x, (const __half*)dy, d_weff, N, D, H, W, Ci, Co, out_scale, out_scale_dev, workspace, st);
-        if (impl == 5 || (impl == 2 && wgrad_use_split()))
-            return wgrad_split((const __half*)x, (const __half*)dy, d_weff, N, D, H, W, Ci, Co, out_scale, out_scale_dev, workspace, st);
-        return wgrad_umma((const __half*)x, (const __half*)dy, d_weff, N, D, H, W, Ci, Co, out_scale, out_scale_dev, workspace, st);
-    }
-    MODE_FAIL("mode_conv3d_wgrad: unknown impl %d", impl);
+    return mode_conv3d_wgrad_ex(x, dy, dtype, d_weff, N, D, H, W, Ci, Co, out_scale, out_scale_dev, workspace, impl, 0, 0, stream);
 }

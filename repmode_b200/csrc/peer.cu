@@ -1,0 +1,166 @@
+// Peer-memory exchange steps of the D-sharded MoDE-conv path over NVLink / NVSwitch: halo planes,
+// BatchNorm partial sums and parameter gradients move between the GPUs of one box by plain stores into the neighbour's
+// memory (CUDA IPC mappings, set up by the host side) plus a release/acquire counter -- no NCCL launch on the data path.
+// The reference has no multi-GPU data path to mirror (fnet/fnet_model.py:40-44 is torch.nn.DataParallel); the spec is
+// one halo exchange per stage, BatchNorm statistics over owned voxels, gradient sum.
+//
+// Protocol (all counters are monotonically increasing uint32 in device memory, so a CUDA graph can replay the step):
+//   producer: writes the payload into the consumer's buffer, __threadfence_system(), then the LAST block of the launch (a
+//             ticket counter in the producer's own memory) does atomicAdd_system(consumer_signal, 1).
+//   consumer: `expect` (its own device counter) += number of producers; spins until signal >= expect with acquire loads.
+//             A wait that does not complete within ~10 s raises the device error flag (code 41) instead of hanging the box.
+// Buffers are reused every step; the write-after-read hazard is closed by the step's own data dependencies (nobody starts
+// step s+1 before the gradient exchange of step s, which every rank enters only after its last read of step s' halos).
+// HBM/NVLink-bound copies: 16-byte vector accesses, grid sized to the payload.
+#include <algorithm>
+
+#include "common.cuh"
+
+namespace mode {
+
+int* device_error_flag();   // mode_abi.cu
+
+__device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
+    uint32_t v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ uint64_t peer_timer_ns() {
+    uint64_t t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+
+// Spin until *signal - base >= want (wrap-safe); false on timeout.
+__device__ __forceinline__ bool wait_signal(const uint32_t* signal, uint32_t target) {
+    const uint64_t t0 = peer_timer_ns();
+    while ((int32_t)(ld_acquire_sys(signal) - target) < 0) {
+        __nanosleep(64);
+        if (peer_timer_ns() - t0 > 10000000000ull) return false;
+    }
+    return true;
+}
+
+// The last block of a launch signals: every block fences its payload stores, takes a ticket; the block that takes the last
+// ticket resets the counter (so the next launch / graph replay starts from 0) and increments the consumer's signal(s).
+struct SignalList { uint32_t* p[8]; int n; };
+__device__ __forceinline__ void finish_and_signal(uint32_t* ticket, const SignalList& sig) {
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const uint32_t total = gridDim.x * gridDim.y * gridDim.z;
+        if (atomicAdd(ticket, 1u) == total - 1) {
+            *ticket = 0;
+            __threadfence_system();
+            for (int i = 0; i < sig.n; ++i) atomicAdd_system(sig.p[i], 1u);
+        }
+    }
+}
+
+// ---- put: up to 8 (src -> dst) segments of equal size, one signal per segment ---------------------------------------
+struct PutList { const uint4* src[8]; uint4* dst[8]; uint32_t* sig[8]; int n; long long vec; };
+__global__ void __launch_bounds__(256) peer_put_kernel(PutList L, uint32_t* ticket) {
+    const int seg = blockIdx.y;
+    const uint4* __restrict__ s = L.src[seg];
+    uint4* __restrict__ d = L.dst[seg];
+    for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < L.vec; i += (long long)gridDim.x * 256) d[i] = s[i];
+    SignalList sg;
+    sg.n = L.n;
+    for (int i = 0; i < 8; ++i) sg.p[i] = L.sig[i];
+    finish_and_signal(ticket, sg);
+}
+
+__global__ void peer_wait_kernel(const uint32_t* signal, uint32_t* expect, uint32_t add, int* error_flag) {
+    const uint32_t target = *expect + add;
+    *expect = target;
+    if (!wait_signal(signal, target)) atomicExch(error_flag, 41);
+}
+
+// ---- one-shot all-reduce: every rank holds slots[world][n]; sum in rank order (deterministic) after all arrived ---------
+template <typename T>
+__global__ void __launch_bounds__(256) peer_sum_slots_kernel(const T* __restrict__ slots, int world, long long n,
+                                                             T* __restrict__ out, const uint32_t* signal, uint32_t* expect,
+                                                             uint32_t* ticket, int* error_flag) {
+    __shared__ uint32_t s_target;
+    __shared__ int s_ok;
+    if (threadIdx.x == 0) {
+        s_target = *expect + (uint32_t)world;
+        s_ok = wait_signal(signal, s_target) ? 1 : 0;
+        if (!s_ok) atomicExch(error_flag, 42);
+    }
+    __syncthreads();
+    for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < n; i += (long long)gridDim.x * 256) {
+        T a = slots[i];
+        for (int r = 1; r < world; ++r) a += slots[(long long)r * n + i];
+        out[i] = a;
+    }
+    // the last block to finish advances `expect` (all blocks read the same old value above)
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        if (atomicAdd(ticket, 1u) == gridDim.x - 1) { *ticket = 0; *expect = s_target; }
+    }
+}
+
+}  // namespace mode
+
+using namespace mode;
+
+extern "C" int mode_peer_enable_access(int32_t peer_device) {
+    int dev = 0;
+    MODE_CUDA(cudaGetDevice(&dev));
+    if (peer_device == dev) return 0;
+    int can = 0;
+    MODE_CUDA(cudaDeviceCanAccessPeer(&can, dev, peer_device));
+    if (!can) MODE_FAIL("mode_peer_enable_access: device %d cannot access device %d (no NVLink / P2P path)", dev, peer_device);
+    cudaError_t e = cudaDeviceEnablePeerAccess(peer_device, 0);
+    if (e == cudaErrorPeerAccessAlreadyEnabled) { cudaGetLastError(); return 0; }
+    MODE_CUDA(e);
+    return 0;
+}
+
+extern "C" int mode_peer_put(const void* const* src_host, void* const* dst_host, void* const* signal_host, int32_t n,
+                             int64_t bytes, void* ticket, void* stream) {
+    if (!src_host || !dst_host || !signal_host || !ticket || n <= 0 || n > 8 || bytes <= 0 || (bytes & 15))
+        MODE_FAIL("mode_peer_put: bad arguments (n=%d bytes=%lld; bytes must be a multiple of 16)", n, (long long)bytes);
+    PutList L;
+    L.n = n;
+    L.vec = bytes / 16;
+    for (int i = 0; i < 8; ++i) {
+        L.src[i] = i < n ? (const uint4*)src_host[i] : nullptr;
+        L.dst[i] = i < n ? (uint4*)dst_host[i] : nullptr;
+        L.sig[i] = i < n ? (uint32_t*)signal_host[i] : nullptr;
+        if (i < n && (!L.src[i] || !L.dst[i] || !L.sig[i] || ((uintptr_t)L.src[i] & 15) || ((uintptr_t)L.dst[i] & 15)))
+            MODE_FAIL("mode_peer_put: null or misaligned segment %d", i);
+    }
+    const int gx = (int)std::max<int64_t>(1, std::min<int64_t>(ceil_div(L.vec, 256 * 4), 2 * sm_count() / n + 1));
+    peer_put_kernel<<<dim3(gx, n), 256, 0, (cudaStream_t)stream>>>(L, (uint32_t*)ticket);
+    MODE_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int mode_peer_wait(const void* signal, void* expect, int32_t add, void* stream) {
+    if (!signal || !expect || add <= 0) MODE_FAIL("mode_peer_wait: bad arguments");
+    int* ef = device_error_flag();
+    if (!ef) MODE_FAIL("mode_peer_wait: could not allocate the device error flag");
+    peer_wait_kernel<<<1, 1, 0, (cudaStream_t)stream>>>((const uint32_t*)signal, (uint32_t*)expect, (uint32_t)add, ef);
+    MODE_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int mode_peer_sum_slots(const void* slots, int32_t world, int64_t n, int32_t is_double, void* out,
+                                   const void* signal, void* expect, void* ticket, void* stream) {
+    if (!slots || !out || !signal || !expect || !ticket || world <= 0 || n <= 0) MODE_FAIL("mode_peer_sum_slots: bad arguments");
+    int* ef = device_error_flag();
+    if (!ef) MODE_FAIL("mode_peer_sum_slots: could not allocate the device error flag");
+    const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(ceil_div(n, 256), sm_count()));
+    if (is_double)
+        peer_sum_slots_kernel<double><<<grid, 256, 0, (cudaStream_t)stream>>>((const double*)slots, world, n, (double*)out,
+                                                                            (const uint32_t*)signal, (uint32_t*)expect,
+                                                                            (uint32_t*)ticket, ef);
+    else
+        peer_sum_slots_kernel<float><<<grid, 256, 0, (cudaStream_t)stream>>>((const float*)slots, world, n, (float*)out,
+                                                                           (const uint32_t*)signal, (uint32_t*)expect,
+                                                                           (uint32_t*)ticket, ef);
+    MODE_LAUNCH_CHECK();
+    return 0;
+}

@@ -1,17 +1,20 @@
-// K4, split-tap wgrad with DEEP tiles -- EXPERIMENTAL, not selected by default and NOT YET RUN ON A GPU (written at the end of
-// round 1 after the GPU budget was spent; opt in with REPMODE_WGRAD_DEEP=1 or impl = 6; tests/test_gpu_umma.py covers it
-// under REPMODE_TEST_EXPERIMENTAL=1).  Same arithmetic and tap cover as wgrad_split.cu:
+// K4 (default): wgrad of the 5x5x5 conv on tcgen05, split-tap cover with DEEP tiles.
 //   d_weff[n][tap][o][i] = sum_p dy[n][p][o] * x[n][p + tap - 2][i]      (autograd of RepMode.py:207)
+// Same arithmetic and tap cover as wgrad_split.cu (the round-1 kernel, kept as the A/B arm REPMODE_WGRAD_SPLIT=1 / impl 5):
+// taps are stacked through overlapping MN-major views of the same shared-memory bricks -- A = dy brick seen through 4 M
+// blocks (row shifts -> kh, or plane shifts -> kd for the kh = 4 units), B = x brick seen through 5 N blocks (voxel shifts ->
+// kw) -- so one M128 N160 K16 MMA accumulates 20 taps.
 //
-// Why: the r1g capture of wgrad_split_kernel fits a per-SM TMA model of ~300 cycles per bulk-tensor request plus ~48 B/clk
-// (profiles/README.md): a tile of 2-3 requests / 22-35 KB feeding only 8-16 MMAs (648-1296 cycles of
-// tensor work) is REQUEST-bound -- the K units run at 115-140 cycles per MMA -- while the L units (3 requests, 74 KB, 32
-// MMAs) run at the tensor pipe's own 80.  So every unit kind here gets >= 32 MMAs per 2 requests:
+// Why deep tiles: the r1g capture of wgrad_split_kernel fits a per-SM TMA model of ~300 cycles per bulk-tensor request plus
+// ~48 B/clk (profiles/README.md): a tile of 2-3 requests / 22-35 KB feeding only 8-16 MMAs (648-1296
+// cycles of tensor work) is REQUEST-bound -- the K units ran at 115-140 cycles per MMA -- while the L units (3 requests,
+// 74 KB, 32 MMAs) ran at the tensor pipe's own 80.  So every unit kind here gets >= 32 MMAs per 2 requests:
 //   A units: kh = 0..3 of kd 0,1   -- tile = 2 dy planes (one 2-plane box) x the 3 x planes they meet (one box): 32 MMAs
 //   B units: kh = 0..3 of kd 2,3,4 -- tile = 2 dy planes x 4 x planes: 48 MMAs, three accumulator sets (480 TMEM columns)
 //   L units: kh = 4 of all kd      -- as wgrad_split.cu, the two x planes in ONE box: 32 MMAs
 // Planes outside the volume are TMA zero fill and are multiplied like any other (~3 % extra MMAs) so that every tile of
 // a kind runs the same branch-free, fully unrolled, warp-uniform issue body.
+// Measured (r2a, headline layer 32 -> 32 @ 32x128x128): 109 us + 4 us reduce against 128 + 7 for wgrad_split.cu.
 // Roofline: tensor pipe; algorithmic work 2*125*Ci*Co FLOP per voxel.
 #include <cuda.h>
 
@@ -51,6 +54,7 @@ static_assert(OPERAND_BYTES + 512 + 1024 <= 227 * 1024, "shared memory budget");
 struct DeepParams {
     float* partial;                 // [units][ENTRIES][32][32]
     int N, D, H, W, Ci, Co;
+    int Dx, x_off;                  // haloed x: Dx planes, dy plane p is centred on x plane p + x_off (Dx = D, 0 without halo)
     int ncic, ncoc;
     int SL, SA, SB;                 // slabs per unit group of each kind
     int nL, nA;                     // unit counts: grid = [L units][A units][B units]
@@ -107,13 +111,16 @@ wgrad_deep_kernel(const __grid_constant__ CUtensorMap dymapK, const __grid_const
     // ---- the unit's tile walk (plane group, then tile row, then tile column) and this slab's share of it ----------
     int dlo, ngroups, tiles_h, nk_last;
     if (kind == 0) {
-        dlo = 0; ngroups = (P.D + 1) >> 1;                              // pairs of x planes
+        // x planes (dy coordinates) that meet a dy plane through a kh = 4 tap of some kd: [-2, D + 1] clipped to the tensor
+        dlo = max(-P.x_off, -2);
+        const int phi = min(P.Dx - P.x_off - 1, P.D + 1);
+        ngroups = (max(0, phi - dlo + 1) + 1) >> 1;                     // pairs of x planes
         tiles_h = P.tiles_hL;
         nk_last = min(8, (P.H - (tiles_h - 1) * wd::TH + 1) >> 1);
     } else {
         // dy planes d whose x plane d + kd - 2 lies inside the volume for at least one kd of the group, in pairs
-        dlo = max(0, 2 - (kd0 + nkd - 1));
-        const int dhi = min(P.D, P.D + 2 - kd0);
+        dlo = max(0, 2 - (kd0 + nkd - 1) - P.x_off);
+        const int dhi = min(P.D, P.Dx + 2 - P.x_off - kd0);
         ngroups = (max(0, dhi - dlo) + wd::PT - 1) / wd::PT;
         tiles_h = P.tiles_hK;
         nk_last = min(8, (P.H - ((tiles_h - 1) * wd::TH - 3) + 1) >> 1);
@@ -148,17 +155,17 @@ wgrad_deep_kernel(const __grid_constant__ CUtensorMap dymapK, const __grid_const
                 if (!mbar_wait(empty + 8 * st, (use & 1) ^ 1)) { atomicExch(P.error_flag, 31); return; }
                 const uint32_t dst = base + st * stage_bytes;
                 if (kind == 0) {
-                    const int p = 2 * tg, vh0 = th * wd::TH;
+                    const int p = dlo + 2 * tg, vh0 = th * wd::TH;
                     mbar_expect_tx(full + 8 * st, wd::L_DY_BYTES + 2 * wd::X_PLANE);
                     tma_load_5d(dst, &dymapL, full + 8 * st, coc * 32, vw0, vh0, p - 2, n);                    // dy planes p-2 .. p+3
-                    tma_load_5d(dst + wd::L_DY_BYTES, &xmapL, full + 8 * st, cic * 32, vw0 - 2, vh0 + 2, p, n); // x planes p, p+1
+                    tma_load_5d(dst + wd::L_DY_BYTES, &xmapL, full + 8 * st, cic * 32, vw0 - 2, vh0 + 2, p + P.x_off, n); // x planes p, p+1
                 } else {
                     const int d = dlo + wd::PT * tg, vh0 = th * wd::TH - 3;
                     const int nxp = wd::PT + nkd - 1;
                     mbar_expect_tx(full + 8 * st, wd::PT * wd::K_DY_PLANE + nxp * wd::X_PLANE);
                     tma_load_5d(dst, &dymapK, full + 8 * st, coc * 32, vw0, vh0, d, n);                        // dy planes d, d+1
                     tma_load_5d(dst + wd::K_DY_SLOT, kind == 1 ? &xmapA : &xmapB, full + 8 * st, cic * 32, vw0 - 2,
-                                vh0 + 1, d + kd0 - 2, n);                                                      // x planes d+kd0-2 ..
+                                vh0 + 1, d + kd0 - 2 + P.x_off, n);                                            // x planes d+kd0-2 ..
                 }
                 if (++st == wd::STAGES) { st = 0; ++use; }
             }
@@ -177,7 +184,12 @@ wgrad_deep_kernel(const __grid_constant__ CUtensorMap dymapK, const __grid_const
             uint32_t st = 0, use = 0, acc = 0;
             int th_c = (t0 / P.tiles_w) % tiles_h, tw_c = t0 % P.tiles_w;
             bool ok = true;
-#define WD_B(xbase, kk) ((((xbase) + 2 * (kk) * wd::X_COLS * 64) >> 4) | lbo_vox)
+// Descriptor low words are (base >> 4 | LBO field) + compile-time offsets: ONE uniform add per operand and MMA
+            // (the address field is 14 bits and every offset keeps it below 2^14, so the add never carries into the LBO
+            // field).  r2a capture: with ((base + off) >> 4) | lbo spelled out per MMA the issue warp ran ~11 uniform
+            // instructions per UTCHMMA and was itself the limiter (tensor pipe 80 % of active cycles, MMA warp waiting
+            // for operands only 7 % of its samples).
+#define WD_OFF(bytes) ((uint32_t)(bytes) >> 4)
 #define WD_MMA(col, alo, blo, a) mma_f16_ss_sel(tm + (col), (alo), hi_a, (blo), hi_b, idesc, (a), sel)
             for (int t = t0; t < t1; ++t) {
                 if (!mbar_wait_warp<false>(full + 8 * st, use & 1)) { ok = false; break; }
@@ -185,15 +197,17 @@ wgrad_deep_kernel(const __grid_constant__ CUtensorMap dymapK, const __grid_const
                 const uint32_t sb = base + st * stage_bytes;
                 const bool full_row = th_c != tiles_h - 1 || nk_last == 8;
                 if (kind == 0) {
-                    const uint32_t x0 = sb + wd::L_DY_BYTES, x1 = x0 + wd::X_PLANE;
+                    const uint32_t ap = (sb >> 4) | lbo_plane;                                   // dy plane 0 of the box
+                    const uint32_t bx = ((sb + wd::L_DY_BYTES) >> 4) | lbo_vox;                  // x plane p
                     if (full_row) {
 #pragma unroll
                         for (int kk = 0; kk < 8; ++kk) {
                             // x plane p: dy planes p-1.. (kd = 3 - bm) and p-2.. (bm = 0: kd = 4); x plane p+1: one plane on
-                            const uint32_t b0 = WD_B(x0, kk), b1 = WD_B(x1, kk);
-                            const uint32_t a0 = ((sb + 0 * wd::L_PLANE + kk * 1024) >> 4) | lbo_plane;
-                            const uint32_t a1 = ((sb + 1 * wd::L_PLANE + kk * 1024) >> 4) | lbo_plane;
-                            const uint32_t a2 = ((sb + 2 * wd::L_PLANE + kk * 1024) >> 4) | lbo_plane;
+                            const uint32_t b0 = bx + WD_OFF(2 * kk * wd::X_COLS * 64);
+                            const uint32_t b1 = bx + WD_OFF(wd::X_PLANE + 2 * kk * wd::X_COLS * 64);
+                            const uint32_t a0 = ap + WD_OFF(0 * wd::L_PLANE + kk * 1024);
+                            const uint32_t a1 = ap + WD_OFF(1 * wd::L_PLANE + kk * 1024);
+                            const uint32_t a2 = ap + WD_OFF(2 * wd::L_PLANE + kk * 1024);
                             WD_MMA(0, a1, b0, acc);
                             WD_MMA(160, a0, b0, acc);
                             WD_MMA(0, a2, b1, 1u);
@@ -203,10 +217,11 @@ wgrad_deep_kernel(const __grid_constant__ CUtensorMap dymapK, const __grid_const
                     } else {
 #pragma unroll 1
                         for (int kk = 0; kk < nk_last; ++kk) {
-                            const uint32_t b0 = WD_B(x0, kk), b1 = WD_B(x1, kk);
-                            const uint32_t a0 = ((sb + 0 * wd::L_PLANE + kk * 1024) >> 4) | lbo_plane;
-                            const uint32_t a1 = ((sb + 1 * wd::L_PLANE + kk * 1024) >> 4) | lbo_plane;
-                            const uint32_t a2 = ((sb + 2 * wd::L_PLANE + kk * 1024) >> 4) | lbo_plane;
+                            const uint32_t b0 = bx + WD_OFF(2 * kk * wd::X_COLS * 64);
+                            const uint32_t b1 = b0 + WD_OFF(wd::X_PLANE);
+                            const uint32_t a0 = ap + WD_OFF(kk * 1024);
+                            const uint32_t a1 = a0 + WD_OFF(wd::L_PLANE);
+                            const uint32_t a2 = a0 + WD_OFF(2 * wd::L_PLANE);
                             WD_MMA(0, a1, b0, acc);
                             WD_MMA(160, a0, b0, acc);
                             WD_MMA(0, a2, b1, 1u);
@@ -216,15 +231,17 @@ wgrad_deep_kernel(const __grid_constant__ CUtensorMap dymapK, const __grid_const
                     }
                 } else {
                     // dy plane pl (row-shifted M blocks: kh = 3 - bm) x x plane pl + j  ->  kd = kd0 + j, accumulator set j
-                    const uint32_t xb = sb + wd::K_DY_SLOT;
+                    const uint32_t ar = (sb >> 4) | lbo_row;
+                    const uint32_t bx = ((sb + wd::K_DY_SLOT) >> 4) | lbo_vox;
                     if (full_row && kind == 1) {
 #pragma unroll
                         for (int pl = 0; pl < wd::PT; ++pl) {
 #pragma unroll
                             for (int kk = 0; kk < 8; ++kk) {
-                                const uint32_t ad = ((sb + pl * wd::K_DY_PLANE + kk * 1024) >> 4) | lbo_row;
-                                WD_MMA(0, ad, WD_B(xb + (pl + 0) * wd::X_PLANE, kk), (pl | kk) ? 1u : acc);
-                                WD_MMA(160, ad, WD_B(xb + (pl + 1) * wd::X_PLANE, kk), (pl | kk) ? 1u : acc);
+                                const uint32_t ad = ar + WD_OFF(pl * wd::K_DY_PLANE + kk * 1024);
+                                const uint32_t bd = bx + WD_OFF(pl * wd::X_PLANE + 2 * kk * wd::X_COLS * 64);
+                                WD_MMA(0, ad, bd, (pl | kk) ? 1u : acc);
+                                WD_MMA(160, ad, bd + WD_OFF(wd::X_PLANE), (pl | kk) ? 1u : acc);
                             }
                         }
                     } else if (full_row) {
@@ -232,10 +249,11 @@ wgrad_deep_kernel(const __grid_constant__ CUtensorMap dymapK, const __grid_const
                         for (int pl = 0; pl < wd::PT; ++pl) {
 #pragma unroll
                             for (int kk = 0; kk < 8; ++kk) {
-                                const uint32_t ad = ((sb + pl * wd::K_DY_PLANE + kk * 1024) >> 4) | lbo_row;
-                                WD_MMA(0, ad, WD_B(xb + (pl + 0) * wd::X_PLANE, kk), (pl | kk) ? 1u : acc);
-                                WD_MMA(160, ad, WD_B(xb + (pl + 1) * wd::X_PLANE, kk), (pl | kk) ? 1u : acc);
-                                WD_MMA(320, ad, WD_B(xb + (pl + 2) * wd::X_PLANE, kk), (pl | kk) ? 1u : acc);
+                                const uint32_t ad = ar + WD_OFF(pl * wd::K_DY_PLANE + kk * 1024);
+                                const uint32_t bd = bx + WD_OFF(pl * wd::X_PLANE + 2 * kk * wd::X_COLS * 64);
+                                WD_MMA(0, ad, bd, (pl | kk) ? 1u : acc);
+                                WD_MMA(160, ad, bd + WD_OFF(wd::X_PLANE), (pl | kk) ? 1u : acc);
+                                WD_MMA(320, ad, bd + WD_OFF(2 * wd::X_PLANE), (pl | kk) ? 1u : acc);
                             }
                         }
                     } else {
@@ -243,11 +261,11 @@ wgrad_deep_kernel(const __grid_constant__ CUtensorMap dymapK, const __grid_const
                         for (int pl = 0; pl < wd::PT; ++pl) {
 #pragma unroll 1
                             for (int kk = 0; kk < nk_last; ++kk) {
-                                const uint32_t ad = ((sb + pl * wd::K_DY_PLANE + kk * 1024) >> 4) | lbo_row;
+                                const uint32_t ad = ar + WD_OFF(pl * wd::K_DY_PLANE + kk * 1024);
+                                const uint32_t bd = bx + WD_OFF(pl * wd::X_PLANE + 2 * kk * wd::X_COLS * 64);
                                 const uint32_t a = (pl | kk) ? 1u : acc;
 #pragma unroll 1
-                                for (int j = 0; j < nkd; ++j)
-                                    WD_MMA(160 * j, ad, WD_B(xb + (pl + j) * wd::X_PLANE, kk), a);
+                                for (int j = 0; j < nkd; ++j) WD_MMA(160 * j, ad, bd + j * WD_OFF(wd::X_PLANE), a);
                             }
                         }
                     }
@@ -257,8 +275,8 @@ wgrad_deep_kernel(const __grid_constant__ CUtensorMap dymapK, const __grid_const
                 if (++st == wd::STAGES) { st = 0; ++use; }
                 if (++tw_c == P.tiles_w) { tw_c = 0; if (++th_c == tiles_h) th_c = 0; }
             }
+#undef WD_OFF
 #undef WD_MMA
-#undef WD_B
             if (ok) mma_commit_sel(done, sel);
             else if (lane == 0) atomicExch(P.error_flag, 32);
         }
@@ -348,7 +366,7 @@ struct DeepPlan { int SL, SA, SB; };
 
 // Slabs per unit kind: one wave of CTAs when the layer has few channel chunks, every CTA carrying about the same number
 // of MMAs (A: 2 kd, B: 3 kd of the row taps per dy plane; L: 2 MMAs per K step and x plane).
-static DeepPlan deep_plan(int N, int D, int H, int W, int Ci, int Co) {
+static DeepPlan deep_plan(int N, int D, int H, int W, int Ci, int Co, int Dx, int x_off) {
     const int groups = N * (Ci / 32) * (Co / 32);
     const int slots = std::max(1, sm_count() / groups);
     const int tiles_w = W / wd::TW;
@@ -356,11 +374,12 @@ static DeepPlan deep_plan(int N, int D, int H, int W, int Ci, int Co) {
     const double stepsK = tiles_w * (8.0 * (tiles_hK - 1) + std::min(8, (H - ((tiles_hK - 1) * wd::TH - 3) + 1) >> 1));
     const double stepsL = tiles_w * (8.0 * (tiles_hL - 1) + std::min(8, (H - (tiles_hL - 1) * wd::TH + 1) >> 1));
     auto planes = [&](int kd0, int nkd) {
-        const int dlo = std::max(0, 2 - (kd0 + nkd - 1)), dhi = std::min(D, D + 2 - kd0);
+        const int dlo = std::max(0, 2 - (kd0 + nkd - 1) - x_off), dhi = std::min(D, Dx + 2 - x_off - kd0);
         return (double)(((std::max(0, dhi - dlo) + wd::PT - 1) / wd::PT) * wd::PT);
     };
     const double cA = planes(0, 2) * 2 * stepsK, cB = planes(2, 3) * 3 * stepsK;
-    const double cL = 2.0 * (2 * ((D + 1) / 2)) * stepsL;
+    const int lplanes = std::max(0, std::min(Dx - x_off - 1, D + 1) - std::max(-x_off, -2) + 1);
+    const double cL = 2.0 * (2 * ((lplanes + 1) / 2)) * stepsL;
     DeepPlan p{1, 1, 1};
     while (p.SA + p.SB + p.SL < slots) {
         const double a = cA / p.SA, b = cB / p.SB, c = cL / p.SL;
@@ -376,22 +395,24 @@ bool wgrad_deep_supported(int D, int H, int W, int Ci, int Co) {
     return Ci % 32 == 0 && Co % 32 == 0 && Ci >= 32 && Co >= 32 && W % wd::TW == 0;
 }
 
-int64_t wgrad_deep_workspace_bytes(int N, int D, int H, int W, int Ci, int Co) {
-    const DeepPlan p = deep_plan(N, D, H, W, Ci, Co);
+int64_t wgrad_deep_workspace_bytes(int N, int D, int H, int W, int Ci, int Co, int Dx, int x_off) {
+    const DeepPlan p = deep_plan(N, D, H, W, Ci, Co, Dx, x_off);
     const int64_t groups = (int64_t)N * (Ci / 32) * (Co / 32);
     return groups * (p.SL + p.SA + p.SB) * wd::PARTIAL_FLOATS * (int64_t)sizeof(float);
 }
 
 int wgrad_deep(const __half* x, const __half* dy, float* dw, int N, int D, int H, int W, int Ci, int Co,
-               float out_scale, const float* out_scale_dev, void* workspace, cudaStream_t st) {
+               float out_scale, const float* out_scale_dev, void* workspace, int Dx, int x_off, cudaStream_t st) {
     if (!workspace) MODE_FAIL("wgrad_deep: workspace is NULL");
     if ((reinterpret_cast<uintptr_t>(x) & 15) || (reinterpret_cast<uintptr_t>(dy) & 15) ||
         (reinterpret_cast<uintptr_t>(workspace) & 15))
         MODE_FAIL("wgrad_deep: pointers must be 16-byte aligned");
-    const DeepPlan plan = deep_plan(N, D, H, W, Ci, Co);
+    if (x_off < 0 || x_off + D > Dx) MODE_FAIL("wgrad_deep: need 0 <= x_off and x_off + D <= Dx (x_off=%d D=%d Dx=%d)", x_off, D, Dx);
+    const DeepPlan plan = deep_plan(N, D, H, W, Ci, Co, Dx, x_off);
     DeepParams P;
     P.partial = (float*)workspace;
     P.N = N; P.D = D; P.H = H; P.W = W; P.Ci = Ci; P.Co = Co;
+    P.Dx = Dx; P.x_off = x_off;
     P.ncic = Ci / 32; P.ncoc = Co / 32;
     P.SL = plan.SL; P.SA = plan.SA; P.SB = plan.SB;
     const int64_t groups = (int64_t)N * P.ncic * P.ncoc;
@@ -406,10 +427,10 @@ int wgrad_deep(const __half* x, const __half* dy, float* dw, int N, int D, int H
     if (!P.error_flag) MODE_FAIL("wgrad_deep: could not allocate the device error flag");
     CUtensorMap dymapK, xmapA, xmapB, dymapL, xmapL;
     if (make_act_map(&dymapK, dy, N, D, H, W, Co, wd::TW, wd::K_DY_ROWS, wd::PT) != 0) return -1;
-    if (make_act_map(&xmapA, x, N, D, H, W, Ci, wd::X_COLS, wd::TH, wd::PT + 1) != 0) return -1;
-    if (make_act_map(&xmapB, x, N, D, H, W, Ci, wd::X_COLS, wd::TH, wd::PT + 2) != 0) return -1;
+    if (make_act_map(&xmapA, x, N, Dx, H, W, Ci, wd::X_COLS, wd::TH, wd::PT + 1) != 0) return -1;
+    if (make_act_map(&xmapB, x, N, Dx, H, W, Ci, wd::X_COLS, wd::TH, wd::PT + 2) != 0) return -1;
     if (make_act_map(&dymapL, dy, N, D, H, W, Co, wd::TW, wd::TH, wd::L_PLANES) != 0) return -1;
-    if (make_act_map(&xmapL, x, N, D, H, W, Ci, wd::X_COLS, wd::TH, 2) != 0) return -1;
+    if (make_act_map(&xmapL, x, N, Dx, H, W, Ci, wd::X_COLS, wd::TH, 2) != 0) return -1;
     const int smem_bytes = wd::OPERAND_BYTES + 512 + 1024;
     MODE_CUDA(cudaFuncSetAttribute(wgrad_deep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
     wgrad_deep_kernel<<<(unsigned)units, wd::THREADS, smem_bytes, st>>>(dymapK, xmapA, xmapB, dymapL, xmapL, P);

@@ -1,8 +1,8 @@
-// K4, second generation: wgrad of the 5x5x5 conv on tcgen05 with the tap set split so that (almost) every
-// accumulator column is a real tap.
+// K4, round-1 kernel (A/B arm: REPMODE_WGRAD_SPLIT=1 or impl = 5; the default is wgrad_deep.cu): wgrad of the 5x5x5 conv
+// on tcgen05 with the tap set split so that (almost) every accumulator column is a real tap.
 //   d_weff[n][tap][o][i] = sum_p dy[n][p][o] * x[n][p + tap - 2][i]      (autograd of RepMode.py:207)
 //
-// wgrad_umma.cu stacks taps through overlapping MN-major views: M = 4 dy row shifts x 32 co, N = 5 x voxel shifts x 32 ci,
+// The first-generation kernel (removed) stacked taps through overlapping MN-major views: M = 4 dy row shifts x 32 co, N = 5 x voxel shifts x 32 ci,
 // one M128 N160 K16 MMA = 20 taps.  Five kh rows do not fit four row shifts, so that kernel spends a second MMA per K
 // step on kh = 4 alone (25 useful of 40 computed tap blocks).  Here the 125 taps are covered by two kinds of work unit:
 //   K units ("rows"):   kh = 0..3 of one or two kd.  Per (d-plane, 8x16 patch): one dy brick (19 rows) and the x brick of

@@ -6,6 +6,7 @@ MoDEConv.forward / backward (fnet/nn_modules/RepMode.py:194-214 in the reference
 hand-written sm_100a kernels.  There is no CPU / eager fallback: a non-CUDA tensor raises.
 """
 import ctypes
+import functools
 import os
 
 import torch
@@ -25,6 +26,20 @@ def default_precision():
 
 def _stream():
     return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _on_device_of_first(fn):
+    """Run an autograd forward / backward with the CUDA device of its first tensor argument made current: the C library
+    launches on the CURRENT device and stream (tensor maps, SM count, error flag are per device), while the reference only
+    ever moves tensors (`.to(cuda:gpu_ids[0])`, fnet_model.py:53) and never calls set_device -- so Model(opts, gpu_ids=1)
+    in a process whose current device is 0 must still run on cuda:1.  CPU tensors pass through to the CUDA-only check."""
+    @functools.wraps(fn)
+    def wrapped(ctx, first, *args, **kwargs):
+        if torch.is_tensor(first) and first.is_cuda:
+            with torch.cuda.device(first.device):
+                return fn(ctx, first, *args, **kwargs)
+        return fn(ctx, first, *args, **kwargs)
+    return wrapped
 
 
 def _p(t):
@@ -101,7 +116,7 @@ def _layer(k5, k3, k1, a3, a5, gate_w, gate_b):
     return L, ci, co
 
 
-UMMA_WGRAD = os.environ.get("REPMODE_UMMA_WGRAD", "1") == "1"   # K4 on tcgen05 (wgrad_umma.cu); 0 -> SIMT fp32 wgrad
+UMMA_WGRAD = os.environ.get("REPMODE_UMMA_WGRAD", "1") == "1"   # K4 on tcgen05 (wgrad_deep.cu); 0 -> SIMT fp32 wgrad
 
 
 def _pad32(c):
@@ -157,13 +172,35 @@ def reparam_fwd(layer, gate_in, U, ci, co, dtype, want_dgrad, w_scale=1.0, fork=
 
 
 def conv3d(x, dtype, w, sample_u, n, d, h, wd, k, nout, out_scale_dev=None, bn_sums=None, impl=0, stat_range=None,
-           out_scale=1.0, out=None):
+           out_scale=1.0, out=None, halo=None, ep=None, y16=None, want_y=True):
+    """K2 / K3 through mode_conv3d_ex.  d = OUTPUT planes.
+    halo = (Dx, x_off): x holds Dx >= d planes and output plane q is centred on input plane q + x_off (D-sharded slabs).
+    ep = (scale[nout] | None, shift[nout] | None, relu): per-channel affine + ReLU fused into the epilogue (eval BatchNorm).
+    y16 = (buffer fp16 [n, Dy16, h, wd, nout], y16_off, scale): fp16 copy of the result written at plane y16_off + q.
+    want_y=False skips the fp32 result (returns None)."""
     lib = _lib.load()
-    y = out if out is not None else torch.empty((n, d, h, wd, nout), dtype=torch.float32, device=x.device)
+    y = out
+    if y is None and want_y:
+        y = torch.empty((n, d, h, wd, nout), dtype=torch.float32, device=x.device)
     lo, hi = stat_range if stat_range is not None else (0, d)
-    _lib.check(lib.mode_conv3d(_p(x), dtype, _p(w), _p(sample_u), _p(y), n, d, h, wd, k, nout, float(out_scale),
-                               _p(out_scale_dev),
-                               _p(bn_sums), lo, hi, impl, _stream()), "mode_conv3d")
+    opts = None
+    if halo is not None or ep is not None or y16 is not None:
+        o = _lib.ModeConvOpts()
+        if halo is not None:
+            o.Dx, o.x_off = int(halo[0]), int(halo[1])
+        keep = []
+        if ep is not None:
+            sc, sh, relu = ep
+            o.ep_scale = sc.data_ptr() if sc is not None else None
+            o.ep_shift = sh.data_ptr() if sh is not None else None
+            o.relu = 1 if relu else 0
+        if y16 is not None:
+            buf, off, scl = y16
+            o.y16 = buf.data_ptr()
+            o.Dy16, o.y16_off, o.y16_scale = int(buf.shape[1]), int(off), float(scl)
+        opts = ctypes.byref(o)
+    _lib.check(lib.mode_conv3d_ex(_p(x), dtype, _p(w), _p(sample_u), _p(y), n, d, h, wd, k, nout, float(out_scale),
+                                  _p(out_scale_dev), _p(bn_sums), lo, hi, impl, opts, _stream()), "mode_conv3d")
     return y
 
 
@@ -193,14 +230,16 @@ class ShardSpec:
             dist.all_reduce(t, group=self.group)
 
 
-def conv3d_wgrad(x, dy, dtype, n, d, h, wd, ci, co, out_scale_dev=None, impl=0):
+def conv3d_wgrad(x, dy, dtype, n, d, h, wd, ci, co, out_scale_dev=None, impl=0, halo=None):
+    """K4.  d = planes of dy (the OWNED planes); halo = (Dx, x_off) when x carries halo planes."""
     lib = _lib.load()
     dw = torch.empty((n, 125, co, ci), dtype=torch.float32, device=x.device)
     impl_eff = impl if impl else (2 if dtype == _lib.MODE_F16 else 1)
     ws_bytes = lib.mode_conv3d_wgrad_workspace_bytes(n, d, h, wd, ci, co, impl_eff)
     ws = torch.empty(max(int(ws_bytes), 16), dtype=torch.uint8, device=x.device)
-    _lib.check(lib.mode_conv3d_wgrad(_p(x), _p(dy), dtype, _p(dw), n, d, h, wd, ci, co, 1.0, _p(out_scale_dev), _p(ws),
-                                     impl_eff, _stream()), "mode_conv3d_wgrad")
+    dx_, xo = (int(halo[0]), int(halo[1])) if halo is not None else (0, 0)
+    _lib.check(lib.mode_conv3d_wgrad_ex(_p(x), _p(dy), dtype, _p(dw), n, d, h, wd, ci, co, 1.0, _p(out_scale_dev), _p(ws),
+                                        impl_eff, dx_, xo, _stream()), "mode_conv3d_wgrad")
     return dw
 
 
@@ -238,6 +277,7 @@ class ModeConvFunction(torch.autograd.Function):
 
     @staticmethod
     @torch.amp.custom_fwd(device_type="cuda", cast_inputs=torch.float32)
+    @_on_device_of_first
     def forward(ctx, x, gate_in, k5, k3, k1, a3, a5, gate_w, gate_b, bn_w, bn_b, running_mean, running_var, training,
                 conv_type, precision, shard=None):
         _require_cuda(x, gate_in, k5)
@@ -323,6 +363,7 @@ class ModeConvFunction(torch.autograd.Function):
 
     @staticmethod
     @torch.amp.custom_bwd(device_type="cuda")
+    @_on_device_of_first
     def backward(ctx, dout):
         if ctx.frozen_bn:
             raise NotImplementedError("MoDEConv backward in eval mode (frozen BatchNorm statistics) is not supported")
@@ -483,6 +524,7 @@ class BnReluFunction(torch.autograd.Function):
 
     @staticmethod
     @torch.amp.custom_fwd(device_type="cuda", cast_inputs=torch.float32)
+    @_on_device_of_first
     def forward(ctx, y, weight, bias, running_mean, running_var, training, shard=None):
         _require_cuda(y)
         lib = _lib.load()
@@ -518,6 +560,7 @@ class BnReluFunction(torch.autograd.Function):
 
     @staticmethod
     @torch.amp.custom_bwd(device_type="cuda")
+    @_on_device_of_first
     def backward(ctx, dout):
         if not ctx.training:
             raise NotImplementedError("BatchNorm backward in eval mode (frozen statistics) is not supported")

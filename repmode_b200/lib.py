@@ -11,15 +11,14 @@ import threading
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 SO_PATH = os.path.join(HERE, "librepmode_b200.so")
-SOURCES = ["mode_abi.cu", "reparam.cu", "conv_simt.cu", "bn.cu", "conv_umma.cu", "conv_pair.cu", "wgrad_umma.cu", "wgrad_split.cu", "wgrad_deep.cu"]
+SOURCES = ["mode_abi.cu", "reparam.cu", "conv_simt.cu", "bn.cu", "conv_umma.cu", "conv_pair.cu", "wgrad_split.cu", "wgrad_deep.cu", "peer.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-shared",
               "-Xcompiler", "-fPIC"]
 
 MODE_F32, MODE_F16 = 0, 1
 IMPL_AUTO, IMPL_SIMT, IMPL_UMMA = 0, 1, 2
 IMPL_UMMA_SINGLE, IMPL_UMMA_PAIR = 3, 4     # force the single-CTA / the CTA-pair (cta_group::2) tcgen05 kernel
-IMPL_WGRAD_STACKED, IMPL_WGRAD_SPLIT = 3, 5  # mode_conv3d_wgrad: force wgrad_umma.cu (10 MMAs per K step) / wgrad_split.cu (7)
-IMPL_WGRAD_DEEP = 6                          # experimental deep-tile variant of the split kernel (wgrad_deep.cu)
+IMPL_WGRAD_SPLIT, IMPL_WGRAD_DEEP = 5, 6     # mode_conv3d_wgrad: force wgrad_split.cu (r1 kernel, A/B arm) / wgrad_deep.cu (default)
 
 _lock = threading.Lock()
 _lib = None
@@ -35,6 +34,12 @@ class ModePlanes(ctypes.Structure):
     _fields_ = [("rows_per_plane", ctypes.c_int64), ("D", ctypes.c_int32), ("own_lo", ctypes.c_int32),
                 ("own_hi", ctypes.c_int32), ("valid_lo", ctypes.c_int32), ("valid_hi", ctypes.c_int32),
                 ("m_global", ctypes.c_int64)]
+
+
+class ModeConvOpts(ctypes.Structure):
+    _fields_ = [("Dx", ctypes.c_int32), ("x_off", ctypes.c_int32), ("ep_scale", ctypes.c_void_p),
+                ("ep_shift", ctypes.c_void_p), ("relu", ctypes.c_int32), ("y16", ctypes.c_void_p),
+                ("Dy16", ctypes.c_int32), ("y16_off", ctypes.c_int32), ("y16_scale", ctypes.c_float)]
 
 
 class ModeCaps(ctypes.Structure):
@@ -82,6 +87,14 @@ SIGNATURES = {
                                         _vp, _vp, _vp, _vp, _vp, _vp]),
     "mode_conv3d": (ctypes.c_int, [_vp, ctypes.c_int, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _f32, _vp, _vp,
                                    _i32, _i32, _i32, _vp]),
+    "mode_conv3d_ex": (ctypes.c_int, [_vp, ctypes.c_int, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _f32, _vp, _vp,
+                                      _i32, _i32, _i32, ctypes.POINTER(ModeConvOpts), _vp]),
+    "mode_conv3d_wgrad_ex": (ctypes.c_int, [_vp, _vp, ctypes.c_int, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _f32, _vp,
+                                            _vp, _i32, _i32, _i32, _vp]),
+    "mode_peer_enable_access": (ctypes.c_int, [_i32]),
+    "mode_peer_put": (ctypes.c_int, [_vp, _vp, _vp, _i32, _i64, _vp, _vp]),
+    "mode_peer_wait": (ctypes.c_int, [_vp, _vp, _i32, _vp]),
+    "mode_peer_sum_slots": (ctypes.c_int, [_vp, _i32, _i64, _i32, _vp, _vp, _vp, _vp, _vp]),
     "mode_conv3d_wgrad_workspace_bytes": (_i64, [_i32, _i32, _i32, _i32, _i32, _i32, _i32]),
     "mode_conv3d_wgrad": (ctypes.c_int, [_vp, _vp, ctypes.c_int, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _f32, _vp,
                                          _vp, _i32, _vp]),
@@ -106,7 +119,7 @@ def load():
     with _lock:
         if _lib is not None:
             return _lib
-        if _needs_build():
+        if _needs_build() and os.environ.get("REPMODE_NO_BUILD", "0") != "1":
             if os.path.exists(os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")):
                 build()
             elif not os.path.exists(SO_PATH):

@@ -54,6 +54,162 @@ def sharded_stage(stage, x_local, t, d_global, group=None):
     return a2[:, :, 2:2 + dl]
 
 
+# ------------------------------------------------------------------------------------- one MoDEConv on a D-slab
+BLOCK_HALO = 2      # a single 5^3 conv reaches 2 planes
+
+
+class ShardedConvFunction(torch.autograd.Function):
+    """One MoDEConv (conv_type 'normal', train mode: RepMode.py:194-214) on this rank's D-slab of ONE volume -- the headline
+    block of BASELINE.json under the D-axis split.  Per step and rank:
+
+      forward   x slab -> conv operand written into the INTERIOR of a haloed buffer [1, D+4, H, W, Ci]; `comm.halo_fill`
+                brings the 2 boundary planes of each neighbour (zeros at the global faces); K2 computes ONLY the D owned
+                output planes from the haloed operand (mode_conv3d_ex: no redundant planes); BatchNorm sums (all output
+                planes are owned) are all-reduced; finalize + apply as on one GPU.
+      backward  BatchNorm-backward sums all-reduced; dy written into the interior of a second haloed buffer and exchanged
+                the same way; K4 runs on (haloed x) x (owned dy), K3 on the haloed dy -> dx of the owned planes; K1b; the
+                partial parameter gradients of the ranks are summed by ONE all-reduce of the flat gradient buffer, so the
+                gradients this node returns are already the sums over the whole volume (do NOT all-reduce them again).
+
+    5 exchange steps per training step (2 halo, 2 BatchNorm, 1 gradient), all through `comm` (peer.PeerComm: stores into the
+    neighbour's memory over NVLink; peer.TorchComm: NCCL / gloo).  N = 1 per rank (one volume)."""
+
+    @staticmethod
+    @torch.amp.custom_fwd(device_type="cuda", cast_inputs=torch.float32)
+    @Fm._on_device_of_first
+    def forward(ctx, x, gate_in, k5, k3, k1, a3, a5, gate_w, gate_b, bn_w, bn_b, running_mean, running_var, eps, momentum,
+                precision, comm, d_global, tag):
+        import ctypes
+        from . import lib as _lib
+        Fm._require_cuda(x, gate_in, k5)
+        lib = _lib.load()
+        n, ci_x, d, h, wd = x.shape
+        if n != 1:
+            raise RuntimeError("sharded MoDEConv: one volume per rank (N = 1)")
+        layer, ci, co = Fm._layer(k5, k3, k1, a3, a5, gate_w, gate_b)
+        if ci_x != ci:
+            raise RuntimeError(f"MoDEConv: input has {ci_x} channels, layer expects {ci}")
+        dev = x.device
+        gate_in = gate_in.contiguous().float() if gate_in.dtype.is_floating_point else gate_in.to(torch.int32).contiguous()
+        use_umma = precision == "f16" and Fm.umma_shape_ok(ci, co, d, h, wd) and ci % 32 == 0 and co % 32 == 0
+        dtype = _lib.MODE_F16 if use_umma else _lib.MODE_F32
+        tdt = torch.float16 if use_umma else torch.float32
+        H2 = BLOCK_HALO
+        sample_u = torch.zeros(1, dtype=torch.int32, device=dev)
+        w_scale = Fm.W_SCALE_F16 if use_umma else 1.0
+        needs_dx = ctx.needs_input_grad[0]
+
+        xn = Fm.to_ndhwc(x)
+        x_ext = comm.alloc((tag, "x_ext", str(tdt)), (1, d + 2 * H2, h, wd, ci), tdt, dev)
+        k1_fork = Fm._Fork(dev, True)
+        g, w_fwd, w_dg = Fm.reparam_fwd(layer, gate_in[:1].contiguous(), 1, ci, co, dtype, needs_dx, w_scale, fork=k1_fork)
+        if use_umma:
+            _lib.check(lib.mode_cast_f16(Fm._p(xn), Fm._p(x_ext[0, H2]), xn.numel(), 1.0, None, Fm._stream()), "mode_cast_f16")
+        else:
+            x_ext[0, H2:H2 + d].copy_(xn[0])
+        comm.halo_fill(x_ext, H2, tag + ".x")
+        k1_fork.join()
+
+        sums = torch.zeros(2 * co, dtype=torch.float64, device=dev)
+        y = Fm.conv3d(x_ext, dtype, w_fwd, sample_u, 1, d, h, wd, ci, co, None, sums, out_scale=1.0 / w_scale,
+                      halo=(d + 2 * H2, H2))
+        comm.all_reduce(sums, tag + ".bnf")
+        m_rows = d * h * wd
+        m_global = d_global * h * wd
+        mean = torch.empty(co, dtype=torch.float32, device=dev)
+        invstd = torch.empty(co, dtype=torch.float32, device=dev)
+        scale = torch.empty(co, dtype=torch.float32, device=dev)
+        shift = torch.empty(co, dtype=torch.float32, device=dev)
+        _lib.check(lib.mode_bn_finalize(Fm._p(sums), m_global, co, Fm._p(bn_w), Fm._p(bn_b), float(eps), float(momentum),
+                                        Fm._p(mean), Fm._p(invstd), Fm._p(scale), Fm._p(shift), Fm._p(running_mean),
+                                        Fm._p(running_var), Fm._stream()), "mode_bn_finalize")
+        out = torch.empty_like(y)
+        _lib.check(lib.mode_bn_apply_relu(Fm._p(y), m_rows, co, Fm._p(scale), Fm._p(shift), 1, Fm._p(out), None, 1.0, None,
+                                          Fm._stream()), "mode_bn_apply_relu")
+        ctx.save_for_backward(y, g, w_dg, gate_in, sample_u, k5, k3, k1, a3, a5, gate_w, gate_b, bn_w, bn_b, mean, invstd)
+        ctx.x_ext = x_ext                 # persistent exchange buffer: not a saved tensor (it is rewritten every step)
+        ctx.cfg = (d, h, wd, ci, co, use_umma, needs_dx, m_global, comm, tag)
+        return Fm.from_ndhwc(out)
+
+    @staticmethod
+    @torch.amp.custom_bwd(device_type="cuda")
+    @Fm._on_device_of_first
+    def backward(ctx, dout):
+        import ctypes
+        from . import lib as _lib
+        lib = _lib.load()
+        y, g, w_dg, gate_in, sample_u, k5, k3, k1, a3, a5, gate_w, gate_b, bn_w, bn_b, mean, invstd = ctx.saved_tensors
+        d, h, wd, ci, co, use_umma, needs_dx, m_global, comm, tag = ctx.cfg
+        x_ext = ctx.x_ext
+        dev = dout.device
+        dtype = _lib.MODE_F16 if use_umma else _lib.MODE_F32
+        tdt = torch.float16 if use_umma else torch.float32
+        H2 = BLOCK_HALO
+        doutn = Fm.to_ndhwc(dout)
+        m_rows = d * h * wd
+        ws = torch.empty(int(lib.mode_bn_bwd_workspace_bytes(co)), dtype=torch.uint8, device=dev)
+        planes = _lib.ModePlanes(h * wd, d, 0, d, 0, d, m_global)
+        pl = ctypes.byref(planes)
+        _lib.check(lib.mode_bn_relu_bwd_reduce(Fm._p(y), Fm._p(doutn), m_rows, co, Fm._p(bn_w), Fm._p(bn_b), Fm._p(mean),
+                                               Fm._p(invstd), pl, Fm._p(ws), Fm._stream()), "mode_bn_relu_bwd_reduce")
+        comm.all_reduce(ws[:16 * co].view(torch.float64), tag + ".bnb")
+        if use_umma:
+            # the fp16 scale of dy must be the SAME on every rank (halo planes travel in fp16): the per-channel maxima
+            # are non-negative floats, and the sum of the ranks' maxima bounds the global maximum
+            comm.all_reduce(ws[16 * co:24 * co].view(torch.float32), tag + ".bnm")
+        dy_ext = comm.alloc((tag, "dy_ext", str(tdt)), (1, d + 2 * H2, h, wd, co), tdt, dev)
+        dgamma = torch.empty(co, dtype=torch.float32, device=dev)
+        dbeta = torch.empty(co, dtype=torch.float32, device=dev)
+        dy_s2 = torch.empty(2, dtype=torch.float32, device=dev) if use_umma else None
+        dy_int = dy_ext[0, H2:H2 + d]
+        _lib.check(lib.mode_bn_relu_bwd_apply(Fm._p(y), Fm._p(doutn), m_rows, co, Fm._p(bn_w), Fm._p(bn_b), Fm._p(mean),
+                                              Fm._p(invstd), Fm._p(dgamma), Fm._p(dbeta),
+                                              None if use_umma else Fm._p(dy_int), Fm._p(dy_int) if use_umma else None,
+                                              Fm._p(dy_s2), pl, Fm._p(ws), Fm._stream()), "mode_bn_relu_bwd_apply")
+        comm.halo_fill(dy_ext, H2, tag + ".dy")
+        inv = dy_s2[1:2] if use_umma else None
+        d_weff = Fm.conv3d_wgrad(x_ext, dy_int, dtype, 1, d, h, wd, ci, co, inv, halo=(d + 2 * H2, H2))
+        dx = None
+        dg_fork = Fm._Fork(dev, needs_dx)
+        if needs_dx:
+            dxn = torch.empty((1, d, h, wd, ci), dtype=torch.float32, device=dev)
+            with dg_fork:
+                Fm.conv3d(dy_ext, dtype, w_dg, sample_u, 1, d, h, wd, co, ci, inv, None,
+                          out_scale=(1.0 / Fm.W_SCALE_F16) if use_umma else 1.0, out=dxn, halo=(d + 2 * H2, H2))
+        layer, _, _ = Fm._layer(k5, k3, k1, a3, a5, gate_w, gate_b)
+        params = (k5, k3, k1, a3, a5, gate_w, gate_b)
+        sizes = [p.numel() for p in params]
+        flat = torch.empty(sum(sizes), dtype=torch.float32, device=dev)
+        outs, off = [], 0
+        for p, sz in zip(params, sizes):
+            outs.append(flat[off:off + sz].view_as(p))
+            off += sz
+        wsb = torch.empty(max(int(lib.mode_reparam_bwd_workspace_bytes(ci, co, 1)), 16), dtype=torch.uint8, device=dev)
+        ids, dense = (gate_in[:1], None) if not gate_in.dtype.is_floating_point else (None, gate_in[:1])
+        _lib.check(lib.mode_reparam_bwd(ctypes.byref(layer), Fm._p(ids), Fm._p(dense), 1, Fm._p(sample_u), 1, Fm._p(g),
+                                        Fm._p(d_weff), *[Fm._p(o) for o in outs], Fm._p(wsb), Fm._stream()),
+                   "mode_reparam_bwd")
+        dg_fork.join()                       # the neighbours may overwrite our dy halo once they see our gradients
+        comm.all_reduce(flat, tag + ".grad")
+        if needs_dx:
+            dx = Fm.from_ndhwc(dxn)
+        return (dx, None, *outs, dgamma, dbeta, None, None, None, None, None, None, None, None)
+
+
+def sharded_mode_conv(mod, x_local, t, comm, d_global, tag="blk"):
+    """mod: a MoDEConv (conv_type 'normal') in train mode; x_local: this rank's slab [1, Ci, D_local, H, W] of one
+    [1, Ci, d_global, H, W] volume.  Returns this rank's slab of the block output; after backward every parameter's .grad
+    holds the gradient summed over all slabs."""
+    if mod.conv_type != "normal" or not mod.training:
+        raise RuntimeError("sharded_mode_conv: train-mode 'normal' MoDEConv only")
+    bn = mod.subsequent_layer[0]
+    if bn.num_batches_tracked is not None:
+        bn.num_batches_tracked.add_(1)
+    return ShardedConvFunction.apply(x_local, t, *mod._params(), bn.weight, bn.bias, bn.running_mean, bn.running_var,
+                                     bn.eps, bn.momentum if bn.momentum is not None else 0.1,
+                                     mod.precision or Fm.default_precision(), comm, d_global, tag)
+
+
 # ---------------------------------------------------------------------------------------------- whole U-Net
 class _AllGatherD(torch.autograd.Function):
     """[N,C,dl,H,W] slabs -> the full [N,C,dl*world,H,W] volume on every rank.  Downstream of it the computation is

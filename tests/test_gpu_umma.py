@@ -149,18 +149,14 @@ WG_SHAPES = [  # N, D, H, W, Ci, Co
 ]
 
 
-EXPERIMENTAL = os.environ.get("REPMODE_TEST_EXPERIMENTAL", "0") == "1"      # kernels that have not been on a GPU yet
-
-
-@pytest.mark.parametrize("impl", ["stacked", "split", pytest.param("deep", marks=pytest.mark.skipif(
-    not EXPERIMENTAL, reason="wgrad_deep.cu is experimental: set REPMODE_TEST_EXPERIMENTAL=1"))])
+@pytest.mark.parametrize("impl", ["split", "deep"])
 @pytest.mark.parametrize("shape", WG_SHAPES)
 def test_wgrad_umma_bitexact(shape, impl):
-    """K4 on tcgen05 (tap-stacking through overlapping MN-major views; wgrad_umma.cu = 10 MMAs per K step, wgrad_split.cu
-    = 7) == SIMT fp32 wgrad == oracle, exactly, on integer-valued data."""
+    """K4 on tcgen05 (tap-stacking through overlapping MN-major views; wgrad_deep.cu = the default, wgrad_split.cu = the
+    round-1 kernel kept as the A/B arm) == SIMT fp32 wgrad == oracle, exactly, on integer-valued data."""
     from repmode_b200 import functional as Fm, lib as L
     n, d, h, w, ci, co = shape
-    which = {"stacked": L.IMPL_WGRAD_STACKED, "split": L.IMPL_WGRAD_SPLIT, "deep": L.IMPL_WGRAD_DEEP}[impl]
+    which = {"split": L.IMPL_WGRAD_SPLIT, "deep": L.IMPL_WGRAD_DEEP}[impl]
     rng = np.random.RandomState(sum(shape) + 1)
     x = rng.randint(-3, 4, size=(n, d, h, w, ci)).astype(np.float32)
     dy = rng.randint(-3, 4, size=(n, d, h, w, co)).astype(np.float32)
@@ -219,3 +215,83 @@ def test_headline_layer_full_size_bitexact_and_adjoint():
     w_tap = torch.from_numpy(weff.reshape(n, co, ci, 125).transpose(0, 3, 1, 2).copy()).cuda()    # [n][tap][o][i]
     c = float((dw_auto.double() * w_tap.double()).sum())
     assert a == b == c, (a, b, c)
+
+
+EX_SHAPES = [  # N, D (output planes), lo halo, hi halo, H, W, K, Nout, impl
+    (1, 6, 2, 2, 32, 16, 32, 32, "pair"),
+    (1, 9, 2, 0, 32, 8, 32, 32, "pair"),        # slab at the upper global face: no halo above
+    (2, 5, 0, 2, 32, 16, 32, 64, "pair"),
+    (1, 12, 4, 4, 32, 8, 64, 32, "pair"),       # streaming plan, 4-plane halo (two-conv stage, conv1)
+    (1, 6, 2, 2, 16, 8, 32, 32, "single"),
+    (2, 7, 2, 3, 24, 16, 64, 64, "single"),
+    (1, 3, 4, 4, 16, 8, 32, 128, "single"),
+    (1, 4, 2, 2, 12, 10, 5, 7, "simt"),
+]
+
+
+@pytest.mark.parametrize("shape", EX_SHAPES)
+def test_conv3d_ex_haloed_input_and_epilogue_bitexact(shape):
+    """mode_conv3d_ex: a haloed input (Dx = lo + D + hi planes, output plane q centred on input plane q + lo) gives exactly the
+    owned planes of the plain 'same' conv over the extended slab, on all three kernels; the fused epilogue (per-channel
+    affine + ReLU, fp16 copy into a plane window of a larger buffer) matches the same arithmetic done afterwards."""
+    from repmode_b200 import functional as Fm, lib as L
+    n, d, lo, hi, h, w, k, nout, which = shape
+    dx = lo + d + hi
+    rng = np.random.RandomState(sum(shape[:8]))
+    x = rng.randint(-3, 4, size=(n, dx, h, w, k)).astype(np.float32)
+    weff = (rng.randint(-4, 5, size=(n, nout, k, 5, 5, 5)) / 8.0).astype(np.float32)
+    su = torch.arange(n, dtype=torch.int32, device="cuda")
+    xg = torch.from_numpy(x).cuda()
+    w32 = torch.from_numpy(pack_weights(weff, half=False)).cuda()
+    ref_full = Fm.conv3d(xg, L.MODE_F32, w32, su, n, dx, h, w, k, nout, None, None, impl=L.IMPL_SIMT)
+    ref = ref_full[:, lo:lo + d].contiguous()
+    if which == "simt":
+        xin, win, dt, impl = xg, w32, L.MODE_F32, L.IMPL_SIMT
+    else:
+        xin, win, dt = xg.half(), torch.from_numpy(pack_weights(weff, half=True)).cuda(), L.MODE_F16
+        impl = L.IMPL_UMMA_PAIR if which == "pair" else L.IMPL_UMMA_SINGLE
+    sums = torch.zeros(2 * nout, dtype=torch.float64, device="cuda")
+    y = Fm.conv3d(xin, dt, win, su, n, d, h, w, k, nout, None, sums, impl=impl, halo=(dx, lo))
+    _poll()
+    assert torch.equal(y, ref)
+    assert torch.allclose(sums[:nout], ref.double().sum(dim=(0, 1, 2, 3)), rtol=1e-12, atol=1e-9)
+    # fused epilogue: power-of-two scale, integer shift -> exact in fp32 either way
+    sc = torch.from_numpy(2.0 ** rng.randint(-2, 2, size=nout)).float().cuda()
+    sh = torch.from_numpy(rng.randint(-5, 6, size=nout).astype(np.float32)).cuda()
+    y16 = torch.full((n, d + 3, h, w, nout), 7.0, dtype=torch.float16, device="cuda")
+    y2 = Fm.conv3d(xin, dt, win, su, n, d, h, w, k, nout, None, None, impl=impl, halo=(dx, lo), ep=(sc, sh, True),
+                   y16=(y16, 1, 0.25))
+    _poll()
+    want = torch.relu(ref * sc + sh)
+    assert torch.equal(y2, want)
+    assert torch.equal(y16[:, 1:1 + d], (want * 0.25).clamp(-65504, 65504).half())
+    assert torch.all(y16[:, 0] == 7.0) and torch.all(y16[:, 1 + d:] == 7.0)       # planes outside the window untouched
+    y16b = torch.zeros((n, d, h, w, nout), dtype=torch.float16, device="cuda")
+    none = Fm.conv3d(xin, dt, win, su, n, d, h, w, k, nout, None, None, impl=impl, halo=(dx, lo), ep=(sc, sh, True),
+                     y16=(y16b, 0, 0.25), want_y=False)
+    _poll()
+    assert none is None and torch.equal(y16b, y16[:, 1:1 + d])
+
+
+@pytest.mark.parametrize("shape", [(1, 6, 2, 2, 32, 16, 32, 32), (1, 5, 2, 0, 16, 8, 32, 64), (2, 4, 0, 2, 24, 8, 64, 32),
+                                   (1, 8, 4, 4, 16, 8, 32, 32), (1, 3, 3, 1, 8, 8, 32, 32)])
+@pytest.mark.parametrize("impl", ["deep", "simt"])
+def test_wgrad_ex_haloed_x_bitexact(shape, impl):
+    """mode_conv3d_wgrad_ex: dy = the D owned planes, x = lo + D + hi planes == the plain wgrad over the extended slab with
+    dy zero outside the owned planes, exactly."""
+    from repmode_b200 import functional as Fm, lib as L
+    n, d, lo, hi, h, w, ci, co = shape
+    dx = lo + d + hi
+    rng = np.random.RandomState(sum(shape) + 3)
+    x = rng.randint(-3, 4, size=(n, dx, h, w, ci)).astype(np.float32)
+    dy = rng.randint(-3, 4, size=(n, d, h, w, co)).astype(np.float32)
+    dy_ext = np.zeros((n, dx, h, w, co), dtype=np.float32)
+    dy_ext[:, lo:lo + d] = dy
+    xg, dyg, dyeg = torch.from_numpy(x).cuda(), torch.from_numpy(dy).cuda(), torch.from_numpy(dy_ext).cuda()
+    ref = Fm.conv3d_wgrad(xg, dyeg, L.MODE_F32, n, dx, h, w, ci, co, None, impl=L.IMPL_SIMT)
+    if impl == "simt":
+        got = Fm.conv3d_wgrad(xg, dyg, L.MODE_F32, n, d, h, w, ci, co, None, impl=L.IMPL_SIMT, halo=(dx, lo))
+    else:
+        got = Fm.conv3d_wgrad(xg.half(), dyg.half(), L.MODE_F16, n, d, h, w, ci, co, None, impl=L.IMPL_WGRAD_DEEP, halo=(dx, lo))
+    _poll()
+    assert torch.equal(got, ref)

@@ -64,10 +64,10 @@ def test_train_step_host_glue(dry, precision, conv_type, ci, co):
     for name, p in m.named_parameters():
         assert p.grad is not None and p.grad.shape == p.shape, name
     c = dry.calls
-    assert c.index("mode_reparam_fwd") < c.index("mode_conv3d")
+    assert c.index("mode_reparam_fwd") < c.index("mode_conv3d_ex")
     # backward order: wgrad before dgrad (dgrad overlaps the K1b chain), K1b last
-    i_w, i_b = c.index("mode_conv3d_wgrad"), c.index("mode_reparam_bwd")
-    i_dgrad = [i for i, n in enumerate(c) if n == "mode_conv3d"][1]
+    i_w, i_b = c.index("mode_conv3d_wgrad_ex"), c.index("mode_reparam_bwd")
+    i_dgrad = [i for i, n in enumerate(c) if n == "mode_conv3d_ex"][1]
     assert i_w < i_dgrad < i_b
 
 
@@ -76,7 +76,7 @@ def test_stem_without_input_grad(dry):
     m = MoDEConv(5, 4, 1, 32).train()
     y = m(torch.randn(1, 1, 2, 16, 8), torch.tensor([0]))
     y.sum().backward()
-    assert dry.calls.count("mode_conv3d") == 1 and "mode_conv3d_wgrad" in dry.calls
+    assert dry.calls.count("mode_conv3d_ex") == 1 and "mode_conv3d_wgrad_ex" in dry.calls
 
 
 @pytest.mark.parametrize("precision", ["f32", "f16"])
@@ -106,8 +106,8 @@ def test_whole_net_host_glue(dry):
     y = net(x, torch.tensor([2]))
     assert y.shape == x.shape
     y.sum().backward()
-    assert dry.calls.count("mode_reparam_fwd") == 19 and dry.calls.count("mode_conv3d_wgrad") == 19
-    assert dry.calls.count("mode_conv3d") == 19 + 18        # no dgrad for the stem
+    assert dry.calls.count("mode_reparam_fwd") == 19 and dry.calls.count("mode_conv3d_wgrad_ex") == 19
+    assert dry.calls.count("mode_conv3d_ex") == 19 + 18        # no dgrad for the stem
     assert all(p.grad is not None for p in net.parameters())
 
 
@@ -138,3 +138,45 @@ def test_side_stream_forks_are_joined(dry, monkeypatch):
     m(x, torch.tensor([1])).sum().backward()
     log = _FakeStream.log
     assert log == [("side", "waits", "main"), ("main", "waits", "side")] * 2, log
+
+
+@pytest.mark.parametrize("precision", ["f32", "f16"])
+def test_sharded_block_host_glue(dry, precision):
+    """repmode_b200.sharded.sharded_mode_conv (the D-sharded headline block): haloed operand buffers, conv on the owned
+    planes only, exchange points in the order halo(x), BN fwd, BN bwd, halo(dy), gradients."""
+    from repmode_b200 import peer, sharded
+    from repmode_b200 import lib as L2
+
+    class _Comm(peer.TorchComm):
+        def __init__(self):
+            super().__init__()
+            self.world = 2                    # pretend: record the exchange points without a process group
+            self.calls = []
+
+        def all_reduce(self, t, tag=""):
+            self.calls.append(("all_reduce", tag, t.numel()))
+            return t
+
+        def halo_fill(self, ext, h, tag=""):
+            self.calls.append(("halo", tag, tuple(ext.shape), h))
+            return ext
+
+    monkeypatch_sharded_lib = L2.load()       # the recorder installed by the fixture
+    assert monkeypatch_sharded_lib is dry
+    comm = _Comm()
+    m = MoDEConv(5, 4, 32, 32).train()
+    m.precision = precision
+    x = torch.randn(1, 32, 6, 16, 8, requires_grad=True)
+    y = sharded.sharded_mode_conv(m, x, torch.tensor([2]), comm, 12, tag="blk")
+    assert y.shape == (1, 32, 6, 16, 8)
+    y.backward(torch.randn_like(y))
+    assert x.grad is not None and all(p.grad is not None and p.grad.shape == p.shape for p in m.parameters())
+    kinds = [(c[0], c[1]) for c in comm.calls]
+    want = [("halo", "blk.x"), ("all_reduce", "blk.bnf"), ("all_reduce", "blk.bnb")]
+    if precision == "f16":
+        want.append(("all_reduce", "blk.bnm"))
+    want += [("halo", "blk.dy"), ("all_reduce", "blk.grad")]
+    assert kinds == want, kinds
+    assert comm.calls[0][2] == (1, 10, 16, 8, 32) and comm.calls[0][3] == 2
+    c = dry.calls
+    assert c.count("mode_conv3d_ex") == 2 and c.count("mode_conv3d_wgrad_ex") == 1

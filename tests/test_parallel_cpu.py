@@ -127,3 +127,27 @@ def _stage(rank, world):
 def test_d_sharded_stage_matches_unsharded():
     for err, scale in _spawn(_stage):
         assert err <= 2e-5 * max(scale, 1.0), (err, scale)
+
+
+# ---------------------------------------------------------------------------------- peer.TorchComm (exchange interface)
+def _comm_steps(rank, world):
+    from repmode_b200 import peer
+    comm = peer.TorchComm()
+    torch.manual_seed(5)
+    full = torch.randn(1, 6 * world, 3, 4, 2)
+    ext = comm.alloc("x", (1, 6 + 4, 3, 4, 2), torch.float32, "cpu")
+    ext[0, 2:8] = full[0, 6 * rank:6 * rank + 6]
+    comm.halo_fill(ext, 2, "t.x")
+    v = torch.arange(5, dtype=torch.float64) + rank
+    comm.all_reduce(v, "t.v")
+    return ext.clone(), v, full, comm.n_collectives
+
+
+def test_torch_comm_halo_fill_and_all_reduce():
+    out = _spawn(_comm_steps)
+    full = out[0][2]
+    padded = F.pad(full, [0, 0, 0, 0, 0, 0, 2, 2])
+    for r in range(2):
+        assert torch.equal(out[r][0], padded[:, 6 * r:6 * r + 10])
+        assert torch.equal(out[r][1], 2 * torch.arange(5, dtype=torch.float64) + 1)
+        assert out[r][3] == 2

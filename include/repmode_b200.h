@@ -233,6 +233,14 @@ int mode_f16_scale(const float* amax, float target, float* scale2, void* stream)
  *                        out[i] = slots[0][i] + slots[1][i] + ... in rank order (deterministic); double or float.
  *   mode_peer_enable_access: cudaDeviceEnablePeerAccess(current device -> peer_device); no-op when already enabled. */
 int mode_peer_enable_access(int32_t peer_device);
+/* Exchange arena of one rank: a zero-filled cudaMalloc block on the current device plus its 64-byte CUDA IPC handle
+ * (`handle64_host`, to be sent to the other ranks by any host channel); _open maps another rank's arena into THIS process
+ * with the current device as the accessing device (peer mapping over NVLink; also valid when both ranks share one GPU);
+ * _close unmaps it, _free releases the owner's block.  Set-up calls: they synchronise. */
+int mode_peer_arena_alloc(int64_t bytes, void** ptr_out, void* handle64_host);
+int mode_peer_arena_open(const void* handle64_host, void** ptr_out);
+int mode_peer_arena_close(void* ptr);
+int mode_peer_arena_free(void* ptr);
 int mode_peer_put(const void* const* src_host, void* const* dst_peer_host, void* const* signal_peer_host, int32_t n,
                   int64_t bytes, void* ticket, void* stream);
 int mode_peer_wait(const void* signal, void* expect, int32_t add, void* stream);

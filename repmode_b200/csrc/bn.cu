@@ -7,6 +7,9 @@
 // a multiple of the SM count, per-thread fp32 partials folded into fp64 block/global sums.
 #include <stdlib.h>
 
+#include <map>
+#include <mutex>
+
 #include "common.cuh"
 
 namespace mode {
@@ -216,7 +219,7 @@ __global__ void __launch_bounds__(BN_THREADS) bn_bwd_reduce_kernel(const float* 
                                                                    const float* __restrict__ beta,
                                                                    const float* __restrict__ mean,
                                                                    const float* __restrict__ invstd,
-                                                                   double* __restrict__ red, int* __restrict__ mx) {
+                                                                   double* __restrict__ red, long long* __restrict__ mx) {
     const int c = blockIdx.y;      // one channel per blockIdx.y (generic in C; strided reads hit L2 lines shared by
     const float mu = mean[c], is = invstd[c], ga = gamma ? gamma[c] : 1.f, be = beta ? beta[c] : 0.f;  // neighbours)
     double s = 0, q = 0;
@@ -244,7 +247,10 @@ __global__ void __launch_bounds__(BN_THREADS) bn_bwd_reduce_kernel(const float* 
         mdz = fmaxf(mdz, __shfl_xor_sync(0xffffffffu, mdz, st));
         mxh = fmaxf(mxh, __shfl_xor_sync(0xffffffffu, mxh, st));
     }
-    if ((threadIdx.x & 31) == 0) { atomicMax(mx + c, __float_as_int(mdz)); atomicMax(mx + C + c, __float_as_int(mxh)); }
+    if ((threadIdx.x & 31) == 0) {
+        atomicMax(mx + c, __double_as_longlong((double)mdz));
+        atomicMax(mx + C + c, __double_as_longlong((double)mxh));
+    }
 }
 
 // vectorised pass 1 for C % 4 == 0: thread t owns the 4 channels of float4 lane t % (C/4).  Four rows (8 independent 16-byte
@@ -258,7 +264,7 @@ __global__ void __launch_bounds__(BN_THREADS, 3) bn_bwd_reduce_vec_kernel(const 
                                                                           const float* __restrict__ beta,
                                                                           const float* __restrict__ mean,
                                                                           const float* __restrict__ invstd,
-                                                                          double* __restrict__ red, int* __restrict__ mx,
+                                                                          double* __restrict__ red, long long* __restrict__ mx,
                                                                           Planes pl, int64_t keep_vec) {
     const int vpr = C >> 2;
     const int rows_per_iter = BN_THREADS / vpr;
@@ -312,19 +318,20 @@ __global__ void __launch_bounds__(BN_THREADS, 3) bn_bwd_reduce_vec_kernel(const 
         atomicMax(&smx[C + lane_v * 4 + j], __float_as_int(mxh[j]));
     }
     block_fold_and_flush(ds, dq, C, vpr, red, sh);     // contains the __syncthreads that also orders smx
-    for (int i = threadIdx.x; i < 2 * C; i += BN_THREADS) atomicMax(mx + i, smx[i]);
+    for (int i = threadIdx.x; i < 2 * C; i += BN_THREADS)
+        atomicMax(mx + i, __double_as_longlong((double)__int_as_float(smx[i])));
 }
 
 // power-of-two fp16 scale for dy from the per-channel bound
 //   |dy_c| <= |gamma_c*invstd_c| * (max|dz|_c + |sum_dz_c|/M + max|xhat|_c * |sum_dzxhat_c|/M)
-__global__ void bn_bwd_scale_kernel(const double* __restrict__ red, const int* __restrict__ mx, long long M, int C,
+__global__ void bn_bwd_scale_kernel(const double* __restrict__ red, const double* __restrict__ mx, long long M, int C,
                                     const float* __restrict__ gamma, const float* __restrict__ invstd, float target,
                                     float* __restrict__ scale2) {
     float b = 0.f;
     for (int c = threadIdx.x; c < C; c += blockDim.x) {
         const float ga = gamma ? gamma[c] : 1.f;
         const float a = fabsf((float)(red[c] / (double)M)), bb = fabsf((float)(red[C + c] / (double)M));
-        b = fmaxf(b, fabsf(ga * invstd[c]) * (__int_as_float(mx[c]) + a + __int_as_float(mx[C + c]) * bb));
+        b = fmaxf(b, fabsf(ga * invstd[c]) * ((float)mx[c] + a + (float)mx[C + c] * bb));
     }
     __shared__ float sh[256];
     sh[threadIdx.x] = b;
@@ -516,6 +523,28 @@ __global__ void f16_scale_kernel(const float* __restrict__ amax, float target, f
 
 // Grid of a grid-stride streaming kernel: enough blocks for the work, at most 8 per SM, and a whole number of blocks per
 // SM (a ragged last wave -- e.g. 1024 blocks on 148 SMs -- costs up to half the kernel's time).
+// Grid of exactly ONE resident wave of a grid-stride kernel: occupancy x SM count blocks (or fewer when the work is small).
+// r2d capture: with 8 blocks per SM on kernels whose registers allow 3-4, the launch runs as two waves of ~10 us each and the
+// drain / refill between them costs these 20-40 us streaming kernels a fifth of their time (DRAM throughput 40-50 % of peak
+// while a plain copy reaches 82 %).
+template <typename K>
+static int wave_grid(K kernel, int threads, int64_t want_blocks) {
+    static std::mutex mu;
+    static std::map<const void*, int> cache;
+    int per_sm = 0;
+    {
+        std::lock_guard<std::mutex> lock(mu);
+        auto it = cache.find((const void*)kernel);
+        if (it != cache.end()) per_sm = it->second;
+    }
+    if (per_sm == 0) {
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, 0) != cudaSuccess || per_sm < 1) per_sm = 2;
+        std::lock_guard<std::mutex> lock(mu);
+        cache[(const void*)kernel] = per_sm;
+    }
+    return (int)max((int64_t)1, min(want_blocks, (int64_t)per_sm * sm_count()));
+}
+
 static int stream_grid(int64_t work_items, int per_block) {
     const int64_t want = ceil_div(work_items, per_block);
     const int64_t sms = sm_count();
@@ -562,12 +591,12 @@ extern "C" int mode_bn_apply_relu(const float* y, int64_t M, int32_t C, const fl
     const bool aligned = ((reinterpret_cast<uintptr_t>(y) | reinterpret_cast<uintptr_t>(out)) & 15) == 0 &&
                          (reinterpret_cast<uintptr_t>(out_f16) & 7) == 0;
     if ((C & 3) == 0 && aligned) {
-        const int grid = stream_grid(total / 4, BN_THREADS * 4);
+        const int64_t want = ceil_div(total / 4, BN_THREADS * 4);
         if (planes)
-            bn_apply_kernel<true><<<grid, BN_THREADS, 0, st>>>(y, total, C, scale, shift, relu, out, (__half*)out_f16,
+            bn_apply_kernel<true><<<wave_grid(bn_apply_kernel<true>, BN_THREADS, want), BN_THREADS, 0, st>>>(y, total, C, scale, shift, relu, out, (__half*)out_f16,
                                                                f16_scale, to_planes(planes));
         else
-            bn_apply_kernel<false><<<grid, BN_THREADS, 0, st>>>(y, total, C, scale, shift, relu, out, (__half*)out_f16,
+            bn_apply_kernel<false><<<wave_grid(bn_apply_kernel<false>, BN_THREADS, want), BN_THREADS, 0, st>>>(y, total, C, scale, shift, relu, out, (__half*)out_f16,
                                                                 f16_scale, Planes{});
     } else {
         if (planes) MODE_FAIL("mode_bn_apply_relu: plane ranges need C %% 4 == 0 and 16-byte aligned tensors");
@@ -578,7 +607,9 @@ extern "C" int mode_bn_apply_relu(const float* y, int64_t M, int32_t C, const fl
     return 0;
 }
 
-extern "C" int64_t mode_bn_bwd_workspace_bytes(int32_t C) { return (int64_t)C * (2 * sizeof(double) + 2 * sizeof(int)); }
+// {sum dz, sum dz*xhat}[C] then {max |dz|, max |xhat|}[C], ALL doubles: one contiguous fp64 vector a D-sharded caller can
+// all-reduce (sum) in one step -- the sum of the ranks' maxima bounds the global maximum, which is all the fp16 scale needs
+extern "C" int64_t mode_bn_bwd_workspace_bytes(int32_t C) { return (int64_t)C * 4 * sizeof(double); }
 
 extern "C" int mode_bn_relu_bwd_reduce(const float* y, const float* dout, int64_t M, int32_t C, const float* gamma,
                                        const float* beta, const float* mean, const float* invstd,
@@ -587,24 +618,19 @@ extern "C" int mode_bn_relu_bwd_reduce(const float* y, const float* dout, int64_
         MODE_FAIL("mode_bn_relu_bwd_reduce: bad arguments (C=%d)", C);
     cudaStream_t st = (cudaStream_t)stream;
     double* workspace = (double*)workspace_v;
-    int* mx = (int*)(workspace + 2 * (size_t)C);
+    long long* mx = (long long*)(workspace + 2 * (size_t)C);
     MODE_CUDA(cudaMemsetAsync(workspace_v, 0, (size_t)mode_bn_bwd_workspace_bytes(C), st));
     const int vpr = C >> 2;
     const bool aligned = ((reinterpret_cast<uintptr_t>(y) | reinterpret_cast<uintptr_t>(dout)) & 15) == 0;
     if ((C & 3) == 0 && vpr <= BN_THREADS && BN_THREADS % vpr == 0 && aligned) {
         const int rpi = BN_THREADS / vpr;
-        int grid = stream_grid(M, rpi * 16);
+        const int64_t want = ceil_div(M, rpi * 4);
         const int64_t keep_vec = std::min<int64_t>(M * C / 4, l2_keep_bytes() / 16) / vpr * vpr;   // whole rows
-        // A/B knob for the next measurement round: blocks per SM of the reduce pass.  Today's heuristic launches 6 short
-        // blocks per SM (3 waves at 2 resident), each ending in 2*C fp64 atomics on the same addresses; the pass runs at
-        // 3.6 TB/s while the apply pass over the same tensors reaches 5.4 (profiles/r1_final_ncu_full_summary.csv).
-        static const int bps = getenv("REPMODE_BN_REDUCE_BPS") ? atoi(getenv("REPMODE_BN_REDUCE_BPS")) : 0;
-        if (bps > 0) grid = (int)min((int64_t)grid, (int64_t)sm_count() * bps);
         if (planes)
-            bn_bwd_reduce_vec_kernel<true><<<grid, BN_THREADS, 0, st>>>(y, dout, M, C, gamma, beta, mean, invstd,
+            bn_bwd_reduce_vec_kernel<true><<<wave_grid(bn_bwd_reduce_vec_kernel<true>, BN_THREADS, want), BN_THREADS, 0, st>>>(y, dout, M, C, gamma, beta, mean, invstd,
                                                                         workspace, mx, to_planes(planes), keep_vec);
         else
-            bn_bwd_reduce_vec_kernel<false><<<grid, BN_THREADS, 0, st>>>(y, dout, M, C, gamma, beta, mean, invstd,
+            bn_bwd_reduce_vec_kernel<false><<<wave_grid(bn_bwd_reduce_vec_kernel<false>, BN_THREADS, want), BN_THREADS, 0, st>>>(y, dout, M, C, gamma, beta, mean, invstd,
                                                                          workspace, mx, Planes{}, keep_vec);
     } else {
         if (planes) MODE_FAIL("mode_bn_relu_bwd_reduce: plane ranges need C %% 4 == 0 and 16-byte aligned tensors");
@@ -624,7 +650,7 @@ extern "C" int mode_bn_relu_bwd_apply(const float* y, const float* dout, int64_t
     if (dy_f16 && !dy_scale2) MODE_FAIL("mode_bn_relu_bwd_apply: dy_f16 needs dy_scale2");
     cudaStream_t st = (cudaStream_t)stream;
     double* workspace = (double*)workspace_v;
-    int* mx = (int*)(workspace + 2 * (size_t)C);
+    const double* mx = workspace + 2 * (size_t)C;
     const long long m_div = planes ? (long long)planes->m_global : (long long)M;
     if (dy_f16) {
         bn_bwd_scale_kernel<<<1, 256, 0, st>>>(workspace, mx, m_div, C, gamma, invstd, 8192.f, dy_scale2);
@@ -634,13 +660,13 @@ extern "C" int mode_bn_relu_bwd_apply(const float* y, const float* dout, int64_t
     const bool vec_ok = (C & 3) == 0 && aligned && ((reinterpret_cast<uintptr_t>(dy) & 15) == 0) &&
                         ((reinterpret_cast<uintptr_t>(dy_f16) & 7) == 0);
     if (vec_ok) {
-        const int grid = stream_grid(M * C / 4, BN_THREADS * 4);
+        const int64_t want = ceil_div(M * C / 4, BN_THREADS * 2);
         if (planes)
-            bn_bwd_apply_vec_kernel<true><<<grid, BN_THREADS, 0, st>>>(y, dout, M, C, gamma, beta, mean, invstd, workspace,
+            bn_bwd_apply_vec_kernel<true><<<wave_grid(bn_bwd_apply_vec_kernel<true>, BN_THREADS, want), BN_THREADS, 0, st>>>(y, dout, M, C, gamma, beta, mean, invstd, workspace,
                                                                        dgamma, dbeta, dy, (__half*)dy_f16, dy_scale2,
                                                                        to_planes(planes), m_div);
         else
-            bn_bwd_apply_vec_kernel<false><<<grid, BN_THREADS, 0, st>>>(y, dout, M, C, gamma, beta, mean, invstd,
+            bn_bwd_apply_vec_kernel<false><<<wave_grid(bn_bwd_apply_vec_kernel<false>, BN_THREADS, want), BN_THREADS, 0, st>>>(y, dout, M, C, gamma, beta, mean, invstd,
                                                                         workspace, dgamma, dbeta, dy, (__half*)dy_f16,
                                                                         dy_scale2, Planes{}, m_div);
     } else {
@@ -666,7 +692,7 @@ extern "C" int mode_cast_f16(const float* src, void* dst_f16, int64_t n, float s
     if (!src || !dst_f16 || n <= 0) MODE_FAIL("mode_cast_f16: bad arguments");
     if ((reinterpret_cast<uintptr_t>(src) & 15) || (reinterpret_cast<uintptr_t>(dst_f16) & 7))
         MODE_FAIL("mode_cast_f16: pointers must be 16-byte (src) / 8-byte (dst) aligned");
-    cast_f16_kernel<<<stream_grid(n / 4 + 1, 256 * 4), 256, 0, (cudaStream_t)stream>>>(src, (__half*)dst_f16, n, scale,
+    cast_f16_kernel<<<wave_grid(cast_f16_kernel, 256, ceil_div(n / 4 + 1, 256 * 4)), 256, 0, (cudaStream_t)stream>>>(src, (__half*)dst_f16, n, scale,
                                                                                          scale_dev);
     MODE_LAUNCH_CHECK();
     return 0;

@@ -556,7 +556,7 @@ int conv3d_umma(const __half* x, const __half* w, const int32_t* sample_u, float
     P.TD = max(1, min(min(256 / P.Nt, 8), D));
     P.ring = P.TD + 4;
     const int wst_bytes = 5 * P.Nt * cu::ROWB;
-    const int budget = 227 * 1024 - 1024 - P.ring * cu::PLANE_BYTES - 1024 - 4096;
+    const int budget = 227 * 1024 - 1024 - P.ring * cu::PLANE_BYTES - 1024 - 4096 - 2048;    // barriers, BN sums, epilogue affine
     P.wstages = min(cu::MAX_WST, budget / wst_bytes);
     if (P.wstages < 2) MODE_FAIL("conv3d_umma: shared memory budget too small for Nt=%d", P.Nt);
     const SmemLayout L = smem_layout(P.ring, P.wstages, P.Nt);

@@ -12,6 +12,8 @@
 // Buffers are reused every step; the write-after-read hazard is closed by the step's own data dependencies (nobody starts
 // step s+1 before the gradient exchange of step s, which every rank enters only after its last read of step s' halos).
 // HBM/NVLink-bound copies: 16-byte vector accesses, grid sized to the payload.
+#include <string.h>
+
 #include <algorithm>
 
 #include "common.cuh"
@@ -63,7 +65,16 @@ __global__ void __launch_bounds__(256) peer_put_kernel(PutList L, uint32_t* tick
     const int seg = blockIdx.y;
     const uint4* __restrict__ s = L.src[seg];
     uint4* __restrict__ d = L.dst[seg];
-    for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < L.vec; i += (long long)gridDim.x * 256) d[i] = s[i];
+    const long long stride = (long long)gridDim.x * 256;
+    for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < L.vec; i += 4 * stride) {      // 4 loads in flight
+        uint4 v[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+            if (i + u * stride < L.vec) v[u] = s[i + u * stride];
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+            if (i + u * stride < L.vec) d[i + u * stride] = v[u];
+    }
     SignalList sg;
     sg.n = L.n;
     for (int i = 0; i < 8; ++i) sg.p[i] = L.sig[i];
@@ -104,6 +115,48 @@ __global__ void __launch_bounds__(256) peer_sum_slots_kernel(const T* __restrict
 }  // namespace mode
 
 using namespace mode;
+
+// ---- exchange arena: one cudaMalloc block per rank, exported / imported through CUDA IPC ------------------------------
+// The import happens with the IMPORTING rank's device current and cudaIpcMemLazyEnablePeerAccess, so the mapping is a
+// peer (NVLink) mapping usable by kernels of this device.  (r2d2: a mapping opened under the OWNER's device -- what
+// torch's storage sharing does -- faults when a kernel of another GPU stores through it.)
+extern "C" int mode_peer_arena_alloc(int64_t bytes, void** ptr_out, void* handle64_host) {
+    if (bytes <= 0 || !ptr_out || !handle64_host) MODE_FAIL("mode_peer_arena_alloc: bad arguments");
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    void* p = nullptr;
+    MODE_CUDA(cudaMalloc(&p, (size_t)bytes));
+    MODE_CUDA(cudaMemset(p, 0, (size_t)bytes));
+    MODE_CUDA(cudaDeviceSynchronize());
+    cudaIpcMemHandle_t h;
+    cudaError_t e = cudaIpcGetMemHandle(&h, p);
+    if (e != cudaSuccess) {
+        cudaFree(p);
+        MODE_FAIL("mode_peer_arena_alloc: cudaIpcGetMemHandle -> %s", cudaGetErrorString(e));
+    }
+    memcpy(handle64_host, &h, sizeof(h));
+    *ptr_out = p;
+    return 0;
+}
+
+extern "C" int mode_peer_arena_open(const void* handle64_host, void** ptr_out) {
+    if (!handle64_host || !ptr_out) MODE_FAIL("mode_peer_arena_open: bad arguments");
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle64_host, sizeof(h));
+    void* p = nullptr;
+    MODE_CUDA(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+    *ptr_out = p;
+    return 0;
+}
+
+extern "C" int mode_peer_arena_close(void* ptr) {
+    if (ptr) MODE_CUDA(cudaIpcCloseMemHandle(ptr));
+    return 0;
+}
+
+extern "C" int mode_peer_arena_free(void* ptr) {
+    if (ptr) MODE_CUDA(cudaFree(ptr));
+    return 0;
+}
 
 extern "C" int mode_peer_enable_access(int32_t peer_device) {
     int dev = 0;

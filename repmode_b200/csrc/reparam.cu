@@ -121,94 +121,107 @@ __global__ void __launch_bounds__(256) reparam_fwd_kernel(mode_layer_t L, const 
     }
 }
 
-// K1 for WIDE layers -- EXPERIMENTAL (REPMODE_K1_WIDE=1; not yet run on a GPU, written after round 1's GPU budget was spent).
-// reparam_fwd_kernel above moves 4.8 KB per block through three barrier phases: on 512 -> 512 (40 960 blocks) it is
-// latency-bound at 1.14 TB/s = 17 % of HBM (profiles/r1h_bench.json).  Here one block owns RB = 4 output channels x one
-// 32-channel chunk x ALL 125 taps: the four [32 ci][125] expert slabs are contiguous 16 KB runs (read with plain
-// coalesced loads into shared memory), the mix is done in place with the SAME expressions and association order as
-// above (bit-identical W_eff), and the pack is written in 256-byte (fp16) / 512-byte (fp32) contiguous runs: 4 rows x
-// 32 columns per (chunk, tap).  78 KB of shared memory per block: two to three blocks per SM overlap load and store.
-// grid (Co / 4, Ci / 32, U), block 256.
-constexpr int K1W_RB = 4;
+// K1, row-block form (the default whenever Ci % 32 == 0 and Co % K1R_ROWS == 0): one block owns K1R_ROWS output channels x
+// one 32-channel chunk x ALL 125 taps and loops over the U gate inputs, so the experts are read from HBM exactly ONCE per
+// step however many distinct tasks the batch holds.  Why this shape (r2a: reparam_fwd_kernel above reaches 1.14 TB/s = 17 %
+// of HBM on 512 -> 512, the 4-row staging variant tried first 0.81 TB/s): the expert slab of a (row, chunk) is ONE contiguous
+// 16 000-byte run of k5 plus 3 456 bytes of k3, so the load phase is ten independent 16-byte loads per thread issued back
+// to back (40 KB in flight per block, 5 blocks per SM), a single barrier, then the mix straight out of shared memory into
+// 128-byte (fp16) / 256-byte (fp32) contiguous pack stores: 2 rows x 32 columns per (chunk, tap).  Shared-memory rows have
+// odd strides (125 / 27 floats) so the transposing reads are conflict free.  Same expressions and association order as
+// reparam_fwd_kernel: bit-identical W_eff.
+// grid (Co / K1R_ROWS, Ci / 32), block 256.
+constexpr int K1R_ROWS = 2;
 template <typename OutT>
-__global__ void __launch_bounds__(256) reparam_fwd_wide_kernel(mode_layer_t L, const int32_t* __restrict__ task_ids,
-                                                               const float* __restrict__ t_dense,
+__global__ void __launch_bounds__(256) reparam_fwd_rows_kernel(mode_layer_t L, const int32_t* __restrict__ task_ids,
+                                                               const float* __restrict__ t_dense, int U,
                                                                float* __restrict__ g_out, OutT* __restrict__ w_fwd,
                                                                float w_scale, const float* __restrict__ w_scale_dev,
                                                                int rows_pad) {
-    extern __shared__ float k1w_smem[];
-    float* s5 = k1w_smem;                               // [RB][32][125]
-    float* s3 = s5 + K1W_RB * 32 * 125;                 // [RB][32][27]
-    float* s1 = s3 + K1W_RB * 32 * 27;                  // [3][RB][32]: k1, a3, a5
-    float* sg = s1 + 3 * K1W_RB * 32;                   // [RB][5]
-    const int o0 = blockIdx.x * K1W_RB, ic = blockIdx.y, u = blockIdx.z;
+    __shared__ __align__(16) float s5[K1R_ROWS * 32 * 125];
+    __shared__ __align__(16) float s3[K1R_ROWS * 32 * 27];
+    __shared__ __align__(16) float s1[3 * K1R_ROWS * 32];     // k1, a3, a5
+    __shared__ float sg[K1R_ROWS * MODE_NUM_EXPERTS];
+    const int o0 = blockIdx.x * K1R_ROWS, ic = blockIdx.y;
     const int Ci = L.ci, Co = L.co, T = L.num_tasks;
     const int tid = threadIdx.x;
-
-    // gate column + bias -> softmax over the 5 experts, one thread per output channel (RepMode.py:198-200)
-    if (tid < K1W_RB) {
-        const int o = o0 + tid;
-        float lg[MODE_NUM_EXPERTS];
-        for (int e = 0; e < MODE_NUM_EXPERTS; ++e) {
-            const int row = e * Co + o;
-            if (task_ids != nullptr) {
-                lg[e] = __fadd_rn(L.gate_w[(size_t)row * T + task_ids[u]], L.gate_b[row]);
-            } else {
-                float acc = 0.f;
-                for (int t = 0; t < T; ++t) acc = fmaf(t_dense[(size_t)u * T + t], L.gate_w[(size_t)row * T + t], acc);
-                lg[e] = acc + L.gate_b[row];
-            }
+    // ---- load phase: contiguous slabs, 16-byte loads, all issued before the first use
+    {
+        constexpr int V5 = 32 * 125 / 4, V3 = 32 * 27 / 4;     // float4 per row slab: 1000, 216
+        float4 r5[K1R_ROWS][4], r3[K1R_ROWS];
+#pragma unroll
+        for (int r = 0; r < K1R_ROWS; ++r) {
+            const size_t oc0 = (size_t)(o0 + r) * Ci + (size_t)ic * 32;
+            const float4* src5 = reinterpret_cast<const float4*>(L.k5 + oc0 * 125);
+            const float4* src3 = reinterpret_cast<const float4*>(L.k3 + oc0 * 27);
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+                if (tid + 256 * k < V5) r5[r][k] = src5[tid + 256 * k];
+            if (tid < V3) r3[r] = src3[tid];
         }
-        float m = lg[0];
-        for (int e = 1; e < MODE_NUM_EXPERTS; ++e) m = fmaxf(m, lg[e]);
-        float ex[MODE_NUM_EXPERTS], ssum = 0.f;
-        for (int e = 0; e < MODE_NUM_EXPERTS; ++e) { ex[e] = expf(lg[e] - m); ssum += ex[e]; }
-        for (int e = 0; e < MODE_NUM_EXPERTS; ++e) {
-            const float gv = ex[e] / ssum;
-            sg[tid * MODE_NUM_EXPERTS + e] = gv;
-            if (ic == 0 && g_out != nullptr) g_out[((size_t)u * MODE_NUM_EXPERTS + e) * Co + o] = gv;
+        float v1 = 0.f;
+        if (tid < 3 * K1R_ROWS * 32) {
+            const int which = tid / (K1R_ROWS * 32), r = (tid / 32) % K1R_ROWS, i = tid & 31;
+            const float* src = which == 0 ? L.k1 : (which == 1 ? L.a3 : L.a5);
+            v1 = src[(size_t)(o0 + r) * Ci + (size_t)ic * 32 + i];
         }
+#pragma unroll
+        for (int r = 0; r < K1R_ROWS; ++r) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+                if (tid + 256 * k < V5) reinterpret_cast<float4*>(s5 + r * 32 * 125)[tid + 256 * k] = r5[r][k];
+            if (tid < V3) reinterpret_cast<float4*>(s3 + r * 32 * 27)[tid] = r3[r];
+        }
+        if (tid < 3 * K1R_ROWS * 32) s1[tid] = v1;
     }
-    // expert slabs of this (4 rows, 32-channel chunk): contiguous runs per row
-    for (int r = 0; r < K1W_RB; ++r) {
-        const size_t oc0 = (size_t)(o0 + r) * Ci + (size_t)ic * 32;
-        const float* src5 = L.k5 + oc0 * 125;
-        for (int idx = tid; idx < 32 * 125; idx += 256) s5[r * 32 * 125 + idx] = src5[idx];
-        const float* src3 = L.k3 + oc0 * 27;
-        for (int idx = tid; idx < 32 * 27; idx += 256) s3[r * 32 * 27 + idx] = src3[idx];
-        if (tid < 32) {
-            s1[(0 * K1W_RB + r) * 32 + tid] = L.k1[oc0 + tid];
-            s1[(1 * K1W_RB + r) * 32 + tid] = L.a3[oc0 + tid];
-            s1[(2 * K1W_RB + r) * 32 + tid] = L.a5[oc0 + tid];
-        }
-    }
-    __syncthreads();
     if (w_scale_dev != nullptr) w_scale *= *w_scale_dev;
     const float c3 = 1.0f / 27, c5 = 1.0f / 125;               // fp32-rounded pool constants (RepMode.py:161-163)
-    // mix in place: s5[r][i][tap] <- W_eff
-    for (int idx = tid; idx < K1W_RB * 32 * 125; idx += 256) {
-        const int r = idx / (32 * 125), rem = idx - r * (32 * 125);
-        const int i = rem / 125, tap = rem - i * 125;
-        const float* g = sg + r * MODE_NUM_EXPERTS;
-        const int kd = tap / 25, kh = (tap / 5) % 5, kw = tap % 5;
-        const bool inner = (kd >= 1 && kd <= 3 && kh >= 1 && kh <= 3 && kw >= 1 && kw <= 3);
-        const float t0 = __fmul_rn(s5[idx], g[0]);
-        float t1 = 0.f, t2 = 0.f, t3 = 0.f;
-        if (inner) {
-            t1 = __fmul_rn(s3[(r * 32 + i) * 27 + ((kd - 1) * 3 + (kh - 1)) * 3 + (kw - 1)], g[1]);
-            t3 = __fmul_rn(__fmul_rn(s1[(1 * K1W_RB + r) * 32 + i], c3), g[3]);
-        }
-        if (tap == 62) t2 = __fmul_rn(s1[(0 * K1W_RB + r) * 32 + i], g[2]);
-        const float t4 = __fmul_rn(__fmul_rn(s1[(2 * K1W_RB + r) * 32 + i], c5), g[4]);
-        // reference association order: ((((e5 + e3) + e1) + ea3) + ea5)   (RepMode.py:184-188)
-        s5[idx] = __fadd_rn(__fadd_rn(__fadd_rn(__fadd_rn(t0, t1), t2), t3), t4);
-    }
-    __syncthreads();
-    // pack: thread -> (tap, row, column); 4 rows x 32 columns of one (chunk, tap) are one contiguous run of the pack
     const int nci = gridDim.y;
-    for (int idx = tid; idx < 125 * K1W_RB * 32; idx += 256) {
-        const int col = idx & 31, r = (idx >> 5) % K1W_RB, tap = idx / (32 * K1W_RB);
-        store_w(w_fwd + pack_index<OutT>(u, tap, ic, nci, o0 + r, rows_pad, col), s5[(r * 32 + col) * 125 + tap] * w_scale);
+    for (int u = 0; u < U; ++u) {
+        __syncthreads();                                       // slabs landed (u = 0) / previous sg consumed (u > 0)
+        // gate column + bias -> softmax over the 5 experts, one thread per output channel (RepMode.py:198-200)
+        if (tid < K1R_ROWS) {
+            const int o = o0 + tid;
+            float lg[MODE_NUM_EXPERTS];
+            for (int e = 0; e < MODE_NUM_EXPERTS; ++e) {
+                const int row = e * Co + o;
+                if (task_ids != nullptr) {
+                    lg[e] = __fadd_rn(L.gate_w[(size_t)row * T + task_ids[u]], L.gate_b[row]);
+                } else {
+                    float acc = 0.f;
+                    for (int t = 0; t < T; ++t) acc = fmaf(t_dense[(size_t)u * T + t], L.gate_w[(size_t)row * T + t], acc);
+                    lg[e] = acc + L.gate_b[row];
+                }
+            }
+            float m = lg[0];
+            for (int e = 1; e < MODE_NUM_EXPERTS; ++e) m = fmaxf(m, lg[e]);
+            float ex[MODE_NUM_EXPERTS], ssum = 0.f;
+            for (int e = 0; e < MODE_NUM_EXPERTS; ++e) { ex[e] = expf(lg[e] - m); ssum += ex[e]; }
+            for (int e = 0; e < MODE_NUM_EXPERTS; ++e) {
+                const float gv = ex[e] / ssum;
+                sg[tid * MODE_NUM_EXPERTS + e] = gv;
+                if (ic == 0 && g_out != nullptr) g_out[((size_t)u * MODE_NUM_EXPERTS + e) * Co + o] = gv;
+            }
+        }
+        __syncthreads();
+        // mix + pack: thread -> (tap, row, column); K1R_ROWS rows x 32 columns of one (chunk, tap) are one contiguous run
+        for (int idx = tid; idx < 125 * K1R_ROWS * 32; idx += 256) {
+            const int col = idx & 31, r = (idx >> 5) % K1R_ROWS, tap = idx / (32 * K1R_ROWS);
+            const float* g = sg + r * MODE_NUM_EXPERTS;
+            const int kd = tap / 25, kh = (tap / 5) % 5, kw = tap % 5;
+            const bool inner = (kd >= 1 && kd <= 3 && kh >= 1 && kh <= 3 && kw >= 1 && kw <= 3);
+            const float t0 = __fmul_rn(s5[(r * 32 + col) * 125 + tap], g[0]);
+            float t1 = 0.f, t2 = 0.f, t3 = 0.f;
+            if (inner) {
+                t1 = __fmul_rn(s3[(r * 32 + col) * 27 + ((kd - 1) * 3 + (kh - 1)) * 3 + (kw - 1)], g[1]);
+                t3 = __fmul_rn(__fmul_rn(s1[(1 * K1R_ROWS + r) * 32 + col], c3), g[3]);
+            }
+            if (tap == 62) t2 = __fmul_rn(s1[(0 * K1R_ROWS + r) * 32 + col], g[2]);
+            const float t4 = __fmul_rn(__fmul_rn(s1[(2 * K1R_ROWS + r) * 32 + col], c5), g[4]);
+            // reference association order: ((((e5 + e3) + e1) + ea3) + ea5)   (RepMode.py:184-188)
+            const float val = __fadd_rn(__fadd_rn(__fadd_rn(__fadd_rn(t0, t1), t2), t3), t4);
+            store_w(w_fwd + pack_index<OutT>(u, tap, ic, nci, o0 + r, rows_pad, col), val * w_scale);
+        }
     }
 }
 
@@ -235,8 +248,9 @@ __global__ void __launch_bounds__(256) pack_dgrad_kernel(const T* __restrict__ s
     }
 }
 
-// K1b main kernel. grid (Co, ceil(Ci/32)), block 128. Loops over the samples; every global access is a
-// contiguous segment (dW rows of 32 ci, expert slabs of 32*125 floats).
+// K1b main kernel. grid (ceil(Ci/32), Co), block 128 -- the ci chunk is the FAST grid index, so blocks that run together
+// read neighbouring 128-byte segments of the same d_weff rows (DRAM page locality). Loops over the samples; every global
+// access is a contiguous segment (dW rows of 32 ci, expert slabs of 32*125 floats).
 __global__ void __launch_bounds__(128) reparam_bwd_kernel(mode_layer_t L, const int32_t* __restrict__ sample_u,
                                                           int n_samples, const float* __restrict__ g,
                                                           const float* __restrict__ d_weff,
@@ -248,7 +262,7 @@ __global__ void __launch_bounds__(128) reparam_bwd_kernel(mode_layer_t L, const 
     __shared__ float sdk3[32 * 27];
     __shared__ float s_all[32], s_inner[32], s_center[32];
     __shared__ float s_dg[2];
-    const int o = blockIdx.x, ic = blockIdx.y;
+    const int ic = blockIdx.x, o = blockIdx.y;
     const int Ci = L.ci, Co = L.co;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int c = ic * 32 + lane;
@@ -417,22 +431,20 @@ extern "C" int mode_reparam_fwd(const mode_layer_t* L, const int32_t* task_ids, 
     cudaStream_t st = (cudaStream_t)stream;
     const int nci = (int)ceil_div(L->ci, 32), nco = (int)ceil_div(L->co, 32);
     dim3 grid(L->co, nci, U * 5);
-    // experimental wide-layer kernel (REPMODE_K1_WIDE=1): whole 32-channel chunks, 4 output channels per block
-    const char* wide_env = getenv("REPMODE_K1_WIDE");          // read per call so that a test can A/B both kernels
-    const bool wide_on = wide_env != nullptr && wide_env[0] == '1';
-    const bool wide = wide_on && L->ci % 32 == 0 && L->co % K1W_RB == 0 && (int64_t)L->ci * L->co >= 128 * 128 &&
-                      U <= 65535;
-    const int wide_smem = (K1W_RB * 32 * (125 + 27 + 3) + K1W_RB * MODE_NUM_EXPERTS) * (int)sizeof(float);
-    const dim3 wgrid(L->co / K1W_RB, nci, U);
+    // row-block kernel (experts read once for all U gate inputs) whenever the chunk is whole; REPMODE_K1_ROWS=0 forces the
+    // per-(row, kd slice) kernel (read per call so that a test can A/B both)
+    const char* rows_env = getenv("REPMODE_K1_ROWS");
+    const bool rows_on = !(rows_env != nullptr && rows_env[0] == '0');
+    const bool rows = rows_on && L->ci % 32 == 0 && L->co % K1R_ROWS == 0 &&
+                      ((reinterpret_cast<uintptr_t>(L->k5) | reinterpret_cast<uintptr_t>(L->k3)) & 15) == 0;
+    const dim3 rgrid(L->co / K1R_ROWS, nci);
     if (w_dtype == MODE_F32) {
-        if (wide) {
-            MODE_CUDA(cudaFuncSetAttribute(reparam_fwd_wide_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, wide_smem));
-            reparam_fwd_wide_kernel<float><<<wgrid, 256, wide_smem, st>>>(*L, task_ids, t_dense, g_out, (float*)w_fwd,
-                                                                          w_scale, w_scale_dev, L->co);
-        } else {
+        if (rows)
+            reparam_fwd_rows_kernel<float><<<rgrid, 256, 0, st>>>(*L, task_ids, t_dense, U, g_out, (float*)w_fwd, w_scale,
+                                                                  w_scale_dev, L->co);
+        else
             reparam_fwd_kernel<float><<<grid, 256, 0, st>>>(*L, task_ids, t_dense, g_out, (float*)w_fwd, w_scale,
                                                             w_scale_dev, L->co);
-        }
         MODE_LAUNCH_CHECK();
         if (w_dgrad) {
             pack_dgrad_kernel<float><<<dim3(nci, nco, U * 125), dim3(32, 8), 0, st>>>((const float*)w_fwd,
@@ -441,14 +453,12 @@ extern "C" int mode_reparam_fwd(const mode_layer_t* L, const int32_t* task_ids, 
             MODE_LAUNCH_CHECK();
         }
     } else if (w_dtype == MODE_F16) {
-        if (wide) {
-            MODE_CUDA(cudaFuncSetAttribute(reparam_fwd_wide_kernel<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, wide_smem));
-            reparam_fwd_wide_kernel<__half><<<wgrid, 256, wide_smem, st>>>(*L, task_ids, t_dense, g_out, (__half*)w_fwd,
-                                                                           w_scale, w_scale_dev, nco * 32);
-        } else {
+        if (rows)
+            reparam_fwd_rows_kernel<__half><<<rgrid, 256, 0, st>>>(*L, task_ids, t_dense, U, g_out, (__half*)w_fwd, w_scale,
+                                                                   w_scale_dev, nco * 32);
+        else
             reparam_fwd_kernel<__half><<<grid, 256, 0, st>>>(*L, task_ids, t_dense, g_out, (__half*)w_fwd, w_scale,
                                                              w_scale_dev, nco * 32);
-        }
         MODE_LAUNCH_CHECK();
         if (w_dgrad) {
             pack_dgrad_kernel<__half><<<dim3(nci, nco, U * 125), dim3(32, 8), 0, st>>>((const __half*)w_fwd,
@@ -476,7 +486,7 @@ extern "C" int mode_reparam_bwd(const mode_layer_t* L, const int32_t* task_ids, 
     (void)U;
     cudaStream_t st = (cudaStream_t)stream;
     const int nci = (int)ceil_div(L->ci, 32);
-    reparam_bwd_kernel<<<dim3(L->co, nci), 128, 0, st>>>(*L, sample_u, n_samples, g, d_weff, dk5, dk3, dk1, da3, da5,
+    reparam_bwd_kernel<<<dim3(nci, L->co), 128, 0, st>>>(*L, sample_u, n_samples, g, d_weff, dk5, dk3, dk1, da3, da5,
                                                         (float*)workspace);
     MODE_LAUNCH_CHECK();
     gate_bwd_kernel<<<(unsigned)ceil_div(L->co, 128), 128, 0, st>>>(*L, task_ids, t_dense, sample_u, n_samples, nci, g,

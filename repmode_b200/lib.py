@@ -92,6 +92,10 @@ SIGNATURES = {
     "mode_conv3d_wgrad_ex": (ctypes.c_int, [_vp, _vp, ctypes.c_int, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _f32, _vp,
                                             _vp, _i32, _i32, _i32, _vp]),
     "mode_peer_enable_access": (ctypes.c_int, [_i32]),
+    "mode_peer_arena_alloc": (ctypes.c_int, [_i64, ctypes.POINTER(ctypes.c_void_p), _vp]),
+    "mode_peer_arena_open": (ctypes.c_int, [_vp, ctypes.POINTER(ctypes.c_void_p)]),
+    "mode_peer_arena_close": (ctypes.c_int, [_vp]),
+    "mode_peer_arena_free": (ctypes.c_int, [_vp]),
     "mode_peer_put": (ctypes.c_int, [_vp, _vp, _vp, _i32, _i64, _vp, _vp]),
     "mode_peer_wait": (ctypes.c_int, [_vp, _vp, _i32, _vp]),
     "mode_peer_sum_slots": (ctypes.c_int, [_vp, _i32, _i64, _i32, _vp, _vp, _vp, _vp, _vp]),

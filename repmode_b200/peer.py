@@ -104,6 +104,14 @@ class TorchComm:
             dist.barrier(group=self.group)
 
 
+class _RawCuda:
+    """A raw device allocation presented through __cuda_array_interface__ so that torch can view it (no ownership)."""
+
+    def __init__(self, ptr, nbytes):
+        self.__cuda_array_interface__ = {"shape": (int(nbytes),), "typestr": "|u1", "data": (int(ptr), False), "version": 3,
+                                         "strides": None}
+
+
 class PeerComm:
     """Exchange steps as stores into peer memory (csrc/peer.cu).  Every rank allocates ONE arena, shares it through CUDA
     IPC and opens the arenas of the others; `alloc` carves named, identically laid out buffers out of it, so the address
@@ -121,27 +129,30 @@ class PeerComm:
         self.n_collectives = 0
         self.log = None
         arena_bytes = (int(arena_bytes) + 4096 + 1023) // 1024 * 1024
+        lib = _lib.load()
+        self._base = ctypes.c_void_p()
+        handle = ctypes.create_string_buffer(64)
         with torch.cuda.device(self.device):
-            # a dedicated cudaMalloc block (not a slice of a cached segment), zero-filled: halo planes at the global
-            # faces are never written and must read as the conv's zero padding
-            self.arena = torch.zeros(arena_bytes, dtype=torch.uint8, device=self.device)
-            torch.cuda.synchronize()
-        share = self.arena.untyped_storage()._share_cuda_()
-        shares = [None] * self.world
-        dist.all_gather_object(shares, share, group=group)
-        self.peers = []
-        for q, sh in enumerate(shares):
-            if q == self.rank:
-                self.peers.append(self.arena)
-                continue
-            dev, handle, size, off, ref_handle, ref_off, ev_handle, ev_sync = sh
-            # the mapping is opened in the context of the device that owns the memory (`dev`, the producer's index: under
-            # torchrun every rank sees all GPUs of the box); kernels on OUR device reach it through peer access
-            st = torch.UntypedStorage._new_shared_cuda(dev, handle, size, off, ref_handle, ref_off, ev_handle, ev_sync)
-            self.peers.append(torch.empty(0, dtype=torch.uint8, device=torch.device("cuda", dev)).set_(st))
-            if dev != self.device.index:
-                with torch.cuda.device(self.device):
-                    _lib.check(_lib.load().mode_peer_enable_access(int(dev)), "mode_peer_enable_access")
+            # a dedicated, zero-filled cudaMalloc block: halo planes at the global faces are never written and must read as
+            # the conv's zero padding
+            _lib.check(lib.mode_peer_arena_alloc(arena_bytes, ctypes.byref(self._base), handle), "mode_peer_arena_alloc")
+        self.arena = torch.as_tensor(_RawCuda(self._base.value, arena_bytes), device=self.device)
+        handles = [None] * self.world
+        dist.all_gather_object(handles, (bytes(handle.raw), self.device.index), group=group)
+        self.peer_base = []                                       # address of rank q's arena in THIS process
+        self._opened = []
+        with torch.cuda.device(self.device):
+            for q, (hb, dev_q) in enumerate(handles):
+                if q == self.rank:
+                    self.peer_base.append(self._base.value)
+                    continue
+                if dev_q != self.device.index:
+                    _lib.check(lib.mode_peer_enable_access(int(dev_q)), "mode_peer_enable_access")
+                ptr = ctypes.c_void_p()
+                _lib.check(lib.mode_peer_arena_open(ctypes.create_string_buffer(hb, 64), ctypes.byref(ptr)),
+                           "mode_peer_arena_open")
+                self.peer_base.append(ptr.value)
+                self._opened.append(ptr.value)
         self._off = 4096                                          # [0, 4096): counters
         self._bufs = {}
         self._sig_next = 0
@@ -171,7 +182,7 @@ class PeerComm:
     def _peer_ptr(self, q, t, byte_off=0):
         off = t.data_ptr() - self.arena.data_ptr()
         assert 0 <= off < self.arena.numel(), "tensor is not part of the exchange arena (allocate it with comm.alloc)"
-        return self.peers[q].data_ptr() + off + byte_off
+        return self.peer_base[q] + off + byte_off
 
     def _signal(self, name):
         """Index of the (signal, expect, ticket) triple of a named exchange point."""
@@ -207,11 +218,11 @@ class PeerComm:
         if self.rank > 0:                                         # my first h interior planes -> lower neighbour's top halo
             srcs.append(ext.data_ptr() + h * plane)
             dsts.append(self._peer_ptr(self.rank - 1, ext, (d + h) * plane))
-            sigs.append(self.peers[self.rank - 1].data_ptr() + 4 * idx)
+            sigs.append(self.peer_base[self.rank - 1] + 4 * idx)
         if self.rank < self.world - 1:                            # my last h interior planes -> upper neighbour's bottom halo
             srcs.append(ext.data_ptr() + d * plane)
             dsts.append(self._peer_ptr(self.rank + 1, ext, 0))
-            sigs.append(self.peers[self.rank + 1].data_ptr() + 4 * idx)
+            sigs.append(self.peer_base[self.rank + 1] + 4 * idx)
         k = len(srcs)
         vp = ctypes.c_void_p * k
         _lib.check(lib.mode_peer_put(vp(*srcs), vp(*dsts), vp(*sigs), k, h * plane, ctypes.c_void_p(ticket), self._stream()),
@@ -229,28 +240,48 @@ class PeerComm:
         assert t.is_contiguous() and t.dtype in (torch.float32, torch.float64)
         self.n_collectives += 1
         n = t.numel()
-        nbytes = (n * t.element_size() + 15) // 16 * 16
+        es = t.element_size()
+        nbytes = (n * es + 15) // 16 * 16
         name = ("ar", tag, n, t.dtype)
-        slots = self.alloc(name, (self.world, nbytes // t.element_size()), t.dtype)
-        stage = self.alloc(name + ("src",), (nbytes // t.element_size(),), t.dtype)
+        slots = self.alloc(name, (self.world, nbytes // es), t.dtype)
         idx = self._signal(name)
         _, expect, ticket = self._sig_ptrs(idx)
-        stage[:n].copy_(t.reshape(-1))
-        vp = ctypes.c_void_p * self.world
-        srcs = [stage.data_ptr()] * self.world
+        direct = nbytes == n * es and t.data_ptr() % 16 == 0          # push from / sum into `t` itself: two launches in all
+        if direct:
+            src = t
+        else:
+            src = self.alloc(name + ("src",), (nbytes // es,), t.dtype)
+            src[:n].copy_(t.reshape(-1))
+        srcs = [src.data_ptr()] * self.world
         dsts = [self._peer_ptr(q, slots, self.rank * nbytes) for q in range(self.world)]
-        sigs = [self.peers[q].data_ptr() + 4 * idx for q in range(self.world)]
+        sigs = [self.peer_base[q] + 4 * idx for q in range(self.world)]
         for q0 in range(0, self.world, 8):
             k = min(8, self.world - q0)
             vk = ctypes.c_void_p * k
             _lib.check(lib.mode_peer_put(vk(*srcs[q0:q0 + k]), vk(*dsts[q0:q0 + k]), vk(*sigs[q0:q0 + k]), k, nbytes,
                                          ctypes.c_void_p(ticket), self._stream()), "mode_peer_put")
-        out = t.reshape(-1)
-        _lib.check(lib.mode_peer_sum_slots(_p(slots), self.world, nbytes // t.element_size(), 1 if t.dtype == torch.float64 else 0,
-                                           _p(stage), ctypes.c_void_p(self.arena.data_ptr() + 4 * idx), ctypes.c_void_p(expect),
+        _lib.check(lib.mode_peer_sum_slots(_p(slots), self.world, nbytes // es, 1 if t.dtype == torch.float64 else 0,
+                                           _p(src), ctypes.c_void_p(self.arena.data_ptr() + 4 * idx), ctypes.c_void_p(expect),
                                            ctypes.c_void_p(ticket), self._stream()), "mode_peer_sum_slots")
-        out.copy_(stage[:n])
+        if not direct:
+            t.reshape(-1).copy_(src[:n])
         return t
 
     def barrier(self):
         dist.barrier(group=self.group)
+
+    def close(self):
+        """Unmap the peers' arenas and free our own (after a barrier: nobody may still be storing into it)."""
+        if self._base is None:
+            return
+        lib = _lib.load()
+        with torch.cuda.device(self.device):
+            torch.cuda.synchronize()
+            dist.barrier(group=self.group)
+            for p in self._opened:
+                lib.mode_peer_arena_close(ctypes.c_void_p(p))
+            dist.barrier(group=self.group)
+            self.arena = None
+            self._bufs = {}
+            lib.mode_peer_arena_free(self._base)
+        self._base = None

@@ -152,11 +152,9 @@ class ShardedConvFunction(torch.autograd.Function):
         pl = ctypes.byref(planes)
         _lib.check(lib.mode_bn_relu_bwd_reduce(Fm._p(y), Fm._p(doutn), m_rows, co, Fm._p(bn_w), Fm._p(bn_b), Fm._p(mean),
                                                Fm._p(invstd), pl, Fm._p(ws), Fm._stream()), "mode_bn_relu_bwd_reduce")
-        comm.all_reduce(ws[:16 * co].view(torch.float64), tag + ".bnb")
-        if use_umma:
-            # the fp16 scale of dy must be the SAME on every rank (halo planes travel in fp16): the per-channel maxima
-            # are non-negative floats, and the sum of the ranks' maxima bounds the global maximum
-            comm.all_reduce(ws[16 * co:24 * co].view(torch.float32), tag + ".bnm")
+        # {sum dz, sum dz*xhat, max|dz|, max|xhat|}[co] as ONE fp64 vector: the fp16 scale of dy must be the SAME on every
+        # rank (halo planes travel in fp16) and the sum of the ranks' maxima bounds the global maximum
+        comm.all_reduce(ws.view(torch.float64), tag + ".bnb")
         dy_ext = comm.alloc((tag, "dy_ext", str(tdt)), (1, d + 2 * H2, h, wd, co), tdt, dev)
         dgamma = torch.empty(co, dtype=torch.float32, device=dev)
         dbeta = torch.empty(co, dtype=torch.float32, device=dev)
@@ -189,8 +187,10 @@ class ShardedConvFunction(torch.autograd.Function):
         _lib.check(lib.mode_reparam_bwd(ctypes.byref(layer), Fm._p(ids), Fm._p(dense), 1, Fm._p(sample_u), 1, Fm._p(g),
                                         Fm._p(d_weff), *[Fm._p(o) for o in outs], Fm._p(wsb), Fm._stream()),
                    "mode_reparam_bwd")
-        dg_fork.join()                       # the neighbours may overwrite our dy halo once they see our gradients
+        # gradient sum over the slabs NEXT TO dgrad (side stream).  No hazard on the dy halo: a neighbour's next dy push comes
+        # after ITS BatchNorm-backward all-reduce of the next step, which needs OUR contribution -- stream-ordered after the join
         comm.all_reduce(flat, tag + ".grad")
+        dg_fork.join()
         if needs_dx:
             dx = Fm.from_ndhwc(dxn)
         return (dx, None, *outs, dgamma, dbeta, None, None, None, None, None, None, None, None)

@@ -91,7 +91,7 @@ def main():
         bad = {k: v for k, (v, tol) in errs.items() if not v <= tol}
         if code.value != 0:
             bad["device_error_flag"] = code.value
-        flag = torch.tensor([1.0 if bad else 0.0])
+        flag = torch.tensor([1.0 if bad else 0.0], device=dev if args.comm == "nccl" else "cpu")
         dist.all_reduce(flag)
         if rank == 0:
             print(f"[{args.comm} x{world} {precision}] collectives/step={comm.n_collectives // args.steps} " +
@@ -100,6 +100,8 @@ def main():
             print(f"rank {rank} [{precision}] FAILED: {bad}", flush=True)
         if flag.item() > 0:
             ok = False
+        if hasattr(comm, "close"):
+            comm.close()
         del comm
     dist.barrier()
     dist.destroy_process_group()

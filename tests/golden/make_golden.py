@@ -116,9 +116,23 @@ def net_case(ref_mod, name, seed, mult_chan, tasks_all, shape, tasks, training):
     print(name, "out", out["out"].shape, "params", sum(v.size for k, v in out.items() if k.startswith("p.")))
 
 
+def main_round2(ref_mod):
+    """Cases added in round 2 (generated on their own so that the round-1 fixtures stay byte-identical)."""
+    # (h) 32 -> 32 'final' layer (no BatchNorm / ReLU), train mode: isolates the tensor-core dgrad / wgrad / K1b on
+    #     real-valued data -- no ReLU mask between the operand rounding and the gradients, so the fp16-operand path is held to
+    #     1e-3 DIRECTLY against these fp32 vectors
+    conv_case(ref_mod, "conv_train_final_c32", 9, 12, 32, 32, (4, 16, 16), [3, 7], True, "final")
+
+
 def main():
     torch.set_num_threads(8)
     ref_mod = _ref()
+    if len(sys.argv) > 1 and sys.argv[1] == "round2":
+        main_round2(ref_mod)
+        with open(os.path.join(HERE, "PROVENANCE.txt"), "a") as f:
+            f.write(f"round 2 additions (make_golden.py round2): conv_train_final_c32; torch {torch.__version__}, "
+                    f"threads {torch.get_num_threads()}, numpy {np.__version__}, CPU fp32\n")
+        return
     # (a) tiny train-mode block, distinct tasks per sample, ragged spatial dims
     conv_case(ref_mod, "conv_train_small", 1, 3, 4, 8, (6, 7, 9), [2, 0], True, "normal")
     # (b) 'final' head (Co=1, no BN), train mode
@@ -134,6 +148,7 @@ def main():
     # (g) whole U-Net at reduced width (mult_chan=2) so the fixture stays small; 16^3 is the minimum volume
     net_case(ref_mod, "net_eval_small", 7, 2, list(range(3)), (16, 16, 16), [1, 1], False)
     net_case(ref_mod, "net_train_small", 8, 2, list(range(3)), (32, 32, 32), [2, 0], True)
+    main_round2(ref_mod)
     with open(os.path.join(HERE, "PROVENANCE.txt"), "w") as f:
         f.write(f"generated by tests/golden/make_golden.py from {REF} (fnet/nn_modules/RepMode.py)\n"
                 f"torch {torch.__version__}, threads {torch.get_num_threads()}, numpy {np.__version__}, CPU fp32\n")

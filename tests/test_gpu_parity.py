@@ -12,7 +12,7 @@ from tests.util import assert_close, load_golden, params_of
 pytestmark = pytest.mark.gpu
 
 CONV_CASES = ["conv_train_small", "conv_train_final", "conv_train_stem", "conv_train_c32", "conv_eval_small",
-              "conv_train_config1"]
+              "conv_train_config1", "conv_train_final_c32"]
 
 
 def _build_conv(d, precision):
@@ -57,9 +57,12 @@ def test_modeconv_vs_golden(name, precision, tol):
         (y * torch.from_numpy(d["dout"]).cuda()).sum().backward()
         ref = d
         tensor_core = precision == "f16" and Fm.umma_shape_ok(m.in_chan, m.out_chan, *x.shape[2:])
-        if tensor_core:
+        if tensor_core and str(d["conv_type"]) == "normal":
             ref = _oracle_f16(d)
             ref["dx"] = ref["dx"][:, :, ::sub, ::sub, ::sub]
+        # a 'final' layer (no BatchNorm / ReLU: conv_train_final_c32 runs dgrad, wgrad and K1b on tcgen05) has no ReLU
+        # mask that operand rounding could flip, so its gradients are held to the tolerance DIRECTLY against the fp32
+        # golden vectors of the live reference
         assert_close(x.grad.cpu().numpy()[:, :, ::sub, ::sub, ::sub], ref["dx"], tol, "dx")
         named = dict(m.named_parameters())
         for k in [k for k in d if k.startswith("grad.")]:
@@ -134,22 +137,22 @@ def test_eval_weight_cache_matches_uncached_and_invalidates(precision, monkeypat
         assert torch.equal(after, m(x, ids))
 
 
-@pytest.mark.skipif(os.environ.get("REPMODE_TEST_EXPERIMENTAL", "0") != "1",
-                    reason="reparam_fwd_wide_kernel is experimental: set REPMODE_TEST_EXPERIMENTAL=1")
 @pytest.mark.parametrize("dtype_name", ["f32", "f16"])
-def test_reparam_wide_kernel_bit_identical(dtype_name, monkeypatch):
-    """K1 for wide layers (REPMODE_K1_WIDE=1: 4 output channels x a whole 32-channel chunk per block) writes the same
-    bits as the per-(o, kd slice) kernel: same expressions, same association order, same pack."""
+@pytest.mark.parametrize("ci,co,U", [(128, 160, 3), (32, 32, 1), (64, 34, 2)])
+def test_reparam_rows_kernel_bit_identical(dtype_name, ci, co, U, monkeypatch):
+    """K1's row-block kernel (2 output channels x a whole 32-channel chunk per block, experts read once for all U gate
+    inputs; the default when Ci % 32 == 0) writes the same bits as the per-(o, kd slice) kernel: same expressions, same
+    association order, same pack -- and the same dgrad pack built from it."""
     from repmode_b200 import functional as Fm, lib as L
     from repmode_b200.nn_modules import MoDEConv
     torch.manual_seed(5)
-    m = MoDEConv(5, 12, 128, 160).cuda()
+    m = MoDEConv(5, 12, ci, co).cuda()
     layer, ci, co = Fm._layer(*m._params())
-    ids = torch.tensor([3, 7, 3], device="cuda", dtype=torch.int32)
+    ids = torch.tensor([3, 7, 3][:U], device="cuda", dtype=torch.int32)
     dtype = L.MODE_F32 if dtype_name == "f32" else L.MODE_F16
     scale = 1.0 if dtype_name == "f32" else Fm.W_SCALE_F16
-    monkeypatch.setenv("REPMODE_K1_WIDE", "0")
-    g0, w0, d0 = Fm.reparam_fwd(layer, ids, 3, ci, co, dtype, True, scale)
-    monkeypatch.setenv("REPMODE_K1_WIDE", "1")
-    g1, w1, d1 = Fm.reparam_fwd(layer, ids, 3, ci, co, dtype, True, scale)
+    monkeypatch.setenv("REPMODE_K1_ROWS", "0")
+    g0, w0, d0 = Fm.reparam_fwd(layer, ids, U, ci, co, dtype, True, scale)
+    monkeypatch.setenv("REPMODE_K1_ROWS", "1")
+    g1, w1, d1 = Fm.reparam_fwd(layer, ids, U, ci, co, dtype, True, scale)
     assert torch.equal(g0, g1) and torch.equal(w0, w1) and torch.equal(d0, d1)

@@ -8,7 +8,7 @@ from oracle import mode_numpy as onp
 from oracle import mode_torch as otc
 from tests.util import assert_close, load_golden, params_of
 
-CONV_TRAIN = ["conv_train_small", "conv_train_final", "conv_train_stem", "conv_train_c32"]
+CONV_TRAIN = ["conv_train_small", "conv_train_final", "conv_train_stem", "conv_train_c32", "conv_train_final_c32"]
 TOL = 2e-5   # fp32 re-association only (the oracles and the reference all compute in fp32)
 
 

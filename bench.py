@@ -47,6 +47,8 @@ def parse():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--comm", default=os.environ.get("REPMODE_BENCH_COMM", "peer"), choices=["peer", "nccl"])
+    # extra lines for BASELINE.json configs 2-5 (the driver runs the default = headline): whole-U-Net workloads
+    ap.add_argument("--config", default="headline", choices=["headline", "net_fwd", "net_train", "cfg4", "cfg5"])
     return ap.parse_args()
 
 
@@ -290,7 +292,11 @@ def run_ours(args, rank, local_rank, world):
         return ms, launches
 
     # ---- the headline arm: N = 1 single volume; N > 1 D-sharded volume through the selected comm
-    if world == 1:
+    if world == 1 and os.environ.get("REPMODE_BENCH_SHARDED_LOCAL", "0") == "1":
+        # diagnostics: the D-sharded formulation (haloed operand buffers, conv on owned planes) with NO neighbour -- what the
+        # slab geometry alone costs against the plain single-volume step
+        main_fn, main_label = make_step_sharded(peer.TorchComm(), "blk"), "d-sharded formulation, no neighbours"
+    elif world == 1:
         main_fn, main_label = step_single, "single volume"
     else:
         main_fn, main_label = make_step_sharded(comms[args.comm], "blk"), f"d-sharded, {args.comm}"
@@ -536,6 +542,181 @@ def run_ours(args, rank, local_rank, world):
     print(json.dumps(line), flush=True)
 
 
+# ------------------------------------------------------------------------------------------- whole-U-Net configs
+NET_FLOP_FWD = 1086.3e9        # MoDE convs of the full U-Net per 32x128x128 sample; fwd+bwd = 3x
+
+
+def run_net_config(args, rank, local_rank, world):
+    """BASELINE.json configs 2-5 through the plugin API (fnet.nn_modules.RepMode.Net):
+       net_fwd   (config 2) eval forward, x[1,1,32,128,128], 1 GPU
+       net_train (config 3) train step (fwd + bwd + Adam), batch 4 x 32x128x128, 4 distinct tasks, 1 GPU
+       cfg4 / cfg5 (configs 4 / 5) train step on ONE volume 64x256x256 / 128x512x512, D-sharded over 4 / 8 GPUs
+    One JSON line on rank 0 with the same keys as the headline line."""
+    import argparse as _ap
+    import importlib
+    import torch.distributed as dist
+    from repmode_b200 import lib as L, parallel as par, sharded
+    dev = torch.device("cuda", local_rank)
+    torch.cuda.set_device(dev)
+    lib = L.load()
+    hbm_gbs, tf_burst, tf_sust, peak_kind = peaks()
+    mod = importlib.import_module("fnet.nn_modules.RepMode")
+    torch.manual_seed(0)
+    net = mod.Net(_ap.Namespace(adopted_datasets=list(range(T)), gpu_ids=local_rank)).to(dev)
+    stream = torch.cuda.current_stream()
+    cfg = args.config
+    sharded_cfg = cfg in ("cfg4", "cfg5")
+    if sharded_cfg:
+        want = 4 if cfg == "cfg4" else 8
+        if world != want:
+            raise SystemExit(f"bench.py --config {cfg} needs --gpus {want} (one rank per GPU under torchrun)")
+        Dg, Hg, Wg = (64, 256, 256) if cfg == "cfg4" else (128, 512, 512)
+        dl = Dg // world
+        batch = 1
+        vox_step = Dg * Hg * Wg
+        g = torch.Generator().manual_seed(100 + rank)
+        x_host = torch.randn(1, 1, dl, Hg, Wg, generator=g).pin_memory()
+        tgt = torch.randn(1, 1, dl, Hg, Wg, generator=g).to(dev)
+        task = torch.tensor([3], device=dev)
+        flop_step = 3 * NET_FLOP_FWD * vox_step / VOX
+    else:
+        batch = 1 if cfg == "net_fwd" else 4
+        vox_step = batch * VOX
+        g = torch.Generator().manual_seed(100)
+        x_host = torch.randn(batch, 1, D, H, W, generator=g).pin_memory()
+        tgt = torch.randn(batch, 1, D, H, W, generator=g).to(dev)
+        task = ((torch.arange(batch) * 3) % T).to(dev) if cfg == "net_train" else torch.tensor([3], device=dev)
+        flop_step = (1 if cfg == "net_fwd" else 3) * NET_FLOP_FWD * batch
+    x_dev = x_host.to(dev)
+    notes = []
+
+    if cfg == "net_fwd":
+        net.eval()
+
+        def step(xin):
+            with torch.no_grad():
+                return net(xin, task)          # from the 2nd call on: one CUDA-graph replay (nn_modules.Net)
+        run = lambda: step(x_dev)              # noqa: E731
+        result_bytes = vox_step * 4
+    else:
+        net.train()
+        params = list(net.parameters())
+        try:
+            opt = torch.optim.Adam(params, lr=1e-4, fused=True, capturable=True)
+        except Exception:  # noqa: BLE001
+            opt = torch.optim.Adam(params, lr=1e-4)
+        loss_buf = torch.zeros((), device=dev)
+
+        def train_step(xin):
+            opt.zero_grad(set_to_none=False)
+            if sharded_cfg:
+                out = sharded.sharded_net_forward(net, xin, task, Dg)
+                loss = torch.sum((out - tgt) ** 2) / float(vox_step)       # each rank: its slab's share of the global mean
+            else:
+                out = net(xin, task)
+                loss = torch.mean((out - tgt) ** 2)
+            loss.backward()
+            if world > 1:
+                par.sync_gradients(params)
+            opt.step()
+            loss_buf.copy_(loss.detach())
+            return loss_buf
+        # warm-up (allocator, lazy state), then try to capture the whole step (fwd + bwd + Adam) as ONE CUDA graph
+        for p in params:
+            p.grad = torch.zeros_like(p)
+        for _ in range(2):
+            train_step(x_dev)
+        torch.cuda.synchronize()
+        run = lambda: train_step(x_dev)        # noqa: E731
+        if os.environ.get("REPMODE_BENCH_GRAPH", "1") == "1" and not sharded_cfg:
+            try:
+                graph = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(graph):
+                    train_step(x_dev)
+                run = graph.replay
+                notes.append("train step (fwd + bwd + fused Adam) captured once as a CUDA graph and replayed")
+            except Exception as e:  # noqa: BLE001
+                notes.append(f"CUDA-graph capture failed, eager launches ({type(e).__name__}: {str(e)[:100]})")
+                torch.cuda.synchronize()
+        result_bytes = 4
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps, warmup):
+        for _ in range(warmup):
+            fn()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        l0 = lib.mode_launch_count()
+        e0.record(stream)
+        for _ in range(steps):
+            fn()
+        e1.record(stream)
+        barrier()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            tms = torch.tensor([ms], device=dev, dtype=torch.float64)
+            dist.all_reduce(tms, op=dist.ReduceOp.MAX)
+            ms = float(tms.item())
+        return ms, lib.mode_launch_count() - l0
+
+    warmup = max(3, args.warmup)
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    l_eager0 = lib.mode_launch_count()
+    run()                                                               # (net_fwd: the call that captures the graph)
+    launches_one = lib.mode_launch_count() - l_eager0
+    ms, launches = timed(run, args.steps, warmup)
+    clocks = sampler.stop() if sampler else None
+    # e2e: input from pinned host memory every step + the step's result read back (prediction / loss)
+    x_in = torch.empty_like(x_dev)
+    res_host = torch.empty(result_bytes // 4, dtype=torch.float32).pin_memory()
+
+    def e2e_step():
+        x_in.copy_(x_host, non_blocking=True)
+        if cfg == "net_fwd":
+            out = step(x_in)
+            res_host.copy_(out.reshape(-1), non_blocking=True)
+        else:
+            x_dev.copy_(x_in)
+            out = run()
+            res_host.copy_(loss_buf.reshape(-1), non_blocking=True)
+        stream.synchronize()
+    ms_e2e, _ = timed(e2e_step, args.steps, warmup)
+    if rank != 0:
+        return
+    tflops = flop_step / (ms / args.steps * 1e-3) / 1e12 / world
+    names = {"net_fwd": "full RepMode U-Net eval forward, x[1,1,32,128,128], task 3 (BASELINE.json config 2)",
+             "net_train": "full RepMode U-Net train step (fwd + bwd + Adam), x[4,1,32,128,128], 4 distinct tasks of 12 "
+                          "(BASELINE.json config 3)",
+             "cfg4": "full RepMode U-Net train step on ONE volume x[1,1,64,256,256] sharded on D over 4 GPUs (config 4)",
+             "cfg5": "full RepMode U-Net train step on ONE volume x[1,1,128,512,512] sharded on D over 8 GPUs (config 5)"}
+    line = {
+        "metric": "voxels/sec full RepMode U-Net " + ("eval forward" if cfg == "net_fwd" else "train step"),
+        "value": vox_step * args.steps / (ms * 1e-3), "unit": "voxels/s", "n_gpus": world, "steps": args.steps,
+        "warmup": warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
+        "scaling": "strong" if sharded_cfg else "weak", "vs_baseline": None,
+        "dtype": "f16 operands (saturating; 10-bit mantissa like TF32), f32 accumulate", "data": "synthetic",
+        "config": {"workload": names[cfg], "layout": "NDHWC (channels_last_3d)", "notes": notes,
+                   "parallelism": (f"d-shard x{world} (halo exchange per two-conv stage, BatchNorm all-reduce, NCCL)"
+                                   if sharded_cfg else "1 GPU")},
+        "e2e": {"value": vox_step * args.steps / (ms_e2e * 1e-3), "unit": "voxels/s",
+                "h2d_bytes_per_step": x_host.numel() * 4 * world, "d2h_bytes_per_step": result_bytes * world,
+                "ms_per_step": ms_e2e / args.steps},
+        "gpu_launches": int(launches if launches > 0 else launches_one * args.steps),
+        "clocks": clocks,
+        "roofline": {"kernel": "all MoDE convs of the U-Net (K2 / K3 / K4)", "bound": "tensor", "achieved": tflops,
+                     "peak": tf_burst, "unit": "TFLOP/s", "frac": tflops / tf_burst, "traffic": None, "per_gpu": True,
+                     "algorithmic_flop_per_step": flop_step,
+                     "peak_source": f"MEASURED_PEAKS.json bf16 burst ({peak_kind})"},
+        "cpu_baseline": None,
+        "mem_gb": torch.cuda.max_memory_allocated() / 2 ** 30,
+    }
+    print(json.dumps(line), flush=True)
+
+
 def main():
     args = parse()
     rank = int(os.environ.get("RANK", "0"))
@@ -551,7 +732,10 @@ def main():
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     try:
-        run_ours(args, rank, local_rank, world)
+        if args.config != "headline":
+            run_net_config(args, rank, local_rank, world)
+        else:
+            run_ours(args, rank, local_rank, world)
         torch.cuda.synchronize()
     finally:
         if world > 1:

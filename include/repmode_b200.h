@@ -120,6 +120,33 @@ int mode_conv3d(const void* x, mode_dtype_t x_dtype, const void* w, const int32_
                 const float* out_scale_dev, double* bn_sums, int32_t stat_d_lo, int32_t stat_d_hi, int32_t impl,
                 void* stream);
 
+/* ---- descriptors of exchange steps FUSED into a kernel (D-sharded slabs over peer memory, see the peer section below) -----
+ * mode_halo_push_t: the kernel that writes a tensor also stores the tensor's first / last `bytes` (its boundary planes) into
+ *   the lower / upper neighbour's halo planes and, when the whole launch is done, increments their counters.
+ * mode_peer_push_t: the last block of a kernel broadcasts a small fp64 vector (its per-channel sums) into slot dst[i] of
+ *   every destination and increments signal[i].
+ * mode_peer_gather_t: the consuming kernel waits until `world` producers have signalled (*signal >= *expect + world), sums
+ *   slots[0..world) in rank order instead of reading a local vector, and advances *expect.
+ * All pointers are device addresses (dst / signal normally on a peer); `ticket` is a zero-initialised local uint32. */
+typedef struct {
+    void* lo_dst; void* lo_signal;      /* NULL lo_dst / hi_dst: no neighbour on that side (global face) */
+    void* hi_dst; void* hi_signal;
+    int64_t bytes;                      /* multiple of 16 */
+    void* ticket;
+} mode_halo_push_t;
+typedef struct {
+    int32_t n;                          /* destinations, <= 8 */
+    void* dst[8];
+    void* signal[8];
+    void* ticket;
+} mode_peer_push_t;
+typedef struct {
+    const void* slots;                  /* [world][count] doubles, local */
+    int32_t world;
+    const void* signal;                 /* local uint32 counter the producers increment */
+    void* expect;                       /* local uint32 */
+} mode_peer_gather_t;
+
 /* Extended form of mode_conv3d (mode_conv3d == mode_conv3d_ex with opts = NULL).  Two things the plain call cannot say:
  *   (1) a HALOED input (D-sharded slabs): x has Dx >= D planes and output plane q is centred on
  *       input plane q + x_off, y[q] = sum_kd w[kd] * x[q + x_off + kd - 2]; input planes outside [0, Dx) are zero (the conv's
@@ -137,6 +164,7 @@ typedef struct {
     void* y16;                      /* fp16 result copy or NULL */
     int32_t Dy16, y16_off;          /* planes of the y16 buffer (0 = D) and the plane output plane 0 lands in */
     float y16_scale;                /* 0 = 1 */
+    const mode_peer_push_t* stats_push;   /* HOST pointer or NULL: the last CTA broadcasts bn_sums (2*Nout doubles) */
 } mode_conv_opts_t;
 int mode_conv3d_ex(const void* x, mode_dtype_t x_dtype, const void* w, const int32_t* sample_u, float* y,
                    int32_t N, int32_t D, int32_t H, int32_t W, int32_t K, int32_t Nout, float out_scale,
@@ -207,9 +235,31 @@ int mode_bn_relu_bwd_apply(const float* y, const float* dout, int64_t M, int32_t
                            float* dy, void* dy_f16, float* dy_scale2, const mode_planes_t* planes_host,
                            void* workspace, void* stream);
 
+/* Fused-exchange forms (peer memory, D-sharded slabs).  NULL descriptors give the plain behaviour.
+ *   mode_bn_finalize_ex:        `gather` != NULL: the statistics are the rank-ordered sum of the gathered slots (sums ignored).
+ *   mode_bn_relu_bwd_reduce_ex: `push` != NULL: the last block broadcasts the 4*C-double workspace vector.
+ *   mode_bn_relu_bwd_apply_ex:  `gather`: wait + sum into the workspace first (replaces the caller's all-reduce);
+ *                               `halo`: boundary planes of the produced dy (the fp16 copy when dy_f16 != NULL, else the fp32
+ *                               tensor) are also stored into the neighbours' halo planes. */
+int mode_bn_finalize_ex(const double* sums, int64_t M, int32_t C, const float* gamma, const float* beta, float eps,
+                        float momentum, float* mean, float* invstd, float* scale, float* shift, float* running_mean,
+                        float* running_var, const mode_peer_gather_t* gather_host, void* stream);
+int mode_bn_relu_bwd_reduce_ex(const float* y, const float* dout, int64_t M, int32_t C, const float* gamma,
+                               const float* beta, const float* mean, const float* invstd,
+                               const mode_planes_t* planes_host, void* workspace, const mode_peer_push_t* push_host,
+                               void* stream);
+int mode_bn_relu_bwd_apply_ex(const float* y, const float* dout, int64_t M, int32_t C, const float* gamma,
+                              const float* beta, const float* mean, const float* invstd, float* dgamma, float* dbeta,
+                              float* dy, void* dy_f16, float* dy_scale2, const mode_planes_t* planes_host,
+                              void* workspace, const mode_peer_gather_t* gather_host, const mode_halo_push_t* halo_host,
+                              void* stream);
+
 /* ---- operand staging -----------------------------------------------------------------------------------
  * fp32 -> fp16 (round to nearest even), value * scale * (scale_dev ? *scale_dev : 1); n elements. */
 int mode_cast_f16(const float* src, void* dst_f16, int64_t n, float scale, const float* scale_dev, void* stream);
+/* ... with the boundary planes of dst also stored into the neighbours' halo planes (halo_host may be NULL). */
+int mode_cast_f16_ex(const float* src, void* dst_f16, int64_t n, float scale, const float* scale_dev,
+                     const mode_halo_push_t* halo_host, void* stream);
 /* amax[0] = max(amax[0], max |src|) (amax must be zero-initialised by the caller; device scalar). */
 int mode_amax(const float* src, int64_t n, float* amax, void* stream);
 /* Same over k <= 8 tensors in one launch (srcs_host / counts_host are HOST arrays of device pointers / sizes). */

@@ -11,42 +11,23 @@
 #include <mutex>
 
 #include "common.cuh"
+#include "peer.cuh"
 
 namespace mode {
+
+int* device_error_flag();   // mode_abi.cu
 
 constexpr int BN_THREADS = 256;
 constexpr int BN_MAXC = 1024;
 
-// L2 residency control for the two-pass BatchNorm backward: pass 1 streams y and dout front to back and asks L2 to KEEP
-// their tails (evict_last); pass 2 walks backwards, finds the tails in the 126 MB L2 and releases them (evict_first).
-__device__ __forceinline__ uint64_t l2_policy_evict_last() {
-    uint64_t p;
-    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
-    return p;
-}
-__device__ __forceinline__ uint64_t l2_policy_evict_first() {
-    uint64_t p;
-    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
-    return p;
-}
-__device__ __forceinline__ float4 ld_f4_hint(const float* p, uint64_t pol) {
+// Streaming 16-byte load for tensors that are read once per kernel: read-only path, no L1 allocation.  Measured with
+// tools/stream_probe.cu on this pool's B200 (profiles/r2_stream_probe.txt): two 64 MB input streams read at 5.1 TB/s with
+// these loads against 4.5 TB/s with plain ld.global (L1 allocation of data that is never reused).
+__device__ __forceinline__ float4 ld_stream(const float* p) {
     float4 v;
-    asm volatile("ld.global.L2::cache_hint.v4.f32 {%0, %1, %2, %3}, [%4], %5;"
-                 : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p), "l"(pol));
+    asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0, %1, %2, %3}, [%4];"
+                 : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
     return v;
-}
-// bytes of each of the two streamed tensors that pass 1 pins for pass 2 (both tails together stay well inside L2)
-static int64_t l2_keep_bytes() {
-    static int64_t keep = -1;
-    if (keep < 0) {
-        int dev = 0, l2 = 0;
-        const char* e = getenv("REPMODE_BN_L2_KEEP_MB");
-        if (e) keep = (int64_t)atoi(e) << 20;
-        else if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetAttribute(&l2, cudaDevAttrL2CacheSize, dev) == cudaSuccess)
-            keep = (int64_t)l2 * 3 / 10;
-        else keep = 0;
-    }
-    return keep;
 }
 
 // D-sharded slab bookkeeping (mode_planes_t by value); kind(row): 0 = outside the global volume, 1 = halo copy,
@@ -55,11 +36,18 @@ struct Planes {
     long long rows_per_plane;
     int D, own_lo, own_hi, valid_lo, valid_hi;
     __device__ __forceinline__ int kind(long long row) const {
-        const int d = (int)((row / rows_per_plane) % D);
+        // 32-bit division whenever the tensor allows it (always on this path: < 2^32 voxels per slab)
+        const int d = (row >> 32) == 0 && (rows_per_plane >> 32) == 0
+                          ? (int)(((unsigned)row / (unsigned)rows_per_plane) % (unsigned)D)
+                          : (int)((row / rows_per_plane) % D);
         if (d < valid_lo || d >= valid_hi) return 0;
         return (d >= own_lo && d < own_hi) ? 2 : 1;
     }
 };
+// every plane owned and inside the volume: only m_global matters (a slab whose halos live elsewhere)
+static bool planes_trivial(const mode_planes_t* p) {
+    return p->own_lo <= 0 && p->own_hi >= p->D && p->valid_lo <= 0 && p->valid_hi >= p->D;
+}
 static Planes to_planes(const mode_planes_t* p) {
     Planes q;
     q.rows_per_plane = p->rows_per_plane; q.D = p->D; q.own_lo = p->own_lo; q.own_hi = p->own_hi;
@@ -131,14 +119,27 @@ __global__ void bn_stats_scalar_kernel(const float* __restrict__ y, int64_t M, i
     if (threadIdx.x == 0) { atomicAdd(sums + c, sh[0][0]); atomicAdd(sums + C + c, sh[1][0]); }
 }
 
+// With `g` (D-sharded slabs over peer memory): ONE block; thread 0 waits until every rank's {sum, sum of squares} vector has
+// landed in the local slots, then the statistics are the rank-ordered sum of the slots (deterministic) instead of `sums`.
 __global__ void bn_finalize_kernel(const double* __restrict__ sums, int64_t M, int C, const float* __restrict__ gamma,
                                    const float* __restrict__ beta, float eps, float momentum, float* mean,
                                    float* invstd, float* scale, float* shift, float* running_mean,
-                                   float* running_var) {
-    const int c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= C) return;
-    const double m = sums[c] / (double)M;
-    double var = sums[C + c] / (double)M - m * m;      // biased variance (training-mode normalisation)
+                                   float* running_var, PeerGather g, int* error_flag) {
+    uint32_t target = 0;
+    if (g.on()) {
+        if (!gather_wait(g, target) && threadIdx.x == 0) atomicExch(error_flag, 43);
+    }
+    for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < C; c += gridDim.x * blockDim.x) {
+    double s1, s2;
+    if (g.on()) {
+        const double* sl = reinterpret_cast<const double*>(g.slots);
+        s1 = 0.0; s2 = 0.0;
+        for (int r = 0; r < g.world; ++r) { s1 += sl[(size_t)r * 2 * C + c]; s2 += sl[(size_t)r * 2 * C + C + c]; }
+    } else {
+        s1 = sums[c]; s2 = sums[C + c];
+    }
+    const double m = s1 / (double)M;
+    double var = s2 / (double)M - m * m;      // biased variance (training-mode normalisation)
     if (var < 0) var = 0;
     const float is = (float)(1.0 / sqrt(var + (double)eps));
     const float ga = gamma ? gamma[c] : 1.f, be = beta ? beta[c] : 0.f;
@@ -151,6 +152,11 @@ __global__ void bn_finalize_kernel(const double* __restrict__ sums, int64_t M, i
     if (running_var) {
         const double unb = M > 1 ? var * (double)M / (double)(M - 1) : var;   // running_var tracks the unbiased estimate
         running_var[c] = (1.f - momentum) * running_var[c] + momentum * (float)unb;
+    }
+    }
+    if (g.on()) {
+        __syncthreads();
+        if (threadIdx.x == 0) *g.expect = target;
     }
 }
 
@@ -173,7 +179,7 @@ __global__ void __launch_bounds__(BN_THREADS) bn_apply_kernel(const float* __res
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
             const int64_t kk = k + u * stride;
-            if (kk < nvec) v[u] = *reinterpret_cast<const float4*>(y + (nvec - 1 - kk) * 4);
+            if (kk < nvec) v[u] = ld_stream(y + (nvec - 1 - kk) * 4);
         }
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
@@ -255,8 +261,7 @@ __global__ void __launch_bounds__(BN_THREADS) bn_bwd_reduce_kernel(const float* 
 
 // vectorised pass 1 for C % 4 == 0: thread t owns the 4 channels of float4 lane t % (C/4).  Four rows (8 independent 16-byte
 // loads) in flight per thread at <= 85 registers, i.e. three blocks per SM: ~96 KB in flight per SM.  A thread sums a few
-// dozen values per channel, so fp32 partials are exact enough; the fold to fp64 happens once per block.  The last
-// `keep_vec` float4 of BOTH tensors are loaded with an evict_last L2 policy: pass 2 reads them first.
+// dozen values per channel, so fp32 partials are exact enough; the fold to fp64 happens once per block.
 template <bool PLANES>
 __global__ void __launch_bounds__(BN_THREADS, 3) bn_bwd_reduce_vec_kernel(const float* __restrict__ y,
                                                                           const float* __restrict__ dout, int64_t M,
@@ -265,7 +270,7 @@ __global__ void __launch_bounds__(BN_THREADS, 3) bn_bwd_reduce_vec_kernel(const 
                                                                           const float* __restrict__ mean,
                                                                           const float* __restrict__ invstd,
                                                                           double* __restrict__ red, long long* __restrict__ mx,
-                                                                          Planes pl, int64_t keep_vec) {
+                                                                          Planes pl, PeerPush pp) {
     const int vpr = C >> 2;
     const int rows_per_iter = BN_THREADS / vpr;
     const int lane_v = threadIdx.x % vpr, lane_r = threadIdx.x / vpr;
@@ -277,18 +282,15 @@ __global__ void __launch_bounds__(BN_THREADS, 3) bn_bwd_reduce_vec_kernel(const 
         ga[j] = gamma ? gamma[c] : 1.f; be[j] = beta ? beta[c] : 0.f;
     }
     float s[4] = {0, 0, 0, 0}, q[4] = {0, 0, 0, 0}, mdz[4] = {0, 0, 0, 0}, mxh[4] = {0, 0, 0, 0};
-    const uint64_t pol_keep = l2_policy_evict_last(), pol_drop = l2_policy_evict_first();
     const int64_t stride = (int64_t)gridDim.x * rows_per_iter;
-    const int64_t keep_row = M - keep_vec / vpr;      // rows >= keep_row are pinned in L2
     for (int64_t r = (int64_t)blockIdx.x * rows_per_iter + lane_r; r < M; r += 4 * stride) {
         float4 yv[4], dv[4];
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
             const int64_t rr = r + u * stride;
             if (rr < M) {
-                const uint64_t pol = rr >= keep_row ? pol_keep : pol_drop;
-                yv[u] = ld_f4_hint(y + rr * C + lane_v * 4, pol);
-                dv[u] = ld_f4_hint(dout + rr * C + lane_v * 4, pol);
+                yv[u] = ld_stream(y + rr * C + lane_v * 4);
+                dv[u] = ld_stream(dout + rr * C + lane_v * 4);
             }
         }
 #pragma unroll
@@ -320,13 +322,30 @@ __global__ void __launch_bounds__(BN_THREADS, 3) bn_bwd_reduce_vec_kernel(const 
     block_fold_and_flush(ds, dq, C, vpr, red, sh);     // contains the __syncthreads that also orders smx
     for (int i = threadIdx.x; i < 2 * C; i += BN_THREADS)
         atomicMax(mx + i, __double_as_longlong((double)__int_as_float(smx[i])));
+    // D-sharded slabs: the last block broadcasts {sum dz, sum dz*xhat, max|dz|, max|xhat|}[C] (red and mx are contiguous)
+    if (pp.n > 0) push_vector_from_last_block(red, 4 * C, pp);
 }
 
-// power-of-two fp16 scale for dy from the per-channel bound
+// (optional) gather of the D-sharded partial sums, then the power-of-two fp16 scale for dy from the per-channel bound
 //   |dy_c| <= |gamma_c*invstd_c| * (max|dz|_c + |sum_dz_c|/M + max|xhat|_c * |sum_dzxhat_c|/M)
-__global__ void bn_bwd_scale_kernel(const double* __restrict__ red, const double* __restrict__ mx, long long M, int C,
+// With `g`: thread 0 waits for every rank's 4*C-double vector, the block sums the slots in rank order INTO the workspace
+// (red, mx) -- the sum of the ranks' maxima bounds the global maximum, and every rank derives the same scale.
+__global__ void bn_bwd_scale_kernel(double* __restrict__ red, double* __restrict__ mx, long long M, int C,
                                     const float* __restrict__ gamma, const float* __restrict__ invstd, float target,
-                                    float* __restrict__ scale2) {
+                                    float* __restrict__ scale2, PeerGather g, int* error_flag) {
+    if (g.on()) {
+        uint32_t tgt = 0;
+        if (!gather_wait(g, tgt) && threadIdx.x == 0) atomicExch(error_flag, 44);
+        const double* sl = reinterpret_cast<const double*>(g.slots);
+        for (int i = threadIdx.x; i < 4 * C; i += blockDim.x) {
+            double a = 0.0;
+            for (int r = 0; r < g.world; ++r) a += sl[(size_t)r * 4 * C + i];
+            red[i] = a;                                   // red[0..2C) then mx[0..2C): one contiguous vector
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) *g.expect = tgt;
+    }
+    if (scale2 == nullptr) return;
     float b = 0.f;
     for (int c = threadIdx.x; c < C; c += blockDim.x) {
         const float ga = gamma ? gamma[c] : 1.f;
@@ -353,8 +372,8 @@ __global__ void bn_bwd_scale_kernel(const double* __restrict__ red, const double
     }
 }
 
-// pass 2, vectorised (C % 4 == 0): float4 in, float4 and/or 4 x fp16 out.  Walks the tensors BACKWARDS: pass 1 pinned their
-// tails in L2 (evict_last); reading them here with evict_first releases the lines.  Two float4 of each tensor (4 loads) in
+// pass 2, vectorised (C % 4 == 0): float4 in, float4 and/or 4 x fp16 out.  Walks the tensors BACKWARDS: pass 1 has just
+// streamed them front to back, so their tails are what the 126 MB L2 still holds.  Two float4 of each tensor (4 loads) in
 // flight per thread.
 template <bool PLANES>
 __global__ void __launch_bounds__(BN_THREADS, 4) bn_bwd_apply_vec_kernel(const float* __restrict__ y,
@@ -367,7 +386,7 @@ __global__ void __launch_bounds__(BN_THREADS, 4) bn_bwd_apply_vec_kernel(const f
                                                                          float* __restrict__ dgamma, float* __restrict__ dbeta,
                                                                          float* __restrict__ dy, __half* __restrict__ dy16,
                                                                          const float* __restrict__ scale2, Planes pl,
-                                                                         long long m_div) {
+                                                                         long long m_div, HaloPush hp) {
     const float f16_scale = (dy16 != nullptr && scale2 != nullptr) ? scale2[0] : 1.f;
     __shared__ float smu[BN_MAXC], sis[BN_MAXC], sga[BN_MAXC], sbe[BN_MAXC], sa[BN_MAXC], sb[BN_MAXC];
     for (int c = threadIdx.x; c < C; c += BN_THREADS) {
@@ -381,7 +400,6 @@ __global__ void __launch_bounds__(BN_THREADS, 4) bn_bwd_apply_vec_kernel(const f
         }
     }
     __syncthreads();
-    const uint64_t pol_drop = l2_policy_evict_first();
     const int64_t nvec = (M * C) >> 2;
     const int64_t stride = (int64_t)gridDim.x * BN_THREADS;
     for (int64_t k = (int64_t)blockIdx.x * BN_THREADS + threadIdx.x; k < nvec; k += 2 * stride) {
@@ -390,8 +408,8 @@ __global__ void __launch_bounds__(BN_THREADS, 4) bn_bwd_apply_vec_kernel(const f
         for (int u = 0; u < 2; ++u) {
             const int64_t kk = k + u * stride;
             if (kk < nvec) {
-                yv[u] = ld_f4_hint(y + (nvec - 1 - kk) * 4, pol_drop);
-                dv[u] = ld_f4_hint(dout + (nvec - 1 - kk) * 4, pol_drop);
+                yv[u] = ld_stream(y + (nvec - 1 - kk) * 4);
+                dv[u] = ld_stream(dout + (nvec - 1 - kk) * 4);
             }
         }
 #pragma unroll
@@ -410,7 +428,11 @@ __global__ void __launch_bounds__(BN_THREADS, 4) bn_bwd_apply_vec_kernel(const f
                 const float dz = (kind != 0 && fmaf(xh, sga[c + j], sbe[c + j]) > 0.f) ? da[j] : 0.f;
                 v[j] = sga[c + j] * sis[c + j] * (dz - own * (sa[c + j] + xh * sb[c + j]));
             }
-            if (dy) *reinterpret_cast<float4*>(dy + i * 4) = make_float4(v[0], v[1], v[2], v[3]);
+            if (dy) {
+                const float4 o4 = make_float4(v[0], v[1], v[2], v[3]);
+                *reinterpret_cast<float4*>(dy + i * 4) = o4;
+                if (hp.on() && dy16 == nullptr) halo_store(hp, i * 16, nvec * 16, o4);
+            }
             if (dy16) {
                 __half2 a = sat_half2(v[0] * f16_scale, v[1] * f16_scale);
                 __half2 b = sat_half2(v[2] * f16_scale, v[3] * f16_scale);
@@ -418,9 +440,11 @@ __global__ void __launch_bounds__(BN_THREADS, 4) bn_bwd_apply_vec_kernel(const f
                 pk.x = *reinterpret_cast<uint32_t*>(&a);
                 pk.y = *reinterpret_cast<uint32_t*>(&b);
                 *reinterpret_cast<uint2*>(dy16 + i * 4) = pk;
+                if (hp.on()) halo_store(hp, i * 8, nvec * 8, pk);
             }
         }
     }
+    if (hp.on()) halo_finish(hp);       // the neighbours' counters move once every block's boundary stores are out
 }
 
 // pass 2: dy = gamma*invstd*(dz - sum_dz/M - xhat*sum_dzxhat/M); also emits dgamma/dbeta (block 0)
@@ -462,7 +486,8 @@ __global__ void __launch_bounds__(BN_THREADS) bn_bwd_apply_kernel(const float* _
 // fp32 -> fp16, round to nearest even, SATURATED to +-65504 (never inf: an out-of-range activation clips instead of
 // poisoning the accumulators).  Four 16-byte loads in flight per thread.
 __global__ void __launch_bounds__(256) cast_f16_kernel(const float* __restrict__ src, __half* __restrict__ dst,
-                                                       int64_t n, float scale, const float* __restrict__ scale_dev) {
+                                                       int64_t n, float scale, const float* __restrict__ scale_dev,
+                                                       HaloPush hp) {
     if (scale_dev != nullptr) scale *= *scale_dev;
     const int64_t nvec = n >> 2;
     const int64_t stride = (int64_t)gridDim.x * 256;
@@ -470,7 +495,7 @@ __global__ void __launch_bounds__(256) cast_f16_kernel(const float* __restrict__
         float4 v[4];
 #pragma unroll
         for (int u = 0; u < 4; ++u)
-            if (i + u * stride < nvec) v[u] = *reinterpret_cast<const float4*>(src + (i + u * stride) * 4);
+            if (i + u * stride < nvec) v[u] = ld_stream(src + (i + u * stride) * 4);
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
             if (i + u * stride >= nvec) continue;
@@ -479,12 +504,14 @@ __global__ void __launch_bounds__(256) cast_f16_kernel(const float* __restrict__
             pk.x = *reinterpret_cast<uint32_t*>(&a);
             pk.y = *reinterpret_cast<uint32_t*>(&b);
             *reinterpret_cast<uint2*>(dst + (i + u * stride) * 4) = pk;
+            if (hp.on()) halo_store(hp, (i + u * stride) * 8, nvec * 8, pk);       // host guarantees n % 4 == 0 with a push
         }
     }
     if (blockIdx.x == 0 && threadIdx.x < (n & 3)) {
         const int64_t i = (nvec << 2) + threadIdx.x;
         dst[i] = __float2half_rn(fminf(fmaxf(src[i] * scale, -65504.f), 65504.f));
     }
+    if (hp.on()) halo_finish(hp);
 }
 
 __global__ void __launch_bounds__(256) amax_kernel(const float* __restrict__ src, int64_t n, float* amax) {
@@ -571,14 +598,27 @@ extern "C" int mode_bn_stats(const float* y, int64_t M, int32_t C, double* sums,
     return 0;
 }
 
+extern "C" int mode_bn_finalize_ex(const double* sums, int64_t M, int32_t C, const float* gamma, const float* beta,
+                                   float eps, float momentum, float* mean, float* invstd, float* scale, float* shift,
+                                   float* running_mean, float* running_var, const mode_peer_gather_t* gather,
+                                   void* stream) {
+    if ((!sums && !gather) || !scale || !shift || M <= 0 || C <= 0) MODE_FAIL("mode_bn_finalize: bad arguments");
+    const PeerGather g = to_peer_gather(gather);
+    if (g.on() && (g.world <= 0 || !g.signal || !g.expect)) MODE_FAIL("mode_bn_finalize: incomplete gather descriptor");
+    int* ef = device_error_flag();
+    if (!ef) MODE_FAIL("mode_bn_finalize: could not allocate the device error flag");
+    const unsigned grid = g.on() ? 1u : (unsigned)ceil_div(C, 128);       // the gathering form waits in ONE block
+    bn_finalize_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(sums, M, C, gamma, beta, eps, momentum, mean, invstd, scale,
+                                                               shift, running_mean, running_var, g, ef);
+    MODE_LAUNCH_CHECK();
+    return 0;
+}
+
 extern "C" int mode_bn_finalize(const double* sums, int64_t M, int32_t C, const float* gamma, const float* beta,
                                 float eps, float momentum, float* mean, float* invstd, float* scale, float* shift,
                                 float* running_mean, float* running_var, void* stream) {
-    if (!sums || !scale || !shift || M <= 0 || C <= 0) MODE_FAIL("mode_bn_finalize: bad arguments");
-    bn_finalize_kernel<<<(unsigned)ceil_div(C, 128), 128, 0, (cudaStream_t)stream>>>(
-        sums, M, C, gamma, beta, eps, momentum, mean, invstd, scale, shift, running_mean, running_var);
-    MODE_LAUNCH_CHECK();
-    return 0;
+    return mode_bn_finalize_ex(sums, M, C, gamma, beta, eps, momentum, mean, invstd, scale, shift, running_mean,
+                               running_var, nullptr, stream);
 }
 
 extern "C" int mode_bn_apply_relu(const float* y, int64_t M, int32_t C, const float* scale, const float* shift,
@@ -592,7 +632,7 @@ extern "C" int mode_bn_apply_relu(const float* y, int64_t M, int32_t C, const fl
                          (reinterpret_cast<uintptr_t>(out_f16) & 7) == 0;
     if ((C & 3) == 0 && aligned) {
         const int64_t want = ceil_div(total / 4, BN_THREADS * 4);
-        if (planes)
+        if (planes && !planes_trivial(planes))
             bn_apply_kernel<true><<<wave_grid(bn_apply_kernel<true>, BN_THREADS, want), BN_THREADS, 0, st>>>(y, total, C, scale, shift, relu, out, (__half*)out_f16,
                                                                f16_scale, to_planes(planes));
         else
@@ -611,11 +651,14 @@ extern "C" int mode_bn_apply_relu(const float* y, int64_t M, int32_t C, const fl
 // all-reduce (sum) in one step -- the sum of the ranks' maxima bounds the global maximum, which is all the fp16 scale needs
 extern "C" int64_t mode_bn_bwd_workspace_bytes(int32_t C) { return (int64_t)C * 4 * sizeof(double); }
 
-extern "C" int mode_bn_relu_bwd_reduce(const float* y, const float* dout, int64_t M, int32_t C, const float* gamma,
-                                       const float* beta, const float* mean, const float* invstd,
-                                       const mode_planes_t* planes, void* workspace_v, void* stream) {
+extern "C" int mode_bn_relu_bwd_reduce_ex(const float* y, const float* dout, int64_t M, int32_t C, const float* gamma,
+                                          const float* beta, const float* mean, const float* invstd,
+                                          const mode_planes_t* planes, void* workspace_v, const mode_peer_push_t* push,
+                                          void* stream) {
     if (!y || !dout || !mean || !invstd || !workspace_v || M <= 0 || C <= 0 || C > BN_MAXC)
         MODE_FAIL("mode_bn_relu_bwd_reduce: bad arguments (C=%d)", C);
+    const PeerPush pp = to_peer_push(push);
+    if (pp.n < 0 || pp.n > 8 || (pp.n > 0 && !pp.ticket)) MODE_FAIL("mode_bn_relu_bwd_reduce: bad push descriptor");
     cudaStream_t st = (cudaStream_t)stream;
     double* workspace = (double*)workspace_v;
     long long* mx = (long long*)(workspace + 2 * (size_t)C);
@@ -625,17 +668,69 @@ extern "C" int mode_bn_relu_bwd_reduce(const float* y, const float* dout, int64_
     if ((C & 3) == 0 && vpr <= BN_THREADS && BN_THREADS % vpr == 0 && aligned) {
         const int rpi = BN_THREADS / vpr;
         const int64_t want = ceil_div(M, rpi * 4);
-        const int64_t keep_vec = std::min<int64_t>(M * C / 4, l2_keep_bytes() / 16) / vpr * vpr;   // whole rows
-        if (planes)
+        if (planes && !planes_trivial(planes))
             bn_bwd_reduce_vec_kernel<true><<<wave_grid(bn_bwd_reduce_vec_kernel<true>, BN_THREADS, want), BN_THREADS, 0, st>>>(y, dout, M, C, gamma, beta, mean, invstd,
-                                                                        workspace, mx, to_planes(planes), keep_vec);
+                                                                        workspace, mx, to_planes(planes), pp);
         else
             bn_bwd_reduce_vec_kernel<false><<<wave_grid(bn_bwd_reduce_vec_kernel<false>, BN_THREADS, want), BN_THREADS, 0, st>>>(y, dout, M, C, gamma, beta, mean, invstd,
-                                                                         workspace, mx, Planes{}, keep_vec);
+                                                                         workspace, mx, Planes{}, pp);
     } else {
         if (planes) MODE_FAIL("mode_bn_relu_bwd_reduce: plane ranges need C %% 4 == 0 and 16-byte aligned tensors");
+        if (pp.n > 0) MODE_FAIL("mode_bn_relu_bwd_reduce: the fused push needs C %% 4 == 0 and 16-byte aligned tensors");
         const int gx = (int)max((int64_t)1, min(ceil_div(M, BN_THREADS * 8), (int64_t)64));
         bn_bwd_reduce_kernel<<<dim3(gx, C), BN_THREADS, 0, st>>>(y, dout, M, C, gamma, beta, mean, invstd, workspace, mx);
+    }
+    MODE_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int mode_bn_relu_bwd_reduce(const float* y, const float* dout, int64_t M, int32_t C, const float* gamma,
+                                       const float* beta, const float* mean, const float* invstd,
+                                       const mode_planes_t* planes, void* workspace_v, void* stream) {
+    return mode_bn_relu_bwd_reduce_ex(y, dout, M, C, gamma, beta, mean, invstd, planes, workspace_v, nullptr, stream);
+}
+
+extern "C" int mode_bn_relu_bwd_apply_ex(const float* y, const float* dout, int64_t M, int32_t C, const float* gamma,
+                                         const float* beta, const float* mean, const float* invstd, float* dgamma,
+                                         float* dbeta, float* dy, void* dy_f16, float* dy_scale2,
+                                         const mode_planes_t* planes, void* workspace_v,
+                                         const mode_peer_gather_t* gather, const mode_halo_push_t* halo, void* stream) {
+    if (!y || !dout || !mean || !invstd || !workspace_v || (!dy && !dy_f16) || M <= 0 || C <= 0 || C > BN_MAXC)
+        MODE_FAIL("mode_bn_relu_bwd_apply: bad arguments (C=%d)", C);
+    if (dy_f16 && !dy_scale2) MODE_FAIL("mode_bn_relu_bwd_apply: dy_f16 needs dy_scale2");
+    cudaStream_t st = (cudaStream_t)stream;
+    double* workspace = (double*)workspace_v;
+    double* mx = workspace + 2 * (size_t)C;
+    const long long m_div = planes ? (long long)planes->m_global : (long long)M;
+    const PeerGather g = to_peer_gather(gather);
+    const HaloPush hp = to_halo_push(halo);
+    if (g.on() && (g.world <= 0 || !g.signal || !g.expect)) MODE_FAIL("mode_bn_relu_bwd_apply: incomplete gather descriptor");
+    if (hp.on() && (hp.bytes <= 0 || (hp.bytes & 15) || !hp.ticket)) MODE_FAIL("mode_bn_relu_bwd_apply: bad halo descriptor");
+    if (dy_f16 || g.on()) {
+        int* ef = device_error_flag();
+        if (!ef) MODE_FAIL("mode_bn_relu_bwd_apply: could not allocate the device error flag");
+        bn_bwd_scale_kernel<<<1, 256, 0, st>>>(workspace, mx, m_div, C, gamma, invstd, 8192.f, dy_f16 ? dy_scale2 : nullptr,
+                                               g, ef);
+        MODE_LAUNCH_CHECK();
+    }
+    const bool aligned = ((reinterpret_cast<uintptr_t>(y) | reinterpret_cast<uintptr_t>(dout)) & 15) == 0;
+    const bool vec_ok = (C & 3) == 0 && aligned && ((reinterpret_cast<uintptr_t>(dy) & 15) == 0) &&
+                        ((reinterpret_cast<uintptr_t>(dy_f16) & 7) == 0);
+    if (vec_ok) {
+        const int64_t want = ceil_div(M * C / 4, BN_THREADS * 2);
+        if (planes && !planes_trivial(planes))
+            bn_bwd_apply_vec_kernel<true><<<wave_grid(bn_bwd_apply_vec_kernel<true>, BN_THREADS, want), BN_THREADS, 0, st>>>(y, dout, M, C, gamma, beta, mean, invstd, workspace,
+                                                                       dgamma, dbeta, dy, (__half*)dy_f16, dy_scale2,
+                                                                       to_planes(planes), m_div, hp);
+        else
+            bn_bwd_apply_vec_kernel<false><<<wave_grid(bn_bwd_apply_vec_kernel<false>, BN_THREADS, want), BN_THREADS, 0, st>>>(y, dout, M, C, gamma, beta, mean, invstd,
+                                                                        workspace, dgamma, dbeta, dy, (__half*)dy_f16,
+                                                                        dy_scale2, Planes{}, m_div, hp);
+    } else {
+        if (planes) MODE_FAIL("mode_bn_relu_bwd_apply: plane ranges need C %% 4 == 0 and 16-byte aligned tensors");
+        if (hp.on()) MODE_FAIL("mode_bn_relu_bwd_apply: the fused halo push needs C %% 4 == 0 and 16-byte aligned tensors");
+        bn_bwd_apply_kernel<<<stream_grid(M * C, BN_THREADS * 8), BN_THREADS, 0, st>>>(
+            y, dout, M, C, gamma, beta, mean, invstd, workspace, dgamma, dbeta, dy, (__half*)dy_f16, dy_scale2);
     }
     MODE_LAUNCH_CHECK();
     return 0;
@@ -645,37 +740,8 @@ extern "C" int mode_bn_relu_bwd_apply(const float* y, const float* dout, int64_t
                                       const float* beta, const float* mean, const float* invstd, float* dgamma,
                                       float* dbeta, float* dy, void* dy_f16, float* dy_scale2,
                                       const mode_planes_t* planes, void* workspace_v, void* stream) {
-    if (!y || !dout || !mean || !invstd || !workspace_v || (!dy && !dy_f16) || M <= 0 || C <= 0 || C > BN_MAXC)
-        MODE_FAIL("mode_bn_relu_bwd_apply: bad arguments (C=%d)", C);
-    if (dy_f16 && !dy_scale2) MODE_FAIL("mode_bn_relu_bwd_apply: dy_f16 needs dy_scale2");
-    cudaStream_t st = (cudaStream_t)stream;
-    double* workspace = (double*)workspace_v;
-    const double* mx = workspace + 2 * (size_t)C;
-    const long long m_div = planes ? (long long)planes->m_global : (long long)M;
-    if (dy_f16) {
-        bn_bwd_scale_kernel<<<1, 256, 0, st>>>(workspace, mx, m_div, C, gamma, invstd, 8192.f, dy_scale2);
-        MODE_LAUNCH_CHECK();
-    }
-    const bool aligned = ((reinterpret_cast<uintptr_t>(y) | reinterpret_cast<uintptr_t>(dout)) & 15) == 0;
-    const bool vec_ok = (C & 3) == 0 && aligned && ((reinterpret_cast<uintptr_t>(dy) & 15) == 0) &&
-                        ((reinterpret_cast<uintptr_t>(dy_f16) & 7) == 0);
-    if (vec_ok) {
-        const int64_t want = ceil_div(M * C / 4, BN_THREADS * 2);
-        if (planes)
-            bn_bwd_apply_vec_kernel<true><<<wave_grid(bn_bwd_apply_vec_kernel<true>, BN_THREADS, want), BN_THREADS, 0, st>>>(y, dout, M, C, gamma, beta, mean, invstd, workspace,
-                                                                       dgamma, dbeta, dy, (__half*)dy_f16, dy_scale2,
-                                                                       to_planes(planes), m_div);
-        else
-            bn_bwd_apply_vec_kernel<false><<<wave_grid(bn_bwd_apply_vec_kernel<false>, BN_THREADS, want), BN_THREADS, 0, st>>>(y, dout, M, C, gamma, beta, mean, invstd,
-                                                                        workspace, dgamma, dbeta, dy, (__half*)dy_f16,
-                                                                        dy_scale2, Planes{}, m_div);
-    } else {
-        if (planes) MODE_FAIL("mode_bn_relu_bwd_apply: plane ranges need C %% 4 == 0 and 16-byte aligned tensors");
-        bn_bwd_apply_kernel<<<stream_grid(M * C, BN_THREADS * 8), BN_THREADS, 0, st>>>(
-            y, dout, M, C, gamma, beta, mean, invstd, workspace, dgamma, dbeta, dy, (__half*)dy_f16, dy_scale2);
-    }
-    MODE_LAUNCH_CHECK();
-    return 0;
+    return mode_bn_relu_bwd_apply_ex(y, dout, M, C, gamma, beta, mean, invstd, dgamma, dbeta, dy, dy_f16, dy_scale2, planes,
+                                     workspace_v, nullptr, nullptr, stream);
 }
 
 extern "C" int mode_bn_relu_bwd(const float* y, const float* dout, int64_t M, int32_t C, const float* gamma,
@@ -687,15 +753,23 @@ extern "C" int mode_bn_relu_bwd(const float* y, const float* dout, int64_t M, in
                                   nullptr, workspace_v, stream);
 }
 
-extern "C" int mode_cast_f16(const float* src, void* dst_f16, int64_t n, float scale, const float* scale_dev,
-                             void* stream) {
+extern "C" int mode_cast_f16_ex(const float* src, void* dst_f16, int64_t n, float scale, const float* scale_dev,
+                                const mode_halo_push_t* halo, void* stream) {
     if (!src || !dst_f16 || n <= 0) MODE_FAIL("mode_cast_f16: bad arguments");
     if ((reinterpret_cast<uintptr_t>(src) & 15) || (reinterpret_cast<uintptr_t>(dst_f16) & 7))
         MODE_FAIL("mode_cast_f16: pointers must be 16-byte (src) / 8-byte (dst) aligned");
-    cast_f16_kernel<<<wave_grid(cast_f16_kernel, 256, ceil_div(n / 4 + 1, 256 * 4)), 256, 0, (cudaStream_t)stream>>>(src, (__half*)dst_f16, n, scale,
-                                                                                         scale_dev);
+    const HaloPush hp = to_halo_push(halo);
+    if (hp.on() && ((n & 3) || hp.bytes <= 0 || (hp.bytes & 15) || hp.bytes > n * 2 || !hp.ticket))
+        MODE_FAIL("mode_cast_f16: bad halo descriptor (n %% 4 == 0, 0 < bytes <= tensor bytes, bytes %% 16 == 0)");
+    cast_f16_kernel<<<wave_grid(cast_f16_kernel, 256, ceil_div(n / 4 + 1, 256 * 4)), 256, 0, (cudaStream_t)stream>>>(
+        src, (__half*)dst_f16, n, scale, scale_dev, hp);
     MODE_LAUNCH_CHECK();
     return 0;
+}
+
+extern "C" int mode_cast_f16(const float* src, void* dst_f16, int64_t n, float scale, const float* scale_dev,
+                             void* stream) {
+    return mode_cast_f16_ex(src, dst_f16, n, scale, scale_dev, nullptr, stream);
 }
 
 extern "C" int mode_amax(const float* src, int64_t n, float* amax, void* stream) {

@@ -7,6 +7,7 @@
 #include <stdio.h>
 
 #include "../../include/repmode_b200.h"
+#include "peer.cuh"
 
 namespace mode {
 
@@ -46,6 +47,7 @@ struct ConvExt {
     __half* y16;                   // optional fp16 copy of the result [N, Dy16, H, W, Nout], output plane q -> plane q + y16_off
     int Dy16, y16_off;
     float y16_scale;
+    PeerPush push;                 // D-sharded slabs: the last CTA broadcasts bn_sums (2 * Nout doubles) to every rank
     __host__ __device__ int p_lo() const { return -x_off; }              // valid input planes in OUTPUT plane coordinates
     __host__ __device__ int p_hi() const { return Dx - x_off - 1; }
 };

@@ -540,6 +540,8 @@ conv3d_pair_kernel(const __grid_constant__ CUtensorMap xmap, const PairParams P)
             const int which = i / cp::NT, ch = i % cp::NT;
             atomicAdd(P.bn_sums + which * P.Nout + n0 + ch, s_bn[i]);
         }
+    // D-sharded slabs: the last CTA of the launch stores the slab's complete sums into every rank's slot and signals
+    if (P.ext.push.n > 0) push_vector_from_last_block(P.bn_sums, 2 * P.Nout, P.ext.push);
     if (warp == 2) tmem_dealloc_pair<512>(tmem);
 }
 

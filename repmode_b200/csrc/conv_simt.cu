@@ -143,6 +143,7 @@ __global__ void __launch_bounds__(256) conv3d_simt_kernel(const float* __restric
             }
         }
     }
+    if (ext.push.n > 0) push_vector_from_last_block(bn_sums, 2 * Nout, ext.push);
 }
 
 // wgrad: grid (125, splits, N*ob*ib), block 256: thread = (o = tid/8, 4 consecutive i)

@@ -400,6 +400,7 @@ conv3d_umma_kernel(const __grid_constant__ CUtensorMap xmap, const ConvParams P)
             const int which = i / P.Nt, ch = i % P.Nt;
             atomicAdd(P.bn_sums + which * P.Nout + n0 + ch, s_bn[i]);
         }
+    if (P.ext.push.n > 0) push_vector_from_last_block(P.bn_sums, 2 * P.Nout, P.ext.push);
     if (warp == 2) tmem_dealloc<512>(tmem);
 }
 

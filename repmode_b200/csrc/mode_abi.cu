@@ -133,6 +133,9 @@ extern "C" int mode_conv3d_ex(const void* x, mode_dtype_t x_dtype, const void* w
     ext.Dy16 = (opts && opts->Dy16 > 0) ? opts->Dy16 : D;
     ext.y16_off = opts ? opts->y16_off : 0;
     ext.y16_scale = (opts && opts->y16_scale != 0.f) ? opts->y16_scale : 1.f;
+    ext.push = to_peer_push(opts ? opts->stats_push : nullptr);
+    if (ext.push.n < 0 || ext.push.n > 8 || (ext.push.n > 0 && (!ext.push.ticket || !bn_sums)))
+        MODE_FAIL("mode_conv3d: bad stats_push descriptor (needs bn_sums, a ticket and <= 8 destinations)");
     if (!x || !w || (!y && !ext.y16)) MODE_FAIL("mode_conv3d: null pointer");
     if (N <= 0 || D <= 0 || H <= 0 || W <= 0 || K <= 0 || Nout <= 0) MODE_FAIL("mode_conv3d: non-positive dimension");
     if (ext.x_off < 0 || ext.x_off + D > ext.Dx)

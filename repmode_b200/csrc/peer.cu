@@ -17,47 +17,11 @@
 #include <algorithm>
 
 #include "common.cuh"
+#include "peer.cuh"
 
 namespace mode {
 
 int* device_error_flag();   // mode_abi.cu
-
-__device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
-    uint32_t v;
-    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-    return v;
-}
-__device__ __forceinline__ uint64_t peer_timer_ns() {
-    uint64_t t;
-    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-    return t;
-}
-
-// Spin until *signal - base >= want (wrap-safe); false on timeout.
-__device__ __forceinline__ bool wait_signal(const uint32_t* signal, uint32_t target) {
-    const uint64_t t0 = peer_timer_ns();
-    while ((int32_t)(ld_acquire_sys(signal) - target) < 0) {
-        __nanosleep(64);
-        if (peer_timer_ns() - t0 > 10000000000ull) return false;
-    }
-    return true;
-}
-
-// The last block of a launch signals: every block fences its payload stores, takes a ticket; the block that takes the last
-// ticket resets the counter (so the next launch / graph replay starts from 0) and increments the consumer's signal(s).
-struct SignalList { uint32_t* p[8]; int n; };
-__device__ __forceinline__ void finish_and_signal(uint32_t* ticket, const SignalList& sig) {
-    __threadfence_system();
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        const uint32_t total = gridDim.x * gridDim.y * gridDim.z;
-        if (atomicAdd(ticket, 1u) == total - 1) {
-            *ticket = 0;
-            __threadfence_system();
-            for (int i = 0; i < sig.n; ++i) atomicAdd_system(sig.p[i], 1u);
-        }
-    }
-}
 
 // ---- put: up to 8 (src -> dst) segments of equal size, one signal per segment ---------------------------------------
 struct PutList { const uint4* src[8]; uint4* dst[8]; uint32_t* sig[8]; int n; long long vec; };
@@ -75,10 +39,7 @@ __global__ void __launch_bounds__(256) peer_put_kernel(PutList L, uint32_t* tick
         for (int u = 0; u < 4; ++u)
             if (i + u * stride < L.vec) d[i + u * stride] = v[u];
     }
-    SignalList sg;
-    sg.n = L.n;
-    for (int i = 0; i < 8; ++i) sg.p[i] = L.sig[i];
-    finish_and_signal(ticket, sg);
+    if (finish_block_is_last(ticket) && threadIdx.x == 0) signal_all(L.sig, L.n);
 }
 
 __global__ void peer_wait_kernel(const uint32_t* signal, uint32_t* expect, uint32_t add, int* error_flag) {

@@ -172,20 +172,23 @@ def reparam_fwd(layer, gate_in, U, ci, co, dtype, want_dgrad, w_scale=1.0, fork=
 
 
 def conv3d(x, dtype, w, sample_u, n, d, h, wd, k, nout, out_scale_dev=None, bn_sums=None, impl=0, stat_range=None,
-           out_scale=1.0, out=None, halo=None, ep=None, y16=None, want_y=True):
+           out_scale=1.0, out=None, halo=None, ep=None, y16=None, want_y=True, stats_push=None):
     """K2 / K3 through mode_conv3d_ex.  d = OUTPUT planes.
     halo = (Dx, x_off): x holds Dx >= d planes and output plane q is centred on input plane q + x_off (D-sharded slabs).
     ep = (scale[nout] | None, shift[nout] | None, relu): per-channel affine + ReLU fused into the epilogue (eval BatchNorm).
     y16 = (buffer fp16 [n, Dy16, h, wd, nout], y16_off, scale): fp16 copy of the result written at plane y16_off + q.
-    want_y=False skips the fp32 result (returns None)."""
+    want_y=False skips the fp32 result (returns None).
+    stats_push = lib.ModePeerPush: the last CTA broadcasts bn_sums to every rank of a D-sharded volume (peer.PeerComm)."""
     lib = _lib.load()
     y = out
     if y is None and want_y:
         y = torch.empty((n, d, h, wd, nout), dtype=torch.float32, device=x.device)
     lo, hi = stat_range if stat_range is not None else (0, d)
     opts = None
-    if halo is not None or ep is not None or y16 is not None:
+    if halo is not None or ep is not None or y16 is not None or stats_push is not None:
         o = _lib.ModeConvOpts()
+        if stats_push is not None:
+            o.stats_push = ctypes.pointer(stats_push)
         if halo is not None:
             o.Dx, o.x_off = int(halo[0]), int(halo[1])
         keep = []
@@ -279,7 +282,7 @@ class ModeConvFunction(torch.autograd.Function):
     @torch.amp.custom_fwd(device_type="cuda", cast_inputs=torch.float32)
     @_on_device_of_first
     def forward(ctx, x, gate_in, k5, k3, k1, a3, a5, gate_w, gate_b, bn_w, bn_b, running_mean, running_var, training,
-                conv_type, precision, shard=None):
+                conv_type, precision, shard=None, eps=BN_EPS, momentum=BN_MOMENTUM):
         _require_cuda(x, gate_in, k5)
         lib = _lib.load()
         n, ci_x, d, h, wd = x.shape
@@ -337,13 +340,14 @@ class ModeConvFunction(torch.autograd.Function):
             if training:
                 mean = torch.empty(co, dtype=torch.float32, device=dev)
                 invstd = torch.empty(co, dtype=torch.float32, device=dev)
-                _lib.check(lib.mode_bn_finalize(_p(sums), m_stat, co, _p(bn_w), _p(bn_b), BN_EPS, BN_MOMENTUM, _p(mean),
-                                                _p(invstd), _p(scale), _p(shift), _p(running_mean), _p(running_var),
-                                                _stream()), "mode_bn_finalize")
+                _lib.check(lib.mode_bn_finalize(_p(sums), m_stat, co, _p(bn_w), _p(bn_b), float(eps), float(momentum),
+                                                _p(mean), _p(invstd), _p(scale), _p(shift), _p(running_mean),
+                                                _p(running_var), _stream()), "mode_bn_finalize")
             else:
-                invstd_r = torch.rsqrt(running_var + BN_EPS)
+                invstd_r = torch.rsqrt(running_var + eps)
                 scale = (bn_w * invstd_r).contiguous()
                 shift = (bn_b - running_mean * scale).contiguous()
+                mean, invstd = running_mean.clone(), invstd_r.contiguous()      # frozen statistics (for a backward pass)
             out = torch.empty_like(y)
             _lib.check(lib.mode_bn_apply_relu(_p(y), m_rows, co, _p(scale), _p(shift), 1, _p(out), None, 1.0,
                                               ctypes.byref(planes) if planes is not None else None, _stream()),
@@ -352,9 +356,7 @@ class ModeConvFunction(torch.autograd.Function):
             out = y
         ctx.frozen_bn = normal and not training
         ctx.shard = shard
-        if ctx.frozen_bn:
-            pass            # eval-mode forward is the supported use; backward through frozen BN raises below
-        elif needs_dx or needs_dw or (normal and (ctx.needs_input_grad[9] or ctx.needs_input_grad[10])):
+        if needs_dx or needs_dw or (normal and (ctx.needs_input_grad[9] or ctx.needs_input_grad[10])):
             x_w = x_op if (UMMA_WGRAD or not use_umma) else xn      # operand K4 will read
             ctx.save_for_backward(None, x_w if needs_dw else None, y if normal else None, g, w_dg,
                                   gate_u, sample_u, k5, k3, k1, a3, a5, gate_w, gate_b, bn_w, bn_b, mean, invstd, w_s2)
@@ -365,8 +367,6 @@ class ModeConvFunction(torch.autograd.Function):
     @torch.amp.custom_bwd(device_type="cuda")
     @_on_device_of_first
     def backward(ctx, dout):
-        if ctx.frozen_bn:
-            raise NotImplementedError("MoDEConv backward in eval mode (frozen BatchNorm statistics) is not supported")
         lib = _lib.load()
         (x_op, x_w, y, g, w_dg, gate_u, sample_u, k5, k3, k1, a3, a5, gate_w, gate_b, bn_w, bn_b, mean, invstd,
          w_s2) = ctx.saved_tensors
@@ -385,6 +385,11 @@ class ModeConvFunction(torch.autograd.Function):
             dbeta = torch.empty(co, dtype=torch.float32, device=dev)
             ws = torch.empty(int(lib.mode_bn_bwd_workspace_bytes(co)), dtype=torch.uint8, device=dev)
             planes = shard.planes(h * wd, d) if shard is not None else None
+            if ctx.frozen_bn:
+                # eval mode (fine-tuning with frozen BatchNorm, saliency maps): the statistics are constants, so
+                # dy = gamma * invstd_running * dz with no mean terms.  That is exactly what the kernels compute for
+                # "halo copy" planes (valid, not owned): declare every plane one.  dgamma / dbeta are still the plain sums.
+                planes = _lib.ModePlanes(m_rows, 1, 0, 0, 0, 1, m_rows)
             pl = ctypes.byref(planes) if planes is not None else None
             _lib.check(lib.mode_bn_relu_bwd_reduce(_p(y), _p(doutn), m_rows, co, _p(bn_w), _p(bn_b), _p(mean), _p(invstd),
                                                    pl, _p(ws), _stream()), "mode_bn_relu_bwd_reduce")
@@ -449,7 +454,7 @@ class ModeConvFunction(torch.autograd.Function):
             if ci_p != ci:
                 dxn = dxn[..., :ci].contiguous()
             dx = from_ndhwc(dxn)
-        return (dx, None, *grads, dgamma, dbeta, None, None, None, None, None, None)
+        return (dx, None, *grads, dgamma, dbeta, None, None, None, None, None, None, None, None)
 
 
 EVAL_CACHE = os.environ.get("REPMODE_EVAL_CACHE", "1") == "1"
@@ -478,44 +483,72 @@ class EvalWeightCache:
         return self.w
 
 
+EVAL_F16_ACT = os.environ.get("REPMODE_EVAL_F16_ACT", "1") == "1"    # eval: 'normal' layers hand fp16 activations on
+EVAL_GRAPH = os.environ.get("REPMODE_EVAL_GRAPH", "1") == "1"        # eval: repeated Net forwards replay one CUDA graph
+
+
+def bn_eval_affine(bn):
+    """(scale, shift) of a frozen BatchNorm: y * scale + shift == (y - running_mean) / sqrt(running_var + eps) * w + b."""
+    bn_w, bn_b, rm, rv = bn[:4]
+    eps = bn[4] if len(bn) > 4 else BN_EPS
+    scale = (bn_w * torch.rsqrt(rv + eps)).contiguous()
+    shift = (bn_b - rm * scale).contiguous()
+    return scale, shift
+
+
 def mode_conv_eval(x, task_ids, params, bn, conv_type, precision, cache):
     """MoDEConv.forward in eval mode without autograd (Model.predict, fnet_model.py:149-223): cached W_eff per task,
-    conv on set task[0] for the whole batch (RepMode.py:209-210), frozen-statistics BatchNorm + ReLU."""
+    conv on set task[0] for the whole batch (RepMode.py:209-210), frozen-statistics BatchNorm + ReLU FOLDED INTO K2's
+    epilogue (RepMode.py:209-212: y is written once and never re-read).  On the tensor-core path a 'normal' layer returns
+    its activation as an fp16 channels_last_3d tensor -- exactly the operand the next conv would have rounded it to -- so a
+    chain of layers is one kernel per layer: no cast, no BatchNorm pass.  'final' layers return fp32."""
     _require_cuda(x, task_ids, params[0])
-    lib = _lib.load()
     n, ci_x, d, h, wd = x.shape
     co, ci = params[0].shape[0], params[0].shape[1]
     if ci_x != ci:
         raise RuntimeError(f"MoDEConv: input has {ci_x} channels, layer expects {ci}")
-    dev = x.device
     use_umma = precision == "f16" and umma_shape_ok(ci, co, d, h, wd)
     dtype = _lib.MODE_F16 if use_umma else _lib.MODE_F32
     ci_p, co_p = (_pad32(ci), _pad32(co)) if use_umma else (ci, co)
     w_scale = W_SCALE_F16 if use_umma else 1.0
     w_all = cache.get(params, params[5].shape[1], ci, co, dtype, w_scale)
-    xn = to_ndhwc(x.float())
-    x_op = pad_channels(cast_f16(xn), ci_p) if use_umma else xn
+    xn = x.permute(0, 2, 3, 4, 1)
+    if use_umma:
+        if xn.dtype == torch.float16 and xn.is_contiguous():
+            x_op = xn                                               # the previous layer's fp16 activation IS the operand
+        else:
+            x_op = cast_f16(xn.contiguous().float())
+        x_op = pad_channels(x_op, ci_p)
+    else:
+        x_op = xn.contiguous().float()
     sample_u = task_ids.to(torch.int32).reshape(-1)[:1].expand(n).contiguous()
-    y = conv3d(x_op, dtype, w_all, sample_u, n, d, h, wd, ci_p, co_p, None, None, out_scale=1.0 / w_scale)
-    if co_p != co:
-        y = y[..., :co].contiguous()
-    if conv_type == "normal":
-        bn_w, bn_b, rm, rv = bn
-        scale = (bn_w * torch.rsqrt(rv + BN_EPS)).contiguous()
-        shift = (bn_b - rm * scale).contiguous()
-        out = torch.empty_like(y)
-        _lib.check(lib.mode_bn_apply_relu(_p(y), n * d * h * wd, co, _p(scale), _p(shift), 1, _p(out), None, 1.0, None,
-                                          _stream()), "mode_bn_apply_relu")
-        y = out
+    normal = conv_type == "normal"
+    ep = None
+    if normal:
+        scale, shift = bn_eval_affine(bn)
+        if co_p != co:
+            scale, shift = pad_channels(scale, co_p), pad_channels(shift, co_p)
+        ep = (scale, shift, True)
+    if use_umma and normal and EVAL_F16_ACT:
+        y16 = torch.empty((n, d, h, wd, co_p), dtype=torch.float16, device=x.device)
+        conv3d(x_op, dtype, w_all, sample_u, n, d, h, wd, ci_p, co_p, None, None, out_scale=1.0 / w_scale, ep=ep,
+               y16=(y16, 0, 1.0), want_y=False)
+        y = y16 if co_p == co else y16[..., :co].contiguous()
+    else:
+        y = conv3d(x_op, dtype, w_all, sample_u, n, d, h, wd, ci_p, co_p, None, None, out_scale=1.0 / w_scale, ep=ep)
+        if co_p != co:
+            y = y[..., :co].contiguous()
     return from_ndhwc(y)
 
 
 def mode_conv(x, gate_in, params, bn, training, conv_type="normal", precision=None, shard=None):
     """Functional MoDEConv. params: (k5,k3,k1,a3,a5,gate_w,gate_b); bn: (weight,bias,running_mean,running_var) or None;
     shard: ShardSpec when x is one D-slab (with halos) of a larger volume."""
-    bn_w, bn_b, rm, rv = bn if bn is not None else (None, None, None, None)
+    bn_w, bn_b, rm, rv = bn[:4] if bn is not None else (None, None, None, None)
+    eps = bn[4] if bn is not None and len(bn) > 4 else BN_EPS
+    momentum = bn[5] if bn is not None and len(bn) > 5 and bn[5] is not None else BN_MOMENTUM
     return ModeConvFunction.apply(x, gate_in, *params, bn_w, bn_b, rm, rv, training, conv_type,
-                                  precision or default_precision(), shard)
+                                  precision or default_precision(), shard, eps, momentum)
 
 
 class BnReluFunction(torch.autograd.Function):
@@ -525,7 +558,7 @@ class BnReluFunction(torch.autograd.Function):
     @staticmethod
     @torch.amp.custom_fwd(device_type="cuda", cast_inputs=torch.float32)
     @_on_device_of_first
-    def forward(ctx, y, weight, bias, running_mean, running_var, training, shard=None):
+    def forward(ctx, y, weight, bias, running_mean, running_var, training, shard=None, eps=BN_EPS, momentum=BN_MOMENTUM):
         _require_cuda(y)
         lib = _lib.load()
         yn = y.contiguous()                                    # [N,D,H,W,C] fp32
@@ -544,26 +577,25 @@ class BnReluFunction(torch.autograd.Function):
             _lib.check(lib.mode_bn_stats(_p(yn), m_rows, c, _p(sums), _stream()), "mode_bn_stats")
             if shard is not None:
                 shard.all_reduce(sums, "bn.fwd")                         # every plane of a stride-2 level is owned: plain sum
-            _lib.check(lib.mode_bn_finalize(_p(sums), m_stat, c, _p(weight), _p(bias), BN_EPS, BN_MOMENTUM, _p(mean),
-                                            _p(invstd), _p(scale), _p(shift), _p(running_mean), _p(running_var),
+            _lib.check(lib.mode_bn_finalize(_p(sums), m_stat, c, _p(weight), _p(bias), float(eps), float(momentum),
+                                            _p(mean), _p(invstd), _p(scale), _p(shift), _p(running_mean), _p(running_var),
                                             _stream()), "mode_bn_finalize")
         else:
-            scale = (weight * torch.rsqrt(running_var + BN_EPS)).contiguous()
+            invstd = torch.rsqrt(running_var + eps).contiguous()
+            mean = running_mean.clone()
+            scale = (weight * invstd).contiguous()
             shift = (bias - running_mean * scale).contiguous()
         out = torch.empty_like(yn)
         _lib.check(lib.mode_bn_apply_relu(_p(yn), m_rows, c, _p(scale), _p(shift), 1, _p(out), None, 1.0, None,
                                           _stream()), "mode_bn_apply_relu")
         ctx.training = training
-        if training:
-            ctx.save_for_backward(yn, weight, bias, mean, invstd)
+        ctx.save_for_backward(yn, weight, bias, mean, invstd)
         return out
 
     @staticmethod
     @torch.amp.custom_bwd(device_type="cuda")
     @_on_device_of_first
     def backward(ctx, dout):
-        if not ctx.training:
-            raise NotImplementedError("BatchNorm backward in eval mode (frozen statistics) is not supported")
         lib = _lib.load()
         yn, weight, bias, mean, invstd = ctx.saved_tensors
         c = yn.shape[-1]
@@ -576,6 +608,8 @@ class BnReluFunction(torch.autograd.Function):
         ws = torch.empty(int(lib.mode_bn_bwd_workspace_bytes(c)), dtype=torch.uint8, device=dev)
         shard = ctx.shard
         planes = shard.planes(m_rows // (yn.shape[0] * yn.shape[1]), yn.shape[1]) if shard is not None else None
+        if not ctx.training:              # frozen statistics: every plane a "halo copy" -> no mean terms (see ModeConvFunction)
+            planes = _lib.ModePlanes(m_rows, 1, 0, 0, 0, 1, m_rows)
         pl = ctypes.byref(planes) if planes is not None else None
         _lib.check(lib.mode_bn_relu_bwd_reduce(_p(yn), _p(doutn), m_rows, c, _p(weight), _p(bias), _p(mean), _p(invstd),
                                                pl, _p(ws), _stream()), "mode_bn_relu_bwd_reduce")
@@ -587,7 +621,7 @@ class BnReluFunction(torch.autograd.Function):
         if shard is not None and shard.world() > 1:
             dgamma /= shard.world()
             dbeta /= shard.world()
-        return dy, dgamma, dbeta, None, None, None, None
+        return dy, dgamma, dbeta, None, None, None, None, None, None
 
 
 def down_conv_bn_relu(x, conv_w, bn, training, shard=None):
@@ -599,8 +633,15 @@ def down_conv_bn_relu(x, conv_w, bn, training, shard=None):
     co = conv_w.shape[0]
     x8 = xn.reshape(n, d // 2, 2, h // 2, 2, w // 2, 2, c).permute(0, 1, 3, 5, 2, 4, 6, 7).reshape(-1, 8 * c)
     wm = conv_w.permute(2, 3, 4, 1, 0).reshape(8 * c, co)                     # [(kd,kh,kw,ci), co]
+    if not training and not torch.is_grad_enabled():
+        # eval: frozen BatchNorm folded into the GEMM (scale into the weight columns, shift as the bias), ReLU in place;
+        # the activation keeps its dtype (fp16 on the tensor-core eval path)
+        scale, shift = bn_eval_affine((bn.weight, bn.bias, bn.running_mean, bn.running_var, bn.eps))
+        y = torch.addmm(shift.to(x8.dtype), x8, (wm * scale).to(x8.dtype)).relu_()
+        return y.view(n, d // 2, h // 2, w // 2, co).permute(0, 4, 1, 2, 3)
     y = (x8 @ wm.to(x8.dtype)).view(n, d // 2, h // 2, w // 2, co)
-    out = BnReluFunction.apply(y, bn.weight, bn.bias, bn.running_mean, bn.running_var, training, shard)
+    out = BnReluFunction.apply(y, bn.weight, bn.bias, bn.running_mean, bn.running_var, training, shard, bn.eps,
+                               bn.momentum if bn.momentum is not None else BN_MOMENTUM)
     return out.permute(0, 4, 1, 2, 3)
 
 
@@ -611,7 +652,14 @@ def up_conv_bn_relu(x, convt_w, bn, training, shard=None):
     n, d, h, w, c = xn.shape
     co = convt_w.shape[1]
     wm = convt_w.permute(0, 2, 3, 4, 1).reshape(c, 8 * co)                    # [ci, (kd,kh,kw,co)]
+    if not training and not torch.is_grad_enabled():
+        scale, shift = bn_eval_affine((bn.weight, bn.bias, bn.running_mean, bn.running_var, bn.eps))
+        wf = (wm.view(c, 8, co) * scale).reshape(c, 8 * co).to(xn.dtype)
+        y8 = torch.addmm(shift.repeat(8).to(xn.dtype), xn.reshape(-1, c), wf).relu_().view(n, d, h, w, 2, 2, 2, co)
+        y = y8.permute(0, 1, 4, 2, 5, 3, 6, 7).reshape(n, 2 * d, 2 * h, 2 * w, co)
+        return y.permute(0, 4, 1, 2, 3)
     y8 = (xn.reshape(-1, c) @ wm.to(xn.dtype)).view(n, d, h, w, 2, 2, 2, co)
     y = y8.permute(0, 1, 4, 2, 5, 3, 6, 7).reshape(n, 2 * d, 2 * h, 2 * w, co)
-    out = BnReluFunction.apply(y, bn.weight, bn.bias, bn.running_mean, bn.running_var, training, shard)
+    out = BnReluFunction.apply(y, bn.weight, bn.bias, bn.running_mean, bn.running_var, training, shard, bn.eps,
+                               bn.momentum if bn.momentum is not None else BN_MOMENTUM)
     return out.permute(0, 4, 1, 2, 3)

@@ -36,10 +36,26 @@ class ModePlanes(ctypes.Structure):
                 ("m_global", ctypes.c_int64)]
 
 
+class ModeHaloPush(ctypes.Structure):
+    _fields_ = [("lo_dst", ctypes.c_void_p), ("lo_signal", ctypes.c_void_p), ("hi_dst", ctypes.c_void_p),
+                ("hi_signal", ctypes.c_void_p), ("bytes", ctypes.c_int64), ("ticket", ctypes.c_void_p)]
+
+
+class ModePeerPush(ctypes.Structure):
+    _fields_ = [("n", ctypes.c_int32), ("dst", ctypes.c_void_p * 8), ("signal", ctypes.c_void_p * 8),
+                ("ticket", ctypes.c_void_p)]
+
+
+class ModePeerGather(ctypes.Structure):
+    _fields_ = [("slots", ctypes.c_void_p), ("world", ctypes.c_int32), ("signal", ctypes.c_void_p),
+                ("expect", ctypes.c_void_p)]
+
+
 class ModeConvOpts(ctypes.Structure):
     _fields_ = [("Dx", ctypes.c_int32), ("x_off", ctypes.c_int32), ("ep_scale", ctypes.c_void_p),
                 ("ep_shift", ctypes.c_void_p), ("relu", ctypes.c_int32), ("y16", ctypes.c_void_p),
-                ("Dy16", ctypes.c_int32), ("y16_off", ctypes.c_int32), ("y16_scale", ctypes.c_float)]
+                ("Dy16", ctypes.c_int32), ("y16_off", ctypes.c_int32), ("y16_scale", ctypes.c_float),
+                ("stats_push", ctypes.POINTER(ModePeerPush))]
 
 
 class ModeCaps(ctypes.Structure):
@@ -104,6 +120,13 @@ SIGNATURES = {
                                          _vp, _i32, _vp]),
     "mode_bn_stats": (ctypes.c_int, [_vp, _i64, _i32, _vp, _vp]),
     "mode_bn_finalize": (ctypes.c_int, [_vp, _i64, _i32, _vp, _vp, _f32, _f32, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "mode_bn_finalize_ex": (ctypes.c_int, [_vp, _i64, _i32, _vp, _vp, _f32, _f32, _vp, _vp, _vp, _vp, _vp, _vp,
+                                           ctypes.POINTER(ModePeerGather), _vp]),
+    "mode_bn_relu_bwd_reduce_ex": (ctypes.c_int, [_vp, _vp, _i64, _i32, _vp, _vp, _vp, _vp, _vp, _vp,
+                                                  ctypes.POINTER(ModePeerPush), _vp]),
+    "mode_bn_relu_bwd_apply_ex": (ctypes.c_int, [_vp, _vp, _i64, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
+                                                 _vp, ctypes.POINTER(ModePeerGather), ctypes.POINTER(ModeHaloPush), _vp]),
+    "mode_cast_f16_ex": (ctypes.c_int, [_vp, _vp, _i64, _f32, _vp, ctypes.POINTER(ModeHaloPush), _vp]),
     "mode_bn_apply_relu": (ctypes.c_int, [_vp, _i64, _i32, _vp, _vp, _i32, _vp, _vp, _f32, _vp, _vp]),
     "mode_bn_relu_bwd_reduce": (ctypes.c_int, [_vp, _vp, _i64, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "mode_bn_relu_bwd_apply": (ctypes.c_int, [_vp, _vp, _i64, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp,

@@ -99,6 +99,8 @@ class TorchComm:
     def _peer(self, r):
         return dist.get_global_rank(self.group, r) if self.group is not None else r
 
+    fused = False            # no kernel-fused exchange steps: callers use halo_fill / all_reduce
+
     def barrier(self):
         if self.world > 1:
             dist.barrier(group=self.group)
@@ -266,6 +268,60 @@ class PeerComm:
         if not direct:
             t.reshape(-1).copy_(src[:n])
         return t
+
+    # ---- descriptors for exchange steps FUSED into kernels (mode_halo_push_t / mode_peer_push_t / mode_peer_gather_t) ----
+    fused = True
+
+    def halo_push_desc(self, ext, h, tag=""):
+        """Descriptor for a kernel that writes the interior planes [h, D + h) of `ext` ([1, D + 2h, H, W, C], allocated with
+        comm.alloc): its first / last h planes also go into the neighbours' halo planes.  Follow the kernel with
+        halo_wait(desc).  Returns (ModeHaloPush, wait_args)."""
+        assert ext.shape[0] == 1 and ext.is_contiguous()
+        d = ext.shape[1] - 2 * h
+        plane = ext[0, 0].numel() * ext.element_size()
+        idx = self._signal(("halo", tag))
+        _, expect, ticket = self._sig_ptrs(idx)
+        hp = _lib.ModeHaloPush()
+        k = 0
+        if self.rank > 0:                                         # my first h interior planes -> lower neighbour's top halo
+            hp.lo_dst = self._peer_ptr(self.rank - 1, ext, (d + h) * plane)
+            hp.lo_signal = self.peer_base[self.rank - 1] + 4 * idx
+            k += 1
+        if self.rank < self.world - 1:                            # my last h interior planes -> upper neighbour's bottom halo
+            hp.hi_dst = self._peer_ptr(self.rank + 1, ext, 0)
+            hp.hi_signal = self.peer_base[self.rank + 1] + 4 * idx
+            k += 1
+        hp.bytes = h * plane
+        hp.ticket = ticket
+        return hp, (self.arena.data_ptr() + 4 * idx, expect, k)
+
+    def halo_wait(self, wait_args):
+        sig, expect, k = wait_args
+        self.n_collectives += 1
+        if k > 0:
+            _lib.check(_lib.load().mode_peer_wait(ctypes.c_void_p(sig), ctypes.c_void_p(expect), k, self._stream()),
+                       "mode_peer_wait")
+
+    def reduce_desc(self, count, tag=""):
+        """(ModePeerPush, ModePeerGather) for `count` doubles: the producing kernel's last block stores the rank's vector
+        into slot[rank] of every rank; the consuming kernel waits for all of them and sums the slots in rank order."""
+        name = ("fused_ar", tag, count)
+        slots = self.alloc(name, (self.world, count), torch.float64)
+        idx = self._signal(name)
+        _, expect, ticket = self._sig_ptrs(idx)
+        pp = _lib.ModePeerPush()
+        pp.n = self.world
+        for q in range(self.world):
+            pp.dst[q] = self._peer_ptr(q, slots, self.rank * count * 8)
+            pp.signal[q] = self.peer_base[q] + 4 * idx
+        pp.ticket = ticket
+        pg = _lib.ModePeerGather()
+        pg.slots = slots.data_ptr()
+        pg.world = self.world
+        pg.signal = self.arena.data_ptr() + 4 * idx
+        pg.expect = expect
+        self.n_collectives += 1
+        return pp, pg
 
     def barrier(self):
         dist.barrier(group=self.group)

@@ -12,6 +12,8 @@ gradients are partial per rank and summed by the usual data-parallel all-reduce 
 Verified on CPU/gloo against the unsharded oracle (tests/test_parallel_cpu.py) and on 2 GPUs against the
 unsharded kernels (tests/check_sharded.py).
 """
+import os
+
 import torch
 import torch.distributed as dist
 
@@ -25,7 +27,7 @@ def _bn(mod):
     if mod.conv_type != "normal":
         return None
     m = mod.subsequent_layer[0]
-    return (m.weight, m.bias, m.running_mean, m.running_var)
+    return (m.weight, m.bias, m.running_mean, m.running_var, m.eps, m.momentum)
 
 
 def sharded_stage(stage, x_local, t, d_global, group=None):
@@ -56,6 +58,9 @@ def sharded_stage(stage, x_local, t, d_global, group=None):
 
 # ------------------------------------------------------------------------------------- one MoDEConv on a D-slab
 BLOCK_HALO = 2      # a single 5^3 conv reaches 2 planes
+# exchange steps fused into the producing / consuming kernels when the comm supports it (peer.PeerComm); 0 = separate
+# put / wait / sum launches (the A/B arm)
+FUSED_EXCHANGE = os.environ.get("REPMODE_FUSED_EXCHANGE", "1") == "1"
 
 
 class ShardedConvFunction(torch.autograd.Function):
@@ -103,32 +108,51 @@ class ShardedConvFunction(torch.autograd.Function):
         x_ext = comm.alloc((tag, "x_ext", str(tdt)), (1, d + 2 * H2, h, wd, ci), tdt, dev)
         k1_fork = Fm._Fork(dev, True)
         g, w_fwd, w_dg = Fm.reparam_fwd(layer, gate_in[:1].contiguous(), 1, ci, co, dtype, needs_dx, w_scale, fork=k1_fork)
-        if use_umma:
-            _lib.check(lib.mode_cast_f16(Fm._p(xn), Fm._p(x_ext[0, H2]), xn.numel(), 1.0, None, Fm._stream()), "mode_cast_f16")
+        fused = FUSED_EXCHANGE and getattr(comm, "fused", False) and comm.world > 1
+        if use_umma and fused:
+            # the cast kernel stores its boundary planes straight into the neighbours' halo planes and signals
+            hp, wait_x = comm.halo_push_desc(x_ext, H2, tag + ".x")
+            _lib.check(lib.mode_cast_f16_ex(Fm._p(xn), Fm._p(x_ext[0, H2]), xn.numel(), 1.0, None, ctypes.byref(hp),
+                                            Fm._stream()), "mode_cast_f16")
+            comm.halo_wait(wait_x)
         else:
-            x_ext[0, H2:H2 + d].copy_(xn[0])
-        comm.halo_fill(x_ext, H2, tag + ".x")
+            if use_umma:
+                _lib.check(lib.mode_cast_f16(Fm._p(xn), Fm._p(x_ext[0, H2]), xn.numel(), 1.0, None, Fm._stream()),
+                           "mode_cast_f16")
+            else:
+                x_ext[0, H2:H2 + d].copy_(xn[0])
+            comm.halo_fill(x_ext, H2, tag + ".x")
         k1_fork.join()
 
         sums = torch.zeros(2 * co, dtype=torch.float64, device=dev)
-        y = Fm.conv3d(x_ext, dtype, w_fwd, sample_u, 1, d, h, wd, ci, co, None, sums, out_scale=1.0 / w_scale,
-                      halo=(d + 2 * H2, H2))
-        comm.all_reduce(sums, tag + ".bnf")
         m_rows = d * h * wd
         m_global = d_global * h * wd
         mean = torch.empty(co, dtype=torch.float32, device=dev)
         invstd = torch.empty(co, dtype=torch.float32, device=dev)
         scale = torch.empty(co, dtype=torch.float32, device=dev)
         shift = torch.empty(co, dtype=torch.float32, device=dev)
-        _lib.check(lib.mode_bn_finalize(Fm._p(sums), m_global, co, Fm._p(bn_w), Fm._p(bn_b), float(eps), float(momentum),
-                                        Fm._p(mean), Fm._p(invstd), Fm._p(scale), Fm._p(shift), Fm._p(running_mean),
-                                        Fm._p(running_var), Fm._stream()), "mode_bn_finalize")
+        if fused:
+            # K2's last CTA broadcasts the slab's sums; the finalize kernel waits for every rank's and adds them up
+            pp, pg = comm.reduce_desc(2 * co, tag + ".bnf")
+            y = Fm.conv3d(x_ext, dtype, w_fwd, sample_u, 1, d, h, wd, ci, co, None, sums, out_scale=1.0 / w_scale,
+                          halo=(d + 2 * H2, H2), stats_push=pp)
+            _lib.check(lib.mode_bn_finalize_ex(Fm._p(sums), m_global, co, Fm._p(bn_w), Fm._p(bn_b), float(eps),
+                                               float(momentum), Fm._p(mean), Fm._p(invstd), Fm._p(scale), Fm._p(shift),
+                                               Fm._p(running_mean), Fm._p(running_var), ctypes.byref(pg), Fm._stream()),
+                       "mode_bn_finalize")
+        else:
+            y = Fm.conv3d(x_ext, dtype, w_fwd, sample_u, 1, d, h, wd, ci, co, None, sums, out_scale=1.0 / w_scale,
+                          halo=(d + 2 * H2, H2))
+            comm.all_reduce(sums, tag + ".bnf")
+            _lib.check(lib.mode_bn_finalize(Fm._p(sums), m_global, co, Fm._p(bn_w), Fm._p(bn_b), float(eps),
+                                            float(momentum), Fm._p(mean), Fm._p(invstd), Fm._p(scale), Fm._p(shift),
+                                            Fm._p(running_mean), Fm._p(running_var), Fm._stream()), "mode_bn_finalize")
         out = torch.empty_like(y)
         _lib.check(lib.mode_bn_apply_relu(Fm._p(y), m_rows, co, Fm._p(scale), Fm._p(shift), 1, Fm._p(out), None, 1.0, None,
                                           Fm._stream()), "mode_bn_apply_relu")
         ctx.save_for_backward(y, g, w_dg, gate_in, sample_u, k5, k3, k1, a3, a5, gate_w, gate_b, bn_w, bn_b, mean, invstd)
         ctx.x_ext = x_ext                 # persistent exchange buffer: not a saved tensor (it is rewritten every step)
-        ctx.cfg = (d, h, wd, ci, co, use_umma, needs_dx, m_global, comm, tag)
+        ctx.cfg = (d, h, wd, ci, co, use_umma, needs_dx, m_global, comm, tag, fused)
         return Fm.from_ndhwc(out)
 
     @staticmethod
@@ -139,7 +163,7 @@ class ShardedConvFunction(torch.autograd.Function):
         from . import lib as _lib
         lib = _lib.load()
         y, g, w_dg, gate_in, sample_u, k5, k3, k1, a3, a5, gate_w, gate_b, bn_w, bn_b, mean, invstd = ctx.saved_tensors
-        d, h, wd, ci, co, use_umma, needs_dx, m_global, comm, tag = ctx.cfg
+        d, h, wd, ci, co, use_umma, needs_dx, m_global, comm, tag, fused = ctx.cfg
         x_ext = ctx.x_ext
         dev = dout.device
         dtype = _lib.MODE_F16 if use_umma else _lib.MODE_F32
@@ -150,21 +174,33 @@ class ShardedConvFunction(torch.autograd.Function):
         ws = torch.empty(int(lib.mode_bn_bwd_workspace_bytes(co)), dtype=torch.uint8, device=dev)
         planes = _lib.ModePlanes(h * wd, d, 0, d, 0, d, m_global)
         pl = ctypes.byref(planes)
-        _lib.check(lib.mode_bn_relu_bwd_reduce(Fm._p(y), Fm._p(doutn), m_rows, co, Fm._p(bn_w), Fm._p(bn_b), Fm._p(mean),
-                                               Fm._p(invstd), pl, Fm._p(ws), Fm._stream()), "mode_bn_relu_bwd_reduce")
-        # {sum dz, sum dz*xhat, max|dz|, max|xhat|}[co] as ONE fp64 vector: the fp16 scale of dy must be the SAME on every
-        # rank (halo planes travel in fp16) and the sum of the ranks' maxima bounds the global maximum
-        comm.all_reduce(ws.view(torch.float64), tag + ".bnb")
         dy_ext = comm.alloc((tag, "dy_ext", str(tdt)), (1, d + 2 * H2, h, wd, co), tdt, dev)
         dgamma = torch.empty(co, dtype=torch.float32, device=dev)
         dbeta = torch.empty(co, dtype=torch.float32, device=dev)
         dy_s2 = torch.empty(2, dtype=torch.float32, device=dev) if use_umma else None
         dy_int = dy_ext[0, H2:H2 + d]
-        _lib.check(lib.mode_bn_relu_bwd_apply(Fm._p(y), Fm._p(doutn), m_rows, co, Fm._p(bn_w), Fm._p(bn_b), Fm._p(mean),
-                                              Fm._p(invstd), Fm._p(dgamma), Fm._p(dbeta),
-                                              None if use_umma else Fm._p(dy_int), Fm._p(dy_int) if use_umma else None,
-                                              Fm._p(dy_s2), pl, Fm._p(ws), Fm._stream()), "mode_bn_relu_bwd_apply")
-        comm.halo_fill(dy_ext, H2, tag + ".dy")
+        apply_args = (Fm._p(y), Fm._p(doutn), m_rows, co, Fm._p(bn_w), Fm._p(bn_b), Fm._p(mean), Fm._p(invstd),
+                      Fm._p(dgamma), Fm._p(dbeta), None if use_umma else Fm._p(dy_int), Fm._p(dy_int) if use_umma else None,
+                      Fm._p(dy_s2), pl, Fm._p(ws))
+        # {sum dz, sum dz*xhat, max|dz|, max|xhat|}[co] travel as ONE fp64 vector: the fp16 scale of dy must be the SAME on
+        # every rank (halo planes travel in fp16) and the sum of the ranks' maxima bounds the global maximum
+        if fused:
+            # the reduce kernel's last block broadcasts the vector; the scale kernel in front of the apply pass gathers it;
+            # the apply pass stores the boundary planes of dy straight into the neighbours' halo planes
+            pp, pg = comm.reduce_desc(4 * co, tag + ".bnb")
+            _lib.check(lib.mode_bn_relu_bwd_reduce_ex(Fm._p(y), Fm._p(doutn), m_rows, co, Fm._p(bn_w), Fm._p(bn_b),
+                                                      Fm._p(mean), Fm._p(invstd), pl, Fm._p(ws), ctypes.byref(pp),
+                                                      Fm._stream()), "mode_bn_relu_bwd_reduce")
+            hp, wait_dy = comm.halo_push_desc(dy_ext, H2, tag + ".dy")
+            _lib.check(lib.mode_bn_relu_bwd_apply_ex(*apply_args, ctypes.byref(pg), ctypes.byref(hp), Fm._stream()),
+                       "mode_bn_relu_bwd_apply")
+            comm.halo_wait(wait_dy)
+        else:
+            _lib.check(lib.mode_bn_relu_bwd_reduce(Fm._p(y), Fm._p(doutn), m_rows, co, Fm._p(bn_w), Fm._p(bn_b), Fm._p(mean),
+                                                   Fm._p(invstd), pl, Fm._p(ws), Fm._stream()), "mode_bn_relu_bwd_reduce")
+            comm.all_reduce(ws.view(torch.float64), tag + ".bnb")
+            _lib.check(lib.mode_bn_relu_bwd_apply(*apply_args, Fm._stream()), "mode_bn_relu_bwd_apply")
+            comm.halo_fill(dy_ext, H2, tag + ".dy")
         inv = dy_s2[1:2] if use_umma else None
         d_weff = Fm.conv3d_wgrad(x_ext, dy_int, dtype, 1, d, h, wd, ci, co, inv, halo=(d + 2 * H2, H2))
         dx = None

@@ -156,3 +156,54 @@ def test_reparam_rows_kernel_bit_identical(dtype_name, ci, co, U, monkeypatch):
     monkeypatch.setenv("REPMODE_K1_ROWS", "1")
     g1, w1, d1 = Fm.reparam_fwd(layer, ids, U, ci, co, dtype, True, scale)
     assert torch.equal(g0, g1) and torch.equal(w0, w1) and torch.equal(d0, d1)
+
+
+def test_frozen_batchnorm_backward_matches_oracle():
+    """Backward through a MoDEConv in EVAL mode (frozen BatchNorm statistics: fine-tuning, saliency maps): dx and every
+    parameter gradient, BatchNorm affine included, against the oracle's autograd through F.batch_norm(training=False)."""
+    from oracle import mode_torch as otc
+    d = load_golden("conv_eval_small")
+    m = _build_conv(d, "f32").eval()
+    x = torch.from_numpy(d["x"]).cuda().requires_grad_(True)
+    t = torch.from_numpy(d["task"]).cuda().to(torch.int32)
+    g = torch.Generator().manual_seed(3)
+    y = m(x, t)
+    dout = torch.randn(y.shape, generator=g)
+    (y * dout.cuda()).sum().backward()
+    p = {k: torch.from_numpy(v).clone().requires_grad_(v.dtype.kind == "f" and "running" not in k and "pool" not in k)
+         for k, v in params_of(d).items()}
+    xc = torch.from_numpy(d["x"]).requires_grad_(True)
+    yc = otc.mode_conv(p, "", xc, torch.from_numpy(d["task"]), False)
+    (yc * dout).sum().backward()
+    assert_close(y.detach().cpu().numpy(), yc.detach().numpy(), 1e-4, "out")
+    assert_close(x.grad.cpu().numpy(), xc.grad.numpy(), 1e-4, "dx")
+    for k, q in m.named_parameters():
+        assert_close(q.grad.cpu().numpy(), p[k].grad.numpy(), 2e-4, k)
+
+
+def test_eval_chain_fp16_activations_match_fp32_activations():
+    """Eval + no_grad on the tensor-core path: BatchNorm + ReLU folded into K2's epilogue and fp16 activations handed from
+    layer to layer (one kernel per MoDEConv) == the same layers with fp32 activations in between, to fp16 rounding of the
+    activation (which the next conv's operand staging applies anyway)."""
+    from repmode_b200 import functional as Fm
+    from repmode_b200.nn_modules import MoDESubNet2Conv
+    torch.manual_seed(2)
+    stage = MoDESubNet2Conv(5, 12, 32, 64).cuda().eval()
+    for c in (stage.conv1, stage.conv2):
+        bn = c.subsequent_layer[0]
+        with torch.no_grad():
+            bn.running_mean.uniform_(-0.2, 0.2); bn.running_var.uniform_(0.5, 1.5)
+            bn.weight.uniform_(0.5, 1.5); bn.bias.uniform_(-0.5, 0.5)
+    x = torch.randn(2, 32, 6, 32, 16, device="cuda")
+    t = torch.tensor([4, 4], device="cuda")
+    with torch.no_grad():
+        a = stage(x, t)
+        assert a.dtype == torch.float16
+        old = Fm.EVAL_F16_ACT
+        Fm.EVAL_F16_ACT = False
+        try:
+            b = stage(x, t)
+        finally:
+            Fm.EVAL_F16_ACT = old
+        assert b.dtype == torch.float32
+    assert_close(a.float().cpu().numpy(), b.cpu().numpy(), 1e-3, "fp16 vs fp32 activations")

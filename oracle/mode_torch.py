@@ -87,28 +87,29 @@ def _bn_relu(p, prefix, y, training, update_running):
     return F.relu(y)
 
 
-def sub2conv(p, prefix, x, t, training):
-    x = mode_conv(p, prefix + "conv1.", x, t, training)
-    return mode_conv(p, prefix + "conv2.", x, t, training)
+def sub2conv(p, prefix, x, t, training, operand_f16=False):
+    x = mode_conv(p, prefix + "conv1.", x, t, training, operand_f16=operand_f16)
+    return mode_conv(p, prefix + "conv2.", x, t, training, operand_f16=operand_f16)
 
 
-def net_forward(p, x, task_ids, training):
-    """Net.forward (RepMode.py:51-71) over a reference-keyed state_dict p."""
+def net_forward(p, x, task_ids, training, operand_f16=False):
+    """Net.forward (RepMode.py:51-71) over a reference-keyed state_dict p.  operand_f16: every MoDEConv with the
+    tensor-core path's operand rounding (see mode_conv)."""
     skips = []
     for k in (1, 2, 3, 4):
         pre = f"encoder_block{k}."
-        s = sub2conv(p, pre + "conv_more.", x, task_ids, training)
+        s = sub2conv(p, pre + "conv_more.", x, task_ids, training, operand_f16)
         skips.append(s)
         x = F.conv3d(s, p[pre + "conv_down.0.weight"], stride=2)
         x = _bn_relu(p, pre + "conv_down.1.", x, training, False)
-    x = sub2conv(p, "bottle_block.", x, task_ids, training)
+    x = sub2conv(p, "bottle_block.", x, task_ids, training, operand_f16)
     for k in (4, 3, 2, 1):
         pre = f"decoder_block{k}."
         x = F.conv_transpose3d(x, p[pre + "convt.0.weight"], stride=2)
         x = _bn_relu(p, pre + "convt.1.", x, training, False)
         x = torch.cat((skips[k - 1], x), dim=1)
-        x = sub2conv(p, pre + "conv_less.", x, task_ids, training)
-    return mode_conv(p, "conv_out.", x, task_ids, training, conv_type="final")
+        x = sub2conv(p, pre + "conv_less.", x, task_ids, training, operand_f16)
+    return mode_conv(p, "conv_out.", x, task_ids, training, conv_type="final", operand_f16=operand_f16)
 
 
 def init_mode_conv_params(num_tasks, ci, co, generator=None, conv_type="normal", prefix=""):

@@ -82,6 +82,10 @@ struct PairParams {
     int32_t bounds[cp::MAX_CLUSTERS + 1];   // cluster c owns plane-units [bounds[c], bounds[c+1]) of (n, th2, tw, d)
     ConvExt ext;                 // haloed input (Dx, x_off) and fused epilogue (affine + ReLU, fp16 copy)
     int p_lo, p_hi;              // valid input planes in output-plane coordinates: [-x_off, Dx - x_off - 1]
+    // K > 32 runs as one RESIDENT-plan launch per 32-channel chunk: this launch reads input channels [x_chan0, x_chan0 + 32)
+    // and the weight chunk P.w points at, and (accum) adds its result to what the previous chunk's launch left in y
+    int x_chan0, accum;
+    long long w_u_stride;        // elements between the weight sets of two gate inputs (covers ALL chunks)
     int* error_flag;
     long long* prof;
     int flags;                   // debug: bit 1 = force the streaming plan even when K == 32
@@ -175,7 +179,7 @@ conv3d_pair_kernel(const __grid_constant__ CUtensorMap xmap, const PairParams P)
                         for (int i = 0; i < gn; ++i) {
                             if (!mbar_wait(plane_empty + 8 * slot, (use & 1) ^ 1)) { atomicExch(P.error_flag, 11); ok = false; break; }
                             mbar_expect_tx(plane_full + 8 * slot, cp::PLANE_BYTES);
-                            tma_load_5d(base + PL::PLANE_OFF + slot * cp::PLANE_BYTES, &xmap, plane_full + 8 * slot, c * 32,
+                            tma_load_5d(base + PL::PLANE_OFF + slot * cp::PLANE_BYTES, &xmap, plane_full + 8 * slot, c * 32 + P.x_chan0,
                                         w0 - 2, h0 + (int)rank * cp::TH - 2, gp + i + P.ext.x_off, n);
                             if (++slot == RING) { slot = 0; ++use; }
                         }
@@ -207,7 +211,7 @@ conv3d_pair_kernel(const __grid_constant__ CUtensorMap xmap, const PairParams P)
             uint32_t nreload = 0;
             while (ok && rw.next(n, h0, w0, da, db)) {
                 const int u = P.sample_u ? P.sample_u[n] : 0;
-                const __half* wu = P.w + (size_t)u * nchunk * 125 * P.Nout * 32;
+                const __half* wu = P.w + (size_t)u * P.w_u_stride;
                 if constexpr (RES) {
                     if (u != cur_u) {                          // (re)load all 25 stages; the previous sample's MMAs must be done
                         if (nreload > 0 && !mbar_wait(w_empty, (nreload - 1) & 1)) { atomicExch(P.error_flag, 12); break; }
@@ -463,6 +467,14 @@ conv3d_pair_kernel(const __grid_constant__ CUtensorMap xmap, const PairParams P)
                         }
 #pragma unroll
                         for (int j = 0; j < 32; ++j) f[j] *= scale;
+                        if (P.accum && row_ok) {                      // later K chunk: add to the earlier chunks' partial result
+                            const float* old = P.y + ((((size_t)n * P.D + q) * P.H + hh) * P.W + w0 + tw) * P.Nout + n0;
+#pragma unroll
+                            for (int j = 0; j < 32; j += 4) {
+                                const float4 o4 = *reinterpret_cast<const float4*>(old + j);
+                                f[j] += o4.x; f[j + 1] += o4.y; f[j + 2] += o4.z; f[j + 3] += o4.w;
+                            }
+                        }
                         if (has_ep) {
 #pragma unroll
                             for (int j = 0; j < 32; ++j) f[j] = fmaf(f[j], s_ep[j], s_ep[cp::NT + j]);
@@ -619,11 +631,13 @@ static void partition_runs(int64_t units, int D, int p_lo, int p_hi, int G, int3
 
 static int pair_clusters(int passes) { return std::max(1, std::min(cp::MAX_CLUSTERS, (sm_count() / 2) / passes)); }
 
-// Auto-selected when every cluster gets a long enough march (otherwise the single-CTA kernel's finer tiles win) and the
-// weights fit the RESIDENT plan (K == 32): the streaming plan re-reads every weight stage per 4 planes from L2 and is
-// slower than the single-CTA kernel today (measured 0.135 vs 0.086 ms on 64->64 @ 16x64x64).
+// Auto-selected when every cluster gets a long enough march (otherwise the single-CTA kernel's finer tiles win).  The
+// weights of ONE 32-channel chunk fit the RESIDENT plan; K > 32 runs as one resident launch per chunk, each later chunk
+// adding to y in the epilogue (the streaming plan re-reads every weight stage per 4 planes from L2 and measured slower
+// than the single-CTA kernel: 0.135 vs 0.086 ms on 64->64 @ 16x64x64).  REPMODE_PAIR_MAXK caps the chunked form (default 128).
 bool conv3d_pair_supported(int N, int D, int H, int W, int K, int Nout) {
-    if (!(K == 32 && Nout % 32 == 0 && Nout >= 32 && W % cp::TW == 0)) return false;
+    static const int maxk = getenv("REPMODE_PAIR_MAXK") ? atoi(getenv("REPMODE_PAIR_MAXK")) : 128;
+    if (!(K % 32 == 0 && K >= 32 && K <= std::max(32, maxk) && Nout % 32 == 0 && Nout >= 32 && W % cp::TW == 0)) return false;
     const int64_t units = (int64_t)N * ceil_div(H, 2 * cp::TH) * (W / cp::TW) * D;
     if (units > 0x7fffffff) return false;
     return units >= (int64_t)12 * pair_clusters(Nout / cp::NT);
@@ -660,10 +674,32 @@ int conv3d_pair(const __half* x, const __half* w, const int32_t* sample_u, float
     if (make_act_map(&xmap, x, N, ext.Dx, H, W, K, cp::BW, cp::BH, 1) != 0) return -1;
     static_assert(cp::Plan<true>::TOTAL + 1024 <= 227 * 1024 && cp::Plan<false>::TOTAL + 1024 <= 227 * 1024,
                   "shared memory budget");
-    if (K == 32 && !(P.flags & 2)) {
+    P.x_chan0 = 0; P.accum = 0;
+    P.w_u_stride = (long long)(K / 32) * 125 * Nout * 32;
+    if (!(P.flags & 2)) {
+        // RESIDENT plan, one launch per 32-channel chunk of K; statistics, affine epilogue, fp16 copy and the stats
+        // broadcast belong to the LAST chunk's launch (the only one that sees the complete sum)
+        const int nchunks = K / 32;
+        if (nchunks > 1 && y == nullptr) MODE_FAIL("conv3d_pair: K > 32 needs the fp32 output buffer (chunk accumulation)");
         const int smem_bytes = (int)cp::Plan<true>::TOTAL + 1024;
         MODE_CUDA(cudaFuncSetAttribute(conv3d_pair_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
-        conv3d_pair_kernel<true><<<dim3(2 * G, passes), cp::THREADS, smem_bytes, st>>>(xmap, P);
+        PairParams Q = P;
+        Q.K = 32;
+        for (int c = 0; c < nchunks; ++c) {
+            const bool last = c == nchunks - 1;
+            Q.x_chan0 = c * 32;
+            Q.w = w + (size_t)c * 125 * Nout * 32;
+            Q.accum = c > 0;
+            Q.bn_sums = last ? bn_sums : nullptr;
+            Q.ext = ext;
+            if (!last) {
+                Q.ext.ep_scale = nullptr; Q.ext.ep_shift = nullptr; Q.ext.relu = 0; Q.ext.y16 = nullptr; Q.ext.push.n = 0;
+                Q.out_scale = out_scale; Q.out_scale_dev = out_scale_dev;
+            }
+            conv3d_pair_kernel<true><<<dim3(2 * G, passes), cp::THREADS, smem_bytes, st>>>(xmap, Q);
+            MODE_LAUNCH_CHECK();
+        }
+        return 0;
     } else {
         const int smem_bytes = (int)cp::Plan<false>::TOTAL + 1024;
         MODE_CUDA(cudaFuncSetAttribute(conv3d_pair_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));

@@ -113,8 +113,8 @@ __global__ void __launch_bounds__(256) conv3d_simt_kernel(const float* __restric
             for (int j = 0; j < 8; ++j) {
                 if (c0 + j < Nout) {
                     float v = acc[j] * out_scale;
-                    if (ext.ep_scale) v *= ext.ep_scale[c0 + j];
-                    if (ext.ep_shift) v += ext.ep_shift[c0 + j];
+                    if (ext.ep_scale || ext.ep_shift)          // one fma, like the tensor-core epilogues and bn_apply
+                        v = fmaf(v, ext.ep_scale ? ext.ep_scale[c0 + j] : 1.f, ext.ep_shift ? ext.ep_shift[c0 + j] : 0.f);
                     if (ext.relu) v = fmaxf(v, 0.f);
                     if (dst) dst[j] = v;
                     if (d16) d16[j] = __float2half_rn(fminf(fmaxf(v * ext.y16_scale, -65504.f), 65504.f));

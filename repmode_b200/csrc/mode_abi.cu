@@ -154,7 +154,8 @@ extern "C" int mode_conv3d_ex(const void* x, mode_dtype_t x_dtype, const void* w
             MODE_FAIL("mode_conv3d: shape D=%d H=%d W=%d K=%d Nout=%d not supported by the tcgen05 path", D, H, W, K, Nout);
         static const bool no_pair = getenv("REPMODE_DISABLE_PAIR") != nullptr;
         // 2: CTA-pair kernel when every cluster gets a long enough march, else the single-CTA kernel; 3 / 4 force one
-        if (impl == 4 || (impl == 2 && !no_pair && conv3d_pair_supported(N, D, H, W, K, Nout)))
+        // (K > 32 on the pair kernel accumulates chunk by chunk in the fp32 output: not available for an fp16-only result)
+        if (impl == 4 || (impl == 2 && !no_pair && (K == 32 || y != nullptr) && conv3d_pair_supported(N, D, H, W, K, Nout)))
             return conv3d_pair((const __half*)x, (const __half*)w, sample_u, y, N, D, H, W, K, Nout, out_scale, out_scale_dev, bn_sums, stat_d_lo, stat_d_hi, ext, st);
         return conv3d_umma((const __half*)x, (const __half*)w, sample_u, y, N, D, H, W, K, Nout, out_scale, out_scale_dev, bn_sums, stat_d_lo, stat_d_hi, ext, st);
     }

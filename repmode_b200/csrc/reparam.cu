@@ -121,6 +121,17 @@ __global__ void __launch_bounds__(256) reparam_fwd_kernel(mode_layer_t L, const 
     }
 }
 
+// Offset of tap `tap` inside the pack of ONE gate input for K chunk `chunk`, row 0, column 0 (the row / column part and
+// the gate-input stride are added by the caller): pack_index = u * pack_u_stride + pack_tap_offset + row * 32 + pack_col.
+template <typename T> __device__ __forceinline__ int pack_tap_offset(int tap, int chunk, int nchunk, int nrows);
+template <> __device__ __forceinline__ int pack_tap_offset<float>(int tap, int chunk, int nchunk, int nrows) {
+    return (tap * nchunk + chunk) * nrows * MODE_KC;
+}
+template <> __device__ __forceinline__ int pack_tap_offset<__half>(int tap, int chunk, int nchunk, int nrows) {
+    const int kd = tap / 25, t = tap - kd * 25;
+    return ((chunk * 25 + t) * 5 + (4 - kd)) * nrows * MODE_KC;
+}
+
 // K1, row-block form (the default whenever Ci % 32 == 0 and Co % K1R_ROWS == 0): one block owns K1R_ROWS output channels x
 // one 32-channel chunk x ALL 125 taps and loops over the U gate inputs, so the experts are read from HBM exactly ONCE per
 // step however many distinct tasks the batch holds.  Why this shape (r2a: reparam_fwd_kernel above reaches 1.14 TB/s = 17 %
@@ -132,8 +143,9 @@ __global__ void __launch_bounds__(256) reparam_fwd_kernel(mode_layer_t L, const 
 // reparam_fwd_kernel: bit-identical W_eff.
 // grid (Co / K1R_ROWS, Ci / 32), block 256.
 constexpr int K1R_ROWS = 2;
+constexpr int K1R_MAXU = 32;          // gate inputs per launch the row-block kernel takes (more -> the per-slice kernel)
 template <typename OutT>
-__global__ void __launch_bounds__(256) reparam_fwd_rows_kernel(mode_layer_t L, const int32_t* __restrict__ task_ids,
+__global__ void __launch_bounds__(256, 4) reparam_fwd_rows_kernel(mode_layer_t L, const int32_t* __restrict__ task_ids,
                                                                const float* __restrict__ t_dense, int U,
                                                                float* __restrict__ g_out, OutT* __restrict__ w_fwd,
                                                                float w_scale, const float* __restrict__ w_scale_dev,
@@ -141,11 +153,23 @@ __global__ void __launch_bounds__(256) reparam_fwd_rows_kernel(mode_layer_t L, c
     __shared__ __align__(16) float s5[K1R_ROWS * 32 * 125];
     __shared__ __align__(16) float s3[K1R_ROWS * 32 * 27];
     __shared__ __align__(16) float s1[3 * K1R_ROWS * 32];     // k1, a3, a5
-    __shared__ float sg[K1R_ROWS * MODE_NUM_EXPERTS];
+    __shared__ float sg[K1R_MAXU * K1R_ROWS * MODE_NUM_EXPERTS];
+    __shared__ int s_tapoff[125];          // per tap: offset inside one gate input's pack (row 0, column 0)
+    __shared__ int s_t3[125];              // per tap: index into the 3^3 expert, -1 outside the inner 3^3
     const int o0 = blockIdx.x * K1R_ROWS, ic = blockIdx.y;
     const int Ci = L.ci, Co = L.co, T = L.num_tasks;
     const int tid = threadIdx.x;
-    // ---- load phase: contiguous slabs, 16-byte loads, all issued before the first use
+    // r2l ncu (512 -> 512): issue slots 76 % busy, DRAM 23 % -- the mix loop was INSTRUCTION bound (tap -> kd/kh/kw divisions
+    // and 64-bit pack addressing per element).  Everything that depends on the tap alone is tabulated once per block.
+    if (tid < 125) {
+        const int kd = tid / 25, kh = (tid / 5) % 5, kw = tid % 5;
+        const bool inner = (kd >= 1 && kd <= 3 && kh >= 1 && kh <= 3 && kw >= 1 && kw <= 3);
+        s_t3[tid] = inner ? ((kd - 1) * 3 + (kh - 1)) * 3 + (kw - 1) : -1;
+        s_tapoff[tid] = pack_tap_offset<OutT>(tid, ic, gridDim.y, rows_pad);
+    }
+    // ---- load phase: contiguous slabs, 16-byte loads, all issued before the first use; the gate softmax of every
+    // (gate input, row) runs on the threads at the END of the block while those loads are in flight (its dependent global
+    // loads -- task id, then gate column -- would otherwise add ~1.5 us of two-thread latency to every block)
     {
         constexpr int V5 = 32 * 125 / 4, V3 = 32 * 27 / 4;     // float4 per row slab: 1000, 216
         float4 r5[K1R_ROWS][4], r3[K1R_ROWS];
@@ -165,23 +189,10 @@ __global__ void __launch_bounds__(256) reparam_fwd_rows_kernel(mode_layer_t L, c
             const float* src = which == 0 ? L.k1 : (which == 1 ? L.a3 : L.a5);
             v1 = src[(size_t)(o0 + r) * Ci + (size_t)ic * 32 + i];
         }
-#pragma unroll
-        for (int r = 0; r < K1R_ROWS; ++r) {
-#pragma unroll
-            for (int k = 0; k < 4; ++k)
-                if (tid + 256 * k < V5) reinterpret_cast<float4*>(s5 + r * 32 * 125)[tid + 256 * k] = r5[r][k];
-            if (tid < V3) reinterpret_cast<float4*>(s3 + r * 32 * 27)[tid] = r3[r];
-        }
-        if (tid < 3 * K1R_ROWS * 32) s1[tid] = v1;
-    }
-    if (w_scale_dev != nullptr) w_scale *= *w_scale_dev;
-    const float c3 = 1.0f / 27, c5 = 1.0f / 125;               // fp32-rounded pool constants (RepMode.py:161-163)
-    const int nci = gridDim.y;
-    for (int u = 0; u < U; ++u) {
-        __syncthreads();                                       // slabs landed (u = 0) / previous sg consumed (u > 0)
-        // gate column + bias -> softmax over the 5 experts, one thread per output channel (RepMode.py:198-200)
-        if (tid < K1R_ROWS) {
-            const int o = o0 + tid;
+        // gate column + bias -> softmax over the 5 experts, one thread per (gate input, output channel) (RepMode.py:198-200)
+        const int gt = 255 - tid;
+        if (gt < U * K1R_ROWS) {
+            const int u = gt / K1R_ROWS, r = gt % K1R_ROWS, o = o0 + r;
             float lg[MODE_NUM_EXPERTS];
             for (int e = 0; e < MODE_NUM_EXPERTS; ++e) {
                 const int row = e * Co + o;
@@ -199,28 +210,54 @@ __global__ void __launch_bounds__(256) reparam_fwd_rows_kernel(mode_layer_t L, c
             for (int e = 0; e < MODE_NUM_EXPERTS; ++e) { ex[e] = expf(lg[e] - m); ssum += ex[e]; }
             for (int e = 0; e < MODE_NUM_EXPERTS; ++e) {
                 const float gv = ex[e] / ssum;
-                sg[tid * MODE_NUM_EXPERTS + e] = gv;
+                sg[(u * K1R_ROWS + r) * MODE_NUM_EXPERTS + e] = gv;
                 if (ic == 0 && g_out != nullptr) g_out[((size_t)u * MODE_NUM_EXPERTS + e) * Co + o] = gv;
             }
         }
-        __syncthreads();
-        // mix + pack: thread -> (tap, row, column); K1R_ROWS rows x 32 columns of one (chunk, tap) are one contiguous run
-        for (int idx = tid; idx < 125 * K1R_ROWS * 32; idx += 256) {
-            const int col = idx & 31, r = (idx >> 5) % K1R_ROWS, tap = idx / (32 * K1R_ROWS);
-            const float* g = sg + r * MODE_NUM_EXPERTS;
-            const int kd = tap / 25, kh = (tap / 5) % 5, kw = tap % 5;
-            const bool inner = (kd >= 1 && kd <= 3 && kh >= 1 && kh <= 3 && kw >= 1 && kw <= 3);
-            const float t0 = __fmul_rn(s5[(r * 32 + col) * 125 + tap], g[0]);
-            float t1 = 0.f, t2 = 0.f, t3 = 0.f;
-            if (inner) {
-                t1 = __fmul_rn(s3[(r * 32 + col) * 27 + ((kd - 1) * 3 + (kh - 1)) * 3 + (kw - 1)], g[1]);
-                t3 = __fmul_rn(__fmul_rn(s1[(1 * K1R_ROWS + r) * 32 + col], c3), g[3]);
+#pragma unroll
+        for (int r = 0; r < K1R_ROWS; ++r) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+                if (tid + 256 * k < V5) reinterpret_cast<float4*>(s5 + r * 32 * 125)[tid + 256 * k] = r5[r][k];
+            if (tid < V3) reinterpret_cast<float4*>(s3 + r * 32 * 27)[tid] = r3[r];
+        }
+        if (tid < 3 * K1R_ROWS * 32) s1[tid] = v1;
+    }
+    if (w_scale_dev != nullptr) w_scale *= *w_scale_dev;
+    const float c3 = 1.0f / 27, c5 = 1.0f / 125;               // fp32-rounded pool constants (RepMode.py:161-163)
+    const int nci = gridDim.y;
+    __syncthreads();                                           // slabs and gates landed
+    for (int u = 0; u < U; ++u) {
+        // mix + pack: a warp owns whole taps (tap = warp, warp + 8, ...), its lanes the 32 columns; the shared-memory reads
+        // walk a column at an odd stride (conflict free) and each store instruction writes one whole 64-byte (fp16) /
+        // 128-byte (fp32) pack row
+        const int warp = tid >> 5, lane = tid & 31;
+        OutT* wu = w_fwd + (size_t)u * 125 * nci * rows_pad * MODE_KC;
+#pragma unroll
+        for (int r = 0; r < K1R_ROWS; ++r) {
+            const float* g = sg + (u * K1R_ROWS + r) * MODE_NUM_EXPERTS;
+            const float g0 = g[0], g1 = g[1];
+            // per-column constants of this row: 1^3 expert (centre tap only), avg3 (inner taps), avg5 (every tap)
+            const float t2c = __fmul_rn(s1[(0 * K1R_ROWS + r) * 32 + lane], g[2]);
+            const float t3c = __fmul_rn(__fmul_rn(s1[(1 * K1R_ROWS + r) * 32 + lane], c3), g[3]);
+            const float t4c = __fmul_rn(__fmul_rn(s1[(2 * K1R_ROWS + r) * 32 + lane], c5), g[4]);
+            const float* k5c = s5 + (r * 32 + lane) * 125;
+            const float* k3c = s3 + (r * 32 + lane) * 27;
+            OutT* wrow = wu + (o0 + r) * MODE_KC + pack_col<OutT>(o0 + r, lane);
+#pragma unroll 4
+            for (int tap = warp; tap < 125; tap += 8) {
+                const int t3i = s_t3[tap];
+                const float t0 = __fmul_rn(k5c[tap], g0);
+                float t1 = 0.f, t2 = 0.f, t3 = 0.f;
+                if (t3i >= 0) {
+                    t1 = __fmul_rn(k3c[t3i], g1);
+                    t3 = t3c;
+                }
+                if (tap == 62) t2 = t2c;
+                // reference association order: ((((e5 + e3) + e1) + ea3) + ea5)   (RepMode.py:184-188)
+                const float val = __fadd_rn(__fadd_rn(__fadd_rn(__fadd_rn(t0, t1), t2), t3), t4c);
+                store_w(wrow + s_tapoff[tap], val * w_scale);
             }
-            if (tap == 62) t2 = __fmul_rn(s1[(0 * K1R_ROWS + r) * 32 + col], g[2]);
-            const float t4 = __fmul_rn(__fmul_rn(s1[(2 * K1R_ROWS + r) * 32 + col], c5), g[4]);
-            // reference association order: ((((e5 + e3) + e1) + ea3) + ea5)   (RepMode.py:184-188)
-            const float val = __fadd_rn(__fadd_rn(__fadd_rn(__fadd_rn(t0, t1), t2), t3), t4);
-            store_w(w_fwd + pack_index<OutT>(u, tap, ic, nci, o0 + r, rows_pad, col), val * w_scale);
         }
     }
 }
@@ -372,6 +409,162 @@ __global__ void __launch_bounds__(128) reparam_bwd_kernel(mode_layer_t L, const 
     }
 }
 
+// K1b, slab form (default): same arithmetic as reparam_bwd_kernel, restructured for occupancy and coalescing.  r2k: the
+// kernel above needs 186 registers (32 loads in flight + 32 accumulators per thread) -> 2 blocks of 128 threads per SM and
+// 1.1 TB/s = 17 % of HBM on 512 -> 512.  Here a block of 256 threads owns one (o, 32-channel chunk): the d_weff slab of a
+// sample (125 segments of 128 bytes) goes through shared memory with four 16-byte loads per thread, the expert slabs with
+// five; every thread then owns 16 fixed (ci, tap) entries of dk5 (a contiguous 16 000-byte run of the output) and 4 of dk3,
+// so the gradients leave in coalesced runs and the per-thread state is ~20 accumulators: <= 85 registers, 3 blocks per SM.
+// grid (ceil(Ci/32), Co), block 256.
+constexpr int K1B_DW_STRIDE = 33;     // floats per tap row of the staged d_weff slab (odd: the transposing reads are conflict free)
+__global__ void __launch_bounds__(256, 3) reparam_bwd_slab_kernel(mode_layer_t L, const int32_t* __restrict__ sample_u,
+                                                                  int n_samples, const float* __restrict__ g,
+                                                                  const float* __restrict__ d_weff,
+                                                                  float* __restrict__ dk5, float* __restrict__ dk3,
+                                                                  float* __restrict__ dk1, float* __restrict__ da3,
+                                                                  float* __restrict__ da5, float* __restrict__ dg_part) {
+    __shared__ float sk5[32 * 125];
+    __shared__ float sk3[32 * 27];
+    __shared__ float sdw[125 * K1B_DW_STRIDE];
+    __shared__ float s_col[2][8][32];        // per-warp column sums: all taps / inner taps
+    __shared__ float s_q[2][8];
+    const int ic = blockIdx.x, o = blockIdx.y;
+    const int Ci = L.ci, Co = L.co;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int nlive = min(32, Ci - ic * 32);
+    const float c3 = 1.0f / 27, c5 = 1.0f / 125;
+    const size_t oc0 = (size_t)o * Ci + (size_t)ic * 32;
+    // stage this (o, ci-block)'s experts: contiguous slabs (zeros beyond the live channels)
+    for (int idx = tid; idx < 32 * 125; idx += 256) sk5[idx] = idx < nlive * 125 ? L.k5[oc0 * 125 + idx] : 0.f;
+    for (int idx = tid; idx < 32 * 27; idx += 256) sk3[idx] = idx < nlive * 27 ? L.k3[oc0 * 27 + idx] : 0.f;
+    const bool colthr = tid < 32;
+    const bool live = colthr && lane < nlive;
+    const float k1v = live ? L.k1[oc0 + lane] : 0.f;
+    const float a3v = live ? L.a3[oc0 + lane] * c3 : 0.f;
+    const float a5v = live ? L.a5[oc0 + lane] * c5 : 0.f;
+    float acc5[16], acc3[4];
+#pragma unroll
+    for (int k = 0; k < 16; ++k) acc5[k] = 0.f;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) acc3[k] = 0.f;
+    float acc_k1 = 0.f, acc_a3 = 0.f, acc_a5 = 0.f;
+    const bool vec_ok = (Ci & 3) == 0 && nlive == 32 && (reinterpret_cast<uintptr_t>(d_weff) & 15) == 0;
+
+    for (int n = 0; n < n_samples; ++n) {
+        const int u = sample_u[n];
+        const float* gu = g + (size_t)u * MODE_NUM_EXPERTS * Co + o;
+        const float g0 = gu[0], g1 = gu[Co], g2 = gu[2 * Co], g3 = gu[3 * Co], g4 = gu[4 * Co];
+        const float* dw = d_weff + ((size_t)n * 125 * Co + o) * Ci + (size_t)ic * 32;
+        __syncthreads();                                   // experts staged (n = 0) / previous slab consumed
+        if (vec_ok) {
+            float4 v[4];
+#pragma unroll
+            for (int p = 0; p < 4; ++p) {
+                const int tap = (tid >> 3) + 32 * p;
+                if (tap < 125) v[p] = *reinterpret_cast<const float4*>(dw + (size_t)tap * Co * Ci + (tid & 7) * 4);
+            }
+#pragma unroll
+            for (int p = 0; p < 4; ++p) {
+                const int tap = (tid >> 3) + 32 * p;
+                if (tap < 125) {
+                    float* d = sdw + tap * K1B_DW_STRIDE + (tid & 7) * 4;
+                    d[0] = v[p].x; d[1] = v[p].y; d[2] = v[p].z; d[3] = v[p].w;
+                }
+            }
+        } else {
+            for (int idx = tid; idx < 125 * 32; idx += 256) {
+                const int tap = idx >> 5, ci = idx & 31;
+                sdw[tap * K1B_DW_STRIDE + ci] = ci < nlive ? dw[(size_t)tap * Co * Ci + ci] : 0.f;
+            }
+        }
+        __syncthreads();
+        float q0 = 0.f, q1 = 0.f;
+#pragma unroll
+        for (int k = 0; k < 16; ++k) {
+            const int idx = tid + 256 * k;
+            if (idx < 32 * 125) {
+                const int ci = idx / 125, tap = idx - ci * 125;
+                const float v = sdw[tap * K1B_DW_STRIDE + ci];
+                acc5[k] = fmaf(g0, v, acc5[k]);
+                q0 = fmaf(sk5[idx], v, q0);
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int idx = tid + 256 * k;
+            if (idx < 32 * 27) {
+                const int ci = idx / 27, t3 = idx - ci * 27;
+                const int tap = (t3 / 9 + 1) * 25 + ((t3 / 3) % 3 + 1) * 5 + (t3 % 3) + 1;
+                const float v = sdw[tap * K1B_DW_STRIDE + ci];
+                acc3[k] = fmaf(g1, v, acc3[k]);
+                q1 = fmaf(sk3[idx], v, q1);
+            }
+        }
+        // column sums over the taps (all / inner): warp w takes taps w, w + 8, ...; lane = ci
+        float p_all = 0.f, p_inner = 0.f;
+        for (int tap = warp; tap < 125; tap += 8) {
+            const float v = sdw[tap * K1B_DW_STRIDE + lane];
+            const int kd = tap / 25, kh = (tap / 5) % 5, kw = tap % 5;
+            p_all += v;
+            if (kd >= 1 && kd <= 3 && kh >= 1 && kh <= 3 && kw >= 1 && kw <= 3) p_inner += v;
+        }
+        s_col[0][warp][lane] = p_all;
+        s_col[1][warp][lane] = p_inner;
+#pragma unroll
+        for (int sft = 16; sft > 0; sft >>= 1) {
+            q0 += __shfl_xor_sync(0xffffffffu, q0, sft);
+            q1 += __shfl_xor_sync(0xffffffffu, q1, sft);
+        }
+        if (lane == 0) { s_q[0][warp] = q0; s_q[1][warp] = q1; }
+        __syncthreads();
+        if (colthr) {
+            float A = 0.f, I = 0.f;
+#pragma unroll
+            for (int w = 0; w < 8; ++w) { A += s_col[0][w][lane]; I += s_col[1][w][lane]; }
+            const float Cn = sdw[62 * K1B_DW_STRIDE + lane];
+            acc_k1 = fmaf(g2, Cn, acc_k1);
+            acc_a3 = fmaf(g3, I * c3, acc_a3);
+            acc_a5 = fmaf(g4, A * c5, acc_a5);
+            float d2 = k1v * Cn, d3 = a3v * I, d4 = a5v * A;
+#pragma unroll
+            for (int sft = 16; sft > 0; sft >>= 1) {
+                d2 += __shfl_xor_sync(0xffffffffu, d2, sft);
+                d3 += __shfl_xor_sync(0xffffffffu, d3, sft);
+                d4 += __shfl_xor_sync(0xffffffffu, d4, sft);
+            }
+            if (lane == 0) {
+                float t0 = 0.f, t1 = 0.f;
+#pragma unroll
+                for (int w = 0; w < 8; ++w) { t0 += s_q[0][w]; t1 += s_q[1][w]; }
+                float* dst = dg_part + (((size_t)ic * n_samples + n) * MODE_NUM_EXPERTS) * Co + o;
+                dst[0] = t0;
+                dst[Co] = t1;
+                dst[2 * Co] = d2;
+                dst[3 * Co] = d3;
+                dst[4 * Co] = d4;
+            }
+        }
+    }
+    // expert gradients leave in contiguous runs
+    float* dst5 = dk5 + oc0 * 125;
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+        const int idx = tid + 256 * k;
+        if (idx < nlive * 125) dst5[idx] = acc5[k];
+    }
+    float* dst3 = dk3 + oc0 * 27;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const int idx = tid + 256 * k;
+        if (idx < nlive * 27) dst3[idx] = acc3[k];
+    }
+    if (live) {
+        dk1[oc0 + lane] = acc_k1;
+        da3[oc0 + lane] = acc_a3;
+        da5[oc0 + lane] = acc_a5;
+    }
+}
+
 // softmax + Linear backward; one thread per output channel o, samples in order -> deterministic.
 __global__ void gate_bwd_kernel(mode_layer_t L, const int32_t* __restrict__ task_ids,
                                 const float* __restrict__ t_dense, const int32_t* __restrict__ sample_u,
@@ -435,7 +628,7 @@ extern "C" int mode_reparam_fwd(const mode_layer_t* L, const int32_t* task_ids, 
     // per-(row, kd slice) kernel (read per call so that a test can A/B both)
     const char* rows_env = getenv("REPMODE_K1_ROWS");
     const bool rows_on = !(rows_env != nullptr && rows_env[0] == '0');
-    const bool rows = rows_on && L->ci % 32 == 0 && L->co % K1R_ROWS == 0 &&
+    const bool rows = rows_on && U <= K1R_MAXU && L->ci % 32 == 0 && L->co % K1R_ROWS == 0 &&
                       ((reinterpret_cast<uintptr_t>(L->k5) | reinterpret_cast<uintptr_t>(L->k3)) & 15) == 0;
     const dim3 rgrid(L->co / K1R_ROWS, nci);
     if (w_dtype == MODE_F32) {
@@ -486,8 +679,13 @@ extern "C" int mode_reparam_bwd(const mode_layer_t* L, const int32_t* task_ids, 
     (void)U;
     cudaStream_t st = (cudaStream_t)stream;
     const int nci = (int)ceil_div(L->ci, 32);
-    reparam_bwd_kernel<<<dim3(nci, L->co), 128, 0, st>>>(*L, sample_u, n_samples, g, d_weff, dk5, dk3, dk1, da3, da5,
-                                                        (float*)workspace);
+    static const bool legacy = getenv("REPMODE_K1B_LEGACY") != nullptr;       // A/B arm: the round-1 kernel
+    if (legacy)
+        reparam_bwd_kernel<<<dim3(nci, L->co), 128, 0, st>>>(*L, sample_u, n_samples, g, d_weff, dk5, dk3, dk1, da3, da5,
+                                                            (float*)workspace);
+    else
+        reparam_bwd_slab_kernel<<<dim3(nci, L->co), 256, 0, st>>>(*L, sample_u, n_samples, g, d_weff, dk5, dk3, dk1, da3,
+                                                                  da5, (float*)workspace);
     MODE_LAUNCH_CHECK();
     gate_bwd_kernel<<<(unsigned)ceil_div(L->co, 128), 128, 0, st>>>(*L, task_ids, t_dense, sample_u, n_samples, nci, g,
                                                                   (const float*)workspace, dgate_w, dgate_b);

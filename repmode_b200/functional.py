@@ -8,6 +8,7 @@ hand-written sm_100a kernels.  There is no CPU / eager fallback: a non-CUDA tens
 import ctypes
 import functools
 import os
+import weakref
 
 import torch
 
@@ -487,13 +488,35 @@ EVAL_F16_ACT = os.environ.get("REPMODE_EVAL_F16_ACT", "1") == "1"    # eval: 'no
 EVAL_GRAPH = os.environ.get("REPMODE_EVAL_GRAPH", "1") == "1"        # eval: repeated Net forwards replay one CUDA graph
 
 
-def bn_eval_affine(bn):
-    """(scale, shift) of a frozen BatchNorm: y * scale + shift == (y - running_mean) / sqrt(running_var + eps) * w + b."""
+_AFFINE_CACHE = {}     # id(BatchNorm weight Parameter) -> (weakref to it, {versions + extra: value})
+
+
+def bn_eval_affine(bn, extra=None):
+    """(scale, shift) of a frozen BatchNorm: y * scale + shift == (y - running_mean) / sqrt(running_var + eps) * w + b.
+    Cached per BatchNorm (keyed on the weight Parameter OBJECT -- storage addresses get recycled between modules -- plus
+    the version counters of its four tensors): an eval forward of the U-Net would otherwise spend ~130 tiny elementwise
+    launches on these 26 vector pairs.  `extra` = (key, fn): also cache fn(scale, shift) (the stride-2 layers fold the pair
+    into their GEMM weights)."""
     bn_w, bn_b, rm, rv = bn[:4]
     eps = bn[4] if len(bn) > 4 else BN_EPS
-    scale = (bn_w * torch.rsqrt(rv + eps)).contiguous()
-    shift = (bn_b - rm * scale).contiguous()
-    return scale, shift
+    ent = _AFFINE_CACHE.get(id(bn_w))
+    if ent is None or ent[0]() is not bn_w:
+        wid = id(bn_w)
+        ent = _AFFINE_CACHE[wid] = (weakref.ref(bn_w, lambda _r, wid=wid: _AFFINE_CACHE.pop(wid, None)), {})
+    per_bn = ent[1]
+    key = (float(eps),) + tuple((t.data_ptr(), t._version) for t in (bn_w, bn_b, rm, rv))
+    if extra is not None:
+        key = key + (extra[0],)
+    hit = per_bn.get(key)
+    if hit is None:
+        if len(per_bn) > 8:
+            per_bn.clear()
+        with torch.no_grad():
+            scale = (bn_w * torch.rsqrt(rv + eps)).contiguous()
+            shift = (bn_b - rm * scale).contiguous()
+            hit = (scale, shift) if extra is None else extra[1](scale, shift)
+        per_bn[key] = hit
+    return hit
 
 
 def mode_conv_eval(x, task_ids, params, bn, conv_type, precision, cache):
@@ -525,14 +548,14 @@ def mode_conv_eval(x, task_ids, params, bn, conv_type, precision, cache):
     normal = conv_type == "normal"
     ep = None
     if normal:
-        scale, shift = bn_eval_affine(bn)
-        if co_p != co:
-            scale, shift = pad_channels(scale, co_p), pad_channels(shift, co_p)
+        scale, shift = bn_eval_affine(bn, (("pad", co_p), lambda sc, sh: (pad_channels(sc, co_p), pad_channels(sh, co_p))))
         ep = (scale, shift, True)
     if use_umma and normal and EVAL_F16_ACT:
         y16 = torch.empty((n, d, h, wd, co_p), dtype=torch.float16, device=x.device)
+        # K > 32: the CTA-pair kernel accumulates the 32-channel chunks in an fp32 buffer (scratch here)
+        scratch = torch.empty((n, d, h, wd, co_p), dtype=torch.float32, device=x.device) if ci_p > 32 else None
         conv3d(x_op, dtype, w_all, sample_u, n, d, h, wd, ci_p, co_p, None, None, out_scale=1.0 / w_scale, ep=ep,
-               y16=(y16, 0, 1.0), want_y=False)
+               y16=(y16, 0, 1.0), want_y=False, out=scratch)
         y = y16 if co_p == co else y16[..., :co].contiguous()
     else:
         y = conv3d(x_op, dtype, w_all, sample_u, n, d, h, wd, ci_p, co_p, None, None, out_scale=1.0 / w_scale, ep=ep)
@@ -636,8 +659,10 @@ def down_conv_bn_relu(x, conv_w, bn, training, shard=None):
     if not training and not torch.is_grad_enabled():
         # eval: frozen BatchNorm folded into the GEMM (scale into the weight columns, shift as the bias), ReLU in place;
         # the activation keeps its dtype (fp16 on the tensor-core eval path)
-        scale, shift = bn_eval_affine((bn.weight, bn.bias, bn.running_mean, bn.running_var, bn.eps))
-        y = torch.addmm(shift.to(x8.dtype), x8, (wm * scale).to(x8.dtype)).relu_()
+        wf, sh = bn_eval_affine((bn.weight, bn.bias, bn.running_mean, bn.running_var, bn.eps),
+                                (("down", conv_w.data_ptr(), conv_w._version, x8.dtype),
+                                 lambda sc, shf: ((wm * sc).to(x8.dtype).contiguous(), shf.to(x8.dtype))))
+        y = torch.addmm(sh, x8, wf).relu_()
         return y.view(n, d // 2, h // 2, w // 2, co).permute(0, 4, 1, 2, 3)
     y = (x8 @ wm.to(x8.dtype)).view(n, d // 2, h // 2, w // 2, co)
     out = BnReluFunction.apply(y, bn.weight, bn.bias, bn.running_mean, bn.running_var, training, shard, bn.eps,
@@ -653,9 +678,11 @@ def up_conv_bn_relu(x, convt_w, bn, training, shard=None):
     co = convt_w.shape[1]
     wm = convt_w.permute(0, 2, 3, 4, 1).reshape(c, 8 * co)                    # [ci, (kd,kh,kw,co)]
     if not training and not torch.is_grad_enabled():
-        scale, shift = bn_eval_affine((bn.weight, bn.bias, bn.running_mean, bn.running_var, bn.eps))
-        wf = (wm.view(c, 8, co) * scale).reshape(c, 8 * co).to(xn.dtype)
-        y8 = torch.addmm(shift.repeat(8).to(xn.dtype), xn.reshape(-1, c), wf).relu_().view(n, d, h, w, 2, 2, 2, co)
+        wf, sh8 = bn_eval_affine((bn.weight, bn.bias, bn.running_mean, bn.running_var, bn.eps),
+                                 (("up", convt_w.data_ptr(), convt_w._version, xn.dtype),
+                                  lambda sc, shf: ((wm.view(c, 8, co) * sc).reshape(c, 8 * co).to(xn.dtype).contiguous(),
+                                                   shf.repeat(8).to(xn.dtype))))
+        y8 = torch.addmm(sh8, xn.reshape(-1, c), wf).relu_().view(n, d, h, w, 2, 2, 2, co)
         y = y8.permute(0, 1, 4, 2, 5, 3, 6, 7).reshape(n, 2 * d, 2 * h, 2 * w, co)
         return y.permute(0, 4, 1, 2, 3)
     y8 = (xn.reshape(-1, c) @ wm.to(xn.dtype)).view(n, d, h, w, 2, 2, 2, co)

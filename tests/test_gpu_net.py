@@ -88,3 +88,51 @@ def test_full_width_net_train_step_runs():
         opt.step()
         losses.append(float(loss))
     assert losses[-1] < losses[0]
+
+
+def test_full_width_train_step_gradients_vs_oracle():
+    """BASELINE.json config 3 in small: one full-width (mult_chan = 32, all 19 MoDEConv shapes) train-mode forward + backward
+    on the tensor-core path against the oracle run with the SAME operand rounding (fp16 conv operands, fp32 accumulate):
+    the loss, the prediction, and the gradients of a handful of parameters of every U-Net level.  Train-mode BatchNorm +
+    ReLU make individual gradient entries chaotic in the last bits (one ReLU-mask flip moves a sum by a whole |dout|), so
+    gradients are judged by direction and norm (cosine similarity, relative L2), not entry by entry."""
+    from oracle import mode_torch as otc
+    import importlib
+    mod = importlib.import_module("fnet.nn_modules.RepMode")
+    torch.manual_seed(21)
+    net = mod.Net(argparse.Namespace(adopted_datasets=list(range(12)), gpu_ids=0)).cuda().train()
+    g = torch.Generator().manual_seed(22)
+    x = torch.randn(2, 1, 32, 64, 64, generator=g)
+    tgt = torch.randn(2, 1, 32, 64, 64, generator=g)
+    t = torch.tensor([1, 7])
+    p = {k: v.detach().cpu().clone() for k, v in net.state_dict().items()}
+    y = net(x.cuda(), t.cuda())
+    loss = torch.mean((y - tgt.cuda()) ** 2)
+    loss.backward()
+    watch = ["encoder_block1.conv_more.conv1.expert_conv5x5_conv", "encoder_block1.conv_more.conv2.expert_conv3x3_conv",
+             "encoder_block1.conv_more.conv2.gate.weight", "encoder_block2.conv_more.conv2.expert_conv5x5_conv",
+             "encoder_block2.conv_down.0.weight", "encoder_block3.conv_more.conv1.expert_avg5x5_conv",
+             "encoder_block4.conv_more.conv2.expert_conv5x5_conv", "bottle_block.conv2.expert_conv1x1_conv",
+             "bottle_block.conv1.subsequent_layer.0.weight", "decoder_block4.convt.0.weight",
+             "decoder_block3.conv_less.conv1.expert_conv5x5_conv", "decoder_block2.conv_less.conv2.expert_avg3x3_conv",
+             "decoder_block1.conv_less.conv1.expert_conv5x5_conv", "decoder_block1.conv_less.conv2.subsequent_layer.0.bias",
+             "conv_out.expert_conv5x5_conv", "conv_out.gate.bias"]
+    for k in watch:
+        p[k].requires_grad_(True)
+    torch.set_num_threads(min(32, torch.get_num_threads()))
+    yc = otc.net_forward(p, x, t, True, operand_f16=True)
+    lc = torch.mean((yc - tgt) ** 2)
+    lc.backward()
+    assert abs(float(loss) - float(lc)) <= 1e-3 * abs(float(lc)), (float(loss), float(lc))
+    assert_close(y.detach().cpu().numpy(), yc.detach().numpy(), 5e-3, "train-mode prediction")
+    named = dict(net.named_parameters())
+    worst = {}
+    for k in watch:
+        a, b = named[k].grad.detach().cpu().double().reshape(-1), p[k].grad.double().reshape(-1)
+        cos = float(torch.dot(a, b) / (a.norm() * b.norm()).clamp_min(1e-300))
+        l2 = float((a - b).norm() / b.norm().clamp_min(1e-300))
+        worst[k] = (cos, l2)
+    bad = {k: v for k, v in worst.items() if not (v[0] >= 0.98 and v[1] <= 0.2)}
+    print("full-width train-step gradients (cosine, rel-L2):", {k.split(".")[0] + ".." + k.split(".")[-1]: (round(c, 5), round(l, 4))
+                                                              for k, (c, l) in worst.items()})
+    assert not bad, bad

@@ -126,7 +126,9 @@ def test_eval_weight_cache_matches_uncached_and_invalidates(precision, monkeypat
             n0 = lib.mode_launch_count()
             b = m(x, ids)
             launches_plain = lib.mode_launch_count() - n0
-            assert torch.equal(a, b) and torch.equal(a, a2)
+            # the cached path folds BatchNorm + ReLU into K2's epilogue (and hands on fp16 on the tensor-core path): the same
+            # fp32 value, rounded once more when the activation is fp16
+            assert torch.equal(a.float(), b.to(a.dtype).float()) and torch.equal(a, a2)
             assert launches_cached < launches_plain          # no re-parameterisation launch on a cache hit
         monkeypatch.setattr(Fm, "EVAL_CACHE", True)
         before = m(x, ids).clone()
@@ -134,7 +136,7 @@ def test_eval_weight_cache_matches_uncached_and_invalidates(precision, monkeypat
         after = m(x, ids)
         monkeypatch.setattr(Fm, "EVAL_CACHE", False)
         assert not torch.equal(before, after)
-        assert torch.equal(after, m(x, ids))
+        assert torch.equal(after.float(), m(x, ids).to(after.dtype).float())
 
 
 @pytest.mark.parametrize("dtype_name", ["f32", "f16"])

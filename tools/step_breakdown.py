@@ -22,19 +22,11 @@ def main():
     dout = torch.randn(1, 32, 32, 128, 128, device=dev).contiguous(memory_format=torch.channels_last_3d)
     task = torch.tensor([3], device=dev, dtype=torch.int32)
 
-    sharded_local = os.environ.get("REPMODE_BENCH_SHARDED_LOCAL", "0") == "1"
-    if sharded_local:
-        from repmode_b200 import peer, sharded
-        comm = peer.TorchComm()
-
     def step():
         for p in params:
             p.grad = None
         x.grad = None
-        if sharded_local:      # the D-sharded formulation (haloed operand buffers, owned-plane conv) without neighbours
-            y = sharded.sharded_mode_conv(m, x, task, comm, 32, tag="blk")
-        else:
-            y = m(x, task)
+        y = m(x, task)
         y.backward(dout)
 
     for _ in range(5):

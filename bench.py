@@ -511,19 +511,20 @@ def run_ours(args, rank, local_rank, world):
         cpu = {"value": VOX * len(times) / sum(times), "unit": "voxels/s", "cores": cores, "kind": "port",
                "sample": "3 full fwd+bwd steps of the same workload after 1 warm-up (oracle/mode_torch.py, fp32)"}
 
-    cfg = workload_config(world)
-    cfg["precision"] = Fm.default_precision()
-    cfg["launch"] = ("forward+backward captured once as a CUDA graph and replayed" if main_graphed else "eager")
+    cfg = workload_config(world)                     # identical to the reference arm's `config`
+    run_info = {"precision": Fm.default_precision(),
+                "launch": "forward+backward captured once as a CUDA graph and replayed" if main_graphed else "eager"}
     if world > 1:
-        cfg["comm"] = ("peer memory over NVLink (repmode_b200/csrc/peer.cu)" if args.comm == "peer" else "NCCL (torch.distributed)")
+        run_info["comm"] = ("peer memory over NVLink (repmode_b200/csrc/peer.cu)" if args.comm == "peer"
+                            else "NCCL (torch.distributed)")
     if notes:
-        cfg["notes"] = notes
+        run_info["notes"] = notes
     line = {
         "metric": METRIC, "value": value, "unit": "voxels/s", "n_gpus": world, "steps": args.steps, "warmup": warmup,
         "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f16 operands (saturating, power-of-two scaled weights / dy; 10-bit mantissa like TF32), f32 accumulate" if use_umma else "f32",
         "data": "synthetic",
-        "config": cfg,
+        "config": cfg, "run": run_info,
         "e2e": {"value": e2e, "unit": "voxels/s", "h2d_bytes_per_step": x_host.numel() * 4 * world,
                 "d2h_bytes_per_step": d2h_bytes * world,
                 "ms_per_step": ms_e2e / args.steps if not fast else None,
@@ -565,12 +566,17 @@ def run_net_config(args, rank, local_rank, world):
     net = mod.Net(_ap.Namespace(adopted_datasets=list(range(T)), gpu_ids=local_rank)).to(dev)
     stream = torch.cuda.current_stream()
     cfg = args.config
+    notes = []
     sharded_cfg = cfg in ("cfg4", "cfg5")
     if sharded_cfg:
         want = 4 if cfg == "cfg4" else 8
-        if world != want:
+        dims = os.environ.get("REPMODE_BENCH_CFG_DIMS")          # dry-run hook: "D,H,W" of a smaller volume on any world
+        if world != want and not dims:
             raise SystemExit(f"bench.py --config {cfg} needs --gpus {want} (one rank per GPU under torchrun)")
         Dg, Hg, Wg = (64, 256, 256) if cfg == "cfg4" else (128, 512, 512)
+        if dims:
+            Dg, Hg, Wg = (int(v) for v in dims.split(","))
+            notes.append(f"DRY RUN on a {Dg}x{Hg}x{Wg} volume over {world} GPUs (REPMODE_BENCH_CFG_DIMS): not config {cfg[-1]}")
         dl = Dg // world
         batch = 1
         vox_step = Dg * Hg * Wg
@@ -588,7 +594,6 @@ def run_net_config(args, rank, local_rank, world):
         task = ((torch.arange(batch) * 3) % T).to(dev) if cfg == "net_train" else torch.tensor([3], device=dev)
         flop_step = (1 if cfg == "net_fwd" else 3) * NET_FLOP_FWD * batch
     x_dev = x_host.to(dev)
-    notes = []
 
     if cfg == "net_fwd":
         net.eval()
@@ -601,10 +606,8 @@ def run_net_config(args, rank, local_rank, world):
     else:
         net.train()
         params = list(net.parameters())
-        try:
-            opt = torch.optim.Adam(params, lr=1e-4, fused=True, capturable=True)
-        except Exception:  # noqa: BLE001
-            opt = torch.optim.Adam(params, lr=1e-4)
+        from repmode_b200.optim import FusedAdam           # the path's multi-tensor Adam (csrc/optim.cu): 2 launches per step
+        opt = FusedAdam(params, lr=1e-4)
         loss_buf = torch.zeros((), device=dev)
 
         def train_step(xin):
@@ -624,8 +627,10 @@ def run_net_config(args, rank, local_rank, world):
         # warm-up (allocator, lazy state), then try to capture the whole step (fwd + bwd + Adam) as ONE CUDA graph
         for p in params:
             p.grad = torch.zeros_like(p)
-        for _ in range(2):
-            train_step(x_dev)
+        train_step(x_dev)
+        l_tr0 = lib.mode_launch_count()
+        train_step(x_dev)
+        launches_eager_step = lib.mode_launch_count() - l_tr0      # a graph replay launches the same kernels
         torch.cuda.synchronize()
         run = lambda: train_step(x_dev)        # noqa: E731
         if os.environ.get("REPMODE_BENCH_GRAPH", "1") == "1" and not sharded_cfg:
@@ -634,7 +639,7 @@ def run_net_config(args, rank, local_rank, world):
                 with torch.cuda.graph(graph):
                     train_step(x_dev)
                 run = graph.replay
-                notes.append("train step (fwd + bwd + fused Adam) captured once as a CUDA graph and replayed")
+                notes.append("train step (fwd + bwd + mode_adam_step) captured once as a CUDA graph and replayed")
             except Exception as e:  # noqa: BLE001
                 notes.append(f"CUDA-graph capture failed, eager launches ({type(e).__name__}: {str(e)[:100]})")
                 torch.cuda.synchronize()
@@ -668,6 +673,8 @@ def run_net_config(args, rank, local_rank, world):
     l_eager0 = lib.mode_launch_count()
     run()                                                               # (net_fwd: the call that captures the graph)
     launches_one = lib.mode_launch_count() - l_eager0
+    if cfg != "net_fwd":
+        launches_one = max(launches_one, launches_eager_step)
     ms, launches = timed(run, args.steps, warmup)
     clocks = sampler.stop() if sampler else None
     # e2e: input from pinned host memory every step + the step's result read back (prediction / loss)

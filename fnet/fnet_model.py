@@ -7,7 +7,6 @@ torch >= 2.6 because the checkpoint pickles an argparse.Namespace), wandb loggin
 and `torch.amp` spellings of autocast / GradScaler.
 """
 import importlib
-import math
 import os
 
 import numpy as np
@@ -54,7 +53,13 @@ class Model(object):
             return
         self.net = importlib.import_module("fnet.nn_modules." + self.nn_module).Net(self.opts)
         self.net.to(self.device)
-        self.optimizer = torch.optim.Adam(self.net.parameters(), lr=self.lr)
+        if self.device.type == "cuda":
+            # same class hierarchy / state layout as torch.optim.Adam (checkpoints are interchangeable); the update of all
+            # 309 tensors is one launch of the path's multi-tensor kernel and GradScaler needs no host sync
+            from repmode_b200.optim import FusedAdam
+            self.optimizer = FusedAdam(self.net.parameters(), lr=self.lr)
+        else:
+            self.optimizer = torch.optim.Adam(self.net.parameters(), lr=self.lr)
 
     # ------------------------------------------------------------------ checkpointing
     _PLAIN_STATE = ("nn_module", "opts", "count_iter", "count_epoch")      # copied as they are; the two state_dicts follow
@@ -69,6 +74,12 @@ class Model(object):
         self.device = _device_of(self.gpu_ids)
         self.net.to(self.device)
         _set_gpu_recursive(self.optimizer.state, self.gpu_ids[0])
+        if self.device.type == "cuda" and type(self.optimizer) is torch.optim.Adam:
+            # built on the CPU (eval.py / load_state construct with gpu_ids=-1 and move afterwards): same state, fused step
+            from repmode_b200.optim import FusedAdam
+            state = self.optimizer.state_dict()
+            self.optimizer = FusedAdam(self.net.parameters(), lr=self.lr)
+            self.optimizer.load_state_dict(state)
 
     def save_state(self, path_save):
         """Checkpoints are written from the CPU copy of the network and optimizer state, then everything moves back."""
@@ -129,20 +140,18 @@ class Model(object):
         signal, task = signal.to(self.device), task.to(self.device)
         self.net.eval()
         size = tuple(signal.shape[-3:])
-        starts_per_axis = []
-        for length, plen in zip(size, patch_size):
-            stride = int(math.ceil(plen * 0.5))
-            steps = int(math.ceil((length - plen) / stride + 1))
-            axis = []
-            for i in range(max(steps, 1)):
-                end = min(i * stride + plen, length)
-                axis.append((max(end - plen, 0), end))
-            starts_per_axis.append(axis)
-        windows = [(a, b, c) for a in starts_per_axis[0] for b in starts_per_axis[1] for c in starts_per_axis[2]]
+        from repmode_b200 import predict as _predict
+        bs = max(1, int(getattr(self.opts, "batch_size_eval", 1)))
+        if self.device.type == "cuda" and signal.shape[0] == 1:
+            # B200 path: blend kernels (csrc/predict.cu); with `predict_group` set (a process group whose ranks hold the same
+            # volume and weights) the windows are dealt out to the ranks and the accumulators summed once
+            gauss = torch.from_numpy(get_gaussian(patch_size))
+            return _predict.sliding_window_predict(self.net, signal, task, patch_size, bs, gauss,
+                                                   group=getattr(self, "predict_group", None)).cpu()
+        windows = _predict.windows(size, patch_size)
         gauss = torch.from_numpy(get_gaussian(patch_size)).to(self.device)
         pred_sum = torch.zeros(signal.shape, device=self.device)
         weight_sum = torch.zeros(signal.shape, device=self.device)
-        bs = max(1, int(getattr(self.opts, "batch_size_eval", 1)))
         for k in range(0, len(windows), bs):
             chunk = windows[k:k + bs]
             batch = torch.cat([signal[:, :, a[0]:a[1], b[0]:b[1], c[0]:c[1]] for a, b, c in chunk], dim=0)

@@ -165,7 +165,14 @@ typedef struct {
     int32_t Dy16, y16_off;          /* planes of the y16 buffer (0 = D) and the plane output plane 0 lands in */
     float y16_scale;                /* 0 = 1 */
     const mode_peer_push_t* stats_push;   /* HOST pointer or NULL: the last CTA broadcasts bn_sums (2*Nout doubles) */
+    void* splitk_ws;                /* device scratch of mode_conv3d_workspace_bytes(...) bytes (16-byte aligned) or NULL */
+    int64_t splitk_ws_bytes;
 } mode_conv_opts_t;
+/* Deep, small-volume layers (the 8x32x32 .. 2x8x8 levels of the U-Net: a handful of 128-voxel tiles against K up to 512)
+ * run the tcgen05 conv SPLIT ALONG K over the SMs: every CTA accumulates a slice of the 32-channel chunks into a partial
+ * result and a second kernel sums the partials in fixed order and applies the epilogue.  Returns the scratch bytes such a
+ * call needs (0 = the shape runs unsplit; then splitk_ws may be NULL).  A call that needs scratch and gets none fails. */
+int64_t mode_conv3d_workspace_bytes(int32_t N, int32_t D, int32_t H, int32_t W, int32_t K, int32_t Nout, mode_dtype_t x_dtype);
 int mode_conv3d_ex(const void* x, mode_dtype_t x_dtype, const void* w, const int32_t* sample_u, float* y,
                    int32_t N, int32_t D, int32_t H, int32_t W, int32_t K, int32_t Nout, float out_scale,
                    const float* out_scale_dev, double* bn_sums, int32_t stat_d_lo, int32_t stat_d_hi, int32_t impl,
@@ -296,6 +303,34 @@ int mode_peer_put(const void* const* src_host, void* const* dst_peer_host, void*
 int mode_peer_wait(const void* signal, void* expect, int32_t add, void* stream);
 int mode_peer_sum_slots(const void* slots, int32_t world, int64_t n, int32_t is_double, void* out, const void* signal,
                         void* expect, void* ticket, void* stream);
+
+/* ---- Model.predict glue (fnet/fnet_model.py:149-223) ------------------------------------------------
+ * Sliding-window inference: the network runs on batches of overlapping patches and the predictions are blended with a
+ * Gaussian importance map.  mode_blend_accumulate replaces the per-patch sliced updates of reference :207-214
+ *     pred_sum[window] += pred_patch * gauss;  weight_sum[window] += gauss
+ * for a whole batch of P <= 64 patches in one pass (deterministic, patches added in batch order); mode_blend_finalize is
+ * reference :220, out = pred_sum / weight_sum.
+ *   pred       [P][C][pd][ph][pw] fp32 dense (NCDHW: what Net.forward returns for C = 1)
+ *   starts_dev [P][3] int32 window origins (d, h, w), DEVICE memory
+ *   gauss      [*][gh][gw] fp32 importance map, indexed with the patch-local coordinate (gh >= ph, gw >= pw)
+ *   pred_sum   [C][D][H][W] fp32, weight_sum [D][H][W] fp32 (kept once: it is identical for every channel) */
+int mode_blend_accumulate(const float* pred, const int32_t* starts_dev, const float* gauss, float* pred_sum,
+                          float* weight_sum, int32_t P, int32_t C, int32_t pd, int32_t ph, int32_t pw, int32_t gh, int32_t gw,
+                          int32_t D, int32_t H, int32_t W, void* stream);
+int mode_blend_finalize(const float* pred_sum, const float* weight_sum, float* out, int32_t C, int64_t voxels, void* stream);
+
+/* ---- Model.do_train_iter glue (fnet/fnet_model.py:96-132) --------------------------------------------
+ * torch.optim.Adam (the optimizer built at fnet_model.py:55; amsgrad = False, maximize = False) over ALL parameter tensors in
+ * one multi-tensor launch, with the GradScaler hand-shake of fnet_model.py:111-113 on the device: gradients are divided by
+ * *grad_scale_dev (NULL = 1) and the whole step -- including the per-tensor step counters -- is skipped when *found_inf_dev is
+ * non-zero (NULL = never), so scaler.step() needs no host synchronisation.
+ *   tensors_dev [ntensors] x {float* p, const float* g, float* m, float* v, float* step, int64 n}   (48-byte records, device)
+ *   chunks_dev  [nchunks]  x {int32 tensor, int32 0, int64 offset}: every tensor cut into pieces of mode_adam_chunk_elems()
+ *   step is torch's per-parameter fp32 scalar state['step'] on the device; it is advanced by 1 BEFORE the update, as in torch. */
+int64_t mode_adam_chunk_elems(void);
+int mode_adam_step(const void* tensors_dev, int32_t ntensors, const void* chunks_dev, int32_t nchunks, double lr, double beta1,
+                   double beta2, double eps, double weight_decay, const float* grad_scale_dev, const float* found_inf_dev,
+                   void* stream);
 
 #ifdef __cplusplus
 }

@@ -47,6 +47,8 @@ struct ConvExt {
     __half* y16;                   // optional fp16 copy of the result [N, Dy16, H, W, Nout], output plane q -> plane q + y16_off
     int Dy16, y16_off;
     float y16_scale;
+    void* splitk_ws;               // split-K scratch (conv_umma.cu) or null
+    long long splitk_ws_bytes;
     PeerPush push;                 // D-sharded slabs: the last CTA broadcasts bn_sums (2 * Nout doubles) to every rank
     __host__ __device__ int p_lo() const { return -x_off; }              // valid input planes in OUTPUT plane coordinates
     __host__ __device__ int p_hi() const { return Dx - x_off - 1; }

@@ -22,6 +22,7 @@
 //   BatchNorm partial sums, then re-zero the accumulators with tcgen05.st so every MMA can accumulate).
 // Roofline: tensor-pipe bound; algorithmic work 2*125*K*Nout FLOP per output voxel.
 #include <cuda.h>
+#include <stdlib.h>
 
 #include <algorithm>
 #include <array>
@@ -62,6 +63,12 @@ struct ConvParams {
     int p_lo, p_hi;              // valid input planes in output-plane coordinates: [-x_off, Dx - x_off - 1]
     int64_t units;               // N * tiles_h * tiles_w * D plane-patches
     int32_t bounds[160];         // CTA c owns units [bounds[c], bounds[c+1]) -- cost-balanced on the host
+    // split-K (deep, small-volume layers): CTA (x, y, z) accumulates the 32-channel chunks [z*cps, (z+1)*cps) only and
+    // stores its RAW fp32 accumulators into part[z] (same NDHWC indexing as y); conv_splitk_reduce_kernel sums the splits
+    // in fixed order and applies the whole epilogue (scale, affine, ReLU, fp16 copy, BatchNorm sums)
+    float* part;                 // null = no split
+    long long part_stride;       // elements per split = N*D*H*W*Nout
+    int cps;                     // chunks per split (nchunk when part == null)
     int* error_flag;
     long long* prof;             // optional [grid][8]: MMA-warp cycles total / wait tmem_empty / wait weights / wait
                                  // planes, then globaltimer ns at CTA entry / MMA loop end / all roles done
@@ -132,6 +139,7 @@ conv3d_umma_kernel(const __grid_constant__ CUtensorMap xmap, const ConvParams P)
     const int n0 = blockIdx.y * P.Nt;
     const uint64_t ts_entry = (P.prof != nullptr && threadIdx.x == 0) ? globaltimer_ns() : 0;
     const int nchunk = P.K / 32;
+    const int c_lo = blockIdx.z * P.cps, c_hi = min(nchunk, c_lo + P.cps);      // this CTA's K slice
     const uint32_t blk_bytes = (uint32_t)P.Nt * cu::ROWB;          // one kd block of a weight stage
     const uint32_t wst_bytes = 5u * blk_bytes;
 
@@ -164,7 +172,7 @@ conv3d_umma_kernel(const __grid_constant__ CUtensorMap xmap, const ConvParams P)
             while (tw_.next(n, h0, w0, d0, td)) {
                 int pmin, pmax;
                 plane_range(d0, td, P.p_lo, P.p_hi, pmin, pmax);
-                for (int c = 0; c < nchunk; ++c) {
+                for (int c = c_lo; c < c_hi; ++c) {
                     for (int p = pmin; p <= pmax; ++p, ++seq) {
                         const uint32_t slot = seq % P.ring, use = seq / P.ring;
                         if (!mbar_wait(plane_empty + 8 * slot, (use & 1) ^ 1)) { atomicExch(P.error_flag, 1); return; }
@@ -184,7 +192,7 @@ conv3d_umma_kernel(const __grid_constant__ CUtensorMap xmap, const ConvParams P)
             while (tw_.next(n, h0, w0, d0, td)) {
                 const int u = P.sample_u ? P.sample_u[n] : 0;
                 const __half* wu = P.w + (size_t)u * nchunk * 125 * P.Nout * 32;
-                for (int c = 0; c < nchunk; ++c) {
+                for (int c = c_lo; c < c_hi; ++c) {
                     for (int t = 0; t < 25; ++t, ++seq) {
                         const uint32_t st = seq % P.wstages, use = seq / P.wstages;
                         if (!mbar_wait(w_empty + 8 * st, (use & 1) ^ 1)) { atomicExch(P.error_flag, 2); return; }
@@ -226,7 +234,7 @@ conv3d_umma_kernel(const __grid_constant__ CUtensorMap xmap, const ConvParams P)
                 if (!mbar_wait(tmem_empty + 8 * buf, (it >> 1) & 1)) { atomicExch(P.error_flag, 3); return; }
                 c_tmem += clock64() - t0;
                 tc_fence_after();
-                for (int c = 0; c < nchunk; ++c) {
+                for (int c = c_lo; c < c_hi; ++c) {
                     // ---- per-chunk plane table
                     uint32_t slot = pslot, use = puse;
                     for (int i = 0; i < nplanes; ++i) {
@@ -323,6 +331,17 @@ conv3d_umma_kernel(const __grid_constant__ CUtensorMap xmap, const ConvParams P)
                         uint32_t v[32];
                         tmem_ld_32x32(taddr, v);
                         tmem_ld_wait();
+                        if (P.part != nullptr) {              // split-K: raw partial sums, epilogue in the reduce kernel
+                            if (row_ok) {
+                                float* dst = P.part + (size_t)blockIdx.z * P.part_stride +
+                                             ((((size_t)n * P.D + d0 + q) * P.H) * P.W + vox) * P.Nout + n0 + cc;
+#pragma unroll
+                                for (int j = 0; j < 32; j += 4)
+                                    *reinterpret_cast<uint4*>(dst + j) = make_uint4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+                            }
+                            tmem_st_32x32(taddr, zeros);
+                            continue;
+                        }
                         float f[32];
 #pragma unroll
                         for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]) * scale;
@@ -395,13 +414,92 @@ conv3d_umma_kernel(const __grid_constant__ CUtensorMap xmap, const ConvParams P)
         o[4] = (long long)ts_entry;                                       // CTA entry
         o[6] = (long long)globaltimer_ns();                               // all roles done (before teardown)
     }
-    if (P.bn_sums != nullptr)
+    if (P.bn_sums != nullptr && P.part == nullptr)
         for (int i = threadIdx.x; i < 2 * P.Nt; i += cu::THREADS) {
             const int which = i / P.Nt, ch = i % P.Nt;
             atomicAdd(P.bn_sums + which * P.Nout + n0 + ch, s_bn[i]);
         }
     if (P.ext.push.n > 0) push_vector_from_last_block(P.bn_sums, 2 * P.Nout, P.ext.push);
     if (warp == 2) tmem_dealloc<512>(tmem);
+}
+
+// ---- split-K reduce + epilogue ----------------------------------------------------------------------------------
+// Sums the ksplit partial results of conv3d_umma_kernel in fixed order (deterministic) and applies the epilogue the
+// unsplit kernel applies in place: out_scale, per-channel affine + ReLU (eval BatchNorm), fp32 result and/or saturated fp16
+// copy, BatchNorm sums over the planes [stat_lo, stat_hi).  HBM/L2-bound: (ksplit + 1) * 4 B per output element, float4
+// accesses, one thread = 4 channels of one voxel.
+struct SplitReduceParams {
+    const float* part; int ksplit; long long part_stride;
+    long long M; int Nout, D; long long HW;
+    float out_scale; const float* out_scale_dev;
+    const float* ep_scale; const float* ep_shift; int relu;
+    float* y; __half* y16; int Dy16, y16_off; float y16_scale;
+    double* bn_sums; int stat_lo, stat_hi;
+};
+
+__global__ void __launch_bounds__(256) conv_splitk_reduce_kernel(const SplitReduceParams R) {
+    extern __shared__ double s_red[];                       // [2][Nout] when bn_sums
+    const int cg = R.Nout >> 2, vpb = 256 / cg;
+    const int tv = threadIdx.x / cg, tc = threadIdx.x - tv * cg;
+    const bool active = tv < vpb;
+    if (R.bn_sums != nullptr) {
+        for (int i = threadIdx.x; i < 2 * R.Nout; i += 256) s_red[i] = 0.0;
+        __syncthreads();
+    }
+    float scale = R.out_scale;
+    if (R.out_scale_dev) scale *= *R.out_scale_dev;
+    const bool has_ep = R.ep_scale != nullptr || R.ep_shift != nullptr;
+    float4 sc = make_float4(1.f, 1.f, 1.f, 1.f), sh = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (active && R.ep_scale) sc = *reinterpret_cast<const float4*>(R.ep_scale + 4 * tc);
+    if (active && R.ep_shift) sh = *reinterpret_cast<const float4*>(R.ep_shift + 4 * tc);
+    float s1[4] = {0.f, 0.f, 0.f, 0.f}, s2[4] = {0.f, 0.f, 0.f, 0.f};
+    if (active) {
+        for (long long v = (long long)blockIdx.x * vpb + tv; v < R.M; v += (long long)gridDim.x * vpb) {
+            const float* p = R.part + v * R.Nout + 4 * tc;
+            float4 a = __ldcs(reinterpret_cast<const float4*>(p));
+            for (int k = 1; k < R.ksplit; ++k) {
+                const float4 b = __ldcs(reinterpret_cast<const float4*>(p + (long long)k * R.part_stride));
+                a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
+            }
+            float f[4] = {a.x * scale, a.y * scale, a.z * scale, a.w * scale};
+            if (has_ep) {
+                f[0] = fmaf(f[0], sc.x, sh.x); f[1] = fmaf(f[1], sc.y, sh.y);
+                f[2] = fmaf(f[2], sc.z, sh.z); f[3] = fmaf(f[3], sc.w, sh.w);
+            }
+            if (R.relu) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) f[j] = fmaxf(f[j], 0.f);
+            }
+            const long long per_n = (long long)R.D * R.HW;
+            const long long nn = v / per_n, rem = v - nn * per_n;
+            const int dpl = (int)(rem / R.HW);
+            if (R.y != nullptr) *reinterpret_cast<float4*>(R.y + v * R.Nout + 4 * tc) = make_float4(f[0], f[1], f[2], f[3]);
+            if (R.y16 != nullptr) {
+                const long long within = rem - (long long)dpl * R.HW;
+                __half* d16 = R.y16 + ((nn * R.Dy16 + dpl + R.y16_off) * R.HW + within) * R.Nout + 4 * tc;
+                const float s16 = R.y16_scale;
+                __half2 h0 = sat_half2(f[0] * s16, f[1] * s16), h1 = sat_half2(f[2] * s16, f[3] * s16);
+                uint2 pk;
+                pk.x = *reinterpret_cast<uint32_t*>(&h0); pk.y = *reinterpret_cast<uint32_t*>(&h1);
+                *reinterpret_cast<uint2*>(d16) = pk;
+            }
+            if (R.bn_sums != nullptr && dpl >= R.stat_lo && dpl < R.stat_hi) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) { s1[j] += f[j]; s2[j] = fmaf(f[j], f[j], s2[j]); }
+            }
+        }
+    }
+    if (R.bn_sums != nullptr) {
+        if (active) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                atomicAdd(s_red + 4 * tc + j, (double)s1[j]);
+                atomicAdd(s_red + R.Nout + 4 * tc + j, (double)s2[j]);
+            }
+        }
+        __syncthreads();
+        for (int i = threadIdx.x; i < 2 * R.Nout; i += 256) atomicAdd(R.bn_sums + i, s_red[i]);
+    }
 }
 
 // ------------------------------------------------------------------------------------------------ host
@@ -523,6 +621,51 @@ static void partition_units(int64_t units, int D, int p_lo, int p_hi, int TD, in
     std::copy(it->second.begin(), it->second.end(), bounds);
 }
 
+// Launch plan: output channels per CTA (Nt), and the K split.  Nt as wide as TMEM allows (<= 128: wide MMAs amortise the
+// exposed A read) when (tiles x channel passes) alone fills half the GPU; otherwise -- the deep, small-volume levels of the
+// U-Net (8x32x32 and below: 4..128 tiles, K up to 512) -- the 32-channel K chunks are split over CTAs as well (blockIdx.z),
+// so that e.g. the 512 -> 512 bottleneck layer on 2x8x8 voxels streams its 65 MB of weights through 64 SMs instead of 16.
+struct UmmaPlan { int Nt, TD, ksplit, cps; int64_t units; };
+static UmmaPlan umma_plan(int N, int D, int H, int W, int K, int Nout, bool no_split) {
+    const char* ms = getenv("REPMODE_UMMA_SPLITK");          // A/B + test hook: cap on the K split (1 = never split)
+    const int max_split = ms ? atoi(ms) : 64;
+    UmmaPlan pl{0, 1, 1, K / 32, 0};
+    pl.units = (int64_t)N * (int64_t)ceil_div(H, cu::TH) * (W / cu::TW) * D;
+    if (Nout > 1024) no_split = true;                       // reduce kernel: one thread per 4 channels, <= 256 per voxel
+    const int nchunk = K / 32, sms = sm_count();
+    double best = 0;
+    for (int nt = 128; nt >= 32; nt >>= 1) {
+        if (Nout % nt != 0) continue;
+        const int td = max(1, min(min(256 / nt, 8), D));
+        const int64_t tiles = ceil_div(pl.units, td), gx = std::min<int64_t>(tiles, sms), passes = Nout / nt;
+        for (int split = 0; split < 2; ++split) {
+            int ks = 1, cps = nchunk;
+            if (split) {
+                const int64_t ctas = gx * passes;
+                if (no_split || nchunk < 2 || max_split < 2 || ctas >= sms / 2) break;     // only when the GPU is under-filled
+                const int want = (int)std::min<int64_t>(std::min(nchunk, max_split), std::max<int64_t>(1, sms / ctas));
+                if (want < 2) break;
+                cps = (int)ceil_div(nchunk, want);
+                ks = (int)ceil_div(nchunk, cps);
+            }
+            // estimated MMA-issue cycles of the slowest SM: waves x tiles per CTA x cycles per tile (+ the reduce pass)
+            const int64_t waves = ceil_div(gx * passes * ks, sms);
+            const double t = (double)waves * (double)ceil_div(tiles, gx) * tile_cost(td, 0, 0, D - 1, nt, cps) + (ks > 1 ? 8000.0 : 0.0);
+            if (pl.Nt == 0 || t < 0.97 * best) {            // ties go to the wider channel pass
+                best = t;
+                pl.Nt = nt; pl.TD = td; pl.ksplit = ks; pl.cps = cps;
+            }
+        }
+    }
+    return pl;
+}
+
+int64_t conv3d_umma_workspace_bytes(int N, int D, int H, int W, int K, int Nout) {
+    if (K % 32 != 0 || Nout % 32 != 0 || W % cu::TW != 0) return 0;
+    const UmmaPlan pl = umma_plan(N, D, H, W, K, Nout, false);
+    return pl.ksplit > 1 ? (int64_t)pl.ksplit * N * D * H * W * Nout * 4 : 0;
+}
+
 bool conv3d_umma_supported(int D, int H, int W, int K, int Nout) {
     (void)D;
     (void)H;
@@ -543,18 +686,21 @@ int conv3d_umma(const __half* x, const __half* w, const int32_t* sample_u, float
     P.stat_lo = stat_lo; P.stat_hi = stat_hi;
     P.ext = ext;
     P.p_lo = ext.p_lo(); P.p_hi = ext.p_hi();
-    // Output channels per CTA: as wide as TMEM allows (<= 128) when the volume alone fills the GPU; narrower for the
-    // deep, small-volume layers so that (tiles x channel passes) still spreads over the SMs.
-    P.units = (int64_t)N * (int64_t)ceil_div(H, cu::TH) * (W / cu::TW) * D;
-    P.Nt = 0;
-    for (int nt = 128; nt >= 32; nt >>= 1) {
-        if (Nout % nt != 0) continue;
-        const int td = max(1, min(min(256 / nt, 8), D));
-        P.Nt = nt;
-        if (ceil_div(P.units, td) * (Nout / nt) >= sm_count() / 2) break;
+    const UmmaPlan plan = umma_plan(N, D, H, W, K, Nout, ext.push.n > 0);
+    if (plan.Nt == 0) MODE_FAIL("conv3d_umma: Nout=%d is not a multiple of 32", Nout);
+    P.units = plan.units;
+    P.Nt = plan.Nt;
+    P.cps = plan.cps;
+    P.part = nullptr;
+    P.part_stride = (long long)N * D * H * W * Nout;
+    if (plan.ksplit > 1) {
+        if (ext.splitk_ws == nullptr || ext.splitk_ws_bytes < (long long)plan.ksplit * P.part_stride * 4)
+            MODE_FAIL("conv3d_umma: this shape runs split-K x%d and needs a %lld-byte workspace (mode_conv3d_workspace_bytes, "
+                      "mode_conv_opts_t.splitk_ws)", plan.ksplit, (long long)plan.ksplit * P.part_stride * 4);
+        if (reinterpret_cast<uintptr_t>(ext.splitk_ws) & 15) MODE_FAIL("conv3d_umma: split-K workspace must be 16-byte aligned");
+        P.part = (float*)ext.splitk_ws;
     }
-    if (P.Nt == 0) MODE_FAIL("conv3d_umma: Nout=%d is not a multiple of 32", Nout);
-    P.TD = max(1, min(min(256 / P.Nt, 8), D));
+    P.TD = plan.TD;
     P.ring = P.TD + 4;
     const int wst_bytes = 5 * P.Nt * cu::ROWB;
     const int budget = 227 * 1024 - 1024 - P.ring * cu::PLANE_BYTES - 1024 - 4096 - 2048;    // barriers, BN sums, epilogue affine
@@ -574,9 +720,23 @@ int conv3d_umma(const __half* x, const __half* w, const int32_t* sample_u, float
     if (make_act_map(&xmap, x, N, ext.Dx, H, W, K, cu::BW, cu::BH, 1) != 0) return -1;
     MODE_CUDA(cudaFuncSetAttribute(conv3d_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
     const int grid = total < (int64_t)sm_count() ? (int)total : std::min(sm_count(), 159);
-    partition_units(P.units, D, P.p_lo, P.p_hi, P.TD, P.Nt, K / 32, grid, P.bounds);
-    conv3d_umma_kernel<<<dim3(grid, Nout / P.Nt), cu::THREADS, smem_bytes, st>>>(xmap, P);
+    partition_units(P.units, D, P.p_lo, P.p_hi, P.TD, P.Nt, P.cps, grid, P.bounds);
+    conv3d_umma_kernel<<<dim3(grid, Nout / P.Nt, plan.ksplit), cu::THREADS, smem_bytes, st>>>(xmap, P);
     MODE_LAUNCH_CHECK();
+    if (plan.ksplit > 1) {
+        SplitReduceParams R;
+        R.part = P.part; R.ksplit = plan.ksplit; R.part_stride = P.part_stride;
+        R.M = (long long)N * D * H * W; R.Nout = Nout; R.D = D; R.HW = (long long)H * W;
+        R.out_scale = out_scale; R.out_scale_dev = out_scale_dev;
+        R.ep_scale = ext.ep_scale; R.ep_shift = ext.ep_shift; R.relu = ext.relu;
+        R.y = y; R.y16 = ext.y16; R.Dy16 = ext.Dy16; R.y16_off = ext.y16_off; R.y16_scale = ext.y16_scale;
+        R.bn_sums = bn_sums; R.stat_lo = stat_lo; R.stat_hi = stat_hi;
+        const int vpb = 256 / (Nout / 4);
+        const int rgrid = (int)std::max<int64_t>(1, std::min<int64_t>(ceil_div(R.M, vpb), 4 * (int64_t)sm_count()));
+        const size_t rsmem = bn_sums ? 2 * (size_t)Nout * sizeof(double) : 0;
+        conv_splitk_reduce_kernel<<<rgrid, 256, rsmem, st>>>(R);
+        MODE_LAUNCH_CHECK();
+    }
     return 0;
 }
 

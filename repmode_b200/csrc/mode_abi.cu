@@ -53,6 +53,7 @@ int wgrad_simt(const float* x, const float* dy, float* dw, int N, int D, int H, 
                const float* out_scale_dev, int Dx, int x_off, cudaStream_t st);
 // conv_umma.cu
 bool conv3d_umma_supported(int D, int H, int W, int K, int Nout);
+int64_t conv3d_umma_workspace_bytes(int N, int D, int H, int W, int K, int Nout);
 int conv3d_umma(const __half* x, const __half* w, const int32_t* sample_u, float* y, int N, int D, int H, int W, int K,
                 int Nout, float out_scale, const float* out_scale_dev, double* bn_sums, int stat_lo, int stat_hi,
                 const ConvExt& ext, cudaStream_t st);
@@ -133,6 +134,8 @@ extern "C" int mode_conv3d_ex(const void* x, mode_dtype_t x_dtype, const void* w
     ext.Dy16 = (opts && opts->Dy16 > 0) ? opts->Dy16 : D;
     ext.y16_off = opts ? opts->y16_off : 0;
     ext.y16_scale = (opts && opts->y16_scale != 0.f) ? opts->y16_scale : 1.f;
+    ext.splitk_ws = opts ? opts->splitk_ws : nullptr;
+    ext.splitk_ws_bytes = opts ? (long long)opts->splitk_ws_bytes : 0;
     ext.push = to_peer_push(opts ? opts->stats_push : nullptr);
     if (ext.push.n < 0 || ext.push.n > 8 || (ext.push.n > 0 && (!ext.push.ticket || !bn_sums)))
         MODE_FAIL("mode_conv3d: bad stats_push descriptor (needs bn_sums, a ticket and <= 8 destinations)");
@@ -160,6 +163,15 @@ extern "C" int mode_conv3d_ex(const void* x, mode_dtype_t x_dtype, const void* w
         return conv3d_umma((const __half*)x, (const __half*)w, sample_u, y, N, D, H, W, K, Nout, out_scale, out_scale_dev, bn_sums, stat_d_lo, stat_d_hi, ext, st);
     }
     MODE_FAIL("mode_conv3d: unknown impl %d", impl);
+}
+
+extern "C" int64_t mode_conv3d_workspace_bytes(int32_t N, int32_t D, int32_t H, int32_t W, int32_t K, int32_t Nout,
+                                               mode_dtype_t x_dtype) {
+    if (x_dtype != MODE_F16 || N <= 0 || D <= 0 || H <= 0 || W <= 0 || K <= 0 || Nout <= 0) return 0;
+    static const bool no_pair = getenv("REPMODE_DISABLE_PAIR") != nullptr;
+    if (!conv3d_umma_supported(D, H, W, K, Nout)) return 0;
+    if (!no_pair && conv3d_pair_supported(N, D, H, W, K, Nout)) return 0;      // the CTA-pair kernel never splits
+    return conv3d_umma_workspace_bytes(N, D, H, W, K, Nout);
 }
 
 extern "C" int mode_conv3d(const void* x, mode_dtype_t x_dtype, const void* w, const int32_t* sample_u, float* y,

@@ -186,8 +186,13 @@ def conv3d(x, dtype, w, sample_u, n, d, h, wd, k, nout, out_scale_dev=None, bn_s
         y = torch.empty((n, d, h, wd, nout), dtype=torch.float32, device=x.device)
     lo, hi = stat_range if stat_range is not None else (0, d)
     opts = None
-    if halo is not None or ep is not None or y16 is not None or stats_push is not None:
+    # deep small-volume layers run split along K and need scratch for the partial results (0 bytes for everything else)
+    ws_bytes = int(lib.mode_conv3d_workspace_bytes(n, d, h, wd, k, nout, dtype)) if (impl in (0, 2, 3) and stats_push is None) else 0
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=x.device) if ws_bytes > 0 else None
+    if halo is not None or ep is not None or y16 is not None or stats_push is not None or ws is not None:
         o = _lib.ModeConvOpts()
+        if ws is not None:
+            o.splitk_ws, o.splitk_ws_bytes = ws.data_ptr(), ws_bytes
         if stats_push is not None:
             o.stats_push = ctypes.pointer(stats_push)
         if halo is not None:
@@ -647,6 +652,48 @@ class BnReluFunction(torch.autograd.Function):
         return dy, dgamma, dbeta, None, None, None, None, None, None
 
 
+class _tf32_matmul:
+    """Scope in which cuBLAS may run fp32 GEMMs on the tensor cores with TF32 operands (10-bit mantissa, fp32 accumulate and
+    result: the precision of the rest of the tensor-core path).  Without it the stride-2 GEMMs of a training step run as SIMT
+    sgemm: 2.1 ms of a 25 ms step at batch 4 for 0.55 % of the FLOPs (r2n profile)."""
+
+    def __enter__(self):
+        self.prev = torch.backends.cuda.matmul.allow_tf32
+        torch.backends.cuda.matmul.allow_tf32 = True
+
+    def __exit__(self, *exc):
+        torch.backends.cuda.matmul.allow_tf32 = self.prev
+        return False
+
+
+class _GemmFunction(torch.autograd.Function):
+    """a [M, K] @ b [K, N] with both backward GEMMs, each inside the TF32 scope (the flag is process-global and backward runs
+    on the autograd thread, so a scope around the forward call alone would not cover them)."""
+
+    @staticmethod
+    @torch.amp.custom_fwd(device_type="cuda", cast_inputs=torch.float32)
+    def forward(ctx, a, b):
+        ctx.save_for_backward(a, b)
+        with _tf32_matmul():
+            return a @ b
+
+    @staticmethod
+    @torch.amp.custom_bwd(device_type="cuda")
+    def backward(ctx, g):
+        a, b = ctx.saved_tensors
+        g = g.contiguous()
+        with _tf32_matmul():
+            da = g @ b.t() if ctx.needs_input_grad[0] else None
+            db = a.t() @ g if ctx.needs_input_grad[1] else None
+        return da, db
+
+
+def _gemm(a, b):
+    if a.is_cuda and a.dtype == torch.float32 and default_precision() == "f16":
+        return _GemmFunction.apply(a, b)
+    return a @ b
+
+
 def down_conv_bn_relu(x, conv_w, bn, training, shard=None):
     """Conv3d(k=2, s=2, bias=False) + BatchNorm3d + ReLU (reference RepMode.py:80-84) on NDHWC data: the stride-2
     conv is a plain GEMM on the space-to-depth view ([voxels/8, 8*Ci] @ [8*Ci, Co], cuBLAS), BN+ReLU are the path's
@@ -664,7 +711,7 @@ def down_conv_bn_relu(x, conv_w, bn, training, shard=None):
                                  lambda sc, shf: ((wm * sc).to(x8.dtype).contiguous(), shf.to(x8.dtype))))
         y = torch.addmm(sh, x8, wf).relu_()
         return y.view(n, d // 2, h // 2, w // 2, co).permute(0, 4, 1, 2, 3)
-    y = (x8 @ wm.to(x8.dtype)).view(n, d // 2, h // 2, w // 2, co)
+    y = _gemm(x8, wm.to(x8.dtype)).view(n, d // 2, h // 2, w // 2, co)
     out = BnReluFunction.apply(y, bn.weight, bn.bias, bn.running_mean, bn.running_var, training, shard, bn.eps,
                                bn.momentum if bn.momentum is not None else BN_MOMENTUM)
     return out.permute(0, 4, 1, 2, 3)
@@ -685,7 +732,7 @@ def up_conv_bn_relu(x, convt_w, bn, training, shard=None):
         y8 = torch.addmm(sh8, xn.reshape(-1, c), wf).relu_().view(n, d, h, w, 2, 2, 2, co)
         y = y8.permute(0, 1, 4, 2, 5, 3, 6, 7).reshape(n, 2 * d, 2 * h, 2 * w, co)
         return y.permute(0, 4, 1, 2, 3)
-    y8 = (xn.reshape(-1, c) @ wm.to(xn.dtype)).view(n, d, h, w, 2, 2, 2, co)
+    y8 = _gemm(xn.reshape(-1, c), wm.to(xn.dtype)).view(n, d, h, w, 2, 2, 2, co)
     y = y8.permute(0, 1, 4, 2, 5, 3, 6, 7).reshape(n, 2 * d, 2 * h, 2 * w, co)
     out = BnReluFunction.apply(y, bn.weight, bn.bias, bn.running_mean, bn.running_var, training, shard, bn.eps,
                                bn.momentum if bn.momentum is not None else BN_MOMENTUM)

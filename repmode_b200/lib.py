@@ -11,7 +11,7 @@ import threading
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 SO_PATH = os.path.join(HERE, "librepmode_b200.so")
-SOURCES = ["mode_abi.cu", "reparam.cu", "conv_simt.cu", "bn.cu", "conv_umma.cu", "conv_pair.cu", "wgrad_split.cu", "wgrad_deep.cu", "peer.cu"]
+SOURCES = ["mode_abi.cu", "reparam.cu", "conv_simt.cu", "bn.cu", "conv_umma.cu", "conv_pair.cu", "wgrad_split.cu", "wgrad_deep.cu", "peer.cu", "predict.cu", "optim.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-shared",
               "-Xcompiler", "-fPIC"]
 
@@ -55,7 +55,8 @@ class ModeConvOpts(ctypes.Structure):
     _fields_ = [("Dx", ctypes.c_int32), ("x_off", ctypes.c_int32), ("ep_scale", ctypes.c_void_p),
                 ("ep_shift", ctypes.c_void_p), ("relu", ctypes.c_int32), ("y16", ctypes.c_void_p),
                 ("Dy16", ctypes.c_int32), ("y16_off", ctypes.c_int32), ("y16_scale", ctypes.c_float),
-                ("stats_push", ctypes.POINTER(ModePeerPush))]
+                ("stats_push", ctypes.POINTER(ModePeerPush)), ("splitk_ws", ctypes.c_void_p),
+                ("splitk_ws_bytes", ctypes.c_int64)]
 
 
 class ModeCaps(ctypes.Structure):
@@ -86,7 +87,7 @@ def build(force=False, verbose=False):
     return SO_PATH
 
 
-_vp, _i32, _i64, _f32 = ctypes.c_void_p, ctypes.c_int32, ctypes.c_int64, ctypes.c_float
+_vp, _i32, _i64, _f32, _f64 = ctypes.c_void_p, ctypes.c_int32, ctypes.c_int64, ctypes.c_float, ctypes.c_double
 SIGNATURES = {
     "mode_last_error": (ctypes.c_char_p, []),
     "mode_version": (ctypes.c_int, []),
@@ -116,6 +117,12 @@ SIGNATURES = {
     "mode_peer_wait": (ctypes.c_int, [_vp, _vp, _i32, _vp]),
     "mode_peer_sum_slots": (ctypes.c_int, [_vp, _i32, _i64, _i32, _vp, _vp, _vp, _vp, _vp]),
     "mode_conv3d_wgrad_workspace_bytes": (_i64, [_i32, _i32, _i32, _i32, _i32, _i32, _i32]),
+    "mode_adam_chunk_elems": (_i64, []),
+    "mode_adam_step": (ctypes.c_int, [_vp, _i32, _vp, _i32, _f64, _f64, _f64, _f64, _f64, _vp, _vp, _vp]),
+    "mode_blend_accumulate": (ctypes.c_int, [_vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32,
+                                             _i32, _vp]),
+    "mode_blend_finalize": (ctypes.c_int, [_vp, _vp, _vp, _i32, _i64, _vp]),
+    "mode_conv3d_workspace_bytes": (_i64, [_i32, _i32, _i32, _i32, _i32, _i32, ctypes.c_int]),
     "mode_conv3d_wgrad": (ctypes.c_int, [_vp, _vp, ctypes.c_int, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _f32, _vp,
                                          _vp, _i32, _vp]),
     "mode_bn_stats": (ctypes.c_int, [_vp, _i64, _i32, _vp, _vp]),

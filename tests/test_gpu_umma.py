@@ -24,7 +24,9 @@ SHAPES = [  # N, D, H, W, K, Nout
     (1, 11, 16, 8, 64, 64),
     (1, 2, 8, 8, 32, 32),          # H < 16: rows past the volume are masked in the epilogue
     (2, 3, 24, 16, 32, 64),        # H % 16 != 0
-    (1, 2, 8, 8, 256, 128),        # deep-level shape (bottleneck-like)
+    (1, 2, 8, 8, 256, 128),        # deep-level shape (bottleneck-like): split-K x8
+    (1, 4, 16, 16, 160, 256),      # split-K over 5 chunks, two channel passes
+    (2, 8, 32, 32, 128, 128),      # level-3 layer of the U-Net at batch 2: split-K x2 over 64 tiles
 ]
 
 
@@ -56,7 +58,36 @@ def test_conv3d_umma_bitexact(shape):
         ref = np.stack([onp.conv3d_fwd(x[i].transpose(3, 0, 1, 2), weff[i]) for i in range(n)])
         assert np.array_equal(y_simt.cpu().numpy(), ref.transpose(0, 2, 3, 4, 1))
     assert torch.equal(y_umma, y_simt)
-    assert torch.allclose(sums16, sums32, rtol=1e-12, atol=1e-9)
+    # the sums pass through fp32 per-warp partials (32 voxels) before the fp64 accumulation: exact while |y|^2 * 32 stays
+    # below 2^24 / 64 (small K), rounded differently by the two kernels beyond that
+    assert torch.allclose(sums16, sums32, rtol=1e-12 if k <= 64 else 1e-6, atol=1e-9)
+
+
+@pytest.mark.parametrize("cap", [1, 3])
+def test_conv3d_umma_splitk_cap_bitexact(cap, monkeypatch):
+    """The K split of the single-CTA kernel (deep small-volume layers) is a launch-plan choice: unsplit (cap 1), an uneven
+    split (5 chunks over 3 CTAs: 2 + 2 + 1) and the default plan give the same bits on integer-valued data, including the
+    BatchNorm sums over a plane sub-range, and the workspace query follows the cap."""
+    from repmode_b200 import functional as Fm, lib as L
+    n, d, h, w, k, nout = 1, 4, 16, 16, 160, 64
+    rng = np.random.RandomState(11)
+    x = rng.randint(-3, 4, size=(n, d, h, w, k)).astype(np.float32)
+    weff = (rng.randint(-4, 5, size=(n, nout, k, 5, 5, 5)) / 8.0).astype(np.float32)
+    su = torch.zeros(n, dtype=torch.int32, device="cuda")
+    xg = torch.from_numpy(x).cuda()
+    w32 = torch.from_numpy(pack_weights(weff, half=False)).cuda()
+    w16 = torch.from_numpy(pack_weights(weff, half=True)).cuda()
+    sums32 = torch.zeros(2 * nout, dtype=torch.float64, device="cuda")
+    y_simt = Fm.conv3d(xg, L.MODE_F32, w32, su, n, d, h, w, k, nout, None, sums32, impl=L.IMPL_SIMT, stat_range=(1, 3))
+    monkeypatch.setenv("REPMODE_UMMA_SPLITK", str(cap))
+    lib = L.load()
+    ws = int(lib.mode_conv3d_workspace_bytes(n, d, h, w, k, nout, L.MODE_F16))
+    assert ws == (0 if cap == 1 else 3 * n * d * h * w * nout * 4)
+    sums16 = torch.zeros(2 * nout, dtype=torch.float64, device="cuda")
+    y = Fm.conv3d(xg.half(), L.MODE_F16, w16, su, n, d, h, w, k, nout, None, sums16, impl=L.IMPL_UMMA, stat_range=(1, 3))
+    _poll()
+    assert torch.equal(y, y_simt)
+    assert torch.allclose(sums16, sums32, rtol=1e-6, atol=1e-9)      # fp32 per-thread partials (see above)
 
 
 PAIR_SHAPES = [  # N, D, H, W, K, Nout, forced clusters (0 = the launcher's choice)
@@ -225,6 +256,8 @@ EX_SHAPES = [  # N, D (output planes), lo halo, hi halo, H, W, K, Nout, impl
     (1, 6, 2, 2, 16, 8, 32, 32, "single"),
     (2, 7, 2, 3, 24, 16, 64, 64, "single"),
     (1, 3, 4, 4, 16, 8, 32, 128, "single"),
+    (1, 2, 1, 1, 8, 8, 96, 64, "single"),          # split-K x3 with halo, epilogue and fp16-only result
+    (1, 4, 0, 2, 16, 16, 256, 128, "single"),
     (1, 4, 2, 2, 12, 10, 5, 7, "simt"),
 ]
 

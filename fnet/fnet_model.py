@@ -117,6 +117,7 @@ class Model(object):
         self.scaler.update()
 
         per_sample = torch.mean(loss_nomean.detach().float(), dim=(1, 2, 3, 4)).cpu().numpy()
+        self._poll_device("do_train_iter")
         task_host = task.cpu().numpy()
         if wandb is not None and getattr(wandb, "run", None) is not None:
             log = {"X-axis/iter": self.count_iter, "loss/iter": float(loss)}
@@ -126,6 +127,14 @@ class Model(object):
         frame = pd.DataFrame({"dataset": [self.opts.adopted_datasets[int(i)] for i in task_host],
                               "loss": list(per_sample)})
         return output.detach().float().cpu(), frame
+
+    def _poll_device(self, what):
+        """The B200 kernels never hang or throw from the device: a timed-out pipeline / an out-of-range task id raises a
+        device flag instead.  Read it where the reference's loop synchronises anyway, so a bad step cannot pass silently."""
+        if self.device.type == "cuda":
+            from repmode_b200 import lib as _mode_lib
+            with torch.cuda.device(self.device):
+                _mode_lib.poll_error(f"Model.{what}")
 
     def do_eval_iter(self, signal, target, task, info):
         pred = self.predict(signal, task, self.patch_size)
@@ -146,8 +155,10 @@ class Model(object):
             # B200 path: blend kernels (csrc/predict.cu); with `predict_group` set (a process group whose ranks hold the same
             # volume and weights) the windows are dealt out to the ranks and the accumulators summed once
             gauss = torch.from_numpy(get_gaussian(patch_size))
-            return _predict.sliding_window_predict(self.net, signal, task, patch_size, bs, gauss,
+            pred = _predict.sliding_window_predict(self.net, signal, task, patch_size, bs, gauss,
                                                    group=getattr(self, "predict_group", None)).cpu()
+            self._poll_device("predict")
+            return pred
         windows = _predict.windows(size, patch_size)
         gauss = torch.from_numpy(get_gaussian(patch_size)).to(self.device)
         pred_sum = torch.zeros(signal.shape, device=self.device)

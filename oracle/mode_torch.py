@@ -92,20 +92,29 @@ def sub2conv(p, prefix, x, t, training, operand_f16=False):
     return mode_conv(p, prefix + "conv2.", x, t, training, operand_f16=operand_f16)
 
 
+def _round_tf32(t):
+    """Round to a 10-bit mantissa (TF32 operand precision; round to nearest, ties away), straight-through gradient."""
+    bits = t.detach().contiguous().view(torch.int32)
+    r = ((bits + 0x1000) & ~0x1FFF).view(torch.float32)
+    return t + (r - t).detach()
+
+
 def net_forward(p, x, task_ids, training, operand_f16=False):
     """Net.forward (RepMode.py:51-71) over a reference-keyed state_dict p.  operand_f16: every MoDEConv with the
-    tensor-core path's operand rounding (see mode_conv)."""
+    tensor-core path's operand rounding (see mode_conv) and the stride-2 convs with TF32 operands (the tensor-core path runs
+    them as TF32 GEMMs in training)."""
+    rnd = _round_tf32 if operand_f16 else (lambda v: v)
     skips = []
     for k in (1, 2, 3, 4):
         pre = f"encoder_block{k}."
         s = sub2conv(p, pre + "conv_more.", x, task_ids, training, operand_f16)
         skips.append(s)
-        x = F.conv3d(s, p[pre + "conv_down.0.weight"], stride=2)
+        x = F.conv3d(rnd(s), rnd(p[pre + "conv_down.0.weight"]), stride=2)
         x = _bn_relu(p, pre + "conv_down.1.", x, training, False)
     x = sub2conv(p, "bottle_block.", x, task_ids, training, operand_f16)
     for k in (4, 3, 2, 1):
         pre = f"decoder_block{k}."
-        x = F.conv_transpose3d(x, p[pre + "convt.0.weight"], stride=2)
+        x = F.conv_transpose3d(rnd(x), rnd(p[pre + "convt.0.weight"]), stride=2)
         x = _bn_relu(p, pre + "convt.1.", x, training, False)
         x = torch.cat((skips[k - 1], x), dim=1)
         x = sub2conv(p, pre + "conv_less.", x, task_ids, training, operand_f16)

@@ -34,7 +34,8 @@ __global__ void __launch_bounds__(512) adam_multi_kernel(const AdamTensor* __res
     const float inv_scale = grad_scale != nullptr ? 1.f / *grad_scale : 1.f;
     // bias corrections in double, like the Python scalars of torch.optim.Adam; rounded to fp32 where torch hands them to
     // its fp32 tensor ops
-    const float b1 = (float)b1_d, b2 = (float)b2_d;
+    const float b2 = (float)b2_d;
+    const float omb1 = (float)(1.0 - b1_d), omb2 = (float)(1.0 - b2_d);     // torch: lerp weight 1 - beta1, addcmul value 1 - beta2
     const float bc2_sqrt = (float)sqrt(1.0 - pow(b2_d, (double)step));
     const float step_size = (float)(lr_d / (1.0 - pow(b1_d, (double)step)));
     const long long end = min(t.n, c.off + (long long)ADAM_CHUNK);
@@ -43,8 +44,8 @@ __global__ void __launch_bounds__(512) adam_multi_kernel(const AdamTensor* __res
     auto upd = [&](float& p, float g, float& m, float& v) {
         g *= inv_scale;
         if (wd != 0.f) g = fmaf(wd, p, g);
-        m = fmaf(b1, m, (1.f - b1) * g);
-        v = fmaf(b2, v, (1.f - b2) * g * g);
+        m = fmaf(omb1, g - m, m);                                  // exp_avg.lerp_(grad, 1 - beta1)
+        v = fmaf(omb2 * g, g, v * b2);                              // exp_avg_sq.mul_(beta2).addcmul_(grad, grad, value=1 - beta2)
         p -= step_size * (m / (sqrtf(v) / bc2_sqrt + eps));
     };
     if (vec) {

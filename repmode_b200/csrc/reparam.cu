@@ -16,6 +16,8 @@
 
 namespace mode {
 
+int* device_error_flag();   // mode_abi.cu
+
 __device__ __forceinline__ void store_w(float* p, float v) { *p = v; }
 __device__ __forceinline__ void store_w(__half* p, float v) {
     *p = __float2half_rn(fminf(fmaxf(v, -65504.f), 65504.f));      // saturate instead of producing inf
@@ -48,6 +50,17 @@ __device__ __forceinline__ size_t pack_index<__half>(int u, int tap, int chunk, 
     return (((((size_t)u * nchunk + chunk) * 25 + t) * 5 + (4 - kd)) * nrows + row) * MODE_KC + pack_col<__half>(row, col);
 }
 
+// Task ids come from the caller's data loader: an id outside [0, T) would index gate_w out of bounds (the reference raises
+// IndexError in its host loop, RepMode.py:44-49).  Here: clamp, and raise the device error flag (code 50, mode_poll_error).
+__device__ __forceinline__ int checked_task(const int32_t* task_ids, int u, int T, int* err) {
+    int t = task_ids[u];
+    if ((unsigned)t >= (unsigned)T) {
+        if (err != nullptr) atomicExch(err, 50);
+        t = min(max(t, 0), T - 1);
+    }
+    return t;
+}
+
 // grid (Co, ceil(Ci/32), U*5), block 256: one block = one (o, 32-ci block, gate input, kd slice of 25 taps).
 // The kd split multiplies the number of resident loads (a 32x32 layer is otherwise only 32 blocks deep and
 // the kernel is pure memory latency).
@@ -56,7 +69,7 @@ __global__ void __launch_bounds__(256) reparam_fwd_kernel(mode_layer_t L, const 
                                                           const float* __restrict__ t_dense,
                                                           float* __restrict__ g_out, OutT* __restrict__ w_fwd,
                                                           float w_scale, const float* __restrict__ w_scale_dev,
-                                                          int rows_pad) {
+                                                          int rows_pad, int* err) {
     __shared__ float sw[32 * 25];    // [i][tap in slice]; stride 25 is odd -> column reads are conflict free
     __shared__ float slog[MODE_NUM_EXPERTS];
     __shared__ float sg[MODE_NUM_EXPERTS];
@@ -68,7 +81,7 @@ __global__ void __launch_bounds__(256) reparam_fwd_kernel(mode_layer_t L, const 
         const int row = tid * Co + o;                         // gate row e*Co+o (RepMode.py:199)
         float logit;
         if (task_ids != nullptr) {
-            logit = __fadd_rn(L.gate_w[(size_t)row * T + task_ids[u]], L.gate_b[row]);
+            logit = __fadd_rn(L.gate_w[(size_t)row * T + checked_task(task_ids, u, T, err)], L.gate_b[row]);
         } else {
             float acc = 0.f;
             for (int t = 0; t < T; ++t) acc = fmaf(t_dense[(size_t)u * T + t], L.gate_w[(size_t)row * T + t], acc);
@@ -149,7 +162,7 @@ __global__ void __launch_bounds__(256, 4) reparam_fwd_rows_kernel(mode_layer_t L
                                                                const float* __restrict__ t_dense, int U,
                                                                float* __restrict__ g_out, OutT* __restrict__ w_fwd,
                                                                float w_scale, const float* __restrict__ w_scale_dev,
-                                                               int rows_pad) {
+                                                               int rows_pad, int* err) {
     __shared__ __align__(16) float s5[K1R_ROWS * 32 * 125];
     __shared__ __align__(16) float s3[K1R_ROWS * 32 * 27];
     __shared__ __align__(16) float s1[3 * K1R_ROWS * 32];     // k1, a3, a5
@@ -197,7 +210,7 @@ __global__ void __launch_bounds__(256, 4) reparam_fwd_rows_kernel(mode_layer_t L
             for (int e = 0; e < MODE_NUM_EXPERTS; ++e) {
                 const int row = e * Co + o;
                 if (task_ids != nullptr) {
-                    lg[e] = __fadd_rn(L.gate_w[(size_t)row * T + task_ids[u]], L.gate_b[row]);
+                    lg[e] = __fadd_rn(L.gate_w[(size_t)row * T + checked_task(task_ids, u, T, err)], L.gate_b[row]);
                 } else {
                     float acc = 0.f;
                     for (int t = 0; t < T; ++t) acc = fmaf(t_dense[(size_t)u * T + t], L.gate_w[(size_t)row * T + t], acc);
@@ -570,7 +583,7 @@ __global__ void gate_bwd_kernel(mode_layer_t L, const int32_t* __restrict__ task
                                 const float* __restrict__ t_dense, const int32_t* __restrict__ sample_u,
                                 int n_samples, int nci, const float* __restrict__ g,
                                 const float* __restrict__ dg_part, float* __restrict__ dgate_w,
-                                float* __restrict__ dgate_b) {
+                                float* __restrict__ dgate_b, int* err) {
     const int o = blockIdx.x * blockDim.x + threadIdx.x;
     const int Co = L.co, T = L.num_tasks;
     if (o >= Co) return;
@@ -593,7 +606,7 @@ __global__ void gate_bwd_kernel(mode_layer_t L, const int32_t* __restrict__ task
             const float dl = gv[e] * (dg[e] - s);
             db[e] += dl;
             float* wrow = dgate_w + ((size_t)e * Co + o) * T;
-            if (task_ids != nullptr) wrow[task_ids[u]] += dl;
+            if (task_ids != nullptr) wrow[checked_task(task_ids, u, T, err)] += dl;
             else
                 for (int t = 0; t < T; ++t) wrow[t] = fmaf(dl, t_dense[(size_t)u * T + t], wrow[t]);
         }
@@ -622,6 +635,7 @@ extern "C" int mode_reparam_fwd(const mode_layer_t* L, const int32_t* task_ids, 
     if (L->ci <= 0 || L->co <= 0 || L->num_tasks <= 0) MODE_FAIL("mode_reparam_fwd: bad layer dims");
     if ((int64_t)U * 125 > 65535) MODE_FAIL("mode_reparam_fwd: U too large (%d)", U);
     cudaStream_t st = (cudaStream_t)stream;
+    int* err = device_error_flag();
     const int nci = (int)ceil_div(L->ci, 32), nco = (int)ceil_div(L->co, 32);
     dim3 grid(L->co, nci, U * 5);
     // row-block kernel (experts read once for all U gate inputs) whenever the chunk is whole; REPMODE_K1_ROWS=0 forces the
@@ -634,10 +648,10 @@ extern "C" int mode_reparam_fwd(const mode_layer_t* L, const int32_t* task_ids, 
     if (w_dtype == MODE_F32) {
         if (rows)
             reparam_fwd_rows_kernel<float><<<rgrid, 256, 0, st>>>(*L, task_ids, t_dense, U, g_out, (float*)w_fwd, w_scale,
-                                                                  w_scale_dev, L->co);
+                                                                  w_scale_dev, L->co, err);
         else
             reparam_fwd_kernel<float><<<grid, 256, 0, st>>>(*L, task_ids, t_dense, g_out, (float*)w_fwd, w_scale,
-                                                            w_scale_dev, L->co);
+                                                            w_scale_dev, L->co, err);
         MODE_LAUNCH_CHECK();
         if (w_dgrad) {
             pack_dgrad_kernel<float><<<dim3(nci, nco, U * 125), dim3(32, 8), 0, st>>>((const float*)w_fwd,
@@ -648,10 +662,10 @@ extern "C" int mode_reparam_fwd(const mode_layer_t* L, const int32_t* task_ids, 
     } else if (w_dtype == MODE_F16) {
         if (rows)
             reparam_fwd_rows_kernel<__half><<<rgrid, 256, 0, st>>>(*L, task_ids, t_dense, U, g_out, (__half*)w_fwd, w_scale,
-                                                                   w_scale_dev, nco * 32);
+                                                                   w_scale_dev, nco * 32, err);
         else
             reparam_fwd_kernel<__half><<<grid, 256, 0, st>>>(*L, task_ids, t_dense, g_out, (__half*)w_fwd, w_scale,
-                                                             w_scale_dev, nco * 32);
+                                                             w_scale_dev, nco * 32, err);
         MODE_LAUNCH_CHECK();
         if (w_dgrad) {
             pack_dgrad_kernel<__half><<<dim3(nci, nco, U * 125), dim3(32, 8), 0, st>>>((const __half*)w_fwd,
@@ -688,7 +702,7 @@ extern "C" int mode_reparam_bwd(const mode_layer_t* L, const int32_t* task_ids, 
                                                                   da5, (float*)workspace);
     MODE_LAUNCH_CHECK();
     gate_bwd_kernel<<<(unsigned)ceil_div(L->co, 128), 128, 0, st>>>(*L, task_ids, t_dense, sample_u, n_samples, nci, g,
-                                                                  (const float*)workspace, dgate_w, dgate_b);
+                                                                  (const float*)workspace, dgate_w, dgate_b, device_error_flag());
     MODE_LAUNCH_CHECK();
     return 0;
 }

@@ -688,13 +688,14 @@ class _GemmFunction(torch.autograd.Function):
         return da, db
 
 
-def _gemm(a, b):
-    if a.is_cuda and a.dtype == torch.float32 and default_precision() == "f16":
+def _gemm(a, b, precision=None):
+    """precision 'f16' (the tensor-core path): TF32 tensor-core GEMM; 'f32': plain fp32 (SIMT sgemm), like the SIMT convs."""
+    if a.is_cuda and a.dtype == torch.float32 and (precision or default_precision()) == "f16":
         return _GemmFunction.apply(a, b)
     return a @ b
 
 
-def down_conv_bn_relu(x, conv_w, bn, training, shard=None):
+def down_conv_bn_relu(x, conv_w, bn, training, shard=None, precision=None):
     """Conv3d(k=2, s=2, bias=False) + BatchNorm3d + ReLU (reference RepMode.py:80-84) on NDHWC data: the stride-2
     conv is a plain GEMM on the space-to-depth view ([voxels/8, 8*Ci] @ [8*Ci, Co], cuBLAS), BN+ReLU are the path's
     own kernels.  x: [N,C,D,H,W] any strides -> [N,Co,D/2,H/2,W/2] channels_last_3d."""
@@ -711,13 +712,13 @@ def down_conv_bn_relu(x, conv_w, bn, training, shard=None):
                                  lambda sc, shf: ((wm * sc).to(x8.dtype).contiguous(), shf.to(x8.dtype))))
         y = torch.addmm(sh, x8, wf).relu_()
         return y.view(n, d // 2, h // 2, w // 2, co).permute(0, 4, 1, 2, 3)
-    y = _gemm(x8, wm.to(x8.dtype)).view(n, d // 2, h // 2, w // 2, co)
+    y = _gemm(x8, wm.to(x8.dtype), precision).view(n, d // 2, h // 2, w // 2, co)
     out = BnReluFunction.apply(y, bn.weight, bn.bias, bn.running_mean, bn.running_var, training, shard, bn.eps,
                                bn.momentum if bn.momentum is not None else BN_MOMENTUM)
     return out.permute(0, 4, 1, 2, 3)
 
 
-def up_conv_bn_relu(x, convt_w, bn, training, shard=None):
+def up_conv_bn_relu(x, convt_w, bn, training, shard=None, precision=None):
     """ConvTranspose3d(k=2, s=2, bias=False) + BatchNorm3d + ReLU (reference RepMode.py:97-101) on NDHWC data:
     [voxels, Ci] @ [Ci, 8*Co] (cuBLAS) followed by the depth-to-space scatter, then the path's BN+ReLU kernels."""
     xn = x.permute(0, 2, 3, 4, 1)
@@ -732,7 +733,7 @@ def up_conv_bn_relu(x, convt_w, bn, training, shard=None):
         y8 = torch.addmm(sh8, xn.reshape(-1, c), wf).relu_().view(n, d, h, w, 2, 2, 2, co)
         y = y8.permute(0, 1, 4, 2, 5, 3, 6, 7).reshape(n, 2 * d, 2 * h, 2 * w, co)
         return y.permute(0, 4, 1, 2, 3)
-    y8 = _gemm(xn.reshape(-1, c), wm.to(xn.dtype)).view(n, d, h, w, 2, 2, 2, co)
+    y8 = _gemm(xn.reshape(-1, c), wm.to(xn.dtype), precision).view(n, d, h, w, 2, 2, 2, co)
     y = y8.permute(0, 1, 4, 2, 5, 3, 6, 7).reshape(n, 2 * d, 2 * h, 2 * w, co)
     out = BnReluFunction.apply(y, bn.weight, bn.bias, bn.running_mean, bn.running_var, training, shard, bn.eps,
                                bn.momentum if bn.momentum is not None else BN_MOMENTUM)

@@ -77,13 +77,27 @@ def build(force=False, verbose=False):
     """Compile every CUDA translation unit for sm_100a into repmode_b200/librepmode_b200.so (in-tree)."""
     if not force and not _needs_build():
         return SO_PATH
-    nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", SO_PATH] + SOURCES
-    res = subprocess.run(cmd, cwd=CSRC, capture_output=True, text=True)
-    if res.returncode != 0:
-        raise RuntimeError("nvcc failed:\n" + res.stdout + res.stderr)
-    if verbose:
-        print(res.stderr)
+    # One builder at a time ACROSS processes (torchrun starts N ranks that may all find stale sources), and the library only
+    # ever appears complete: nvcc writes a private temporary that is renamed over SO_PATH.
+    import fcntl
+    with open(SO_PATH + ".lock", "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        try:
+            if not force and not _needs_build():          # another rank built it while we waited
+                return SO_PATH
+            nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+            tmp = f"{SO_PATH}.{os.getpid()}.tmp"
+            cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", tmp] + SOURCES
+            res = subprocess.run(cmd, cwd=CSRC, capture_output=True, text=True)
+            if res.returncode != 0:
+                if os.path.exists(tmp):
+                    os.remove(tmp)
+                raise RuntimeError("nvcc failed:\n" + res.stdout + res.stderr)
+            os.replace(tmp, SO_PATH)
+            if verbose:
+                print(res.stderr)
+        finally:
+            fcntl.flock(lock, fcntl.LOCK_UN)
     return SO_PATH
 
 
@@ -167,6 +181,20 @@ def load():
             raise RuntimeError("librepmode_b200.so ABI version mismatch")
         _lib = lib
         return lib
+
+
+def poll_error(what="repmode_b200"):
+    """Synchronise the current device and raise if a kernel raised the device error flag since the last poll: a tcgen05
+    pipeline or peer-exchange wait that timed out (codes 1-6, 41-44: the kernel bailed out and its output is incomplete) or
+    a task id outside [0, num_tasks) (code 50: clamped).  Called once per Model.do_train_iter / predict, which synchronise
+    anyway."""
+    code = ctypes.c_int32(0)
+    check(load().mode_poll_error(ctypes.byref(code)), "mode_poll_error")
+    if code.value == 50:
+        raise IndexError(f"{what}: a task id was outside [0, num_tasks) (the reference raises IndexError at RepMode.py:47)")
+    if code.value != 0:
+        raise RuntimeError(f"{what}: device error flag {code.value} (a kernel's pipeline / exchange wait timed out; "
+                           "results of this step are incomplete)")
 
 
 def check(rc, what):

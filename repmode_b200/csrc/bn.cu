@@ -20,15 +20,6 @@ int* device_error_flag();   // mode_abi.cu
 constexpr int BN_THREADS = 256;
 constexpr int BN_MAXC = 1024;
 
-// Streaming 16-byte load for tensors that are read once per kernel: read-only path, no L1 allocation.  Measured with
-// tools/stream_probe.cu on this pool's B200 (profiles/r2_stream_probe.txt): two 64 MB input streams read at 5.1 TB/s with
-// these loads against 4.5 TB/s with plain ld.global (L1 allocation of data that is never reused).
-__device__ __forceinline__ float4 ld_stream(const float* p) {
-    float4 v;
-    asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0, %1, %2, %3}, [%4];"
-                 : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
-    return v;
-}
 
 // D-sharded slab bookkeeping (mode_planes_t by value); kind(row): 0 = outside the global volume, 1 = halo copy,
 // 2 = owned
@@ -514,6 +505,29 @@ __global__ void __launch_bounds__(256) cast_f16_kernel(const float* __restrict__
     if (hp.on()) halo_finish(hp);
 }
 
+// fp32 [rows][c] -> fp16 [rows][c_pad] with zero channels appended (the U-Net stem: c = 1 -> 32), saturated like
+// cast_f16_kernel.  One thread per 16-byte output chunk (8 channels): the stores of a warp are 512 contiguous bytes.
+// Replaces cast + torch.zeros + strided copy (three passes, 283 us of a batch-4 train step in r2q) by one.
+__global__ void __launch_bounds__(256) cast_f16_pad_kernel(const float* __restrict__ src, __half* __restrict__ dst,
+                                                           int64_t rows, int c, int c_pad) {
+    const int chunks = c_pad >> 3;
+    const int64_t total = rows * chunks;
+    for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < total; i += (int64_t)gridDim.x * 256) {
+        const int64_t row = i / chunks;
+        const int c0 = (int)(i - row * chunks) * 8;
+        float v[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) v[e] = c0 + e < c ? src[row * c + c0 + e] : 0.f;
+        __half2 h0 = sat_half2(v[0], v[1]), h1 = sat_half2(v[2], v[3]), h2 = sat_half2(v[4], v[5]), h3 = sat_half2(v[6], v[7]);
+        uint4 pk;
+        pk.x = *reinterpret_cast<uint32_t*>(&h0);
+        pk.y = *reinterpret_cast<uint32_t*>(&h1);
+        pk.z = *reinterpret_cast<uint32_t*>(&h2);
+        pk.w = *reinterpret_cast<uint32_t*>(&h3);
+        *reinterpret_cast<uint4*>(dst + i * 8) = pk;
+    }
+}
+
 __global__ void __launch_bounds__(256) amax_kernel(const float* __restrict__ src, int64_t n, float* amax) {
     float m = 0.f;
     for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < n; i += (int64_t)gridDim.x * 256)
@@ -770,6 +784,16 @@ extern "C" int mode_cast_f16_ex(const float* src, void* dst_f16, int64_t n, floa
 extern "C" int mode_cast_f16(const float* src, void* dst_f16, int64_t n, float scale, const float* scale_dev,
                              void* stream) {
     return mode_cast_f16_ex(src, dst_f16, n, scale, scale_dev, nullptr, stream);
+}
+
+extern "C" int mode_cast_f16_pad(const float* src, void* dst_f16, int64_t rows, int32_t c, int32_t c_pad, void* stream) {
+    if (!src || !dst_f16 || rows <= 0 || c <= 0 || c_pad < c || (c_pad & 7)) MODE_FAIL("mode_cast_f16_pad: bad arguments");
+    if (reinterpret_cast<uintptr_t>(dst_f16) & 15) MODE_FAIL("mode_cast_f16_pad: dst must be 16-byte aligned");
+    const int64_t total = rows * (c_pad >> 3);
+    cast_f16_pad_kernel<<<wave_grid(cast_f16_pad_kernel, 256, ceil_div(total, 256)), 256, 0, (cudaStream_t)stream>>>(
+        src, (__half*)dst_f16, rows, c, c_pad);
+    MODE_LAUNCH_CHECK();
+    return 0;
 }
 
 extern "C" int mode_amax(const float* src, int64_t n, float* amax, void* stream) {

@@ -54,6 +54,16 @@ struct ConvExt {
     __host__ __device__ int p_hi() const { return Dx - x_off - 1; }
 };
 
+// Streaming 16-byte load for tensors that are read once per kernel: read-only path, no L1 allocation.  Measured with
+// tools/stream_probe.cu on this pool's B200 (profiles/r2_stream_probe.txt): two 64 MB input streams read at 5.1 TB/s with
+// these loads against 4.5 TB/s with plain ld.global (L1 allocation of data that is never reused).
+__device__ __forceinline__ float4 ld_stream(const float* p) {
+    float4 v;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0, %1, %2, %3}, [%4];"
+                 : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+    return v;
+}
+
 // fp32 -> fp16 with saturation (never inf): operands of the tcgen05 kernels
 __device__ __forceinline__ __half2 sat_half2(float a, float b) {
     return __floats2half2_rn(fminf(fmaxf(a, -65504.f), 65504.f), fminf(fmaxf(b, -65504.f), 65504.f));

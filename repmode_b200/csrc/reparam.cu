@@ -298,6 +298,57 @@ __global__ void __launch_bounds__(256) pack_dgrad_kernel(const T* __restrict__ s
     }
 }
 
+// fwd pack -> dgrad pack for the fp16 (stage-major, 64-byte-swizzled) layout with 16-byte global accesses (r2u; the kernel
+// above moves 2 bytes per thread and reached 1.5 TB/s: 1.05 ms of a 23 ms batch-4 train step).  A 32 x 32 tile of one
+// (gate input, tap, ci chunk, co block) is a CONTIGUOUS 2 KB block of the source pack and a contiguous 2 KB block of the
+// destination pack: 128 threads move one tile (one 16-byte chunk each way, transposed through shared memory), a block of
+// 256 threads PD_TILES tiles with all of its loads in flight before the first use.  Pad rows / columns of the source are
+// zero (the caller zero-initialises padded packs), so whole tiles are moved blindly.  grid ceil(n_tiles / PD_TILES).
+constexpr int PD_TILES = 8;
+__global__ void __launch_bounds__(256) pack_dgrad_h16_kernel(const __half* __restrict__ src, __half* __restrict__ dst,
+                                                             int nci, int nco, int src_rows_pad, int dst_rows_pad,
+                                                             long long n_tiles) {
+    __shared__ __align__(16) __half tile[PD_TILES][32][34];       // [ci][o], 68-byte rows (4-byte aligned, odd word stride)
+    const int tid = threadIdx.x, grp = tid >> 7, j = tid & 127;
+    const int r = j >> 2, pc = j & 3;
+    const int lc = pc ^ ((r >> 1) & 3);                           // logical 8-column chunk behind physical chunk pc of row r
+    const long long t0 = (long long)blockIdx.x * PD_TILES;
+    uint4 v[PD_TILES / 2];
+    size_t dbase[PD_TILES / 2];
+#pragma unroll
+    for (int k = 0; k < PD_TILES / 2; ++k) {
+        const long long tl = t0 + 2 * k + grp;
+        v[k] = make_uint4(0u, 0u, 0u, 0u);
+        dbase[k] = 0;
+        if (tl < n_tiles) {
+            const int oc = (int)(tl % nco);
+            long long q = tl / nco;
+            const int ic = (int)(q % nci);
+            q /= nci;
+            const int tap = (int)(q % 125), u = (int)(q / 125);
+            const int kd = tap / 25, t = tap - kd * 25;
+            const size_t sbase = (((((size_t)u * nci + ic) * 25 + t) * 5 + (4 - kd)) * src_rows_pad + (size_t)oc * 32) * MODE_KC;
+            // destination tap 124 - tap = (4 - kd, 24 - t): its block index inside the stage is 4 - (4 - kd) = kd
+            dbase[k] = (((((size_t)u * nco + oc) * 25 + (24 - t)) * 5 + kd) * dst_rows_pad + (size_t)ic * 32) * MODE_KC;
+            v[k] = *reinterpret_cast<const uint4*>(src + sbase + r * 32 + pc * 8);
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < PD_TILES / 2; ++k) {
+        const __half* h = reinterpret_cast<const __half*>(&v[k]);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) tile[2 * k + grp][lc * 8 + e][r] = h[e];     // source (row o = r, col ci) -> [ci][o]
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < PD_TILES / 2; ++k) {
+        const long long tl = t0 + 2 * k + grp;
+        if (tl >= n_tiles) continue;
+        const uint32_t* w = reinterpret_cast<const uint32_t*>(&tile[2 * k + grp][r][lc * 8]);   // dest row ci = r, cols o
+        *reinterpret_cast<uint4*>(dst + dbase[k] + r * 32 + pc * 8) = make_uint4(w[0], w[1], w[2], w[3]);
+    }
+}
+
 // K1b main kernel. grid (ceil(Ci/32), Co), block 128 -- the ci chunk is the FAST grid index, so blocks that run together
 // read neighbouring 128-byte segments of the same d_weff rows (DRAM page locality). Loops over the samples; every global
 // access is a contiguous segment (dW rows of 32 ci, expert slabs of 32*125 floats).
@@ -578,39 +629,243 @@ __global__ void __launch_bounds__(256, 3) reparam_bwd_slab_kernel(mode_layer_t L
     }
 }
 
+// K1b, register form (r2u, default whenever the 32-channel chunk is whole): same arithmetic as the slab kernel, without the
+// shared-memory round trip of d_weff.  The slab kernel staged every sample's [125][32] slab through shared memory (two
+// barriers per sample, no load of sample n + 1 in flight while sample n is consumed) and sat at 1.5 TB/s = 23 % of HBM on
+// 512 -> 512 (r2q), 1.68 ms of a 23 ms batch-4 train step.  Here a thread KEEPS the 16 values it loaded -- taps tr, tr + 32,
+// tr + 64, tr + 96 of one channel quad (four 16-byte loads) -- as its share of the work: the dk5 / dk3 accumulators for
+// exactly those (tap, ci) entries, its part of the two expert dot products (the staged experts are read at [ci][tap], odd
+// stride: conflict free) and of the per-channel column sums (reduced by shuffles inside the warp, across the 8 warps through
+// a double-buffered table: ONE barrier per sample).  The next sample's loads are issued before the current one is consumed.
+// dk5 leaves through the expert buffer (coalesced 16-byte stores), dk3 is accumulated in shared memory (every (ci, t3) entry
+// has exactly one owner thread).  grid (Ci / 32, Co), block 256.
+__global__ void __launch_bounds__(256, 3) reparam_bwd_reg_kernel(mode_layer_t L, const int32_t* __restrict__ sample_u,
+                                                                 int n_samples, const float* __restrict__ g,
+                                                                 const float* __restrict__ d_weff,
+                                                                 float* __restrict__ dk5, float* __restrict__ dk3,
+                                                                 float* __restrict__ dk1, float* __restrict__ da3,
+                                                                 float* __restrict__ da5, float* __restrict__ dg_part) {
+    __shared__ __align__(16) float sk5[32 * 125];     // experts [ci][tap]; reused as the dk5 staging buffer at the end
+    __shared__ __align__(16) float sk3[32 * 27];
+    __shared__ __align__(16) float sdk3[32 * 27];
+    __shared__ float s_col[2][2][8][32];              // [buffer][all / inner taps][warp][ci]
+    __shared__ float s_q[2][2][8];                    // [buffer][k5 / k3 dot product][warp]
+    __shared__ float s_cn[2][32];                     // centre-tap values [buffer][ci]
+    const int ic = blockIdx.x, o = blockIdx.y;
+    const int Ci = L.ci, Co = L.co;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int cq = tid & 7, tr = tid >> 3;            // channel quad 4cq..4cq+3; taps tr + 32p
+    const float c3 = 1.0f / 27, c5 = 1.0f / 125;
+    const size_t oc0 = (size_t)o * Ci + (size_t)ic * 32;
+    const size_t tap_stride = (size_t)Co * Ci;
+
+    float4 cur[4], nxt[4];
+    auto load_slab = [&](int n, float4 (&v)[4]) {
+        const float* dw = d_weff + ((size_t)n * 125 * Co + o) * Ci + (size_t)ic * 32 + cq * 4;
+#pragma unroll
+        for (int p = 0; p < 4; ++p) {
+            const int tap = tr + 32 * p;
+            v[p] = tap < 125 ? ld_stream(dw + (size_t)tap * tap_stride) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+    };
+    load_slab(0, cur);
+    // this thread's taps: index into the 3^3 expert (-1 outside the inner 3^3)
+    int t3i[4];
+#pragma unroll
+    for (int p = 0; p < 4; ++p) {
+        const int tap = tr + 32 * p;
+        const int kd = tap / 25, kh = (tap / 5) % 5, kw = tap % 5;
+        const bool inner = tap < 125 && kd >= 1 && kd <= 3 && kh >= 1 && kh <= 3 && kw >= 1 && kw <= 3;
+        t3i[p] = inner ? ((kd - 1) * 3 + (kh - 1)) * 3 + (kw - 1) : -1;
+    }
+    {   // experts of this (o, chunk): contiguous slabs, 16-byte loads
+        const float4* s5 = reinterpret_cast<const float4*>(L.k5 + oc0 * 125);
+        const float4* s3 = reinterpret_cast<const float4*>(L.k3 + oc0 * 27);
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+            if (tid + 256 * k < 1000) reinterpret_cast<float4*>(sk5)[tid + 256 * k] = s5[tid + 256 * k];
+        if (tid < 216) {
+            reinterpret_cast<float4*>(sk3)[tid] = s3[tid];
+            reinterpret_cast<float4*>(sdk3)[tid] = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+    }
+    const bool colthr = tid < 32;
+    const float k1v = colthr ? L.k1[oc0 + lane] : 0.f;
+    const float a3v = colthr ? L.a3[oc0 + lane] * c3 : 0.f;
+    const float a5v = colthr ? L.a5[oc0 + lane] * c5 : 0.f;
+    float acc5[4][4];
+#pragma unroll
+    for (int p = 0; p < 4; ++p)
+#pragma unroll
+        for (int q = 0; q < 4; ++q) acc5[p][q] = 0.f;
+    float acc_k1 = 0.f, acc_a3 = 0.f, acc_a5 = 0.f;
+    __syncthreads();                                  // experts staged
+
+    for (int n = 0; n < n_samples; ++n) {
+        const int buf = n & 1;
+        if (n + 1 < n_samples) load_slab(n + 1, nxt);
+        const int u = sample_u[n];
+        const float* gu = g + (size_t)u * MODE_NUM_EXPERTS * Co + o;
+        const float g0 = gu[0], g1 = gu[Co], g2 = gu[2 * Co], g3 = gu[3 * Co], g4 = gu[4 * Co];
+        float q0 = 0.f, q1 = 0.f, pa[4] = {0.f, 0.f, 0.f, 0.f}, pi[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int p = 0; p < 4; ++p) {
+            const int tap = tr + 32 * p;
+            if (tap < 125) {
+                const float vv[4] = {cur[p].x, cur[p].y, cur[p].z, cur[p].w};
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const int ci = cq * 4 + q;
+                    const float v = vv[q];
+                    acc5[p][q] = fmaf(g0, v, acc5[p][q]);
+                    q0 = fmaf(sk5[ci * 125 + tap], v, q0);
+                    pa[q] += v;
+                    if (t3i[p] >= 0) {
+                        pi[q] += v;
+                        q1 = fmaf(sk3[ci * 27 + t3i[p]], v, q1);
+                        sdk3[ci * 27 + t3i[p]] = fmaf(g1, v, sdk3[ci * 27 + t3i[p]]);      // owned by this thread only
+                    }
+                    if (tap == 62) s_cn[buf][ci] = v;
+                }
+            }
+        }
+        // column sums: lanes with the same channel quad (lane & 7) hold different taps
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            pa[q] += __shfl_xor_sync(0xffffffffu, pa[q], 8);
+            pa[q] += __shfl_xor_sync(0xffffffffu, pa[q], 16);
+            pi[q] += __shfl_xor_sync(0xffffffffu, pi[q], 8);
+            pi[q] += __shfl_xor_sync(0xffffffffu, pi[q], 16);
+        }
+        if (lane < 8) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                s_col[buf][0][warp][lane * 4 + q] = pa[q];
+                s_col[buf][1][warp][lane * 4 + q] = pi[q];
+            }
+        }
+#pragma unroll
+        for (int sft = 16; sft > 0; sft >>= 1) {
+            q0 += __shfl_xor_sync(0xffffffffu, q0, sft);
+            q1 += __shfl_xor_sync(0xffffffffu, q1, sft);
+        }
+        if (lane == 0) { s_q[buf][0][warp] = q0; s_q[buf][1][warp] = q1; }
+        __syncthreads();          // the only barrier per sample: buffer `buf` is rewritten two samples later, i.e. after the
+                                  // next barrier, which warp 0 only reaches once it has read it
+        if (colthr) {
+            float A = 0.f, I = 0.f;
+#pragma unroll
+            for (int w = 0; w < 8; ++w) { A += s_col[buf][0][w][lane]; I += s_col[buf][1][w][lane]; }
+            const float Cn = s_cn[buf][lane];
+            acc_k1 = fmaf(g2, Cn, acc_k1);
+            acc_a3 = fmaf(g3, I * c3, acc_a3);
+            acc_a5 = fmaf(g4, A * c5, acc_a5);
+            float d2 = k1v * Cn, d3 = a3v * I, d4 = a5v * A;
+#pragma unroll
+            for (int sft = 16; sft > 0; sft >>= 1) {
+                d2 += __shfl_xor_sync(0xffffffffu, d2, sft);
+                d3 += __shfl_xor_sync(0xffffffffu, d3, sft);
+                d4 += __shfl_xor_sync(0xffffffffu, d4, sft);
+            }
+            if (lane == 0) {
+                float t0 = 0.f, t1 = 0.f;
+#pragma unroll
+                for (int w = 0; w < 8; ++w) { t0 += s_q[buf][0][w]; t1 += s_q[buf][1][w]; }
+                float* dst = dg_part + (((size_t)ic * n_samples + n) * MODE_NUM_EXPERTS) * Co + o;
+                dst[0] = t0;
+                dst[Co] = t1;
+                dst[2 * Co] = d2;
+                dst[3 * Co] = d3;
+                dst[4 * Co] = d4;
+            }
+        }
+#pragma unroll
+        for (int p = 0; p < 4; ++p) cur[p] = nxt[p];
+    }
+    __syncthreads();                                  // every thread is done with the staged experts
+#pragma unroll
+    for (int p = 0; p < 4; ++p) {
+        const int tap = tr + 32 * p;
+        if (tap < 125) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) sk5[(cq * 4 + q) * 125 + tap] = acc5[p][q];
+        }
+    }
+    __syncthreads();
+    float4* dst5 = reinterpret_cast<float4*>(dk5 + oc0 * 125);
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+        if (tid + 256 * k < 1000) dst5[tid + 256 * k] = reinterpret_cast<const float4*>(sk5)[tid + 256 * k];
+    if (tid < 216) reinterpret_cast<float4*>(dk3 + oc0 * 27)[tid] = reinterpret_cast<const float4*>(sdk3)[tid];
+    if (colthr) {
+        dk1[oc0 + lane] = acc_k1;
+        da3[oc0 + lane] = acc_a3;
+        da5[oc0 + lane] = acc_a5;
+    }
+}
+
 // softmax + Linear backward; one thread per output channel o, samples in order -> deterministic.
 __global__ void gate_bwd_kernel(mode_layer_t L, const int32_t* __restrict__ task_ids,
                                 const float* __restrict__ t_dense, const int32_t* __restrict__ sample_u,
                                 int n_samples, int nci, const float* __restrict__ g,
                                 const float* __restrict__ dg_part, float* __restrict__ dgate_w,
                                 float* __restrict__ dgate_b, int* err) {
+    // r2u: samples are taken eight at a time with their logit gradients held in registers and dgate_w written once per
+    // (expert, task) at the end of the chunk -- the first version zeroed dgate_w in global memory and then read-modified-
+    // wrote it per sample (a chain of dependent global round trips: 10 us for ONE sample, 21 us at batch 4, r2q).  Same
+    // summation order as before (samples in order, starting from 0): bit-identical results.
     const int o = blockIdx.x * blockDim.x + threadIdx.x;
     const int Co = L.co, T = L.num_tasks;
     if (o >= Co) return;
     float db[MODE_NUM_EXPERTS];
-    for (int e = 0; e < MODE_NUM_EXPERTS; ++e) {
-        db[e] = 0.f;
-        for (int t = 0; t < T; ++t) dgate_w[((size_t)e * Co + o) * T + t] = 0.f;
-    }
-    for (int n = 0; n < n_samples; ++n) {
-        const int u = sample_u[n];
-        float gv[MODE_NUM_EXPERTS], dg[MODE_NUM_EXPERTS], s = 0.f;
-        for (int e = 0; e < MODE_NUM_EXPERTS; ++e) {
-            gv[e] = g[((size_t)u * MODE_NUM_EXPERTS + e) * Co + o];
-            float a = 0.f;
-            for (int b = 0; b < nci; ++b) a += dg_part[(((size_t)b * n_samples + n) * MODE_NUM_EXPERTS + e) * Co + o];
-            dg[e] = a;
-            s = fmaf(gv[e], a, s);
+#pragma unroll
+    for (int e = 0; e < MODE_NUM_EXPERTS; ++e) db[e] = 0.f;
+    for (int n0 = 0; n0 < n_samples; n0 += 8) {
+        float dlv[8][MODE_NUM_EXPERTS];
+        int col[8];                                   // task column (id mode) / gate-input row (dense mode); -1 = no sample
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            col[j] = -1;
+#pragma unroll
+            for (int e = 0; e < MODE_NUM_EXPERTS; ++e) dlv[j][e] = 0.f;
+            const int n = n0 + j;
+            if (n < n_samples) {
+                const int u = sample_u[n];
+                col[j] = task_ids != nullptr ? checked_task(task_ids, u, T, err) : u;
+                float gv[MODE_NUM_EXPERTS], dg[MODE_NUM_EXPERTS], s = 0.f;
+#pragma unroll
+                for (int e = 0; e < MODE_NUM_EXPERTS; ++e) {
+                    gv[e] = g[((size_t)u * MODE_NUM_EXPERTS + e) * Co + o];
+                    float a = 0.f;
+                    for (int b = 0; b < nci; ++b) a += dg_part[(((size_t)b * n_samples + n) * MODE_NUM_EXPERTS + e) * Co + o];
+                    dg[e] = a;
+                    s = fmaf(gv[e], a, s);
+                }
+#pragma unroll
+                for (int e = 0; e < MODE_NUM_EXPERTS; ++e) {
+                    dlv[j][e] = gv[e] * (dg[e] - s);
+                    db[e] += dlv[j][e];
+                }
+            }
         }
-        for (int e = 0; e < MODE_NUM_EXPERTS; ++e) {
-            const float dl = gv[e] * (dg[e] - s);
-            db[e] += dl;
-            float* wrow = dgate_w + ((size_t)e * Co + o) * T;
-            if (task_ids != nullptr) wrow[checked_task(task_ids, u, T, err)] += dl;
-            else
-                for (int t = 0; t < T; ++t) wrow[t] = fmaf(dl, t_dense[(size_t)u * T + t], wrow[t]);
+        for (int t = 0; t < T; ++t) {
+#pragma unroll
+            for (int e = 0; e < MODE_NUM_EXPERTS; ++e) {
+                float w = 0.f;
+                if (task_ids != nullptr) {
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) w += col[j] == t ? dlv[j][e] : 0.f;
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 8; ++j)
+                        if (col[j] >= 0) w = fmaf(dlv[j][e], t_dense[(size_t)col[j] * T + t], w);
+                }
+                float* dst = dgate_w + ((size_t)e * Co + o) * T + t;
+                *dst = n0 == 0 ? w : *dst + w;
+            }
         }
     }
+#pragma unroll
     for (int e = 0; e < MODE_NUM_EXPERTS; ++e) dgate_b[(size_t)e * Co + o] = db[e];
 }
 
@@ -668,9 +923,18 @@ extern "C" int mode_reparam_fwd(const mode_layer_t* L, const int32_t* task_ids, 
                                                              w_scale_dev, nco * 32, err);
         MODE_LAUNCH_CHECK();
         if (w_dgrad) {
-            pack_dgrad_kernel<__half><<<dim3(nci, nco, U * 125), dim3(32, 8), 0, st>>>((const __half*)w_fwd,
-                                                                                    (__half*)w_dgrad, L->ci, L->co,
-                                                                                    nco * 32, nci * 32);
+            const char* pd_env = getenv("REPMODE_PACK_DGRAD_V1");                // A/B arm: the 2-byte-per-thread kernel
+            const bool pd_v1 = (pd_env != nullptr && pd_env[0] == '1') ||
+                               ((reinterpret_cast<uintptr_t>(w_fwd) | reinterpret_cast<uintptr_t>(w_dgrad)) & 15) != 0;
+            if (pd_v1) {
+                pack_dgrad_kernel<__half><<<dim3(nci, nco, U * 125), dim3(32, 8), 0, st>>>((const __half*)w_fwd,
+                                                                                        (__half*)w_dgrad, L->ci, L->co,
+                                                                                        nco * 32, nci * 32);
+            } else {
+                const long long n_tiles = (long long)U * 125 * nci * nco;
+                pack_dgrad_h16_kernel<<<(unsigned)ceil_div(n_tiles, PD_TILES), 256, 0, st>>>(
+                    (const __half*)w_fwd, (__half*)w_dgrad, nci, nco, nco * 32, nci * 32, n_tiles);
+            }
             MODE_LAUNCH_CHECK();
         }
     } else {
@@ -697,6 +961,11 @@ extern "C" int mode_reparam_bwd(const mode_layer_t* L, const int32_t* task_ids, 
     if (legacy)
         reparam_bwd_kernel<<<dim3(nci, L->co), 128, 0, st>>>(*L, sample_u, n_samples, g, d_weff, dk5, dk3, dk1, da3, da5,
                                                             (float*)workspace);
+    else if (L->ci % 32 == 0 && getenv("REPMODE_K1B_SLAB") == nullptr &&
+             ((reinterpret_cast<uintptr_t>(d_weff) | reinterpret_cast<uintptr_t>(L->k5) | reinterpret_cast<uintptr_t>(L->k3) |
+               reinterpret_cast<uintptr_t>(dk5) | reinterpret_cast<uintptr_t>(dk3)) & 15) == 0)
+        reparam_bwd_reg_kernel<<<dim3(nci, L->co), 256, 0, st>>>(*L, sample_u, n_samples, g, d_weff, dk5, dk3, dk1, da3,
+                                                                 da5, (float*)workspace);
     else
         reparam_bwd_slab_kernel<<<dim3(nci, L->co), 256, 0, st>>>(*L, sample_u, n_samples, g, d_weff, dk5, dk3, dk1, da3,
                                                                   da5, (float*)workspace);

@@ -276,6 +276,15 @@ def cast_f16(x, scale_dev=None):
     return out
 
 
+def cast_f16_pad(x, c_pad):
+    """fp32 [..., C] -> fp16 [..., c_pad] with zero channels appended, one kernel (the stem layer's Ci = 1 -> 32 operand)."""
+    lib = _lib.load()
+    c = x.shape[-1]
+    out = torch.empty(x.shape[:-1] + (c_pad,), dtype=torch.float16, device=x.device)
+    _lib.check(lib.mode_cast_f16_pad(_p(x), _p(out), x.numel() // c, c, c_pad, _stream()), "mode_cast_f16_pad")
+    return out
+
+
 class ModeConvFunction(torch.autograd.Function):
     """MoDEConv.forward as one autograd node.
 
@@ -321,7 +330,7 @@ class ModeConvFunction(torch.autograd.Function):
         k1_fork = _Fork(dev, use_umma)
         g, w_fwd, w_dg = reparam_fwd(layer, gate_u, U, ci, co, dtype, needs_dx, w_scale, fork=k1_fork)
         if use_umma:
-            x_op = pad_channels(cast_f16(xn), ci_p)
+            x_op = cast_f16(xn) if ci_p == ci else cast_f16_pad(xn, ci_p)
         else:
             x_op = xn
         k1_fork.join()
@@ -545,7 +554,8 @@ def mode_conv_eval(x, task_ids, params, bn, conv_type, precision, cache):
         if xn.dtype == torch.float16 and xn.is_contiguous():
             x_op = xn                                               # the previous layer's fp16 activation IS the operand
         else:
-            x_op = cast_f16(xn.contiguous().float())
+            xf = xn.contiguous().float()
+            x_op = cast_f16(xf) if ci_p == ci else cast_f16_pad(xf, ci_p)
         x_op = pad_channels(x_op, ci_p)
     else:
         x_op = xn.contiguous().float()

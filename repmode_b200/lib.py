@@ -155,6 +155,7 @@ SIGNATURES = {
     "mode_bn_bwd_workspace_bytes": (_i64, [_i32]),
     "mode_bn_relu_bwd": (ctypes.c_int, [_vp, _vp, _i64, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "mode_cast_f16": (ctypes.c_int, [_vp, _vp, _i64, _f32, _vp, _vp]),
+    "mode_cast_f16_pad": (ctypes.c_int, [_vp, _vp, _i64, _i32, _i32, _vp]),
     "mode_amax": (ctypes.c_int, [_vp, _i64, _vp, _vp]),
     "mode_amax_multi": (ctypes.c_int, [_vp, _vp, _i32, _vp, _vp]),
     "mode_f16_scale": (ctypes.c_int, [_vp, _f32, _vp, _vp]),

@@ -317,7 +317,8 @@ def sharded_net_forward(net, x_local, t, d_global, group=None, probe=None, repli
         bump(bn)
         _, _, dl, h, w = x_skip.shape
         spec = _full_spec(n, dl // 2, h // 2, w // 2, dg // 2, group) if sharded else None
-        x = keep(f"enc{li + 1}.down", Fm.down_conv_bn_relu(x_skip, blk.conv_down[0].weight, bn, training, spec))
+        x = keep(f"enc{li + 1}.down", Fm.down_conv_bn_relu(x_skip, blk.conv_down[0].weight, bn, training, spec,
+                                                            precision=blk.conv_more.conv2.precision))
         dg //= 2
     if sharded and dg // world < HALO:
         x = _AllGatherD.apply(x, group)
@@ -333,7 +334,8 @@ def sharded_net_forward(net, x_local, t, d_global, group=None, probe=None, repli
             sharded = True
         _, _, dl, h, w = x.shape
         spec = _full_spec(n, 2 * dl, 2 * h, 2 * w, 2 * dg, group) if sharded else None
-        x = keep(f"dec{4 - li}.up", Fm.up_conv_bn_relu(x, blk.convt[0].weight, bn, training, spec))
+        x = keep(f"dec{4 - li}.up", Fm.up_conv_bn_relu(x, blk.convt[0].weight, bn, training, spec,
+                                                         precision=blk.conv_less.conv1.precision))
         dg *= 2
         xc = torch.cat((x_skip, x), 1)
         x = keep(f"dec{4 - li}.out", sharded_stage(blk.conv_less, xc, t, dg, group) if sharded else blk.conv_less(xc, t))

@@ -160,6 +160,80 @@ def test_reparam_rows_kernel_bit_identical(dtype_name, ci, co, U, monkeypatch):
     assert torch.equal(g0, g1) and torch.equal(w0, w1) and torch.equal(d0, d1)
 
 
+@pytest.mark.parametrize("ci,co,U", [(128, 160, 3), (32, 32, 1), (64, 34, 2), (1, 32, 2), (32, 1, 1)])
+def test_pack_dgrad_vector_kernel_bit_identical(ci, co, U, monkeypatch):
+    """The 16-byte-access dgrad-pack kernel (pack_dgrad_h16_kernel, default) == the element-wise one, including packs whose
+    rows / columns are zero-padded to 32 (stem Ci = 1, head Co = 1)."""
+    from repmode_b200 import functional as Fm, lib as L
+    from repmode_b200.nn_modules import MoDEConv
+    torch.manual_seed(6)
+    m = MoDEConv(5, 12, ci, co).cuda()
+    layer, ci, co = Fm._layer(*m._params())
+    ids = torch.tensor([3, 7, 3][:U], device="cuda", dtype=torch.int32)
+    monkeypatch.setenv("REPMODE_PACK_DGRAD_V1", "1")
+    _, w0, d0 = Fm.reparam_fwd(layer, ids, U, ci, co, L.MODE_F16, True, Fm.W_SCALE_F16)
+    monkeypatch.setenv("REPMODE_PACK_DGRAD_V1", "0")
+    _, w1, d1 = Fm.reparam_fwd(layer, ids, U, ci, co, L.MODE_F16, True, Fm.W_SCALE_F16)
+    assert torch.equal(w0, w1) and torch.equal(d0, d1) and float(d1.float().abs().max()) > 0
+
+
+@pytest.mark.parametrize("ci,co,n", [(32, 32, 1), (64, 48, 3), (128, 32, 10)])
+def test_reparam_bwd_register_kernel_matches_slab_kernel(ci, co, n, monkeypatch):
+    """K1b's register-form kernel (default when Ci % 32 == 0) against the slab kernel on random d_weff: every expert
+    gradient and the gate gradients (through gate_bwd, batches beyond its 8-sample chunk included) to fp32 re-association."""
+    import ctypes
+    from repmode_b200 import functional as Fm, lib as L
+    from repmode_b200.nn_modules import MoDEConv
+    torch.manual_seed(8)
+    m = MoDEConv(5, 12, ci, co).cuda()
+    layer, ci, co = Fm._layer(*m._params())
+    lib = L.load()
+    ids = (torch.arange(n, device="cuda", dtype=torch.int32) * 5) % 12
+    sample_u = torch.arange(n, device="cuda", dtype=torch.int32)
+    g = torch.softmax(torch.randn(n, 5, co, device="cuda"), dim=1).contiguous()
+    d_weff = torch.randn(n, 125, co, ci, device="cuda")
+
+    def run():
+        outs = [torch.empty_like(q) for q in m._params()]
+        ws = torch.empty(max(int(lib.mode_reparam_bwd_workspace_bytes(ci, co, n)), 16), dtype=torch.uint8, device="cuda")
+        L.check(lib.mode_reparam_bwd(ctypes.byref(layer), Fm._p(ids), None, n, Fm._p(sample_u), n, Fm._p(g), Fm._p(d_weff),
+                                     *[Fm._p(o) for o in outs], Fm._p(ws), Fm._stream()), "mode_reparam_bwd")
+        torch.cuda.synchronize()
+        return outs
+    monkeypatch.setenv("REPMODE_K1B_SLAB", "1")
+    ref = run()
+    monkeypatch.delenv("REPMODE_K1B_SLAB")
+    got = run()
+    # closed form of the expert gradients (RepMode.py:171-192 differentiated): dk5 = sum_n g0[n, o] * dW[n]
+    dk5 = torch.einsum("no,ntoi->oit", g[:, 0], d_weff).reshape(co, ci, 5, 5, 5)
+    assert_close(got[0].cpu().numpy(), dk5.cpu().numpy(), 1e-5, "dk5 vs closed form")
+    for a, b, k in zip(got, ref, ("dk5", "dk3", "dk1", "da3", "da5", "dgate_w", "dgate_b")):
+        assert_close(a.cpu().numpy(), b.cpu().numpy(), 2e-5, k)
+    # closed form of the gate gradients (softmax + Linear backward on the given g): dg[n,e,o] = <dW[n,:,o,:], K_e[o]>
+    import torch.nn.functional as F
+    k5, k3, k1, a3, a5 = [q.detach() for q in m._params()[:5]]
+    pad = lambda k: F.pad(k, [(5 - k.shape[-1]) // 2] * 6)  # noqa: E731
+    ks = torch.stack([k5, pad(k3), pad(k1), pad(a3.expand(-1, -1, 3, 3, 3) / 27), a5.expand(-1, -1, 5, 5, 5) / 125])
+    dg = torch.einsum("ntoi,eoit->neo", d_weff.double(), ks.reshape(5, co, ci, 125).double())
+    dl = g.double() * (dg - (g.double() * dg).sum(dim=1, keepdim=True))          # [n, e, o]
+    dgb = dl.sum(dim=0).reshape(-1)
+    dgw = torch.zeros(5 * co, 12, dtype=torch.float64, device="cuda")
+    dgw.index_add_(1, ids.long(), dl.permute(1, 2, 0).reshape(5 * co, n))
+    assert_close(got[6].cpu().numpy(), dgb.float().cpu().numpy(), 1e-4, "dgate_b vs closed form")
+    assert_close(got[5].cpu().numpy(), dgw.float().cpu().numpy(), 1e-4, "dgate_w vs closed form")
+
+
+def test_cast_f16_pad_matches_cast_then_pad():
+    from repmode_b200 import functional as Fm
+    x = torch.randn(2, 3, 8, 16, 1, device="cuda") * 3
+    x[0, 0, 0, 0, 0] = 1e6                                         # saturates instead of becoming inf
+    got = Fm.cast_f16_pad(x, 32)
+    want = Fm.pad_channels(Fm.cast_f16(x), 32)
+    assert got.shape == want.shape and torch.equal(got, want) and float(got[0, 0, 0, 0, 0]) == 65504.0
+    x5 = torch.randn(37, 5, device="cuda")
+    assert torch.equal(Fm.cast_f16_pad(x5, 8), Fm.pad_channels(Fm.cast_f16(x5), 8))
+
+
 def test_frozen_batchnorm_backward_matches_oracle():
     """Backward through a MoDEConv in EVAL mode (frozen BatchNorm statistics: fine-tuning, saliency maps): dx and every
     parameter gradient, BatchNorm affine included, against the oracle's autograd through F.batch_norm(training=False)."""

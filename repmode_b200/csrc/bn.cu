@@ -476,33 +476,53 @@ __global__ void __launch_bounds__(BN_THREADS) bn_bwd_apply_kernel(const float* _
 // ---- operand staging ---------------------------------------------------------------------------------------
 // fp32 -> fp16, round to nearest even, SATURATED to +-65504 (never inf: an out-of-range activation clips instead of
 // poisoning the accumulators).  Four 16-byte loads in flight per thread.
+// With a halo push (D-sharded slabs) the traversal is ROTATED so that it starts at the upper boundary region and wraps
+// into the lower one: both regions are written -- locally and into the neighbours' halo planes -- in the first pass of the
+// grid-stride loop, and every block takes its ticket as soon as its share of them is done.  The neighbours' counters then
+// move after ~a quarter of the kernel instead of at its end (r2v: the conv that follows marches from the lower halo plane
+// upwards, so it needs the halo at once; the rest of this kernel now hides the NVLink flight time and the rank skew).
 __global__ void __launch_bounds__(256) cast_f16_kernel(const float* __restrict__ src, __half* __restrict__ dst,
                                                        int64_t n, float scale, const float* __restrict__ scale_dev,
                                                        HaloPush hp) {
     if (scale_dev != nullptr) scale *= *scale_dev;
     const int64_t nvec = n >> 2;
     const int64_t stride = (int64_t)gridDim.x * 256;
-    for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < nvec; i += 4 * stride) {
+    const bool push = hp.on();
+    const int64_t bvec = push ? (hp.bytes >> 3) : 0;               // 8-byte output vectors per boundary region
+    const int64_t shift = push ? nvec - bvec : 0;
+    const int64_t early = 2 * bvec;                                // rotated indices below this touch a boundary region
+    bool signalled = false;
+    for (int64_t j0 = (int64_t)blockIdx.x * 256; j0 < nvec; j0 += 4 * stride) {          // block-uniform trip count
+        if (push && !signalled && j0 >= early) {
+            halo_finish(hp);
+            signalled = true;
+        }
+        const int64_t j = j0 + threadIdx.x;
         float4 v[4];
-#pragma unroll
-        for (int u = 0; u < 4; ++u)
-            if (i + u * stride < nvec) v[u] = ld_stream(src + (i + u * stride) * 4);
+        int64_t idx[4];
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
-            if (i + u * stride >= nvec) continue;
+            int64_t i = j + u * stride + shift;
+            if (i >= nvec) i -= nvec;
+            idx[u] = j + u * stride < nvec ? i : -1;
+            if (idx[u] >= 0) v[u] = ld_stream(src + idx[u] * 4);
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            if (idx[u] < 0) continue;
             __half2 a = sat_half2(v[u].x * scale, v[u].y * scale), b = sat_half2(v[u].z * scale, v[u].w * scale);
             uint2 pk;
             pk.x = *reinterpret_cast<uint32_t*>(&a);
             pk.y = *reinterpret_cast<uint32_t*>(&b);
-            *reinterpret_cast<uint2*>(dst + (i + u * stride) * 4) = pk;
-            if (hp.on()) halo_store(hp, (i + u * stride) * 8, nvec * 8, pk);       // host guarantees n % 4 == 0 with a push
+            *reinterpret_cast<uint2*>(dst + idx[u] * 4) = pk;
+            if (push) halo_store(hp, idx[u] * 8, nvec * 8, pk);                    // host guarantees n % 4 == 0 with a push
         }
     }
     if (blockIdx.x == 0 && threadIdx.x < (n & 3)) {
         const int64_t i = (nvec << 2) + threadIdx.x;
         dst[i] = __float2half_rn(fminf(fmaxf(src[i] * scale, -65504.f), 65504.f));
     }
-    if (hp.on()) halo_finish(hp);
+    if (push && !signalled) halo_finish(hp);
 }
 
 // fp32 [rows][c] -> fp16 [rows][c_pad] with zero channels appended (the U-Net stem: c = 1 -> 32), saturated like

@@ -804,6 +804,78 @@ __global__ void __launch_bounds__(256, 3) reparam_bwd_reg_kernel(mode_layer_t L,
     }
 }
 
+// softmax + Linear backward, block form (r2v, default): the one-thread-per-channel kernel below is a single latency chain
+// (5 * nci dependent-issue loads per sample on 1..4 warps of the whole GPU: 30 us per layer at batch 4, 0.58 ms of a 21.8 ms
+// train step in r2u).  Here a block owns 32 output channels (lane = channel): warp w turns sample n0 + w of a chunk of eight
+// into its logit gradients (all 5 * nci partial sums of a sample are independent, coalesced 128-byte loads), then the owner
+// thread (expert e = warp, channel = lane) folds the chunk into db and into its [T] row of dgate_w in shared memory --
+// samples in order, starting from 0: the same summation order as the serial kernel, bit-identical results.
+// grid ceil(Co / 32), block 256, dynamic shared memory 5 * 32 * T floats.
+__global__ void __launch_bounds__(256) gate_bwd_block_kernel(mode_layer_t L, const int32_t* __restrict__ task_ids,
+                                                             const float* __restrict__ t_dense,
+                                                             const int32_t* __restrict__ sample_u, int n_samples, int nci,
+                                                             const float* __restrict__ g, const float* __restrict__ dg_part,
+                                                             float* __restrict__ dgate_w, float* __restrict__ dgate_b,
+                                                             int* err) {
+    extern __shared__ float s_w[];                    // [expert][channel][T]
+    __shared__ float s_dl[8][MODE_NUM_EXPERTS][32];
+    __shared__ int s_col[8];
+    const int Co = L.co, T = L.num_tasks;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int o = blockIdx.x * 32 + lane;
+    const bool valid = o < Co;
+    for (int i = tid; i < MODE_NUM_EXPERTS * 32 * T; i += 256) s_w[i] = 0.f;
+    float db = 0.f;
+    for (int n0 = 0; n0 < n_samples; n0 += 8) {
+        const int n = n0 + warp;
+        if (n < n_samples) {
+            const int u = sample_u[n];
+            if (lane == 0) s_col[warp] = task_ids != nullptr ? checked_task(task_ids, u, T, err) : u;
+            float gv[MODE_NUM_EXPERTS], dg[MODE_NUM_EXPERTS], s = 0.f;
+#pragma unroll
+            for (int e = 0; e < MODE_NUM_EXPERTS; ++e) {
+                gv[e] = valid ? g[((size_t)u * MODE_NUM_EXPERTS + e) * Co + o] : 0.f;
+                dg[e] = 0.f;
+            }
+            if (valid) {
+#pragma unroll 4
+                for (int b = 0; b < nci; ++b) {
+                    const float* src = dg_part + (((size_t)b * n_samples + n) * MODE_NUM_EXPERTS) * Co + o;
+#pragma unroll
+                    for (int e = 0; e < MODE_NUM_EXPERTS; ++e) dg[e] += src[(size_t)e * Co];
+                }
+            }
+#pragma unroll
+            for (int e = 0; e < MODE_NUM_EXPERTS; ++e) s = fmaf(gv[e], dg[e], s);
+#pragma unroll
+            for (int e = 0; e < MODE_NUM_EXPERTS; ++e) s_dl[warp][e][lane] = gv[e] * (dg[e] - s);
+        }
+        __syncthreads();
+        if (warp < MODE_NUM_EXPERTS) {
+            float* wrow = s_w + ((size_t)warp * 32 + lane) * T;
+            const int cnt = min(8, n_samples - n0);
+            for (int j = 0; j < cnt; ++j) db += s_dl[j][warp][lane];
+            for (int t = 0; t < T; ++t) {              // per-chunk partial first, then added: the serial kernel's rounding
+                float w = 0.f;
+                if (task_ids != nullptr) {
+                    for (int j = 0; j < cnt; ++j) w += s_col[j] == t ? s_dl[j][warp][lane] : 0.f;
+                } else {
+                    for (int j = 0; j < cnt; ++j) w = fmaf(s_dl[j][warp][lane], t_dense[(size_t)s_col[j] * T + t], w);
+                }
+                wrow[t] = n0 == 0 ? w : wrow[t] + w;
+            }
+        }
+        __syncthreads();
+    }
+    // [E][Co][T]: the 32 channels of this block are one contiguous run of 32 * T floats per expert
+    const int run = 32 * T;
+    for (int i = tid; i < MODE_NUM_EXPERTS * run; i += 256) {
+        const int e = i / run, r = i - e * run;
+        if (blockIdx.x * 32 + r / T < Co) dgate_w[((size_t)e * Co + (size_t)blockIdx.x * 32) * T + r] = s_w[i];
+    }
+    if (warp < MODE_NUM_EXPERTS && valid) dgate_b[(size_t)warp * Co + o] = db;
+}
+
 // softmax + Linear backward; one thread per output channel o, samples in order -> deterministic.
 __global__ void gate_bwd_kernel(mode_layer_t L, const int32_t* __restrict__ task_ids,
                                 const float* __restrict__ t_dense, const int32_t* __restrict__ sample_u,
@@ -970,8 +1042,16 @@ extern "C" int mode_reparam_bwd(const mode_layer_t* L, const int32_t* task_ids, 
         reparam_bwd_slab_kernel<<<dim3(nci, L->co), 256, 0, st>>>(*L, sample_u, n_samples, g, d_weff, dk5, dk3, dk1, da3,
                                                                   da5, (float*)workspace);
     MODE_LAUNCH_CHECK();
-    gate_bwd_kernel<<<(unsigned)ceil_div(L->co, 128), 128, 0, st>>>(*L, task_ids, t_dense, sample_u, n_samples, nci, g,
-                                                                  (const float*)workspace, dgate_w, dgate_b, device_error_flag());
+    const size_t gate_smem = (size_t)MODE_NUM_EXPERTS * 32 * L->num_tasks * sizeof(float);
+    const bool gate_serial = getenv("REPMODE_GATE_BWD_SERIAL") != nullptr;      // A/B arm: one thread per channel
+    if (!gate_serial && gate_smem <= 40 * 1024)
+        gate_bwd_block_kernel<<<(unsigned)ceil_div(L->co, 32), 256, gate_smem, st>>>(
+            *L, task_ids, t_dense, sample_u, n_samples, nci, g, (const float*)workspace, dgate_w, dgate_b,
+            device_error_flag());
+    else
+        gate_bwd_kernel<<<(unsigned)ceil_div(L->co, 128), 128, 0, st>>>(*L, task_ids, t_dense, sample_u, n_samples, nci, g,
+                                                                      (const float*)workspace, dgate_w, dgate_b,
+                                                                      device_error_flag());
     MODE_LAUNCH_CHECK();
     return 0;
 }

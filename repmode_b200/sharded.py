@@ -194,7 +194,8 @@ class ShardedConvFunction(torch.autograd.Function):
             hp, wait_dy = comm.halo_push_desc(dy_ext, H2, tag + ".dy")
             _lib.check(lib.mode_bn_relu_bwd_apply_ex(*apply_args, ctypes.byref(pg), ctypes.byref(hp), Fm._stream()),
                        "mode_bn_relu_bwd_apply")
-            comm.halo_wait(wait_dy)
+            # the wait for the neighbours' dy planes is issued in front of K3, the only consumer of the dy halo: K4 reads the
+            # OWNED dy planes only, so the exchange's flight time and the rank skew hide behind it (r2v)
         else:
             _lib.check(lib.mode_bn_relu_bwd_reduce(Fm._p(y), Fm._p(doutn), m_rows, co, Fm._p(bn_w), Fm._p(bn_b), Fm._p(mean),
                                                    Fm._p(invstd), pl, Fm._p(ws), Fm._stream()), "mode_bn_relu_bwd_reduce")
@@ -205,9 +206,13 @@ class ShardedConvFunction(torch.autograd.Function):
         d_weff = Fm.conv3d_wgrad(x_ext, dy_int, dtype, 1, d, h, wd, ci, co, inv, halo=(d + 2 * H2, H2))
         dx = None
         dg_fork = Fm._Fork(dev, needs_dx)
+        if fused and not needs_dx:
+            comm.halo_wait(wait_dy)                     # nobody reads the halo, but the counter protocol still advances
         if needs_dx:
             dxn = torch.empty((1, d, h, wd, ci), dtype=torch.float32, device=dev)
             with dg_fork:
+                if fused:
+                    comm.halo_wait(wait_dy)
                 Fm.conv3d(dy_ext, dtype, w_dg, sample_u, 1, d, h, wd, co, ci, inv, None,
                           out_scale=(1.0 / Fm.W_SCALE_F16) if use_umma else 1.0, out=dxn, halo=(d + 2 * H2, H2))
         layer, _, _ = Fm._layer(k5, k3, k1, a3, a5, gate_w, gate_b)

@@ -223,6 +223,40 @@ def test_reparam_bwd_register_kernel_matches_slab_kernel(ci, co, n, monkeypatch)
     assert_close(got[5].cpu().numpy(), dgw.float().cpu().numpy(), 1e-4, "dgate_w vs closed form")
 
 
+@pytest.mark.parametrize("ci,co,n,dense", [(32, 32, 1, False), (64, 48, 20, False), (32, 80, 9, True), (96, 512, 4, False)])
+def test_gate_bwd_block_kernel_bit_identical_to_serial(ci, co, n, dense, monkeypatch):
+    """The block-form gate backward (32 channels per block, a warp per sample) against the one-thread-per-channel kernel:
+    same summation order, so dgate_w / dgate_b must be bit-identical -- task-id and dense gate inputs, Co not a multiple
+    of 32, batches beyond the 8-sample chunk."""
+    import ctypes
+    from repmode_b200 import functional as Fm, lib as L
+    from repmode_b200.nn_modules import MoDEConv
+    torch.manual_seed(9)
+    m = MoDEConv(5, 12, ci, co).cuda()
+    layer, ci, co = Fm._layer(*m._params())
+    lib = L.load()
+    ids = torch.randint(0, 12, (n,), generator=torch.Generator().manual_seed(n)).to("cuda", torch.int32)   # repeats inside a chunk
+    emb = torch.randn(n, 12, device="cuda")
+    sample_u = torch.arange(n, device="cuda", dtype=torch.int32)
+    g = torch.softmax(torch.randn(n, 5, co, device="cuda"), dim=1).contiguous()
+    d_weff = torch.randn(n, 125, co, ci, device="cuda")
+
+    def run():
+        outs = [torch.full_like(q, float("nan")) for q in m._params()]
+        ws = torch.empty(max(int(lib.mode_reparam_bwd_workspace_bytes(ci, co, n)), 16), dtype=torch.uint8, device="cuda")
+        L.check(lib.mode_reparam_bwd(ctypes.byref(layer), None if dense else Fm._p(ids), Fm._p(emb) if dense else None, n,
+                                     Fm._p(sample_u), n, Fm._p(g), Fm._p(d_weff), *[Fm._p(o) for o in outs], Fm._p(ws),
+                                     Fm._stream()), "mode_reparam_bwd")
+        torch.cuda.synchronize()
+        return outs
+    monkeypatch.setenv("REPMODE_GATE_BWD_SERIAL", "1")
+    ref = run()
+    monkeypatch.delenv("REPMODE_GATE_BWD_SERIAL")
+    got = run()
+    assert torch.equal(got[5], ref[5]) and torch.equal(got[6], ref[6])
+    assert bool(torch.isfinite(got[5]).all()) and bool(torch.isfinite(got[6]).all())
+
+
 def test_cast_f16_pad_matches_cast_then_pad():
     from repmode_b200 import functional as Fm
     x = torch.randn(2, 3, 8, 16, 1, device="cuda") * 3

@@ -86,6 +86,18 @@ int mode_debug_profile(void* buf);
 int mode_reparam_fwd(const mode_layer_t* layer_host, const int32_t* task_ids, const float* t_dense, int32_t U,
                      float* g_out, void* w_fwd, void* w_dgrad, mode_dtype_t w_dtype, float w_scale,
                      const float* w_scale_dev, void* stream);
+/* K1 for several layers in ONE launch (plus one grouped dgrad-pack launch): the layers of a U-Net step share the gate
+ * inputs (Net.forward hands the same t to every MoDEConv, RepMode.py:51-71).  fp16 packs only; every item needs
+ * Ci % 32 == 0 and Co % 32 == 0 (the stem / head layers go through mode_reparam_fwd); w_dgrad may be NULL per item. */
+#define MODE_REPARAM_GROUP_MAX 24
+typedef struct {
+    mode_layer_t layer;
+    float* g_out;        /* [U,5,Co] */
+    void* w_fwd;         /* U * mode_packed_weight_elems_f16(ci, co) halves */
+    void* w_dgrad;       /* U * mode_packed_weight_elems_f16(co, ci) halves, or NULL */
+} mode_reparam_item_t;
+int mode_reparam_fwd_grouped(const mode_reparam_item_t* items_host, int32_t n_items, const int32_t* task_ids,
+                             const float* t_dense, int32_t U, mode_dtype_t w_dtype, float w_scale, void* stream);
 int64_t mode_packed_weight_elems(int32_t k_channels, int32_t n_channels);       /* fp32 pack, per gate input u */
 /* fp16 pack: rows padded to a multiple of 32 too (pad rows are NOT written: zero-initialise when n % 32 != 0) */
 int64_t mode_packed_weight_elems_f16(int32_t k_channels, int32_t n_channels);
@@ -241,6 +253,22 @@ int mode_bn_relu_bwd_apply(const float* y, const float* dout, int64_t M, int32_t
                            const float* beta, const float* mean, const float* invstd, float* dgamma, float* dbeta,
                            float* dy, void* dy_f16, float* dy_scale2, const mode_planes_t* planes_host,
                            void* workspace, void* stream);
+
+/* Launch-structure forms (same arithmetic, fewer kernel boundaries on the critical path of a training step):
+ *   mode_bn_finalize_apply_relu:       mode_bn_finalize + mode_bn_apply_relu as ONE kernel -- every block derives scale / shift
+ *                                      from `sums` (M_stat = the statistics' divisor), block 0 writes mean / invstd / scale /
+ *                                      shift and updates the running statistics; y has M rows.
+ *   mode_bn_relu_bwd_reduce_prezeroed: mode_bn_relu_bwd_reduce for a workspace the caller has ALREADY zeroed (e.g. during the
+ *                                      forward, off the critical path): no memset in front of the reduction.
+ * mode_bn_relu_bwd_apply derives the fp16 scale of dy inside the apply kernel (no separate scale launch) unless a gather
+ * descriptor is given. */
+int mode_bn_finalize_apply_relu(const double* sums, int64_t M_stat, int32_t C, const float* gamma, const float* beta,
+                                float eps, float momentum, float* mean, float* invstd, float* scale, float* shift,
+                                float* running_mean, float* running_var, const float* y, int64_t M, int32_t relu,
+                                float* out, void* out_f16, float f16_scale, const mode_planes_t* planes_host, void* stream);
+int mode_bn_relu_bwd_reduce_prezeroed(const float* y, const float* dout, int64_t M, int32_t C, const float* gamma,
+                                      const float* beta, const float* mean, const float* invstd,
+                                      const mode_planes_t* planes_host, void* workspace, void* stream);
 
 /* Fused-exchange forms (peer memory, D-sharded slabs).  NULL descriptors give the plain behaviour.
  *   mode_bn_finalize_ex:        `gather` != NULL: the statistics are the rank-ordered sum of the gathered slots (sums ignored).

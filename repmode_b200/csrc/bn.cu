@@ -154,14 +154,46 @@ __global__ void bn_finalize_kernel(const double* __restrict__ sums, int64_t M, i
 // ---- apply: out = relu(y*scale + shift), optional fp16 copy ----------------------------------------------
 // Four independent 16-byte loads in flight per thread (one per thread leaves the SM far below the bytes-in-flight HBM
 // needs), and the tensor is walked BACKWARDS: K2 has just written y front to back, so its tail is what the L2 still holds.
+// With `fin.sums` the kernel FINALIZES the statistics itself (r2w): every block derives scale / shift of all C channels from
+// the fp64 sums (same arithmetic as bn_finalize_kernel, so the same bits), block 0 also writes mean / invstd / scale / shift
+// and updates the running statistics -- one kernel boundary less on the critical path of every training forward.
+struct BnFinalize {
+    const double* sums; long long M; const float* gamma; const float* beta; float eps, momentum;
+    float *mean, *invstd, *scale, *shift, *running_mean, *running_var;
+};
 template <bool PLANES>
 __global__ void __launch_bounds__(BN_THREADS) bn_apply_kernel(const float* __restrict__ y, int64_t total, int C,
                                                               const float* __restrict__ scale,
                                                               const float* __restrict__ shift, int relu,
                                                               float* __restrict__ out, __half* __restrict__ out16,
-                                                              float f16_scale, Planes pl) {
+                                                              float f16_scale, Planes pl, BnFinalize fin) {
     __shared__ float ssc[BN_MAXC], ssh[BN_MAXC];
-    for (int i = threadIdx.x; i < C; i += BN_THREADS) { ssc[i] = scale[i]; ssh[i] = shift[i]; }
+    if (fin.sums != nullptr) {
+        for (int c = threadIdx.x; c < C; c += BN_THREADS) {
+            const double s1 = fin.sums[c], s2 = fin.sums[C + c];
+            const double m = s1 / (double)fin.M;
+            double var = s2 / (double)fin.M - m * m;
+            if (var < 0) var = 0;
+            const float is = (float)(1.0 / sqrt(var + (double)fin.eps));
+            const float ga = fin.gamma ? fin.gamma[c] : 1.f, be = fin.beta ? fin.beta[c] : 0.f;
+            const float sc = ga * is;
+            const float sh = be - (float)m * sc;
+            ssc[c] = sc; ssh[c] = sh;
+            if (blockIdx.x == 0) {
+                if (fin.mean) fin.mean[c] = (float)m;
+                if (fin.invstd) fin.invstd[c] = is;
+                if (fin.scale) fin.scale[c] = sc;
+                if (fin.shift) fin.shift[c] = sh;
+                if (fin.running_mean) fin.running_mean[c] = (1.f - fin.momentum) * fin.running_mean[c] + fin.momentum * (float)m;
+                if (fin.running_var) {
+                    const double unb = fin.M > 1 ? var * (double)fin.M / (double)(fin.M - 1) : var;
+                    fin.running_var[c] = (1.f - fin.momentum) * fin.running_var[c] + fin.momentum * (float)unb;
+                }
+            }
+        }
+    } else {
+        for (int i = threadIdx.x; i < C; i += BN_THREADS) { ssc[i] = scale[i]; ssh[i] = shift[i]; }
+    }
     __syncthreads();
     const int64_t nvec = total >> 2;
     const int64_t stride = (int64_t)gridDim.x * BN_THREADS;
@@ -376,21 +408,46 @@ __global__ void __launch_bounds__(BN_THREADS, 4) bn_bwd_apply_vec_kernel(const f
                                                                          const double* __restrict__ red,
                                                                          float* __restrict__ dgamma, float* __restrict__ dbeta,
                                                                          float* __restrict__ dy, __half* __restrict__ dy16,
-                                                                         const float* __restrict__ scale2, Planes pl,
-                                                                         long long m_div, HaloPush hp) {
-    const float f16_scale = (dy16 != nullptr && scale2 != nullptr) ? scale2[0] : 1.f;
+                                                                         float* __restrict__ scale2, Planes pl,
+                                                                         long long m_div, HaloPush hp,
+                                                                         const double* __restrict__ mx_own) {
+    // mx_own != nullptr (r2w): the power-of-two fp16 scale of dy is derived HERE, by every block, from the per-channel
+    // bound of bn_bwd_scale_kernel (same expression, same bits); block 0 publishes {scale, 1/scale} for K3 / K4.  Saves the
+    // one-block scale kernel and its boundary on the critical path of every training backward.
     __shared__ float smu[BN_MAXC], sis[BN_MAXC], sga[BN_MAXC], sbe[BN_MAXC], sa[BN_MAXC], sb[BN_MAXC];
+    __shared__ float s_bound[BN_THREADS];
+    float bnd = 0.f;
     for (int c = threadIdx.x; c < C; c += BN_THREADS) {
         smu[c] = mean[c]; sis[c] = invstd[c];
         sga[c] = gamma ? gamma[c] : 1.f; sbe[c] = beta ? beta[c] : 0.f;
         sa[c] = (float)(red[c] / (double)m_div);
         sb[c] = (float)(red[C + c] / (double)m_div);
+        if (mx_own != nullptr)
+            bnd = fmaxf(bnd, fabsf(sga[c] * sis[c]) * ((float)mx_own[c] + fabsf(sa[c]) + (float)mx_own[C + c] * fabsf(sb[c])));
         if (blockIdx.x == 0) {
             if (dbeta) dbeta[c] = (float)red[c];
             if (dgamma) dgamma[c] = (float)red[C + c];
         }
     }
-    __syncthreads();
+    float f16_scale = 1.f;
+    if (mx_own != nullptr) {
+        s_bound[threadIdx.x] = bnd;
+        __syncthreads();
+        for (int st = BN_THREADS / 2; st > 0; st >>= 1) {
+            if (threadIdx.x < st) s_bound[threadIdx.x] = fmaxf(s_bound[threadIdx.x], s_bound[threadIdx.x + st]);
+            __syncthreads();
+        }
+        const float bound = s_bound[0];
+        if (bound > 0.f && isfinite(bound)) {
+            int e = (int)floorf(log2f(8192.f / bound));
+            e = max(-60, min(60, e));
+            f16_scale = exp2f((float)e);
+        }
+        if (blockIdx.x == 0 && threadIdx.x == 0) { scale2[0] = f16_scale; scale2[1] = 1.f / f16_scale; }
+    } else {
+        if (dy16 != nullptr && scale2 != nullptr) f16_scale = scale2[0];
+        __syncthreads();
+    }
     const int64_t nvec = (M * C) >> 2;
     const int64_t stride = (int64_t)gridDim.x * BN_THREADS;
     for (int64_t k = (int64_t)blockIdx.x * BN_THREADS + threadIdx.x; k < nvec; k += 2 * stride) {
@@ -655,11 +712,9 @@ extern "C" int mode_bn_finalize(const double* sums, int64_t M, int32_t C, const 
                                running_var, nullptr, stream);
 }
 
-extern "C" int mode_bn_apply_relu(const float* y, int64_t M, int32_t C, const float* scale, const float* shift,
-                                  int32_t relu, float* out, void* out_f16, float f16_scale,
-                                  const mode_planes_t* planes, void* stream) {
-    if (!y || !scale || !shift || (!out && !out_f16) || M <= 0 || C <= 0 || C > BN_MAXC)
-        MODE_FAIL("mode_bn_apply_relu: bad arguments (C=%d)", C);
+static int bn_apply_launch(const float* y, int64_t M, int32_t C, const float* scale, const float* shift, int32_t relu,
+                           float* out, void* out_f16, float f16_scale, const mode_planes_t* planes, const BnFinalize& fin,
+                           void* stream) {
     cudaStream_t st = (cudaStream_t)stream;
     const int64_t total = M * C;
     const bool aligned = ((reinterpret_cast<uintptr_t>(y) | reinterpret_cast<uintptr_t>(out)) & 15) == 0 &&
@@ -668,12 +723,21 @@ extern "C" int mode_bn_apply_relu(const float* y, int64_t M, int32_t C, const fl
         const int64_t want = ceil_div(total / 4, BN_THREADS * 4);
         if (planes && !planes_trivial(planes))
             bn_apply_kernel<true><<<wave_grid(bn_apply_kernel<true>, BN_THREADS, want), BN_THREADS, 0, st>>>(y, total, C, scale, shift, relu, out, (__half*)out_f16,
-                                                               f16_scale, to_planes(planes));
+                                                               f16_scale, to_planes(planes), fin);
         else
             bn_apply_kernel<false><<<wave_grid(bn_apply_kernel<false>, BN_THREADS, want), BN_THREADS, 0, st>>>(y, total, C, scale, shift, relu, out, (__half*)out_f16,
-                                                                f16_scale, Planes{});
+                                                                f16_scale, Planes{}, fin);
     } else {
         if (planes) MODE_FAIL("mode_bn_apply_relu: plane ranges need C %% 4 == 0 and 16-byte aligned tensors");
+        if (fin.sums != nullptr) {                 // scalar layout: finalize as its own launch
+            bn_finalize_kernel<<<(unsigned)ceil_div(C, 128), 128, 0, st>>>(fin.sums, fin.M, C, fin.gamma, fin.beta, fin.eps,
+                                                                           fin.momentum, fin.mean, fin.invstd, fin.scale,
+                                                                           fin.shift, fin.running_mean, fin.running_var,
+                                                                           PeerGather{nullptr, 0, nullptr, nullptr},
+                                                                           device_error_flag());
+            MODE_LAUNCH_CHECK();
+            scale = fin.scale; shift = fin.shift;
+        }
         bn_apply_scalar_kernel<<<stream_grid(total, BN_THREADS * 4), BN_THREADS, 0, st>>>(
             y, total, C, scale, shift, relu, out, (__half*)out_f16, f16_scale);
     }
@@ -681,14 +745,33 @@ extern "C" int mode_bn_apply_relu(const float* y, int64_t M, int32_t C, const fl
     return 0;
 }
 
+extern "C" int mode_bn_apply_relu(const float* y, int64_t M, int32_t C, const float* scale, const float* shift,
+                                  int32_t relu, float* out, void* out_f16, float f16_scale,
+                                  const mode_planes_t* planes, void* stream) {
+    if (!y || !scale || !shift || (!out && !out_f16) || M <= 0 || C <= 0 || C > BN_MAXC)
+        MODE_FAIL("mode_bn_apply_relu: bad arguments (C=%d)", C);
+    return bn_apply_launch(y, M, C, scale, shift, relu, out, out_f16, f16_scale, planes, BnFinalize{}, stream);
+}
+
+extern "C" int mode_bn_finalize_apply_relu(const double* sums, int64_t M_stat, int32_t C, const float* gamma,
+                                           const float* beta, float eps, float momentum, float* mean, float* invstd,
+                                           float* scale, float* shift, float* running_mean, float* running_var,
+                                           const float* y, int64_t M, int32_t relu, float* out, void* out_f16,
+                                           float f16_scale, const mode_planes_t* planes, void* stream) {
+    if (!sums || !scale || !shift || !y || (!out && !out_f16) || M <= 0 || M_stat <= 0 || C <= 0 || C > BN_MAXC)
+        MODE_FAIL("mode_bn_finalize_apply_relu: bad arguments (C=%d)", C);
+    BnFinalize fin{sums, (long long)M_stat, gamma, beta, eps, momentum, mean, invstd, scale, shift, running_mean, running_var};
+    return bn_apply_launch(y, M, C, scale, shift, relu, out, out_f16, f16_scale, planes, fin, stream);
+}
+
 // {sum dz, sum dz*xhat}[C] then {max |dz|, max |xhat|}[C], ALL doubles: one contiguous fp64 vector a D-sharded caller can
 // all-reduce (sum) in one step -- the sum of the ranks' maxima bounds the global maximum, which is all the fp16 scale needs
 extern "C" int64_t mode_bn_bwd_workspace_bytes(int32_t C) { return (int64_t)C * 4 * sizeof(double); }
 
-extern "C" int mode_bn_relu_bwd_reduce_ex(const float* y, const float* dout, int64_t M, int32_t C, const float* gamma,
-                                          const float* beta, const float* mean, const float* invstd,
-                                          const mode_planes_t* planes, void* workspace_v, const mode_peer_push_t* push,
-                                          void* stream) {
+static int bn_bwd_reduce_launch(const float* y, const float* dout, int64_t M, int32_t C, const float* gamma,
+                                const float* beta, const float* mean, const float* invstd,
+                                const mode_planes_t* planes, void* workspace_v, const mode_peer_push_t* push,
+                                bool workspace_is_zero, void* stream) {
     if (!y || !dout || !mean || !invstd || !workspace_v || M <= 0 || C <= 0 || C > BN_MAXC)
         MODE_FAIL("mode_bn_relu_bwd_reduce: bad arguments (C=%d)", C);
     const PeerPush pp = to_peer_push(push);
@@ -696,7 +779,7 @@ extern "C" int mode_bn_relu_bwd_reduce_ex(const float* y, const float* dout, int
     cudaStream_t st = (cudaStream_t)stream;
     double* workspace = (double*)workspace_v;
     long long* mx = (long long*)(workspace + 2 * (size_t)C);
-    MODE_CUDA(cudaMemsetAsync(workspace_v, 0, (size_t)mode_bn_bwd_workspace_bytes(C), st));
+    if (!workspace_is_zero) MODE_CUDA(cudaMemsetAsync(workspace_v, 0, (size_t)mode_bn_bwd_workspace_bytes(C), st));
     const int vpr = C >> 2;
     const bool aligned = ((reinterpret_cast<uintptr_t>(y) | reinterpret_cast<uintptr_t>(dout)) & 15) == 0;
     if ((C & 3) == 0 && vpr <= BN_THREADS && BN_THREADS % vpr == 0 && aligned) {
@@ -718,10 +801,24 @@ extern "C" int mode_bn_relu_bwd_reduce_ex(const float* y, const float* dout, int
     return 0;
 }
 
+extern "C" int mode_bn_relu_bwd_reduce_ex(const float* y, const float* dout, int64_t M, int32_t C, const float* gamma,
+                                          const float* beta, const float* mean, const float* invstd,
+                                          const mode_planes_t* planes, void* workspace_v, const mode_peer_push_t* push,
+                                          void* stream) {
+    return bn_bwd_reduce_launch(y, dout, M, C, gamma, beta, mean, invstd, planes, workspace_v, push, false, stream);
+}
+
 extern "C" int mode_bn_relu_bwd_reduce(const float* y, const float* dout, int64_t M, int32_t C, const float* gamma,
                                        const float* beta, const float* mean, const float* invstd,
                                        const mode_planes_t* planes, void* workspace_v, void* stream) {
-    return mode_bn_relu_bwd_reduce_ex(y, dout, M, C, gamma, beta, mean, invstd, planes, workspace_v, nullptr, stream);
+    return bn_bwd_reduce_launch(y, dout, M, C, gamma, beta, mean, invstd, planes, workspace_v, nullptr, false, stream);
+}
+
+extern "C" int mode_bn_relu_bwd_reduce_prezeroed(const float* y, const float* dout, int64_t M, int32_t C,
+                                                 const float* gamma, const float* beta, const float* mean,
+                                                 const float* invstd, const mode_planes_t* planes, void* workspace_v,
+                                                 void* stream) {
+    return bn_bwd_reduce_launch(y, dout, M, C, gamma, beta, mean, invstd, planes, workspace_v, nullptr, true, stream);
 }
 
 extern "C" int mode_bn_relu_bwd_apply_ex(const float* y, const float* dout, int64_t M, int32_t C, const float* gamma,
@@ -740,26 +837,29 @@ extern "C" int mode_bn_relu_bwd_apply_ex(const float* y, const float* dout, int6
     const HaloPush hp = to_halo_push(halo);
     if (g.on() && (g.world <= 0 || !g.signal || !g.expect)) MODE_FAIL("mode_bn_relu_bwd_apply: incomplete gather descriptor");
     if (hp.on() && (hp.bytes <= 0 || (hp.bytes & 15) || !hp.ticket)) MODE_FAIL("mode_bn_relu_bwd_apply: bad halo descriptor");
-    if (dy_f16 || g.on()) {
+    const bool aligned = ((reinterpret_cast<uintptr_t>(y) | reinterpret_cast<uintptr_t>(dout)) & 15) == 0;
+    const bool vec_ok = (C & 3) == 0 && aligned && ((reinterpret_cast<uintptr_t>(dy) & 15) == 0) &&
+                        ((reinterpret_cast<uintptr_t>(dy_f16) & 7) == 0);
+    // the apply kernel derives the fp16 scale itself unless the sums still have to be gathered from the other ranks
+    const bool scale_in_kernel = vec_ok && dy_f16 != nullptr && !g.on() && getenv("REPMODE_BN_SCALE_KERNEL") == nullptr;
+    const double* mx_own = scale_in_kernel ? mx : nullptr;
+    if ((dy_f16 || g.on()) && !scale_in_kernel) {
         int* ef = device_error_flag();
         if (!ef) MODE_FAIL("mode_bn_relu_bwd_apply: could not allocate the device error flag");
         bn_bwd_scale_kernel<<<1, 256, 0, st>>>(workspace, mx, m_div, C, gamma, invstd, 8192.f, dy_f16 ? dy_scale2 : nullptr,
                                                g, ef);
         MODE_LAUNCH_CHECK();
     }
-    const bool aligned = ((reinterpret_cast<uintptr_t>(y) | reinterpret_cast<uintptr_t>(dout)) & 15) == 0;
-    const bool vec_ok = (C & 3) == 0 && aligned && ((reinterpret_cast<uintptr_t>(dy) & 15) == 0) &&
-                        ((reinterpret_cast<uintptr_t>(dy_f16) & 7) == 0);
     if (vec_ok) {
         const int64_t want = ceil_div(M * C / 4, BN_THREADS * 2);
         if (planes && !planes_trivial(planes))
             bn_bwd_apply_vec_kernel<true><<<wave_grid(bn_bwd_apply_vec_kernel<true>, BN_THREADS, want), BN_THREADS, 0, st>>>(y, dout, M, C, gamma, beta, mean, invstd, workspace,
                                                                        dgamma, dbeta, dy, (__half*)dy_f16, dy_scale2,
-                                                                       to_planes(planes), m_div, hp);
+                                                                       to_planes(planes), m_div, hp, mx_own);
         else
             bn_bwd_apply_vec_kernel<false><<<wave_grid(bn_bwd_apply_vec_kernel<false>, BN_THREADS, want), BN_THREADS, 0, st>>>(y, dout, M, C, gamma, beta, mean, invstd,
                                                                         workspace, dgamma, dbeta, dy, (__half*)dy_f16,
-                                                                        dy_scale2, Planes{}, m_div, hp);
+                                                                        dy_scale2, Planes{}, m_div, hp, mx_own);
     } else {
         if (planes) MODE_FAIL("mode_bn_relu_bwd_apply: plane ranges need C %% 4 == 0 and 16-byte aligned tensors");
         if (hp.on()) MODE_FAIL("mode_bn_relu_bwd_apply: the fused halo push needs C %% 4 == 0 and 16-byte aligned tensors");

@@ -158,18 +158,18 @@ template <> __device__ __forceinline__ int pack_tap_offset<__half>(int tap, int 
 constexpr int K1R_ROWS = 2;
 constexpr int K1R_MAXU = 32;          // gate inputs per launch the row-block kernel takes (more -> the per-slice kernel)
 template <typename OutT>
-__global__ void __launch_bounds__(256, 4) reparam_fwd_rows_kernel(mode_layer_t L, const int32_t* __restrict__ task_ids,
-                                                               const float* __restrict__ t_dense, int U,
-                                                               float* __restrict__ g_out, OutT* __restrict__ w_fwd,
-                                                               float w_scale, const float* __restrict__ w_scale_dev,
-                                                               int rows_pad, int* err) {
+__device__ __forceinline__ void reparam_rows_body(const mode_layer_t& L, const int32_t* __restrict__ task_ids,
+                                                  const float* __restrict__ t_dense, int U, float* __restrict__ g_out,
+                                                  OutT* __restrict__ w_fwd, float w_scale,
+                                                  const float* __restrict__ w_scale_dev, int rows_pad, int* err,
+                                                  const int row_block, const int chunk, const int nci) {
     __shared__ __align__(16) float s5[K1R_ROWS * 32 * 125];
     __shared__ __align__(16) float s3[K1R_ROWS * 32 * 27];
     __shared__ __align__(16) float s1[3 * K1R_ROWS * 32];     // k1, a3, a5
     __shared__ float sg[K1R_MAXU * K1R_ROWS * MODE_NUM_EXPERTS];
     __shared__ int s_tapoff[125];          // per tap: offset inside one gate input's pack (row 0, column 0)
     __shared__ int s_t3[125];              // per tap: index into the 3^3 expert, -1 outside the inner 3^3
-    const int o0 = blockIdx.x * K1R_ROWS, ic = blockIdx.y;
+    const int o0 = row_block * K1R_ROWS, ic = chunk;
     const int Ci = L.ci, Co = L.co, T = L.num_tasks;
     const int tid = threadIdx.x;
     // r2l ncu (512 -> 512): issue slots 76 % busy, DRAM 23 % -- the mix loop was INSTRUCTION bound (tap -> kd/kh/kw divisions
@@ -178,7 +178,7 @@ __global__ void __launch_bounds__(256, 4) reparam_fwd_rows_kernel(mode_layer_t L
         const int kd = tid / 25, kh = (tid / 5) % 5, kw = tid % 5;
         const bool inner = (kd >= 1 && kd <= 3 && kh >= 1 && kh <= 3 && kw >= 1 && kw <= 3);
         s_t3[tid] = inner ? ((kd - 1) * 3 + (kh - 1)) * 3 + (kw - 1) : -1;
-        s_tapoff[tid] = pack_tap_offset<OutT>(tid, ic, gridDim.y, rows_pad);
+        s_tapoff[tid] = pack_tap_offset<OutT>(tid, ic, nci, rows_pad);
     }
     // ---- load phase: contiguous slabs, 16-byte loads, all issued before the first use; the gate softmax of every
     // (gate input, row) runs on the threads at the END of the block while those loads are in flight (its dependent global
@@ -238,7 +238,6 @@ __global__ void __launch_bounds__(256, 4) reparam_fwd_rows_kernel(mode_layer_t L
     }
     if (w_scale_dev != nullptr) w_scale *= *w_scale_dev;
     const float c3 = 1.0f / 27, c5 = 1.0f / 125;               // fp32-rounded pool constants (RepMode.py:161-163)
-    const int nci = gridDim.y;
     __syncthreads();                                           // slabs and gates landed
     for (int u = 0; u < U; ++u) {
         // mix + pack: a warp owns whole taps (tap = warp, warp + 8, ...), its lanes the 32 columns; the shared-memory reads
@@ -275,6 +274,49 @@ __global__ void __launch_bounds__(256, 4) reparam_fwd_rows_kernel(mode_layer_t L
     }
 }
 
+template <typename OutT>
+__global__ void __launch_bounds__(256, 4) reparam_fwd_rows_kernel(mode_layer_t L, const int32_t* __restrict__ task_ids,
+                                                               const float* __restrict__ t_dense, int U,
+                                                               float* __restrict__ g_out, OutT* __restrict__ w_fwd,
+                                                               float w_scale, const float* __restrict__ w_scale_dev,
+                                                               int rows_pad, int* err) {
+    reparam_rows_body<OutT>(L, task_ids, t_dense, U, g_out, w_fwd, w_scale, w_scale_dev, rows_pad, err, (int)blockIdx.x,
+                            (int)blockIdx.y, (int)gridDim.y);
+}
+
+// K1 for SEVERAL layers in one launch ("a single grouped launch, not 19x"): the per-layer descriptors
+// travel as a __grid_constant__ kernel parameter; a block finds its layer from the cumulative block counts and runs the
+// row-block body above on it.  All layers share the gate inputs of the step (Net.forward passes the same t to every
+// MoDEConv, RepMode.py:51-71).  The 17 row-eligible layers of the U-Net are 4 000 - 70 000 blocks of identical shape: the
+// 7 us latency floor of the narrow layers disappears into the wide ones.
+struct K1GroupItem {
+    mode_layer_t L;
+    float* g_out;
+    void* w_fwd;
+    void* w_dgrad;
+    int rows_pad;              // fwd pack rows (co padded to 32)
+    int block_begin;           // first block of this layer in the grouped K1 grid
+    long long tile_begin;      // first 32x32 tile of this layer in the grouped dgrad-pack grid
+};
+struct K1Group {
+    int n;
+    K1GroupItem it[MODE_REPARAM_GROUP_MAX];
+};
+template <typename OutT>
+__global__ void __launch_bounds__(256, 4) reparam_fwd_rows_grouped_kernel(const __grid_constant__ K1Group G,
+                                                                       const int32_t* __restrict__ task_ids,
+                                                                       const float* __restrict__ t_dense, int U,
+                                                                       float w_scale, int* err) {
+    const int b = (int)blockIdx.x;
+    int k = 0;
+    while (k + 1 < G.n && b >= G.it[k + 1].block_begin) ++k;
+    const K1GroupItem& it = G.it[k];
+    const int local = b - it.block_begin;
+    const int row_blocks = it.L.co / K1R_ROWS;
+    reparam_rows_body<OutT>(it.L, task_ids, t_dense, U, it.g_out, (OutT*)it.w_fwd, w_scale, nullptr, it.rows_pad, err,
+                            local % row_blocks, local / row_blocks, it.L.ci / 32);
+}
+
 // fwd pack (rows = co, k = ci)  ->  dgrad pack (tap -> 124-tap, rows = ci, k = co)
 // grid (ceil(Ci/32), ceil(Co/32), U*125), block (32, 8)
 template <typename T>
@@ -305,32 +347,37 @@ __global__ void __launch_bounds__(256) pack_dgrad_kernel(const T* __restrict__ s
 // 256 threads PD_TILES tiles with all of its loads in flight before the first use.  Pad rows / columns of the source are
 // zero (the caller zero-initialises padded packs), so whole tiles are moved blindly.  grid ceil(n_tiles / PD_TILES).
 constexpr int PD_TILES = 8;
-__global__ void __launch_bounds__(256) pack_dgrad_h16_kernel(const __half* __restrict__ src, __half* __restrict__ dst,
-                                                             int nci, int nco, int src_rows_pad, int dst_rows_pad,
-                                                             long long n_tiles) {
+struct PdLayer {                 // one layer's packs as the tile mover sees them
+    const __half* src; __half* dst;
+    int nci, nco, src_rows_pad, dst_rows_pad;
+};
+template <typename Locate>
+__device__ __forceinline__ void pack_dgrad_h16_body(const Locate& locate, long long n_tiles) {
     __shared__ __align__(16) __half tile[PD_TILES][32][34];       // [ci][o], 68-byte rows (4-byte aligned, odd word stride)
     const int tid = threadIdx.x, grp = tid >> 7, j = tid & 127;
     const int r = j >> 2, pc = j & 3;
     const int lc = pc ^ ((r >> 1) & 3);                           // logical 8-column chunk behind physical chunk pc of row r
     const long long t0 = (long long)blockIdx.x * PD_TILES;
     uint4 v[PD_TILES / 2];
-    size_t dbase[PD_TILES / 2];
+    __half* dptr[PD_TILES / 2];
 #pragma unroll
     for (int k = 0; k < PD_TILES / 2; ++k) {
-        const long long tl = t0 + 2 * k + grp;
+        const long long tg = t0 + 2 * k + grp;
         v[k] = make_uint4(0u, 0u, 0u, 0u);
-        dbase[k] = 0;
-        if (tl < n_tiles) {
-            const int oc = (int)(tl % nco);
-            long long q = tl / nco;
-            const int ic = (int)(q % nci);
-            q /= nci;
+        dptr[k] = nullptr;
+        if (tg < n_tiles) {
+            PdLayer P;
+            const long long tl = locate(tg, P);                   // tile index inside its layer
+            const int oc = (int)(tl % P.nco);
+            long long q = tl / P.nco;
+            const int ic = (int)(q % P.nci);
+            q /= P.nci;
             const int tap = (int)(q % 125), u = (int)(q / 125);
             const int kd = tap / 25, t = tap - kd * 25;
-            const size_t sbase = (((((size_t)u * nci + ic) * 25 + t) * 5 + (4 - kd)) * src_rows_pad + (size_t)oc * 32) * MODE_KC;
+            const size_t sbase = (((((size_t)u * P.nci + ic) * 25 + t) * 5 + (4 - kd)) * P.src_rows_pad + (size_t)oc * 32) * MODE_KC;
             // destination tap 124 - tap = (4 - kd, 24 - t): its block index inside the stage is 4 - (4 - kd) = kd
-            dbase[k] = (((((size_t)u * nco + oc) * 25 + (24 - t)) * 5 + kd) * dst_rows_pad + (size_t)ic * 32) * MODE_KC;
-            v[k] = *reinterpret_cast<const uint4*>(src + sbase + r * 32 + pc * 8);
+            dptr[k] = P.dst + (((((size_t)u * P.nco + oc) * 25 + (24 - t)) * 5 + kd) * P.dst_rows_pad + (size_t)ic * 32) * MODE_KC;
+            v[k] = *reinterpret_cast<const uint4*>(P.src + sbase + r * 32 + pc * 8);
         }
     }
 #pragma unroll
@@ -342,11 +389,34 @@ __global__ void __launch_bounds__(256) pack_dgrad_h16_kernel(const __half* __res
     __syncthreads();
 #pragma unroll
     for (int k = 0; k < PD_TILES / 2; ++k) {
-        const long long tl = t0 + 2 * k + grp;
-        if (tl >= n_tiles) continue;
+        if (dptr[k] == nullptr) continue;
         const uint32_t* w = reinterpret_cast<const uint32_t*>(&tile[2 * k + grp][r][lc * 8]);   // dest row ci = r, cols o
-        *reinterpret_cast<uint4*>(dst + dbase[k] + r * 32 + pc * 8) = make_uint4(w[0], w[1], w[2], w[3]);
+        *reinterpret_cast<uint4*>(dptr[k] + r * 32 + pc * 8) = make_uint4(w[0], w[1], w[2], w[3]);
     }
+}
+struct PdSingleLocate {
+    PdLayer P;
+    __device__ __forceinline__ long long operator()(long long tg, PdLayer& out) const { out = P; return tg; }
+};
+__global__ void __launch_bounds__(256) pack_dgrad_h16_kernel(const __half* __restrict__ src, __half* __restrict__ dst,
+                                                             int nci, int nco, int src_rows_pad, int dst_rows_pad,
+                                                             long long n_tiles) {
+    pack_dgrad_h16_body(PdSingleLocate{PdLayer{src, dst, nci, nco, src_rows_pad, dst_rows_pad}}, n_tiles);
+}
+// the same over the layers of a K1 group (one launch; a block's tiles may belong to two neighbouring layers)
+struct PdGroupLocate {
+    const K1Group* G;
+    __device__ __forceinline__ long long operator()(long long tg, PdLayer& out) const {
+        int k = 0;
+        while (k + 1 < G->n && tg >= G->it[k + 1].tile_begin) ++k;
+        const K1GroupItem& it = G->it[k];
+        const int nci = it.L.ci / 32, nco = it.L.co / 32;
+        out = PdLayer{(const __half*)it.w_fwd, (__half*)it.w_dgrad, nci, nco, nco * 32, nci * 32};
+        return tg - it.tile_begin;
+    }
+};
+__global__ void __launch_bounds__(256) pack_dgrad_h16_grouped_kernel(const __grid_constant__ K1Group G, long long n_tiles) {
+    pack_dgrad_h16_body(PdGroupLocate{&G}, n_tiles);
 }
 
 // K1b main kernel. grid (ceil(Ci/32), Co), block 128 -- the ci chunk is the FAST grid index, so blocks that run together
@@ -1011,6 +1081,48 @@ extern "C" int mode_reparam_fwd(const mode_layer_t* L, const int32_t* task_ids, 
         }
     } else {
         MODE_FAIL("mode_reparam_fwd: unknown dtype %d", (int)w_dtype);
+    }
+    return 0;
+}
+
+extern "C" int mode_reparam_fwd_grouped(const mode_reparam_item_t* items, int32_t n_items, const int32_t* task_ids,
+                                        const float* t_dense, int32_t U, mode_dtype_t w_dtype, float w_scale,
+                                        void* stream) {
+    if (!items || n_items <= 0 || n_items > MODE_REPARAM_GROUP_MAX || U <= 0 || U > K1R_MAXU)
+        MODE_FAIL("mode_reparam_fwd_grouped: bad arguments (n_items=%d, U=%d)", n_items, U);
+    if ((task_ids == nullptr) == (t_dense == nullptr))
+        MODE_FAIL("mode_reparam_fwd_grouped: pass exactly one of task_ids / t_dense");
+    if (w_dtype != MODE_F16) MODE_FAIL("mode_reparam_fwd_grouped: fp16 packs only (the tensor-core path)");
+    K1Group G;
+    G.n = n_items;
+    long long blocks = 0, tiles = 0;
+    bool any_dgrad = false;
+    for (int k = 0; k < n_items; ++k) {
+        const mode_reparam_item_t& s = items[k];
+        const mode_layer_t& L = s.layer;
+        if (L.ci <= 0 || L.co <= 0 || L.num_tasks <= 0 || L.ci % 32 != 0 || L.co % 32 != 0 || !s.w_fwd)
+            MODE_FAIL("mode_reparam_fwd_grouped: item %d: needs Ci %% 32 == 0, Co %% 32 == 0 and a w_fwd buffer", k);
+        if (((reinterpret_cast<uintptr_t>(L.k5) | reinterpret_cast<uintptr_t>(L.k3) | reinterpret_cast<uintptr_t>(s.w_fwd) |
+              reinterpret_cast<uintptr_t>(s.w_dgrad)) & 15) != 0)
+            MODE_FAIL("mode_reparam_fwd_grouped: item %d: experts and packs must be 16-byte aligned", k);
+        K1GroupItem& it = G.it[k];
+        it.L = L; it.g_out = s.g_out; it.w_fwd = s.w_fwd; it.w_dgrad = s.w_dgrad;
+        it.rows_pad = L.co;                          // Co % 32 == 0: no padding rows
+        it.block_begin = (int)blocks;
+        it.tile_begin = tiles;
+        blocks += (long long)(L.co / K1R_ROWS) * (L.ci / 32);
+        if (s.w_dgrad) { tiles += (long long)U * 125 * (L.ci / 32) * (L.co / 32); any_dgrad = true; }
+        if (blocks > 0x7fffffffLL) MODE_FAIL("mode_reparam_fwd_grouped: too many blocks");
+    }
+    // layers without a dgrad pack (no input gradient wanted) own an empty tile range: tile_begin of the next layer equals
+    // theirs, and the locate loop (">= next begin") skips them
+    cudaStream_t st = (cudaStream_t)stream;
+    reparam_fwd_rows_grouped_kernel<__half><<<(unsigned)blocks, 256, 0, st>>>(G, task_ids, t_dense, U, w_scale,
+                                                                             device_error_flag());
+    MODE_LAUNCH_CHECK();
+    if (any_dgrad) {
+        pack_dgrad_h16_grouped_kernel<<<(unsigned)ceil_div(tiles, PD_TILES), 256, 0, st>>>(G, tiles);
+        MODE_LAUNCH_CHECK();
     }
     return 0;
 }

@@ -145,9 +145,10 @@ W_SCALE_F16 = 256.0     # fixed power-of-two scale of the fp16 weight pack: |W_e
                         # 2^-8 * 6e-5 = 2.4e-7 in absolute resolution; no per-call amax pass over the experts
 
 
-def reparam_fwd(layer, gate_in, U, ci, co, dtype, want_dgrad, w_scale=1.0, fork=None):
+def reparam_fwd(layer, gate_in, U, ci, co, dtype, want_dgrad, w_scale=1.0, fork=None, post=None):
     """K1. Returns g [U,5,Co], w_fwd, w_dgrad (packed, see header).  With `fork` (a _Fork) the kernels are launched
-    on the side stream (outputs are still allocated on the caller's stream); the caller joins before using them."""
+    on the side stream (outputs are still allocated on the caller's stream); the caller joins before using them.
+    `post()` runs inside the fork after the K1 launches (small independent work kept off the caller's stream)."""
     lib = _lib.load()
     dev = gate_in.device
     tdt = torch.float16 if dtype == _lib.MODE_F16 else torch.float32
@@ -167,8 +168,12 @@ def reparam_fwd(layer, gate_in, U, ci, co, dtype, want_dgrad, w_scale=1.0, fork=
     if fork is not None:
         with fork:
             launch()
+            if post is not None:
+                post()
     else:
         launch()
+        if post is not None:
+            post()
     return g, w_fwd, w_dg
 
 
@@ -285,6 +290,26 @@ def cast_f16_pad(x, c_pad):
     return out
 
 
+_sample_index_cache = {}
+
+
+def _sample_index(n, dev, identity):
+    """arange(n) (train: sample i uses weight slot i) or zeros(n) (eval: everybody uses slot 0) as int32 -- constants, cached
+    per (n, device) so that no arange / fill launch sits in front of every layer.  Never cached from inside a CUDA-graph
+    capture (the tensor would live in the graph's private pool)."""
+    make = lambda: (torch.arange(n, dtype=torch.int32, device=dev) if identity  # noqa: E731
+                    else torch.zeros(n, dtype=torch.int32, device=dev))
+    if dev.type != "cuda":
+        return make()
+    key = (n, dev.index if dev.index is not None else torch.cuda.current_device(), identity)
+    t = _sample_index_cache.get(key)
+    if t is None:
+        t = make()
+        if not torch.cuda.is_current_stream_capturing():
+            _sample_index_cache[key] = t
+    return t
+
+
 class ModeConvFunction(torch.autograd.Function):
     """MoDEConv.forward as one autograd node.
 
@@ -297,7 +322,7 @@ class ModeConvFunction(torch.autograd.Function):
     @torch.amp.custom_fwd(device_type="cuda", cast_inputs=torch.float32)
     @_on_device_of_first
     def forward(ctx, x, gate_in, k5, k3, k1, a3, a5, gate_w, gate_b, bn_w, bn_b, running_mean, running_var, training,
-                conv_type, precision, shard=None, eps=BN_EPS, momentum=BN_MOMENTUM):
+                conv_type, precision, shard=None, eps=BN_EPS, momentum=BN_MOMENTUM, batches_tracked=None):
         _require_cuda(x, gate_in, k5)
         lib = _lib.load()
         n, ci_x, d, h, wd = x.shape
@@ -312,10 +337,9 @@ class ModeConvFunction(torch.autograd.Function):
             gate_in = gate_in.to(torch.int32).contiguous()
         if training:
             U, gate_u = n, gate_in
-            sample_u = torch.arange(n, dtype=torch.int32, device=dev)
         else:                                   # eval: the whole batch uses sample 0's kernel (RepMode.py:209-210)
             U, gate_u = 1, gate_in[:1].contiguous()
-            sample_u = torch.zeros(n, dtype=torch.int32, device=dev)
+        sample_u = _sample_index(n, dev, training)
         needs_dx = ctx.needs_input_grad[0]
         needs_dw = any(ctx.needs_input_grad[2:9])
         use_umma = precision == "f16" and umma_shape_ok(ci, co, d, h, wd)
@@ -328,15 +352,31 @@ class ModeConvFunction(torch.autograd.Function):
         # K1 (re-param, ~10 us of latency-bound work on a small layer) does not depend on x: it runs on the side stream
         # while the main stream stages the fp16 operand
         k1_fork = _Fork(dev, use_umma)
-        g, w_fwd, w_dg = reparam_fwd(layer, gate_u, U, ci, co, dtype, needs_dx, w_scale, fork=k1_fork)
+        bn_train = normal and training
+        wants_grad = needs_dx or needs_dw or (normal and (ctx.needs_input_grad[9] or ctx.needs_input_grad[10]))
+        # the buffers that must be ZERO before their kernels accumulate into them -- the BatchNorm sums of K2's epilogue and
+        # the workspace of the BatchNorm-backward reduction -- are one allocation cleared by one fill on the side stream,
+        # next to K1; the running-statistics step counter is bumped there too (nothing of this on the critical path)
+        sums = bwd_ws = zbuf = None
+        if bn_train:
+            n_sums = 2 * co_p * 8
+            n_ws = int(lib.mode_bn_bwd_workspace_bytes(co)) if (wants_grad and shard is None) else 0
+            zbuf = torch.empty(n_sums + n_ws, dtype=torch.uint8, device=dev)
+            sums = zbuf[:n_sums].view(torch.float64)
+            bwd_ws = zbuf[n_sums:] if n_ws else None
+
+        def side_work():
+            if zbuf is not None:
+                zbuf.zero_()
+            if batches_tracked is not None:
+                batches_tracked.add_(1)
+        g, w_fwd, w_dg = reparam_fwd(layer, gate_u, U, ci, co, dtype, needs_dx, w_scale, fork=k1_fork, post=side_work)
         if use_umma:
             x_op = cast_f16(xn) if ci_p == ci else cast_f16_pad(xn, ci_p)
         else:
             x_op = xn
         k1_fork.join()
 
-        bn_train = normal and training
-        sums = torch.zeros(2 * co_p, dtype=torch.float64, device=dev) if bn_train else None
         y = conv3d(x_op, dtype, w_fwd, sample_u, n, d, h, wd, ci_p, co_p, None, sums,
                    stat_range=shard.own if shard is not None else None, out_scale=1.0 / w_scale)
         if co_p != co:                              # drop the zero-padded output channels (head layer, Co = 1)
@@ -352,26 +392,29 @@ class ModeConvFunction(torch.autograd.Function):
         if normal:
             scale = torch.empty(co, dtype=torch.float32, device=dev)
             shift = torch.empty(co, dtype=torch.float32, device=dev)
+            out = torch.empty_like(y)
+            pl_ref = ctypes.byref(planes) if planes is not None else None
             if training:
+                # finalize + apply as ONE kernel (every block derives scale / shift from the sums)
                 mean = torch.empty(co, dtype=torch.float32, device=dev)
                 invstd = torch.empty(co, dtype=torch.float32, device=dev)
-                _lib.check(lib.mode_bn_finalize(_p(sums), m_stat, co, _p(bn_w), _p(bn_b), float(eps), float(momentum),
-                                                _p(mean), _p(invstd), _p(scale), _p(shift), _p(running_mean),
-                                                _p(running_var), _stream()), "mode_bn_finalize")
+                _lib.check(lib.mode_bn_finalize_apply_relu(_p(sums), m_stat, co, _p(bn_w), _p(bn_b), float(eps),
+                                                           float(momentum), _p(mean), _p(invstd), _p(scale), _p(shift),
+                                                           _p(running_mean), _p(running_var), _p(y), m_rows, 1, _p(out),
+                                                           None, 1.0, pl_ref, _stream()), "mode_bn_finalize_apply_relu")
             else:
                 invstd_r = torch.rsqrt(running_var + eps)
                 scale = (bn_w * invstd_r).contiguous()
                 shift = (bn_b - running_mean * scale).contiguous()
                 mean, invstd = running_mean.clone(), invstd_r.contiguous()      # frozen statistics (for a backward pass)
-            out = torch.empty_like(y)
-            _lib.check(lib.mode_bn_apply_relu(_p(y), m_rows, co, _p(scale), _p(shift), 1, _p(out), None, 1.0,
-                                              ctypes.byref(planes) if planes is not None else None, _stream()),
-                       "mode_bn_apply_relu")
+                _lib.check(lib.mode_bn_apply_relu(_p(y), m_rows, co, _p(scale), _p(shift), 1, _p(out), None, 1.0, pl_ref,
+                                                  _stream()), "mode_bn_apply_relu")
         else:
             out = y
         ctx.frozen_bn = normal and not training
         ctx.shard = shard
-        if needs_dx or needs_dw or (normal and (ctx.needs_input_grad[9] or ctx.needs_input_grad[10])):
+        ctx.bwd_ws = bwd_ws if wants_grad else None     # already zero: the backward reduction skips its memset (once)
+        if wants_grad:
             x_w = x_op if (UMMA_WGRAD or not use_umma) else xn      # operand K4 will read
             ctx.save_for_backward(None, x_w if needs_dw else None, y if normal else None, g, w_dg,
                                   gate_u, sample_u, k5, k3, k1, a3, a5, gate_w, gate_b, bn_w, bn_b, mean, invstd, w_s2)
@@ -398,7 +441,10 @@ class ModeConvFunction(torch.autograd.Function):
             shard = ctx.shard
             dgamma = torch.empty(co, dtype=torch.float32, device=dev)
             dbeta = torch.empty(co, dtype=torch.float32, device=dev)
-            ws = torch.empty(int(lib.mode_bn_bwd_workspace_bytes(co)), dtype=torch.uint8, device=dev)
+            ws, ctx.bwd_ws = ctx.bwd_ws, None           # zeroed during the forward; a second backward zeroes its own
+            reduce_fn = lib.mode_bn_relu_bwd_reduce_prezeroed if ws is not None else lib.mode_bn_relu_bwd_reduce
+            if ws is None:
+                ws = torch.empty(int(lib.mode_bn_bwd_workspace_bytes(co)), dtype=torch.uint8, device=dev)
             planes = shard.planes(h * wd, d) if shard is not None else None
             if ctx.frozen_bn:
                 # eval mode (fine-tuning with frozen BatchNorm, saliency maps): the statistics are constants, so
@@ -406,8 +452,8 @@ class ModeConvFunction(torch.autograd.Function):
                 # "halo copy" planes (valid, not owned): declare every plane one.  dgamma / dbeta are still the plain sums.
                 planes = _lib.ModePlanes(m_rows, 1, 0, 0, 0, 1, m_rows)
             pl = ctypes.byref(planes) if planes is not None else None
-            _lib.check(lib.mode_bn_relu_bwd_reduce(_p(y), _p(doutn), m_rows, co, _p(bn_w), _p(bn_b), _p(mean), _p(invstd),
-                                                   pl, _p(ws), _stream()), "mode_bn_relu_bwd_reduce")
+            _lib.check(reduce_fn(_p(y), _p(doutn), m_rows, co, _p(bn_w), _p(bn_b), _p(mean), _p(invstd), pl, _p(ws),
+                                 _stream()), "mode_bn_relu_bwd_reduce")
             if shard is not None:
                 shard.all_reduce(ws[:16 * co].view(torch.float64), "mode.bwd")      # {sum dz, sum dz*xhat} over every slab
             dy_f32 = None
@@ -469,7 +515,7 @@ class ModeConvFunction(torch.autograd.Function):
             if ci_p != ci:
                 dxn = dxn[..., :ci].contiguous()
             dx = from_ndhwc(dxn)
-        return (dx, None, *grads, dgamma, dbeta, None, None, None, None, None, None, None, None)
+        return (dx, None, *grads, dgamma, dbeta, None, None, None, None, None, None, None, None, None)
 
 
 EVAL_CACHE = os.environ.get("REPMODE_EVAL_CACHE", "1") == "1"
@@ -585,8 +631,9 @@ def mode_conv(x, gate_in, params, bn, training, conv_type="normal", precision=No
     bn_w, bn_b, rm, rv = bn[:4] if bn is not None else (None, None, None, None)
     eps = bn[4] if bn is not None and len(bn) > 4 else BN_EPS
     momentum = bn[5] if bn is not None and len(bn) > 5 and bn[5] is not None else BN_MOMENTUM
+    tracked = bn[6] if bn is not None and len(bn) > 6 else None      # num_batches_tracked: bumped off the critical path
     return ModeConvFunction.apply(x, gate_in, *params, bn_w, bn_b, rm, rv, training, conv_type,
-                                  precision or default_precision(), shard, eps, momentum)
+                                  precision or default_precision(), shard, eps, momentum, tracked)
 
 
 class BnReluFunction(torch.autograd.Function):
@@ -615,17 +662,19 @@ class BnReluFunction(torch.autograd.Function):
             _lib.check(lib.mode_bn_stats(_p(yn), m_rows, c, _p(sums), _stream()), "mode_bn_stats")
             if shard is not None:
                 shard.all_reduce(sums, "bn.fwd")                         # every plane of a stride-2 level is owned: plain sum
-            _lib.check(lib.mode_bn_finalize(_p(sums), m_stat, c, _p(weight), _p(bias), float(eps), float(momentum),
-                                            _p(mean), _p(invstd), _p(scale), _p(shift), _p(running_mean), _p(running_var),
-                                            _stream()), "mode_bn_finalize")
+            out = torch.empty_like(yn)
+            _lib.check(lib.mode_bn_finalize_apply_relu(_p(sums), m_stat, c, _p(weight), _p(bias), float(eps), float(momentum),
+                                                       _p(mean), _p(invstd), _p(scale), _p(shift), _p(running_mean),
+                                                       _p(running_var), _p(yn), m_rows, 1, _p(out), None, 1.0, None,
+                                                       _stream()), "mode_bn_finalize_apply_relu")
         else:
             invstd = torch.rsqrt(running_var + eps).contiguous()
             mean = running_mean.clone()
             scale = (weight * invstd).contiguous()
             shift = (bias - running_mean * scale).contiguous()
-        out = torch.empty_like(yn)
-        _lib.check(lib.mode_bn_apply_relu(_p(yn), m_rows, c, _p(scale), _p(shift), 1, _p(out), None, 1.0, None,
-                                          _stream()), "mode_bn_apply_relu")
+            out = torch.empty_like(yn)
+            _lib.check(lib.mode_bn_apply_relu(_p(yn), m_rows, c, _p(scale), _p(shift), 1, _p(out), None, 1.0, None,
+                                              _stream()), "mode_bn_apply_relu")
         ctx.training = training
         ctx.save_for_backward(yn, weight, bias, mean, invstd)
         return out

@@ -149,6 +149,9 @@ SIGNATURES = {
                                                  _vp, ctypes.POINTER(ModePeerGather), ctypes.POINTER(ModeHaloPush), _vp]),
     "mode_cast_f16_ex": (ctypes.c_int, [_vp, _vp, _i64, _f32, _vp, ctypes.POINTER(ModeHaloPush), _vp]),
     "mode_bn_apply_relu": (ctypes.c_int, [_vp, _i64, _i32, _vp, _vp, _i32, _vp, _vp, _f32, _vp, _vp]),
+    "mode_bn_finalize_apply_relu": (ctypes.c_int, [_vp, _i64, _i32, _vp, _vp, _f32, _f32, _vp, _vp, _vp, _vp, _vp, _vp,
+                                                   _vp, _i64, _i32, _vp, _vp, _f32, _vp, _vp]),
+    "mode_bn_relu_bwd_reduce_prezeroed": (ctypes.c_int, [_vp, _vp, _i64, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "mode_bn_relu_bwd_reduce": (ctypes.c_int, [_vp, _vp, _i64, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "mode_bn_relu_bwd_apply": (ctypes.c_int, [_vp, _vp, _i64, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
                                               _vp, _vp]),

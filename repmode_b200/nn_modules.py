@@ -75,9 +75,9 @@ class MoDEConv(torch.nn.Module):
         bn = None
         if self.conv_type == 'normal':
             m = self.subsequent_layer[0]
-            bn = (m.weight, m.bias, m.running_mean, m.running_var, m.eps, m.momentum)
-            if self.training and m.track_running_stats and m.num_batches_tracked is not None:
-                m.num_batches_tracked.add_(1)
+            tracked = (m.num_batches_tracked if self.training and m.track_running_stats
+                       and m.num_batches_tracked is not None else None)      # +1 per training forward, like nn.BatchNorm3d
+            bn = (m.weight, m.bias, m.running_mean, m.running_var, m.eps, m.momentum, tracked)
         if (not self.training and not torch.is_grad_enabled() and not t.dtype.is_floating_point
                 and Fm.EVAL_CACHE):
             # Model.predict path (eval + no_grad, int task ids): W_eff of every task is built once and reused

@@ -100,14 +100,16 @@ class ShardedConvFunction(torch.autograd.Function):
         dtype = _lib.MODE_F16 if use_umma else _lib.MODE_F32
         tdt = torch.float16 if use_umma else torch.float32
         H2 = BLOCK_HALO
-        sample_u = torch.zeros(1, dtype=torch.int32, device=dev)
+        sample_u = Fm._sample_index(1, dev, False)
         w_scale = Fm.W_SCALE_F16 if use_umma else 1.0
         needs_dx = ctx.needs_input_grad[0]
 
         xn = Fm.to_ndhwc(x)
         x_ext = comm.alloc((tag, "x_ext", str(tdt)), (1, d + 2 * H2, h, wd, ci), tdt, dev)
         k1_fork = Fm._Fork(dev, True)
-        g, w_fwd, w_dg = Fm.reparam_fwd(layer, gate_in[:1].contiguous(), 1, ci, co, dtype, needs_dx, w_scale, fork=k1_fork)
+        sums = torch.empty(2 * co, dtype=torch.float64, device=dev)      # cleared on the side stream, next to K1
+        g, w_fwd, w_dg = Fm.reparam_fwd(layer, gate_in[:1].contiguous(), 1, ci, co, dtype, needs_dx, w_scale, fork=k1_fork,
+                                        post=sums.zero_)
         fused = FUSED_EXCHANGE and getattr(comm, "fused", False) and comm.world > 1
         if use_umma and fused:
             # the cast kernel stores its boundary planes straight into the neighbours' halo planes and signals
@@ -124,7 +126,6 @@ class ShardedConvFunction(torch.autograd.Function):
             comm.halo_fill(x_ext, H2, tag + ".x")
         k1_fork.join()
 
-        sums = torch.zeros(2 * co, dtype=torch.float64, device=dev)
         m_rows = d * h * wd
         m_global = d_global * h * wd
         mean = torch.empty(co, dtype=torch.float32, device=dev)

@@ -257,6 +257,72 @@ def test_gate_bwd_block_kernel_bit_identical_to_serial(ci, co, n, dense, monkeyp
     assert bool(torch.isfinite(got[5]).all()) and bool(torch.isfinite(got[6]).all())
 
 
+@pytest.mark.parametrize("m_rows,c", [(4096, 32), (1000, 48), (513, 256)])
+def test_bn_finalize_apply_one_kernel_matches_two(m_rows, c):
+    """mode_bn_finalize_apply_relu (finalize folded into the apply kernel's prologue) against mode_bn_finalize followed by
+    mode_bn_apply_relu: output, saved statistics and running statistics bit-identical."""
+    from repmode_b200 import functional as Fm, lib as L
+    lib = L.load()
+    torch.manual_seed(3)
+    y = (torch.randn(m_rows, c, device="cuda") * 2 + 0.5).contiguous()
+    gamma, beta = torch.rand(c, device="cuda") + 0.5, torch.randn(c, device="cuda")
+    sums = torch.zeros(2 * c, dtype=torch.float64, device="cuda")
+    L.check(lib.mode_bn_stats(Fm._p(y), m_rows, c, Fm._p(sums), Fm._stream()), "mode_bn_stats")
+
+    def bufs():
+        return [torch.empty(c, device="cuda") for _ in range(4)] + [torch.full((c,), 0.25, device="cuda"),
+                                                                    torch.full((c,), 1.5, device="cuda")]
+    a, b = bufs(), bufs()
+    out_a, out_b = torch.empty_like(y), torch.empty_like(y)
+    L.check(lib.mode_bn_finalize(Fm._p(sums), m_rows, c, Fm._p(gamma), Fm._p(beta), 1e-5, 0.1, *[Fm._p(t) for t in a],
+                                 Fm._stream()), "mode_bn_finalize")
+    L.check(lib.mode_bn_apply_relu(Fm._p(y), m_rows, c, Fm._p(a[2]), Fm._p(a[3]), 1, Fm._p(out_a), None, 1.0, None,
+                                   Fm._stream()), "mode_bn_apply_relu")
+    L.check(lib.mode_bn_finalize_apply_relu(Fm._p(sums), m_rows, c, Fm._p(gamma), Fm._p(beta), 1e-5, 0.1,
+                                            *[Fm._p(t) for t in b], Fm._p(y), m_rows, 1, Fm._p(out_b), None, 1.0, None,
+                                            Fm._stream()), "mode_bn_finalize_apply_relu")
+    torch.cuda.synchronize()
+    assert torch.equal(out_a, out_b)
+    for ta, tb, name in zip(a, b, ("mean", "invstd", "scale", "shift", "running_mean", "running_var")):
+        assert torch.equal(ta, tb), name
+    ref = torch.relu(torch.nn.functional.batch_norm(y, None, None, gamma, beta, True, 0.0, 1e-5))
+    assert_close(out_b.cpu().numpy(), ref.cpu().numpy(), 1e-5, "fused finalize+apply vs torch batch_norm")
+
+
+@pytest.mark.parametrize("m_rows,c", [(4096, 32), (1000, 64)])
+def test_bn_bwd_scale_inside_apply_matches_scale_kernel(m_rows, c, monkeypatch):
+    """The fp16 scale of dy derived inside the BatchNorm-backward apply kernel against the separate one-block scale kernel
+    (REPMODE_BN_SCALE_KERNEL=1): the published {scale, 1/scale}, the fp16 dy and dgamma / dbeta bit-identical."""
+    from repmode_b200 import functional as Fm, lib as L
+    lib = L.load()
+    torch.manual_seed(4)
+    y = torch.randn(m_rows, c, device="cuda").contiguous()
+    dout = (torch.randn(m_rows, c, device="cuda") * 1e-3).contiguous()
+    gamma, beta = torch.rand(c, device="cuda") + 0.5, torch.randn(c, device="cuda") * 0.1
+    mean, var = y.mean(0), y.var(0, unbiased=False)
+    invstd = torch.rsqrt(var + 1e-5)
+
+    def run():
+        dgamma, dbeta = torch.empty(c, device="cuda"), torch.empty(c, device="cuda")
+        dy16 = torch.empty(m_rows, c, dtype=torch.float16, device="cuda")
+        s2 = torch.zeros(2, device="cuda")
+        ws = torch.empty(int(lib.mode_bn_bwd_workspace_bytes(c)), dtype=torch.uint8, device="cuda")
+        L.check(lib.mode_bn_relu_bwd_reduce(Fm._p(y), Fm._p(dout), m_rows, c, Fm._p(gamma), Fm._p(beta), Fm._p(mean),
+                                            Fm._p(invstd), None, Fm._p(ws), Fm._stream()), "mode_bn_relu_bwd_reduce")
+        L.check(lib.mode_bn_relu_bwd_apply(Fm._p(y), Fm._p(dout), m_rows, c, Fm._p(gamma), Fm._p(beta), Fm._p(mean),
+                                           Fm._p(invstd), Fm._p(dgamma), Fm._p(dbeta), None, Fm._p(dy16), Fm._p(s2), None,
+                                           Fm._p(ws), Fm._stream()), "mode_bn_relu_bwd_apply")
+        torch.cuda.synchronize()
+        return dgamma, dbeta, dy16, s2
+    monkeypatch.setenv("REPMODE_BN_SCALE_KERNEL", "1")
+    ref = run()
+    monkeypatch.delenv("REPMODE_BN_SCALE_KERNEL")
+    got = run()
+    for a, b, name in zip(got, ref, ("dgamma", "dbeta", "dy16", "scale2")):
+        assert torch.equal(a, b), name
+    assert float(got[3][0]) > 1.0 and float(got[3][0] * got[3][1]) == 1.0      # small gradients are scaled UP, by a power of two
+
+
 def test_cast_f16_pad_matches_cast_then_pad():
     from repmode_b200 import functional as Fm
     x = torch.randn(2, 3, 8, 16, 1, device="cuda") * 3

@@ -358,6 +358,7 @@ __device__ __forceinline__ void pack_dgrad_h16_body(const Locate& locate, long l
     const int r = j >> 2, pc = j & 3;
     const int lc = pc ^ ((r >> 1) & 3);                           // logical 8-column chunk behind physical chunk pc of row r
     const long long t0 = (long long)blockIdx.x * PD_TILES;
+    int hint = locate.first_layer(t0);                            // block-uniform: the layer of the block's first tile
     uint4 v[PD_TILES / 2];
     __half* dptr[PD_TILES / 2];
 #pragma unroll
@@ -367,7 +368,7 @@ __device__ __forceinline__ void pack_dgrad_h16_body(const Locate& locate, long l
         dptr[k] = nullptr;
         if (tg < n_tiles) {
             PdLayer P;
-            const long long tl = locate(tg, P);                   // tile index inside its layer
+            const long long tl = locate(tg, P, hint);             // tile index inside its layer (hint only moves forward)
             const int oc = (int)(tl % P.nco);
             long long q = tl / P.nco;
             const int ic = (int)(q % P.nci);
@@ -396,7 +397,8 @@ __device__ __forceinline__ void pack_dgrad_h16_body(const Locate& locate, long l
 }
 struct PdSingleLocate {
     PdLayer P;
-    __device__ __forceinline__ long long operator()(long long tg, PdLayer& out) const { out = P; return tg; }
+    __device__ __forceinline__ int first_layer(long long) const { return 0; }
+    __device__ __forceinline__ long long operator()(long long tg, PdLayer& out, int&) const { out = P; return tg; }
 };
 __global__ void __launch_bounds__(256) pack_dgrad_h16_kernel(const __half* __restrict__ src, __half* __restrict__ dst,
                                                              int nci, int nco, int src_rows_pad, int dst_rows_pad,
@@ -406,9 +408,13 @@ __global__ void __launch_bounds__(256) pack_dgrad_h16_kernel(const __half* __res
 // the same over the layers of a K1 group (one launch; a block's tiles may belong to two neighbouring layers)
 struct PdGroupLocate {
     const K1Group* G;
-    __device__ __forceinline__ long long operator()(long long tg, PdLayer& out) const {
+    __device__ __forceinline__ int first_layer(long long t0) const {
         int k = 0;
-        while (k + 1 < G->n && tg >= G->it[k + 1].tile_begin) ++k;
+        while (k + 1 < G->n && t0 >= G->it[k + 1].tile_begin) ++k;
+        return k;
+    }
+    __device__ __forceinline__ long long operator()(long long tg, PdLayer& out, int& k) const {
+        while (k + 1 < G->n && tg >= G->it[k + 1].tile_begin) ++k;      // a block's 8 tiles rarely cross a layer boundary
         const K1GroupItem& it = G->it[k];
         const int nci = it.L.ci / 32, nco = it.L.co / 32;
         out = PdLayer{(const __half*)it.w_fwd, (__half*)it.w_dgrad, nci, nco, nco * 32, nci * 32};

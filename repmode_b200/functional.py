@@ -177,6 +177,87 @@ def reparam_fwd(layer, gate_in, U, ci, co, dtype, want_dgrad, w_scale=1.0, fork=
     return g, w_fwd, w_dg
 
 
+K1_GROUPED = os.environ.get("REPMODE_K1_GROUPED", "1") == "1"
+_plan_streams = {}
+
+
+def _plan_stream(dev):
+    """A second side stream for the step-level K1 plan: its kernels must not sit in front of the per-layer forks, which
+    join the ordinary side stream back into the caller's stream a few microseconds after they fork."""
+    key = (dev.type, dev.index if dev.index is not None else torch.cuda.current_device())
+    st = _plan_streams.get(key)
+    if st is None:
+        st = _plan_streams[key] = torch.cuda.Stream(device=dev)
+    return st
+
+
+class K1Plan:
+    """K1 of every row-eligible MoDEConv of a training step as grouped launches (mode_reparam_fwd_grouped: one K1 + one
+    dgrad-pack launch per group) at the START of the step, on their own stream -- SURVEY.md section 8d's "single grouped
+    launch, not 19x".  All layers of a step share the gate inputs (RepMode.py:51-71).  Two groups: the layers the forward
+    needs first (a few narrow ones, ~10 us) and the rest (the wide, HBM-bound ones), which then runs UNDER the first conv
+    layers instead of in front of its own.  `take(mod)` hands a layer its (g, w_fwd, w_dgrad) after making the caller's
+    stream wait for the group's event."""
+
+    def __init__(self):
+        self.entries = {}
+
+    @staticmethod
+    def eligible(mod, x_is_cuda, w_last):
+        ci, co = mod.in_chan, mod.out_chan
+        return (x_is_cuda and (mod.precision or default_precision()) == "f16" and ci % 32 == 0 and co % 32 == 0
+                and w_last % 8 == 0 and os.environ.get("REPMODE_DISABLE_UMMA", "0") != "1")
+
+    @classmethod
+    def build(cls, mods, gate_in, dev, first_group=3):
+        """mods: eligible MoDEConv modules in execution order; gate_in: int32 task ids [U] (contiguous, on dev)."""
+        lib = _lib.load()
+        U = gate_in.shape[0]
+        if not mods or U > 32 or len(mods) > 2 * _lib.REPARAM_GROUP_MAX:
+            return None
+        plan = cls()
+        main = torch.cuda.current_stream(dev)
+        side = _plan_stream(dev)
+        items = []
+        for m in mods:
+            layer, ci, co = _layer(*m._params())
+            g = torch.empty((U, E, co), dtype=torch.float32, device=dev)
+            w_fwd = torch.empty(U * lib.mode_packed_weight_elems_f16(ci, co), dtype=torch.float16, device=dev)
+            w_dg = torch.empty(U * lib.mode_packed_weight_elems_f16(co, ci), dtype=torch.float16, device=dev)
+            items.append((m, layer, g, w_fwd, w_dg))
+        side.wait_stream(main)
+        with torch.cuda.stream(side):
+            for grp in (items[:first_group], items[first_group:]):
+                for k0 in range(0, len(grp), _lib.REPARAM_GROUP_MAX):
+                    part = grp[k0:k0 + _lib.REPARAM_GROUP_MAX]
+                    arr = (_lib.ModeReparamItem * len(part))()
+                    for a, (m, layer, g, w_fwd, w_dg) in zip(arr, part):
+                        a.layer, a.g_out, a.w_fwd, a.w_dgrad = layer, g.data_ptr(), w_fwd.data_ptr(), w_dg.data_ptr()
+                    _lib.check(lib.mode_reparam_fwd_grouped(arr, len(part), _p(gate_in), None, U, _lib.MODE_F16,
+                                                            float(W_SCALE_F16), _stream()), "mode_reparam_fwd_grouped")
+                if grp:
+                    ev = torch.cuda.Event()
+                    ev.record(side)
+                    for m, layer, g, w_fwd, w_dg in grp:
+                        plan.entries[id(m)] = (g, w_fwd, w_dg, ev)
+        return plan
+
+    def take(self, mod, dev):
+        ent = self.entries.pop(id(mod), None)
+        if ent is None:
+            return None
+        g, w_fwd, w_dg, ev = ent
+        torch.cuda.current_stream(dev).wait_event(ev)
+        return g, w_fwd, w_dg
+
+    def finish(self, dev):
+        """Join whatever was not consumed (an exception, a skipped layer): the plan stream must be back in the caller's
+        stream before a CUDA-graph capture can end."""
+        if self.entries:
+            torch.cuda.current_stream(dev).wait_stream(_plan_stream(dev))
+            self.entries.clear()
+
+
 def conv3d(x, dtype, w, sample_u, n, d, h, wd, k, nout, out_scale_dev=None, bn_sums=None, impl=0, stat_range=None,
            out_scale=1.0, out=None, halo=None, ep=None, y16=None, want_y=True, stats_push=None):
     """K2 / K3 through mode_conv3d_ex.  d = OUTPUT planes.
@@ -322,7 +403,7 @@ class ModeConvFunction(torch.autograd.Function):
     @torch.amp.custom_fwd(device_type="cuda", cast_inputs=torch.float32)
     @_on_device_of_first
     def forward(ctx, x, gate_in, k5, k3, k1, a3, a5, gate_w, gate_b, bn_w, bn_b, running_mean, running_var, training,
-                conv_type, precision, shard=None, eps=BN_EPS, momentum=BN_MOMENTUM, batches_tracked=None):
+                conv_type, precision, shard=None, eps=BN_EPS, momentum=BN_MOMENTUM, batches_tracked=None, prebuilt=None):
         _require_cuda(x, gate_in, k5)
         lib = _lib.load()
         n, ci_x, d, h, wd = x.shape
@@ -370,7 +451,12 @@ class ModeConvFunction(torch.autograd.Function):
                 zbuf.zero_()
             if batches_tracked is not None:
                 batches_tracked.add_(1)
-        g, w_fwd, w_dg = reparam_fwd(layer, gate_u, U, ci, co, dtype, needs_dx, w_scale, fork=k1_fork, post=side_work)
+        if prebuilt is not None and use_umma and training:
+            g, w_fwd, w_dg = prebuilt                    # built by the step's grouped K1 launch (K1Plan); already awaited
+            with k1_fork:
+                side_work()
+        else:
+            g, w_fwd, w_dg = reparam_fwd(layer, gate_u, U, ci, co, dtype, needs_dx, w_scale, fork=k1_fork, post=side_work)
         if use_umma:
             x_op = cast_f16(xn) if ci_p == ci else cast_f16_pad(xn, ci_p)
         else:
@@ -515,7 +601,7 @@ class ModeConvFunction(torch.autograd.Function):
             if ci_p != ci:
                 dxn = dxn[..., :ci].contiguous()
             dx = from_ndhwc(dxn)
-        return (dx, None, *grads, dgamma, dbeta, None, None, None, None, None, None, None, None, None)
+        return (dx, None, *grads, dgamma, dbeta, None, None, None, None, None, None, None, None, None, None)
 
 
 EVAL_CACHE = os.environ.get("REPMODE_EVAL_CACHE", "1") == "1"
@@ -625,7 +711,7 @@ def mode_conv_eval(x, task_ids, params, bn, conv_type, precision, cache):
     return from_ndhwc(y)
 
 
-def mode_conv(x, gate_in, params, bn, training, conv_type="normal", precision=None, shard=None):
+def mode_conv(x, gate_in, params, bn, training, conv_type="normal", precision=None, shard=None, prebuilt=None):
     """Functional MoDEConv. params: (k5,k3,k1,a3,a5,gate_w,gate_b); bn: (weight,bias,running_mean,running_var) or None;
     shard: ShardSpec when x is one D-slab (with halos) of a larger volume."""
     bn_w, bn_b, rm, rv = bn[:4] if bn is not None else (None, None, None, None)
@@ -633,7 +719,7 @@ def mode_conv(x, gate_in, params, bn, training, conv_type="normal", precision=No
     momentum = bn[5] if bn is not None and len(bn) > 5 and bn[5] is not None else BN_MOMENTUM
     tracked = bn[6] if bn is not None and len(bn) > 6 else None      # num_batches_tracked: bumped off the critical path
     return ModeConvFunction.apply(x, gate_in, *params, bn_w, bn_b, rm, rv, training, conv_type,
-                                  precision or default_precision(), shard, eps, momentum, tracked)
+                                  precision or default_precision(), shard, eps, momentum, tracked, prebuilt)
 
 
 class BnReluFunction(torch.autograd.Function):

@@ -30,6 +30,13 @@ class ModeLayer(ctypes.Structure):
                 ("ci", ctypes.c_int32), ("co", ctypes.c_int32), ("num_tasks", ctypes.c_int32)]
 
 
+class ModeReparamItem(ctypes.Structure):
+    _fields_ = [("layer", ModeLayer), ("g_out", ctypes.c_void_p), ("w_fwd", ctypes.c_void_p), ("w_dgrad", ctypes.c_void_p)]
+
+
+REPARAM_GROUP_MAX = 24
+
+
 class ModePlanes(ctypes.Structure):
     _fields_ = [("rows_per_plane", ctypes.c_int64), ("D", ctypes.c_int32), ("own_lo", ctypes.c_int32),
                 ("own_hi", ctypes.c_int32), ("valid_lo", ctypes.c_int32), ("valid_hi", ctypes.c_int32),
@@ -109,6 +116,7 @@ SIGNATURES = {
     "mode_query": (ctypes.c_int, [ctypes.c_int, ctypes.POINTER(ModeCaps)]),
     "mode_poll_error": (ctypes.c_int, [ctypes.POINTER(ctypes.c_int32)]),
     "mode_debug_profile": (ctypes.c_int, [_vp]),
+    "mode_reparam_fwd_grouped": (ctypes.c_int, [_vp, _i32, _vp, _vp, _i32, ctypes.c_int, _f32, _vp]),
     "mode_reparam_fwd": (ctypes.c_int, [ctypes.POINTER(ModeLayer), _vp, _vp, _i32, _vp, _vp, _vp, ctypes.c_int, _f32,
                                         _vp, _vp]),
     "mode_packed_weight_elems": (_i64, [_i32, _i32]),

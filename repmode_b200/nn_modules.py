@@ -83,7 +83,9 @@ class MoDEConv(torch.nn.Module):
             # Model.predict path (eval + no_grad, int task ids): W_eff of every task is built once and reused
             return Fm.mode_conv_eval(x, t, self._params(), bn, self.conv_type,
                                      self.precision or Fm.default_precision(), self._eval_cache)
-        return Fm.mode_conv(x, t, self._params(), bn, self.training, self.conv_type, self.precision)
+        plan = self.__dict__.pop("_k1_plan", None)         # set by Net.forward for the layers of a grouped K1 launch
+        prebuilt = plan.take(self, x.device) if plan is not None else None
+        return Fm.mode_conv(x, t, self._params(), bn, self.training, self.conv_type, self.precision, prebuilt=prebuilt)
 
 
 class MoDESubNet2Conv(torch.nn.Module):
@@ -216,8 +218,38 @@ class Net(torch.nn.Module):
         graph.replay()
         return gout.clone()
 
+    def _mode_convs(self):
+        """The 19 MoDEConv call sites in execution order (RepMode.py:51-71) with the U-Net level (0 = full resolution,
+        4 = bottleneck: the volume is 2^level times smaller per axis) each one runs at."""
+        out = []
+        for lv, blk in enumerate((self.encoder_block1, self.encoder_block2, self.encoder_block3, self.encoder_block4)):
+            out += [(blk.conv_more.conv1, lv), (blk.conv_more.conv2, lv)]
+        out += [(self.bottle_block.conv1, 4), (self.bottle_block.conv2, 4)]
+        for lv, blk in zip((3, 2, 1, 0), (self.decoder_block4, self.decoder_block3, self.decoder_block2,
+                                          self.decoder_block1)):
+            out += [(blk.conv_less.conv1, lv), (blk.conv_less.conv2, lv)]
+        return out + [(self.conv_out, 0)]
+
     def _forward_impl(self, x, t):
         t = t.to(device=x.device, dtype=torch.int32).reshape(-1)      # task ids, never a one-hot tensor
+        plan = None
+        if self.training and torch.is_grad_enabled() and Fm.K1_GROUPED and x.is_cuda and t.shape[0] == x.shape[0]:
+            # K1 of every row-eligible layer as grouped launches at the start of the step (functional.K1Plan)
+            mods = [m for m, lv in self._mode_convs() if Fm.K1Plan.eligible(m, True, x.shape[-1] >> lv)]
+            with torch.cuda.device(x.device):
+                plan = Fm.K1Plan.build(mods, t.contiguous(), x.device)
+            if plan is not None:
+                for m in mods:
+                    m.__dict__["_k1_plan"] = plan
+        try:
+            return self._forward_layers(x, t)
+        finally:
+            if plan is not None:
+                for m, _ in self._mode_convs():
+                    m.__dict__.pop("_k1_plan", None)
+                plan.finish(x.device)
+
+    def _forward_layers(self, x, t):
         x, x_skip1 = self.encoder_block1(x, t)
         x, x_skip2 = self.encoder_block2(x, t)
         x, x_skip3 = self.encoder_block3(x, t)

@@ -140,3 +140,41 @@ def test_full_width_train_step_gradients_vs_oracle():
     print("full-width train-step gradients (cosine, rel-L2):", {k.split(".")[0] + ".." + k.split(".")[-1]: (round(c, 5), round(l, 4))
                                                               for k, (c, l) in worst.items()})
     assert not bad, bad
+
+
+def test_grouped_k1_plan_step_bit_identical_to_per_layer_k1(monkeypatch):
+    """A full-width train step with the step-level K1 plan (two grouped K1 + dgrad-pack launches at the start of the step,
+    functional.K1Plan) against the same step with one K1 launch pair per layer: same kernels' arithmetic, same packs, so the
+    prediction and every parameter gradient must be bit-identical.  64-wide volume: the 4-wide bottleneck level is not
+    row-eligible and keeps its per-layer K1 -- both kinds of layer in one step."""
+    import importlib
+    from repmode_b200 import functional as Fm, lib as L
+    mod = importlib.import_module("fnet.nn_modules.RepMode")
+    torch.manual_seed(31)
+    net = mod.Net(argparse.Namespace(adopted_datasets=list(range(12)), gpu_ids=0)).cuda().train()
+    sd0 = {k: v.clone() for k, v in net.state_dict().items()}
+    g = torch.Generator().manual_seed(32)
+    x = torch.randn(2, 1, 16, 64, 64, generator=g).cuda()
+    dout = torch.randn(2, 1, 16, 64, 64, generator=g).cuda()
+    t = torch.tensor([2, 9]).cuda()
+    lib = L.load()
+
+    def step(grouped):
+        monkeypatch.setattr(Fm, "K1_GROUPED", grouped)
+        net.load_state_dict(sd0)
+        for p in net.parameters():
+            p.grad = None
+        n0 = lib.mode_launch_count()
+        y = net(x, t)
+        y.backward(dout)
+        torch.cuda.synchronize()
+        L.poll_error("grouped K1 test")
+        return y.detach().clone(), {k: p.grad.clone() for k, p in net.named_parameters()}, lib.mode_launch_count() - n0
+    y_ref, g_ref, n_ref = step(False)
+    y_got, g_got, n_got = step(True)
+    assert torch.equal(y_got, y_ref)
+    for k in g_ref:
+        assert torch.equal(g_got[k], g_ref[k]), k
+    assert n_got < n_ref, (n_got, n_ref)            # 15 eligible layers: 30 K1 / pack launches became 4
+    bt = net.encoder_block2.conv_more.conv1.subsequent_layer[0].num_batches_tracked
+    assert int(bt) == 1                              # load_state_dict reset it; one bump per training forward, plan or not

@@ -323,6 +323,44 @@ def test_bn_bwd_scale_inside_apply_matches_scale_kernel(m_rows, c, monkeypatch):
     assert float(got[3][0]) > 1.0 and float(got[3][0] * got[3][1]) == 1.0      # small gradients are scaled UP, by a power of two
 
 
+def test_reparam_fwd_grouped_bit_identical_to_per_layer():
+    """mode_reparam_fwd_grouped (one K1 + one dgrad-pack launch over several layers, the descriptors as a kernel parameter)
+    against mode_reparam_fwd per layer: gates, forward packs and dgrad packs bit-identical; a layer without a dgrad buffer
+    in the middle of the group (empty tile range) is skipped by the grouped pack kernel."""
+    import ctypes
+    from repmode_b200 import functional as Fm, lib as L
+    from repmode_b200.nn_modules import MoDEConv
+    lib = L.load()
+    torch.manual_seed(12)
+    shapes = [(32, 32), (32, 64), (64, 64), (128, 32), (96, 160)]
+    mods = [MoDEConv(5, 12, ci, co).cuda() for ci, co in shapes]
+    U = 3
+    ids = torch.tensor([4, 11, 4], device="cuda", dtype=torch.int32)
+    ref = []
+    for i, m in enumerate(mods):
+        layer, ci, co = Fm._layer(*m._params())
+        ref.append(Fm.reparam_fwd(layer, ids, U, ci, co, L.MODE_F16, i != 2, 256.0))
+    arr = (L.ModeReparamItem * len(mods))()
+    got = []
+    for i, (a, m) in enumerate(zip(arr, mods)):
+        layer, ci, co = Fm._layer(*m._params())
+        g = torch.full((U, 5, co), float("nan"), device="cuda")
+        w = torch.full((U * lib.mode_packed_weight_elems_f16(ci, co),), float("nan"), dtype=torch.float16, device="cuda")
+        wd = (torch.full((U * lib.mode_packed_weight_elems_f16(co, ci),), float("nan"), dtype=torch.float16, device="cuda")
+              if i != 2 else None)
+        a.layer, a.g_out, a.w_fwd, a.w_dgrad = layer, g.data_ptr(), w.data_ptr(), wd.data_ptr() if wd is not None else None
+        got.append((g, w, wd))
+    L.check(lib.mode_reparam_fwd_grouped(arr, len(mods), Fm._p(ids), None, U, L.MODE_F16, 256.0, Fm._stream()),
+            "mode_reparam_fwd_grouped")
+    torch.cuda.synchronize()
+    L.poll_error("grouped K1")
+    for (g0, w0, d0), (g1, w1, d1), sh in zip(ref, got, shapes):
+        assert torch.equal(g0, g1), sh
+        assert torch.equal(w0.view(torch.int16), w1.view(torch.int16)), sh
+        if d0 is not None:
+            assert torch.equal(d0.view(torch.int16), d1.view(torch.int16)), sh
+
+
 def test_cast_f16_pad_matches_cast_then_pad():
     from repmode_b200 import functional as Fm
     x = torch.randn(2, 3, 8, 16, 1, device="cuda") * 3

@@ -254,21 +254,40 @@ int mode_bn_relu_bwd_apply(const float* y, const float* dout, int64_t M, int32_t
                            float* dy, void* dy_f16, float* dy_scale2, const mode_planes_t* planes_host,
                            void* workspace, void* stream);
 
-/* Launch-structure forms (same arithmetic, fewer kernel boundaries on the critical path of a training step):
- *   mode_bn_finalize_apply_relu:       mode_bn_finalize + mode_bn_apply_relu as ONE kernel -- every block derives scale / shift
- *                                      from `sums` (M_stat = the statistics' divisor), block 0 writes mean / invstd / scale /
- *                                      shift and updates the running statistics; y has M rows.
- *   mode_bn_relu_bwd_reduce_prezeroed: mode_bn_relu_bwd_reduce for a workspace the caller has ALREADY zeroed (e.g. during the
- *                                      forward, off the critical path): no memset in front of the reduction.
- * mode_bn_relu_bwd_apply derives the fp16 scale of dy inside the apply kernel (no separate scale launch) unless a gather
- * descriptor is given. */
+/* Launch-structure forms (same arithmetic, fewer kernel boundaries / copies around the BatchNorm of a training step):
+ *   mode_bn_finalize_apply_relu: mode_bn_finalize + mode_bn_apply_relu as ONE kernel -- every block derives scale / shift
+ *                                from `sums` (M_stat = the statistics' divisor), block 0 writes mean / invstd / scale /
+ *                                shift and updates the running statistics; y has M rows.
+ *   mode_bn_relu_bwd_reduce_v2:  workspace_is_zero != 0: the caller has ALREADY zeroed the workspace (e.g. during the
+ *                                forward, off the critical path): no memset in front of the reduction.
+ *   mode_bn_relu_bwd_apply_v2:   mode_bn_relu_bwd_apply with a row map for dout.
+ * mode_rowmap_t says where row r of the tensor the kernel WALKS (y) lives in the second tensor (out / dout):
+ *   d2s != 0: y is the [voxels][8][C] result of the transposed stride-2 conv as a GEMM (ConvTranspose3d(k=2, s=2),
+ *             fnet/nn_modules/RepMode.py:97-101; rows ordered (n, d, h, w, kd, kh, kw), D/H/W = the LOW-resolution grid) and
+ *             the mapped tensor is the NDHWC volume [N][2D][2H][2W]: the depth-to-space scatter (forward) / gather
+ *             (backward) happens inside the BatchNorm kernels instead of as a permute copy;
+ *   pitch:    floats between rows of the mapped tensor (0 = C): a channel range of a wider tensor, e.g. the gradient of
+ *             one half of the decoder's concatenated input (RepMode.py:106).
+ * NULL = identity.  mode_bn_relu_bwd_apply derives the fp16 scale of dy inside the apply kernel (no separate scale launch)
+ * unless a gather descriptor is given. */
+typedef struct {
+    int32_t d2s;
+    int32_t D, H, W;
+    int64_t pitch;
+} mode_rowmap_t;
 int mode_bn_finalize_apply_relu(const double* sums, int64_t M_stat, int32_t C, const float* gamma, const float* beta,
                                 float eps, float momentum, float* mean, float* invstd, float* scale, float* shift,
                                 float* running_mean, float* running_var, const float* y, int64_t M, int32_t relu,
-                                float* out, void* out_f16, float f16_scale, const mode_planes_t* planes_host, void* stream);
-int mode_bn_relu_bwd_reduce_prezeroed(const float* y, const float* dout, int64_t M, int32_t C, const float* gamma,
-                                      const float* beta, const float* mean, const float* invstd,
-                                      const mode_planes_t* planes_host, void* workspace, void* stream);
+                                float* out, void* out_f16, float f16_scale, const mode_planes_t* planes_host,
+                                const mode_rowmap_t* out_map_host, void* stream);
+int mode_bn_relu_bwd_reduce_v2(const float* y, const float* dout, int64_t M, int32_t C, const float* gamma,
+                               const float* beta, const float* mean, const float* invstd,
+                               const mode_planes_t* planes_host, void* workspace, int32_t workspace_is_zero,
+                               const mode_rowmap_t* dout_map_host, void* stream);
+int mode_bn_relu_bwd_apply_v2(const float* y, const float* dout, int64_t M, int32_t C, const float* gamma,
+                              const float* beta, const float* mean, const float* invstd, float* dgamma, float* dbeta,
+                              float* dy, void* dy_f16, float* dy_scale2, const mode_planes_t* planes_host,
+                              void* workspace, const mode_rowmap_t* dout_map_host, void* stream);
 
 /* Fused-exchange forms (peer memory, D-sharded slabs).  NULL descriptors give the plain behaviour.
  *   mode_bn_finalize_ex:        `gather` != NULL: the statistics are the rank-ordered sum of the gathered slots (sums ignored).
@@ -298,6 +317,9 @@ int mode_cast_f16_ex(const float* src, void* dst_f16, int64_t n, float scale, co
 /* fp32 [rows][c] -> fp16 [rows][c_pad], zero channels appended (c_pad % 8 == 0; the stem layer's Ci = 1 -> 32 operand):
  * replaces the host-side zero-pad copy in front of F.conv3d's operand (fnet/nn_modules/RepMode.py:207). */
 int mode_cast_f16_pad(const float* src, void* dst_f16, int64_t rows, int32_t c, int32_t c_pad, void* stream);
+/* fp32 [rows][ca] ++ fp32 [rows][cb] -> fp16 [rows][ca + cb] (saturated): the decoder's torch.cat((x_skip, x), 1)
+ * (fnet/nn_modules/RepMode.py:106) folded into the staging of the conv operand; ca, cb multiples of 4. */
+int mode_cast_f16_cat(const float* a, int32_t ca, const float* b, int32_t cb, void* dst_f16, int64_t rows, void* stream);
 /* amax[0] = max(amax[0], max |src|) (amax must be zero-initialised by the caller; device scalar). */
 int mode_amax(const float* src, int64_t n, float* amax, void* stream);
 /* Same over k <= 8 tensors in one launch (srcs_host / counts_host are HOST arrays of device pointers / sizes). */

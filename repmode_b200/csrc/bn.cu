@@ -39,6 +39,40 @@ struct Planes {
 static bool planes_trivial(const mode_planes_t* p) {
     return p->own_lo <= 0 && p->own_hi >= p->D && p->valid_lo <= 0 && p->valid_hi >= p->D;
 }
+// Where row r of the tensor a kernel WALKS lives in a second tensor it reads or writes (mode_rowmap_t by value):
+//   d2s: the walked tensor is the [voxels][8][C] output of the transposed stride-2 GEMM (RepMode.py:97-101 as a GEMM, rows in
+//        (n, d, h, w, kd, kh, kw) order) and the mapped tensor is the NDHWC volume of twice the size per axis -- the
+//        depth-to-space scatter / gather happens inside the BatchNorm kernels instead of as a permute copy;
+//   pitch: floats between consecutive rows of the mapped tensor (a channel range of a wider tensor: the gradient of one
+//        half of the decoder's concatenated input).
+struct RowMap {
+    int active, d2s;
+    int D, H, W;               // the LOW-resolution grid (rows / 8 = N * D * H * W)
+    long long pitch;
+    __device__ __forceinline__ long long offset(long long row, int C) const {     // element offset of (row, channel 0)
+        if (!active) return row * C;
+        long long r = row;
+        if (d2s) {
+            const unsigned tap = (unsigned)(row & 7);
+            unsigned m = (unsigned)(row >> 3);                                    // < 2^32 voxels on this path
+            const unsigned w = m % (unsigned)W; m /= (unsigned)W;
+            const unsigned h = m % (unsigned)H; m /= (unsigned)H;
+            const unsigned d = m % (unsigned)D; const unsigned n = m / (unsigned)D;
+            r = (((long long)n * (2 * D) + (2 * d + (tap >> 2))) * (2 * H) + (2 * h + ((tap >> 1) & 1))) * (2LL * W) +
+                (2 * w + (tap & 1));
+        }
+        return r * pitch;
+    }
+};
+static RowMap to_rowmap(const mode_rowmap_t* m, int C) {
+    RowMap r{0, 0, 1, 1, 1, (long long)C};
+    if (m != nullptr) {
+        r.d2s = m->d2s; r.D = m->D; r.H = m->H; r.W = m->W;
+        r.pitch = m->pitch > 0 ? m->pitch : C;
+        r.active = (r.d2s != 0 || r.pitch != C) ? 1 : 0;
+    }
+    return r;
+}
 static Planes to_planes(const mode_planes_t* p) {
     Planes q;
     q.rows_per_plane = p->rows_per_plane; q.D = p->D; q.own_lo = p->own_lo; q.own_hi = p->own_hi;
@@ -166,7 +200,7 @@ __global__ void __launch_bounds__(BN_THREADS) bn_apply_kernel(const float* __res
                                                               const float* __restrict__ scale,
                                                               const float* __restrict__ shift, int relu,
                                                               float* __restrict__ out, __half* __restrict__ out16,
-                                                              float f16_scale, Planes pl, BnFinalize fin) {
+                                                              float f16_scale, Planes pl, BnFinalize fin, RowMap om) {
     __shared__ float ssc[BN_MAXC], ssh[BN_MAXC];
     if (fin.sums != nullptr) {
         for (int c = threadIdx.x; c < C; c += BN_THREADS) {
@@ -215,14 +249,15 @@ __global__ void __launch_bounds__(BN_THREADS) bn_apply_kernel(const float* __res
             w.z = fmaf(w.z, ssc[c + 2], ssh[c + 2]); w.w = fmaf(w.w, ssc[c + 3], ssh[c + 3]);
             if (relu) { w.x = fmaxf(w.x, 0.f); w.y = fmaxf(w.y, 0.f); w.z = fmaxf(w.z, 0.f); w.w = fmaxf(w.w, 0.f); }
             if (PLANES && pl.kind((i * 4) / C) == 0) w = make_float4(0.f, 0.f, 0.f, 0.f);   // beyond the global volume
-            if (out) *reinterpret_cast<float4*>(out + i * 4) = w;
+            const int64_t o = om.active ? om.offset((i * 4) / C, C) + c : i * 4;            // (depth-to-space) destination
+            if (out) *reinterpret_cast<float4*>(out + o) = w;
             if (out16) {
                 __half2 a = sat_half2(w.x * f16_scale, w.y * f16_scale);
                 __half2 b = sat_half2(w.z * f16_scale, w.w * f16_scale);
                 uint2 pk;
                 pk.x = *reinterpret_cast<uint32_t*>(&a);
                 pk.y = *reinterpret_cast<uint32_t*>(&b);
-                *reinterpret_cast<uint2*>(out16 + i * 4) = pk;
+                *reinterpret_cast<uint2*>(out16 + o) = pk;
             }
         }
     }
@@ -293,7 +328,7 @@ __global__ void __launch_bounds__(BN_THREADS, 3) bn_bwd_reduce_vec_kernel(const 
                                                                           const float* __restrict__ mean,
                                                                           const float* __restrict__ invstd,
                                                                           double* __restrict__ red, long long* __restrict__ mx,
-                                                                          Planes pl, PeerPush pp) {
+                                                                          Planes pl, PeerPush pp, RowMap dm) {
     const int vpr = C >> 2;
     const int rows_per_iter = BN_THREADS / vpr;
     const int lane_v = threadIdx.x % vpr, lane_r = threadIdx.x / vpr;
@@ -313,7 +348,7 @@ __global__ void __launch_bounds__(BN_THREADS, 3) bn_bwd_reduce_vec_kernel(const 
             const int64_t rr = r + u * stride;
             if (rr < M) {
                 yv[u] = ld_stream(y + rr * C + lane_v * 4);
-                dv[u] = ld_stream(dout + rr * C + lane_v * 4);
+                dv[u] = ld_stream(dout + (dm.active ? dm.offset(rr, C) : rr * C) + lane_v * 4);
             }
         }
 #pragma unroll
@@ -410,7 +445,7 @@ __global__ void __launch_bounds__(BN_THREADS, 4) bn_bwd_apply_vec_kernel(const f
                                                                          float* __restrict__ dy, __half* __restrict__ dy16,
                                                                          float* __restrict__ scale2, Planes pl,
                                                                          long long m_div, HaloPush hp,
-                                                                         const double* __restrict__ mx_own) {
+                                                                         const double* __restrict__ mx_own, RowMap dm) {
     // mx_own != nullptr (r2w): the power-of-two fp16 scale of dy is derived HERE, by every block, from the per-channel
     // bound of bn_bwd_scale_kernel (same expression, same bits); block 0 publishes {scale, 1/scale} for K3 / K4.  Saves the
     // one-block scale kernel and its boundary on the critical path of every training backward.
@@ -456,8 +491,9 @@ __global__ void __launch_bounds__(BN_THREADS, 4) bn_bwd_apply_vec_kernel(const f
         for (int u = 0; u < 2; ++u) {
             const int64_t kk = k + u * stride;
             if (kk < nvec) {
-                yv[u] = ld_stream(y + (nvec - 1 - kk) * 4);
-                dv[u] = ld_stream(dout + (nvec - 1 - kk) * 4);
+                const int64_t iv = nvec - 1 - kk;
+                yv[u] = ld_stream(y + iv * 4);
+                dv[u] = ld_stream(dout + (dm.active ? dm.offset((iv * 4) / C, C) + (iv * 4) % C : iv * 4));
             }
         }
 #pragma unroll
@@ -605,6 +641,38 @@ __global__ void __launch_bounds__(256) cast_f16_pad_kernel(const float* __restri
     }
 }
 
+// fp32 [rows][ca] ++ fp32 [rows][cb] -> fp16 [rows][ca + cb]: the decoder's skip concatenation (torch.cat((x_skip, x), 1),
+// RepMode.py:106) folded into the operand staging of the conv that consumes it -- the concatenated fp32 tensor is never
+// written.  One thread per 4 output channels (ca, cb multiples of 4), four loads in flight, saturated like cast_f16_kernel.
+__global__ void __launch_bounds__(256) cast_f16_cat_kernel(const float* __restrict__ a, int ca, const float* __restrict__ b,
+                                                           int cb, __half* __restrict__ dst, int64_t rows) {
+    const int cv = (ca + cb) >> 2, cav = ca >> 2;
+    const int64_t nvec = rows * cv;
+    const int64_t stride = (int64_t)gridDim.x * 256;
+    for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < nvec; i += 4 * stride) {
+        float4 v[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int64_t k = i + u * stride;
+            if (k < nvec) {
+                const int64_t row = k / cv;
+                const int col = (int)(k - row * cv);
+                v[u] = col < cav ? ld_stream(a + (row * cav + col) * 4) : ld_stream(b + (row * (cv - cav) + (col - cav)) * 4);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int64_t k = i + u * stride;
+            if (k >= nvec) continue;
+            __half2 lo = sat_half2(v[u].x, v[u].y), hi = sat_half2(v[u].z, v[u].w);
+            uint2 pk;
+            pk.x = *reinterpret_cast<uint32_t*>(&lo);
+            pk.y = *reinterpret_cast<uint32_t*>(&hi);
+            *reinterpret_cast<uint2*>(dst + k * 4) = pk;
+        }
+    }
+}
+
 __global__ void __launch_bounds__(256) amax_kernel(const float* __restrict__ src, int64_t n, float* amax) {
     float m = 0.f;
     for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < n; i += (int64_t)gridDim.x * 256)
@@ -714,7 +782,11 @@ extern "C" int mode_bn_finalize(const double* sums, int64_t M, int32_t C, const 
 
 static int bn_apply_launch(const float* y, int64_t M, int32_t C, const float* scale, const float* shift, int32_t relu,
                            float* out, void* out_f16, float f16_scale, const mode_planes_t* planes, const BnFinalize& fin,
-                           void* stream) {
+                           const mode_rowmap_t* out_map, void* stream) {
+    const RowMap om = to_rowmap(out_map, C);
+    if (om.active && (om.pitch & 3)) MODE_FAIL("mode_bn_apply_relu: mapped output needs pitch %% 4 == 0");
+    if (om.d2s && ((M & 7) || M / 8 % ((int64_t)om.D * om.H * om.W) != 0))
+        MODE_FAIL("mode_bn_apply_relu: depth-to-space map does not match M");
     cudaStream_t st = (cudaStream_t)stream;
     const int64_t total = M * C;
     const bool aligned = ((reinterpret_cast<uintptr_t>(y) | reinterpret_cast<uintptr_t>(out)) & 15) == 0 &&
@@ -723,12 +795,13 @@ static int bn_apply_launch(const float* y, int64_t M, int32_t C, const float* sc
         const int64_t want = ceil_div(total / 4, BN_THREADS * 4);
         if (planes && !planes_trivial(planes))
             bn_apply_kernel<true><<<wave_grid(bn_apply_kernel<true>, BN_THREADS, want), BN_THREADS, 0, st>>>(y, total, C, scale, shift, relu, out, (__half*)out_f16,
-                                                               f16_scale, to_planes(planes), fin);
+                                                               f16_scale, to_planes(planes), fin, om);
         else
             bn_apply_kernel<false><<<wave_grid(bn_apply_kernel<false>, BN_THREADS, want), BN_THREADS, 0, st>>>(y, total, C, scale, shift, relu, out, (__half*)out_f16,
-                                                                f16_scale, Planes{}, fin);
+                                                                f16_scale, Planes{}, fin, om);
     } else {
         if (planes) MODE_FAIL("mode_bn_apply_relu: plane ranges need C %% 4 == 0 and 16-byte aligned tensors");
+        if (om.active) MODE_FAIL("mode_bn_apply_relu: a mapped output needs C %% 4 == 0 and 16-byte aligned tensors");
         if (fin.sums != nullptr) {                 // scalar layout: finalize as its own launch
             bn_finalize_kernel<<<(unsigned)ceil_div(C, 128), 128, 0, st>>>(fin.sums, fin.M, C, fin.gamma, fin.beta, fin.eps,
                                                                            fin.momentum, fin.mean, fin.invstd, fin.scale,
@@ -750,18 +823,19 @@ extern "C" int mode_bn_apply_relu(const float* y, int64_t M, int32_t C, const fl
                                   const mode_planes_t* planes, void* stream) {
     if (!y || !scale || !shift || (!out && !out_f16) || M <= 0 || C <= 0 || C > BN_MAXC)
         MODE_FAIL("mode_bn_apply_relu: bad arguments (C=%d)", C);
-    return bn_apply_launch(y, M, C, scale, shift, relu, out, out_f16, f16_scale, planes, BnFinalize{}, stream);
+    return bn_apply_launch(y, M, C, scale, shift, relu, out, out_f16, f16_scale, planes, BnFinalize{}, nullptr, stream);
 }
 
 extern "C" int mode_bn_finalize_apply_relu(const double* sums, int64_t M_stat, int32_t C, const float* gamma,
                                            const float* beta, float eps, float momentum, float* mean, float* invstd,
                                            float* scale, float* shift, float* running_mean, float* running_var,
                                            const float* y, int64_t M, int32_t relu, float* out, void* out_f16,
-                                           float f16_scale, const mode_planes_t* planes, void* stream) {
+                                           float f16_scale, const mode_planes_t* planes, const mode_rowmap_t* out_map,
+                                           void* stream) {
     if (!sums || !scale || !shift || !y || (!out && !out_f16) || M <= 0 || M_stat <= 0 || C <= 0 || C > BN_MAXC)
         MODE_FAIL("mode_bn_finalize_apply_relu: bad arguments (C=%d)", C);
     BnFinalize fin{sums, (long long)M_stat, gamma, beta, eps, momentum, mean, invstd, scale, shift, running_mean, running_var};
-    return bn_apply_launch(y, M, C, scale, shift, relu, out, out_f16, f16_scale, planes, fin, stream);
+    return bn_apply_launch(y, M, C, scale, shift, relu, out, out_f16, f16_scale, planes, fin, out_map, stream);
 }
 
 // {sum dz, sum dz*xhat}[C] then {max |dz|, max |xhat|}[C], ALL doubles: one contiguous fp64 vector a D-sharded caller can
@@ -771,9 +845,11 @@ extern "C" int64_t mode_bn_bwd_workspace_bytes(int32_t C) { return (int64_t)C * 
 static int bn_bwd_reduce_launch(const float* y, const float* dout, int64_t M, int32_t C, const float* gamma,
                                 const float* beta, const float* mean, const float* invstd,
                                 const mode_planes_t* planes, void* workspace_v, const mode_peer_push_t* push,
-                                bool workspace_is_zero, void* stream) {
+                                bool workspace_is_zero, const mode_rowmap_t* dout_map, void* stream) {
     if (!y || !dout || !mean || !invstd || !workspace_v || M <= 0 || C <= 0 || C > BN_MAXC)
         MODE_FAIL("mode_bn_relu_bwd_reduce: bad arguments (C=%d)", C);
+    const RowMap dm = to_rowmap(dout_map, C);
+    if (dm.active && (dm.pitch & 3)) MODE_FAIL("mode_bn_relu_bwd_reduce: mapped dout needs pitch %% 4 == 0");
     const PeerPush pp = to_peer_push(push);
     if (pp.n < 0 || pp.n > 8 || (pp.n > 0 && !pp.ticket)) MODE_FAIL("mode_bn_relu_bwd_reduce: bad push descriptor");
     cudaStream_t st = (cudaStream_t)stream;
@@ -787,12 +863,13 @@ static int bn_bwd_reduce_launch(const float* y, const float* dout, int64_t M, in
         const int64_t want = ceil_div(M, rpi * 4);
         if (planes && !planes_trivial(planes))
             bn_bwd_reduce_vec_kernel<true><<<wave_grid(bn_bwd_reduce_vec_kernel<true>, BN_THREADS, want), BN_THREADS, 0, st>>>(y, dout, M, C, gamma, beta, mean, invstd,
-                                                                        workspace, mx, to_planes(planes), pp);
+                                                                        workspace, mx, to_planes(planes), pp, dm);
         else
             bn_bwd_reduce_vec_kernel<false><<<wave_grid(bn_bwd_reduce_vec_kernel<false>, BN_THREADS, want), BN_THREADS, 0, st>>>(y, dout, M, C, gamma, beta, mean, invstd,
-                                                                         workspace, mx, Planes{}, pp);
+                                                                         workspace, mx, Planes{}, pp, dm);
     } else {
         if (planes) MODE_FAIL("mode_bn_relu_bwd_reduce: plane ranges need C %% 4 == 0 and 16-byte aligned tensors");
+        if (dm.active) MODE_FAIL("mode_bn_relu_bwd_reduce: a mapped dout needs C %% 4 == 0 and 16-byte aligned tensors");
         if (pp.n > 0) MODE_FAIL("mode_bn_relu_bwd_reduce: the fused push needs C %% 4 == 0 and 16-byte aligned tensors");
         const int gx = (int)max((int64_t)1, min(ceil_div(M, BN_THREADS * 8), (int64_t)64));
         bn_bwd_reduce_kernel<<<dim3(gx, C), BN_THREADS, 0, st>>>(y, dout, M, C, gamma, beta, mean, invstd, workspace, mx);
@@ -805,29 +882,33 @@ extern "C" int mode_bn_relu_bwd_reduce_ex(const float* y, const float* dout, int
                                           const float* beta, const float* mean, const float* invstd,
                                           const mode_planes_t* planes, void* workspace_v, const mode_peer_push_t* push,
                                           void* stream) {
-    return bn_bwd_reduce_launch(y, dout, M, C, gamma, beta, mean, invstd, planes, workspace_v, push, false, stream);
+    return bn_bwd_reduce_launch(y, dout, M, C, gamma, beta, mean, invstd, planes, workspace_v, push, false, nullptr, stream);
 }
 
 extern "C" int mode_bn_relu_bwd_reduce(const float* y, const float* dout, int64_t M, int32_t C, const float* gamma,
                                        const float* beta, const float* mean, const float* invstd,
                                        const mode_planes_t* planes, void* workspace_v, void* stream) {
-    return bn_bwd_reduce_launch(y, dout, M, C, gamma, beta, mean, invstd, planes, workspace_v, nullptr, false, stream);
+    return bn_bwd_reduce_launch(y, dout, M, C, gamma, beta, mean, invstd, planes, workspace_v, nullptr, false, nullptr, stream);
 }
 
-extern "C" int mode_bn_relu_bwd_reduce_prezeroed(const float* y, const float* dout, int64_t M, int32_t C,
-                                                 const float* gamma, const float* beta, const float* mean,
-                                                 const float* invstd, const mode_planes_t* planes, void* workspace_v,
-                                                 void* stream) {
-    return bn_bwd_reduce_launch(y, dout, M, C, gamma, beta, mean, invstd, planes, workspace_v, nullptr, true, stream);
+extern "C" int mode_bn_relu_bwd_reduce_v2(const float* y, const float* dout, int64_t M, int32_t C, const float* gamma,
+                                          const float* beta, const float* mean, const float* invstd,
+                                          const mode_planes_t* planes, void* workspace_v, int32_t workspace_is_zero,
+                                          const mode_rowmap_t* dout_map, void* stream) {
+    return bn_bwd_reduce_launch(y, dout, M, C, gamma, beta, mean, invstd, planes, workspace_v, nullptr,
+                                workspace_is_zero != 0, dout_map, stream);
 }
 
-extern "C" int mode_bn_relu_bwd_apply_ex(const float* y, const float* dout, int64_t M, int32_t C, const float* gamma,
-                                         const float* beta, const float* mean, const float* invstd, float* dgamma,
-                                         float* dbeta, float* dy, void* dy_f16, float* dy_scale2,
-                                         const mode_planes_t* planes, void* workspace_v,
-                                         const mode_peer_gather_t* gather, const mode_halo_push_t* halo, void* stream) {
+static int bn_bwd_apply_launch(const float* y, const float* dout, int64_t M, int32_t C, const float* gamma,
+                               const float* beta, const float* mean, const float* invstd, float* dgamma,
+                               float* dbeta, float* dy, void* dy_f16, float* dy_scale2,
+                               const mode_planes_t* planes, void* workspace_v,
+                               const mode_peer_gather_t* gather, const mode_halo_push_t* halo,
+                               const mode_rowmap_t* dout_map, void* stream) {
     if (!y || !dout || !mean || !invstd || !workspace_v || (!dy && !dy_f16) || M <= 0 || C <= 0 || C > BN_MAXC)
         MODE_FAIL("mode_bn_relu_bwd_apply: bad arguments (C=%d)", C);
+    const RowMap dm = to_rowmap(dout_map, C);
+    if (dm.active && (dm.pitch & 3)) MODE_FAIL("mode_bn_relu_bwd_apply: mapped dout needs pitch %% 4 == 0");
     if (dy_f16 && !dy_scale2) MODE_FAIL("mode_bn_relu_bwd_apply: dy_f16 needs dy_scale2");
     cudaStream_t st = (cudaStream_t)stream;
     double* workspace = (double*)workspace_v;
@@ -855,19 +936,38 @@ extern "C" int mode_bn_relu_bwd_apply_ex(const float* y, const float* dout, int6
         if (planes && !planes_trivial(planes))
             bn_bwd_apply_vec_kernel<true><<<wave_grid(bn_bwd_apply_vec_kernel<true>, BN_THREADS, want), BN_THREADS, 0, st>>>(y, dout, M, C, gamma, beta, mean, invstd, workspace,
                                                                        dgamma, dbeta, dy, (__half*)dy_f16, dy_scale2,
-                                                                       to_planes(planes), m_div, hp, mx_own);
+                                                                       to_planes(planes), m_div, hp, mx_own, dm);
         else
             bn_bwd_apply_vec_kernel<false><<<wave_grid(bn_bwd_apply_vec_kernel<false>, BN_THREADS, want), BN_THREADS, 0, st>>>(y, dout, M, C, gamma, beta, mean, invstd,
                                                                         workspace, dgamma, dbeta, dy, (__half*)dy_f16,
-                                                                        dy_scale2, Planes{}, m_div, hp, mx_own);
+                                                                        dy_scale2, Planes{}, m_div, hp, mx_own, dm);
     } else {
         if (planes) MODE_FAIL("mode_bn_relu_bwd_apply: plane ranges need C %% 4 == 0 and 16-byte aligned tensors");
+        if (dm.active) MODE_FAIL("mode_bn_relu_bwd_apply: a mapped dout needs C %% 4 == 0 and 16-byte aligned tensors");
         if (hp.on()) MODE_FAIL("mode_bn_relu_bwd_apply: the fused halo push needs C %% 4 == 0 and 16-byte aligned tensors");
         bn_bwd_apply_kernel<<<stream_grid(M * C, BN_THREADS * 8), BN_THREADS, 0, st>>>(
             y, dout, M, C, gamma, beta, mean, invstd, workspace, dgamma, dbeta, dy, (__half*)dy_f16, dy_scale2);
     }
     MODE_LAUNCH_CHECK();
     return 0;
+}
+
+extern "C" int mode_bn_relu_bwd_apply_ex(const float* y, const float* dout, int64_t M, int32_t C, const float* gamma,
+                                         const float* beta, const float* mean, const float* invstd, float* dgamma,
+                                         float* dbeta, float* dy, void* dy_f16, float* dy_scale2,
+                                         const mode_planes_t* planes, void* workspace_v,
+                                         const mode_peer_gather_t* gather, const mode_halo_push_t* halo, void* stream) {
+    return bn_bwd_apply_launch(y, dout, M, C, gamma, beta, mean, invstd, dgamma, dbeta, dy, dy_f16, dy_scale2, planes,
+                               workspace_v, gather, halo, nullptr, stream);
+}
+
+extern "C" int mode_bn_relu_bwd_apply_v2(const float* y, const float* dout, int64_t M, int32_t C, const float* gamma,
+                                         const float* beta, const float* mean, const float* invstd, float* dgamma,
+                                         float* dbeta, float* dy, void* dy_f16, float* dy_scale2,
+                                         const mode_planes_t* planes, void* workspace_v, const mode_rowmap_t* dout_map,
+                                         void* stream) {
+    return bn_bwd_apply_launch(y, dout, M, C, gamma, beta, mean, invstd, dgamma, dbeta, dy, dy_f16, dy_scale2, planes,
+                               workspace_v, nullptr, nullptr, dout_map, stream);
 }
 
 extern "C" int mode_bn_relu_bwd_apply(const float* y, const float* dout, int64_t M, int32_t C, const float* gamma,
@@ -912,6 +1012,19 @@ extern "C" int mode_cast_f16_pad(const float* src, void* dst_f16, int64_t rows, 
     const int64_t total = rows * (c_pad >> 3);
     cast_f16_pad_kernel<<<wave_grid(cast_f16_pad_kernel, 256, ceil_div(total, 256)), 256, 0, (cudaStream_t)stream>>>(
         src, (__half*)dst_f16, rows, c, c_pad);
+    MODE_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int mode_cast_f16_cat(const float* a, int32_t ca, const float* b, int32_t cb, void* dst_f16, int64_t rows,
+                                 void* stream) {
+    if (!a || !b || !dst_f16 || rows <= 0 || ca <= 0 || cb <= 0 || (ca & 3) || (cb & 3))
+        MODE_FAIL("mode_cast_f16_cat: bad arguments (ca=%d, cb=%d: multiples of 4)", ca, cb);
+    if ((reinterpret_cast<uintptr_t>(a) | reinterpret_cast<uintptr_t>(b)) & 15 || (reinterpret_cast<uintptr_t>(dst_f16) & 7))
+        MODE_FAIL("mode_cast_f16_cat: pointers must be 16-byte (sources) / 8-byte (dst) aligned");
+    const int64_t nvec = rows * ((ca + cb) >> 2);
+    cast_f16_cat_kernel<<<wave_grid(cast_f16_cat_kernel, 256, ceil_div(nvec, 256 * 4)), 256, 0, (cudaStream_t)stream>>>(
+        a, ca, b, cb, (__half*)dst_f16, rows);
     MODE_LAUNCH_CHECK();
     return 0;
 }

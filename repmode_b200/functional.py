@@ -391,6 +391,15 @@ def _sample_index(n, dev, identity):
     return t
 
 
+def cast_f16_cat(a, b):
+    """fp32 [..., Ca] ++ fp32 [..., Cb] -> fp16 [..., Ca + Cb] in one pass (the skip concatenation folded into the cast)."""
+    lib = _lib.load()
+    ca, cb = a.shape[-1], b.shape[-1]
+    out = torch.empty(a.shape[:-1] + (ca + cb,), dtype=torch.float16, device=a.device)
+    _lib.check(lib.mode_cast_f16_cat(_p(a), ca, _p(b), cb, _p(out), a.numel() // ca, _stream()), "mode_cast_f16_cat")
+    return out
+
+
 class ModeConvFunction(torch.autograd.Function):
     """MoDEConv.forward as one autograd node.
 
@@ -403,11 +412,17 @@ class ModeConvFunction(torch.autograd.Function):
     @torch.amp.custom_fwd(device_type="cuda", cast_inputs=torch.float32)
     @_on_device_of_first
     def forward(ctx, x, gate_in, k5, k3, k1, a3, a5, gate_w, gate_b, bn_w, bn_b, running_mean, running_var, training,
-                conv_type, precision, shard=None, eps=BN_EPS, momentum=BN_MOMENTUM, batches_tracked=None, prebuilt=None):
+                conv_type, precision, shard=None, eps=BN_EPS, momentum=BN_MOMENTUM, batches_tracked=None, prebuilt=None,
+                x2=None):
+        """x2 (optional): a second input concatenated to x along the channels -- MoDEConv(cat((x, x2), 1), t), the decoder's
+        skip connection (RepMode.py:106) -- without the concatenated fp32 tensor ever being written."""
         _require_cuda(x, gate_in, k5)
         lib = _lib.load()
         n, ci_x, d, h, wd = x.shape
         layer, ci, co = _layer(k5, k3, k1, a3, a5, gate_w, gate_b)
+        c1 = ci_x
+        if x2 is not None:
+            ci_x += x2.shape[1]
         if ci_x != ci:
             raise RuntimeError(f"MoDEConv: input has {ci_x} channels, layer expects {ci}")
         dev = x.device
@@ -421,12 +436,16 @@ class ModeConvFunction(torch.autograd.Function):
         else:                                   # eval: the whole batch uses sample 0's kernel (RepMode.py:209-210)
             U, gate_u = 1, gate_in[:1].contiguous()
         sample_u = _sample_index(n, dev, training)
-        needs_dx = ctx.needs_input_grad[0]
+        needs_dx = ctx.needs_input_grad[0] or (x2 is not None and ctx.needs_input_grad[-1])
         needs_dw = any(ctx.needs_input_grad[2:9])
         use_umma = precision == "f16" and umma_shape_ok(ci, co, d, h, wd)
         dtype = _lib.MODE_F16 if use_umma else _lib.MODE_F32
 
+        fold_cat = x2 is not None and use_umma and c1 % 4 == 0 and (ci - c1) % 4 == 0 and ci % 32 == 0
+        if x2 is not None and not fold_cat:
+            x = torch.cat((x, x2), 1)                   # fp32 SIMT path / odd widths: the plain concatenation
         xn = to_ndhwc(x)
+        x2n = to_ndhwc(x2) if fold_cat else None
         w_s2 = None
         ci_p, co_p = (_pad32(ci), _pad32(co)) if use_umma else (ci, co)
         w_scale = W_SCALE_F16 if use_umma else 1.0
@@ -457,7 +476,9 @@ class ModeConvFunction(torch.autograd.Function):
                 side_work()
         else:
             g, w_fwd, w_dg = reparam_fwd(layer, gate_u, U, ci, co, dtype, needs_dx, w_scale, fork=k1_fork, post=side_work)
-        if use_umma:
+        if fold_cat:
+            x_op = cast_f16_cat(xn, x2n)
+        elif use_umma:
             x_op = cast_f16(xn) if ci_p == ci else cast_f16_pad(xn, ci_p)
         else:
             x_op = xn
@@ -487,7 +508,7 @@ class ModeConvFunction(torch.autograd.Function):
                 _lib.check(lib.mode_bn_finalize_apply_relu(_p(sums), m_stat, co, _p(bn_w), _p(bn_b), float(eps),
                                                            float(momentum), _p(mean), _p(invstd), _p(scale), _p(shift),
                                                            _p(running_mean), _p(running_var), _p(y), m_rows, 1, _p(out),
-                                                           None, 1.0, pl_ref, _stream()), "mode_bn_finalize_apply_relu")
+                                                           None, 1.0, pl_ref, None, _stream()), "mode_bn_finalize_apply_relu")
             else:
                 invstd_r = torch.rsqrt(running_var + eps)
                 scale = (bn_w * invstd_r).contiguous()
@@ -505,6 +526,7 @@ class ModeConvFunction(torch.autograd.Function):
             ctx.save_for_backward(None, x_w if needs_dw else None, y if normal else None, g, w_dg,
                                   gate_u, sample_u, k5, k3, k1, a3, a5, gate_w, gate_b, bn_w, bn_b, mean, invstd, w_s2)
             ctx.cfg = (n, d, h, wd, ci, co, U, normal, use_umma, needs_dx, needs_dw, ci_p, co_p)
+            ctx.split = c1 if x2 is not None else None
         return from_ndhwc(out)
 
     @staticmethod
@@ -528,7 +550,7 @@ class ModeConvFunction(torch.autograd.Function):
             dgamma = torch.empty(co, dtype=torch.float32, device=dev)
             dbeta = torch.empty(co, dtype=torch.float32, device=dev)
             ws, ctx.bwd_ws = ctx.bwd_ws, None           # zeroed during the forward; a second backward zeroes its own
-            reduce_fn = lib.mode_bn_relu_bwd_reduce_prezeroed if ws is not None else lib.mode_bn_relu_bwd_reduce
+            prezeroed = 1 if ws is not None else 0
             if ws is None:
                 ws = torch.empty(int(lib.mode_bn_bwd_workspace_bytes(co)), dtype=torch.uint8, device=dev)
             planes = shard.planes(h * wd, d) if shard is not None else None
@@ -538,8 +560,9 @@ class ModeConvFunction(torch.autograd.Function):
                 # "halo copy" planes (valid, not owned): declare every plane one.  dgamma / dbeta are still the plain sums.
                 planes = _lib.ModePlanes(m_rows, 1, 0, 0, 0, 1, m_rows)
             pl = ctypes.byref(planes) if planes is not None else None
-            _lib.check(reduce_fn(_p(y), _p(doutn), m_rows, co, _p(bn_w), _p(bn_b), _p(mean), _p(invstd), pl, _p(ws),
-                                 _stream()), "mode_bn_relu_bwd_reduce")
+            _lib.check(lib.mode_bn_relu_bwd_reduce_v2(_p(y), _p(doutn), m_rows, co, _p(bn_w), _p(bn_b), _p(mean),
+                                                      _p(invstd), pl, _p(ws), prezeroed, None, _stream()),
+                       "mode_bn_relu_bwd_reduce")
             if shard is not None:
                 shard.all_reduce(ws[:16 * co].view(torch.float64), "mode.bwd")      # {sum dz, sum dz*xhat} over every slab
             dy_f32 = None
@@ -597,11 +620,14 @@ class ModeConvFunction(torch.autograd.Function):
                                             *[_p(o) for o in outs], _p(ws), _stream()), "mode_reparam_bwd")
             grads = outs
         dg_fork.join()
+        dx2 = None
         if needs_dx:
             if ci_p != ci:
                 dxn = dxn[..., :ci].contiguous()
             dx = from_ndhwc(dxn)
-        return (dx, None, *grads, dgamma, dbeta, None, None, None, None, None, None, None, None, None, None)
+            if ctx.split is not None:                   # two inputs: their gradients are the two channel ranges of dx
+                dx, dx2 = dx[:, :ctx.split], dx[:, ctx.split:]
+        return (dx, None, *grads, dgamma, dbeta, None, None, None, None, None, None, None, None, None, None, dx2)
 
 
 EVAL_CACHE = os.environ.get("REPMODE_EVAL_CACHE", "1") == "1"
@@ -711,7 +737,7 @@ def mode_conv_eval(x, task_ids, params, bn, conv_type, precision, cache):
     return from_ndhwc(y)
 
 
-def mode_conv(x, gate_in, params, bn, training, conv_type="normal", precision=None, shard=None, prebuilt=None):
+def mode_conv(x, gate_in, params, bn, training, conv_type="normal", precision=None, shard=None, prebuilt=None, x2=None):
     """Functional MoDEConv. params: (k5,k3,k1,a3,a5,gate_w,gate_b); bn: (weight,bias,running_mean,running_var) or None;
     shard: ShardSpec when x is one D-slab (with halos) of a larger volume."""
     bn_w, bn_b, rm, rv = bn[:4] if bn is not None else (None, None, None, None)
@@ -719,28 +745,57 @@ def mode_conv(x, gate_in, params, bn, training, conv_type="normal", precision=No
     momentum = bn[5] if bn is not None and len(bn) > 5 and bn[5] is not None else BN_MOMENTUM
     tracked = bn[6] if bn is not None and len(bn) > 6 else None      # num_batches_tracked: bumped off the critical path
     return ModeConvFunction.apply(x, gate_in, *params, bn_w, bn_b, rm, rv, training, conv_type,
-                                  precision or default_precision(), shard, eps, momentum, tracked, prebuilt)
+                                  precision or default_precision(), shard, eps, momentum, tracked, prebuilt, x2)
+
+
+def _row_pitch(t, c):
+    """t: logical [N, D, H, W, C] tensor.  Returns the row pitch (floats) if t is a channel range of a dense NDHWC tensor
+    (rows of c contiguous floats at a constant pitch >= c, pitch % 4 == 0, 16-byte aligned start), else None."""
+    if t.dtype != torch.float32 or t.dim() != 5 or t.shape[-1] != c or t.stride(-1) != 1 or (c & 3):
+        return None
+    p = t.stride(-2)
+    n, d, h, w = t.shape[:4]
+    if p < c or (p & 3) or t.data_ptr() & 15:
+        return None
+    if t.stride(2) != w * p or t.stride(1) != h * w * p or t.stride(0) != d * h * w * p:
+        return None
+    return p
 
 
 class BnReluFunction(torch.autograd.Function):
     """BatchNorm3d (+ReLU) on an NDHWC tensor with the path's own kernels (mode_bn_*): the non-MoDE BatchNorms of
-    the U-Net (`conv_down.1`, `convt.1`, reference RepMode.py:80-84,97-101) so that no layer leaves NDHWC."""
+    the U-Net (`conv_down.1`, `convt.1`, reference RepMode.py:80-84,97-101) so that no layer leaves NDHWC.
+
+    d2s = (n, d, h, w): y is the [n*d*h*w*8, C] result of the transposed stride-2 conv as a GEMM (rows in (voxel, kd, kh, kw)
+    order); the output is the NDHWC volume [n, 2d, 2h, 2w, C] -- the depth-to-space scatter happens in the apply kernel's
+    stores, the gather of the incoming gradient in the backward kernels' loads, dy comes back in y's own row order (what
+    the GEMM's backward wants): no permute copy in either direction.  An incoming gradient that is a channel range of a
+    wider NDHWC tensor (the second half of the decoder's concatenated input) is read in place through its row pitch."""
 
     @staticmethod
     @torch.amp.custom_fwd(device_type="cuda", cast_inputs=torch.float32)
     @_on_device_of_first
-    def forward(ctx, y, weight, bias, running_mean, running_var, training, shard=None, eps=BN_EPS, momentum=BN_MOMENTUM):
+    def forward(ctx, y, weight, bias, running_mean, running_var, training, shard=None, eps=BN_EPS, momentum=BN_MOMENTUM,
+                d2s=None):
         _require_cuda(y)
         lib = _lib.load()
-        yn = y.contiguous()                                    # [N,D,H,W,C] fp32
+        yn = y.contiguous()                                    # [N,D,H,W,C] fp32  (d2s: [rows, C])
         c = yn.shape[-1]
         m_rows = yn.numel() // c
         m_stat = shard.m_global if shard is not None else m_rows
         ctx.shard = shard
+        ctx.d2s = d2s
         dev = yn.device
         scale = torch.empty(c, dtype=torch.float32, device=dev)
         shift = torch.empty(c, dtype=torch.float32, device=dev)
         mean = invstd = None
+        omap = None
+        if d2s is not None:
+            n_, d_, h_, w_ = d2s
+            out = torch.empty((n_, 2 * d_, 2 * h_, 2 * w_, c), dtype=torch.float32, device=dev)
+            omap = ctypes.byref(_lib.ModeRowMap(1, d_, h_, w_, c))
+        else:
+            out = torch.empty_like(yn)
         if training:
             sums = torch.zeros(2 * c, dtype=torch.float64, device=dev)
             mean = torch.empty(c, dtype=torch.float32, device=dev)
@@ -748,17 +803,17 @@ class BnReluFunction(torch.autograd.Function):
             _lib.check(lib.mode_bn_stats(_p(yn), m_rows, c, _p(sums), _stream()), "mode_bn_stats")
             if shard is not None:
                 shard.all_reduce(sums, "bn.fwd")                         # every plane of a stride-2 level is owned: plain sum
-            out = torch.empty_like(yn)
             _lib.check(lib.mode_bn_finalize_apply_relu(_p(sums), m_stat, c, _p(weight), _p(bias), float(eps), float(momentum),
                                                        _p(mean), _p(invstd), _p(scale), _p(shift), _p(running_mean),
-                                                       _p(running_var), _p(yn), m_rows, 1, _p(out), None, 1.0, None,
+                                                       _p(running_var), _p(yn), m_rows, 1, _p(out), None, 1.0, None, omap,
                                                        _stream()), "mode_bn_finalize_apply_relu")
         else:
             invstd = torch.rsqrt(running_var + eps).contiguous()
             mean = running_mean.clone()
             scale = (weight * invstd).contiguous()
             shift = (bias - running_mean * scale).contiguous()
-            out = torch.empty_like(yn)
+            if omap is not None:
+                raise NotImplementedError("BnReluFunction: the depth-to-space form is a training-path fusion")
             _lib.check(lib.mode_bn_apply_relu(_p(yn), m_rows, c, _p(scale), _p(shift), 1, _p(out), None, 1.0, None,
                                               _stream()), "mode_bn_apply_relu")
         ctx.training = training
@@ -774,7 +829,18 @@ class BnReluFunction(torch.autograd.Function):
         c = yn.shape[-1]
         m_rows = yn.numel() // c
         dev = yn.device
-        doutn = dout.contiguous().float()
+        d2s = ctx.d2s
+        # the incoming gradient is read IN PLACE when it is a channel range of a dense NDHWC tensor (no .contiguous() copy)
+        pitch = _row_pitch(dout, c) if (d2s is not None or dout.dim() == 5) else None
+        if pitch is None:
+            doutn = dout.contiguous().float()
+            pitch = c
+        else:
+            doutn = dout
+        dmap = None
+        if d2s is not None or pitch != c:
+            n_, d_, h_, w_ = d2s if d2s is not None else (1, 1, 1, 1)
+            dmap = ctypes.byref(_lib.ModeRowMap(1 if d2s is not None else 0, d_, h_, w_, pitch))
         dgamma = torch.empty(c, dtype=torch.float32, device=dev)
         dbeta = torch.empty(c, dtype=torch.float32, device=dev)
         dy = torch.empty_like(yn)
@@ -784,17 +850,20 @@ class BnReluFunction(torch.autograd.Function):
         if not ctx.training:              # frozen statistics: every plane a "halo copy" -> no mean terms (see ModeConvFunction)
             planes = _lib.ModePlanes(m_rows, 1, 0, 0, 0, 1, m_rows)
         pl = ctypes.byref(planes) if planes is not None else None
-        _lib.check(lib.mode_bn_relu_bwd_reduce(_p(yn), _p(doutn), m_rows, c, _p(weight), _p(bias), _p(mean), _p(invstd),
-                                               pl, _p(ws), _stream()), "mode_bn_relu_bwd_reduce")
+        _lib.check(lib.mode_bn_relu_bwd_reduce_v2(_p(yn), _p(doutn), m_rows, c, _p(weight), _p(bias), _p(mean), _p(invstd),
+                                                  pl, _p(ws), 0, dmap, _stream()), "mode_bn_relu_bwd_reduce")
         if shard is not None:
             shard.all_reduce(ws[:16 * c].view(torch.float64), "bn.bwd")
-        _lib.check(lib.mode_bn_relu_bwd_apply(_p(yn), _p(doutn), m_rows, c, _p(weight), _p(bias), _p(mean), _p(invstd),
-                                              _p(dgamma), _p(dbeta), _p(dy), None, None, pl, _p(ws), _stream()),
+        _lib.check(lib.mode_bn_relu_bwd_apply_v2(_p(yn), _p(doutn), m_rows, c, _p(weight), _p(bias), _p(mean), _p(invstd),
+                                                 _p(dgamma), _p(dbeta), _p(dy), None, None, pl, _p(ws), dmap, _stream()),
                    "mode_bn_relu_bwd_apply")
         if shard is not None and shard.world() > 1:
             dgamma /= shard.world()
             dbeta /= shard.world()
-        return dy, dgamma, dbeta, None, None, None, None, None, None
+        return dy, dgamma, dbeta, None, None, None, None, None, None, None
+
+
+D2S_FUSED = os.environ.get("REPMODE_D2S_FUSED", "1") == "1"     # A/B: 0 = depth-to-space as a permute copy
 
 
 class _tf32_matmul:
@@ -878,8 +947,13 @@ def up_conv_bn_relu(x, convt_w, bn, training, shard=None, precision=None):
         y8 = torch.addmm(sh8, xn.reshape(-1, c), wf).relu_().view(n, d, h, w, 2, 2, 2, co)
         y = y8.permute(0, 1, 4, 2, 5, 3, 6, 7).reshape(n, 2 * d, 2 * h, 2 * w, co)
         return y.permute(0, 4, 1, 2, 3)
-    y8 = _gemm(xn.reshape(-1, c), wm.to(xn.dtype), precision).view(n, d, h, w, 2, 2, 2, co)
-    y = y8.permute(0, 1, 4, 2, 5, 3, 6, 7).reshape(n, 2 * d, 2 * h, 2 * w, co)
-    out = BnReluFunction.apply(y, bn.weight, bn.bias, bn.running_mean, bn.running_var, training, shard, bn.eps,
-                               bn.momentum if bn.momentum is not None else BN_MOMENTUM)
+    y8 = _gemm(xn.reshape(-1, c), wm.to(xn.dtype), precision)                 # [voxels, (kd,kh,kw,co)]
+    mom = bn.momentum if bn.momentum is not None else BN_MOMENTUM
+    if training and shard is None and y8.is_cuda and co % 4 == 0 and D2S_FUSED:
+        # the depth-to-space scatter rides on the BatchNorm apply pass (and its gather on the backward passes)
+        out = BnReluFunction.apply(y8.view(-1, co), bn.weight, bn.bias, bn.running_mean, bn.running_var, training, None,
+                                   bn.eps, mom, (n, d, h, w))
+        return out.permute(0, 4, 1, 2, 3)
+    y = y8.view(n, d, h, w, 2, 2, 2, co).permute(0, 1, 4, 2, 5, 3, 6, 7).reshape(n, 2 * d, 2 * h, 2 * w, co)
+    out = BnReluFunction.apply(y, bn.weight, bn.bias, bn.running_mean, bn.running_var, training, shard, bn.eps, mom)
     return out.permute(0, 4, 1, 2, 3)

@@ -43,6 +43,11 @@ class ModePlanes(ctypes.Structure):
                 ("m_global", ctypes.c_int64)]
 
 
+class ModeRowMap(ctypes.Structure):
+    _fields_ = [("d2s", ctypes.c_int32), ("D", ctypes.c_int32), ("H", ctypes.c_int32), ("W", ctypes.c_int32),
+                ("pitch", ctypes.c_int64)]
+
+
 class ModeHaloPush(ctypes.Structure):
     _fields_ = [("lo_dst", ctypes.c_void_p), ("lo_signal", ctypes.c_void_p), ("hi_dst", ctypes.c_void_p),
                 ("hi_signal", ctypes.c_void_p), ("bytes", ctypes.c_int64), ("ticket", ctypes.c_void_p)]
@@ -158,8 +163,10 @@ SIGNATURES = {
     "mode_cast_f16_ex": (ctypes.c_int, [_vp, _vp, _i64, _f32, _vp, ctypes.POINTER(ModeHaloPush), _vp]),
     "mode_bn_apply_relu": (ctypes.c_int, [_vp, _i64, _i32, _vp, _vp, _i32, _vp, _vp, _f32, _vp, _vp]),
     "mode_bn_finalize_apply_relu": (ctypes.c_int, [_vp, _i64, _i32, _vp, _vp, _f32, _f32, _vp, _vp, _vp, _vp, _vp, _vp,
-                                                   _vp, _i64, _i32, _vp, _vp, _f32, _vp, _vp]),
-    "mode_bn_relu_bwd_reduce_prezeroed": (ctypes.c_int, [_vp, _vp, _i64, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+                                                   _vp, _i64, _i32, _vp, _vp, _f32, _vp, _vp, _vp]),
+    "mode_bn_relu_bwd_reduce_v2": (ctypes.c_int, [_vp, _vp, _i64, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _vp, _vp]),
+    "mode_bn_relu_bwd_apply_v2": (ctypes.c_int, [_vp, _vp, _i64, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
+                                                 _vp, _vp, _vp]),
     "mode_bn_relu_bwd_reduce": (ctypes.c_int, [_vp, _vp, _i64, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "mode_bn_relu_bwd_apply": (ctypes.c_int, [_vp, _vp, _i64, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
                                               _vp, _vp]),
@@ -167,6 +174,7 @@ SIGNATURES = {
     "mode_bn_relu_bwd": (ctypes.c_int, [_vp, _vp, _i64, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "mode_cast_f16": (ctypes.c_int, [_vp, _vp, _i64, _f32, _vp, _vp]),
     "mode_cast_f16_pad": (ctypes.c_int, [_vp, _vp, _i64, _i32, _i32, _vp]),
+    "mode_cast_f16_cat": (ctypes.c_int, [_vp, _i32, _vp, _i32, _vp, _i64, _vp]),
     "mode_amax": (ctypes.c_int, [_vp, _i64, _vp, _vp]),
     "mode_amax_multi": (ctypes.c_int, [_vp, _vp, _i32, _vp, _vp]),
     "mode_f16_scale": (ctypes.c_int, [_vp, _f32, _vp, _vp]),

@@ -71,7 +71,9 @@ class MoDEConv(torch.nn.Module):
         return (self.expert_conv5x5_conv, self.expert_conv3x3_conv, self.expert_conv1x1_conv,
                 self.expert_avg3x3_conv, self.expert_avg5x5_conv, self.gate.weight, self.gate.bias)
 
-    def forward(self, x, t):
+    def forward(self, x, t, x2=None):
+        """x2: optional second input, concatenated to x along the channels (the decoder's skip connection) inside the
+        operand staging instead of by torch.cat."""
         bn = None
         if self.conv_type == 'normal':
             m = self.subsequent_layer[0]
@@ -81,11 +83,14 @@ class MoDEConv(torch.nn.Module):
         if (not self.training and not torch.is_grad_enabled() and not t.dtype.is_floating_point
                 and Fm.EVAL_CACHE):
             # Model.predict path (eval + no_grad, int task ids): W_eff of every task is built once and reused
+            if x2 is not None:
+                x = torch.cat((x, x2), 1)
             return Fm.mode_conv_eval(x, t, self._params(), bn, self.conv_type,
                                      self.precision or Fm.default_precision(), self._eval_cache)
         plan = self.__dict__.pop("_k1_plan", None)         # set by Net.forward for the layers of a grouped K1 launch
         prebuilt = plan.take(self, x.device) if plan is not None else None
-        return Fm.mode_conv(x, t, self._params(), bn, self.training, self.conv_type, self.precision, prebuilt=prebuilt)
+        return Fm.mode_conv(x, t, self._params(), bn, self.training, self.conv_type, self.precision, prebuilt=prebuilt,
+                            x2=x2)
 
 
 class MoDESubNet2Conv(torch.nn.Module):
@@ -94,8 +99,8 @@ class MoDESubNet2Conv(torch.nn.Module):
         self.conv1 = MoDEConv(num_experts, num_tasks, n_in, n_out, kernel_size=5, padding='same')
         self.conv2 = MoDEConv(num_experts, num_tasks, n_out, n_out, kernel_size=5, padding='same')
 
-    def forward(self, x, t):
-        return self.conv2(self.conv1(x, t), t)
+    def forward(self, x, t, x2=None):
+        return self.conv2(self.conv1(x, t) if x2 is None else self.conv1(x, t, x2), t)
 
 
 class MoDEEncoderBlock(torch.nn.Module):
@@ -137,7 +142,7 @@ class MoDEDecoderBlock(torch.nn.Module):
         if self.training and bn.num_batches_tracked is not None:
             bn.num_batches_tracked.add_(1)
         x = Fm.up_conv_bn_relu(x, self.convt[0].weight, bn, self.training, precision=self.conv_less.conv1.precision)
-        return self.conv_less(torch.cat((x_skip, x), 1), t)
+        return self.conv_less(x_skip, t, x)              # cat((x_skip, x), 1) happens inside conv1's operand staging
 
 
 class Net(torch.nn.Module):

@@ -279,7 +279,7 @@ def test_bn_finalize_apply_one_kernel_matches_two(m_rows, c):
     L.check(lib.mode_bn_apply_relu(Fm._p(y), m_rows, c, Fm._p(a[2]), Fm._p(a[3]), 1, Fm._p(out_a), None, 1.0, None,
                                    Fm._stream()), "mode_bn_apply_relu")
     L.check(lib.mode_bn_finalize_apply_relu(Fm._p(sums), m_rows, c, Fm._p(gamma), Fm._p(beta), 1e-5, 0.1,
-                                            *[Fm._p(t) for t in b], Fm._p(y), m_rows, 1, Fm._p(out_b), None, 1.0, None,
+                                            *[Fm._p(t) for t in b], Fm._p(y), m_rows, 1, Fm._p(out_b), None, 1.0, None, None,
                                             Fm._stream()), "mode_bn_finalize_apply_relu")
     torch.cuda.synchronize()
     assert torch.equal(out_a, out_b)
@@ -359,6 +359,72 @@ def test_reparam_fwd_grouped_bit_identical_to_per_layer():
         assert torch.equal(w0.view(torch.int16), w1.view(torch.int16)), sh
         if d0 is not None:
             assert torch.equal(d0.view(torch.int16), d1.view(torch.int16)), sh
+
+
+@pytest.mark.parametrize("precision", ["f16", "f32"])
+def test_two_input_modeconv_matches_concatenated_input(precision):
+    """MoDEConv(x, t, x2) -- the decoder's skip concatenation folded into the operand cast (mode_cast_f16_cat) -- against
+    MoDEConv(torch.cat((x, x2), 1), t): output and every gradient (both inputs, all parameters) bit-identical."""
+    from repmode_b200.nn_modules import MoDEConv
+    torch.manual_seed(14)
+    m = MoDEConv(5, 12, 64, 32).cuda().train()
+    m.precision = precision
+    a = torch.randn(2, 32, 6, 16, 16, device="cuda")
+    b = torch.randn(2, 32, 6, 16, 16, device="cuda")
+    dout = torch.randn(2, 32, 6, 16, 16, device="cuda")
+    t = torch.tensor([3, 8], device="cuda")
+
+    def run(two):
+        for p in m.parameters():
+            p.grad = None
+        x1, x2 = a.clone().requires_grad_(True), b.clone().requires_grad_(True)
+        y = m(x1, t, x2) if two else m(torch.cat((x1, x2), 1), t)
+        y.backward(dout)
+        torch.cuda.synchronize()
+        return [y.detach().clone(), x1.grad.clone(), x2.grad.clone()] + [p.grad.clone() for p in m.parameters()]
+    ref, got = run(False), run(True)
+    for i, (r, g) in enumerate(zip(ref, got)):
+        assert torch.equal(r, g), i
+
+
+@pytest.mark.parametrize("via_cat", [False, True])
+def test_up_conv_depth_to_space_inside_batchnorm_matches_permute_copy(via_cat, monkeypatch):
+    """ConvTranspose3d(k=2, s=2) + BatchNorm + ReLU (RepMode.py:97-101) with the depth-to-space scatter / gather folded into
+    the BatchNorm kernels' stores / loads (mode_rowmap_t) against the same layer with the permute copy, and (via_cat) with
+    the incoming gradient arriving as a channel range of a wider tensor -- read in place through its row pitch -- as the
+    decoder's concatenation produces it.  Output, dx, dW, dgamma, dbeta to fp32 re-association (the statistics are summed
+    in a different row order)."""
+    from repmode_b200 import functional as Fm
+    torch.manual_seed(15)
+    n, c, co, d, h, w = 2, 64, 32, 3, 6, 8
+    convt = torch.nn.ConvTranspose3d(c, co, 2, stride=2, bias=False).cuda()
+    bn = torch.nn.BatchNorm3d(co).cuda()
+    with torch.no_grad():
+        bn.weight.uniform_(0.5, 1.5); bn.bias.normal_()
+    x0 = torch.randn(n, d, h, w, c, device="cuda").permute(0, 4, 1, 2, 3)
+    skip = torch.randn(n, 2 * d, 2 * h, 2 * w, co, device="cuda").permute(0, 4, 1, 2, 3)
+    dout = torch.randn(n, 2 * d, 2 * h, 2 * w, 2 * co if via_cat else co, device="cuda").permute(0, 4, 1, 2, 3)
+
+    def run(fused):
+        monkeypatch.setattr(Fm, "D2S_FUSED", fused)
+        for p in list(convt.parameters()) + list(bn.parameters()):
+            p.grad = None
+        bn.running_mean.zero_(); bn.running_var.fill_(1.0)
+        x = x0.clone().requires_grad_(True)
+        y = Fm.up_conv_bn_relu(x, convt.weight, bn, True, precision="f32")
+        z = torch.cat((skip, y), 1) if via_cat else y
+        (z * dout).sum().backward()
+        torch.cuda.synchronize()
+        return [y.detach().clone(), x.grad.clone(), convt.weight.grad.clone(), bn.weight.grad.clone(), bn.bias.grad.clone(),
+                bn.running_mean.clone(), bn.running_var.clone()]
+    ref, got = run(False), run(True)
+    for r, g, name in zip(ref, got, ("out", "dx", "dW", "dgamma", "dbeta", "running_mean", "running_var")):
+        assert_close(g.cpu().numpy(), r.cpu().numpy(), 2e-5, name)
+    # and against torch's own layer
+    x = x0.clone().requires_grad_(True)
+    yt = torch.relu(torch.nn.functional.batch_norm(torch.nn.functional.conv_transpose3d(x, convt.weight, stride=2), None, None,
+                                                   bn.weight, bn.bias, True, 0.0, bn.eps))
+    assert_close(got[0].cpu().numpy(), yt.detach().cpu().numpy(), 1e-4, "out vs torch")
 
 
 def test_cast_f16_pad_matches_cast_then_pad():

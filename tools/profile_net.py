@@ -29,12 +29,13 @@ def main():
     events = []
     orig = NM.MoDEConv.forward
 
-    def timed_forward(self, xx, tt):
+    def timed_forward(self, xx, tt, x2=None):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        out = orig(self, xx, tt)
+        out = orig(self, xx, tt, x2)
         e1.record()
-        events.append((names[self], tuple(xx.shape), self.out_chan, e0, e1))
+        shape = tuple(xx.shape) if x2 is None else (xx.shape[0], xx.shape[1] + x2.shape[1]) + tuple(xx.shape[2:])
+        events.append((names[self], shape, self.out_chan, e0, e1))
         return out
 
     if a.train:

@@ -35,7 +35,7 @@ T = 12
 VOX = D * H * W
 FLOP_CONV = 2.0 * 125 * CI * CO * VOX            # one of fwd / dgrad / wgrad
 METRIC = "voxels/sec MoDE-conv fwd+bwd @32x128x128x32ch"
-TRAFFIC_FILES = ("r2_traffic.json", "r1_final_traffic.json", "r1e_traffic.json", "r1b_traffic.json")   # newest ncu --set full
+TRAFFIC_FILES = ("r2f_traffic.json", "r2_traffic.json", "r1_final_traffic.json", "r1e_traffic.json", "r1b_traffic.json")   # newest ncu --set full
 TRAFFIC_FILE = next((f for f in TRAFFIC_FILES                                                          # capture first
                      if os.path.exists(os.path.join(ROOT, "profiles", f))), TRAFFIC_FILES[-1])
 

@@ -661,16 +661,33 @@ def run_net_config(args, rank, local_rank, world):
         launches_eager_step = lib.mode_launch_count() - l_tr0      # a graph replay launches the same kernels
         torch.cuda.synchronize()
         run = lambda: train_step(x_dev)        # noqa: E731
-        if os.environ.get("REPMODE_BENCH_GRAPH", "1") == "1" and not sharded_cfg:
+        # the D-sharded configs go through NCCL collectives (halo send/recv, BatchNorm all-reduces): captured too, with the
+        # capture policing this thread only (NCCL's watchdog thread polls events meanwhile); the ranks agree on the outcome
+        # so that nobody replays a graph against an eagerly launching neighbour
+        want_graph = os.environ.get("REPMODE_BENCH_GRAPH", "1") == "1" and (
+            not sharded_cfg or os.environ.get("REPMODE_BENCH_GRAPH_SHARDED", "1") == "1")
+        if want_graph:
+            graph, why = None, ""
             try:
+                if world > 1:
+                    dist.barrier()
                 graph = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(graph):
+                mode = {"capture_error_mode": "thread_local"} if world > 1 else {}
+                with torch.cuda.graph(graph, **mode):
                     train_step(x_dev)
+            except Exception as e:  # noqa: BLE001
+                graph, why = None, f"{type(e).__name__}: {str(e)[:100]}"
+                torch.cuda.synchronize()
+            if world > 1:
+                ok = torch.tensor([1.0 if graph is not None else 0.0], device=dev)
+                dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+                if float(ok.item()) == 0.0 and graph is not None:
+                    graph, why = None, "another rank's capture failed"
+            if graph is not None:
                 run = graph.replay
                 notes.append("train step (fwd + bwd + mode_adam_step) captured once as a CUDA graph and replayed")
-            except Exception as e:  # noqa: BLE001
-                notes.append(f"CUDA-graph capture failed, eager launches ({type(e).__name__}: {str(e)[:100]})")
-                torch.cuda.synchronize()
+            else:
+                notes.append(f"CUDA-graph capture failed, eager launches ({why})")
         result_bytes = 4
 
     def barrier():

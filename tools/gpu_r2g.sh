@@ -1,13 +1,12 @@
 #!/bin/bash
-# r2g (1 GPU): BN streaming loads / trivial-planes fast path: tests + bench + per-kernel breakdown
-TAG=${1:-r2g}
-O=gpurun_out
-mkdir -p $O
-export PYTHONDONTWRITEBYTECODE=1
-export REPMODE_NO_BUILD=1
-timeout 500 python -m pytest tests -m gpu -q -p no:cacheprovider --timeout 120 > $O/${TAG}_pytest.log 2>&1
-echo "pytest exit $?"; grep -E "^(FAILED|ERROR)|passed|failed" $O/${TAG}_pytest.log | tail -12 | cut -c1-300
-REPMODE_BENCH_FAST=1 timeout 200 python bench.py --steps 20 --warmup 5 > $O/${TAG}_bench.json 2> $O/${TAG}_bench.err
-grep -o '"ms_per_step": [0-9.]*' $O/${TAG}_bench.json | head -1
-python tools/step_breakdown.py > $O/${TAG}_breakdown.log 2>&1; tail -22 $O/${TAG}_breakdown.log | cut -c1-120 | head -12
+# r2g (2 GPUs): does the D-sharded whole-Net train step capture as a CUDA graph with its NCCL collectives inside?
+# cfg4's per-rank slab shape (16 planes of 256x256 per rank) on 2 ranks through the dry-run hook, graph vs eager; plus smoke().
+O=gpurun_out; mkdir -p $O
+export PYTHONDONTWRITEBYTECODE=1 REPMODE_NO_BUILD=1
+timeout 120 python -c "import __graft_entry__ as g; g.smoke()" > $O/r2g_smoke.log 2>&1; echo "smoke exit $?"; tail -1 $O/r2g_smoke.log | cut -c1-300
+TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1"
+REPMODE_BENCH_CFG_DIMS=32,256,256 timeout 150 $TR --master-port 29551 bench.py --gpus 2 --config cfg4 --steps 5 --warmup 3 > $O/r2g_cfg4dims_graph.json 2> $O/r2g_cfg4dims_graph.err
+echo "graph exit $?"; grep -o '"ms_per_step": [0-9.]*\|"notes": \[[^]]*\]' $O/r2g_cfg4dims_graph.json | head -4; tail -2 $O/r2g_cfg4dims_graph.err | cut -c1-300
+REPMODE_BENCH_GRAPH_SHARDED=0 REPMODE_BENCH_CFG_DIMS=32,256,256 timeout 150 $TR --master-port 29552 bench.py --gpus 2 --config cfg4 --steps 5 --warmup 3 > $O/r2g_cfg4dims_eager.json 2> $O/r2g_cfg4dims_eager.err
+echo "eager exit $?"; grep -o '"ms_per_step": [0-9.]*\|"notes": \[[^]]*\]' $O/r2g_cfg4dims_eager.json | head -4
 echo done

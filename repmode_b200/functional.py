@@ -646,6 +646,17 @@ class EvalWeightCache:
         self.key = None
         self.w = None
 
+    def invalidate(self):
+        """Forget the cached kernels.  Needed only after an update that the version counters cannot see -- an in-place
+        write through `param.data` (EMA / SWA style); MoDEConv calls it on every switch to train mode and on
+        load_state_dict, the points at which such updates happen in practice."""
+        self.key = None
+        self.w = None
+
+    def nbytes(self):
+        """Bytes held (0.2 GB fp16 / 0.4 GB fp32 per task over the full-width U-Net's 19 layers)."""
+        return 0 if self.w is None else self.w.numel() * self.w.element_size()
+
     def get(self, params, num_tasks, ci, co, dtype, w_scale):
         key = (dtype, float(w_scale)) + tuple((p.data_ptr(), p._version) for p in params)
         if key != self.key:

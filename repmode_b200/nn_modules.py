@@ -59,6 +59,15 @@ class MoDEConv(torch.nn.Module):
         self.precision = None          # None -> REPMODE_PRECISION env / default ('f16' tensor-core path)
         self._eval_cache = Fm.EvalWeightCache()      # per-task W_eff for eval mode (not part of the state_dict)
 
+    def train(self, mode=True):
+        if mode:
+            self._eval_cache.invalidate()      # whatever updates the weights next may bypass the version counters (.data)
+        return super().train(mode)
+
+    def _load_from_state_dict(self, *args, **kwargs):
+        self._eval_cache.invalidate()
+        return super()._load_from_state_dict(*args, **kwargs)
+
     def gen_conv_kernel(self, Co, Ci, K):
         weight = torch.nn.Parameter(torch.empty(Co, Ci, K, K, K))
         torch.nn.init.kaiming_uniform_(weight, a=math.sqrt(5))

@@ -178,3 +178,25 @@ def test_sharded_block_host_glue(dry, precision):
     assert comm.calls[0][2] == (1, 10, 16, 8, 32) and comm.calls[0][3] == 2
     c = dry.calls
     assert c.count("mode_conv3d_ex") == 2 and c.count("mode_conv3d_wgrad_ex") == 1
+
+
+def test_eval_cache_invalidated_by_train_switch_and_load_state_dict(dry):
+    """Updates the tensor version counters cannot see (an in-place write through `param.data`, EMA / SWA style) are covered by
+    dropping the cached eval kernels on every switch to train mode and on load_state_dict."""
+    m = MoDEConv(5, 4, 32, 32).eval()
+    m.precision = "f16"
+    x = torch.randn(1, 32, 2, 16, 8)
+    t = torch.tensor([1])
+    with torch.no_grad():
+        m(x, t)
+        assert dry.calls.count("mode_reparam_fwd") == 1 and m._eval_cache.key is not None
+        m.expert_conv5x5_conv.data.mul_(0.5)            # invisible to _version ...
+        m(x, t)
+        assert dry.calls.count("mode_reparam_fwd") == 1
+        m.train(); m.eval()                             # ... but a train/eval round trip drops the cache
+        assert m._eval_cache.key is None and m._eval_cache.nbytes() == 0
+        m(x, t)
+        assert dry.calls.count("mode_reparam_fwd") == 2
+        m.load_state_dict(m.state_dict())
+        m(x, t)
+        assert dry.calls.count("mode_reparam_fwd") == 3

@@ -178,6 +178,12 @@ class Net(torch.nn.Module):
         self.conv_out = MoDEConv(E, T, self.mult_chan, self.out_channels, kernel_size=5, padding='same',
                                  conv_type='final')
 
+    def train(self, mode=True):
+        if mode:
+            # the captured eval graphs hold pointers into the per-layer W_eff caches, which a switch to train mode drops
+            self.__dict__.pop("_eval_graph_state", None)
+        return super().train(mode)
+
     def one_hot_task_embedding(self, task_id):
         """Kept for API compatibility (RepMode.py:44-49); built on the device without a host loop."""
         return torch.nn.functional.one_hot(task_id.to(torch.int64), self.num_tasks).float()

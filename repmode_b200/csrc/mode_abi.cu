@@ -72,7 +72,7 @@ int wgrad_split(const __half* x, const __half* dy, float* dw, int N, int D, int 
 bool wgrad_deep_supported(int D, int H, int W, int Ci, int Co);
 int64_t wgrad_deep_workspace_bytes(int N, int D, int H, int W, int Ci, int Co, int Dx, int x_off);
 int wgrad_deep(const __half* x, const __half* dy, float* dw, int N, int D, int H, int W, int Ci, int Co,
-               float out_scale, const float* out_scale_dev, void* workspace, int Dx, int x_off, cudaStream_t st);
+               float out_scale, const float* out_scale_dev, void* workspace, int Dx, int x_off, cudaStream_t st, int phase);
 
 // tcgen05 wgrad flavour behind impl = 2: the deep-tile kernel (wgrad_deep.cu; r2a on the headline layer: 112 us against
 // 135 us for the split-tap kernel of round 1); REPMODE_WGRAD_SPLIT=1 selects wgrad_split.cu (the A/B arm)
@@ -200,7 +200,12 @@ extern "C" int mode_conv3d_wgrad_ex(const void* x, const void* dy, mode_dtype_t 
         MODE_FAIL("mode_conv3d_wgrad: haloed x needs 0 <= x_off and x_off + D <= Dx (x_off=%d D=%d Dx=%d)", x_off, D, Dx);
     const bool halo = Dx != D || x_off != 0;
     cudaStream_t st = (cudaStream_t)stream;
+    // bits 8-9 of impl: 0 = the whole wgrad; 1 = the tensor-core part only; 2 = what is left after it (the slab reduce of the
+    // deep-tile kernel; nothing for the other kernels) -- a caller may start K3 between the two calls
+    const int phase = (impl >> 8) & 3;
+    impl &= 0xff;
     if (impl == 0) impl = (dtype == MODE_F16) ? 2 : 1;
+    if (phase == 2 && !(impl == 6 || (impl == 2 && (wgrad_use_deep() || halo)))) return 0;
     if (impl == 1) {
         if (dtype != MODE_F32) MODE_FAIL("mode_conv3d_wgrad: the SIMT path takes fp32 operands");
         return wgrad_simt((const float*)x, (const float*)dy, d_weff, N, D, H, W, Ci, Co, out_scale, out_scale_dev, Dx, x_off, st);
@@ -211,7 +216,7 @@ extern "C" int mode_conv3d_wgrad_ex(const void* x, const void* dy, mode_dtype_t 
             MODE_FAIL("mode_conv3d_wgrad: shape not supported by the tcgen05 path");
         // 2: deep-tile kernel unless REPMODE_WGRAD_SPLIT; 5 / 6 force the split-tap / the deep-tile kernel
         if (impl == 6 || (impl == 2 && (wgrad_use_deep() || halo)))
-            return wgrad_deep((const __half*)x, (const __half*)dy, d_weff, N, D, H, W, Ci, Co, out_scale, out_scale_dev, workspace, Dx, x_off, st);
+            return wgrad_deep((const __half*)x, (const __half*)dy, d_weff, N, D, H, W, Ci, Co, out_scale, out_scale_dev, workspace, Dx, x_off, st, phase);
         if (halo) MODE_FAIL("mode_conv3d_wgrad: the split-tap kernel (impl 5) does not take a haloed x");
         return wgrad_split((const __half*)x, (const __half*)dy, d_weff, N, D, H, W, Ci, Co, out_scale, out_scale_dev, workspace, st);
     }

@@ -401,8 +401,11 @@ int64_t wgrad_deep_workspace_bytes(int N, int D, int H, int W, int Ci, int Co, i
     return groups * (p.SL + p.SA + p.SB) * wd::PARTIAL_FLOATS * (int64_t)sizeof(float);
 }
 
+// phase: 0 = both kernels; 1 = the tensor-core kernel only (partials into the workspace); 2 = the reduce kernel only -- so
+// that a caller can start K3 (which needs nothing from K4) between the two (functional.py)
 int wgrad_deep(const __half* x, const __half* dy, float* dw, int N, int D, int H, int W, int Ci, int Co,
-               float out_scale, const float* out_scale_dev, void* workspace, int Dx, int x_off, cudaStream_t st) {
+               float out_scale, const float* out_scale_dev, void* workspace, int Dx, int x_off, cudaStream_t st,
+               int phase) {
     if (!workspace) MODE_FAIL("wgrad_deep: workspace is NULL");
     if ((reinterpret_cast<uintptr_t>(x) & 15) || (reinterpret_cast<uintptr_t>(dy) & 15) ||
         (reinterpret_cast<uintptr_t>(workspace) & 15))
@@ -432,9 +435,12 @@ int wgrad_deep(const __half* x, const __half* dy, float* dw, int N, int D, int H
     if (make_act_map(&dymapL, dy, N, D, H, W, Co, wd::TW, wd::TH, wd::L_PLANES) != 0) return -1;
     if (make_act_map(&xmapL, x, N, Dx, H, W, Ci, wd::X_COLS, wd::TH, 2) != 0) return -1;
     const int smem_bytes = wd::OPERAND_BYTES + 512 + 1024;
-    MODE_CUDA(cudaFuncSetAttribute(wgrad_deep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
-    wgrad_deep_kernel<<<(unsigned)units, wd::THREADS, smem_bytes, st>>>(dymapK, xmapA, xmapB, dymapL, xmapL, P);
-    MODE_LAUNCH_CHECK();
+    if (phase != 2) {
+        MODE_CUDA(cudaFuncSetAttribute(wgrad_deep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
+        wgrad_deep_kernel<<<(unsigned)units, wd::THREADS, smem_bytes, st>>>(dymapK, xmapA, xmapB, dymapL, xmapL, P);
+        MODE_LAUNCH_CHECK();
+    }
+    if (phase == 1) return 0;
     const int64_t total = (int64_t)N * 125 * Co * Ci / 4;
     if (total > 0x7fffffff) MODE_FAIL("wgrad_deep: d_weff too large for 32-bit indexing");
     const int grid = (int)std::max((int64_t)1, std::min(ceil_div(total, 256), (int64_t)sm_count() * 16));

@@ -325,17 +325,29 @@ class ShardSpec:
             dist.all_reduce(t, group=self.group)
 
 
-def conv3d_wgrad(x, dy, dtype, n, d, h, wd, ci, co, out_scale_dev=None, impl=0, halo=None):
-    """K4.  d = planes of dy (the OWNED planes); halo = (Dx, x_off) when x carries halo planes."""
+WGRAD_SPLIT_PHASES = os.environ.get("REPMODE_WGRAD_PHASES", "1") == "1"
+
+
+def conv3d_wgrad(x, dy, dtype, n, d, h, wd, ci, co, out_scale_dev=None, impl=0, halo=None, two_phase=False):
+    """K4.  d = planes of dy (the OWNED planes); halo = (Dx, x_off) when x carries halo planes.
+    two_phase: launch only the tensor-core part now and return (dw, finish): the caller forks K3 -- which needs nothing from
+    K4 -- onto the side stream and THEN calls finish() (the deterministic slab reduce that completes dw), so the reduce no
+    longer sits between the two tensor-core kernels of the backward pass."""
     lib = _lib.load()
     dw = torch.empty((n, 125, co, ci), dtype=torch.float32, device=x.device)
     impl_eff = impl if impl else (2 if dtype == _lib.MODE_F16 else 1)
     ws_bytes = lib.mode_conv3d_wgrad_workspace_bytes(n, d, h, wd, ci, co, impl_eff)
     ws = torch.empty(max(int(ws_bytes), 16), dtype=torch.uint8, device=x.device)
     dx_, xo = (int(halo[0]), int(halo[1])) if halo is not None else (0, 0)
-    _lib.check(lib.mode_conv3d_wgrad_ex(_p(x), _p(dy), dtype, _p(dw), n, d, h, wd, ci, co, 1.0, _p(out_scale_dev), _p(ws),
-                                        impl_eff, dx_, xo, _stream()), "mode_conv3d_wgrad")
-    return dw
+
+    def launch(phase):
+        _lib.check(lib.mode_conv3d_wgrad_ex(_p(x), _p(dy), dtype, _p(dw), n, d, h, wd, ci, co, 1.0, _p(out_scale_dev),
+                                            _p(ws), impl_eff | (phase << 8), dx_, xo, _stream()), "mode_conv3d_wgrad")
+    if two_phase and WGRAD_SPLIT_PHASES:
+        launch(1)
+        return dw, lambda: launch(2)
+    launch(0)
+    return (dw, lambda: None) if two_phase else dw
 
 
 def f16_scale_of(tensors, target):
@@ -596,11 +608,14 @@ class ModeConvFunction(torch.autograd.Function):
         # stream -- the CTA-pair dgrad leaves SMs idle on a single volume (64 clusters on 148 SMs) and K1b / gate
         # backward are small latency-bound kernels, so they hide completely behind it.
         d_weff = None
+        finish_wgrad = None
         if needs_dw:
             if wgrad_f32:
                 d_weff = conv3d_wgrad(x_w, dy32, _lib.MODE_F32, n, d, h, wd, ci, co, None)
             else:
-                d_weff = conv3d_wgrad(x_w, dy_op, dtype, n, d, h, wd, ci_p, co_p, dy_s2[1:2] if use_umma else None)
+                # the tensor-core part of K4 now; its slab reduce after K3 has been forked (K3 needs nothing from K4)
+                d_weff, finish_wgrad = conv3d_wgrad(x_w, dy_op, dtype, n, d, h, wd, ci_p, co_p,
+                                                    dy_s2[1:2] if use_umma else None, two_phase=True)
         dx = None
         dg_fork = _Fork(dev, needs_dx and needs_dw)
         if needs_dx:
@@ -608,6 +623,8 @@ class ModeConvFunction(torch.autograd.Function):
             with dg_fork:
                 conv3d(dy_op, dtype, w_dg, sample_u, n, d, h, wd, co_p, ci_p, dy_s2[1:2] if use_umma else None, None,
                        out_scale=(1.0 / W_SCALE_F16) if use_umma else 1.0, out=dxn)
+        if finish_wgrad is not None:
+            finish_wgrad()
         grads = [None] * 7
         if needs_dw:
             if not wgrad_f32 and (ci_p != ci or co_p != co):

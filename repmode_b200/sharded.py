@@ -204,7 +204,8 @@ class ShardedConvFunction(torch.autograd.Function):
             _lib.check(lib.mode_bn_relu_bwd_apply(*apply_args, Fm._stream()), "mode_bn_relu_bwd_apply")
             comm.halo_fill(dy_ext, H2, tag + ".dy")
         inv = dy_s2[1:2] if use_umma else None
-        d_weff = Fm.conv3d_wgrad(x_ext, dy_int, dtype, 1, d, h, wd, ci, co, inv, halo=(d + 2 * H2, H2))
+        d_weff, finish_wgrad = Fm.conv3d_wgrad(x_ext, dy_int, dtype, 1, d, h, wd, ci, co, inv, halo=(d + 2 * H2, H2),
+                                               two_phase=True)
         dx = None
         dg_fork = Fm._Fork(dev, needs_dx)
         if fused and not needs_dx:
@@ -216,6 +217,7 @@ class ShardedConvFunction(torch.autograd.Function):
                     comm.halo_wait(wait_dy)
                 Fm.conv3d(dy_ext, dtype, w_dg, sample_u, 1, d, h, wd, co, ci, inv, None,
                           out_scale=(1.0 / Fm.W_SCALE_F16) if use_umma else 1.0, out=dxn, halo=(d + 2 * H2, H2))
+        finish_wgrad()                                  # K4's slab reduce, now next to K3 instead of in front of it
         layer, _, _ = Fm._layer(k5, k3, k1, a3, a5, gate_w, gate_b)
         params = (k5, k3, k1, a3, a5, gate_w, gate_b)
         sizes = [p.numel() for p in params]

@@ -427,6 +427,30 @@ def test_up_conv_depth_to_space_inside_batchnorm_matches_permute_copy(via_cat, m
     assert_close(got[0].cpu().numpy(), yt.detach().cpu().numpy(), 1e-4, "out vs torch")
 
 
+def test_wgrad_two_phase_launch_bit_identical(monkeypatch):
+    """K4 launched as two calls (tensor-core kernel, then -- after K3 has been forked onto the side stream -- its slab
+    reduce; impl bits 8-9 of mode_conv3d_wgrad_ex) against the single call: every gradient bit-identical."""
+    from repmode_b200 import functional as Fm
+    from repmode_b200.nn_modules import MoDEConv
+    torch.manual_seed(16)
+    m = MoDEConv(5, 12, 32, 64).cuda().train()
+    x0 = torch.randn(2, 32, 8, 32, 32, device="cuda")
+    dout = torch.randn(2, 64, 8, 32, 32, device="cuda")
+    t = torch.tensor([5, 0], device="cuda")
+
+    def run(phases):
+        monkeypatch.setattr(Fm, "WGRAD_SPLIT_PHASES", phases)
+        for p in m.parameters():
+            p.grad = None
+        x = x0.clone().requires_grad_(True)
+        m(x, t).backward(dout)
+        torch.cuda.synchronize()
+        return [x.grad.clone()] + [p.grad.clone() for p in m.parameters()]
+    ref, got = run(False), run(True)
+    for i, (r, g) in enumerate(zip(ref, got)):
+        assert torch.equal(r, g), i
+
+
 def test_cast_f16_pad_matches_cast_then_pad():
     from repmode_b200 import functional as Fm
     x = torch.randn(2, 3, 8, 16, 1, device="cuda") * 3

@@ -106,8 +106,11 @@ def test_whole_net_host_glue(dry):
     y = net(x, torch.tensor([2]))
     assert y.shape == x.shape
     y.sum().backward()
-    assert dry.calls.count("mode_reparam_fwd") == 19 and dry.calls.count("mode_conv3d_wgrad_ex") == 19
+    # K4 is two calls per layer: the tensor-core part, then -- after K3 has been forked -- its slab reduce
+    assert dry.calls.count("mode_reparam_fwd") == 19 and dry.calls.count("mode_conv3d_wgrad_ex") == 2 * 19
     assert dry.calls.count("mode_conv3d_ex") == 19 + 18        # no dgrad for the stem
+    bwd = [c for c in dry.calls if c in ("mode_conv3d_wgrad_ex", "mode_conv3d_ex")][19:]
+    assert bwd[:3] == ["mode_conv3d_wgrad_ex", "mode_conv3d_ex", "mode_conv3d_wgrad_ex"], bwd[:6]   # K4, K3, K4 reduce
     assert all(p.grad is not None for p in net.parameters())
 
 
@@ -177,7 +180,7 @@ def test_sharded_block_host_glue(dry, precision):
     assert kinds == want, kinds
     assert comm.calls[0][2] == (1, 10, 16, 8, 32) and comm.calls[0][3] == 2
     c = dry.calls
-    assert c.count("mode_conv3d_ex") == 2 and c.count("mode_conv3d_wgrad_ex") == 1
+    assert c.count("mode_conv3d_ex") == 2 and c.count("mode_conv3d_wgrad_ex") == 2      # K4 + its reduce phase
 
 
 def test_eval_cache_invalidated_by_train_switch_and_load_state_dict(dry):

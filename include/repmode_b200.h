@@ -114,6 +114,19 @@ int mode_reparam_bwd(const mode_layer_t* layer_host, const int32_t* task_ids, co
                      float* dk5, float* dk3, float* dk1, float* da3, float* da5, float* dgate_w, float* dgate_b,
                      void* workspace, void* stream);
 
+/* K1b straight out of K4's work-unit partials: when mode_conv3d_wgrad_ex's tensor-core phase (impl | 0x100) ran ONE slab per
+ * unit group -- mode_conv3d_wgrad_partial_layout() returns 0 and layout5 = {SL, SA, SB, nL, nA} with SL = SA = SB = 1 --
+ * its reduce phase is a pure re-layout of d_weff, which this entry point performs inside K1b's loads instead: d_weff is
+ * never written.  `k4_partials` is the workspace that wgrad call filled; scale * (scale_dev ? *scale_dev : 1) is the
+ * out_scale the reduce phase would have applied.  Same outputs, bit for bit, as the reduce phase + mode_reparam_bwd. */
+int mode_conv3d_wgrad_partial_layout(mode_dtype_t dtype, int32_t N, int32_t D, int32_t H, int32_t W, int32_t Ci, int32_t Co,
+                                     int32_t impl, int32_t Dx, int32_t x_off, int32_t* layout5_host);
+int mode_reparam_bwd_partial(const mode_layer_t* layer_host, const int32_t* task_ids, const float* t_dense, int32_t U,
+                             const int32_t* sample_u, int32_t n_samples, const float* g, const float* k4_partials,
+                             const int32_t* layout5_host, float scale, const float* scale_dev, float* dk5, float* dk3,
+                             float* dk1, float* da3, float* da5, float* dgate_w, float* dgate_b, void* workspace,
+                             void* stream);
+
 /* ---- K2 / K3: 5x5x5 'same' cross-correlation, stride 1, zero pad 2, no bias ---------------------------
  * Replaces F.conv3d(x[i:i+1], w[i], padding='same') per sample (RepMode.py:204-210) and, called with the
  * w_dgrad pack and dy as input, its autograd dgrad.

@@ -54,6 +54,10 @@ struct ConvExt {
     __host__ __device__ int p_hi() const { return Dx - x_off - 1; }
 };
 
+// Floats of one K4 (wgrad_deep.cu) work-unit partial: [60 entries][32 co][32 ci].  K1b reads these partials directly when a
+// layer's wgrad runs one slab per unit (reparam.cu), so the layout is shared.
+constexpr int K4_DEEP_PARTIAL_FLOATS = 60 * 32 * 32;
+
 // Streaming 16-byte load for tensors that are read once per kernel: read-only path, no L1 allocation.  Measured with
 // tools/stream_probe.cu on this pool's B200 (profiles/r2_stream_probe.txt): two 64 MB input streams read at 5.1 TB/s with
 // these loads against 4.5 TB/s with plain ld.global (L1 allocation of data that is never reused).

@@ -71,6 +71,7 @@ int wgrad_split(const __half* x, const __half* dy, float* dw, int N, int D, int 
 // wgrad_deep.cu
 bool wgrad_deep_supported(int D, int H, int W, int Ci, int Co);
 int64_t wgrad_deep_workspace_bytes(int N, int D, int H, int W, int Ci, int Co, int Dx, int x_off);
+void wgrad_deep_layout(int N, int D, int H, int W, int Ci, int Co, int Dx, int x_off, int32_t out[5]);
 int wgrad_deep(const __half* x, const __half* dy, float* dw, int N, int D, int H, int W, int Ci, int Co,
                float out_scale, const float* out_scale_dev, void* workspace, int Dx, int x_off, cudaStream_t st, int phase);
 
@@ -221,6 +222,20 @@ extern "C" int mode_conv3d_wgrad_ex(const void* x, const void* dy, mode_dtype_t 
         return wgrad_split((const __half*)x, (const __half*)dy, d_weff, N, D, H, W, Ci, Co, out_scale, out_scale_dev, workspace, st);
     }
     MODE_FAIL("mode_conv3d_wgrad: unknown impl %d", impl);
+}
+
+extern "C" int mode_conv3d_wgrad_partial_layout(mode_dtype_t dtype, int32_t N, int32_t D, int32_t H, int32_t W, int32_t Ci,
+                                                int32_t Co, int32_t impl, int32_t Dx, int32_t x_off, int32_t* layout5) {
+    if (!layout5) MODE_FAIL("mode_conv3d_wgrad_partial_layout: layout5 is NULL");
+    if (Dx <= 0) { Dx = D; x_off = 0; }
+    const bool halo = Dx != D || x_off != 0;
+    impl &= 0xff;
+    if (impl == 0) impl = (dtype == MODE_F16) ? 2 : 1;
+    const bool deep = dtype == MODE_F16 && (impl == 6 || (impl == 2 && (wgrad_use_deep() || halo))) &&
+                      wgrad_deep_supported(D, H, W, Ci, Co);
+    if (!deep) return 1;                       // not an error: this wgrad does not leave deep-tile partials behind
+    wgrad_deep_layout(N, D, H, W, Ci, Co, Dx, x_off, layout5);
+    return 0;
 }
 
 extern "C" int mode_conv3d_wgrad(const void* x, const void* dy, mode_dtype_t dtype, float* d_weff, int32_t N,

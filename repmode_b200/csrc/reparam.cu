@@ -715,12 +715,26 @@ __global__ void __launch_bounds__(256, 3) reparam_bwd_slab_kernel(mode_layer_t L
 // a double-buffered table: ONE barrier per sample).  The next sample's loads are issued before the current one is consumed.
 // dk5 leaves through the expert buffer (coalesced 16-byte stores), dk3 is accumulated in shared memory (every (ci, t3) entry
 // has exactly one owner thread).  grid (Ci / 32, Co), block 256.
+// d_weff read straight out of K4's work-unit partials (r2j): when a layer's wgrad runs ONE slab per unit group (every wide
+// layer of the U-Net: N * Ci/32 * Co/32 >= 50), the reduce kernel of wgrad_deep.cu is a pure re-layout -- partial
+// [unit][entry][o % 32][ci % 32] -> d_weff [n][tap][o][ci], times the dy scale -- that K1b can do in its own loads: a tap's
+// 32-channel row is a contiguous 128-byte run in either layout.  Saves writing and re-reading d_weff (the largest tensor of
+// the backward pass of those layers).  (0 + v) * scale is what the reduce kernel computes for one slab: bit-identical.
+struct K4Partials {
+    const float* partial;          // nullptr: read d_weff
+    int nL, nA;                    // first unit of the A / B groups (SL = SA = SB = 1)
+    int ncic, ncoc;
+    float scale;
+    const float* scale_dev;
+};
+template <bool PARTIAL>
 __global__ void __launch_bounds__(256, 3) reparam_bwd_reg_kernel(mode_layer_t L, const int32_t* __restrict__ sample_u,
                                                                  int n_samples, const float* __restrict__ g,
                                                                  const float* __restrict__ d_weff,
                                                                  float* __restrict__ dk5, float* __restrict__ dk3,
                                                                  float* __restrict__ dk1, float* __restrict__ da3,
-                                                                 float* __restrict__ da5, float* __restrict__ dg_part) {
+                                                                 float* __restrict__ da5, float* __restrict__ dg_part,
+                                                                 K4Partials kp) {
     __shared__ __align__(16) float sk5[32 * 125];     // experts [ci][tap]; reused as the dk5 staging buffer at the end
     __shared__ __align__(16) float sk3[32 * 27];
     __shared__ __align__(16) float sdk3[32 * 27];
@@ -736,7 +750,41 @@ __global__ void __launch_bounds__(256, 3) reparam_bwd_reg_kernel(mode_layer_t L,
     const size_t tap_stride = (size_t)Co * Ci;
 
     float4 cur[4], nxt[4];
+    // partial mode: float offset of this thread's 16 bytes of each of its four taps inside sample 0's units; a sample further
+    // on is `pstride` floats away (one unit per group and kind)
+    uint32_t poff[4] = {0u, 0u, 0u, 0u};
+    size_t pstride = 0;
+    float pscale = 1.f;
+    if (PARTIAL) {
+        const uint32_t g0 = (uint32_t)((o >> 5) * kp.ncic + ic);
+        pstride = (size_t)kp.ncoc * kp.ncic * K4_DEEP_PARTIAL_FLOATS;
+        pscale = kp.scale * (kp.scale_dev != nullptr ? *kp.scale_dev : 1.f);
+#pragma unroll
+        for (int p = 0; p < 4; ++p) {
+            const int tap = min(tr + 32 * p, 124);
+            const int kd = tap / 25, kh = (tap / 5) % 5, kw = tap % 5;
+            uint32_t unit, entry;
+            if (kh == 4) { unit = g0; entry = kd * 5 + kw; }
+            else if (kd < 2) { unit = kp.nL + g0; entry = kd * 20 + kh * 5 + kw; }
+            else { unit = kp.nL + kp.nA + g0; entry = (kd - 2) * 20 + kh * 5 + kw; }
+            poff[p] = unit * (uint32_t)K4_DEEP_PARTIAL_FLOATS + (entry * 32u + (uint32_t)(o & 31)) * 32u + cq * 4;
+        }
+    }
     auto load_slab = [&](int n, float4 (&v)[4]) {
+        if (PARTIAL) {
+            const float* base = kp.partial + (size_t)n * pstride;
+#pragma unroll
+            for (int p = 0; p < 4; ++p) {
+                float4 w = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (tr + 32 * p < 125) {
+                    w = ld_stream(base + poff[p]);
+                    w.x = (0.f + w.x) * pscale; w.y = (0.f + w.y) * pscale;
+                    w.z = (0.f + w.z) * pscale; w.w = (0.f + w.w) * pscale;
+                }
+                v[p] = w;
+            }
+            return;
+        }
         const float* dw = d_weff + ((size_t)n * 125 * Co + o) * Ci + (size_t)ic * 32 + cq * 4;
 #pragma unroll
         for (int p = 0; p < 4; ++p) {
@@ -1137,25 +1185,31 @@ extern "C" int64_t mode_reparam_bwd_workspace_bytes(int32_t ci, int32_t co, int3
     return (int64_t)ceil_div(ci, 32) * n_samples * MODE_NUM_EXPERTS * co * sizeof(float);
 }
 
-extern "C" int mode_reparam_bwd(const mode_layer_t* L, const int32_t* task_ids, const float* t_dense, int32_t U,
-                                const int32_t* sample_u, int32_t n_samples, const float* g, const float* d_weff,
-                                float* dk5, float* dk3, float* dk1, float* da3, float* da5, float* dgate_w,
-                                float* dgate_b, void* workspace, void* stream) {
-    if (!L || !sample_u || !g || !d_weff || !workspace) MODE_FAIL("mode_reparam_bwd: null argument");
+static int reparam_bwd_launch(const mode_layer_t* L, const int32_t* task_ids, const float* t_dense, int32_t U,
+                              const int32_t* sample_u, int32_t n_samples, const float* g, const float* d_weff,
+                              const K4Partials& kp, float* dk5, float* dk3, float* dk1, float* da3, float* da5,
+                              float* dgate_w, float* dgate_b, void* workspace, void* stream) {
+    if (!L || !sample_u || !g || (!d_weff && !kp.partial) || !workspace) MODE_FAIL("mode_reparam_bwd: null argument");
     if ((task_ids == nullptr) == (t_dense == nullptr)) MODE_FAIL("mode_reparam_bwd: pass exactly one of task_ids / t_dense");
     if (!dk5 || !dk3 || !dk1 || !da3 || !da5 || !dgate_w || !dgate_b) MODE_FAIL("mode_reparam_bwd: null output");
     (void)U;
     cudaStream_t st = (cudaStream_t)stream;
     const int nci = (int)ceil_div(L->ci, 32);
     static const bool legacy = getenv("REPMODE_K1B_LEGACY") != nullptr;       // A/B arm: the round-1 kernel
-    if (legacy)
+    const bool reg_ok = L->ci % 32 == 0 &&
+                        ((reinterpret_cast<uintptr_t>(d_weff) | reinterpret_cast<uintptr_t>(L->k5) |
+                          reinterpret_cast<uintptr_t>(L->k3) | reinterpret_cast<uintptr_t>(dk5) |
+                          reinterpret_cast<uintptr_t>(dk3) | reinterpret_cast<uintptr_t>(kp.partial)) & 15) == 0;
+    if (kp.partial != nullptr) {
+        if (!reg_ok || L->co % 32 != 0) MODE_FAIL("mode_reparam_bwd_partial: needs Ci %% 32 == 0, Co %% 32 == 0, 16-byte aligned buffers");
+        reparam_bwd_reg_kernel<true><<<dim3(nci, L->co), 256, 0, st>>>(*L, sample_u, n_samples, g, nullptr, dk5, dk3, dk1,
+                                                                       da3, da5, (float*)workspace, kp);
+    } else if (legacy)
         reparam_bwd_kernel<<<dim3(nci, L->co), 128, 0, st>>>(*L, sample_u, n_samples, g, d_weff, dk5, dk3, dk1, da3, da5,
                                                             (float*)workspace);
-    else if (L->ci % 32 == 0 && getenv("REPMODE_K1B_SLAB") == nullptr &&
-             ((reinterpret_cast<uintptr_t>(d_weff) | reinterpret_cast<uintptr_t>(L->k5) | reinterpret_cast<uintptr_t>(L->k3) |
-               reinterpret_cast<uintptr_t>(dk5) | reinterpret_cast<uintptr_t>(dk3)) & 15) == 0)
-        reparam_bwd_reg_kernel<<<dim3(nci, L->co), 256, 0, st>>>(*L, sample_u, n_samples, g, d_weff, dk5, dk3, dk1, da3,
-                                                                 da5, (float*)workspace);
+    else if (reg_ok && getenv("REPMODE_K1B_SLAB") == nullptr)
+        reparam_bwd_reg_kernel<false><<<dim3(nci, L->co), 256, 0, st>>>(*L, sample_u, n_samples, g, d_weff, dk5, dk3, dk1,
+                                                                        da3, da5, (float*)workspace, K4Partials{});
     else
         reparam_bwd_slab_kernel<<<dim3(nci, L->co), 256, 0, st>>>(*L, sample_u, n_samples, g, d_weff, dk5, dk3, dk1, da3,
                                                                   da5, (float*)workspace);
@@ -1172,4 +1226,29 @@ extern "C" int mode_reparam_bwd(const mode_layer_t* L, const int32_t* task_ids, 
                                                                       device_error_flag());
     MODE_LAUNCH_CHECK();
     return 0;
+}
+
+extern "C" int mode_reparam_bwd(const mode_layer_t* L, const int32_t* task_ids, const float* t_dense, int32_t U,
+                                const int32_t* sample_u, int32_t n_samples, const float* g, const float* d_weff,
+                                float* dk5, float* dk3, float* dk1, float* da3, float* da5, float* dgate_w,
+                                float* dgate_b, void* workspace, void* stream) {
+    return reparam_bwd_launch(L, task_ids, t_dense, U, sample_u, n_samples, g, d_weff, K4Partials{}, dk5, dk3, dk1, da3, da5,
+                              dgate_w, dgate_b, workspace, stream);
+}
+
+extern "C" int mode_reparam_bwd_partial(const mode_layer_t* L, const int32_t* task_ids, const float* t_dense, int32_t U,
+                                        const int32_t* sample_u, int32_t n_samples, const float* g,
+                                        const float* k4_partials, const int32_t* layout5, float scale,
+                                        const float* scale_dev, float* dk5, float* dk3, float* dk1, float* da3,
+                                        float* da5, float* dgate_w, float* dgate_b, void* workspace, void* stream) {
+    if (!L || !k4_partials || !layout5) MODE_FAIL("mode_reparam_bwd_partial: null argument");
+    if (layout5[0] != 1 || layout5[1] != 1 || layout5[2] != 1)
+        MODE_FAIL("mode_reparam_bwd_partial: the wgrad ran several slabs per unit (%d, %d, %d): reduce it first", layout5[0],
+                  layout5[1], layout5[2]);
+    const int64_t groups = (int64_t)n_samples * (L->ci / 32) * (L->co / 32);
+    if (groups * 3 * K4_DEEP_PARTIAL_FLOATS > 0x7fffffffLL * 2)
+        MODE_FAIL("mode_reparam_bwd_partial: partials too large for 32-bit offsets");
+    K4Partials kp{k4_partials, layout5[3], layout5[4], L->ci / 32, L->co / 32, scale, scale_dev};
+    return reparam_bwd_launch(L, task_ids, t_dense, U, sample_u, n_samples, g, nullptr, kp, dk5, dk3, dk1, da3, da5, dgate_w,
+                              dgate_b, workspace, stream);
 }

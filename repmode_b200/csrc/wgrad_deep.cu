@@ -45,6 +45,7 @@ constexpr int OPERAND_BYTES = STAGES * L_STAGE;      // the largest kind
 constexpr int THREADS = 256;
 constexpr int ENTRIES = 60;                          // [32 co][32 ci] fp32 blocks per unit partial (B units: 3 kd x 20)
 constexpr int PARTIAL_FLOATS = ENTRIES * 32 * 32;
+static_assert(PARTIAL_FLOATS == K4_DEEP_PARTIAL_FLOATS, "K1b (reparam.cu) reads the partials through this layout");
 static_assert(PT * K_DY_PLANE <= K_DY_SLOT && K_DY_PLANE % 512 == 0, "dy slot");
 static_assert(A_STAGE % 1024 == 0 && B_STAGE % 1024 == 0 && L_STAGE % 1024 == 0, "swizzle atoms");
 static_assert(STAGES * B_STAGE <= OPERAND_BYTES && STAGES * A_STAGE <= OPERAND_BYTES, "operand area");
@@ -393,6 +394,15 @@ static DeepPlan deep_plan(int N, int D, int H, int W, int Ci, int Co, int Dx, in
 bool wgrad_deep_supported(int D, int H, int W, int Ci, int Co) {
     (void)D; (void)H;
     return Ci % 32 == 0 && Co % 32 == 0 && Ci >= 32 && Co >= 32 && W % wd::TW == 0;
+}
+
+// {SL, SA, SB, nL, nA}: slabs per unit group of each kind and the first unit of the A / B groups -- what a reader of the
+// partials needs (the reduce kernel below, or K1b when every S is 1)
+void wgrad_deep_layout(int N, int D, int H, int W, int Ci, int Co, int Dx, int x_off, int32_t out[5]) {
+    const DeepPlan p = deep_plan(N, D, H, W, Ci, Co, Dx, x_off);
+    const int64_t groups = (int64_t)N * (Ci / 32) * (Co / 32);
+    out[0] = p.SL; out[1] = p.SA; out[2] = p.SB;
+    out[3] = (int32_t)(groups * p.SL); out[4] = (int32_t)(groups * p.SA);
 }
 
 int64_t wgrad_deep_workspace_bytes(int N, int D, int H, int W, int Ci, int Co, int Dx, int x_off) {

@@ -326,6 +326,7 @@ class ShardSpec:
 
 
 WGRAD_SPLIT_PHASES = os.environ.get("REPMODE_WGRAD_PHASES", "1") == "1"
+K1B_FROM_PARTIALS = os.environ.get("REPMODE_K1B_FROM_PARTIALS", "1") == "1"   # K1b reads K4's partials (no d_weff) when it can
 
 
 def conv3d_wgrad(x, dy, dtype, n, d, h, wd, ci, co, out_scale_dev=None, impl=0, halo=None, two_phase=False):
@@ -345,9 +346,13 @@ def conv3d_wgrad(x, dy, dtype, n, d, h, wd, ci, co, out_scale_dev=None, impl=0, 
                                             _p(ws), impl_eff | (phase << 8), dx_, xo, _stream()), "mode_conv3d_wgrad")
     if two_phase and WGRAD_SPLIT_PHASES:
         launch(1)
-        return dw, lambda: launch(2)
+        # when every unit group ran ONE slab the partials ARE d_weff in another layout: K1b can read them (reparam_bwd)
+        lay = (ctypes.c_int32 * 5)()
+        rc = lib.mode_conv3d_wgrad_partial_layout(dtype, n, d, h, wd, ci, co, impl_eff, dx_, xo, lay)
+        partials = (ws, lay) if (rc == 0 and lay[0] == 1 and lay[1] == 1 and lay[2] == 1) else None
+        return dw, (lambda: launch(2)), partials
     launch(0)
-    return (dw, lambda: None) if two_phase else dw
+    return (dw, (lambda: None), None) if two_phase else dw
 
 
 def f16_scale_of(tensors, target):
@@ -609,13 +614,18 @@ class ModeConvFunction(torch.autograd.Function):
         # backward are small latency-bound kernels, so they hide completely behind it.
         d_weff = None
         finish_wgrad = None
+        k4_partials = None
         if needs_dw:
             if wgrad_f32:
                 d_weff = conv3d_wgrad(x_w, dy32, _lib.MODE_F32, n, d, h, wd, ci, co, None)
             else:
                 # the tensor-core part of K4 now; its slab reduce after K3 has been forked (K3 needs nothing from K4)
-                d_weff, finish_wgrad = conv3d_wgrad(x_w, dy_op, dtype, n, d, h, wd, ci_p, co_p,
-                                                    dy_s2[1:2] if use_umma else None, two_phase=True)
+                d_weff, finish_wgrad, k4_partials = conv3d_wgrad(x_w, dy_op, dtype, n, d, h, wd, ci_p, co_p,
+                                                                 dy_s2[1:2] if use_umma else None, two_phase=True)
+                if not (K1B_FROM_PARTIALS and use_umma and ci_p == ci and co_p == co):
+                    k4_partials = None
+                if k4_partials is not None:
+                    finish_wgrad = None                 # no reduce phase, no d_weff: K1b reads the partials
         dx = None
         dg_fork = _Fork(dev, needs_dx and needs_dw)
         if needs_dx:
@@ -633,8 +643,14 @@ class ModeConvFunction(torch.autograd.Function):
             outs = [torch.empty_like(t) for t in (k5, k3, k1, a3, a5, gate_w, gate_b)]
             ws = torch.empty(max(int(lib.mode_reparam_bwd_workspace_bytes(ci, co, n)), 16), dtype=torch.uint8, device=dev)
             ids, dense = (gate_u, None) if not gate_u.dtype.is_floating_point else (None, gate_u)
-            _lib.check(lib.mode_reparam_bwd(ctypes.byref(layer), _p(ids), _p(dense), U, _p(sample_u), n, _p(g), _p(d_weff),
-                                            *[_p(o) for o in outs], _p(ws), _stream()), "mode_reparam_bwd")
+            if k4_partials is not None:
+                part, lay = k4_partials
+                _lib.check(lib.mode_reparam_bwd_partial(ctypes.byref(layer), _p(ids), _p(dense), U, _p(sample_u), n, _p(g),
+                                                        _p(part), lay, 1.0, _p(dy_s2[1:2]), *[_p(o) for o in outs], _p(ws),
+                                                        _stream()), "mode_reparam_bwd_partial")
+            else:
+                _lib.check(lib.mode_reparam_bwd(ctypes.byref(layer), _p(ids), _p(dense), U, _p(sample_u), n, _p(g),
+                                                _p(d_weff), *[_p(o) for o in outs], _p(ws), _stream()), "mode_reparam_bwd")
             grads = outs
         dg_fork.join()
         dx2 = None

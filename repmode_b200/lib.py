@@ -129,6 +129,9 @@ SIGNATURES = {
     "mode_reparam_bwd_workspace_bytes": (_i64, [_i32, _i32, _i32]),
     "mode_reparam_bwd": (ctypes.c_int, [ctypes.POINTER(ModeLayer), _vp, _vp, _i32, _vp, _i32, _vp, _vp, _vp, _vp, _vp,
                                         _vp, _vp, _vp, _vp, _vp, _vp]),
+    "mode_reparam_bwd_partial": (ctypes.c_int, [ctypes.POINTER(ModeLayer), _vp, _vp, _i32, _vp, _i32, _vp, _vp, _vp, _f32, _vp,
+                                                _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "mode_conv3d_wgrad_partial_layout": (ctypes.c_int, [ctypes.c_int, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _vp]),
     "mode_conv3d": (ctypes.c_int, [_vp, ctypes.c_int, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _f32, _vp, _vp,
                                    _i32, _i32, _i32, _vp]),
     "mode_conv3d_ex": (ctypes.c_int, [_vp, ctypes.c_int, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _f32, _vp, _vp,

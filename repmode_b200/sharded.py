@@ -204,8 +204,8 @@ class ShardedConvFunction(torch.autograd.Function):
             _lib.check(lib.mode_bn_relu_bwd_apply(*apply_args, Fm._stream()), "mode_bn_relu_bwd_apply")
             comm.halo_fill(dy_ext, H2, tag + ".dy")
         inv = dy_s2[1:2] if use_umma else None
-        d_weff, finish_wgrad = Fm.conv3d_wgrad(x_ext, dy_int, dtype, 1, d, h, wd, ci, co, inv, halo=(d + 2 * H2, H2),
-                                               two_phase=True)
+        d_weff, finish_wgrad, _ = Fm.conv3d_wgrad(x_ext, dy_int, dtype, 1, d, h, wd, ci, co, inv, halo=(d + 2 * H2, H2),
+                                                  two_phase=True)
         dx = None
         dg_fork = Fm._Fork(dev, needs_dx)
         if fused and not needs_dx:

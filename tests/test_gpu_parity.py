@@ -451,6 +451,41 @@ def test_wgrad_two_phase_launch_bit_identical(monkeypatch):
         assert torch.equal(r, g), i
 
 
+@pytest.mark.parametrize("ci,co,n", [(128, 128, 4), (256, 64, 4), (64, 64, 2)])
+def test_k1b_from_k4_partials_bit_identical(ci, co, n, monkeypatch):
+    """K1b reading d_weff straight out of K4's work-unit partials (mode_reparam_bwd_partial: taken when the wgrad ran one
+    slab per unit group, N * Ci/32 * Co/32 >= 50) against the reduce phase + mode_reparam_bwd: every gradient bit-identical.
+    (64, 64, 2) has 8 unit groups -> several slabs per unit: the layout query must send it down the ordinary path."""
+    import ctypes
+    from repmode_b200 import functional as Fm, lib as L
+    from repmode_b200.nn_modules import MoDEConv
+    lib = L.load()
+    lay = (ctypes.c_int32 * 5)()
+    rc = lib.mode_conv3d_wgrad_partial_layout(L.MODE_F16, n, 4, 16, 16, ci, co, 2, 0, 0, lay)
+    assert rc == 0 and (list(lay)[:3] == [1, 1, 1]) == (n * (ci // 32) * (co // 32) >= 50), list(lay)
+    torch.manual_seed(17)
+    m = MoDEConv(5, 12, ci, co).cuda().train()
+    x0 = torch.randn(n, ci, 4, 16, 16, device="cuda")
+    dout = torch.randn(n, co, 4, 16, 16, device="cuda")
+    t = (torch.arange(n, device="cuda") * 5) % 12
+
+    def run(flag):
+        monkeypatch.setattr(Fm, "K1B_FROM_PARTIALS", flag)
+        for p in m.parameters():
+            p.grad = None
+        x = x0.clone().requires_grad_(True)
+        n0 = lib.mode_launch_count()
+        m(x, t).backward(dout)
+        torch.cuda.synchronize()
+        L.poll_error("K1b from partials")
+        return [x.grad.clone()] + [p.grad.clone() for p in m.parameters()], lib.mode_launch_count() - n0
+    (ref, n_ref), (got, n_got) = run(False), run(True)
+    for i, (r, g) in enumerate(zip(ref, got)):
+        assert torch.equal(r, g), i
+    if list(lay)[:3] == [1, 1, 1]:
+        assert n_got == n_ref - 1, (n_got, n_ref)          # the reduce launch is gone
+
+
 def test_cast_f16_pad_matches_cast_then_pad():
     from repmode_b200 import functional as Fm
     x = torch.randn(2, 3, 8, 16, 1, device="cuda") * 3

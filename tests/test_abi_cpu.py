@@ -80,3 +80,28 @@ def test_pack_weights_helper_roundtrip():
     w = np.random.RandomState(0).randn(1, 8, 40, 5, 5, 5).astype(np.float32)
     p = pack_weights(w, half=False).reshape(1, 125, 2, 8, 32)
     assert p[0, 62, 1, 3, 7] == w[0, 3, 39, 2, 2, 2] and p[0, 62, 1, 3, 8] == 0
+
+
+def test_header_is_plain_c(tmp_path):
+    """include/repmode_b200.h is the drop-in boundary: it must compile as C99 on its own (no C++-isms, every type it uses
+    declared before use) and link against the shipped library."""
+    import os
+    import shutil
+    import subprocess
+    gcc = shutil.which("gcc")
+    if gcc is None:
+        pytest.skip("no gcc")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    src = tmp_path / "hdr.c"
+    src.write_text('#include "repmode_b200.h"\n'
+                   "int main(void) {\n"
+                   "    mode_rowmap_t m = {0, 1, 1, 1, 0};\n"
+                   "    mode_reparam_item_t it;\n"
+                   "    mode_planes_t p;\n"
+                   "    (void)m; (void)it; (void)p;\n"
+                   "    return mode_version() > 0 ? 0 : 1;\n"
+                   "}\n")
+    obj = tmp_path / "hdr.o"
+    r = subprocess.run([gcc, "-std=c99", "-Wall", "-Wextra", "-Werror", "-I", os.path.join(root, "include"), "-c", str(src),
+                        "-o", str(obj)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
